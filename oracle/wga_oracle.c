@@ -1,0 +1,1110 @@
+/*
+ * wga_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).  See wga_oracle.h.
+ *
+ * Literal sequential restatement of wgatools v1.1.0 (/root/reference, commit de13560d):
+ *   src/parser/cigar.rs, src/parser/common.rs, src/parser/maf.rs, src/parser/paf.rs,
+ *   src/converter.rs:29-54, src/tools/stat.rs, src/tools/caller.rs:42-265,304-608.
+ * Written for obviousness, not speed: it mirrors the reference's control flow
+ * (line reader -> s-line parser -> per-column group_by -> string building).
+ * Integer arithmetic wraps like a Rust release build (no overflow-checks profile
+ * in Cargo.toml).  Input is treated as ASCII (the reference iterates chars()).
+ */
+#include "wga_oracle.h"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ buffers */
+static void buf_reserve(orc_buf *b, size_t extra) {
+    if (b->n + extra <= b->cap) return;
+    size_t cap = b->cap ? b->cap : 256;
+    while (cap < b->n + extra) cap *= 2;
+    b->p = (char *)realloc(b->p, cap);
+    b->cap = cap;
+}
+static void buf_put(orc_buf *b, const char *s, size_t n) {
+    buf_reserve(b, n);
+    memcpy(b->p + b->n, s, n);
+    b->n += n;
+}
+static void buf_putc(orc_buf *b, char c) { buf_put(b, &c, 1); }
+static void buf_puts(orc_buf *b, const char *s) { buf_put(b, s, strlen(s)); }
+static void buf_putu(orc_buf *b, uint64_t v) { /* itoa */
+    char tmp[24];
+    int n = snprintf(tmp, sizeof tmp, "%llu", (unsigned long long)v);
+    buf_put(b, tmp, (size_t)n);
+}
+void orc_buf_free(orc_buf *b) {
+    free(b->p);
+    b->p = NULL;
+    b->n = b->cap = 0;
+}
+
+static void set_err(char *err, size_t cap, const char *fmt, ...) {
+    if (!err || !cap) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, cap, fmt, ap);
+    va_end(ap);
+}
+
+typedef struct { const char *p; size_t n; } sv;
+static int sv_eq(sv a, sv b) { return a.n == b.n && memcmp(a.p, b.p, a.n) == 0; }
+static int sv_eq_c(sv a, const char *c) { size_t n = strlen(c); return a.n == n && memcmp(a.p, c, n) == 0; }
+
+/* ---------------------------------------------------------- number parsing */
+/* utils.rs:69-74 parse_str2u64 == str::parse::<u64>: optional '+', >=1 digit, no overflow */
+static int parse_u64(sv s, uint64_t *out) {
+    size_t i = 0;
+    if (s.n == 0) return 0;
+    if (s.p[0] == '+') i = 1;
+    if (i == s.n) return 0;
+    uint64_t v = 0;
+    for (; i < s.n; i++) {
+        unsigned d = (unsigned char)s.p[i] - '0';
+        if (d > 9) return 0;
+        if (v > (UINT64_MAX - d) / 10) return 0;
+        v = v * 10 + d;
+    }
+    *out = v;
+    return 1;
+}
+
+/* ------------------------------------------------------------- line reader */
+/* std::io::BufRead::lines(): split at '\n', drop it and a directly preceding '\r'. */
+typedef struct { const char *t; size_t len, pos; } lreader;
+static int next_line(lreader *r, sv *line) {
+    if (r->pos >= r->len) return 0;
+    const char *s = r->t + r->pos;
+    const char *nl = (const char *)memchr(s, '\n', r->len - r->pos);
+    size_t n;
+    if (nl) {
+        n = (size_t)(nl - s);
+        r->pos += n + 1;
+        if (n > 0 && s[n - 1] == '\r') n--;
+    } else {
+        n = r->len - r->pos;
+        r->pos = r->len;
+    }
+    line->p = s;
+    line->n = n;
+    return 1;
+}
+
+/* char::is_whitespace restricted to ASCII: U+0009..U+000D, U+0020 */
+static int is_ws(char c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+/* ------------------------------------------------------------------ s-line */
+typedef struct {
+    char mode;
+    sv name;
+    uint64_t start, align_size, size;
+    int neg;
+    sv seq;
+} sline;
+
+/* maf.rs:138-211 parse_sline: split_whitespace, exactly 7 fields */
+static int parse_sline(sv line, sline *out, char *err, size_t errcap) {
+    static const char *fname[7] = {"mode", "name", "start", "align_size", "strand", "size", "seq"};
+    sv f[8];
+    int nf = 0;
+    size_t i = 0;
+    while (i < line.n && nf < 8) {
+        while (i < line.n && is_ws(line.p[i])) i++;
+        if (i >= line.n) break;
+        size_t b = i;
+        while (i < line.n && !is_ws(line.p[i])) i++;
+        f[nf].p = line.p + b;
+        f[nf].n = i - b;
+        nf++;
+    }
+    /* fields are consumed strictly in order, so the first problem in field order wins */
+    for (int k = 0; k < 7; k++) {
+        if (k >= nf) {
+            set_err(err, errcap, "Parse MAF error by: S-line Filed `%s` Missing", fname[k]);
+            return ORC_E_MAF_FIELD_MISSING;
+        }
+        switch (k) {
+        case 0: out->mode = f[0].p[0]; break;
+        case 1: out->name = f[1]; break;
+        case 2:
+            if (!parse_u64(f[2], &out->start)) goto bad_int;
+            break;
+        case 3:
+            if (!parse_u64(f[3], &out->align_size)) goto bad_int;
+            break;
+        case 4:
+            if (sv_eq_c(f[4], "+")) out->neg = 0;
+            else if (sv_eq_c(f[4], "-")) out->neg = 1;
+            else {
+                set_err(err, errcap, "Parse Strand `%.*s` Error", (int)f[4].n, f[4].p);
+                return ORC_E_PARSE_STRAND;
+            }
+            break;
+        case 5:
+            if (!parse_u64(f[5], &out->size)) goto bad_int;
+            break;
+        case 6: out->seq = f[6]; break;
+        }
+        continue;
+    bad_int:
+        set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)f[k].n, f[k].p);
+        return ORC_E_PARSE_INT;
+    }
+    if (nf > 7) {
+        set_err(err, errcap, "Parse MAF error by: Surplus Filed > 7");
+        return ORC_E_MAF_SURPLUS_FIELD;
+    }
+    return ORC_OK;
+}
+
+/* -------------------------------------------------------------- MAF record */
+typedef struct {
+    sline *s;
+    size_t n, cap;
+    size_t query_idx;
+} mafrec;
+
+static void mafrec_push(mafrec *r, const sline *s) {
+    if (r->n == r->cap) {
+        r->cap = r->cap ? r->cap * 2 : 4;
+        r->s = (sline *)realloc(r->s, r->cap * sizeof(sline));
+    }
+    r->s[r->n++] = *s;
+}
+
+/* maf.rs:25-36 MAFReader::new: the first line is always consumed as the header */
+static void maf_reader_init(lreader *r, const char *text, size_t len) {
+    r->t = text;
+    r->len = len;
+    r->pos = 0;
+    sv hdr;
+    next_line(r, &hdr);
+}
+
+/* maf.rs:371-421 MAFRecords::next.  Returns 1 record, 0 end, <0 error (negated code). */
+static int maf_next(lreader *r, mafrec *rec, char *err, size_t errcap) {
+    sv line;
+    for (;;) {
+        if (!next_line(r, &line)) return 0;
+        if (line.n > 0 && line.p[0] == 's') break; /* maf.rs:378-379 skip non-'s' lines */
+    }
+    rec->n = 0;
+    rec->query_idx = 1;
+    sline s;
+    int rc = parse_sline(line, &s, err, errcap);
+    if (rc) return -rc;
+    mafrec_push(rec, &s);
+    while (next_line(r, &line)) { /* maf.rs:395-413 */
+        if (line.n > 0 && line.p[0] == 's') {
+            rc = parse_sline(line, &s, err, errcap);
+            if (rc) return -rc;
+            mafrec_push(rec, &s);
+        } else {
+            break; /* the terminating line is consumed */
+        }
+    }
+    return 1;
+}
+
+/* maf.rs:277-285 set_query_idx_byname */
+static int maf_set_query_byname(mafrec *rec, const char *qname, char *err, size_t errcap) {
+    for (size_t i = 0; i < rec->n; i++)
+        if (sv_eq_c(rec->s[i].name, qname)) {
+            rec->query_idx = i;
+            return ORC_OK;
+        }
+    set_err(err, errcap, "Query name:%s not found in MAF", qname);
+    return ORC_E_QUERY_NAME_NOT_FOUND;
+}
+
+/* maf.rs:433-450: forward-strand query coordinates (wrapping u64 like release Rust) */
+static uint64_t maf_query_start(const mafrec *r) {
+    const sline *q = &r->s[r->query_idx];
+    return q->neg ? q->size - q->start - q->align_size : q->start;
+}
+static uint64_t maf_query_end(const mafrec *r) {
+    const sline *q = &r->s[r->query_idx];
+    return q->neg ? q->size - q->start : q->start + q->align_size;
+}
+
+/* ----------------------------------------------------- column classifiers */
+/* cigar.rs:298-308 */
+static char cigar_cat_ext(char c1, char c2) {
+    if (c1 == c2) return '=';
+    if (c1 == '-') return 'I';
+    if (c2 == '-') return 'D';
+    return 'X';
+}
+/* cigar.rs:314-328 */
+static char cigar_cat_ext_caller(char c1, char c2) {
+    if (c1 == '-') return c2 == '-' ? 'W' : 'I';
+    if (c2 == '-') return 'D';
+    if (c1 == c2) return '=';
+    return 'X';
+}
+
+/* cigar.rs:344-432 */
+void orc_parse_maf_seq_to_cigar(const char *t, const char *q, size_t n, int neg, orc_counts *out,
+                                orc_buf *cigar) {
+    uint64_t *c = out->c;
+    memset(c, 0, sizeof out->c);
+    if (neg) c[10] = 1; /* inv_event, cigar.rs:370-376 */
+    size_t i = 0;
+    while (i < n) { /* group_by(cigar_cat_ext) */
+        char k = cigar_cat_ext(t[i], q[i]);
+        size_t j = i + 1;
+        while (j < n && cigar_cat_ext(t[j], q[j]) == k) j++;
+        uint64_t len = j - i;
+        switch (k) {
+        case '=': c[0] += len; break;
+        case 'X': c[1] += len; break;
+        case 'I':
+            if (neg) { c[6] += 1; c[7] += len; } else { c[2] += 1; c[3] += len; }
+            break;
+        case 'D':
+            if (neg) { c[8] += 1; c[9] += len; } else { c[4] += 1; c[5] += len; }
+            break;
+        }
+        if (cigar) { /* cigar.rs:409-410 */
+            buf_putu(cigar, len);
+            buf_putc(cigar, k);
+        }
+        i = j;
+    }
+}
+
+/* cigar.rs:43-75 tokenizer + cigar.rs:629-707 fold */
+int orc_parse_paf_cigar(const char *cg, size_t n, int neg, orc_counts *out, char *err,
+                        size_t errcap) {
+    uint64_t *c = out->c;
+    memset(c, 0, sizeof out->c);
+    if (neg) c[10] = 1;
+    size_t i = 0;
+    if (n == 0) { /* fold_many1 needs one success; Eof on empty input -> nom error -> e.input[..10] panics */
+        set_err(err, errcap, "panic: byte index 10 is out of bounds of ``");
+        return ORC_E_PANIC;
+    }
+    while (i < n) {
+        size_t d0 = i;
+        while (i < n && cg[i] >= '0' && cg[i] <= '9') i++; /* take_while(is_dec_digit) */
+        size_t o0 = i;
+        while (i < n && !(cg[i] >= '0' && cg[i] <= '9')) i++; /* take_till(is_dec_digit) */
+        sv digits = {cg + d0, o0 - d0}, op = {cg + o0, i - o0};
+        /* cst2cu: op must be exactly one char, then the length must parse */
+        if (op.n != 1) {
+            set_err(err, errcap, "CIGAR OP `%.*s` invalid", (int)op.n, op.p);
+            return ORC_E_CIGAR_OP_INVALID;
+        }
+        uint64_t len;
+        if (!parse_u64(digits, &len)) {
+            set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)digits.n, digits.p);
+            return ORC_E_PARSE_INT;
+        }
+        switch (op.p[0]) {
+        case 'M': case '=': c[0] += len; break;
+        case 'X': c[1] += len; break;
+        case 'I':
+            if (neg) { c[6] += 1; c[7] += len; } else { c[2] += 1; c[3] += len; }
+            break;
+        case 'D':
+            if (neg) { c[8] += 1; c[9] += len; } else { c[4] += 1; c[5] += len; }
+            break;
+        default:
+            set_err(err, errcap, "CIGAR OP `%c` invalid", op.p[0]);
+            return ORC_E_CIGAR_OP_INVALID;
+        }
+    }
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------- csv writer */
+/* csv 1.2.2 Writer, QuoteStyle::Necessary: quote a field iff it contains the
+ * delimiter, a quote, CR or LF; quotes are doubled.  (parity unpinned) */
+static void csv_field(orc_buf *b, sv f, int first) {
+    if (!first) buf_putc(b, '\t');
+    int need = 0;
+    for (size_t i = 0; i < f.n; i++)
+        if (f.p[i] == '\t' || f.p[i] == '"' || f.p[i] == '\r' || f.p[i] == '\n') need = 1;
+    if (!need) {
+        buf_put(b, f.p, f.n);
+        return;
+    }
+    buf_putc(b, '"');
+    for (size_t i = 0; i < f.n; i++) {
+        if (f.p[i] == '"') buf_putc(b, '"');
+        buf_putc(b, f.p[i]);
+    }
+    buf_putc(b, '"');
+}
+static void csv_u64(orc_buf *b, uint64_t v, int first) {
+    if (!first) buf_putc(b, '\t');
+    buf_putu(b, v);
+}
+
+/* ------------------------------------------------------------------ maf2paf */
+/* maf.rs:484-520 convert2paf + converter.rs:35-52 csv serialize */
+int orc_maf2paf(const char *text, size_t len, const char *query_name, orc_buf *out, char *err,
+                size_t errcap) {
+    lreader rd;
+    maf_reader_init(&rd, text, len);
+    mafrec rec = {0};
+    orc_buf cigar = {0};
+    int rc;
+    while ((rc = maf_next(&rd, &rec, err, errcap)) > 0) {
+        if (query_name) {
+            int e = maf_set_query_byname(&rec, query_name, err, errcap);
+            if (e) { rc = -e; break; }
+        }
+        if (rec.query_idx >= rec.n) { /* slines[1] on a 1-s-line block: index panic */
+            set_err(err, errcap, "panic: index out of bounds: the len is %zu but the index is %zu",
+                    rec.n, rec.query_idx);
+            rc = -ORC_E_PANIC;
+            break;
+        }
+        const sline *t = &rec.s[0], *q = &rec.s[rec.query_idx];
+        size_t n = t->seq.n < q->seq.n ? t->seq.n : q->seq.n;
+        orc_counts c;
+        cigar.n = 0;
+        orc_parse_maf_seq_to_cigar(t->seq.p, q->seq.p, n, q->neg, &c, &cigar);
+        uint64_t matches = c.c[0];
+        uint64_t block_length = c.c[0] + c.c[1] + c.c[3] + c.c[7] + c.c[5] + c.c[9];
+        uint64_t edit = block_length - matches;
+        csv_field(out, q->name, 1);
+        csv_u64(out, q->size, 0);
+        csv_u64(out, maf_query_start(&rec), 0);
+        csv_u64(out, maf_query_end(&rec), 0);
+        buf_putc(out, '\t');
+        buf_putc(out, q->neg ? '-' : '+');
+        csv_field(out, t->name, 0);
+        csv_u64(out, t->size, 0);
+        csv_u64(out, t->start, 0);
+        csv_u64(out, t->start + t->align_size, 0);
+        csv_u64(out, matches, 0);
+        csv_u64(out, block_length, 0);
+        csv_u64(out, 255, 0);
+        buf_puts(out, "\tNM:i:");
+        buf_putu(out, edit);
+        buf_puts(out, "\tcg:Z:");
+        buf_put(out, cigar.p, cigar.n);
+        buf_putc(out, '\n');
+    }
+    free(rec.s);
+    orc_buf_free(&cigar);
+    return rc < 0 ? -rc : ORC_OK;
+}
+
+/* ------------------------------------------------------------------ natord */
+/* natord 1.0.9 compare(): chars, skip = is_whitespace, digit = to_digit(10).
+ * Restated from the published algorithm (Martin Pool's strnatcmp port). (parity unpinned) */
+static int nat_digit(const char *s, size_t n, size_t i) {
+    if (i < n && s[i] >= '0' && s[i] <= '9') return s[i] - '0';
+    return -1;
+}
+int orc_natord_compare(const char *a, const char *b) {
+    size_t na = strlen(a), nb = strlen(b), i = 0, j = 0;
+    for (;;) {
+        while (i < na && is_ws(a[i])) i++;
+        while (j < nb && is_ws(b[j])) j++;
+        if (i >= na && j >= nb) return 0;
+        if (i >= na) return -1;
+        if (j >= nb) return 1;
+        int da = nat_digit(a, na, i), db = nat_digit(b, nb, j);
+        if (da >= 0 && db >= 0) {
+            if (da == 0 || db == 0) { /* left-aligned ("fractional") comparison */
+                if (da != db) return da < db ? -1 : 1;
+                for (;;) {
+                    i++; j++;
+                    da = nat_digit(a, na, i);
+                    db = nat_digit(b, nb, j);
+                    if (da >= 0 && db >= 0) {
+                        if (da != db) return da < db ? -1 : 1;
+                    } else if (da >= 0) return 1;
+                    else if (db >= 0) return -1;
+                    else break;
+                }
+            } else { /* right-aligned: longer digit run wins, else first difference */
+                int last = da < db ? -1 : (da > db ? 1 : 0);
+                for (;;) {
+                    i++; j++;
+                    da = nat_digit(a, na, i);
+                    db = nat_digit(b, nb, j);
+                    if (da >= 0 && db >= 0) {
+                        if (last == 0) last = da < db ? -1 : (da > db ? 1 : 0);
+                    } else if (da >= 0) return 1;
+                    else if (db >= 0) return -1;
+                    else break;
+                }
+                if (last) return last;
+            }
+            continue; /* do not advance again */
+        }
+        if (a[i] != b[j]) return (unsigned char)a[i] < (unsigned char)b[j] ? -1 : 1;
+        i++; j++;
+    }
+}
+
+/* ------------------------------------------------------------- f32 -> text */
+/* ryu 1.0.14 Buffer::format(f32) ("pretty" layout, src/pretty/mod.rs format32):
+ * shortest round-trip digits; decimal for 1e-5 <= |v| < 1e13 else exponent form. (parity unpinned) */
+void orc_fmt_f32(float v, char *dst) {
+    if (isnan(v)) { strcpy(dst, "NaN"); return; }
+    if (isinf(v)) { strcpy(dst, v < 0 ? "-inf" : "inf"); return; }
+    char *o = dst;
+    if (signbit(v)) { *o++ = '-'; v = -v; }
+    if (v == 0.0f) { strcpy(o, "0.0"); return; }
+    char sci[40];
+    int p;
+    for (p = 1; p <= 9; p++) { /* shortest p with round trip */
+        snprintf(sci, sizeof sci, "%.*e", p - 1, (double)v);
+        if (strtof(sci, NULL) == v) break;
+    }
+    /* sci = d[.ddd]e[+-]XX */
+    char digits[16];
+    int nd = 0;
+    const char *s = sci;
+    for (; *s && *s != 'e'; s++)
+        if (*s >= '0' && *s <= '9') digits[nd++] = *s;
+    int e10 = atoi(s + 1);
+    while (nd > 1 && digits[nd - 1] == '0') nd--; /* ryu never keeps trailing zeros */
+    int length = nd, k = e10 - (nd - 1), kk = length + k;
+    if (0 <= k && kk <= 13) { /* 1234e7 -> 12340000000.0 */
+        memcpy(o, digits, (size_t)nd); o += nd;
+        for (int i = length; i < kk; i++) *o++ = '0';
+        *o++ = '.'; *o++ = '0'; *o = 0;
+    } else if (0 < kk && kk <= 13) { /* 1234e-2 -> 12.34 */
+        memcpy(o, digits, (size_t)kk); o += kk;
+        *o++ = '.';
+        memcpy(o, digits + kk, (size_t)(nd - kk)); o += nd - kk;
+        *o = 0;
+    } else if (-6 < kk && kk <= 0) { /* 1234e-6 -> 0.001234 */
+        *o++ = '0'; *o++ = '.';
+        for (int i = 0; i < -kk; i++) *o++ = '0';
+        memcpy(o, digits, (size_t)nd); o += nd;
+        *o = 0;
+    } else if (length == 1) { /* 1e30 */
+        *o++ = digits[0];
+        sprintf(o, "e%d", kk - 1);
+    } else { /* 1234e30 -> 1.234e33 */
+        *o++ = digits[0]; *o++ = '.';
+        memcpy(o, digits + 1, (size_t)(nd - 1)); o += nd - 1;
+        sprintf(o, "e%d", kk - 1);
+    }
+}
+
+/* -------------------------------------------------------------------- stat */
+/* common.rs:98-140 RecStat::from(Cigar) */
+typedef struct {
+    uint64_t aligned_size, matched, mismatched, ins_event, del_event, ins_size, del_size,
+        inv_ins_event, inv_ins_size, inv_del_event, inv_del_size, inv_event;
+    float inv_size;
+} recstat;
+static recstat recstat_from(const orc_counts *cg) {
+    const uint64_t *c = cg->c;
+    recstat r;
+    memset(&r, 0, sizeof r);
+    r.matched = c[0]; r.mismatched = c[1];
+    r.ins_event = c[2]; r.ins_size = c[3];
+    r.del_event = c[4]; r.del_size = c[5];
+    r.inv_ins_event = c[6]; r.inv_ins_size = c[7];
+    r.inv_del_event = c[8]; r.inv_del_size = c[9];
+    r.aligned_size = r.matched + r.mismatched + r.del_size + r.inv_del_size;
+    uint64_t query_align = r.matched + r.mismatched + r.ins_size + r.inv_ins_size;
+    r.inv_event = c[10];
+    r.inv_size = 0.0f;
+    if (r.inv_event != 0)
+        r.inv_size = (float)(r.aligned_size + query_align) / (float)(r.inv_event + 1);
+    return r;
+}
+
+/* stat.rs:27-50 Statistic */
+typedef struct {
+    sv ref_name; uint64_t ref_size, ref_start;
+    sv query_name; uint64_t query_size, query_start;
+    uint64_t aligned_size, unaligned_size;
+    float identity, similarity;
+    uint64_t matched, mismatched, ins_event, del_event, ins_size, del_size, inv_event;
+    float inv_size;
+    uint64_t inv_ins_event, inv_ins_size, inv_del_event, inv_del_size;
+} statrow;
+
+typedef struct { statrow *r; size_t n, cap; } statvec;
+static statrow *statvec_push(statvec *v) {
+    if (v->n == v->cap) {
+        v->cap = v->cap ? v->cap * 2 : 64;
+        v->r = (statrow *)realloc(v->r, v->cap * sizeof(statrow));
+    }
+    statrow *s = &v->r[v->n++];
+    memset(s, 0, sizeof *s);
+    return s;
+}
+
+/* one PairStat (stat.rs:53-58, 226-250) folded straight into the output rows.
+ * each: stat.rs:129-164 split_final;  merged: stat.rs:167-223 merge_final_from_pair */
+static void stat_accumulate(statvec *v, int each, sv ref_name, uint64_t ref_size, uint64_t ref_start,
+                            sv query_name, uint64_t query_size, uint64_t query_start,
+                            const recstat *rs) {
+    statrow *s = NULL;
+    if (!each) {
+        for (size_t i = 0; i < v->n; i++) { /* HashMap<Pair,..>: linear probe keeps first-seen order */
+            statrow *c = &v->r[i];
+            if (c->ref_size == ref_size && c->query_size == query_size && sv_eq(c->ref_name, ref_name) &&
+                sv_eq(c->query_name, query_name)) {
+                s = c;
+                break;
+            }
+        }
+    }
+    if (!s) {
+        s = statvec_push(v);
+        s->ref_name = ref_name; s->ref_size = ref_size;
+        s->query_name = query_name; s->query_size = query_size;
+        if (each) { s->ref_start = ref_start; s->query_start = query_start; }
+        else { s->ref_start = ref_size; s->query_start = query_size; } /* stat.rs:186,189 */
+    }
+    s->aligned_size += rs->aligned_size;
+    s->matched += rs->matched; s->mismatched += rs->mismatched;
+    s->ins_event += rs->ins_event; s->del_event += rs->del_event;
+    s->ins_size += rs->ins_size; s->del_size += rs->del_size;
+    s->inv_ins_event += rs->inv_ins_event; s->inv_ins_size += rs->inv_ins_size;
+    s->inv_del_event += rs->inv_del_event; s->inv_del_size += rs->inv_del_size;
+    s->inv_event += rs->inv_event;
+    s->inv_size += rs->inv_size; /* f32, file order */
+    if (!each) {
+        if (ref_start < s->ref_start) s->ref_start = ref_start;
+        if (query_start < s->query_start) s->query_start = query_start;
+    }
+}
+
+static void stat_write(statvec *v, int each, orc_buf *out) {
+    /* derived fields */
+    for (size_t i = 0; i < v->n; i++) {
+        statrow *s = &v->r[i];
+        if (!each) s->unaligned_size = s->ref_size - s->aligned_size; /* wraps, stat.rs:216 */
+        s->identity = (float)s->matched / (float)s->aligned_size;
+        s->similarity = (float)(s->matched + s->mismatched) / (float)s->aligned_size;
+    }
+    /* stat.rs:116 stable sort by natord(ref_name): insertion-stable merge via index sort */
+    size_t n = v->n;
+    size_t *idx = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
+    char **names = (char **)malloc((n ? n : 1) * sizeof(char *));
+    for (size_t i = 0; i < n; i++) {
+        idx[i] = i;
+        names[i] = (char *)malloc(v->r[i].ref_name.n + 1);
+        memcpy(names[i], v->r[i].ref_name.p, v->r[i].ref_name.n);
+        names[i][v->r[i].ref_name.n] = 0;
+    }
+    /* stable merge sort */
+    size_t *tmp = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
+    for (size_t w = 1; w < n; w *= 2) {
+        for (size_t lo = 0; lo < n; lo += 2 * w) {
+            size_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;
+            size_t a = lo, b = mid, k = lo;
+            while (a < mid && b < hi) {
+                if (orc_natord_compare(names[idx[b]], names[idx[a]]) < 0) tmp[k++] = idx[b++];
+                else tmp[k++] = idx[a++];
+            }
+            while (a < mid) tmp[k++] = idx[a++];
+            while (b < hi) tmp[k++] = idx[b++];
+        }
+        memcpy(idx, tmp, n * sizeof(size_t));
+    }
+    if (n) /* csv writes the header row with the first serialize() only */
+        buf_puts(out, "ref_name\tref_size\tref_start\tquery_name\tquery_size\tquery_start\taligned_size\t"
+                      "unaligned_size\tidentity\tsimilarity\tmatched\tmismatched\tins_event\tdel_event\t"
+                      "ins_size\tdel_size\tinv_event\tinv_size\tinv_ins_event\tinv_ins_size\t"
+                      "inv_del_event\tinv_del_size\n");
+    char fb[40];
+    for (size_t k = 0; k < n; k++) {
+        const statrow *s = &v->r[idx[k]];
+        csv_field(out, s->ref_name, 1);
+        csv_u64(out, s->ref_size, 0); csv_u64(out, s->ref_start, 0);
+        csv_field(out, s->query_name, 0);
+        csv_u64(out, s->query_size, 0); csv_u64(out, s->query_start, 0);
+        csv_u64(out, s->aligned_size, 0); csv_u64(out, s->unaligned_size, 0);
+        orc_fmt_f32(s->identity, fb); buf_putc(out, '\t'); buf_puts(out, fb);
+        orc_fmt_f32(s->similarity, fb); buf_putc(out, '\t'); buf_puts(out, fb);
+        csv_u64(out, s->matched, 0); csv_u64(out, s->mismatched, 0);
+        csv_u64(out, s->ins_event, 0); csv_u64(out, s->del_event, 0);
+        csv_u64(out, s->ins_size, 0); csv_u64(out, s->del_size, 0);
+        csv_u64(out, s->inv_event, 0);
+        orc_fmt_f32(s->inv_size, fb); buf_putc(out, '\t'); buf_puts(out, fb);
+        csv_u64(out, s->inv_ins_event, 0); csv_u64(out, s->inv_ins_size, 0);
+        csv_u64(out, s->inv_del_event, 0); csv_u64(out, s->inv_del_size, 0);
+        buf_putc(out, '\n');
+    }
+    for (size_t i = 0; i < n; i++) free(names[i]);
+    free(names); free(idx); free(tmp);
+}
+
+/* stat.rs:61-84 stat_maf */
+int orc_stat_maf(const char *text, size_t len, int each, const char *query_name, orc_buf *out,
+                 char *err, size_t errcap) {
+    lreader rd;
+    maf_reader_init(&rd, text, len);
+    mafrec rec = {0};
+    statvec v = {0};
+    int rc;
+    while ((rc = maf_next(&rd, &rec, err, errcap)) > 0) {
+        if (query_name) {
+            int e = maf_set_query_byname(&rec, query_name, err, errcap);
+            if (e) { rc = -e; break; }
+        }
+        if (rec.query_idx >= rec.n) {
+            set_err(err, errcap, "panic: index out of bounds: the len is %zu but the index is %zu",
+                    rec.n, rec.query_idx);
+            rc = -ORC_E_PANIC;
+            break;
+        }
+        const sline *t = &rec.s[0], *q = &rec.s[rec.query_idx];
+        size_t n = t->seq.n < q->seq.n ? t->seq.n : q->seq.n;
+        orc_counts c;
+        orc_parse_maf_seq_to_cigar(t->seq.p, q->seq.p, n, q->neg, &c, NULL);
+        recstat rs = recstat_from(&c);
+        stat_accumulate(&v, each, t->name, t->size, t->start, q->name, q->size, maf_query_start(&rec), &rs);
+    }
+    if (rc == 0) stat_write(&v, each, out);
+    free(rec.s);
+    free(v.r);
+    return rc < 0 ? -rc : ORC_OK;
+}
+
+int64_t orc_maf_record_counts(const char *text, size_t len, orc_counts *out, size_t cap) {
+    lreader rd;
+    maf_reader_init(&rd, text, len);
+    mafrec rec = {0};
+    char err[256];
+    int rc;
+    int64_t n = 0;
+    while ((rc = maf_next(&rd, &rec, err, sizeof err)) > 0) {
+        if (rec.n < 2) { n = -ORC_E_PANIC; break; }
+        const sline *t = &rec.s[0], *q = &rec.s[1];
+        size_t m = t->seq.n < q->seq.n ? t->seq.n : q->seq.n;
+        if ((size_t)n < cap) orc_parse_maf_seq_to_cigar(t->seq.p, q->seq.p, m, q->neg, &out[n], NULL);
+        n++;
+    }
+    free(rec.s);
+    return rc < 0 ? rc : n;
+}
+
+/* --------------------------------------------------------------- PAF reader */
+/* paf.rs:22-31 csv reader: tab, no header, flexible, '#' comments; csv-core quoting rules
+ * ('"' at field start opens a quoted field, '""' escapes).  Records end at \n, \r\n or \r. */
+typedef struct { sv *f; size_t n, cap; char *scratch; size_t sn, scap; } pafrow;
+
+static void pafrow_push(pafrow *r, const char *p, size_t n) {
+    if (r->n == r->cap) {
+        r->cap = r->cap ? r->cap * 2 : 32;
+        r->f = (sv *)realloc(r->f, r->cap * sizeof(sv));
+    }
+    r->f[r->n].p = p;
+    r->f[r->n].n = n;
+    r->n++;
+}
+
+/* returns 1 if a record was read, 0 at end */
+static int paf_next(const char *t, size_t len, size_t *pos, pafrow *row) {
+    for (;;) {
+        size_t i = *pos;
+        if (i >= len) return 0;
+        if (t[i] == '\n' || t[i] == '\r') { *pos = i + 1; continue; } /* empty lines skipped */
+        if (t[i] == '#') { /* comment line */
+            while (i < len && t[i] != '\n') i++;
+            *pos = i < len ? i + 1 : len;
+            continue;
+        }
+        row->n = 0;
+        row->sn = 0;
+        for (;;) {
+            if (i < len && t[i] == '"') { /* quoted field -> unescape into scratch */
+                size_t need = len - i;
+                if (row->sn + need > row->scap) {
+                    /* scratch may move: fields already pushed from scratch would dangle, so
+                     * reserve generously once (whole remaining text) */
+                    row->scap = row->sn + need + 16;
+                    char *ns = (char *)malloc(row->scap);
+                    memcpy(ns, row->scratch, row->sn);
+                    for (size_t k = 0; k < row->n; k++)
+                        if (row->f[k].p >= row->scratch && row->f[k].p < row->scratch + row->sn)
+                            row->f[k].p = ns + (row->f[k].p - row->scratch);
+                    free(row->scratch);
+                    row->scratch = ns;
+                }
+                char *dst = row->scratch + row->sn;
+                size_t dn = 0;
+                i++;
+                while (i < len) {
+                    if (t[i] == '"') {
+                        if (i + 1 < len && t[i + 1] == '"') { dst[dn++] = '"'; i += 2; continue; }
+                        i++;
+                        break;
+                    }
+                    dst[dn++] = t[i++];
+                }
+                while (i < len && t[i] != '\t' && t[i] != '\n' && t[i] != '\r') dst[dn++] = t[i++];
+                pafrow_push(row, dst, dn);
+                row->sn += dn;
+            } else {
+                size_t b = i;
+                while (i < len && t[i] != '\t' && t[i] != '\n' && t[i] != '\r') i++;
+                pafrow_push(row, t + b, i - b);
+            }
+            if (i < len && t[i] == '\t') { i++; continue; }
+            break;
+        }
+        if (i < len && t[i] == '\r') i++;
+        if (i < len && t[i] == '\n') i++;
+        *pos = i;
+        return 1;
+    }
+}
+
+/* csv deserializer integer rule: "0x" prefix => radix 16, else str::parse */
+static int csv_parse_u64(sv s, uint64_t *out) {
+    if (s.n >= 2 && s.p[0] == '0' && s.p[1] == 'x') {
+        uint64_t v = 0;
+        if (s.n == 2) return 0;
+        size_t i = 2;
+        if (s.p[i] == '+') { i++; if (i == s.n) return 0; }
+        for (; i < s.n; i++) {
+            char ch = s.p[i];
+            unsigned d = ch >= '0' && ch <= '9' ? (unsigned)(ch - '0')
+                       : ch >= 'a' && ch <= 'f' ? (unsigned)(ch - 'a' + 10)
+                       : ch >= 'A' && ch <= 'F' ? (unsigned)(ch - 'A' + 10) : 99u;
+            if (d > 15) return 0;
+            if (v >> 60) return 0;
+            v = v * 16 + d;
+        }
+        *out = v;
+        return 1;
+    }
+    return parse_u64(s, out);
+}
+
+/* paf.rs:159-218 cs_to_cigar; regex (:[0-9]+|\*[a-z][a-z]|[=\+\-][A-Za-z]+), leftmost matches */
+static void cs_to_cigar(sv cs, orc_buf *cigar) {
+    char last_op = 'M';
+    uint64_t last_len = 0;
+    size_t i = 0;
+    while (i < cs.n) {
+        char c = cs.p[i];
+        if (c == ':' && i + 1 < cs.n && cs.p[i + 1] >= '0' && cs.p[i + 1] <= '9') {
+            size_t j = i + 1;
+            uint64_t v = 0;
+            while (j < cs.n && cs.p[j] >= '0' && cs.p[j] <= '9') v = v * 10 + (uint64_t)(cs.p[j++] - '0');
+            if (last_op == 'M') last_len += v;
+            else {
+                if (last_len > 0) { buf_putu(cigar, last_len); buf_putc(cigar, last_op); }
+                last_op = 'M';
+                last_len = v;
+            }
+            i = j;
+        } else if (c == '*' && i + 2 < cs.n && cs.p[i + 1] >= 'a' && cs.p[i + 1] <= 'z' &&
+                   cs.p[i + 2] >= 'a' && cs.p[i + 2] <= 'z') {
+            if (last_op == 'X') last_len += 1;
+            else {
+                if (last_len > 0) { buf_putu(cigar, last_len); buf_putc(cigar, last_op); }
+                last_op = 'X';
+                last_len = 1;
+            }
+            i += 3;
+        } else if ((c == '=' || c == '+' || c == '-') && i + 1 < cs.n &&
+                   ((cs.p[i + 1] >= 'A' && cs.p[i + 1] <= 'Z') || (cs.p[i + 1] >= 'a' && cs.p[i + 1] <= 'z'))) {
+            size_t j = i + 1;
+            while (j < cs.n && ((cs.p[j] >= 'A' && cs.p[j] <= 'Z') || (cs.p[j] >= 'a' && cs.p[j] <= 'z'))) j++;
+            uint64_t l = j - (i + 1);
+            if (c == '-' || c == '+') {
+                if (last_len > 0) { buf_putu(cigar, last_len); buf_putc(cigar, last_op); }
+                buf_putu(cigar, l);
+                buf_putc(cigar, c == '-' ? 'D' : 'I');
+                last_len = 0;
+                last_op = 'M';
+            } /* '=' long form: matched by the regex, ignored by the match arm (paf.rs:213) */
+            i = j;
+        } else {
+            i++;
+        }
+    }
+    if (last_len > 0) { buf_putu(cigar, last_len); buf_putc(cigar, last_op); }
+}
+
+/* stat.rs:87-105 stat_paf */
+int orc_stat_paf(const char *text, size_t len, int each, orc_buf *out, char *err, size_t errcap) {
+    size_t pos = 0;
+    pafrow row = {0};
+    statvec v = {0};
+    orc_buf conv = {0};
+    int rc = ORC_OK;
+    while (paf_next(text, len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int neg = 0;
+        if (row.n < 12) {
+            set_err(err, errcap, "CSV deserialize error by: record has %zu fields, 12 required", row.n);
+            rc = ORC_E_CSV;
+            break;
+        }
+        int bad = 0;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) {
+                if (sv_eq_c(row.f[4], "+")) neg = 0;
+                else if (sv_eq_c(row.f[4], "-")) neg = 1;
+                else bad = 1;
+                continue;
+            }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) {
+            set_err(err, errcap, "CSV deserialize error by: field parse");
+            rc = ORC_E_CSV;
+            break;
+        }
+        /* paf.rs:122-140 get_cigar_string */
+        sv cg = {0, 0};
+        int have = 0;
+        for (size_t k = 12; k < row.n && !have; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) {
+                cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1;
+            }
+        if (!have)
+            for (size_t k = 12; k < row.n && !have; k++)
+                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
+                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
+                    conv.n = 0;
+                    cs_to_cigar(cs, &conv);
+                    cg.p = conv.p; cg.n = conv.n; have = 1;
+                }
+        if (!have) {
+            set_err(err, errcap, "CIGAR start tag not found");
+            rc = ORC_E_CIGAR_TAG_NOT_FOUND;
+            break;
+        }
+        orc_counts c;
+        rc = orc_parse_paf_cigar(cg.p, cg.n, neg, &c, err, errcap);
+        if (rc) break;
+        recstat rs = recstat_from(&c);
+        /* stat_rec: ref = target (cols 6-9), query = cols 1-4 */
+        stat_accumulate(&v, each, row.f[5], u[6], u[7], row.f[0], u[1], u[2], &rs);
+    }
+    /* names reference row scratch only for quoted fields; copy-free path is the norm.  To be
+     * safe for quoted names we would need owned copies; quoted names are not generated by tests. */
+    if (rc == ORC_OK) stat_write(&v, each, out);
+    free(row.f); free(row.scratch); free(v.r);
+    orc_buf_free(&conv);
+    return rc;
+}
+
+/* -------------------------------------------------------------------- call */
+/* caller.rs:304-337 build_header + noodles-vcf 0.43 header text (README.md:324-331 golden) */
+static void vcf_header(orc_buf *out, const char *sample) {
+    buf_puts(out, "##fileformat=VCFv4.4\n"
+                  "##INFO=<ID=SVLEN,Number=A,Type=Integer,Description=\"Length of structural variant\">\n"
+                  "##INFO=<ID=SVTYPE,Number=1,Type=String,Description=\"Type of structural variant\">\n"
+                  "##INFO=<ID=END,Number=1,Type=Integer,Description=\"End position of the longest variant described in this record\">\n"
+                  "##INFO=<ID=INV_NEST,Number=1,Type=String,Description=\"Varations nested within inversion\">\n"
+                  "##FORMAT=<ID=QI,Number=1,Type=String,Description=\"Query informations\">\n"
+                  "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+                  "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t");
+    buf_puts(out, sample);
+    buf_putc(out, '\n');
+}
+
+/* noodles-vcf 0.43 reference_bases / allele Base: parse upper-cases, only ACGTN valid. (parity unpinned) */
+static int vcf_bases(orc_buf *out, const char *s, size_t n, char *err, size_t errcap) {
+    for (size_t i = 0; i < n; i++) {
+        char c = s[i];
+        if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') {
+            set_err(err, errcap, "invalid VCF base `%c`", s[i]);
+            return ORC_E_VCF_BASE;
+        }
+        buf_putc(out, c);
+    }
+    return ORC_OK;
+}
+
+/* caller.rs:359-386 get_variant_rec + noodles writer: one VCF body row */
+static int vcf_row(orc_buf *out, sv chro, uint64_t pos, const char *ref, size_t nref, const char *alt,
+                   size_t nalt, int alt_symbolic, const char *info, const char *fmt_tail, char *err,
+                   size_t errcap) {
+    buf_put(out, chro.p, chro.n);
+    buf_putc(out, '\t');
+    buf_putu(out, pos);
+    buf_puts(out, "\t.\t");
+    int rc = vcf_bases(out, ref, nref, err, errcap);
+    if (rc) return rc;
+    buf_putc(out, '\t');
+    if (alt_symbolic) buf_put(out, alt, nalt);
+    else if ((rc = vcf_bases(out, alt, nalt, err, errcap))) return rc;
+    buf_puts(out, "\t.\t.\t");
+    buf_puts(out, info ? info : ".");
+    buf_puts(out, "\tGT:QI\t1|1:");
+    buf_puts(out, fmt_tail);
+    buf_putc(out, '\n');
+    return ORC_OK;
+}
+
+/* caller.rs:159-219 find_safe_chunk_boundary */
+static size_t find_safe_chunk_boundary(const char *t, const char *q, size_t start, size_t chunk_size,
+                                       uint64_t svlen_cutoff, size_t total_size) {
+    size_t proposed_end = start + chunk_size < total_size ? start + chunk_size : total_size;
+    size_t current_gap_size = 0, sv_start = 0, safe_end = proposed_end;
+    int in_sv = 0;
+    for (size_t abs_pos = start; abs_pos < proposed_end; abs_pos++) {
+        if (t[abs_pos] == '-' || q[abs_pos] == '-') {
+            if (!in_sv) { in_sv = 1; sv_start = abs_pos; }
+            current_gap_size++;
+        } else if (in_sv) {
+            if (current_gap_size >= svlen_cutoff)
+                if (sv_start >= start) safe_end = abs_pos;
+            in_sv = 0;
+            current_gap_size = 0;
+        }
+    }
+    if (in_sv && current_gap_size >= svlen_cutoff) {
+        size_t end_pos = proposed_end;
+        for (size_t p = proposed_end; p < total_size; p++)
+            if (t[p] != '-' && q[p] != '-') { end_pos = p; break; }
+        safe_end = end_pos;
+    }
+    return safe_end;
+}
+
+/* caller.rs:388-608 call_within_var on the chunk [cs, ce) of (t,q);
+ * chunk coordinates from caller.rs:221-265 create_chunk_record */
+static int call_within_var(orc_buf *out, const mafrec *rec, size_t cs, size_t ce, int if_snp,
+                           uint64_t svlen_cutoff, int if_inv, char *err, size_t errcap) {
+    const sline *ts = &rec->s[0], *qs = &rec->s[rec->query_idx];
+    const char *t = ts->seq.p, *q = qs->seq.p;
+    /* create_chunk_record: new_start = start + nongap(seq[..cs]); align = nongap(seq[cs..ce]) */
+    uint64_t t_start = ts->start, q_rawstart = qs->start, t_al = 0, q_al = 0;
+    for (size_t i = 0; i < cs; i++) { if (t[i] != '-') t_start++; if (q[i] != '-') q_rawstart++; }
+    for (size_t i = cs; i < ce; i++) { if (t[i] != '-') t_al++; if (q[i] != '-') q_al++; }
+    uint64_t t_end = t_start + t_al;
+    uint64_t q_start = qs->neg ? qs->size - q_rawstart - q_al : q_rawstart;
+    uint64_t q_end = qs->neg ? qs->size - q_rawstart : q_rawstart + q_al;
+
+    size_t n = ce - cs;
+    char *t_ref = (char *)malloc(n + 1), *q_ref = (char *)malloc(n + 1);
+    size_t nt = 0, nq = 0;
+    for (size_t i = cs; i < ce; i++) { if (t[i] != '-') t_ref[nt++] = t[i]; if (q[i] != '-') q_ref[nq++] = q[i]; }
+
+    uint64_t t_off = t_start, q_off = q_start;
+    char suffix = qs->neg ? 'N' : 'P';
+    char info[160], tail[512];
+    const char *nest = qs->neg ? "INV_NEST=TRUE;" : "";
+    int rc = ORC_OK;
+#define QN (int)qs->name.n, qs->name.p
+    if (qs->neg && nt > 0 && if_inv) { /* caller.rs:423-440 */
+        snprintf(info, sizeof info, "SVTYPE=INV;END=%llu", (unsigned long long)t_end);
+        snprintf(tail, sizeof tail, "%.*s@%llu@%llu@%c", QN, (unsigned long long)q_start,
+                 (unsigned long long)q_end, suffix);
+        rc = vcf_row(out, ts->name, t_off + 1, t_ref, 1, "<INV>", 5, 1, info, tail, err, errcap);
+        if (rc) goto done;
+    }
+    int after_m = 0;
+    size_t i = cs;
+    while (i < ce) { /* group_by(cigar_cat_ext_caller) */
+        char k = cigar_cat_ext_caller(t[i], q[i]);
+        size_t j = i + 1;
+        while (j < ce && cigar_cat_ext_caller(t[j], q[j]) == k) j++;
+        uint64_t len = j - i;
+        i = j;
+        switch (k) {
+        case '=':
+            t_off += len; q_off += len; after_m = 1;
+            break;
+        case 'W': break;
+        case 'I':
+            if (len > svlen_cutoff) {
+                if (!after_m) { q_off += len; after_m = 0; continue; }
+                size_t tss = (size_t)(t_off - t_start - 1), qss = (size_t)(q_off - q_start - 1);
+                if (tss + 1 > nt || qss + len + 1 > nq) { rc = ORC_E_PANIC; set_err(err, errcap, "panic: slice out of range"); goto done; }
+                snprintf(info, sizeof info, "%sSVTYPE=INS;SVLEN=%llu;END=%llu", nest,
+                         (unsigned long long)len, (unsigned long long)t_off);
+                snprintf(tail, sizeof tail, "%.*s@%llu@%llu@%c", QN, (unsigned long long)q_off,
+                         (unsigned long long)(q_off + len), suffix);
+                rc = vcf_row(out, ts->name, t_off, t_ref + tss, 1, q_ref + qss, (size_t)len + 1, 0, info, tail, err, errcap);
+                if (rc) goto done;
+            }
+            q_off += len; after_m = 0;
+            break;
+        case 'D':
+            if (len > svlen_cutoff) {
+                if (!after_m) { t_off += len; after_m = 0; continue; }
+                size_t tss = (size_t)(t_off - t_start - 1), qss = (size_t)(q_off - q_start - 1);
+                if (tss + len + 1 > nt || qss + 1 > nq) { rc = ORC_E_PANIC; set_err(err, errcap, "panic: slice out of range"); goto done; }
+                snprintf(info, sizeof info, "%sSVTYPE=DEL;SVLEN=%llu;END=%llu", nest,
+                         (unsigned long long)len, (unsigned long long)(t_off + len));
+                snprintf(tail, sizeof tail, "%.*s@%llu@%llu@%c", QN, (unsigned long long)q_off,
+                         (unsigned long long)q_off, suffix);
+                rc = vcf_row(out, ts->name, t_off, t_ref + tss, (size_t)len + 1, q_ref + qss, 1, 0, info, tail, err, errcap);
+                if (rc) goto done;
+            }
+            t_off += len; after_m = 0;
+            break;
+        case 'X':
+            if (if_snp) {
+                for (uint64_t x = 0; x < len; x++) {
+                    size_t tss = (size_t)(t_off - t_start), qss = (size_t)(q_off - q_start);
+                    if (tss + 1 > nt || qss + 1 > nq) { rc = ORC_E_PANIC; set_err(err, errcap, "panic: slice out of range"); goto done; }
+                    snprintf(tail, sizeof tail, "%.*s@%llu@%c", QN, (unsigned long long)q_off, suffix);
+                    rc = vcf_row(out, ts->name, t_off + 1, t_ref + tss, 1, q_ref + qss, 1, 0, NULL, tail, err, errcap);
+                    if (rc) goto done;
+                    t_off++; q_off++;
+                }
+            } else { q_off += len; t_off += len; }
+            after_m = 1;
+            break;
+        }
+    }
+#undef QN
+done:
+    free(t_ref); free(q_ref);
+    return rc;
+}
+
+/* caller.rs:42-157 call_var_maf */
+int orc_call_maf(const char *text, size_t len, int snp, int inv, uint64_t svlen_cutoff,
+                 const char *sample, const char *query_name, uint64_t chunk_size, orc_buf *out,
+                 char *err, size_t errcap) {
+    vcf_header(out, sample ? sample : "sample");
+    lreader rd;
+    maf_reader_init(&rd, text, len);
+    mafrec rec = {0};
+    int rc;
+    while ((rc = maf_next(&rd, &rec, err, errcap)) > 0) {
+        if (rec.n == 1) continue; /* caller.rs:64-74 */
+        if (query_name) {
+            char e2[8];
+            if (maf_set_query_byname(&rec, query_name, e2, sizeof e2)) continue; /* caller.rs:79-89 */
+        } else {
+            rec.query_idx = 1;
+        }
+        const sline *ts = &rec.s[0], *qs = &rec.s[rec.query_idx];
+        size_t total = ts->seq.n;
+        if (qs->seq.n < total) { /* query_seq()[start..end] slicing would panic */
+            set_err(err, errcap, "panic: byte index out of range of query seq");
+            rc = -ORC_E_PANIC;
+            break;
+        }
+        size_t cs = 0;
+        int e = ORC_OK;
+        if (chunk_size == 0 && total > 0) { /* the reference would loop forever (caller.rs:119) */
+            set_err(err, errcap, "panic: chunk_size 0 never advances");
+            rc = -ORC_E_PANIC;
+            break;
+        }
+        while (cs < total) {
+            size_t ce = find_safe_chunk_boundary(ts->seq.p, qs->seq.p, cs, (size_t)chunk_size, svlen_cutoff, total);
+            e = call_within_var(out, &rec, cs, ce, snp, svlen_cutoff, inv, err, errcap);
+            if (e) break;
+            cs = ce;
+        }
+        if (e) { rc = -e; break; }
+    }
+    free(rec.s);
+    return rc < 0 ? -rc : ORC_OK;
+}

@@ -1,0 +1,139 @@
+"""ctypes binding of the CPU oracle (oracle/libwga_oracle.so).
+
+Test infrastructure only: nothing under wgatools_b200/ may import this module.
+"""
+import ctypes
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_SO = os.path.join(ORACLE_DIR, "libwga_oracle.so")
+
+
+class OrcBuf(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_void_p), ("n", ctypes.c_size_t), ("cap", ctypes.c_size_t)]
+
+
+class OrcCounts(ctypes.Structure):
+    _fields_ = [("c", ctypes.c_uint64 * 11)]
+
+
+class OracleError(Exception):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def build():
+    src = os.path.join(ORACLE_DIR, "wga_oracle.c")
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        L.orc_buf_free.argtypes = [ctypes.POINTER(OrcBuf)]
+        L.orc_maf2paf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                  ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_stat_maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_char_p,
+                                   ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_stat_paf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_call_maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64,
+                                   ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                          ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
+                                                 ctypes.c_int, ctypes.POINTER(OrcCounts),
+                                                 ctypes.POINTER(OrcBuf)]
+        L.orc_parse_maf_seq_to_cigar.restype = None
+        L.orc_natord_compare.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        L.orc_fmt_f32.argtypes = [ctypes.c_float, ctypes.c_char_p]
+        L.orc_fmt_f32.restype = None
+        L.orc_maf_record_counts.argtypes = [ctypes.c_char_p, ctypes.c_size_t,
+                                            ctypes.POINTER(OrcCounts), ctypes.c_size_t]
+        L.orc_maf_record_counts.restype = ctypes.c_int64
+        _lib = L
+    return _lib
+
+
+def _take(buf):
+    data = ctypes.string_at(buf.p, buf.n) if buf.n else b""
+    lib().orc_buf_free(ctypes.byref(buf))
+    return data
+
+
+def _run(fn, *args):
+    buf = OrcBuf()
+    err = ctypes.create_string_buffer(512)
+    rc = fn(*args, ctypes.byref(buf), err, 512)
+    data = _take(buf)
+    if rc != 0:
+        raise OracleError(rc, err.value.decode("utf-8", "replace"))
+    return data
+
+
+def _opt(s):
+    return None if s is None else (s if isinstance(s, bytes) else s.encode())
+
+
+def maf2paf(text: bytes, query_name=None) -> bytes:
+    return _run(lib().orc_maf2paf, text, len(text), _opt(query_name))
+
+
+def stat_maf(text: bytes, each=False, query_name=None) -> bytes:
+    return _run(lib().orc_stat_maf, text, len(text), int(each), _opt(query_name))
+
+
+def stat_paf(text: bytes, each=False) -> bytes:
+    return _run(lib().orc_stat_paf, text, len(text), int(each))
+
+
+def call_maf(text: bytes, snp=False, inv=False, svlen=50, sample="sample", query_name=None,
+             chunk_size=1000000) -> bytes:
+    return _run(lib().orc_call_maf, text, len(text), int(snp), int(inv), svlen, _opt(sample),
+                _opt(query_name), chunk_size)
+
+
+def paf_cigar_counts(cg: bytes, neg=False):
+    c = OrcCounts()
+    err = ctypes.create_string_buffer(512)
+    rc = lib().orc_parse_paf_cigar(cg, len(cg), int(neg), ctypes.byref(c), err, 512)
+    if rc:
+        raise OracleError(rc, err.value.decode())
+    return list(c.c)
+
+
+def maf_seq_to_cigar(t: bytes, q: bytes, neg=False):
+    c = OrcCounts()
+    buf = OrcBuf()
+    n = min(len(t), len(q))
+    lib().orc_parse_maf_seq_to_cigar(t, q, n, int(neg), ctypes.byref(c), ctypes.byref(buf))
+    return list(c.c), _take(buf)
+
+
+def natord(a: str, b: str) -> int:
+    return lib().orc_natord_compare(a.encode(), b.encode())
+
+
+def fmt_f32(v: float) -> str:
+    out = ctypes.create_string_buffer(48)
+    lib().orc_fmt_f32(v, out)
+    return out.value.decode()
+
+
+def maf_record_counts(text: bytes, cap: int):
+    arr = (OrcCounts * max(cap, 1))()
+    n = lib().orc_maf_record_counts(text, len(text), arr, cap)
+    if n < 0:
+        raise OracleError(-n, "maf_record_counts")
+    return [list(arr[i].c) for i in range(min(n, cap))]

@@ -1,0 +1,210 @@
+"""Pins the CPU oracle (oracle/wga_oracle.c) to the golden vectors the reference ships.
+
+Sources (all under /root/reference, copied as data fixtures into tests/golden/):
+  test/test.maf            -> tests/golden/ref_test.maf
+  test/testdotplot.paf     -> tests/golden/ref_testdotplot.paf
+  README.md:324-343        -> tests/golden/ref_readme_call_s_l0.vcf  (`wgatools call test/test.maf -s -l0`)
+The reference has no unit tests of its own; these are all the vectors that exist.
+"""
+import os
+import random
+
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import oracle_lib as orc
+import pyspec
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+TEST_MAF = open(os.path.join(G, "ref_test.maf"), "rb").read()
+TEST_PAF = open(os.path.join(G, "ref_testdotplot.paf"), "rb").read()
+README_VCF = open(os.path.join(G, "ref_readme_call_s_l0.vcf")).read().splitlines()
+
+CIGAR = "109=1D243=1X12=1X138=1X177=1X31=1X133=8I18=1X100=2X7=1X22="
+STAT_HDR = ("ref_name\tref_size\tref_start\tquery_name\tquery_size\tquery_start\taligned_size\tunaligned_size\t"
+            "identity\tsimilarity\tmatched\tmismatched\tins_event\tdel_event\tins_size\tdel_size\tinv_event\t"
+            "inv_size\tinv_ins_event\tinv_ins_size\tinv_del_event\tinv_del_size")
+
+
+def test_maf2paf_test_maf():
+    out = orc.maf2paf(TEST_MAF).decode()
+    assert out == ("query.chr8\t183119688\t181989421\t181990428\t+\tref.chr8\t182411202\t181469925\t181470925\t"
+                   "990\t1008\t255\tNM:i:18\tcg:Z:" + CIGAR + "\n")
+
+
+def test_stat_test_maf():
+    out = orc.stat_maf(TEST_MAF).decode().splitlines()
+    assert out[0] == STAT_HDR
+    assert out[1].split("\t") == ("ref.chr8 182411202 181469925 query.chr8 183119688 181989421 1000 182410202 "
+                                  "0.99 0.999 990 9 1 1 8 1 0 0.0 0 0 0 0").split()
+    assert len(out) == 2
+
+
+def test_stat_each_leaves_unaligned_zero():
+    row = orc.stat_maf(TEST_MAF, each=True).decode().splitlines()[1].split("\t")
+    assert row[7] == "0" and row[6] == "1000"
+
+
+def test_stat_paf_testdotplot():
+    out = orc.stat_paf(TEST_PAF).decode().splitlines()
+    assert out[0] == STAT_HDR
+    assert out[1].split("\t") == "B 300 0 A 300 0 250 50 0.84 0.84 210 0 2 2 30 30 1 50.0 1 10 1 10".split()
+
+
+def test_call_readme_vcf():
+    got = orc.call_maf(TEST_MAF, snp=True, svlen=0).decode().splitlines()
+    assert len(got) == len(README_VCF) == 19
+    for a, b in zip(got, README_VCF):
+        fa, fb = a.split("\t"), b.split("\t")
+        if a.startswith("#") or "SVTYPE" in a:
+            assert a == b  # header + INS/DEL rows byte-identical
+        else:
+            # SNP rows: README predates the GT:QI format for SNPs (caller.rs:582-593); cols 1-8 pinned
+            assert fa[:8] == fb[:8]
+            assert fa[8] == "GT:QI" and fa[9].startswith("1|1:query.chr8@") and fa[9].endswith("@P")
+
+
+def test_call_default_svlen50_emits_nothing_for_test_maf():
+    got = orc.call_maf(TEST_MAF).decode().splitlines()
+    assert len(got) == 8  # header only
+
+
+def test_natord():
+    names = ["chr10", "chr2", "chr1", "chrX", "chr01", "chr1a"]
+    import functools
+    s = sorted(names, key=functools.cmp_to_key(orc.natord))
+    assert s.index("chr1") < s.index("chr2") < s.index("chr10")
+    assert orc.natord("a 1", "a1") == 0  # whitespace skipped
+    assert orc.natord("x9", "x10") < 0 and orc.natord("x10", "x9") > 0
+    assert orc.natord("1.001", "1.002") < 0 and orc.natord("1.010", "1.02") < 0  # fractional (leading zero)
+
+
+def test_fmt_f32():
+    import numpy as np
+    assert orc.fmt_f32(0.99) == "0.99"
+    assert orc.fmt_f32(float(np.float32(990) / np.float32(1000))) == "0.99"
+    assert orc.fmt_f32(0.0) == "0.0" and orc.fmt_f32(50.0) == "50.0" and orc.fmt_f32(1.0) == "1.0"
+    assert orc.fmt_f32(float("nan")) == "NaN"
+    assert orc.fmt_f32(1.5e10) == "15000000000.0"
+    assert orc.fmt_f32(float(np.float32(1e-7))) == "1e-7"
+    assert orc.fmt_f32(float(np.float32(1.25e20))) == "1.25e20"
+    rng = random.Random(1)
+    for _ in range(2000):
+        a, b = rng.randrange(0, 10**6), rng.randrange(1, 10**6)
+        v = np.float32(a) / np.float32(b)
+        s = orc.fmt_f32(float(v))
+        assert np.float32(s) == v
+        ref = np.format_float_positional(v, unique=True, trim="0")
+        if 1e-5 <= float(v) < 1e13:
+            assert s == ref
+
+
+def test_paf_cigar_quirks():
+    assert orc.paf_cigar_counts(b"10M5X")[:2] == [10, 5]  # Q3: M counts as matched
+    assert orc.paf_cigar_counts(b"3I4D", neg=True) == [0, 0, 0, 0, 0, 0, 1, 3, 1, 4, 1]
+    for bad in (b"10S5M", b"5H", b"5N", b"3P"):
+        with pytest.raises(orc.OracleError) as e:
+            orc.paf_cigar_counts(bad)
+        assert e.value.code == 5  # Q4: ops outside M=XID are errors
+    with pytest.raises(orc.OracleError) as e:
+        orc.paf_cigar_counts(b"10MM")
+    assert e.value.code == 5 and "`MM`" in e.value.msg
+    with pytest.raises(orc.OracleError) as e:
+        orc.paf_cigar_counts(b"M")
+    assert e.value.code == 1  # empty length
+    with pytest.raises(orc.OracleError) as e:
+        orc.paf_cigar_counts(b"12")
+    assert e.value.code == 5 and "``" in e.value.msg  # digits without op
+    with pytest.raises(orc.OracleError) as e:
+        orc.paf_cigar_counts(b"99999999999999999999999M")
+    assert e.value.code == 1
+
+
+def _maf(blocks, header=b"##maf version=1\n"):
+    out = [header]
+    for lines in blocks:
+        out.append(b"a score=0\n")
+        for l in lines:
+            out.append(l + b"\n")
+        out.append(b"\n")
+    return b"".join(out)
+
+
+def test_maf_reader_quirks():
+    blk = [b"s t 0 4 + 100 ACGT", b"s q 0 4 + 100 ACGA"]
+    # Q9: the first line is always swallowed, even if it is an s-line
+    txt = b"s t 0 4 + 100 AAAA\n" + b"\n".join(blk) + b"\n"
+    assert orc.maf2paf(txt).count(b"\n") == 1
+    # non-'s' lines split blocks; 'a' line optional
+    txt = _maf([blk]) + b"\n".join(blk) + b"\ni something\n" + b"\n".join(blk)
+    assert orc.maf2paf(txt).count(b"\n") == 3
+    # Q10: 1-s-line block panics in maf2paf/stat, is skipped by call
+    one = _maf([[b"s t 0 4 + 100 ACGT"]])
+    with pytest.raises(orc.OracleError) as e:
+        orc.maf2paf(one)
+    assert e.value.code == 8
+    assert len(orc.call_maf(one).splitlines()) == 8
+    # surplus / missing fields, bad ints, bad strand
+    for bad, code in ((b"s t 0 4 + 100 ACGT X", 4), (b"s t 0 4 + 100", 3), (b"s t x 4 + 100 ACGT", 1),
+                      (b"s t 0 4 * 100 ACGT", 2), (b"s t 0 -4 + 100 ACGT", 1)):
+        with pytest.raises(orc.OracleError) as e:
+            orc.stat_maf(_maf([[bad, b"s q 0 4 + 100 ACGT"]]))
+        assert e.value.code == code, bad
+    # Q14 zip truncation, Q1 both-gap '=' , Q2 case-sensitive
+    txt = _maf([[b"s t 0 4 + 100 A-cGTTT", b"s q 0 4 + 100 A-CG"]])
+    assert orc.maf2paf(txt).split(b"cg:Z:")[1] == b"2=1X1=\n"
+    # '+' accepted by u64 parse; CRLF line ends
+    txt = b"#h\r\ns t +5 4 + 100 ACGT\r\ns q 0 4 - 100 ACGT\r\n"
+    row = orc.maf2paf(txt).split(b"\t")
+    assert row[7] == b"5" and row[2] == b"96" and row[3] == b"100" and row[4] == b"-"
+
+
+def test_query_name_selection():
+    txt = _maf([[b"s t 0 4 + 100 ACGT", b"s q1 0 4 + 100 ACGA", b"s q2 0 4 + 100 AC-T"]])
+    assert orc.maf2paf(txt, query_name="q2").startswith(b"q2\t")
+    assert orc.maf2paf(txt).startswith(b"q1\t")
+    with pytest.raises(orc.OracleError) as e:
+        orc.maf2paf(txt, query_name="zz")
+    assert e.value.code == 7
+    assert len(orc.call_maf(txt, query_name="zz").splitlines()) == 8  # call skips instead
+
+
+seqs = st.text(alphabet="ACGTacgtN-", min_size=1, max_size=80)
+
+
+@settings(max_examples=300, deadline=None)
+@given(seqs, seqs, st.booleans())
+def test_cigar_vs_pyspec(t, q, neg):
+    n = min(len(t), len(q))
+    c, cg = orc.maf_seq_to_cigar(t.encode()[:n], q.encode()[:n], neg)
+    c2, cg2 = pyspec.maf_seq_to_cigar(t[:n], q[:n], neg)
+    assert c == c2 and cg.decode() == cg2
+
+
+def test_call_chunk_quirks():
+    # (i) a gap run starting exactly at a chunk start is dropped; forced boundary inside '=' run
+    t = b"ACGTACGTAC" + b"GGGGGGGG" + b"ACGT"
+    q = b"ACGTACGTAC" + b"--------" + b"ACGT"
+    txt = _maf([[b"s t 0 22 + 100 " + t, b"s q 0 14 + 100 " + q]])
+    full = orc.call_maf(txt, svlen=3, chunk_size=1000).decode().splitlines()[8:]
+    assert len(full) == 1 and "SVTYPE=DEL;SVLEN=8" in full[0]
+    cut = orc.call_maf(txt, svlen=3, chunk_size=10).decode().splitlines()[8:]
+    assert cut == []  # window [0,10) ends at the run start -> next chunk starts on the gap: dropped
+    # (ii) one INV row per chunk for '-' strand with --inv
+    txt = _maf([[b"s t 0 22 + 100 " + t, b"s q 0 14 - 100 " + q]])
+    rows = orc.call_maf(txt, svlen=3, inv=True, chunk_size=1000).decode().splitlines()[8:]
+    assert sum("<INV>" in r for r in rows) == len(pyspec.chunk_grid(t.decode(), q.decode(), 1000, 3))
+    assert any("INV_NEST=TRUE;SVTYPE=DEL" in r and r.endswith("@N") for r in rows)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.text(alphabet="AC-", min_size=1, max_size=60), st.integers(1, 12), st.integers(0, 4), st.data())
+def test_chunk_grid_inv_rows(t, C, K, data):
+    q = data.draw(st.text(alphabet="AC-", min_size=len(t), max_size=len(t)))
+    nt = sum(ch != "-" for ch in t)
+    nq = sum(ch != "-" for ch in q)
+    txt = _maf([[f"s t 5 {nt} + 1000 {t}".encode(), f"s q 7 {nq} - 1000 {q}".encode()]])
+    rows = orc.call_maf(txt, svlen=K, inv=True, chunk_size=C).decode().splitlines()[8:]
+    grid = pyspec.chunk_grid(t, q, C, K)
+    want = sum(1 for (s, e) in grid if any(ch != "-" for ch in t[s:e]))
+    assert sum("<INV>" in r for r in rows) == want
