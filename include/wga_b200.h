@@ -1,0 +1,142 @@
+/*
+ * wga_b200.h -- C ABI of the B200-native hot path of wgatools (maf2paf / stat / call).
+ *
+ * The reference (wjwei-handsome/wgatools v1.1.0) has no FFI of its own; the path sits behind two
+ * Rust surfaces:
+ *   - trait AlignRecord            src/parser/common.rs:142-176 (get_stat, convert2paf, get_cigar_string)
+ *   - the L3 tool/converter fns    src/converter.rs:29-33 (maf2paf), src/tools/stat.rs:61-66,87-91
+ *                                  (stat_maf, stat_paf), src/tools/caller.rs:42-54 (call_var_maf)
+ * A per-record FFI call would serialise the GPU, so the boundary is batched at the level the L3
+ * functions work at: a slab of MAF/PAF text in, the command's output bytes (or stat partials) out.
+ * INTEGRATION.md shows the `extern "C"` block a maintainer adds to the Rust crate.
+ *
+ * Conventions
+ *   - every entry returns int: 0 = ok, otherwise a WGA_E_* code; never aborts or throws.
+ *     Codes 1..11 mirror WGAError variants (src/errors.rs:8-86); wga_last_error() returns the
+ *     reference's Display text for them.  First-error-wins with the LOWEST file position, i.e.
+ *     what the reference's sequential `-t 1` run reports.
+ *   - inputs are caller-owned and read-only for the duration of the call;
+ *     outputs are library-owned and valid until the next call on the same ctx.
+ *   - one ctx per (host thread, GPU); a ctx is not thread-safe; different ctxs may run concurrently.
+ *   - there is NO CPU fallback: without a CUDA device wga_ctx_create fails with WGA_E_CUDA.
+ *   - device-resident inputs (mem == WGA_MEM_DEVICE) must be 16-byte aligned and readable up to
+ *     the next multiple of 16 past `len` (true for any cudaMalloc'ed / torch buffer).
+ */
+#ifndef WGA_B200_H
+#define WGA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum wga_status {
+    WGA_OK = 0,
+    /* mirrors of WGAError (src/errors.rs) */
+    WGA_E_PARSE_INT = 1,            /* ParseIntError        errors.rs:50-52 */
+    WGA_E_PARSE_STRAND = 2,         /* ParseStrand          errors.rs:48-49 */
+    WGA_E_MAF_FIELD_MISSING = 3,    /* ParseMaf(FiledMissing) errors.rs:99-105 */
+    WGA_E_MAF_SURPLUS_FIELD = 4,    /* ParseMaf(SurplusField) */
+    WGA_E_CIGAR_OP_INVALID = 5,     /* CigarOpInvalid       errors.rs:58-59 */
+    WGA_E_CIGAR_TAG_NOT_FOUND = 6,  /* CigarTagNotFound     errors.rs:56-57 */
+    WGA_E_QUERY_NAME_NOT_FOUND = 7, /* QueryNameNotFound    errors.rs:80-81 */
+    WGA_E_REF_PANIC = 8,            /* input on which the reference panics (e.g. 1-s-line block in
+                                       stat/maf2paf: slines[1], maf.rs:426-453) */
+    WGA_E_CSV = 9,                  /* CsvDeserialize       errors.rs:20-21 */
+    WGA_E_VCF_BASE = 10,            /* noodles REF/ALT base outside ACGTNacgtn (caller.rs:379-382) */
+    WGA_E_NOM = 11,
+    /* library errors */
+    WGA_E_CUDA = 100,
+    WGA_E_INVALID_ARG = 101,
+    WGA_E_UNSUPPORTED = 102,
+    WGA_E_NOMEM = 103,
+    WGA_E_INTERNAL = 104
+};
+
+enum { WGA_MEM_HOST = 0, WGA_MEM_DEVICE = 1 };
+/* the slab starts at byte 0 of the file: its first line is the header MAFReader::new swallows
+ * unconditionally (src/parser/maf.rs:25-36).  Slabs of one file must be cut before a line that
+ * does not start with 's' (wga_maf_safe_cut) so that s-line groups are never split. */
+enum { WGA_F_FIRST_SLAB = 1u };
+
+typedef struct wga_ctx wga_ctx;
+
+typedef struct {
+    const void *data; /* same memory kind as the input text (pinned host or device) */
+    uint64_t len;
+} wga_span;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to enqueue all work on (e.g. torch's current stream), or NULL for a
+ * private stream.  Every entry point is synchronous at return. */
+int wga_ctx_create(int device, void *stream, wga_ctx **out);
+void wga_ctx_destroy(wga_ctx *ctx);
+/* Display text of the last error (WGAError wording for codes 1..11); *where = line index (MAF) or
+ * record index (PAF) it was raised at. */
+const char *wga_last_error(const wga_ctx *ctx, uint64_t *where);
+/* number of kernels this ctx launched since creation (hand-written kernels / CUB utility scans) */
+void wga_ctx_launch_counts(const wga_ctx *ctx, uint64_t *own_kernels, uint64_t *cub_calls);
+/* elapsed device milliseconds of the dense column-walk kernel(s) of the last command and the
+ * algorithmic bytes they covered (sum over launches) -- measured with CUDA events on the ctx stream */
+void wga_ctx_last_walk(const wga_ctx *ctx, float *ms, uint64_t *alg_bytes, uint32_t *launches);
+
+/* pinned host memory for callers that want full PCIe rate on the host-buffer entry points */
+void *wga_host_alloc(uint64_t bytes);
+void wga_host_free(void *p);
+/* offset of the last line in text[0..len) (other than the first) that does not start with 's':
+ * cutting a file there never splits an s-line group (maf.rs:395-413).  0 if there is none. */
+uint64_t wga_maf_safe_cut(const char *text, uint64_t len);
+
+/* ---- maf2paf: src/converter.rs:29-54 + MAFRecord::convert2paf src/parser/maf.rs:484-520 ------ */
+/* out = PAF rows (14 tab-separated fields, '\n'-terminated), one per MAF record, file order.
+ * query_name = Some(name) selects the query s-line by name (maf.rs:277-285), NULL = s-line 1. */
+int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags,
+                const char *query_name, wga_span *out);
+
+/* ---- stat: src/tools/stat.rs:61-126 ------------------------------------------------------------ */
+/* Host-side accumulator of PairStat partials; slabs (and ranks) are added in file order. */
+typedef struct wga_stat_acc wga_stat_acc;
+wga_stat_acc *wga_stat_acc_create(int each);
+void wga_stat_acc_destroy(wga_stat_acc *acc);
+/* stat_maf (stat.rs:61-84) over one slab: per-record counters on the GPU, pair reduction on the GPU,
+ * partial table merged into acc. */
+int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags,
+                 const char *query_name, wga_stat_acc *acc);
+/* stat_paf (stat.rs:87-105) over one slab of PAF text (whole lines). */
+int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags,
+                 wga_stat_acc *acc);
+/* write_style_result (stat.rs:107-126): TSV with header; text valid until the next write/destroy */
+int wga_stat_acc_write(wga_stat_acc *acc, wga_span *out);
+/* flat export/import for the cross-rank reduction (8(e)): keys = n_pairs records of
+ * "ref_name\0query_name\0" + {ref_size, query_size}; vals = n_pairs x 13 u64
+ * (11 counters of struct Cigar order + ref_start_min + query_start_min);
+ * inv = per '-'-strand-record (pair index, (aligned+query_aligned) numerator) in file order. */
+int wga_stat_acc_export(wga_stat_acc *acc, wga_span *blob);
+int wga_stat_acc_import(wga_stat_acc *acc, const void *blob, uint64_t len);
+uint64_t wga_stat_acc_npairs(const wga_stat_acc *acc);
+
+/* ---- call: src/tools/caller.rs:42-157, 159-265, 388-608 ------------------------------------- */
+typedef struct {
+    int32_t snp;           /* -s/--snp   (cli.rs:146-147) */
+    int32_t inv;           /* -i/--inv   (cli.rs:149-150) */
+    uint64_t svlen_cutoff; /* -l/--svlen, default 50 (cli.rs:152-153) */
+    uint64_t chunk_size;   /* -c/--chunk-size, default 1000000 (cli.rs:171-173); 0 is rejected */
+    const char *query_name; /* --query-name or NULL (query regex is not supported: WGA_E_UNSUPPORTED) */
+} wga_call_opts;
+/* VCF header text for `sample` (caller.rs:304-337; no <maf>.index => no ##contig lines) */
+int wga_vcf_header(wga_ctx *ctx, const char *sample, wga_span *out);
+/* VCF body rows of one slab, file order */
+int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags,
+                 const wga_call_opts *opts, wga_span *out);
+
+/* ---- AlignRecord-level batch access (common.rs:142-176 get_stat / get_cigar_string) --------- */
+/* per-record counters of the last wga_maf2paf / wga_maf_stat / wga_paf_stat call, struct Cigar order
+ * (cigar.rs:16-29): match, mismatch, ins_event, ins, del_event, del, inv_ins_event, inv_ins,
+ * inv_del_event, inv_del, inv_event.  Copies n_records x 11 u64 into dst (host). */
+int wga_last_record_counts(wga_ctx *ctx, uint64_t *dst, uint64_t cap_records, uint64_t *n_records);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,231 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the host mirror) against the CPU oracle on the same
+inputs -- byte-identical PAF / TSV, identical integers.  Run on the B200 box: pytest -m gpu."""
+import ctypes
+import io
+import os
+import random
+
+import numpy as np
+import pytest
+
+import bench_support as bs
+import oracle_lib as orc
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+TEST_MAF = open(os.path.join(G, "ref_test.maf"), "rb").read()
+
+
+@pytest.fixture(scope="module")
+def w():
+    import __graft_entry__ as g
+    g.build()
+    import wgatools_b200 as w
+    return w
+
+
+@pytest.fixture(scope="module")
+def ctx(w):
+    return w.Context(0)
+
+
+def paf(w, ctx, text, qn=None):
+    return w.run_bytes(w.maf2paf, w.MAFReader(text), qn, ctx=ctx)
+
+
+def stat(w, ctx, text, each=False, qn=None):
+    return w.run_bytes(w.stat_maf, w.MAFReader(text), each, qn, ctx=ctx)
+
+
+def check_both(w, ctx, text, qn=None):
+    assert paf(w, ctx, text, qn) == orc.maf2paf(text, qn)
+    assert stat(w, ctx, text, False, qn) == orc.stat_maf(text, False, qn)
+    assert stat(w, ctx, text, True, qn) == orc.stat_maf(text, True, qn)
+
+
+def test_golden_test_maf(w, ctx):
+    out = paf(w, ctx, TEST_MAF).decode()
+    assert out.endswith("cg:Z:109=1D243=1X12=1X138=1X177=1X31=1X133=8I18=1X100=2X7=1X22=\n")
+    check_both(w, ctx, TEST_MAF)
+    c = ctx.last_record_counts()
+    assert c.tolist() == [[990, 9, 1, 8, 1, 1, 0, 0, 0, 0, 0]]
+
+
+def _maf(blocks, header=b"##maf version=1\n"):
+    out = [header]
+    for lines in blocks:
+        out.append(b"a score=0\n")
+        out += [l + b"\n" for l in lines]
+        out.append(b"\n")
+    return b"".join(out)
+
+
+def test_empty_and_header_only(w, ctx):
+    for t in (b"", b"##maf\n", b"##maf", b"\n\n\n", b"##maf\na score=0\n\n"):
+        assert paf(w, ctx, t) == orc.maf2paf(t) == b""
+        assert stat(w, ctx, t) == orc.stat_maf(t) == b""
+
+
+def test_reader_quirks(w, ctx):
+    blk = [b"s t 0 4 + 100 ACGT", b"s q 0 4 + 100 ACGA"]
+    cases = [
+        b"s t 0 4 + 100 AAAA\n" + b"\n".join(blk) + b"\n",                       # Q9 first line swallowed
+        _maf([blk]) + b"\n".join(blk) + b"\ni something\n" + b"\n".join(blk),     # no trailing newline
+        _maf([[b"s t 0 4 + 100 A-cGTTT", b"s q 0 4 + 100 A-CG"]]),                # Q14 zip, Q1, Q2
+        b"#h\r\ns t +5 4 + 100 ACGT\r\ns q 0 4 - 100 ACGT\r\n",                   # '+' ints, CRLF, '-' strand
+        _maf([[b"s\tt.x\t0\t4\t+\t100\tACGT", b"s  q\"y   0 4 + 100 AC-T  "]]),   # tabs, runs of blanks, quote
+        _maf([[b"s t 0 4 + 100 ACGT", b"s q 0 4 + 100 ACGT", b"s r 0 4 + 100 AAAA"]]),
+        _maf([[b"s t 0 2 + 100 ----AC", b"s q 0 4 + 100 GGTTAC"]]),               # leading insertion
+        _maf([[b"s t 0 6 + 100 ACGTAC", b"s q 0 2 + 100 AC----"]]),               # trailing deletion
+        _maf([[b"s t 0 1 + 100 A", b"s q 0 1 + 100 C"]]),
+        _maf([[b"s t 0 0 + 100 -", b"s q 0 0 + 100 -"]]),
+    ]
+    for t in cases:
+        check_both(w, ctx, t)
+
+
+def test_errors_match_oracle(w, ctx):
+    bad = [
+        (_maf([[b"s t 0 4 + 100 ACGT X", b"s q 0 4 + 100 ACGT"]]), 4),
+        (_maf([[b"s t 0 4 + 100", b"s q 0 4 + 100 ACGT"]]), 3),
+        (_maf([[b"s t x 4 + 100 ACGT", b"s q 0 4 + 100 ACGT"]]), 1),
+        (_maf([[b"s t 0 4 * 100 ACGT", b"s q 0 4 + 100 ACGT"]]), 2),
+        (_maf([[b"s t 0 -4 + 100 ACGT", b"s q 0 4 + 100 ACGT"]]), 1),
+        (_maf([[b"s t 0 4 + 99999999999999999999999 ACGT", b"s q 0 4 + 100 ACGT"]]), 1),
+        (_maf([[b"s t 0 4 + 100 ACGT"]]), 8),
+        (_maf([[b"s", b"s q 0 4 + 100 ACGT"]]), 3),
+        # the first error in file order wins: bad int in block 2 precedes the 1-s-line block 3
+        (_maf([[b"s t 0 4 + 100 ACGT", b"s q 0 4 + 100 ACGT"], [b"s t 0 4 + 100 ACGT", b"s q zz 4 + 100 ACGT"],
+               [b"s t 0 4 + 100 ACGT"]]), 1),
+        (_maf([[b"s t 0 4 + 100 ACGT"], [b"s t 0 4 + 100 ACGT", b"s q zz 4 + 100 ACGT"]]), 8),
+    ]
+    for text, code in bad:
+        for fn_o, fn_g in ((orc.maf2paf, lambda t: paf(w, ctx, t)), (orc.stat_maf, lambda t: stat(w, ctx, t))):
+            with pytest.raises(orc.OracleError) as eo:
+                fn_o(text)
+            with pytest.raises(w.WGAError) as eg:
+                fn_g(text)
+            assert eo.value.code == code == eg.value.code, text
+            if code != 8:
+                assert str(eg.value) == eo.value.msg, text
+    # after an error the context keeps working
+    check_both(w, ctx, TEST_MAF)
+
+
+def test_query_name(w, ctx):
+    t = _maf([[b"s t 0 4 + 100 ACGT", b"s q1 0 4 + 100 ACGA", b"s q2 0 4 - 100 AC-T"],
+              [b"s t 9 4 + 100 ACGT", b"s q2 0 4 + 100 ACGA", b"s q1 0 4 + 100 AC-T"]])
+    for qn in (None, "q1", "q2", "t"):
+        check_both(w, ctx, t, qn)
+    with pytest.raises(w.WGAError) as e:
+        paf(w, ctx, t, "zz")
+    assert e.value.code == 7 and str(e.value) == "Query name:zz not found in MAF"
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (1, {}), (2, dict(p_bothgap=2e-3, p_lower=0.3)), (3, dict(p_neg=0.5, p_gap=5e-3, gap_mean=6.0)),
+    (4, dict(len_median=60000.0, len_sigma=1.2, len_max=400000, p_sv=2e-4, sv_min=50, sv_max=40000)),
+    (5, dict(p_mis=0.2, p_gap=0.05)), (6, dict(len_median=80.0, len_min=1, len_sigma=1.5)),
+])
+def test_synthetic_parity(w, ctx, seed, kw):
+    n = 400 if kw.get("len_median", 2000.0) < 10000 else 60
+    text = bs.gen_maf(bs.maf_params(n, seed=seed, **kw))
+    check_both(w, ctx, text)
+    cnt = ctx.last_record_counts()
+    assert cnt.tolist() == orc.maf_record_counts(text, len(cnt) + 5)
+
+
+def test_random_small_blocks(w, ctx):
+    rng = random.Random(11)
+    alpha = "ACGTacgtN-"
+    for it in range(40):
+        blocks = []
+        for b in range(rng.randrange(1, 30)):
+            L = rng.choice([1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 511, 512, 513, 1000])
+            mode = rng.random()
+            t = "".join(rng.choice(alpha if mode < 0.5 else "AC-") for _ in range(L))
+            q = "".join((tc if rng.random() < 0.7 else rng.choice(alpha)) for tc in t)
+            if rng.random() < 0.2:
+                q = q[:rng.randrange(1, L + 1)]
+            st = rng.choice("+-")
+            blocks.append([f"s tgt{b % 3} {rng.randrange(1000)} {sum(c != '-' for c in t)} + 5000 {t}".encode(),
+                           f"s qry{b % 2} {rng.randrange(1000)} {sum(c != '-' for c in q)} {st} 7000 {q}".encode()])
+        check_both(w, ctx, _maf(blocks))
+
+
+def test_alignment_offsets(w, ctx):
+    # every (target, query) start misalignment modulo 16, runs crossing 16-byte and 512-byte boundaries
+    rng = random.Random(5)
+    for pad_t in range(0, 16):
+        for pad_q in (0, 1, 3, 4, 7, 8, 13, 15):
+            L = rng.choice([5, 40, 530, 1100])
+            t = "".join(rng.choice("ACGT-") for _ in range(L))
+            q = "".join((c if rng.random() < 0.8 else rng.choice("ACGT-")) for c in t)
+            text = _maf([[("s " + "t" * (1 + pad_t) + f" 1 1 + 99 {t}").encode(),
+                          ("s " + "q" * (1 + pad_q) + f" 1 1 + 99 {q}").encode()]])
+            assert paf(w, ctx, text) == orc.maf2paf(text), (pad_t, pad_q, L)
+
+
+def test_long_record_multi_item(w, ctx):
+    # records longer than one work item (16384 columns), runs spanning item boundaries
+    rng = random.Random(9)
+    L = 16384 * 3 + 777
+    t = bytearray(rng.choice(b"ACGT") for _ in range(L))
+    q = bytearray(t)
+    for lo, hi, kind in ((16380, 16390, "D"), (32768 - 3, 32768 + 40, "I"), (16384 * 3 - 1, 16384 * 3 + 1, "X"),
+                         (100, 101, "X"), (16384, 16385, "D")):
+        for i in range(lo, hi):
+            if kind == "D": q[i] = ord("-")
+            elif kind == "I": t[i] = ord("-")
+            else: q[i] = ord("A") if t[i] != ord("A") else ord("C")
+    text = _maf([[b"s t 0 1 + 9 " + bytes(t), b"s q 0 1 - 9 " + bytes(q)],
+                 [b"s t 0 1 + 9 " + bytes(t[:16384]), b"s q 0 1 + 9 " + bytes(q[:16384])],
+                 [b"s t 0 1 + 9 " + bytes(t[:16385]), b"s q 0 1 + 9 " + bytes(q[:16385])]])
+    check_both(w, ctx, text)
+
+
+def _dev_bytes(ptr, n):
+    import torch
+
+    class Raw:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+    return torch.as_tensor(Raw(), device="cuda").cpu().numpy().tobytes() if n else b""
+
+
+def test_device_resident_input(w, ctx):
+    import torch
+    text = bs.gen_maf(bs.maf_params(500, seed=21))
+    d = torch.zeros(len(text) + 64, dtype=torch.uint8, device="cuda")
+    d[:len(text)].copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    ptr, n = ctx.maf2paf_raw(ctypes.c_void_p(d.data_ptr()), len(text), 1, 1)
+    assert _dev_bytes(ptr, n) == orc.maf2paf(text)
+    acc = w.StatAcc(False)
+    ctx.maf_stat_raw(ctypes.c_void_p(d.data_ptr()), len(text), 1, 1, acc)
+    assert acc.write() == orc.stat_maf(text)
+
+
+def test_multi_slab_matches_single(w, ctx):
+    text = bs.gen_maf(bs.maf_params(800, seed=33, p_neg=0.3))
+    old = w.api.SLAB_BYTES
+    try:
+        w.api.SLAB_BYTES = 200_000
+        check_both(w, ctx, text)
+    finally:
+        w.api.SLAB_BYTES = old
+
+
+def test_stat_export_import_roundtrip(w, ctx):
+    text = bs.gen_maf(bs.maf_params(600, seed=44, p_neg=0.4))
+    L = ctx.L
+    cut = L.wga_maf_safe_cut(text, len(text) // 2)
+    assert 0 < cut < len(text)
+    a, b = w.StatAcc(False), w.StatAcc(False)
+    ka, pa = w.api._host_ptr(text)
+    ctx.maf_stat_raw(ctypes.c_void_p(pa), cut, 0, 1, a)
+    ctx.maf_stat_raw(ctypes.c_void_p(pa + cut), len(text) - cut, 0, 0, b)
+    m = w.StatAcc(False)
+    m.import_(a.export())
+    m.import_(b.export())
+    assert m.write() == orc.stat_maf(text)

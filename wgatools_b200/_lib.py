@@ -1,0 +1,71 @@
+"""Loads the in-tree CUDA library (wgatools_b200/libwga_b200.so) and declares the C ABI of include/wga_b200.h.
+
+There is no CPU fallback: if the library is missing this module raises, and if no CUDA device is present
+wga_ctx_create fails with WGA_E_CUDA.
+"""
+import ctypes
+import os
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_DIR, "libwga_b200.so")
+
+WGA_MEM_HOST, WGA_MEM_DEVICE = 0, 1
+WGA_F_FIRST_SLAB = 1
+
+
+class Span(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("len", ctypes.c_uint64)]
+
+
+class CallOpts(ctypes.Structure):
+    _fields_ = [("snp", ctypes.c_int32), ("inv", ctypes.c_int32), ("svlen_cutoff", ctypes.c_uint64),
+                ("chunk_size", ctypes.c_uint64), ("query_name", ctypes.c_char_p)]
+
+
+# every symbol include/wga_b200.h declares: name -> (restype, argtypes)
+_P = ctypes.POINTER
+ABI = {
+    "wga_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _P(ctypes.c_void_p)]),
+    "wga_ctx_destroy": (None, [ctypes.c_void_p]),
+    "wga_last_error": (ctypes.c_char_p, [ctypes.c_void_p, _P(ctypes.c_uint64)]),
+    "wga_ctx_launch_counts": (None, [ctypes.c_void_p, _P(ctypes.c_uint64), _P(ctypes.c_uint64)]),
+    "wga_ctx_last_walk": (None, [ctypes.c_void_p, _P(ctypes.c_float), _P(ctypes.c_uint64), _P(ctypes.c_uint32)]),
+    "wga_host_alloc": (ctypes.c_void_p, [ctypes.c_uint64]),
+    "wga_host_free": (None, [ctypes.c_void_p]),
+    "wga_maf_safe_cut": (ctypes.c_uint64, [ctypes.c_void_p, ctypes.c_uint64]),
+    "wga_maf2paf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
+                                  ctypes.c_char_p, _P(Span)]),
+    "wga_stat_acc_create": (ctypes.c_void_p, [ctypes.c_int]),
+    "wga_stat_acc_destroy": (None, [ctypes.c_void_p]),
+    "wga_maf_stat": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
+                                   ctypes.c_char_p, ctypes.c_void_p]),
+    "wga_paf_stat": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
+                                   ctypes.c_void_p]),
+    "wga_stat_acc_write": (ctypes.c_int, [ctypes.c_void_p, _P(Span)]),
+    "wga_stat_acc_export": (ctypes.c_int, [ctypes.c_void_p, _P(Span)]),
+    "wga_stat_acc_import": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]),
+    "wga_stat_acc_npairs": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "wga_vcf_header": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _P(Span)]),
+    "wga_maf_call": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
+                                   _P(CallOpts), _P(Span)]),
+    "wga_last_record_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, _P(ctypes.c_uint64)]),
+}
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library; raises (loudly) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). wgatools_b200 has no CPU fallback.")
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

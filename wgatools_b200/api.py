@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as the Rust functions they stand in for:
+  maf2paf(mafreader, writer, query_name)          src/converter.rs:29-33
+  stat_maf(reader, writer, each, query_name)      src/tools/stat.rs:61-66
+  stat_paf(reader, writer, each)                  src/tools/stat.rs:87-91
+  call_var_maf(mafreader, mafindex, writer, ...)  src/tools/caller.rs:42-54
+Errors surface as WGAError whose str() is the reference's `impl Display for WGAError` text
+(src/errors.rs:8-86) and whose .code is the C-ABI status.  All compute happens in the CUDA library
+behind include/wga_b200.h; nothing here touches sequence bytes.
+"""
+import ctypes
+import io
+import os
+
+from . import _lib
+from ._lib import WGA_F_FIRST_SLAB, WGA_MEM_DEVICE, WGA_MEM_HOST, CallOpts, Span
+
+SLAB_BYTES = 1 << 30  # host inputs larger than this are cut into slabs at s-line-group boundaries
+
+
+class WGAError(Exception):
+    """src/errors.rs:8-86"""
+
+    def __init__(self, code, msg, where=0):
+        super().__init__(msg)
+        self.code = code
+        self.where = where
+
+
+class Context:
+    """One per (host thread, GPU).  stream: an int cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.L.wga_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(h))
+        if rc != 0:
+            raise WGAError(rc, "wga_ctx_create failed (no CUDA device? wgatools_b200 has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wga_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            where = ctypes.c_uint64()
+            msg = self.L.wga_last_error(self.h, ctypes.byref(where))
+            raise WGAError(rc, (msg or b"").decode("utf-8", "replace"), where.value)
+
+    def launch_counts(self):
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self.L.wga_ctx_launch_counts(self.h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def last_walk(self):
+        ms, by, n = ctypes.c_float(), ctypes.c_uint64(), ctypes.c_uint32()
+        self.L.wga_ctx_last_walk(self.h, ctypes.byref(ms), ctypes.byref(by), ctypes.byref(n))
+        return ms.value, by.value, n.value
+
+    # ---- raw entry points (ptr = host address or device address) -------------------------------
+    def maf2paf_raw(self, ptr, n, mem, flags, query_name=None):
+        sp = Span()
+        self._check(self.L.wga_maf2paf(self.h, ptr, n, mem, flags, _opt(query_name), ctypes.byref(sp)))
+        return sp.data, sp.len
+
+    def maf_stat_raw(self, ptr, n, mem, flags, acc, query_name=None):
+        self._check(self.L.wga_maf_stat(self.h, ptr, n, mem, flags, _opt(query_name), acc.h))
+
+    def paf_stat_raw(self, ptr, n, mem, flags, acc):
+        self._check(self.L.wga_paf_stat(self.h, ptr, n, mem, flags, acc.h))
+
+    def maf_call_raw(self, ptr, n, mem, flags, opts):
+        sp = Span()
+        self._check(self.L.wga_maf_call(self.h, ptr, n, mem, flags, ctypes.byref(opts), ctypes.byref(sp)))
+        return sp.data, sp.len
+
+    def vcf_header(self, sample="sample"):
+        sp = Span()
+        self._check(self.L.wga_vcf_header(self.h, _opt(sample), ctypes.byref(sp)))
+        return ctypes.string_at(sp.data, sp.len)
+
+    def last_record_counts(self):
+        n = ctypes.c_uint64()
+        self._check(self.L.wga_last_record_counts(self.h, None, 0, ctypes.byref(n)))
+        import numpy as np
+        out = np.zeros((n.value, 11), dtype=np.uint64)
+        if n.value:
+            self._check(self.L.wga_last_record_counts(self.h, out.ctypes.data, n.value, ctypes.byref(n)))
+        return out
+
+
+class StatAcc:
+    def __init__(self, each=False):
+        self.L = _lib.load()
+        self.h = ctypes.c_void_p(self.L.wga_stat_acc_create(int(bool(each))))
+
+    def write(self) -> bytes:
+        sp = Span()
+        rc = self.L.wga_stat_acc_write(self.h, ctypes.byref(sp))
+        if rc:
+            raise WGAError(rc, "wga_stat_acc_write failed")
+        return ctypes.string_at(sp.data, sp.len) if sp.len else b""
+
+    def export(self) -> bytes:
+        sp = Span()
+        rc = self.L.wga_stat_acc_export(self.h, ctypes.byref(sp))
+        if rc:
+            raise WGAError(rc, "wga_stat_acc_export failed")
+        return ctypes.string_at(sp.data, sp.len)
+
+    def import_(self, blob: bytes):
+        rc = self.L.wga_stat_acc_import(self.h, blob, len(blob))
+        if rc:
+            raise WGAError(rc, "wga_stat_acc_import failed")
+
+    def npairs(self):
+        return self.L.wga_stat_acc_npairs(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.wga_stat_acc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _opt(s):
+    return None if s is None else (s if isinstance(s, bytes) else str(s).encode())
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _read_all(src) -> bytes:
+    if isinstance(src, (bytes, bytearray, memoryview)):
+        return bytes(src)
+    if isinstance(src, (str, os.PathLike)):
+        with open(src, "rb") as f:
+            return f.read()
+    return src.read()
+
+
+class MAFReader:
+    """src/parser/maf.rs:15-44.  new() consumes the first line as the header (maf.rs:25-36)."""
+
+    def __init__(self, reader):
+        self.data = _read_all(reader)
+        nl = self.data.find(b"\n")
+        self.header = (self.data if nl < 0 else self.data[:nl + 1]).decode("utf-8", "replace")
+
+    @classmethod
+    def from_path(cls, path):
+        if not os.path.exists(path):
+            raise WGAError(-1, f"File path `{path}` not exist")
+        return cls(path)
+
+
+class PAFReader:
+    """src/parser/paf.rs:13-46"""
+
+    def __init__(self, reader):
+        self.data = _read_all(reader)
+
+
+def _slabs(data: bytes, L):
+    """yield (offset, length, flags): slabs cut right before a line that is not an s-line"""
+    n = len(data)
+    if n <= SLAB_BYTES:
+        yield 0, n, WGA_F_FIRST_SLAB
+        return
+    buf = ctypes.c_char_p(data)
+    base = ctypes.cast(buf, ctypes.c_void_p).value
+    off = 0
+    first = True
+    while off < n:
+        want = min(SLAB_BYTES, n - off)
+        cut = want
+        if off + want < n:
+            cut = L.wga_maf_safe_cut(ctypes.c_void_p(base + off), want)
+            if cut == 0:  # an s-line group larger than a slab: take the remainder in one piece
+                cut = n - off
+        yield off, cut, (WGA_F_FIRST_SLAB if first else 0)
+        first = False
+        off += cut
+
+
+def _host_ptr(data: bytes):
+    buf = ctypes.c_char_p(data)
+    return buf, ctypes.cast(buf, ctypes.c_void_p).value
+
+
+def maf2paf(mafreader: MAFReader, writer, query_name=None, ctx=None):
+    """src/converter.rs:29-54: every MAF record -> one PAF row (file order, i.e. the `-t 1` order)."""
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(mafreader.data)
+    for off, n, flags in _slabs(mafreader.data, ctx.L):
+        ptr, ln = ctx.maf2paf_raw(ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags, query_name)
+        if ln:
+            writer.write(ctypes.string_at(ptr, ln))
+
+
+def stat_maf(reader: MAFReader, writer, each=False, query_name=None, ctx=None):
+    """src/tools/stat.rs:61-84"""
+    ctx = ctx or default_context()
+    acc = StatAcc(each)
+    keep, base = _host_ptr(reader.data)
+    for off, n, flags in _slabs(reader.data, ctx.L):
+        ctx.maf_stat_raw(ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags, acc, query_name)
+    writer.write(acc.write())
+
+
+def stat_paf(reader: PAFReader, writer, each=False, ctx=None):
+    """src/tools/stat.rs:87-105"""
+    ctx = ctx or default_context()
+    acc = StatAcc(each)
+    keep, base = _host_ptr(reader.data)
+    ctx.paf_stat_raw(ctypes.c_void_p(base), len(reader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, acc)
+    writer.write(acc.write())
+
+
+def call_var_maf(mafreader: MAFReader, mafindex, writer, if_snp=False, if_inv=False, svlen_cutoff=50,
+                 _between=False, sample=None, query_name=None, query_regex=None, chunk_size=None, ctx=None):
+    """src/tools/caller.rs:42-157.  mafindex (contig lines) and query_regex are not supported."""
+    ctx = ctx or default_context()
+    if mafindex is not None or query_regex is not None:
+        raise WGAError(102, "mafindex / query_regex are outside the accelerated path")
+    writer.write(ctx.vcf_header(sample or "sample"))
+    opts = CallOpts(snp=int(bool(if_snp)), inv=int(bool(if_inv)), svlen_cutoff=int(svlen_cutoff),
+                    chunk_size=int(1000000 if chunk_size is None else chunk_size), query_name=_opt(query_name))
+    keep, base = _host_ptr(mafreader.data)
+    for off, n, flags in _slabs(mafreader.data, ctx.L):
+        ptr, ln = ctx.maf_call_raw(ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags, opts)
+        if ln:
+            writer.write(ctypes.string_at(ptr, ln))
+
+
+def run_bytes(fn, *args, **kw) -> bytes:
+    """convenience: run one of the functions above into a bytes object"""
+    w = io.BytesIO()
+    fn(*args[:1], w, *args[1:], **kw)
+    return w.getvalue()

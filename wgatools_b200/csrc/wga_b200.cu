@@ -1,0 +1,716 @@
+// wga_b200.cu -- C ABI entry points (include/wga_b200.h) and host orchestration of the kernels.
+#include <algorithm>
+#include <numeric>
+
+#include "ctx.cuh"
+#include "emit_paf.cuh"
+#include "stat.cuh"
+#include "stat_acc.hpp"
+#include "tokenize.cuh"
+#include "walk.cuh"
+#ifdef WGA_WITH_CALL
+#include "call.cuh"
+#endif
+#ifdef WGA_WITH_PAF
+#include "paf.cuh"
+#endif
+
+using namespace wga;
+
+namespace {
+
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                          \
+    do {                                                               \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->n_own++;                                                \
+    } while (0)
+
+int sync_check(wga_ctx *ctx) {
+    WGA_CK(cudaStreamSynchronize(ctx->stream));
+    WGA_CK(cudaGetLastError());
+    return WGA_OK;
+}
+
+// copy `count` u64 scalars device -> pinned host and wait
+int read_scalars(wga_ctx *ctx, std::initializer_list<const void *> srcs, uint64_t *dst) {
+    int i = 0;
+    for (const void *s : srcs) {
+        WGA_CK(cudaMemcpyAsync(ctx->h_scal + i, s, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ++i;
+    }
+    WGA_TRY(sync_check(ctx));
+    for (int k = 0; k < i; ++k) dst[k] = ctx->h_scal[k];
+    return WGA_OK;
+}
+
+// host restatement of parse_sline's error wording (src/parser/maf.rs:138-211, src/errors.rs)
+std::string sline_error_text(const std::string &line, int code) {
+    static const char *fname[7] = {"mode", "name", "start", "align_size", "strand", "size", "seq"};
+    std::vector<std::string> f;
+    size_t i = 0;
+    while (i < line.size()) {
+        while (i < line.size() && nat_ws(line[i])) ++i;
+        if (i >= line.size()) break;
+        size_t b = i;
+        while (i < line.size() && !nat_ws(line[i])) ++i;
+        f.push_back(line.substr(b, i - b));
+    }
+    auto bad_int = [](const std::string &s) {
+        uint64_t v;
+        return !parse_u64_bytes((const unsigned char *)s.data(), s.size(), &v);
+    };
+    for (int k = 0; k < 7; ++k) {
+        if ((size_t)k >= f.size()) return std::string("Parse MAF error by: S-line Filed `") + fname[k] + "` Missing";
+        if ((k == 2 || k == 3 || k == 5) && bad_int(f[k])) return "Parse `" + f[k] + "` Into Integer Error";
+        if (k == 4 && f[k] != "+" && f[k] != "-") return "Parse Strand `" + f[k] + "` Error";
+    }
+    if (f.size() > 7) return "Parse MAF error by: Surplus Filed > 7";
+    return "MAF parse error code " + std::to_string(code);
+}
+
+__global__ void k_line_bounds(LineView lv, uint64_t k, uint64_t *out) {
+    out[0] = lv.start(k);
+    out[1] = lv.end(k);
+}
+
+__global__ void k_init_u64(unsigned long long *p, uint64_t n, unsigned long long v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_pt_init(unsigned long long *vals, uint64_t cap) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap * kPairVals) return;
+    vals[i] = (i % kPairVals) >= 11 ? ~0ull : 0ull;
+}
+__global__ void k_iota(uint64_t *p, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+__global__ void k_each_name_len(uint64_t n_rec, const uint32_t *tl, const uint32_t *ql, uint32_t *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n_rec) { if (i == 2 * n_rec) out[i] = 0; return; }
+    out[i] = (i & 1) ? ql[i >> 1] : tl[i >> 1];
+}
+
+struct Prep {
+    LineView lv;
+    SLines sl;
+    Recs rc;
+    uint64_t *item_base = nullptr;
+    uint32_t *item_rec = nullptr, *item_seg = nullptr;
+    unsigned long long *err_key = nullptr;
+    uint64_t total_cols = 0;
+};
+
+// stage the slab on the device (host input) or adopt the device pointer
+int stage_text(wga_ctx *ctx, const void *text, uint64_t len, int mem) {
+    ctx->last_counts_valid = false;
+    ctx->text_len = len;
+    ctx->h_text = nullptr;
+    if (mem == WGA_MEM_DEVICE) {
+        if (reinterpret_cast<uintptr_t>(text) & 15u) {
+            ctx->set_error(WGA_E_INVALID_ARG, 0, "device text must be 16-byte aligned");
+            return WGA_E_INVALID_ARG;
+        }
+        ctx->d_text = (const uint8_t *)text;
+        return WGA_OK;
+    }
+    if (mem != WGA_MEM_HOST) {
+        ctx->set_error(WGA_E_INVALID_ARG, 0, "mem must be WGA_MEM_HOST or WGA_MEM_DEVICE");
+        return WGA_E_INVALID_ARG;
+    }
+    uint8_t *d = (uint8_t *)ctx->ensure(B_TEXT, len + 64);
+    if (!d) return ctx->err_code;
+    if (len) WGA_CK(cudaMemcpyAsync(d, text, len, cudaMemcpyHostToDevice, ctx->stream));
+    WGA_CK(cudaMemsetAsync(d + len, 0, 64, ctx->stream));
+    ctx->d_text = d;
+    ctx->h_text = (const char *)text;
+    return WGA_OK;
+}
+
+int fetch_line(wga_ctx *ctx, const LineView &lv, uint64_t k, std::string *line) {
+    uint64_t *d = ctx->buf<uint64_t>(B_SCALARS, 8);
+    if (!d) return ctx->err_code;
+    LAUNCH(ctx, k_line_bounds, 1, 1, lv, k, d);
+    uint64_t se[2];
+    WGA_TRY(read_scalars(ctx, {d, d + 1}, se));
+    uint64_t n = std::min<uint64_t>(se[1] - se[0], 1u << 16);
+    line->resize(n);
+    if (n) WGA_CK(cudaMemcpy(&(*line)[0], lv.text + se[0], n, cudaMemcpyDeviceToHost));
+    while (!line->empty() && line->back() == '\r') line->pop_back();
+    return WGA_OK;
+}
+
+// turn the device error key into code + reference wording
+int resolve_error(wga_ctx *ctx, const Prep &P, uint64_t key, const char *qname) {
+    int code = (int)(key & 0xFF);
+    uint64_t where = key >> 8;
+    std::string msg;
+    switch (code) {
+        case WGA_E_PARSE_INT: case WGA_E_PARSE_STRAND: case WGA_E_MAF_FIELD_MISSING: case WGA_E_MAF_SURPLUS_FIELD: {
+            std::string line;
+            if (fetch_line(ctx, P.lv, where, &line) == WGA_OK) msg = sline_error_text(line, code);
+            break;
+        }
+        case WGA_E_QUERY_NAME_NOT_FOUND:
+            msg = std::string("Query name:") + (qname ? qname : "") + " not found in MAF";
+            break;
+        case WGA_E_REF_PANIC:
+            msg = "the reference panics on this block (s-line index out of range: a block needs a target and a query s-line)";
+            break;
+        default: msg = "internal error (pair-key collision or inconsistent index)"; break;
+    }
+    ctx->set_error(code, where, msg);
+    return code;
+}
+
+// tokenise the slab: whitespace index -> lines -> s-lines -> records -> work items
+int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep *P) {
+    const uint64_t len = ctx->text_len;
+    const uint8_t *text = ctx->d_text;
+    ctx->n_rec = ctx->n_items = ctx->n_runs = 0;
+    P->err_key = ctx->buf<unsigned long long>(B_ERR, 1);
+    if (!P->err_key) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, P->err_key, 1, kNoErr);
+    if (len == 0) return WGA_OK;
+
+    // 1. whitespace index
+    const uint64_t n_tiles = (len + kWsTile - 1) / kWsTile;
+    uint64_t *tile_ws = ctx->buf<uint64_t>(B_TILE_WS, n_tiles + 1), *tile_nl = ctx->buf<uint64_t>(B_TILE_NL, n_tiles + 1);
+    uint64_t *ws_off = ctx->buf<uint64_t>(B_TILE_WS_OFF, n_tiles + 1), *nl_off = ctx->buf<uint64_t>(B_TILE_NL_OFF, n_tiles + 1);
+    if (!tile_ws || !tile_nl || !ws_off || !nl_off) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(tile_ws + n_tiles, 0, 8, ctx->stream));
+    WGA_CK(cudaMemsetAsync(tile_nl + n_tiles, 0, 8, ctx->stream));
+    LAUNCH(ctx, k_ws_count, (unsigned)n_tiles, kWsThreads, text, len, tile_ws, tile_nl);
+    WGA_TRY(exclusive_sum(ctx, tile_ws, ws_off, n_tiles + 1));
+    WGA_TRY(exclusive_sum(ctx, tile_nl, nl_off, n_tiles + 1));
+    uint64_t tot[2];
+    WGA_TRY(read_scalars(ctx, {ws_off + n_tiles, nl_off + n_tiles}, tot));
+    const uint64_t n_ws = tot[0], n_nl = tot[1];
+    uint8_t last_byte = 0;
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal + 8, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t *ws_ent = ctx->buf<uint64_t>(B_WS, n_ws + 1), *nl_idx = ctx->buf<uint64_t>(B_NLIDX, n_nl + 1);
+    if (!ws_ent || !nl_idx) return ctx->err_code;
+    LAUNCH(ctx, k_ws_fill, (unsigned)n_tiles, kWsThreads, text, len, ws_off, nl_off, ws_ent, nl_idx);
+    WGA_TRY(sync_check(ctx));
+    last_byte = *(uint8_t *)(ctx->h_scal + 8);
+    const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
+    ctx->n_ws = n_ws; ctx->n_nl = n_nl; ctx->n_lines = n_lines;
+
+    LineView &lv = P->lv;
+    lv.text = text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
+    lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = (flags & WGA_F_FIRST_SLAB) ? 1u : 0u;
+
+    // 2. lines -> record heads
+    uint8_t *lflags = ctx->buf<uint8_t>(B_LINE_FLAGS, n_lines + 1);
+    uint32_t *lhead = ctx->buf<uint32_t>(B_LINE_HEAD, n_lines + 1), *lscan = ctx->buf<uint32_t>(B_LINE_REC, n_lines + 1);
+    if (!lflags || !lhead || !lscan) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(lhead + n_lines, 0, 4, ctx->stream));
+    LAUNCH(ctx, k_line_flags, grid_for(n_lines, 256), 256, lv, lflags, lhead);
+    WGA_TRY(exclusive_sum(ctx, lhead, lscan, n_lines + 1));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal, lscan + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    const uint64_t n_rec = *(uint32_t *)ctx->h_scal;
+    ctx->n_rec = n_rec;
+
+    // 3. s-line fields
+    SLines &sl = P->sl;
+    sl.name_off = ctx->buf<uint64_t>(B_SL_NAME_OFF, n_lines); sl.name_len = ctx->buf<uint32_t>(B_SL_NAME_LEN, n_lines);
+    sl.start = ctx->buf<uint64_t>(B_SL_START, n_lines); sl.ali = ctx->buf<uint64_t>(B_SL_ALI, n_lines);
+    sl.src = ctx->buf<uint64_t>(B_SL_SRC, n_lines); sl.neg = ctx->buf<uint8_t>(B_SL_NEG, n_lines);
+    sl.seq_off = ctx->buf<uint64_t>(B_SL_SEQ_OFF, n_lines); sl.seq_len = ctx->buf<uint64_t>(B_SL_SEQ_LEN, n_lines);
+    Recs &rc = P->rc;
+    rc.first = ctx->buf<uint64_t>(B_REC_FIRST, n_rec + 1); rc.last = ctx->buf<uint64_t>(B_REC_LAST, n_rec + 1);
+    rc.tl = ctx->buf<uint64_t>(B_REC_TL, n_rec + 1); rc.ql = ctx->buf<uint64_t>(B_REC_QL, n_rec + 1);
+    rc.t_off = ctx->buf<uint64_t>(B_REC_TOFF, n_rec + 1); rc.q_off = ctx->buf<uint64_t>(B_REC_QOFF, n_rec + 1);
+    rc.ncols = ctx->buf<uint64_t>(B_REC_NCOLS, n_rec + 1); rc.neg = ctx->buf<uint8_t>(B_REC_NEG, n_rec + 1);
+    rc.skip = ctx->buf<uint8_t>(B_REC_SKIP, n_rec + 1); rc.n_items = ctx->buf<uint32_t>(B_REC_NITEMS, n_rec + 1);
+    P->item_base = ctx->buf<uint64_t>(B_REC_ITEMBASE, n_rec + 1);
+    uint64_t *colsum = ctx->buf<uint64_t>(B_GEN_H, n_rec + 1);
+    if (!sl.name_off || !sl.name_len || !sl.start || !sl.ali || !sl.src || !sl.neg || !sl.seq_off || !sl.seq_len ||
+        !rc.first || !rc.last || !rc.tl || !rc.ql || !rc.t_off || !rc.q_off || !rc.ncols || !rc.neg || !rc.skip ||
+        !rc.n_items || !P->item_base || !colsum)
+        return ctx->err_code;
+    LAUNCH(ctx, k_parse_slines, grid_for(n_lines, 256), 256, lv, lflags, lscan, sl, rc.first, rc.last, P->err_key);
+    if (n_rec == 0) {
+        uint64_t key;
+        WGA_TRY(read_scalars(ctx, {P->err_key}, &key));
+        if (key != kNoErr) return resolve_error(ctx, *P, key, qname);
+        return WGA_OK;
+    }
+
+    // 4. records + work items
+    uint8_t *d_q = nullptr;
+    uint32_t qlen = qname ? (uint32_t)strlen(qname) : 0;
+    if (qname) {
+        d_q = ctx->buf<uint8_t>(B_QNAME, qlen + 1);
+        if (!d_q) return ctx->err_code;
+        WGA_CK(cudaMemcpyAsync(d_q, qname, qlen, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(ctx, k_build_records, grid_for(n_rec, 256), 256, n_rec, text, sl, rc, d_q, qlen, qname ? 1 : 0, mode, P->err_key);
+    WGA_CK(cudaMemsetAsync(rc.n_items + n_rec, 0, 4, ctx->stream));
+    WGA_CK(cudaMemsetAsync(rc.ncols + n_rec, 0, 8, ctx->stream));
+    WGA_TRY(exclusive_sum(ctx, rc.n_items, P->item_base, n_rec + 1));
+    WGA_TRY(exclusive_sum(ctx, rc.ncols, colsum, n_rec + 1));
+    uint64_t sc[3];
+    WGA_TRY(read_scalars(ctx, {P->item_base + n_rec, P->err_key, colsum + n_rec}, sc));
+    if (sc[1] != kNoErr) return resolve_error(ctx, *P, sc[1], qname);
+    ctx->n_items = sc[0];
+    P->total_cols = sc[2];
+    if (ctx->n_items) {
+        P->item_rec = ctx->buf<uint32_t>(B_ITEM_REC, ctx->n_items);
+        P->item_seg = ctx->buf<uint32_t>(B_ITEM_SEG, ctx->n_items);
+        if (!P->item_rec || !P->item_seg) return ctx->err_code;
+        LAUNCH(ctx, k_fill_items, grid_for(n_rec, 256), 256, n_rec, rc.n_items, P->item_base, P->item_rec, P->item_seg);
+    }
+    return WGA_OK;
+}
+
+WalkArgs walk_args(wga_ctx *ctx, const Prep &P, unsigned long long *rec_cnt) {
+    WalkArgs A;
+    memset(&A, 0, sizeof A);
+    A.text = ctx->d_text;
+    A.t_off = P.rc.t_off; A.q_off = P.rc.q_off; A.ncols = P.rc.ncols;
+    A.rec_n_items = P.rc.n_items;
+    A.item_rec = P.item_rec; A.item_seg = P.item_seg;
+    A.n_items = ctx->n_items;
+    A.rec_cnt = rec_cnt;
+    return A;
+}
+
+void walk_begin(wga_ctx *ctx) {
+    ctx->walk_ms = 0.f;
+    ctx->walk_bytes = 0;
+    ctx->walk_launches = 0;
+}
+template <class F>
+int timed_walk(wga_ctx *ctx, const Prep &P, F &&launch) {
+    WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    launch();
+    WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->walk_launches++;
+    ctx->walk_bytes += 2 * P.total_cols + 64 * ctx->n_items;
+    return WGA_OK;
+}
+int walk_collect(wga_ctx *ctx, float *acc) {  // call after a sync that covers ev1
+    float ms = 0.f;
+    WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *acc += ms;
+    return WGA_OK;
+}
+
+// hand the command's output back in the caller's memory kind
+int finish_output(wga_ctx *ctx, const void *d_out, uint64_t n, int mem, wga_span *out) {
+    if (mem == WGA_MEM_DEVICE || n == 0) {
+        out->data = n ? d_out : nullptr;
+        out->len = n;
+        return sync_check(ctx);
+    }
+    void *h = ctx->ensure_host_out(n);
+    if (!h) return ctx->err_code;
+    WGA_CK(cudaMemcpyAsync(h, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    out->data = h;
+    out->len = n;
+    return WGA_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+int wga_ctx_create(int device, void *stream, wga_ctx **out) {
+    if (!out) return WGA_E_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return WGA_E_CUDA;  // no CPU fallback
+    if (device < 0 || device >= ndev) return WGA_E_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return WGA_E_CUDA;
+    wga_ctx *ctx = new wga_ctx();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return WGA_E_CUDA; }
+        ctx->own_stream = true;
+    }
+    if (cudaHostAlloc((void **)&ctx->h_scal, 64 * 8, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return WGA_E_CUDA;
+    }
+    *out = ctx;
+    return WGA_OK;
+}
+
+void wga_ctx_destroy(wga_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->bufs)
+        if (b.p) cudaFree(b.p);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *wga_last_error(const wga_ctx *ctx, uint64_t *where) {
+    if (!ctx) return "no context (CUDA device unavailable)";
+    if (where) *where = ctx->err_where;
+    return ctx->err_msg.c_str();
+}
+
+void wga_ctx_launch_counts(const wga_ctx *ctx, uint64_t *own, uint64_t *cub_calls) {
+    if (own) *own = ctx ? ctx->n_own : 0;
+    if (cub_calls) *cub_calls = ctx ? ctx->n_cub : 0;
+}
+
+void wga_ctx_last_walk(const wga_ctx *ctx, float *ms, uint64_t *alg_bytes, uint32_t *launches) {
+    if (ms) *ms = ctx->walk_ms;
+    if (alg_bytes) *alg_bytes = ctx->walk_bytes;
+    if (launches) *launches = ctx->walk_launches;
+}
+
+void *wga_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void wga_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t wga_maf_safe_cut(const char *text, uint64_t len) {
+    // start offset of the last line (other than the first) that does not begin with 's'; 0 if none
+    uint64_t i = len;
+    while (i > 0) {
+        uint64_t j = i - 1;  // start of the line that contains byte j
+        while (j > 0 && text[j - 1] != '\n') --j;
+        if (j == 0) break;
+        if (text[j] != 's') return j;
+        i = j;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- maf2paf
+int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name,
+                wga_span *out) {
+    if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    Prep P;
+    WGA_TRY(prepare_maf(ctx, flags, query_name, 0, &P));
+    const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
+    if (n_rec == 0 || n_items == 0) return sync_check(ctx);
+
+    unsigned long long *rec_cnt = ctx->buf<unsigned long long>(B_REC_CNT, n_rec * 5);
+    uint32_t *nheads = ctx->buf<uint32_t>(B_ITEM_NHEADS, n_items + 1);
+    uint64_t *run_base = ctx->buf<uint64_t>(B_RUN_BASE, n_items + 1);
+    if (!rec_cnt || !nheads || !run_base) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
+    WGA_CK(cudaMemsetAsync(nheads + n_items, 0, 4, ctx->stream));
+    WalkArgs A = walk_args(ctx, P, rec_cnt);
+    A.item_nheads = nheads;
+    const unsigned wgrid = grid_for(n_items, kWalkWarps);
+    auto kw_count = k_walk<MODE_RUNS_EXT, false>;
+    auto kw_emit = k_walk<MODE_RUNS_EXT, true>;
+    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_count, wgrid, kWalkThreads, A); }));
+    WGA_TRY(exclusive_sum(ctx, nheads, run_base, n_items + 1));
+    uint64_t n_runs;
+    WGA_TRY(read_scalars(ctx, {run_base + n_items}, &n_runs));
+    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
+    ctx->n_runs = n_runs;
+
+    uint64_t *run_pos = ctx->buf<uint64_t>(B_RUN_POS, n_runs + 1), *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
+    uint32_t *run_rec = ctx->buf<uint32_t>(B_RUN_REC, n_runs + 1), *run_dl = ctx->buf<uint32_t>(B_RUN_DL, n_runs + 1);
+    uint8_t *run_cls = ctx->buf<uint8_t>(B_RUN_CLS, n_runs + 1);
+    uint64_t *cig_off = ctx->buf<uint64_t>(B_RUN_CIGOFF, n_runs + 1);
+    uint64_t *rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
+    uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
+    uint32_t *row_fixed = ctx->buf<uint32_t>(B_ROW_FIXED, n_rec + 1);
+    if (!run_pos || !run_len || !run_rec || !run_dl || !run_cls || !cig_off || !rec_run_first || !row_len || !row_off ||
+        !row_fixed)
+        return ctx->err_code;
+    A.run_base = run_base; A.run_pos = run_pos; A.run_rec = run_rec; A.run_cls = run_cls;
+    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_emit, wgrid, kWalkThreads, A); }));
+    LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, run_base, n_items, n_runs, rec_run_first);
+    LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, run_pos, run_rec, P.rc.ncols, run_len, run_dl);
+    WGA_TRY(exclusive_sum(ctx, run_dl, cig_off, n_runs + 1));
+    PafRowArgs R;
+    R.n_rec = n_rec; R.text = ctx->d_text; R.sl = P.sl; R.tl = P.rc.tl; R.ql = P.rc.ql; R.ncols = P.rc.ncols;
+    R.skip = P.rc.skip; R.rec_cnt = rec_cnt; R.rec_run_first = rec_run_first; R.cig_off = cig_off;
+    R.row_len = row_len; R.row_fixed = row_fixed; R.row_off = row_off; R.out = nullptr;
+    LAUNCH(ctx, k_paf_rows<0>, grid_for(n_rec + 1, 256), 256, R);
+    WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
+    uint64_t total;
+    WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
+    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    R.out = d_out;
+    LAUNCH(ctx, k_paf_rows<1>, grid_for(n_rec + 1, 256), 256, R);
+    LAUNCH(ctx, k_paf_cigar, grid_for(n_runs, 256), 256, n_runs, run_rec, run_cls, run_len, run_dl, cig_off, rec_run_first,
+           row_off, row_fixed, d_out);
+    // per-record 11 counters stay available for wga_last_record_counts
+    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
+    if (!cnt11) return ctx->err_code;
+    LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
+    ctx->last_counts_valid = true;
+    return finish_output(ctx, d_out, total, mem, out);
+}
+
+// ---------------------------------------------------------------- stat
+wga_stat_acc *wga_stat_acc_create(int each) {
+    wga_stat_acc *a = new wga_stat_acc();
+    a->each = each ? 1 : 0;
+    return a;
+}
+void wga_stat_acc_destroy(wga_stat_acc *acc) { delete acc; }
+uint64_t wga_stat_acc_npairs(const wga_stat_acc *acc) { return acc ? acc->rows.size() : 0; }
+int wga_stat_acc_write(wga_stat_acc *acc, wga_span *out) {
+    if (!acc || !out) return WGA_E_INVALID_ARG;
+    acc->write();
+    out->data = acc->text.data();
+    out->len = acc->text.size();
+    return WGA_OK;
+}
+int wga_stat_acc_export(wga_stat_acc *acc, wga_span *blob) {
+    if (!acc || !blob) return WGA_E_INVALID_ARG;
+    acc->export_blob();
+    blob->data = acc->blob.data();
+    blob->len = acc->blob.size();
+    return WGA_OK;
+}
+int wga_stat_acc_import(wga_stat_acc *acc, const void *blob, uint64_t len) {
+    if (!acc || !blob) return WGA_E_INVALID_ARG;
+    return acc->import_blob((const char *)blob, len);
+}
+
+}  // extern "C"
+
+namespace {
+
+// shared tail of stat_maf / stat_paf: pair reduction on the device, merge into the host accumulator
+int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned long long *cnt11,
+                unsigned long long *err_key, wga_stat_acc *acc) {
+    std::vector<uint64_t> h_first, h_vals, h_sizes, h_inv_num;
+    std::vector<uint32_t> h_nlen, h_inv_pair;
+    std::vector<char> h_names;
+    uint64_t n_pairs = 0, n_inv = 0;
+    if (!acc->each) {
+        uint64_t cap = 1024;
+        while (cap < 2 * n_rec) cap <<= 1;
+        unsigned long long *keys = ctx->buf<unsigned long long>(B_PT_KEYS, cap);
+        unsigned long long *first = ctx->buf<unsigned long long>(B_PT_FIRST, cap);
+        unsigned long long *vals = ctx->buf<unsigned long long>(B_PT_VALS, cap * kPairVals);
+        uint64_t *rec_slot = ctx->buf<uint64_t>(B_REC_SLOT, n_rec);
+        uint32_t *flag = ctx->buf<uint32_t>(B_PT_FLAG, cap + 1), *idx = ctx->buf<uint32_t>(B_PT_IDX, cap + 1);
+        if (!keys || !first || !vals || !rec_slot || !flag || !idx) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(keys, 0, cap * 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(first, 0xFF, cap * 8, ctx->stream));
+        LAUNCH(ctx, k_pt_init, grid_for(cap * kPairVals, 256), 256, vals, cap);
+        LAUNCH(ctx, k_pair_insert, grid_for(n_rec, 256), 256, n_rec, M, cnt11, cap - 1, keys, first, vals, rec_slot);
+        LAUNCH(ctx, k_pair_verify, grid_for(n_rec, 256), 256, n_rec, M, first, rec_slot, err_key);
+        WGA_CK(cudaMemsetAsync(flag + cap, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_slot_flags, grid_for(cap, 256), 256, cap, keys, flag);
+        WGA_TRY(exclusive_sum(ctx, flag, idx, cap + 1));
+        // '-'-strand records in order
+        uint32_t *iflag = ctx->buf<uint32_t>(B_INV_FLAG, n_rec + 1);
+        uint64_t *iidx = ctx->buf<uint64_t>(B_INV_IDX, n_rec + 1);
+        if (!iflag || !iidx) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(iflag + n_rec, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_inv_flags, grid_for(n_rec, 256), 256, n_rec, M.neg, M.skip, iflag);
+        WGA_TRY(exclusive_sum(ctx, iflag, iidx, n_rec + 1));
+        WGA_CK(cudaMemcpyAsync(ctx->h_scal, idx + cap, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_CK(cudaMemcpyAsync(ctx->h_scal + 1, iidx + n_rec, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_CK(cudaMemcpyAsync(ctx->h_scal + 2, err_key, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_TRY(sync_check(ctx));
+        n_pairs = *(uint32_t *)ctx->h_scal;
+        n_inv = ctx->h_scal[1];
+        if (ctx->h_scal[2] != kNoErr) {
+            ctx->set_error(WGA_E_INTERNAL, ctx->h_scal[2] >> 8, "pair-key hash collision; refusing to merge distinct pairs");
+            return WGA_E_INTERNAL;
+        }
+        uint64_t *p_first = ctx->buf<uint64_t>(B_PAIR_FIRST, n_pairs + 1);
+        uint64_t *p_vals = ctx->buf<uint64_t>(B_PAIR_VALS, (n_pairs + 1) * kPairVals);
+        uint64_t *p_sizes = ctx->buf<uint64_t>(B_GEN_B, (n_pairs + 1) * 2);
+        uint32_t *nlen = ctx->buf<uint32_t>(B_NAME_LEN, 2 * n_pairs + 1);
+        uint64_t *noff = ctx->buf<uint64_t>(B_NAME_OFF, 2 * n_pairs + 1);
+        uint32_t *inv_pair = ctx->buf<uint32_t>(B_INV_PAIR, n_inv + 1);
+        uint64_t *inv_num = ctx->buf<uint64_t>(B_INV_NUM, n_inv + 1);
+        if (!p_first || !p_vals || !p_sizes || !nlen || !noff || !inv_pair || !inv_num) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(nlen + 2 * n_pairs, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_pair_gather, grid_for(cap, 256), 256, cap, flag, idx, first, vals, M, p_first, p_vals, p_sizes, nlen);
+        WGA_TRY(exclusive_sum(ctx, nlen, noff, 2 * n_pairs + 1));
+        uint64_t name_total;
+        WGA_TRY(read_scalars(ctx, {noff + 2 * n_pairs}, &name_total));
+        char *nbuf = (char *)ctx->ensure(B_NAME_BUF, name_total + 1);
+        if (!nbuf) return ctx->err_code;
+        LAUNCH(ctx, k_pair_names, grid_for(2 * n_pairs, 256), 256, n_pairs, p_first, M, noff, nbuf);
+        LAUNCH(ctx, k_inv_gather, grid_for(n_rec, 256), 256, n_rec, iflag, iidx, rec_slot, idx, cnt11, inv_pair, inv_num);
+        h_first.resize(n_pairs); h_vals.resize(n_pairs * kPairVals); h_sizes.resize(n_pairs * 2);
+        h_nlen.resize(2 * n_pairs); h_names.resize(name_total + 1); h_inv_pair.resize(n_inv); h_inv_num.resize(n_inv);
+        if (n_pairs) {
+            WGA_CK(cudaMemcpyAsync(h_first.data(), p_first, n_pairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(h_vals.data(), p_vals, n_pairs * kPairVals * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(h_sizes.data(), p_sizes, n_pairs * 16, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(h_nlen.data(), nlen, n_pairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (name_total) WGA_CK(cudaMemcpyAsync(h_names.data(), nbuf, name_total, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (n_inv) {
+            WGA_CK(cudaMemcpyAsync(h_inv_pair.data(), inv_pair, n_inv * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(h_inv_num.data(), inv_num, n_inv * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        WGA_TRY(sync_check(ctx));
+        // merge in first-occurrence order (the reference's HashMap order is unspecified; natord sort is stable)
+        std::vector<uint32_t> order(n_pairs), map(n_pairs);
+        std::iota(order.begin(), order.end(), 0u);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_first[a] < h_first[b]; });
+        std::vector<uint64_t> name_pos(2 * n_pairs + 1, 0);
+        for (uint64_t i = 0; i < 2 * n_pairs; ++i) name_pos[i + 1] = name_pos[i] + h_nlen[i];
+        for (uint32_t p : order) {
+            std::string rn(h_names.data() + name_pos[2 * p], h_nlen[2 * p]);
+            std::string qn(h_names.data() + name_pos[2 * p + 1], h_nlen[2 * p + 1]);
+            map[p] = acc->find_or_add(rn, h_sizes[2 * p], qn, h_sizes[2 * p + 1]);
+            acc->add_pair_vals(map[p], &h_vals[(uint64_t)p * kPairVals]);
+        }
+        for (uint64_t i = 0; i < n_inv; ++i) {
+            acc->inv_pair.push_back(map[h_inv_pair[i]]);
+            acc->inv_num.push_back(h_inv_num[i]);
+        }
+        return WGA_OK;
+    }
+    // --each: one row per record (stat.rs:129-164)
+    uint64_t *iota = ctx->buf<uint64_t>(B_PAIR_FIRST, n_rec + 1);
+    uint32_t *nlen = ctx->buf<uint32_t>(B_NAME_LEN, 2 * n_rec + 1);
+    uint64_t *noff = ctx->buf<uint64_t>(B_NAME_OFF, 2 * n_rec + 1);
+    if (!iota || !nlen || !noff) return ctx->err_code;
+    LAUNCH(ctx, k_iota, grid_for(n_rec, 256), 256, iota, n_rec);
+    LAUNCH(ctx, k_each_name_len, grid_for(2 * n_rec + 1, 256), 256, n_rec, M.t_name_len, M.q_name_len, nlen);
+    WGA_TRY(exclusive_sum(ctx, nlen, noff, 2 * n_rec + 1));
+    uint64_t name_total;
+    WGA_TRY(read_scalars(ctx, {noff + 2 * n_rec}, &name_total));
+    char *nbuf = (char *)ctx->ensure(B_NAME_BUF, name_total + 1);
+    if (!nbuf) return ctx->err_code;
+    LAUNCH(ctx, k_pair_names, grid_for(2 * n_rec, 256), 256, n_rec, iota, M, noff, nbuf);
+    std::vector<uint64_t> c11(n_rec * 11), tsz(n_rec), qsz(n_rec), tst(n_rec), qst(n_rec);
+    std::vector<uint8_t> neg(n_rec), skip(n_rec, 0);
+    h_nlen.resize(2 * n_rec);
+    h_names.resize(name_total + 1);
+    WGA_CK(cudaMemcpyAsync(c11.data(), cnt11, n_rec * 88, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(tsz.data(), M.t_size, n_rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(qsz.data(), M.q_size, n_rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(tst.data(), M.t_start, n_rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(qst.data(), M.q_start, n_rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(neg.data(), M.neg, n_rec, cudaMemcpyDeviceToHost, ctx->stream));
+    if (M.skip) WGA_CK(cudaMemcpyAsync(skip.data(), M.skip, n_rec, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(h_nlen.data(), nlen, n_rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (name_total) WGA_CK(cudaMemcpyAsync(h_names.data(), nbuf, name_total, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    uint64_t pos = 0;
+    for (uint64_t r = 0; r < n_rec; ++r) {
+        std::string rn(h_names.data() + pos, h_nlen[2 * r]);
+        pos += h_nlen[2 * r];
+        std::string qn(h_names.data() + pos, h_nlen[2 * r + 1]);
+        pos += h_nlen[2 * r + 1];
+        if (skip[r]) continue;
+        wga_stat_acc::Row row;
+        row.ref_name = rn; row.query_name = qn; row.ref_size = tsz[r]; row.query_size = qsz[r];
+        const uint64_t *c = &c11[r * 11];
+        for (int i = 0; i < 11; ++i) row.v[i] = c[i];
+        row.v[11] = tst[r];
+        row.v[12] = qst[r];
+        if (c[10]) {
+            uint64_t aligned = c[0] + c[1] + c[5] + c[9], qal = c[0] + c[1] + c[3] + c[7];
+            row.inv_size = (float)(aligned + qal) / (float)(c[10] + 1);
+        }
+        acc->rows.push_back(std::move(row));
+    }
+    return WGA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name,
+                 wga_stat_acc *acc) {
+    if (!ctx || !acc || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    Prep P;
+    WGA_TRY(prepare_maf(ctx, flags, query_name, 0, &P));
+    const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
+    if (n_rec == 0) return sync_check(ctx);
+    unsigned long long *rec_cnt = ctx->buf<unsigned long long>(B_REC_CNT, n_rec * 5);
+    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
+    if (!rec_cnt || !cnt11) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
+    if (n_items) {
+        WalkArgs A = walk_args(ctx, P, rec_cnt);
+        auto kw_stat = k_walk<MODE_STAT, false>;
+        WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_stat, grid_for(n_items, kWalkWarps), kWalkThreads, A); }));
+    }
+    LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
+    RecMeta M;
+    M.text = ctx->d_text;
+    uint64_t *tno = ctx->buf<uint64_t>(B_GEN_C, n_rec), *qno = ctx->buf<uint64_t>(B_GEN_D, n_rec);
+    uint32_t *tnl = ctx->buf<uint32_t>(B_GEN_E, n_rec), *qnl = ctx->buf<uint32_t>(B_GEN_F, n_rec);
+    uint64_t *m4 = ctx->buf<uint64_t>(B_GEN_G, 4 * n_rec);
+    if (!tno || !qno || !tnl || !qnl || !m4) return ctx->err_code;
+    LAUNCH(ctx, k_maf_meta, grid_for(n_rec, 256), 256, n_rec, P.sl, P.rc.tl, P.rc.ql, tno, qno, tnl, qnl, m4, m4 + n_rec,
+           m4 + 2 * n_rec, m4 + 3 * n_rec);
+    M.t_name_off = tno; M.q_name_off = qno; M.t_name_len = tnl; M.q_name_len = qnl;
+    M.t_size = m4; M.q_size = m4 + n_rec; M.t_start = m4 + 2 * n_rec; M.q_start = m4 + 3 * n_rec;
+    M.neg = P.rc.neg; M.skip = P.rc.skip;
+    int rc = stat_reduce(ctx, n_rec, M, cnt11, P.err_key, acc);
+    if (rc) return rc;
+    if (ctx->walk_launches) WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
+    ctx->last_counts_valid = true;
+    return WGA_OK;
+}
+
+int wga_last_record_counts(wga_ctx *ctx, uint64_t *dst, uint64_t cap_records, uint64_t *n_records) {
+    if (!ctx || !n_records) return WGA_E_INVALID_ARG;
+    if (!ctx->last_counts_valid) {
+        ctx->set_error(WGA_E_INVALID_ARG, 0, "no per-record counters available (run maf2paf/stat first)");
+        return WGA_E_INVALID_ARG;
+    }
+    *n_records = ctx->n_rec;
+    uint64_t n = std::min(cap_records, ctx->n_rec);
+    if (n && dst) {
+        WGA_CK(cudaMemcpyAsync(dst, ctx->bufs[B_GEN_A].p, n * 88, cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_TRY(sync_check(ctx));
+    }
+    return WGA_OK;
+}
+
+#ifndef WGA_WITH_PAF
+int wga_paf_stat(wga_ctx *ctx, const void *, uint64_t, int, uint32_t, wga_stat_acc *) {
+    if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "paf stat not built");
+    return WGA_E_UNSUPPORTED;
+}
+#endif
+#ifndef WGA_WITH_CALL
+int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
+    if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "call not built");
+    return WGA_E_UNSUPPORTED;
+}
+int wga_maf_call(wga_ctx *ctx, const void *, uint64_t, int, uint32_t, const wga_call_opts *, wga_span *) {
+    if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "call not built");
+    return WGA_E_UNSUPPORTED;
+}
+#endif
+
+}  // extern "C"
