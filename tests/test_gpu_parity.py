@@ -189,7 +189,7 @@ def _dev_bytes(ptr, n):
     import torch
 
     class Raw:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
     return torch.as_tensor(Raw(), device="cuda").cpu().numpy().tobytes() if n else b""
 
 
@@ -229,3 +229,117 @@ def test_stat_export_import_roundtrip(w, ctx):
     m.import_(a.export())
     m.import_(b.export())
     assert m.write() == orc.stat_maf(text)
+
+
+# ------------------------------------------------------------------------------------------- call
+def vcf(w, ctx, text, **kw):
+    return w.run_bytes(w.call_var_maf, w.MAFReader(text), None, kw.get("snp", False), kw.get("inv", False),
+                       kw.get("svlen", 50), False, kw.get("sample"), kw.get("query_name"), None,
+                       kw.get("chunk_size"), ctx=ctx)
+
+
+def check_call(w, ctx, text, **kw):
+    want = orc.call_maf(text, snp=kw.get("snp", False), inv=kw.get("inv", False), svlen=kw.get("svlen", 50),
+                        sample=kw.get("sample") or "sample", query_name=kw.get("query_name"),
+                        chunk_size=kw.get("chunk_size") or 1000000)
+    got = vcf(w, ctx, text, **kw)
+    if got != want:
+        gl, wl = got.splitlines(), want.splitlines()
+        for i, (a, b) in enumerate(zip(gl, wl)):
+            assert a == b, (i, a, b, kw)
+        assert len(gl) == len(wl), (len(gl), len(wl), kw)
+    assert got == want
+
+
+def test_call_golden(w, ctx):
+    check_call(w, ctx, TEST_MAF, snp=True, svlen=0)
+    check_call(w, ctx, TEST_MAF)
+    check_call(w, ctx, TEST_MAF, snp=True, svlen=0, inv=True, sample="hg002", chunk_size=100)
+    got = vcf(w, ctx, TEST_MAF, snp=True, svlen=0).decode().splitlines()
+    readme = open(os.path.join(G, "ref_readme_call_s_l0.vcf")).read().splitlines()
+    for a, b in zip(got, readme):
+        if a.startswith("#") or "SVTYPE" in a:
+            assert a == b
+        else:
+            assert a.split("\t")[:8] == b.split("\t")[:8]
+
+
+def test_call_quirks(w, ctx):
+    t = b"ACGTACGTAC" + b"GGGGGGGG" + b"ACGT"
+    q = b"ACGTACGTAC" + b"--------" + b"ACGT"
+    for strand in (b"+", b"-"):
+        text = _maf([[b"s t 0 22 + 100 " + t, b"s q 0 14 " + strand + b" 100 " + q]])
+        for cs in (1000, 10, 11, 14, 3, 1):
+            for K in (0, 3, 8, 9):
+                check_call(w, ctx, text, svlen=K, chunk_size=cs, inv=True, snp=True)
+    one = _maf([[b"s t 0 4 + 100 ACGT"]])
+    assert vcf(w, ctx, one) == orc.call_maf(one)
+    three = _maf([[b"s t 0 4 + 100 ACGT", b"s q1 0 4 + 100 AC-T", b"s q2 0 4 - 100 A-GA"],
+                  [b"s t 0 4 + 100 ACGT", b"s q1 0 4 + 100 ACGT"]])
+    for qn in (None, "q2", "zz", "t"):
+        check_call(w, ctx, three, svlen=0, snp=True, inv=True, query_name=qn)
+    # both-gap columns (W), adjacent I/D, leading / trailing gaps, lower case upper-cased on output
+    text = _maf([[b"s t 0 9 + 100 --AC-GT--AaC---GT", b"s q 0 9 + 100 GGAC-G-TTAcCTTT--"]])
+    check_call(w, ctx, text, svlen=0, snp=True)
+    check_call(w, ctx, text, svlen=1, snp=True, inv=True)
+    # a base outside ACGTN in REF/ALT is an error (noodles)
+    bad = _maf([[b"s t 0 4 + 100 ACRT", b"s q 0 4 + 100 ACGT"]])
+    with pytest.raises(orc.OracleError) as eo:
+        orc.call_maf(bad, snp=True)
+    with pytest.raises(w.WGAError) as eg:
+        vcf(w, ctx, bad, snp=True)
+    assert eo.value.code == eg.value.code == 10
+    assert vcf(w, ctx, bad) == orc.call_maf(bad)  # no SNP rows requested: the base is never printed
+    with pytest.raises(w.WGAError) as e:
+        vcf(w, ctx, TEST_MAF, chunk_size=0)
+    assert e.value.code == 101
+
+
+def test_call_random_chunks(w, ctx):
+    rng = random.Random(17)
+    for it in range(60):
+        blocks = []
+        for b in range(rng.randrange(1, 12)):
+            L = rng.choice([1, 2, 5, 17, 40, 64, 130, 600])
+            kind = rng.random()
+            t, q = [], []
+            while len(t) < L:
+                r = rng.random()
+                n = rng.randrange(1, 9)
+                if r < 0.5:
+                    for _ in range(n):
+                        c = rng.choice("ACGT"); t.append(c); q.append(c)
+                elif r < 0.65:
+                    for _ in range(n):
+                        c = rng.choice("ACGT"); t.append(c); q.append(rng.choice([x for x in "ACGT" if x != c]))
+                elif r < 0.8:
+                    t += ["-"] * n; q += [rng.choice("ACGT") for _ in range(n)]
+                elif r < 0.95:
+                    q += ["-"] * n; t += [rng.choice("ACGT") for _ in range(n)]
+                else:
+                    t += ["-"] * n; q += ["-"] * n
+            t, q = "".join(t[:L]), "".join(q[:L])
+            st = rng.choice("+-")
+            nt, nq = sum(c != "-" for c in t), sum(c != "-" for c in q)
+            blocks.append([f"s chr{b % 2} {rng.randrange(100, 900)} {nt} + 5000 {t}".encode(),
+                           f"s q.{b % 3} {rng.randrange(100, 900)} {nq} {st} 7000 {q}".encode()])
+        text = _maf(blocks)
+        for kw in (dict(snp=True, svlen=0, inv=True, chunk_size=rng.choice([1, 2, 3, 7, 16, 50, 1000])),
+                   dict(snp=False, svlen=rng.choice([1, 2, 4]), inv=True, chunk_size=rng.choice([5, 9, 33])),
+                   dict(snp=True, svlen=3, inv=False, chunk_size=rng.choice([4, 10, 100]))):
+            check_call(w, ctx, text, **kw)
+
+
+@pytest.mark.parametrize("seed,kw,ckw", [
+    (1, {}, dict(snp=True, svlen=0)),
+    (2, dict(p_bothgap=2e-3, p_neg=0.3), dict(snp=True, svlen=0, inv=True)),
+    (3, dict(len_median=60000.0, len_sigma=1.2, len_max=400000, p_sv=3e-4, sv_min=50, sv_max=30000, p_neg=0.3),
+     dict(inv=True, chunk_size=20000)),
+    (4, dict(len_median=60000.0, len_sigma=1.2, len_max=400000, p_sv=3e-4, sv_min=50, sv_max=30000, p_neg=0.3),
+     dict(snp=True, svlen=2, inv=True, chunk_size=5000)),
+    (5, dict(p_mis=0.1, p_gap=0.05, p_neg=0.5), dict(snp=True, svlen=1, inv=True, chunk_size=300)),
+])
+def test_call_synthetic(w, ctx, seed, kw, ckw):
+    n = 300 if kw.get("len_median", 2000.0) < 10000 else 40
+    text = bs.gen_maf(bs.maf_params(n, seed=100 + seed, **kw))
+    check_call(w, ctx, text, **ckw)

@@ -696,6 +696,123 @@ int wga_last_record_counts(wga_ctx *ctx, uint64_t *dst, uint64_t cap_records, ui
     return WGA_OK;
 }
 
+#ifdef WGA_WITH_CALL
+// ---------------------------------------------------------------- call
+int wga_vcf_header(wga_ctx *ctx, const char *sample, wga_span *out) {
+    if (!ctx || !out) return WGA_E_INVALID_ARG;
+    // caller.rs:304-337 build_header through noodles-vcf 0.43 (README.md:324-331 pins the text)
+    static thread_local std::string hdr;
+    hdr = "##fileformat=VCFv4.4\n"
+          "##INFO=<ID=SVLEN,Number=A,Type=Integer,Description=\"Length of structural variant\">\n"
+          "##INFO=<ID=SVTYPE,Number=1,Type=String,Description=\"Type of structural variant\">\n"
+          "##INFO=<ID=END,Number=1,Type=Integer,Description=\"End position of the longest variant described in this record\">\n"
+          "##INFO=<ID=INV_NEST,Number=1,Type=String,Description=\"Varations nested within inversion\">\n"
+          "##FORMAT=<ID=QI,Number=1,Type=String,Description=\"Query informations\">\n"
+          "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+          "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t";
+    hdr += sample ? sample : "sample";
+    hdr += "\n";
+    out->data = hdr.data();
+    out->len = hdr.size();
+    return WGA_OK;
+}
+
+int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_call_opts *opts,
+                 wga_span *out) {
+    if (!ctx || !out || !opts || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    if (opts->chunk_size == 0) {
+        ctx->set_error(WGA_E_INVALID_ARG, 0, "chunk_size must be > 0 (the reference never terminates on 0)");
+        return WGA_E_INVALID_ARG;
+    }
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    Prep P;
+    WGA_TRY(prepare_maf(ctx, flags, opts->query_name, 1, &P));
+    const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
+    if (n_rec == 0 || n_items == 0) return sync_check(ctx);
+
+    // dense pass: caller-classified run list
+    uint32_t *nheads = ctx->buf<uint32_t>(B_ITEM_NHEADS, n_items + 1);
+    uint64_t *run_base = ctx->buf<uint64_t>(B_RUN_BASE, n_items + 1);
+    if (!nheads || !run_base) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(nheads + n_items, 0, 4, ctx->stream));
+    WalkArgs A = walk_args(ctx, P, nullptr);
+    A.item_nheads = nheads;
+    const unsigned wgrid = grid_for(n_items, kWalkWarps);
+    auto kw_count = k_walk<MODE_RUNS_CALLER, false>;
+    auto kw_emit = k_walk<MODE_RUNS_CALLER, true>;
+    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_count, wgrid, kWalkThreads, A); }));
+    WGA_TRY(exclusive_sum(ctx, nheads, run_base, n_items + 1));
+    uint64_t n_runs;
+    WGA_TRY(read_scalars(ctx, {run_base + n_items}, &n_runs));
+    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
+    ctx->n_runs = n_runs;
+    uint64_t *run_pos = ctx->buf<uint64_t>(B_RUN_POS, n_runs + 1), *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
+    uint32_t *run_rec = ctx->buf<uint32_t>(B_RUN_REC, n_runs + 1);
+    uint8_t *run_cls = ctx->buf<uint8_t>(B_RUN_CLS, n_runs + 1);
+    uint64_t *rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
+    uint64_t *tcon = ctx->buf<uint64_t>(B_GEN_A, n_runs + 1), *qcon = ctx->buf<uint64_t>(B_GEN_B, n_runs + 1);
+    uint64_t *St = ctx->buf<uint64_t>(B_GEN_C, n_runs + 1), *Sq = ctx->buf<uint64_t>(B_GEN_D, n_runs + 1);
+    uint64_t *nchunks = ctx->buf<uint64_t>(B_GEN_E, n_rec + 1), *rec_chunk_first = ctx->buf<uint64_t>(B_GEN_F, n_rec + 1);
+    if (!run_pos || !run_len || !run_rec || !run_cls || !rec_run_first || !tcon || !qcon || !St || !Sq || !nchunks ||
+        !rec_chunk_first)
+        return ctx->err_code;
+    A.run_base = run_base; A.run_pos = run_pos; A.run_rec = run_rec; A.run_cls = run_cls;
+    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_emit, wgrid, kWalkThreads, A); }));
+    LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, run_base, n_items, n_runs, rec_run_first);
+    LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, run_pos, run_rec, P.rc.ncols, run_len, (uint32_t *)nullptr);
+    LAUNCH(ctx, k_run_contrib, grid_for(n_runs + 1, 256), 256, n_runs, run_cls, run_len, tcon, qcon);
+    WGA_TRY(exclusive_sum(ctx, tcon, St, n_runs + 1));
+    WGA_TRY(exclusive_sum(ctx, qcon, Sq, n_runs + 1));
+    // chunk grid
+    LAUNCH(ctx, k_chunks<0>, grid_for(n_rec + 1, 128), 128, n_rec, rec_run_first, run_pos, run_cls, P.rc.ncols, P.rc.skip,
+           opts->chunk_size, opts->svlen_cutoff, nchunks, (const uint64_t *)nullptr, (uint64_t *)nullptr);
+    WGA_TRY(exclusive_sum(ctx, nchunks, rec_chunk_first, n_rec + 1));
+    uint64_t n_chunks;
+    WGA_TRY(read_scalars(ctx, {rec_chunk_first + n_rec}, &n_chunks));
+    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
+    uint64_t *chunk_cs = ctx->buf<uint64_t>(B_GEN_G, n_chunks + 1);
+    uint32_t *chunk_rec = ctx->buf<uint32_t>(B_PT_FLAG, n_chunks + 1), *chunk_inv = ctx->buf<uint32_t>(B_PT_IDX, n_chunks + 1);
+    uint64_t *inv_cum = ctx->buf<uint64_t>(B_INV_IDX, n_chunks + 1);
+    uint64_t *rows = ctx->buf<uint64_t>(B_RUN_CIGOFF, n_runs + 1), *rowbase = ctx->buf<uint64_t>(B_NAME_OFF, n_runs + 1);
+    if (!chunk_cs || !chunk_rec || !chunk_inv || !inv_cum || !rows || !rowbase) return ctx->err_code;
+    LAUNCH(ctx, k_chunks<1>, grid_for(n_rec + 1, 128), 128, n_rec, rec_run_first, run_pos, run_cls, P.rc.ncols, P.rc.skip,
+           opts->chunk_size, opts->svlen_cutoff, nchunks, rec_chunk_first, chunk_cs);
+    LAUNCH(ctx, k_chunk_rec, grid_for(n_rec, 256), 256, n_rec, rec_chunk_first, chunk_rec);
+    CallView V;
+    V.n_rec = n_rec; V.n_runs = n_runs; V.text = ctx->d_text; V.sl = P.sl; V.tl = P.rc.tl; V.ql = P.rc.ql;
+    V.ncols = P.rc.ncols; V.t_off = P.rc.t_off; V.q_off = P.rc.q_off; V.neg = P.rc.neg; V.skip = P.rc.skip;
+    V.rec_run_first = rec_run_first; V.run_pos = run_pos; V.run_len = run_len; V.run_rec = run_rec; V.run_cls = run_cls;
+    V.St = St; V.Sq = Sq; V.chunk_size = opts->chunk_size; V.svlen = opts->svlen_cutoff; V.snp = opts->snp; V.inv = opts->inv;
+    V.rec_chunk_first = rec_chunk_first; V.chunk_cs = chunk_cs; V.chunk_inv = chunk_inv; V.inv_cum = inv_cum;
+    LAUNCH(ctx, k_chunk_inv, grid_for(n_chunks + 1, 256), 256, V, n_chunks, chunk_rec, chunk_inv);
+    WGA_TRY(exclusive_sum(ctx, chunk_inv, inv_cum, n_chunks + 1));
+    LAUNCH(ctx, k_run_rows, grid_for(n_runs + 1, 256), 256, V, rows);
+    WGA_TRY(exclusive_sum(ctx, rows, rowbase, n_runs + 1));
+    uint64_t n_rows;
+    WGA_TRY(read_scalars(ctx, {rowbase + n_runs}, &n_rows));
+    if (n_rows == 0) return sync_check(ctx);
+    uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rows + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rows + 1);
+    if (!row_len || !row_off) return ctx->err_code;
+    LAUNCH(ctx, k_vcf_rows<0>, grid_for(n_rows + 1, 128), 128, V, n_rows, rowbase, row_len, (const uint64_t *)nullptr,
+           (char *)nullptr, P.err_key);
+    WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rows + 1));
+    uint64_t sc[2];
+    WGA_TRY(read_scalars(ctx, {row_off + n_rows, P.err_key}, sc));
+    if (sc[1] != kNoErr) {
+        ctx->set_error(WGA_E_VCF_BASE, sc[1] >> 8, "REF/ALT base outside ACGTNacgtn (noodles-vcf rejects the record)");
+        return WGA_E_VCF_BASE;
+    }
+    char *d_out = (char *)ctx->ensure(B_OUT, sc[0] + 16);
+    if (!d_out) return ctx->err_code;
+    LAUNCH(ctx, k_vcf_rows<1>, grid_for(n_rows, 128), 128, V, n_rows, rowbase, row_len, row_off, d_out, P.err_key);
+    return finish_output(ctx, d_out, sc[0], mem, out);
+}
+#endif
+
 #ifndef WGA_WITH_PAF
 int wga_paf_stat(wga_ctx *ctx, const void *, uint64_t, int, uint32_t, wga_stat_acc *) {
     if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "paf stat not built");
