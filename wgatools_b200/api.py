@@ -252,7 +252,9 @@ def call_var_maf(mafreader: MAFReader, mafindex, writer, if_snp=False, if_inv=Fa
 
 
 def run_bytes(fn, *args, **kw) -> bytes:
-    """convenience: run one of the functions above into a bytes object"""
+    """convenience: run one of the functions above into a bytes object (the writer argument is inserted
+    where the reference signature has it: 2nd for maf2paf/stat_*, 3rd for call_var_maf)"""
     w = io.BytesIO()
-    fn(*args[:1], w, *args[1:], **kw)
+    pos = 2 if fn is call_var_maf else 1
+    fn(*args[:pos], w, *args[pos:], **kw)
     return w.getvalue()
