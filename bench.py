@@ -6,7 +6,7 @@ A "step" is one pass of the three commands over the batch.  `value` times the pa
 already resident in HBM (inputs larger than L2, so no flush is needed); `e2e` times the same pass
 through the host-buffer C-ABI entry points (pinned host text in, host PAF / VCF / stat partials out:
 H2D and D2H copies inside the timed region).  `roofline` is the dense column-walk kernel: algorithmic
-bytes (2 B per column + 64 B per work item) over its CUDA-event time, against MEASURED_PEAKS.json.
+bytes (2 B per column + 32 B per work item) over its CUDA-event time, against MEASURED_PEAKS.json.
 `cpu_baseline` is the oracle (C restatement of the reference algorithm) on a bounded sample of the same
 workload.  `--impl reference` times that CPU path alone, on every host core it can use.
 

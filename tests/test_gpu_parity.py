@@ -343,3 +343,13 @@ def test_call_synthetic(w, ctx, seed, kw, ckw):
     n = 300 if kw.get("len_median", 2000.0) < 10000 else 40
     text = bs.gen_maf(bs.maf_params(n, seed=100 + seed, **kw))
     check_call(w, ctx, text, **ckw)
+
+
+def test_dense_whitespace_falls_back_to_exact_index(w, ctx):
+    # > 128 whitespace bytes inside one 4 KiB tile overflows the single-pass index -> exact two-pass path
+    blk = [b"s t 0 4 + 100 ACGT", b"s q 0 4 + 100 AC-A"]
+    text = b"##maf\n" + b"\n" * 6000 + _maf([blk], header=b"") + b" \t " * 3000 + b"\n" + _maf([blk, blk], header=b"")
+    check_both(w, ctx, text)
+    check_call(w, ctx, text, snp=True, svlen=0)
+    big = bs.gen_maf(bs.maf_params(300, seed=5)) + b"\n" * 9000 + b"a\n" + b"\n".join(blk) + b"\n"
+    check_both(w, ctx, big)

@@ -59,6 +59,7 @@ struct DevBuf {
 
 struct wga_ctx {
     int device = 0;
+    int n_sm = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     wga::DevBuf bufs[wga::B_COUNT_];

@@ -115,6 +115,89 @@ __global__ void __launch_bounds__(kWsThreads) k_ws_fill(const uint8_t *__restric
     }
 }
 
+// ---------------------------------------------------------------- 1b. single-pass whitespace index
+// The exact two-pass index above reads the slab twice.  Whitespace is sparse in MAF (~7 bytes per s-line of
+// several kB), so the fast path reads the slab ONCE: a warp owns a 4 KiB tile, keeps its 8 x 512 B of loads
+// in flight, and writes the (tile-relative) whitespace offsets into a fixed slot region of kTokCap entries
+// per tile; a sparse pass then compacts the slots into ws_ent / nl_ws_idx.  A tile with more than kTokCap
+// whitespace bytes raises the overflow flag and the caller falls back to the exact two-pass kernels.
+constexpr int kTokTile = 4096;
+constexpr int kTokCap = 128;
+constexpr int kTokWarps = 8;
+
+__global__ void __launch_bounds__(kTokWarps * 32) k_ws_scan(const uint8_t *__restrict__ text, uint64_t len, uint64_t n_tiles,
+                                                            uint64_t *__restrict__ tile_ws, uint64_t *__restrict__ tile_nl,
+                                                            uint16_t *__restrict__ slots, uint32_t *__restrict__ overflow) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_warps = (uint64_t)gridDim.x * kTokWarps;
+    for (uint64_t tile = (uint64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5); tile < n_tiles; tile += n_warps) {
+        const uint64_t base = tile * kTokTile;
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint64_t off = base + (uint64_t)k * 512 + lane * 16;
+            v[k] = off < len ? ldg16(text + off) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t cw = 0, cn = 0;
+        uint16_t *slot = slots + tile * kTokCap;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t off = base + (uint64_t)k * 512 + lane * 16;
+            const int64_t rem = (int64_t)len - (int64_t)off;
+            uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, ws[4], nl[4];
+            uint32_t c = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t valid = rem >= 4 * (i + 1) ? kHi : (rem > 4 * i ? range_flags(0, (int)(rem - 4 * i)) : 0u);
+                ws[i] = ws_bytes(w[i]) & valid;
+                nl[i] = nl_bytes(w[i]) & valid;
+                c += __popc(ws[i]);
+                cn += __popc(nl[i]);
+            }
+            if (__ballot_sync(0xFFFFFFFFu, c != 0)) {
+                uint32_t tot;
+                uint32_t idx = cw + warp_excl_scan(c, &tot);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t m = ws[i];
+                    while (m) {
+                        int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        uint32_t rel = (uint32_t)k * 512u + lane * 16u + 4u * i + (uint32_t)(bit >> 3);
+                        if (idx < (uint32_t)kTokCap) slot[idx] = (uint16_t)(rel | (((nl[i] >> bit) & 1u) << 15));
+                        ++idx;
+                    }
+                }
+                cw += tot;
+            }
+        }
+        cn = warp_sum(cn);
+        if (lane == 0) {
+            tile_ws[tile] = cw;
+            tile_nl[tile] = cn;
+            if (cw > (uint32_t)kTokCap) atomicOr(overflow, 1u);
+        }
+    }
+}
+
+__global__ void k_ws_compact(uint64_t n_tiles, const uint64_t *__restrict__ tile_ws, const uint64_t *__restrict__ ws_off,
+                             const uint64_t *__restrict__ nl_off, const uint16_t *__restrict__ slots,
+                             uint64_t *__restrict__ ws_ent, uint64_t *__restrict__ nl_ws_idx) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint32_t c = (uint32_t)tile_ws[t];
+    if (c > (uint32_t)kTokCap) c = kTokCap;  // overflow: the caller discards this index
+    uint64_t wo = ws_off[t], no = nl_off[t];
+    const uint64_t base = t * kTokTile;
+    const uint16_t *slot = slots + t * kTokCap;
+    for (uint32_t i = 0; i < c; ++i) {
+        uint32_t e = slot[i];
+        bool isnl = e >> 15;
+        ws_ent[wo + i] = (base + (e & 0x7FFFu)) | (isnl ? ~kPosMask : 0ull);
+        if (isnl) nl_ws_idx[no++] = wo + i;
+    }
+}
+
 // ---------------------------------------------------------------- 2. lines and records
 struct LineView {
     const uint8_t *text;

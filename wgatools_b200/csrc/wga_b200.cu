@@ -99,7 +99,7 @@ struct Prep {
     SLines sl;
     Recs rc;
     uint64_t *item_base = nullptr;
-    uint32_t *item_rec = nullptr, *item_seg = nullptr;
+    ItemDesc *items = nullptr;
     unsigned long long *err_key = nullptr;
     uint64_t total_cols = 0;
 };
@@ -176,25 +176,55 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
     LAUNCH(ctx, k_init_u64, 1, 1, P->err_key, 1, kNoErr);
     if (len == 0) return WGA_OK;
 
-    // 1. whitespace index
-    const uint64_t n_tiles = (len + kWsTile - 1) / kWsTile;
-    uint64_t *tile_ws = ctx->buf<uint64_t>(B_TILE_WS, n_tiles + 1), *tile_nl = ctx->buf<uint64_t>(B_TILE_NL, n_tiles + 1);
-    uint64_t *ws_off = ctx->buf<uint64_t>(B_TILE_WS_OFF, n_tiles + 1), *nl_off = ctx->buf<uint64_t>(B_TILE_NL_OFF, n_tiles + 1);
-    if (!tile_ws || !tile_nl || !ws_off || !nl_off) return ctx->err_code;
-    WGA_CK(cudaMemsetAsync(tile_ws + n_tiles, 0, 8, ctx->stream));
-    WGA_CK(cudaMemsetAsync(tile_nl + n_tiles, 0, 8, ctx->stream));
-    LAUNCH(ctx, k_ws_count, (unsigned)n_tiles, kWsThreads, text, len, tile_ws, tile_nl);
-    WGA_TRY(exclusive_sum(ctx, tile_ws, ws_off, n_tiles + 1));
-    WGA_TRY(exclusive_sum(ctx, tile_nl, nl_off, n_tiles + 1));
-    uint64_t tot[2];
-    WGA_TRY(read_scalars(ctx, {ws_off + n_tiles, nl_off + n_tiles}, tot));
-    const uint64_t n_ws = tot[0], n_nl = tot[1];
+    // 1. whitespace index: single-pass fast path, exact two-pass fallback when a tile overflows
+    uint64_t n_ws = 0, n_nl = 0;
+    uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
     uint8_t last_byte = 0;
-    WGA_CK(cudaMemcpyAsync(ctx->h_scal + 8, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
-    uint64_t *ws_ent = ctx->buf<uint64_t>(B_WS, n_ws + 1), *nl_idx = ctx->buf<uint64_t>(B_NLIDX, n_nl + 1);
-    if (!ws_ent || !nl_idx) return ctx->err_code;
-    LAUNCH(ctx, k_ws_fill, (unsigned)n_tiles, kWsThreads, text, len, ws_off, nl_off, ws_ent, nl_idx);
-    WGA_TRY(sync_check(ctx));
+    bool indexed = false;
+    {
+        const uint64_t n_tiles = (len + kTokTile - 1) / kTokTile;
+        uint64_t *tile_ws = ctx->buf<uint64_t>(B_TILE_WS, n_tiles + 1), *tile_nl = ctx->buf<uint64_t>(B_TILE_NL, n_tiles + 1);
+        uint64_t *ws_off = ctx->buf<uint64_t>(B_TILE_WS_OFF, n_tiles + 1), *nl_off = ctx->buf<uint64_t>(B_TILE_NL_OFF, n_tiles + 1);
+        uint16_t *slots = ctx->buf<uint16_t>(B_PAF_A, n_tiles * kTokCap);
+        uint32_t *ovf = ctx->buf<uint32_t>(B_SCALARS, 16);
+        if (!tile_ws || !tile_nl || !ws_off || !nl_off || !slots || !ovf) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(tile_ws + n_tiles, 0, 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(tile_nl + n_tiles, 0, 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(ovf, 0, 4, ctx->stream));
+        uint64_t want = (n_tiles + kTokWarps - 1) / kTokWarps, cap = (uint64_t)ctx->n_sm * 8;
+        LAUNCH(ctx, k_ws_scan, (unsigned)(want < cap ? want : cap), kTokWarps * 32, text, len, n_tiles, tile_ws, tile_nl, slots, ovf);
+        WGA_TRY(exclusive_sum(ctx, tile_ws, ws_off, n_tiles + 1));
+        WGA_TRY(exclusive_sum(ctx, tile_nl, nl_off, n_tiles + 1));
+        WGA_CK(cudaMemcpyAsync(ctx->h_scal + 8, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        uint64_t tot[3];
+        WGA_TRY(read_scalars(ctx, {ws_off + n_tiles, nl_off + n_tiles, ovf}, tot));
+        if ((uint32_t)tot[2] == 0) {
+            n_ws = tot[0]; n_nl = tot[1];
+            ws_ent = ctx->buf<uint64_t>(B_WS, n_ws + 1); nl_idx = ctx->buf<uint64_t>(B_NLIDX, n_nl + 1);
+            if (!ws_ent || !nl_idx) return ctx->err_code;
+            LAUNCH(ctx, k_ws_compact, grid_for(n_tiles, 256), 256, n_tiles, tile_ws, ws_off, nl_off, slots, ws_ent, nl_idx);
+            indexed = true;
+        }
+    }
+    if (!indexed) {
+        const uint64_t n_tiles = (len + kWsTile - 1) / kWsTile;
+        uint64_t *tile_ws = ctx->buf<uint64_t>(B_TILE_WS, n_tiles + 1), *tile_nl = ctx->buf<uint64_t>(B_TILE_NL, n_tiles + 1);
+        uint64_t *ws_off = ctx->buf<uint64_t>(B_TILE_WS_OFF, n_tiles + 1), *nl_off = ctx->buf<uint64_t>(B_TILE_NL_OFF, n_tiles + 1);
+        if (!tile_ws || !tile_nl || !ws_off || !nl_off) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(tile_ws + n_tiles, 0, 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(tile_nl + n_tiles, 0, 8, ctx->stream));
+        LAUNCH(ctx, k_ws_count, (unsigned)n_tiles, kWsThreads, text, len, tile_ws, tile_nl);
+        WGA_TRY(exclusive_sum(ctx, tile_ws, ws_off, n_tiles + 1));
+        WGA_TRY(exclusive_sum(ctx, tile_nl, nl_off, n_tiles + 1));
+        uint64_t tot[2];
+        WGA_TRY(read_scalars(ctx, {ws_off + n_tiles, nl_off + n_tiles}, tot));
+        n_ws = tot[0]; n_nl = tot[1];
+        ws_ent = ctx->buf<uint64_t>(B_WS, n_ws + 1); nl_idx = ctx->buf<uint64_t>(B_NLIDX, n_nl + 1);
+        if (!ws_ent || !nl_idx) return ctx->err_code;
+        LAUNCH(ctx, k_ws_fill, (unsigned)n_tiles, kWsThreads, text, len, ws_off, nl_off, ws_ent, nl_idx);
+        WGA_CK(cudaMemcpyAsync(ctx->h_scal + 8, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_TRY(sync_check(ctx));
+    }
     last_byte = *(uint8_t *)(ctx->h_scal + 8);
     const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
     ctx->n_ws = n_ws; ctx->n_nl = n_nl; ctx->n_lines = n_lines;
@@ -260,10 +290,10 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
     ctx->n_items = sc[0];
     P->total_cols = sc[2];
     if (ctx->n_items) {
-        P->item_rec = ctx->buf<uint32_t>(B_ITEM_REC, ctx->n_items);
-        P->item_seg = ctx->buf<uint32_t>(B_ITEM_SEG, ctx->n_items);
-        if (!P->item_rec || !P->item_seg) return ctx->err_code;
-        LAUNCH(ctx, k_fill_items, grid_for(n_rec, 256), 256, n_rec, rc.n_items, P->item_base, P->item_rec, P->item_seg);
+        P->items = ctx->buf<ItemDesc>(B_ITEM_REC, ctx->n_items);
+        if (!P->items) return ctx->err_code;
+        LAUNCH(ctx, k_fill_item_desc, grid_for(n_rec, 256), 256, n_rec, rc.n_items, P->item_base, rc.t_off, rc.q_off, rc.ncols,
+               P->items);
     }
     return WGA_OK;
 }
@@ -272,12 +302,17 @@ WalkArgs walk_args(wga_ctx *ctx, const Prep &P, unsigned long long *rec_cnt) {
     WalkArgs A;
     memset(&A, 0, sizeof A);
     A.text = ctx->d_text;
-    A.t_off = P.rc.t_off; A.q_off = P.rc.q_off; A.ncols = P.rc.ncols;
-    A.rec_n_items = P.rc.n_items;
-    A.item_rec = P.item_rec; A.item_seg = P.item_seg;
+    A.items = P.items;
+    A.ncols = P.rc.ncols;
     A.n_items = ctx->n_items;
     A.rec_cnt = rec_cnt;
     return A;
+}
+
+unsigned walk_grid(wga_ctx *ctx, uint64_t n_items) {  // persistent warps: kWalkCtasPerSm CTAs per SM
+    uint64_t want = (n_items + kWalkWarps - 1) / kWalkWarps;
+    uint64_t cap = (uint64_t)ctx->n_sm * kWalkCtasPerSm;
+    return (unsigned)(want < cap ? want : cap);
 }
 
 void walk_begin(wga_ctx *ctx) {
@@ -291,7 +326,7 @@ int timed_walk(wga_ctx *ctx, const Prep &P, F &&launch) {
     launch();
     WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->walk_launches++;
-    ctx->walk_bytes += 2 * P.total_cols + 64 * ctx->n_items;
+    ctx->walk_bytes += 2 * P.total_cols + 32 * ctx->n_items;
     return WGA_OK;
 }
 int walk_collect(wga_ctx *ctx, float *acc) {  // call after a sync that covers ev1
@@ -331,6 +366,8 @@ int wga_ctx_create(int device, void *stream, wga_ctx **out) {
     if (cudaSetDevice(device) != cudaSuccess) return WGA_E_CUDA;
     wga_ctx *ctx = new wga_ctx();
     ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->n_sm <= 0) ctx->n_sm = 148;
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -421,7 +458,7 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     WGA_CK(cudaMemsetAsync(nheads + n_items, 0, 4, ctx->stream));
     WalkArgs A = walk_args(ctx, P, rec_cnt);
     A.item_nheads = nheads;
-    const unsigned wgrid = grid_for(n_items, kWalkWarps);
+    const unsigned wgrid = walk_grid(ctx, n_items);
     auto kw_count = k_walk<MODE_RUNS_EXT, false>;
     auto kw_emit = k_walk<MODE_RUNS_EXT, true>;
     WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_count, wgrid, kWalkThreads, A); }));
@@ -660,7 +697,7 @@ int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (n_items) {
         WalkArgs A = walk_args(ctx, P, rec_cnt);
         auto kw_stat = k_walk<MODE_STAT, false>;
-        WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_stat, grid_for(n_items, kWalkWarps), kWalkThreads, A); }));
+        WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_stat, walk_grid(ctx, n_items), kWalkThreads, A); }));
     }
     LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
     RecMeta M;
@@ -741,7 +778,7 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     WGA_CK(cudaMemsetAsync(nheads + n_items, 0, 4, ctx->stream));
     WalkArgs A = walk_args(ctx, P, nullptr);
     A.item_nheads = nheads;
-    const unsigned wgrid = grid_for(n_items, kWalkWarps);
+    const unsigned wgrid = walk_grid(ctx, n_items);
     auto kw_count = k_walk<MODE_RUNS_CALLER, false>;
     auto kw_emit = k_walk<MODE_RUNS_CALLER, true>;
     WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_count, wgrid, kWalkThreads, A); }));
