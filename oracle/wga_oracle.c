@@ -1108,3 +1108,228 @@ int orc_call_maf(const char *text, size_t len, int snp, int inv, uint64_t svlen_
     free(rec.s);
     return rc < 0 ? -rc : ORC_OK;
 }
+
+/* ======================================================================================
+ * Threaded restatement of the reference's rayon structure (bench baseline only).
+ *
+ * src/converter.rs:41-48 and src/tools/stat.rs:67-81 run `records().par_bridge()`: the record
+ * iterator (BufRead::lines -> String per line, parse_sline -> name.to_string(), seq.to_string())
+ * is pulled under par_bridge's lock, i.e. SERIALLY, and only the per-record closure
+ * (convert2paf / stat_rec) runs on the worker pool; results are written by the calling thread.
+ * `call` is strictly sequential (src/tools/caller.rs:62).  The functions below reproduce exactly
+ * that split with pthreads, including the reference's per-line and per-field copies, so that the
+ * CPU baseline has the reference's parallel structure rather than an idealised sharding.
+ * ====================================================================================== */
+#include <pthread.h>
+
+typedef struct {
+    sline *s;       /* owned copies: name.p / seq.p are malloc'ed */
+    size_t n;
+    size_t query_idx;
+} owned_rec;
+
+static void owned_free(owned_rec *r) {
+    for (size_t i = 0; i < r->n; i++) { free((void *)r->s[i].name.p); free((void *)r->s[i].seq.p); }
+    free(r->s);
+    r->s = NULL;
+    r->n = 0;
+}
+
+/* one s-line the way the reference materialises it: lines() allocates a String for the line and checks
+ * UTF-8, parse_sline copies name and seq into fresh Strings, then the line String is dropped */
+static int owned_sline(sv line, sline *out, char *err, size_t errcap) {
+    char *copy = (char *)malloc(line.n + 1);
+    memcpy(copy, line.p, line.n);
+    unsigned char hi = 0;
+    for (size_t i = 0; i < line.n; i++) hi |= (unsigned char)copy[i]; /* from_utf8 ASCII fast path */
+    if (hi & 0x80) { /* non-ASCII: full validation would follow; treated as valid here */ }
+    sv lc = {copy, line.n};
+    int rc = parse_sline(lc, out, err, errcap);
+    if (rc == ORC_OK) {
+        char *nm = (char *)malloc(out->name.n + 1), *sq = (char *)malloc(out->seq.n + 1);
+        memcpy(nm, out->name.p, out->name.n);
+        memcpy(sq, out->seq.p, out->seq.n);
+        out->name.p = nm;
+        out->seq.p = sq;
+    }
+    free(copy);
+    return rc;
+}
+
+/* MAFRecords::next with owned s-lines; same control flow as maf_next */
+static int maf_next_owned(lreader *r, owned_rec *rec, char *err, size_t errcap) {
+    sv line;
+    for (;;) {
+        if (!next_line(r, &line)) return 0;
+        if (line.n > 0 && line.p[0] == 's') break;
+    }
+    size_t cap = 4;
+    rec->s = (sline *)malloc(cap * sizeof(sline));
+    rec->n = 0;
+    rec->query_idx = 1;
+    sline s;
+    int rc = owned_sline(line, &s, err, errcap);
+    if (rc) { owned_free(rec); return -rc; }
+    rec->s[rec->n++] = s;
+    while (next_line(r, &line)) {
+        if (line.n > 0 && line.p[0] == 's') {
+            rc = owned_sline(line, &s, err, errcap);
+            if (rc) { owned_free(rec); return -rc; }
+            if (rec->n == cap) { cap *= 2; rec->s = (sline *)realloc(rec->s, cap * sizeof(sline)); }
+            rec->s[rec->n++] = s;
+        } else break;
+    }
+    return 1;
+}
+
+typedef struct {
+    /* shared */
+    pthread_mutex_t mu;
+    lreader rd;
+    size_t next_idx;
+    int err;            /* first error code (lowest record index wins) */
+    size_t err_idx;
+    char errmsg[256];
+    const char *query_name;
+    int mode;           /* 0 maf2paf rows, 1 stat */
+    /* results, indexed by record: grown under mu */
+    orc_buf *rows;      /* mode 0: one PAF row per record */
+    struct statres { sv ref_name, query_name; uint64_t ref_size, ref_start, query_size, query_start; recstat rs; char *own; } *st;
+    size_t cap;
+} par_state;
+
+static void par_reserve(par_state *ps, size_t idx) {
+    if (idx < ps->cap) return;
+    size_t nc = ps->cap ? ps->cap : 1024;
+    while (nc <= idx) nc *= 2;
+    if (ps->mode == 0) {
+        ps->rows = (orc_buf *)realloc(ps->rows, nc * sizeof(orc_buf));
+        memset(ps->rows + ps->cap, 0, (nc - ps->cap) * sizeof(orc_buf));
+    } else {
+        ps->st = (struct statres *)realloc(ps->st, nc * sizeof(*ps->st));
+        memset(ps->st + ps->cap, 0, (nc - ps->cap) * sizeof(*ps->st));
+    }
+    ps->cap = nc;
+}
+
+static void *par_worker(void *vp) {
+    par_state *ps = (par_state *)vp;
+    orc_buf cigar = {0};
+    for (;;) {
+        owned_rec rec = {0};
+        char err[256];
+        pthread_mutex_lock(&ps->mu); /* par_bridge: the iterator is advanced under a lock */
+        if (ps->err) { pthread_mutex_unlock(&ps->mu); break; }
+        int rc = maf_next_owned(&ps->rd, &rec, err, sizeof err);
+        size_t idx = ps->next_idx;
+        if (rc > 0) { ps->next_idx++; par_reserve(ps, idx); }
+        else if (rc < 0) { ps->err = -rc; ps->err_idx = idx; memcpy(ps->errmsg, err, sizeof err); }
+        pthread_mutex_unlock(&ps->mu);
+        if (rc <= 0) break;
+        int e = ORC_OK;
+        if (ps->query_name) {
+            e = ORC_E_QUERY_NAME_NOT_FOUND;
+            for (size_t i = 0; i < rec.n; i++)
+                if (sv_eq_c(rec.s[i].name, ps->query_name)) { rec.query_idx = i; e = ORC_OK; break; }
+            if (e) snprintf(err, sizeof err, "Query name:%s not found in MAF", ps->query_name);
+        }
+        if (!e && rec.query_idx >= rec.n) {
+            e = ORC_E_PANIC;
+            snprintf(err, sizeof err, "panic: index out of bounds: the len is %zu but the index is %zu", rec.n, rec.query_idx);
+        }
+        if (e) {
+            pthread_mutex_lock(&ps->mu);
+            if (!ps->err || idx < ps->err_idx) { ps->err = e; ps->err_idx = idx; memcpy(ps->errmsg, err, sizeof err); }
+            pthread_mutex_unlock(&ps->mu);
+            owned_free(&rec);
+            break;
+        }
+        const sline *t = &rec.s[0], *q = &rec.s[rec.query_idx];
+        size_t n = t->seq.n < q->seq.n ? t->seq.n : q->seq.n;
+        orc_counts c;
+        mafrec view = {rec.s, rec.n, rec.n, rec.query_idx};
+        if (ps->mode == 0) {
+            cigar.n = 0;
+            orc_parse_maf_seq_to_cigar(t->seq.p, q->seq.p, n, q->neg, &c, &cigar);
+            orc_buf row = {0};
+            uint64_t matches = c.c[0], bl = c.c[0] + c.c[1] + c.c[3] + c.c[7] + c.c[5] + c.c[9];
+            csv_field(&row, q->name, 1); csv_u64(&row, q->size, 0);
+            csv_u64(&row, maf_query_start(&view), 0); csv_u64(&row, maf_query_end(&view), 0);
+            buf_putc(&row, '\t'); buf_putc(&row, q->neg ? '-' : '+');
+            csv_field(&row, t->name, 0); csv_u64(&row, t->size, 0); csv_u64(&row, t->start, 0);
+            csv_u64(&row, t->start + t->align_size, 0); csv_u64(&row, matches, 0); csv_u64(&row, bl, 0);
+            csv_u64(&row, 255, 0);
+            buf_puts(&row, "\tNM:i:"); buf_putu(&row, bl - matches);
+            buf_puts(&row, "\tcg:Z:"); buf_put(&row, cigar.p, cigar.n); buf_putc(&row, '\n');
+            pthread_mutex_lock(&ps->mu);
+            ps->rows[idx] = row;
+            pthread_mutex_unlock(&ps->mu);
+        } else {
+            orc_parse_maf_seq_to_cigar(t->seq.p, q->seq.p, n, q->neg, &c, &cigar);
+            cigar.n = 0; /* get_stat builds (and drops) the cigar string too (maf.rs:535-539) */
+            struct statres sr;
+            sr.rs = recstat_from(&c);
+            sr.own = (char *)malloc(t->name.n + q->name.n + 2); /* Pair{ref_name.to_string(), query_name.to_string()} */
+            memcpy(sr.own, t->name.p, t->name.n);
+            memcpy(sr.own + t->name.n, q->name.p, q->name.n);
+            sr.ref_name.p = sr.own; sr.ref_name.n = t->name.n;
+            sr.query_name.p = sr.own + t->name.n; sr.query_name.n = q->name.n;
+            sr.ref_size = t->size; sr.ref_start = t->start; sr.query_size = q->size;
+            sr.query_start = maf_query_start(&view);
+            pthread_mutex_lock(&ps->mu);
+            ps->st[idx] = sr;
+            pthread_mutex_unlock(&ps->mu);
+        }
+        owned_free(&rec);
+    }
+    orc_buf_free(&cigar);
+    return NULL;
+}
+
+static int par_run(par_state *ps, const char *text, size_t len, int threads) {
+    pthread_mutex_init(&ps->mu, NULL);
+    maf_reader_init(&ps->rd, text, len);
+    if (threads < 1) threads = 1;
+    if (threads > 512) threads = 512;
+    pthread_t th[512];
+    for (int i = 0; i < threads; i++) pthread_create(&th[i], NULL, par_worker, ps);
+    for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
+    pthread_mutex_destroy(&ps->mu);
+    return ps->err;
+}
+
+int orc_maf2paf_mt(const char *text, size_t len, const char *query_name, int threads, orc_buf *out, char *err, size_t errcap) {
+    par_state ps;
+    memset(&ps, 0, sizeof ps);
+    ps.query_name = query_name;
+    ps.mode = 0;
+    int rc = par_run(&ps, text, len, threads);
+    if (rc) set_err(err, errcap, "%s", ps.errmsg);
+    for (size_t i = 0; i < ps.next_idx; i++) { /* converter.rs:49-52: serial csv write */
+        if (!rc && ps.rows[i].p) buf_put(out, ps.rows[i].p, ps.rows[i].n);
+        orc_buf_free(&ps.rows[i]);
+    }
+    free(ps.rows);
+    return rc;
+}
+
+int orc_stat_maf_mt(const char *text, size_t len, int each, const char *query_name, int threads, orc_buf *out, char *err, size_t errcap) {
+    par_state ps;
+    memset(&ps, 0, sizeof ps);
+    ps.query_name = query_name;
+    ps.mode = 1;
+    int rc = par_run(&ps, text, len, threads);
+    if (rc) set_err(err, errcap, "%s", ps.errmsg);
+    statvec v = {0};
+    if (!rc) {
+        for (size_t i = 0; i < ps.next_idx; i++) {
+            struct statres *s = &ps.st[i];
+            stat_accumulate(&v, each, s->ref_name, s->ref_size, s->ref_start, s->query_name, s->query_size, s->query_start, &s->rs);
+        }
+        stat_write(&v, each, out);
+    }
+    for (size_t i = 0; i < ps.next_idx; i++) free(ps.st[i].own);
+    free(ps.st);
+    free(v.r);
+    return rc;
+}

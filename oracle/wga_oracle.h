@@ -81,6 +81,13 @@ int orc_call_maf(const char *text, size_t len, int snp, int inv, uint64_t svlen_
                  const char *sample, const char *query_name, uint64_t chunk_size,
                  orc_buf *out, char *err, size_t errcap);
 
+/* the reference's rayon structure with `-t threads` (serial reader under par_bridge's lock + worker pool);
+ * output identical to the sequential functions (file order).  Used as the CPU baseline of bench.py. */
+int orc_maf2paf_mt(const char *text, size_t len, const char *query_name, int threads, orc_buf *out,
+                   char *err, size_t errcap);
+int orc_stat_maf_mt(const char *text, size_t len, int each, const char *query_name, int threads, orc_buf *out,
+                    char *err, size_t errcap);
+
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */
 void orc_fmt_f32(float v, char *dst /* >= 32 bytes */);      /* ryu 1.0.14 Buffer::format(f32) */

@@ -50,6 +50,10 @@ def lib():
         L.orc_call_maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64,
                                    ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_maf2paf_mt.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int,
+                                     ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_stat_maf_mt.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
+                                      ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -92,6 +96,14 @@ def maf2paf(text: bytes, query_name=None) -> bytes:
 
 def stat_maf(text: bytes, each=False, query_name=None) -> bytes:
     return _run(lib().orc_stat_maf, text, len(text), int(each), _opt(query_name))
+
+
+def maf2paf_mt(text: bytes, threads, query_name=None) -> bytes:
+    return _run(lib().orc_maf2paf_mt, text, len(text), _opt(query_name), int(threads))
+
+
+def stat_maf_mt(text: bytes, threads, each=False, query_name=None) -> bytes:
+    return _run(lib().orc_stat_maf_mt, text, len(text), int(each), _opt(query_name), int(threads))
 
 
 def stat_paf(text: bytes, each=False) -> bytes:

@@ -4,19 +4,20 @@
 // cigar_cat_ext :298-308) and of src/tools/caller.rs:442-446 (classifier cigar_cat_ext_caller,
 // cigar.rs:314-328).
 //
-// Shape (v2).  Persistent warps; a warp walks one work item (<= kSeg columns of one record) at a time.
+// Shape (v3).  Persistent warps; a warp walks one work item (<= kSeg columns of one record) at a time.
 // Lane i of step k owns the 16 columns of chunk j = 32k+i: one aligned 16-byte load of the target and a
-// funnel-shifted pair of 16-byte loads of the query (the two streams are misaligned against each other
-// by an arbitrary number of bytes).  Alignments are >99 % identical columns, so the dense part of the
-// kernel is only a 128-bit compare: a chunk whose 16 columns and whose preceding column are all '=' can
-// neither contain nor start a run and is skipped.  Every other chunk ("slow": contains a mismatch/gap,
-// follows one, or touches the item boundary) is pushed -- data words included -- into a per-warp queue in
-// shared memory; whenever 32 slow chunks are queued the warp classifies them in lock-step, one chunk per
-// lane, with the byte-SIMD flag words of hd_core.h:
-//   MODE_STAT  : X / I / D column counts and I / D run starts (events);
-//   MODE_RUNS_*: additionally every run head (class change), counted (EMIT=false) or written as
-//                (column, class) entries in column order (EMIT=true; warp scan over the batch).
-// Algorithmic traffic: 2 bytes per column (+ 32 B of item descriptor).
+// funnel-shifted pair of 16-byte loads of the query (the two streams are misaligned against each other by
+// an arbitrary number of bytes).  Alignments are >99 % identical columns, so the dense part of the kernel
+// is only a 128-bit compare: a chunk whose 16 columns and whose preceding column are all '=' can neither
+// contain nor start a run and is skipped.  Every other chunk ("slow": contains a mismatch/gap, follows
+// one, or touches the item boundary) is pushed -- data words and item context included -- into a per-warp
+// queue in shared memory.  Whenever 32 slow chunks are queued (from any number of items) the warp
+// classifies them in lock-step, one chunk per lane, with the byte-SIMD flag words of hd_core.h:
+//   - X / I / D column counts and I / D run starts (events) -> atomics on the record's counter row;
+//   - run heads (class changes) -> (column-in-item, class) entries appended, in column order, to the
+//     item's slot region (capacity n/8+16 by default; an overflow is reported and the caller re-runs with
+//     worst-case capacity), so maf2paf / call need ONE dense pass; a sparse kernel compacts the slots.
+// Algorithmic traffic: 2 bytes per column (+ 48 B of item descriptor).
 #pragma once
 #include "ctx.cuh"
 #include "tokenize.cuh"
@@ -26,164 +27,291 @@ namespace wga {
 enum { MODE_STAT = 0, MODE_RUNS_EXT = 1, MODE_RUNS_CALLER = 2 };
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
-constexpr int kWalkCtasPerSm = 4;
+constexpr int kWalkCtasPerSm = 3;
+constexpr int kQWords = 14;  // queue entry: t[4] q[4] prev meta item rec col_lo col_hi
+constexpr uint32_t kSlotPad = 16;
 
 struct __align__(16) ItemDesc {  // one work item: columns [seg*kSeg, seg*kSeg+n) of record rec
     uint64_t t_off, q_off;       // byte offsets of the item's first column in target / query
-    uint32_t n, rec, seg, single;  // single: the record has exactly one item (plain stores, no atomics)
+    uint64_t slot_base;          // first slot of the item's run-head region
+    uint32_t n, rec;
+    uint32_t seg, tail, pad0, pad1;  // tail: columns of the record after this item, clipped to 16
 };
+static_assert(sizeof(ItemDesc) == 48, "ItemDesc is read as three 16-byte vectors");
 
 struct WalkArgs {
     const uint8_t *text;
     const ItemDesc *items;
-    const uint64_t *ncols;
     uint64_t n_items;
-    unsigned long long *rec_cnt;  // [n_rec][5]: X, I_events, I_cols, D_events, D_cols
-    uint32_t *item_nheads;        // RUNS, EMIT=false
-    const uint64_t *run_base;     // RUNS, EMIT=true
-    uint64_t *run_pos;
-    uint32_t *run_rec;
-    uint8_t *run_cls;
+    unsigned long long *rec_cnt;  // [n_rec][5]: X, I_events, I_cols, D_events, D_cols (zero-initialised)
+    uint32_t *item_nheads;        // [n_items] zero-initialised
+    uint32_t *slots;              // run-head slots
+    uint32_t cap_shift;           // slot capacity of an item = (n >> cap_shift) + kSlotPad
+    uint32_t *overflow;
 };
+
+__device__ __host__ __forceinline__ uint64_t slot_cap(uint64_t n, uint32_t shift) { return (n >> shift) + kSlotPad; }
+
+// rec_slot_base: exclusive scan over records of the summed capacities of their items
+__global__ void k_rec_slot_need(uint64_t n_rec, const uint32_t *__restrict__ n_items, const uint64_t *__restrict__ ncols,
+                                uint32_t shift, uint64_t *__restrict__ need) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rec) return;
+    uint64_t v = 0;
+    if (r < n_rec) {
+        uint32_t n = n_items[r];
+        if (n) v = (uint64_t)(n - 1) * slot_cap(kSeg, shift) + slot_cap(ncols[r] - (uint64_t)(n - 1) * kSeg, shift);
+    }
+    need[r] = v;
+}
 
 __global__ void k_fill_item_desc(uint64_t n_rec, const uint32_t *__restrict__ n_items,
                                  const uint64_t *__restrict__ item_base, const uint64_t *__restrict__ t_off,
                                  const uint64_t *__restrict__ q_off, const uint64_t *__restrict__ ncols,
+                                 const uint64_t *__restrict__ rec_slot_base, uint32_t shift,
                                  ItemDesc *__restrict__ items) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
     uint64_t b = item_base[r], nc = ncols[r];
     uint32_t n = n_items[r];
+    uint64_t sb = rec_slot_base ? rec_slot_base[r] : 0;
     for (uint32_t s = 0; s < n; ++s) {
         ItemDesc d;
         uint64_t c0 = (uint64_t)s * kSeg;
         d.t_off = t_off[r] + c0;
         d.q_off = q_off[r] + c0;
+        d.slot_base = sb + (uint64_t)s * slot_cap(kSeg, shift);
         d.n = (uint32_t)(nc - c0 < (uint64_t)kSeg ? nc - c0 : (uint64_t)kSeg);
+        uint64_t tail = nc - c0 - d.n;
         d.rec = (uint32_t)r;
         d.seg = s;
-        d.single = n == 1;
+        d.tail = (uint32_t)(tail > 16 ? 16 : tail);
+        d.pad0 = d.pad1 = 0;
         items[b + s] = d;
     }
 }
 
-// 5 consecutive words starting at word index ws (0..3) of the 8-word window {a,b}
-__device__ __forceinline__ void select5(const uint4 &a, const uint4 &b, uint32_t ws, uint32_t w[5]) {
-    switch (ws) {
-        case 0: w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; break;
-        case 1: w[0] = a.y; w[1] = a.z; w[2] = a.w; w[3] = b.x; w[4] = b.y; break;
-        case 2: w[0] = a.z; w[1] = a.w; w[2] = b.x; w[3] = b.y; w[4] = b.z; break;
-        default: w[0] = a.w; w[1] = b.x; w[2] = b.y; w[3] = b.z; w[4] = b.w; break;
-    }
-}
 __device__ __forceinline__ uint32_t has_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & kHi; }
+__device__ __forceinline__ int clamp16(int64_t v) { return v < 0 ? 0 : (v > 16 ? 16 : (int)v); }
 
-struct WalkAcc {
-    uint32_t cX, cI, cD, eI, eD, nheads;
-    uint64_t out;
+struct WarpEmit {  // run-head emission state of the warp: the item whose slot region is still being filled
+    uint32_t open_item;   // 0xFFFFFFFF = none
+    uint32_t open_count;
 };
 
-// classify one queued chunk per lane (lanes >= cnt idle), accumulate counts, emit heads in order
-template <int MODE, bool EMIT>
-__device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64], uint32_t cnt, uint32_t lane,
-                                           uint32_t a, uint32_t n, uint64_t c0, uint64_t ncols, uint32_t rec,
-                                           WalkAcc &acc) {
+// classify one queued chunk per lane (lanes >= cnt idle); counts -> atomics, heads -> item slots in order
+template <int MODE>
+__device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64], uint32_t cnt, uint32_t lane, WarpEmit &E) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
     constexpr bool RUNS = MODE != MODE_STAT;
-    constexpr bool COUNTS = MODE == MODE_STAT || (MODE == MODE_RUNS_EXT && !EMIT);  // counted once
-    uint32_t H[4] = {0, 0, 0, 0}, hc = 0, j = 0;
+    constexpr bool COUNTS = MODE != MODE_RUNS_CALLER;
+    uint32_t H[4] = {0, 0, 0, 0}, hc = 0, item = 0xFFFFFFFFu, colrel = 0;
     Flags4 F[4];
-    if (lane < cnt) {
-        j = Q[0][lane];
-        const uint32_t pv = Q[1][lane];  // bit16: valid, bits 0-7 target byte, 8-15 query byte
+    const bool act = lane < cnt;
+    if (act) {
         uint32_t tw[4], qw[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { tw[k] = Q[2 + k][lane]; qw[k] = Q[6 + k][lane]; }
-        const int64_t lo = (int64_t)a - 16ll * j;                  // bytes below lo precede the item
-        const int64_t hi = (int64_t)n + (int64_t)a - 16ll * j;     // bytes from hi on follow the item
-        const int64_t glo = c0 == 0 ? lo : -1;                     // bytes below glo precede the record
-        const int64_t ghi = (int64_t)(ncols - c0) + (int64_t)a - 16ll * j;  // bytes from ghi on follow it
-        const bool interior = lo <= 0 && hi >= 16;
-        uint32_t cm[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t ctx = kHi;
-            cm[k] = kHi;
-            if (!interior) {
-                int f0 = (int)(lo - 4 * k), t0 = (int)(hi - 4 * k > 4 ? 4 : hi - 4 * k);
-                cm[k] = range_flags(f0 < 0 ? 0 : f0, t0);
-                int f1 = glo < 0 ? 0 : (int)(glo - 4 * k > 4 ? 4 : glo - 4 * k);
-                int t1 = (int)(ghi - 4 * k > 4 ? 4 : ghi - 4 * k);
-                ctx = range_flags(f1 < 0 ? 0 : f1, t1);
-            }
-            F[k] = classify4<CALLER>(tw[k], qw[k], ctx);
-        }
+        for (int k = 0; k < 4; ++k) { tw[k] = Q[k][lane]; qw[k] = Q[4 + k][lane]; }
+        const uint32_t pv = Q[8][lane];    // bit16: valid, bits 0-7 target byte, 8-15 query byte
+        const uint32_t meta = Q[9][lane];  // f0 | t0<<5 | t1<<10 | seg0<<15 | colrel<<16 (column of byte 0 + 16, in item)
+        item = Q[10][lane];
+        const int f0 = meta & 31, t0 = (meta >> 5) & 31, t1 = (meta >> 10) & 31;
+        const int f1 = ((meta >> 15) & 1u) ? f0 : 0;  // bytes before the record start are not columns
+        colrel = meta >> 16;
+        uint32_t cX = 0, cI = 0, cD = 0, eI = 0, eD = 0;
         Flags4 pf = classify_prev<CALLER>(pv & 0xFFu, (pv >> 8) & 0xFFu, (pv >> 16) & 1u);
         uint32_t p_eq = pf.eq, p_x = pf.x, p_i = pf.i, p_d = pf.d, p_w = pf.w;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            const uint32_t cm = range_flags(f0 - 4 * k, t0 - 4 * k), ctx = range_flags(f1 - 4 * k, t1 - 4 * k);
+            F[k] = classify4<CALLER>(tw[k], qw[k], ctx);
             uint32_t Pi = prev_flags(p_i, F[k].i), Pd = prev_flags(p_d, F[k].d);
             if (COUNTS) {
-                acc.cX += __popc(F[k].x & cm[k]);
-                acc.cI += __popc(F[k].i & cm[k]);
-                acc.cD += __popc(F[k].d & cm[k]);
-                acc.eI += __popc(F[k].i & ~Pi & cm[k]);
-                acc.eD += __popc(F[k].d & ~Pd & cm[k]);
+                cX += __popc(F[k].x & cm);
+                cI += __popc(F[k].i & cm);
+                cD += __popc(F[k].d & cm);
+                eI += __popc(F[k].i & ~Pi & cm);
+                eD += __popc(F[k].d & ~Pd & cm);
             }
             if (RUNS) {
                 uint32_t Pe = prev_flags(p_eq, F[k].eq), Px = prev_flags(p_x, F[k].x);
                 uint32_t same = (F[k].eq & Pe) | (F[k].x & Px) | (F[k].i & Pi) | (F[k].d & Pd);
                 if (CALLER) same |= F[k].w & prev_flags(p_w, F[k].w);
-                H[k] = cm[k] & ~same;
+                H[k] = cm & ~same;
                 hc += __popc(H[k]);
             }
             p_eq = F[k].eq; p_x = F[k].x; p_i = F[k].i; p_d = F[k].d; p_w = F[k].w;
         }
+        if (COUNTS && (cX | cI | cD)) {
+            unsigned long long *c = A.rec_cnt + (uint64_t)Q[11][lane] * 5;
+            if (cX) atomicAdd(c + 0, (unsigned long long)cX);
+            if (eI) atomicAdd(c + 1, (unsigned long long)eI);
+            if (cI) atomicAdd(c + 2, (unsigned long long)cI);
+            if (eD) atomicAdd(c + 3, (unsigned long long)eD);
+            if (cD) atomicAdd(c + 4, (unsigned long long)cD);
+        }
     }
     if (RUNS) {
-        if (!EMIT) {
-            acc.nheads += hc;
-        } else {
-            uint32_t tot;
-            uint32_t off = warp_excl_scan(hc, &tot);
-            uint64_t o = acc.out + off;
+        // segmented exclusive scan of hc keyed by item (lanes of one item are contiguous)
+        uint32_t x = hc;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t m = H[k];
-                while (m) {
-                    int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    uint32_t cls = ((F[k].x >> bit) & 1u) * CLS_X + ((F[k].i >> bit) & 1u) * CLS_I +
-                                   ((F[k].d >> bit) & 1u) * CLS_D + ((F[k].w >> bit) & 1u) * CLS_W;
-                    A.run_pos[o] = c0 + (uint64_t)(16u * j + 4u * k + (uint32_t)(bit >> 3)) - a;
-                    A.run_rec[o] = rec;
-                    A.run_cls[o] = (uint8_t)cls;
-                    ++o;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            uint32_t it = __shfl_up_sync(0xFFFFFFFFu, item, d);
+            if (lane >= (uint32_t)d && it == item) x += y;
+        }
+        const uint32_t first_item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        const uint32_t next_item = __shfl_down_sync(0xFFFFFFFFu, item, 1);
+        // the previously open item is complete once the batch starts with another item
+        if (E.open_item != 0xFFFFFFFFu && first_item != E.open_item) {
+            if (lane == 0) A.item_nheads[E.open_item] = E.open_count;
+            E.open_item = 0xFFFFFFFFu;
+            E.open_count = 0;
+        }
+        const uint32_t carry = (item == E.open_item) ? E.open_count : 0u;
+        const uint32_t incl = carry + x;  // heads of this item up to and including this lane
+        if (act) {
+            const uint4 *dp = reinterpret_cast<const uint4 *>(A.items + item);
+            const uint4 d1 = __ldg(dp + 1);
+            const uint64_t sbase = ((uint64_t)d1.y << 32) | d1.x;
+            const uint32_t cap = (uint32_t)slot_cap(d1.z, A.cap_shift);
+            uint32_t o = incl - hc;
+            if (incl > cap) {
+                atomicOr(A.overflow, 1u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t m = H[k];
+                    while (m) {
+                        int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        uint32_t cls = ((F[k].x >> bit) & 1u) * CLS_X + ((F[k].i >> bit) & 1u) * CLS_I +
+                                       ((F[k].d >> bit) & 1u) * CLS_D + ((F[k].w >> bit) & 1u) * CLS_W;
+                        uint32_t col = colrel + 4u * k + (uint32_t)(bit >> 3) - 16u;
+                        A.slots[sbase + o] = (col << 3) | cls;
+                        ++o;
+                    }
                 }
             }
-            acc.out += tot;
+            const bool seg_end = lane + 1 == cnt || next_item != item;
+            if (seg_end && lane + 1 != cnt) A.item_nheads[item] = incl;  // item complete inside the batch
         }
+        // the last lane's item stays open
+        const uint32_t last = cnt - 1;
+        E.open_item = __shfl_sync(0xFFFFFFFFu, item, last);
+        E.open_count = __shfl_sync(0xFFFFFFFFu, incl, last);
     }
 }
 
-template <int MODE, bool EMIT>
-__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs A) {
+// one item: stream its chunks, push the slow ones.  WS = word part of the query misalignment.
+template <int MODE, int WS>
+__device__ __forceinline__ void walk_item(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane,
+                                          uint32_t item, const uint8_t *tbase, const uint8_t *qbase, uint32_t bs,
+                                          bool q_two, uint32_t a, uint32_t n, uint32_t nch, uint32_t q_last,
+                                          uint32_t first_prev, uint32_t rec, uint32_t seg, uint32_t tail) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // interior chunks: fully inside the item -> 16j >= a and 16j+16 <= n+a
+    const uint32_t jf = (a + 15u) >> 4, jl = (n + a) >> 4;  // interior iff jf <= j < jl  (and j != 0)
+    uint32_t carry = 0;  // (t,q) bytes of the column before this step's first chunk: t | q<<8
+    uint4 tv = make_uint4(0, 0, 0, 0), q0 = tv, q1 = tv;
+    if (lane < nch) {
+        tv = ldg16(tbase + 16ull * lane);
+        q0 = ldg16(qbase + 16ull * lane);
+        if (q_two && lane + 1 <= q_last) q1 = ldg16(qbase + 16ull * (lane + 1));
+    }
+    for (uint32_t j0 = 0; j0 < nch; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool act = j < nch;
+        uint4 ntv = make_uint4(0, 0, 0, 0), nq0 = ntv, nq1 = ntv;
+        {
+            const uint32_t jn = j + 32;
+            if (jn < nch) {
+                ntv = ldg16(tbase + 16ull * jn);
+                nq0 = ldg16(qbase + 16ull * jn);
+                if (q_two && jn + 1 <= q_last) nq1 = ldg16(qbase + 16ull * (jn + 1));
+            }
+        }
+        uint32_t w0, w1, w2, w3, w4;
+        if (WS == 0) { w0 = q0.x; w1 = q0.y; w2 = q0.z; w3 = q0.w; w4 = q1.x; }
+        else if (WS == 1) { w0 = q0.y; w1 = q0.z; w2 = q0.w; w3 = q1.x; w4 = q1.y; }
+        else if (WS == 2) { w0 = q0.z; w1 = q0.w; w2 = q1.x; w3 = q1.y; w4 = q1.z; }
+        else { w0 = q0.w; w1 = q1.x; w2 = q1.y; w3 = q1.z; w4 = q1.w; }
+        const uint32_t sh = bs * 8;
+        const uint32_t qw0 = __funnelshift_r(w0, w1, sh), qw1 = __funnelshift_r(w1, w2, sh),
+                       qw2 = __funnelshift_r(w2, w3, sh), qw3 = __funnelshift_r(w3, w4, sh);
+        // last column of this chunk -> neighbour lane (previous column of the next chunk)
+        const uint32_t lastb = act ? ((tv.w >> 24) | ((qw3 >> 24) << 8)) : 0u;
+        uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, lastb, 1);
+        if (lane == 0) pb = carry;
+        carry = __shfl_sync(0xFFFFFFFFu, lastb, 31);
+        uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | (tv.w ^ qw3);
+        bool prev_ne = (pb & 0xFFu) != (pb >> 8);
+        if (CALLER) {
+            x |= has_zero_byte(tv.x ^ kGap4) | has_zero_byte(tv.y ^ kGap4) | has_zero_byte(tv.z ^ kGap4) |
+                 has_zero_byte(tv.w ^ kGap4);
+            prev_ne |= (pb & 0xFFu) == '-';
+        }
+        const bool edge = j == 0 || j < jf || j >= jl;
+        const bool slow = act && (edge || x != 0u || prev_ne);
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
+        if (mask) {
+            if (slow) {
+                const uint32_t slot = qn + __popc(mask & lt_mask);
+                Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
+                Q[4][slot] = qw0; Q[5][slot] = qw1; Q[6][slot] = qw2; Q[7][slot] = qw3;
+                Q[8][slot] = j == 0 ? first_prev : ((1u << 16) | pb);
+                uint32_t f0 = 0, t0 = 16, t1 = 16;
+                if (edge) {
+                    const int64_t lo = (int64_t)a - 16ll * j, hi = (int64_t)n + (int64_t)a - 16ll * j;
+                    f0 = clamp16(lo);
+                    t0 = clamp16(hi);
+                    t1 = clamp16(hi + (int64_t)tail);  // columns of the next item are context only
+                }
+                Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | ((seg == 0 ? 1u : 0u) << 15) | ((16u * j + 16u - a) << 16);
+                Q[10][slot] = item;
+                Q[11][slot] = rec;
+            }
+            qn += __popc(mask);
+            __syncwarp();
+            if (qn >= 32) {
+                walk_batch<MODE>(A, Q, 32, lane, E);
+                __syncwarp();
+                qn -= 32;
+                uint32_t mv[12];
+                if (lane < qn) {
+#pragma unroll
+                    for (int f = 0; f < 12; ++f) mv[f] = Q[f][lane + 32];
+                }
+                __syncwarp();
+                if (lane < qn) {
+#pragma unroll
+                    for (int f = 0; f < 12; ++f) Q[f][lane] = mv[f];
+                }
+                __syncwarp();
+            }
+        }
+        tv = ntv; q0 = nq0; q1 = nq1;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs A) {
     constexpr bool RUNS = MODE != MODE_STAT;
-    constexpr bool COUNTS = MODE == MODE_STAT || (MODE == MODE_RUNS_EXT && !EMIT);
-    __shared__ uint32_t s_queue[kWalkWarps][10][64];  // per warp: j, prev, t[4], q[4] (SoA, 64 slots)
+    __shared__ uint32_t s_queue[kWalkWarps][12][64];  // per warp, SoA, 64 slots
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t (*Q)[64] = s_queue[wid];
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint64_t n_warps = (uint64_t)gridDim.x * kWalkWarps;
+    uint32_t qn = 0;
+    WarpEmit E;
+    E.open_item = 0xFFFFFFFFu;
+    E.open_count = 0;
 
     for (uint64_t item = (uint64_t)blockIdx.x * kWalkWarps + wid; item < A.n_items; item += n_warps) {
         const uint4 *dp = reinterpret_cast<const uint4 *>(A.items + item);
-        const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+        const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
         const uint64_t t_off = ((uint64_t)d0.y << 32) | d0.x, q_off = ((uint64_t)d0.w << 32) | d0.z;
-        const uint32_t n = d1.x, rec = d1.y, seg = d1.z, single = d1.w;
-        const uint64_t c0 = (uint64_t)seg * kSeg;
-        const uint64_t ncols = A.ncols[rec];
+        const uint32_t n = d1.z, rec = d1.w, seg = d2.x, tail = d2.y;
         const uint8_t *tp = A.text + t_off;
         const uint8_t *qp = A.text + q_off;
         const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(tp) & 15u);
@@ -193,113 +321,39 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs 
         const uint8_t *qbase = qv - s;
         const uint32_t nch = (n + a + 15u) >> 4;
         const uint32_t q_last = (s + n + a - 1u) >> 4;  // last query vector holding a needed byte
-        const uint32_t ws = s >> 2, bs = s & 3u;
-
-        WalkAcc acc;
-        acc.cX = acc.cI = acc.cD = acc.eI = acc.eD = acc.nheads = 0;
-        acc.out = 0;
-        if (RUNS && EMIT) acc.out = A.run_base[item];
         // column preceding chunk 0 (only matters when a == 0; otherwise it sits inside chunk 0)
-        uint32_t carry_t = 0, carry_q = 0, first_prev = 0;
+        uint32_t first_prev = 0;
         if (a == 0 && seg > 0) first_prev = (1u << 16) | ((uint32_t)qp[-1] << 8) | (uint32_t)tp[-1];
-        uint32_t qn = 0;
+        const uint32_t it32 = (uint32_t)item;
+        switch (s >> 2) {
+            case 0: walk_item<MODE, 0>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, s != 0, a, n, nch, q_last, first_prev, rec, seg, tail); break;
+            case 1: walk_item<MODE, 1>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, true, a, n, nch, q_last, first_prev, rec, seg, tail); break;
+            case 2: walk_item<MODE, 2>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, true, a, n, nch, q_last, first_prev, rec, seg, tail); break;
+            default: walk_item<MODE, 3>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, true, a, n, nch, q_last, first_prev, rec, seg, tail); break;
+        }
+    }
+    if (qn) {
+        walk_batch<MODE>(A, Q, qn, lane, E);
+        __syncwarp();
+    }
+    if (RUNS && E.open_item != 0xFFFFFFFFu && lane == 0) A.item_nheads[E.open_item] = E.open_count;
+}
 
-        // software pipeline: vectors of step k+1 are requested before step k is examined
-        uint4 tv = make_uint4(0, 0, 0, 0), q0 = tv, q1 = tv;
-        {
-            const uint32_t j = lane;
-            if (j < nch) {
-                tv = ldg16(tbase + 16ull * j);
-                q0 = ldg16(qbase + 16ull * j);
-                if (s != 0 && j + 1 <= q_last) q1 = ldg16(qbase + 16ull * (j + 1));
-            }
-        }
-        for (uint32_t j0 = 0; j0 < nch; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            const bool act = j < nch;
-            uint4 ntv = make_uint4(0, 0, 0, 0), nq0 = ntv, nq1 = ntv;
-            {
-                const uint32_t jn = j + 32;
-                if (jn < nch) {
-                    ntv = ldg16(tbase + 16ull * jn);
-                    nq0 = ldg16(qbase + 16ull * jn);
-                    if (s != 0 && jn + 1 <= q_last) nq1 = ldg16(qbase + 16ull * (jn + 1));
-                }
-            }
-            uint32_t w5[5];
-            select5(q0, q1, ws, w5);
-            uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w}, qw[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) qw[k] = funnel_r_bytes(w5[k], w5[k + 1], bs);
-            // last column of this chunk -> neighbour lane (previous column of the next chunk)
-            const uint32_t tl = act ? (tw[3] >> 24) : 0u, ql = act ? (qw[3] >> 24) : 0u;
-            uint32_t pt = __shfl_up_sync(0xFFFFFFFFu, tl, 1), pq = __shfl_up_sync(0xFFFFFFFFu, ql, 1);
-            if (lane == 0) { pt = carry_t; pq = carry_q; }
-            carry_t = __shfl_sync(0xFFFFFFFFu, tl, 31);
-            carry_q = __shfl_sync(0xFFFFFFFFu, ql, 31);
-            uint32_t x = (tw[0] ^ qw[0]) | (tw[1] ^ qw[1]) | (tw[2] ^ qw[2]) | (tw[3] ^ qw[3]);
-            bool prev_ne = pt != pq;
-            if (CALLER) {
-                x |= has_zero_byte(tw[0] ^ kGap4) | has_zero_byte(tw[1] ^ kGap4) | has_zero_byte(tw[2] ^ kGap4) |
-                     has_zero_byte(tw[3] ^ kGap4);
-                prev_ne |= pt == '-';
-            }
-            const bool interior = 16u * j >= a && 16u * j + 16u <= n + a;
-            const bool slow = act && (j == 0 || !interior || x != 0u || prev_ne);
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
-            if (mask) {
-                if (slow) {
-                    const uint32_t slot = qn + __popc(mask & lt_mask);
-                    Q[0][slot] = j;
-                    Q[1][slot] = j == 0 ? first_prev : ((1u << 16) | (pq << 8) | pt);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { Q[2 + k][slot] = tw[k]; Q[6 + k][slot] = qw[k]; }
-                }
-                qn += __popc(mask);
-                __syncwarp();
-                if (qn >= 32) {
-                    walk_batch<MODE, EMIT>(A, Q, 32, lane, a, n, c0, ncols, rec, acc);
-                    __syncwarp();
-                    qn -= 32;
-                    uint32_t mv[10];
-                    if (lane < qn) {
-#pragma unroll
-                        for (int f = 0; f < 10; ++f) mv[f] = Q[f][lane + 32];
-                    }
-                    __syncwarp();
-                    if (lane < qn) {
-#pragma unroll
-                        for (int f = 0; f < 10; ++f) Q[f][lane] = mv[f];
-                    }
-                    __syncwarp();
-                }
-            }
-            tv = ntv; q0 = nq0; q1 = nq1;
-        }
-        if (qn) {
-            walk_batch<MODE, EMIT>(A, Q, qn, lane, a, n, c0, ncols, rec, acc);
-            __syncwarp();
-        }
-        if (COUNTS) {
-            uint32_t cX = warp_sum(acc.cX), cI = warp_sum(acc.cI), cD = warp_sum(acc.cD), eI = warp_sum(acc.eI),
-                     eD = warp_sum(acc.eD);
-            if (lane == 0) {
-                unsigned long long *c = A.rec_cnt + (uint64_t)rec * 5;
-                if (single) {
-                    c[0] = cX; c[1] = eI; c[2] = cI; c[3] = eD; c[4] = cD;
-                } else {
-                    if (cX) atomicAdd(c + 0, (unsigned long long)cX);
-                    if (eI) atomicAdd(c + 1, (unsigned long long)eI);
-                    if (cI) atomicAdd(c + 2, (unsigned long long)cI);
-                    if (eD) atomicAdd(c + 3, (unsigned long long)eD);
-                    if (cD) atomicAdd(c + 4, (unsigned long long)cD);
-                }
-            }
-        }
-        if (RUNS && !EMIT) {
-            uint32_t nh = warp_sum(acc.nheads);
-            if (lane == 0) A.item_nheads[item] = nh;
-        }
+// sparse: item slot regions -> dense run arrays (run_base = exclusive scan of item_nheads)
+__global__ void k_runs_compact(uint64_t n_items, const ItemDesc *__restrict__ items, const uint32_t *__restrict__ item_nheads,
+                               const uint64_t *__restrict__ run_base, const uint32_t *__restrict__ slots,
+                               uint64_t *__restrict__ run_pos, uint32_t *__restrict__ run_rec, uint8_t *__restrict__ run_cls) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= n_items) return;
+    const ItemDesc d = items[warp];
+    const uint32_t nh = item_nheads[warp];
+    const uint64_t rb = run_base[warp], c0 = (uint64_t)d.seg * kSeg;
+    for (uint32_t i = lane; i < nh; i += 32) {
+        uint32_t e = slots[d.slot_base + i];
+        run_pos[rb + i] = c0 + (e >> 3);
+        run_rec[rb + i] = d.rec;
+        run_cls[rb + i] = (uint8_t)(e & 7u);
     }
 }
 

@@ -289,24 +289,7 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
     if (sc[1] != kNoErr) return resolve_error(ctx, *P, sc[1], qname);
     ctx->n_items = sc[0];
     P->total_cols = sc[2];
-    if (ctx->n_items) {
-        P->items = ctx->buf<ItemDesc>(B_ITEM_REC, ctx->n_items);
-        if (!P->items) return ctx->err_code;
-        LAUNCH(ctx, k_fill_item_desc, grid_for(n_rec, 256), 256, n_rec, rc.n_items, P->item_base, rc.t_off, rc.q_off, rc.ncols,
-               P->items);
-    }
     return WGA_OK;
-}
-
-WalkArgs walk_args(wga_ctx *ctx, const Prep &P, unsigned long long *rec_cnt) {
-    WalkArgs A;
-    memset(&A, 0, sizeof A);
-    A.text = ctx->d_text;
-    A.items = P.items;
-    A.ncols = P.rc.ncols;
-    A.n_items = ctx->n_items;
-    A.rec_cnt = rec_cnt;
-    return A;
 }
 
 unsigned walk_grid(wga_ctx *ctx, uint64_t n_items) {  // persistent warps: kWalkCtasPerSm CTAs per SM
@@ -320,20 +303,75 @@ void walk_begin(wga_ctx *ctx) {
     ctx->walk_bytes = 0;
     ctx->walk_launches = 0;
 }
-template <class F>
-int timed_walk(wga_ctx *ctx, const Prep &P, F &&launch) {
-    WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    launch();
-    WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->walk_launches++;
-    ctx->walk_bytes += 2 * P.total_cols + 32 * ctx->n_items;
-    return WGA_OK;
-}
-int walk_collect(wga_ctx *ctx, float *acc) {  // call after a sync that covers ev1
-    float ms = 0.f;
-    WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    *acc += ms;
-    return WGA_OK;
+
+struct Runs {
+    uint64_t n_runs = 0;
+    uint64_t *run_base = nullptr, *run_pos = nullptr;
+    uint32_t *run_rec = nullptr;
+    uint8_t *run_cls = nullptr;
+};
+
+// the dense pass: one k_walk launch (timed with CUDA events on the ctx stream); for the RUNS modes the item slot
+// regions are compacted into dense run arrays afterwards.  rec_cnt must be zeroed by the caller.
+template <int MODE>
+int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
+    constexpr bool RUNS = MODE != MODE_STAT;
+    const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
+    P.items = ctx->buf<ItemDesc>(B_ITEM_REC, n_items);
+    uint32_t *nheads = ctx->buf<uint32_t>(B_ITEM_NHEADS, n_items + 1);
+    uint32_t *ovf = ctx->buf<uint32_t>(B_SCALARS, 16);
+    if (!P.items || !nheads || !ovf) return ctx->err_code;
+    for (uint32_t shift = 3;; shift = 0) {
+        uint64_t *slot_base = nullptr;
+        uint32_t *slots = nullptr;
+        if (RUNS) {
+            uint64_t *need = ctx->buf<uint64_t>(B_GEN_H, n_rec + 1);
+            slot_base = ctx->buf<uint64_t>(B_RUN_BASE, n_rec + 1);
+            if (!need || !slot_base) return ctx->err_code;
+            LAUNCH(ctx, k_rec_slot_need, grid_for(n_rec + 1, 256), 256, n_rec, P.rc.n_items, P.rc.ncols, shift, need);
+            WGA_TRY(exclusive_sum(ctx, need, slot_base, n_rec + 1));
+            uint64_t total;
+            WGA_TRY(read_scalars(ctx, {slot_base + n_rec}, &total));
+            slots = ctx->buf<uint32_t>(B_PAF_B, total + 1);
+            if (!slots) return ctx->err_code;
+        }
+        LAUNCH(ctx, k_fill_item_desc, grid_for(n_rec, 256), 256, n_rec, P.rc.n_items, P.item_base, P.rc.t_off, P.rc.q_off,
+               P.rc.ncols, (const uint64_t *)slot_base, shift, P.items);
+        WGA_CK(cudaMemsetAsync(nheads, 0, (n_items + 1) * 4, ctx->stream));
+        WGA_CK(cudaMemsetAsync(ovf, 0, 4, ctx->stream));
+        WalkArgs A;
+        A.text = ctx->d_text; A.items = P.items; A.n_items = n_items; A.rec_cnt = rec_cnt;
+        A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf;
+        auto kern = k_walk<MODE>;
+        WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        LAUNCH(ctx, kern, walk_grid(ctx, n_items), kWalkThreads, A);
+        WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->walk_launches++;
+        ctx->walk_bytes += 2 * P.total_cols + 48 * n_items;
+        if (!RUNS) return WGA_OK;  // caller collects the event time after its next sync
+        R->run_base = ctx->buf<uint64_t>(B_GEN_H, n_items + 1);
+        if (!R->run_base) return ctx->err_code;
+        WGA_TRY(exclusive_sum(ctx, nheads, R->run_base, n_items + 1));
+        uint64_t sc[2];
+        WGA_TRY(read_scalars(ctx, {R->run_base + n_items, ovf}, sc));
+        float ms = 0.f;
+        WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->walk_ms += ms;
+        if ((uint32_t)sc[1]) {  // some item has more run heads than n/8+16: redo with worst-case capacity
+            if (shift == 0) { ctx->set_error(WGA_E_INTERNAL, 0, "run slot overflow at full capacity"); return WGA_E_INTERNAL; }
+            if (rec_cnt) WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
+            continue;
+        }
+        const uint64_t n_runs = sc[0];
+        R->n_runs = ctx->n_runs = n_runs;
+        R->run_pos = ctx->buf<uint64_t>(B_RUN_POS, n_runs + 1);
+        R->run_rec = ctx->buf<uint32_t>(B_RUN_REC, n_runs + 1);
+        R->run_cls = ctx->buf<uint8_t>(B_RUN_CLS, n_runs + 1);
+        if (!R->run_pos || !R->run_rec || !R->run_cls) return ctx->err_code;
+        LAUNCH(ctx, k_runs_compact, grid_for(n_items * 32, 256), 256, n_items, P.items, nheads, R->run_base, slots, R->run_pos,
+               R->run_rec, R->run_cls);
+        return WGA_OK;
+    }
 }
 
 // hand the command's output back in the caller's memory kind
@@ -451,35 +489,21 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     if (n_rec == 0 || n_items == 0) return sync_check(ctx);
 
     unsigned long long *rec_cnt = ctx->buf<unsigned long long>(B_REC_CNT, n_rec * 5);
-    uint32_t *nheads = ctx->buf<uint32_t>(B_ITEM_NHEADS, n_items + 1);
-    uint64_t *run_base = ctx->buf<uint64_t>(B_RUN_BASE, n_items + 1);
-    if (!rec_cnt || !nheads || !run_base) return ctx->err_code;
+    if (!rec_cnt) return ctx->err_code;
     WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
-    WGA_CK(cudaMemsetAsync(nheads + n_items, 0, 4, ctx->stream));
-    WalkArgs A = walk_args(ctx, P, rec_cnt);
-    A.item_nheads = nheads;
-    const unsigned wgrid = walk_grid(ctx, n_items);
-    auto kw_count = k_walk<MODE_RUNS_EXT, false>;
-    auto kw_emit = k_walk<MODE_RUNS_EXT, true>;
-    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_count, wgrid, kWalkThreads, A); }));
-    WGA_TRY(exclusive_sum(ctx, nheads, run_base, n_items + 1));
-    uint64_t n_runs;
-    WGA_TRY(read_scalars(ctx, {run_base + n_items}, &n_runs));
-    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
-    ctx->n_runs = n_runs;
-
-    uint64_t *run_pos = ctx->buf<uint64_t>(B_RUN_POS, n_runs + 1), *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
-    uint32_t *run_rec = ctx->buf<uint32_t>(B_RUN_REC, n_runs + 1), *run_dl = ctx->buf<uint32_t>(B_RUN_DL, n_runs + 1);
-    uint8_t *run_cls = ctx->buf<uint8_t>(B_RUN_CLS, n_runs + 1);
+    Runs RU;
+    WGA_TRY(run_walk<MODE_RUNS_EXT>(ctx, P, rec_cnt, &RU));
+    const uint64_t n_runs = RU.n_runs;
+    uint64_t *run_base = RU.run_base, *run_pos = RU.run_pos;
+    uint32_t *run_rec = RU.run_rec;
+    uint8_t *run_cls = RU.run_cls;
+    uint64_t *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
+    uint32_t *run_dl = ctx->buf<uint32_t>(B_RUN_DL, n_runs + 1);
     uint64_t *cig_off = ctx->buf<uint64_t>(B_RUN_CIGOFF, n_runs + 1);
     uint64_t *rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
     uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
     uint32_t *row_fixed = ctx->buf<uint32_t>(B_ROW_FIXED, n_rec + 1);
-    if (!run_pos || !run_len || !run_rec || !run_dl || !run_cls || !cig_off || !rec_run_first || !row_len || !row_off ||
-        !row_fixed)
-        return ctx->err_code;
-    A.run_base = run_base; A.run_pos = run_pos; A.run_rec = run_rec; A.run_cls = run_cls;
-    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_emit, wgrid, kWalkThreads, A); }));
+    if (!run_len || !run_dl || !cig_off || !rec_run_first || !row_len || !row_off || !row_fixed) return ctx->err_code;
     LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, run_base, n_items, n_runs, rec_run_first);
     LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, run_pos, run_rec, P.rc.ncols, run_len, run_dl);
     WGA_TRY(exclusive_sum(ctx, run_dl, cig_off, n_runs + 1));
@@ -491,7 +515,6 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
     WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
-    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
     char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_out) return ctx->err_code;
     R.out = d_out;
@@ -694,11 +717,7 @@ int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
     if (!rec_cnt || !cnt11) return ctx->err_code;
     WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
-    if (n_items) {
-        WalkArgs A = walk_args(ctx, P, rec_cnt);
-        auto kw_stat = k_walk<MODE_STAT, false>;
-        WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_stat, walk_grid(ctx, n_items), kWalkThreads, A); }));
-    }
+    if (n_items) WGA_TRY(run_walk<MODE_STAT>(ctx, P, rec_cnt, nullptr));
     LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
     RecMeta M;
     M.text = ctx->d_text;
@@ -713,7 +732,11 @@ int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     M.neg = P.rc.neg; M.skip = P.rc.skip;
     int rc = stat_reduce(ctx, n_rec, M, cnt11, P.err_key, acc);
     if (rc) return rc;
-    if (ctx->walk_launches) WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
+    if (ctx->walk_launches) {
+        float ms = 0.f;
+        WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->walk_ms += ms;
+    }
     ctx->last_counts_valid = true;
     return WGA_OK;
 }
@@ -772,33 +795,18 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (n_rec == 0 || n_items == 0) return sync_check(ctx);
 
     // dense pass: caller-classified run list
-    uint32_t *nheads = ctx->buf<uint32_t>(B_ITEM_NHEADS, n_items + 1);
-    uint64_t *run_base = ctx->buf<uint64_t>(B_RUN_BASE, n_items + 1);
-    if (!nheads || !run_base) return ctx->err_code;
-    WGA_CK(cudaMemsetAsync(nheads + n_items, 0, 4, ctx->stream));
-    WalkArgs A = walk_args(ctx, P, nullptr);
-    A.item_nheads = nheads;
-    const unsigned wgrid = walk_grid(ctx, n_items);
-    auto kw_count = k_walk<MODE_RUNS_CALLER, false>;
-    auto kw_emit = k_walk<MODE_RUNS_CALLER, true>;
-    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_count, wgrid, kWalkThreads, A); }));
-    WGA_TRY(exclusive_sum(ctx, nheads, run_base, n_items + 1));
-    uint64_t n_runs;
-    WGA_TRY(read_scalars(ctx, {run_base + n_items}, &n_runs));
-    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
-    ctx->n_runs = n_runs;
-    uint64_t *run_pos = ctx->buf<uint64_t>(B_RUN_POS, n_runs + 1), *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
-    uint32_t *run_rec = ctx->buf<uint32_t>(B_RUN_REC, n_runs + 1);
-    uint8_t *run_cls = ctx->buf<uint8_t>(B_RUN_CLS, n_runs + 1);
+    Runs RU;
+    WGA_TRY(run_walk<MODE_RUNS_CALLER>(ctx, P, nullptr, &RU));
+    const uint64_t n_runs = RU.n_runs;
+    uint64_t *run_base = RU.run_base, *run_pos = RU.run_pos;
+    uint32_t *run_rec = RU.run_rec;
+    uint8_t *run_cls = RU.run_cls;
+    uint64_t *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
     uint64_t *rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
     uint64_t *tcon = ctx->buf<uint64_t>(B_GEN_A, n_runs + 1), *qcon = ctx->buf<uint64_t>(B_GEN_B, n_runs + 1);
     uint64_t *St = ctx->buf<uint64_t>(B_GEN_C, n_runs + 1), *Sq = ctx->buf<uint64_t>(B_GEN_D, n_runs + 1);
     uint64_t *nchunks = ctx->buf<uint64_t>(B_GEN_E, n_rec + 1), *rec_chunk_first = ctx->buf<uint64_t>(B_GEN_F, n_rec + 1);
-    if (!run_pos || !run_len || !run_rec || !run_cls || !rec_run_first || !tcon || !qcon || !St || !Sq || !nchunks ||
-        !rec_chunk_first)
-        return ctx->err_code;
-    A.run_base = run_base; A.run_pos = run_pos; A.run_rec = run_rec; A.run_cls = run_cls;
-    WGA_TRY(timed_walk(ctx, P, [&] { LAUNCH(ctx, kw_emit, wgrid, kWalkThreads, A); }));
+    if (!run_len || !rec_run_first || !tcon || !qcon || !St || !Sq || !nchunks || !rec_chunk_first) return ctx->err_code;
     LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, run_base, n_items, n_runs, rec_run_first);
     LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, run_pos, run_rec, P.rc.ncols, run_len, (uint32_t *)nullptr);
     LAUNCH(ctx, k_run_contrib, grid_for(n_runs + 1, 256), 256, n_runs, run_cls, run_len, tcon, qcon);
@@ -810,7 +818,6 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     WGA_TRY(exclusive_sum(ctx, nchunks, rec_chunk_first, n_rec + 1));
     uint64_t n_chunks;
     WGA_TRY(read_scalars(ctx, {rec_chunk_first + n_rec}, &n_chunks));
-    WGA_TRY(walk_collect(ctx, &ctx->walk_ms));
     uint64_t *chunk_cs = ctx->buf<uint64_t>(B_GEN_G, n_chunks + 1);
     uint32_t *chunk_rec = ctx->buf<uint32_t>(B_PT_FLAG, n_chunks + 1), *chunk_inv = ctx->buf<uint32_t>(B_PT_IDX, n_chunks + 1);
     uint64_t *inv_cum = ctx->buf<uint64_t>(B_INV_IDX, n_chunks + 1);
