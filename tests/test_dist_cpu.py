@@ -1,0 +1,93 @@
+"""world_size-2 gloo test of the only exchange step of the path: the stat counter all-reduce
+(wgatools_b200/dist.py).  The per-rank partial tables are built from the oracle's per-record counters (no GPU
+here); the merged TSV must equal the oracle's stat of the whole file, including the order-dependent f32
+inv_size."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _partial_blob(text: bytes):
+    """emulates what wga_maf_stat leaves in a StatAcc for one shard (merged mode)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    from wgatools_b200 import dist as wd
+    lines = text.split(b"\n")[1:]
+    recs, cur = [], []
+    for l in lines:
+        if l.startswith(b"s"):
+            cur.append(l.split())
+        elif cur:
+            recs.append(cur)
+            cur = []
+    if cur:
+        recs.append(cur)
+    cnt = orc.maf_record_counts(text, len(recs))
+    keys, index, vals, inv_pair, inv_num = [], {}, [], [], []
+    for r, c in zip(recs, cnt):
+        t, q = r[0], r[1]
+        rs, qs = int(t[5]), int(q[5])
+        key = (t[1], rs, q[1], qs)
+        neg = q[4] == b"-"
+        qstart = qs - int(q[2]) - int(q[3]) if neg else int(q[2])
+        if key not in index:
+            index[key] = len(keys)
+            keys.append(key)
+            vals.append([0] * 11 + [rs, qs])
+        v = vals[index[key]]
+        for i in range(11):
+            v[i] += c[i]
+        v[11] = min(v[11], int(t[2]))
+        v[12] = min(v[12], qstart)
+        if neg:
+            inv_pair.append(index[key])
+            inv_num.append(2 * (c[0] + c[1]) + c[5] + c[9] + c[3] + c[7])
+    return wd.build_blob(0, keys, np.array(vals, dtype=np.uint64).reshape(len(keys), 13), np.zeros(len(keys), np.float32),
+                         np.array(inv_pair, dtype=np.uint32), np.array(inv_num, dtype=np.uint64))
+
+
+def _worker(rank, world, port, shards, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import wgatools_b200 as w
+    from wgatools_b200 import dist as wd
+    acc = w.StatAcc(False)
+    acc.import_(_partial_blob(shards[rank]))
+    merged = wd.allreduce_stat(acc, dist)
+    q.put((rank, merged.write()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stat_allreduce_gloo_world2():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as g
+    g.build()
+    import bench_support as bs
+    import oracle_lib as orc
+    text = bs.gen_maf(bs.maf_params(600, seed=77, p_neg=0.45))
+    # shard at an s-line-group boundary; the second shard gets a dummy first line (only rank 0 has the header)
+    cut = text.find(b"\n\n", len(text) // 2) + 2
+    shards = [text[:cut], b"#shard\n" + text[cut:]]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, shards, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    outs = dict(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = orc.stat_maf(text)
+    assert outs[0] == want and outs[1] == want
