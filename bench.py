@@ -103,38 +103,24 @@ def cpu_sample_len(host_ptr, nbytes, want, L=None):
 
 
 def run_cpu(host_ptr, nbytes, sample_bytes, threads, do_call=True):
-    """times the oracle (port of the reference algorithm) on text[0:sample]; threads>1 shards the sample into
-    contiguous ranges of whole blocks, one process-thread each (ctypes releases the GIL)."""
+    """times the CPU port of the reference on text[0:sample] with the reference's own parallel structure at
+    `-t threads`: maf2paf and stat pull records from a serial reader (par_bridge, src/converter.rs:41-48,
+    src/tools/stat.rs:67-81) into a worker pool; call is strictly sequential (src/tools/caller.rs:62)."""
     import oracle_lib as orc
     orc.lib()
     n = cpu_sample_len(host_ptr, nbytes, int(sample_bytes))
     text = ctypes.string_at(host_ptr, n)
-    cuts = [0]
-    for i in range(1, threads):
-        p = text.find(b"\n\n", n * i // threads)
-        cuts.append(p + 2 if p >= 0 else n)
-    cuts.append(n)
-    shards = []
-    for i in range(threads):
-        s = text[cuts[i]:cuts[i + 1]]
-        if i > 0:
-            s = b"#shard\n" + s  # MAFReader::new swallows the first line of every shard
-        shards.append(s)
-
-    def work(s):
-        orc.maf2paf(s)
-        orc.stat_maf(s)
-        if do_call:
-            orc.call_maf(s, snp=True, svlen=0)
-
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(s,)) for s in shards if len(s) > 8]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
+    orc.maf2paf_mt(text, threads)
+    orc.stat_maf_mt(text, threads)
+    if do_call:
+        orc.call_maf(text, snp=True, svlen=0)
     dt = time.perf_counter() - t0
     return n / dt / 1e9, n, dt
+
+
+CPU_KIND_NOTE = ("C restatement of the reference algorithm (Rust toolchain unavailable) with the reference's rayon "
+                 "structure: serial record reader feeding a worker pool for maf2paf/stat, sequential call")
 
 
 def main():
@@ -157,8 +143,11 @@ def main():
         import __graft_entry__ as g
         g.build()
         cores = os.cpu_count() or 1
-        # bounded sample: a few hundred MB per step so that K+W steps end within minutes
-        sample_blocks = max(1000, min(args.blocks, int(os.environ.get("WGA_REF_BLOCKS", 8000 * cores))))
+        # bounded sample: sized so that the whole (warmup + steps) run ends within ~2-3 minutes at the ~0.15 GB/s
+        # the three commands reach together (the sequential `call` dominates)
+        budget_s = 150.0 / max(args.warmup + args.steps, 1)
+        sample_mb = min(1500.0, max(40.0, budget_s * 150.0))
+        sample_blocks = max(1000, min(args.blocks, int(sample_mb * 1e6 / 6700)))
 
         def alloc(n):
             a = np.empty(n, dtype=np.uint8)
@@ -177,8 +166,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
                                  "sample": f"{sample_blocks} blocks ({nbytes / 1e6:.0f} MB) of the same generator per step; "
-                                           "C restatement of the reference algorithm (Rust toolchain unavailable), "
-                                           f"{cores} threads over contiguous block ranges"},
+                                           + CPU_KIND_NOTE + f", -t {cores}"},
                 "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -309,11 +297,11 @@ def main():
             "input_bytes_per_gpu": nbytes, "columns_per_gpu": ncols, "gen_seconds": t_gen}
     if rank == 0:
         if world == 1:
-            cores = 1
+            cores = os.cpu_count() or 1
             gbs, n, dt = run_cpu(host_ptr, nbytes, args.cpu_sample_mb * 1e6, cores, do_call)
             line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
-                                    "sample": f"first {n / 1e6:.0f} MB of the same MAF ({dt:.1f} s), oracle = C restatement of "
-                                              "the reference algorithm, single thread (the reference default -t 1)"}
+                                    "sample": f"first {n / 1e6:.0f} MB of the same MAF ({dt:.1f} s); " + CPU_KIND_NOTE
+                                              + f", -t {cores}"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

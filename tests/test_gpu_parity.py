@@ -353,3 +353,23 @@ def test_dense_whitespace_falls_back_to_exact_index(w, ctx):
     check_call(w, ctx, text, snp=True, svlen=0)
     big = bs.gen_maf(bs.maf_params(300, seed=5)) + b"\n" * 9000 + b"a\n" + b"\n".join(blk) + b"\n"
     check_both(w, ctx, big)
+
+
+def test_cli_matches_oracle(w, ctx, tmp_path):
+    import subprocess
+    import sys
+    maf = tmp_path / "in.maf"
+    text = bs.gen_maf(bs.maf_params(120, seed=9, p_neg=0.2))
+    maf.write_bytes(text)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    def run(*args):
+        return subprocess.run([sys.executable, "-m", "wgatools_b200", *args], cwd=root, capture_output=True)
+    r = run("m2p", str(maf))
+    assert r.returncode == 0 and r.stdout == orc.maf2paf(text)
+    out = tmp_path / "o.tsv"
+    assert run("-o", str(out), "st", str(maf)).returncode == 0 and out.read_bytes() == orc.stat_maf(text)
+    assert run("-o", str(out), "st", str(maf)).returncode == 1  # refuses to overwrite without -r
+    r = run("c", str(maf), "-s", "-l", "0", "-n", "hg1")
+    assert r.returncode == 0 and r.stdout == orc.call_maf(text, snp=True, svlen=0, sample="hg1")
+    r = run("m2p", str(maf), "-q", "nope")
+    assert r.returncode == 1 and b"Query name:nope not found in MAF" in r.stderr

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_DIR, "libwga_b200.so")
+SO_PATH = os.environ.get("WGA_B200_LIB") or os.path.join(_DIR, "libwga_b200.so")  # override: A/B builds
 
 WGA_MEM_HOST, WGA_MEM_DEVICE = 0, 1
 WGA_F_FIRST_SLAB = 1

@@ -236,13 +236,36 @@ struct RowOut {
     }
 };
 
-// one VCF body row.  PASS 0: row_len[row] = bytes; PASS 1: write at row_off[row]
+constexpr int kVcfThreads = 128;
+constexpr int kVcfSpan = 6144;  // bytes of output one warp (32 consecutive rows) may stage in shared memory
+
+// one VCF body row per thread.  PASS 0: row_len[row] = bytes.  PASS 1: the 32 rows of a warp are consecutive in
+// the output, so they are formatted into one shared-memory span and copied out with aligned word stores
+// (a span longer than kVcfSpan -- long SV rows -- is written directly).
 template <int PASS>
-__global__ void k_vcf_rows(CallView V, uint64_t n_rows, const uint64_t *__restrict__ rowbase, uint64_t *__restrict__ row_len,
-                           const uint64_t *__restrict__ row_off, char *__restrict__ out, unsigned long long *err_key) {
+__global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n_rows, const uint64_t *__restrict__ rowbase,
+                                                          uint64_t *__restrict__ row_len, const uint64_t *__restrict__ row_off,
+                                                          char *__restrict__ out, unsigned long long *err_key) {
+    __shared__ __align__(16) char s_span[PASS == 1 ? kVcfThreads / 32 : 1][PASS == 1 ? kVcfSpan + 16 : 16];
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row > n_rows) return;
-    if (row == n_rows) { if (PASS == 0) row_len[row] = 0; return; }
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t span_lo = 0, span_hi = 0;
+    bool staged = false;
+    if (PASS == 1) {
+        const uint64_t first = row - lane;
+        if (first < n_rows) {
+            const uint64_t lastp1 = first + 32 < n_rows ? first + 32 : n_rows;
+            span_lo = row_off[first];
+            span_hi = row_off[lastp1];
+            staged = span_hi - span_lo <= (uint64_t)kVcfSpan;
+        }
+    }
+    if (PASS == 0) {
+        if (row > n_rows) return;
+        if (row == n_rows) { row_len[row] = 0; return; }
+    }
+    const bool have_row = row < n_rows;
+    if (have_row) {
     // run owning this row: last j with rowbase[j] <= row
     uint64_t lo = 0, hi = V.n_runs;
     while (hi - lo > 1) { uint64_t m = (lo + hi) >> 1; if (rowbase[m] <= row) lo = m; else hi = m; }
@@ -284,7 +307,8 @@ __global__ void k_vcf_rows(CallView V, uint64_t n_rows, const uint64_t *__restri
     const bool neg = V.neg[rec];
     const uint64_t t_start = V.sl.start[tl], q_raw = V.sl.start[ql], q_size = V.sl.src[ql];
     RowOut R;
-    R.o = PASS == 1 ? out + row_off[row] : nullptr;
+    R.o = nullptr;
+    if (PASS == 1) R.o = staged ? s_span[threadIdx.x >> 5] + (span_lo & 3u) + (row_off[row] - span_lo) : out + row_off[row];
     R.n = 0;
     R.bad_base = false;
     R.bytes(V.text + V.sl.name_off[tl], V.sl.name_len[tl]);
@@ -367,6 +391,26 @@ __global__ void k_vcf_rows(CallView V, uint64_t n_rows, const uint64_t *__restri
     if (PASS == 0) {
         row_len[row] = R.n;
         if (R.bad_base) atomicMin(err_key, (unsigned long long)((V.rec_run_first[rec] /*stable per record*/ << 8) | WGA_E_VCF_BASE));
+    }
+    }  // have_row
+    if (PASS == 1) {
+        __syncwarp();
+        if (staged) {
+            const char *sp = s_span[threadIdx.x >> 5];
+            const uint32_t al = (uint32_t)(span_lo & 3u);
+            const uint64_t nbytes = span_hi - span_lo;
+            char *gbase = out + (span_lo - al);            // 4-byte aligned (out comes from cudaMalloc)
+            const uint64_t nwords = (al + nbytes + 3) >> 2;
+            for (uint64_t wi = lane; wi < nwords; wi += 32) {
+                const uint64_t b0 = wi * 4;
+                if (b0 >= al && b0 + 4 <= al + nbytes) {
+                    *reinterpret_cast<uint32_t *>(gbase + b0) = *reinterpret_cast<const uint32_t *>(sp + b0);
+                } else {
+                    for (uint64_t b = b0; b < b0 + 4; ++b)
+                        if (b >= al && b < al + nbytes) gbase[b] = sp[b];
+                }
+            }
+        }
     }
 }
 

@@ -143,17 +143,15 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_ws_scan(const uint8_t *__res
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint64_t off = base + (uint64_t)k * 512 + lane * 16;
-            const int64_t rem = (int64_t)len - (int64_t)off;
-            uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, ws[4], nl[4];
-            uint32_t c = 0;
+            uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, ws[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t valid = rem >= 4 * (i + 1) ? kHi : (rem > 4 * i ? range_flags(0, (int)(rem - 4 * i)) : 0u);
-                ws[i] = ws_bytes(w[i]) & valid;
-                nl[i] = nl_bytes(w[i]) & valid;
-                c += __popc(ws[i]);
-                cn += __popc(nl[i]);
+            for (int i = 0; i < 4; ++i) ws[i] = ws_bytes(w[i]);
+            if (off + 16 > len) {  // the vector straddles the end of the text: mask the bytes past it
+                const int64_t rem = (int64_t)len - (int64_t)off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ws[i] &= rem > 4 * i ? range_flags(0, (int)(rem - 4 * i)) : 0u;
             }
+            const uint32_t c = __popc(ws[0]) + __popc(ws[1]) + __popc(ws[2]) + __popc(ws[3]);
             if (__ballot_sync(0xFFFFFFFFu, c != 0)) {
                 uint32_t tot;
                 uint32_t idx = cw + warp_excl_scan(c, &tot);
@@ -163,8 +161,11 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_ws_scan(const uint8_t *__res
                     while (m) {
                         int bit = __ffs(m) - 1;
                         m &= m - 1;
-                        uint32_t rel = (uint32_t)k * 512u + lane * 16u + 4u * i + (uint32_t)(bit >> 3);
-                        if (idx < (uint32_t)kTokCap) slot[idx] = (uint16_t)(rel | (((nl[i] >> bit) & 1u) << 15));
+                        const uint32_t byte = (uint32_t)(bit >> 3);
+                        const uint32_t isnl = ((w[i] >> (8 * byte)) & 0xFFu) == 0x0Au;  // newline among the whitespace
+                        const uint32_t rel = (uint32_t)k * 512u + lane * 16u + 4u * i + byte;
+                        if (idx < (uint32_t)kTokCap) slot[idx] = (uint16_t)(rel | (isnl << 15));
+                        cn += isnl;
                         ++idx;
                     }
                 }

@@ -27,7 +27,10 @@ namespace wga {
 enum { MODE_STAT = 0, MODE_RUNS_EXT = 1, MODE_RUNS_CALLER = 2 };
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
-constexpr int kWalkCtasPerSm = 3;
+#ifndef WGA_WALK_CTAS
+#define WGA_WALK_CTAS 3
+#endif
+constexpr int kWalkCtasPerSm = WGA_WALK_CTAS;
 constexpr int kQWords = 14;  // queue entry: t[4] q[4] prev meta item rec col_lo col_hi
 constexpr uint32_t kSlotPad = 16;
 
@@ -48,6 +51,7 @@ struct WalkArgs {
     uint32_t *slots;              // run-head slots
     uint32_t cap_shift;           // slot capacity of an item = (n >> cap_shift) + kSlotPad
     uint32_t *overflow;
+    unsigned int *sched;          // dynamic work counter (zero-initialised)
 };
 
 __device__ __host__ __forceinline__ uint64_t slot_cap(uint64_t n, uint32_t shift) { return (n >> shift) + kSlotPad; }
@@ -203,95 +207,121 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
     }
 }
 
-// one item: stream its chunks, push the slow ones.  WS = word part of the query misalignment.
-template <int MODE, int WS>
-__device__ __forceinline__ void walk_item(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane,
-                                          uint32_t item, const uint8_t *tbase, const uint8_t *qbase, uint32_t bs,
-                                          bool q_two, uint32_t a, uint32_t n, uint32_t nch, uint32_t q_last,
-                                          uint32_t first_prev, uint32_t rec, uint32_t seg, uint32_t tail) {
-    constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    // interior chunks: fully inside the item -> 16j >= a and 16j+16 <= n+a
-    const uint32_t jf = (a + 15u) >> 4, jl = (n + a) >> 4;  // interior iff jf <= j < jl  (and j != 0)
-    uint32_t carry = 0;  // (t,q) bytes of the column before this step's first chunk: t | q<<8
-    uint4 tv = make_uint4(0, 0, 0, 0), q0 = tv, q1 = tv;
-    if (lane < nch) {
-        tv = ldg16(tbase + 16ull * lane);
-        q0 = ldg16(qbase + 16ull * lane);
-        if (q_two && lane + 1 <= q_last) q1 = ldg16(qbase + 16ull * (lane + 1));
+// geometry of one work item in the 16-byte frame of its target stream
+struct Geom {
+    const uint8_t *tbase, *qbase;  // 16-byte aligned; chunk j covers item columns [16j-a, 16j-a+16)
+    uint32_t a, s, n, nch, q_last, rec, seg, tail, item, first_prev;
+};
+
+__device__ __forceinline__ Geom make_geom(const WalkArgs &A, const uint4 &d0, const uint4 &d1, const uint4 &d2, uint32_t item) {
+    Geom g;
+    const uint64_t t_off = ((uint64_t)d0.y << 32) | d0.x, q_off = ((uint64_t)d0.w << 32) | d0.z;
+    g.n = d1.z; g.rec = d1.w; g.seg = d2.x; g.tail = d2.y; g.item = item;
+    const uint8_t *tp = A.text + t_off, *qp = A.text + q_off;
+    g.a = (uint32_t)(reinterpret_cast<uintptr_t>(tp) & 15u);
+    g.tbase = tp - g.a;
+    const uint8_t *qv = qp - g.a;  // query byte stream in the same column frame
+    g.s = (uint32_t)(reinterpret_cast<uintptr_t>(qv) & 15u);
+    g.qbase = qv - g.s;
+    g.nch = (g.n + g.a + 15u) >> 4;
+    g.q_last = (g.s + g.n + g.a - 1u) >> 4;  // last query vector holding a needed byte
+    // column preceding chunk 0 (only matters when a == 0; otherwise it sits inside chunk 0)
+    g.first_prev = 0;
+    if (g.a == 0 && g.seg > 0) g.first_prev = (1u << 16) | ((uint32_t)qp[-1] << 8) | (uint32_t)tp[-1];
+    return g;
+}
+
+struct Vec3 { uint4 t, q0, q1; };
+__device__ __forceinline__ Vec3 load_vec(const Geom &g, uint32_t j) {
+    Vec3 v;
+    v.t = make_uint4(0, 0, 0, 0); v.q0 = v.t; v.q1 = v.t;
+    if (j < g.nch) {
+        v.t = ldg16(g.tbase + 16ull * j);
+        v.q0 = ldg16(g.qbase + 16ull * j);
+        if (g.s != 0 && j + 1 <= g.q_last) v.q1 = ldg16(g.qbase + 16ull * (j + 1));
     }
-    for (uint32_t j0 = 0; j0 < nch; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        const bool act = j < nch;
-        uint4 ntv = make_uint4(0, 0, 0, 0), nq0 = ntv, nq1 = ntv;
-        {
-            const uint32_t jn = j + 32;
-            if (jn < nch) {
-                ntv = ldg16(tbase + 16ull * jn);
-                nq0 = ldg16(qbase + 16ull * jn);
-                if (q_two && jn + 1 <= q_last) nq1 = ldg16(qbase + 16ull * (jn + 1));
+    return v;
+}
+
+template <int WS>
+__device__ __forceinline__ void realign(const uint4 &q0, const uint4 &q1, uint32_t sh, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
+    uint32_t w0, w1, w2, w3, w4;
+    if (WS == 0) { w0 = q0.x; w1 = q0.y; w2 = q0.z; w3 = q0.w; w4 = q1.x; }
+    else if (WS == 1) { w0 = q0.y; w1 = q0.z; w2 = q0.w; w3 = q1.x; w4 = q1.y; }
+    else if (WS == 2) { w0 = q0.z; w1 = q0.w; w2 = q1.x; w3 = q1.y; w4 = q1.z; }
+    else { w0 = q0.w; w1 = q1.x; w2 = q1.y; w3 = q1.z; w4 = q1.w; }
+    o0 = __funnelshift_r(w0, w1, sh); o1 = __funnelshift_r(w1, w2, sh);
+    o2 = __funnelshift_r(w2, w3, sh); o3 = __funnelshift_r(w3, w4, sh);
+}
+
+// one step (32 chunks) of the current item: 128-bit compare, push the slow chunks, run a batch when 32 are queued
+template <int MODE>
+__device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane,
+                                          const Geom &g, uint32_t j0, const Vec3 &v, uint32_t &carry) {
+    constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
+    const uint32_t j = j0 + lane;
+    const bool act = j < g.nch;
+    const uint4 tv = v.t;
+    uint32_t qw0, qw1, qw2, qw3;
+    const uint32_t sh = (g.s & 3u) * 8u;
+    switch (g.s >> 2) {  // warp-uniform
+        case 0: realign<0>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
+        case 1: realign<1>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
+        case 2: realign<2>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
+        default: realign<3>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
+    }
+    // last column of this chunk -> neighbour lane (previous column of the next chunk)
+    const uint32_t lastb = act ? ((tv.w >> 24) | ((qw3 >> 24) << 8)) : 0u;
+    uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, lastb, 1);
+    if (lane == 0) pb = carry;
+    carry = __shfl_sync(0xFFFFFFFFu, lastb, 31);
+    uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | (tv.w ^ qw3);
+    bool prev_ne = (pb & 0xFFu) != (pb >> 8);
+    if (CALLER) {
+        x |= has_zero_byte(tv.x ^ kGap4) | has_zero_byte(tv.y ^ kGap4) | has_zero_byte(tv.z ^ kGap4) |
+             has_zero_byte(tv.w ^ kGap4);
+        prev_ne |= (pb & 0xFFu) == '-';
+    }
+    // interior chunks: fully inside the item -> 16j >= a and 16j+16 <= n+a
+    const uint32_t jf = (g.a + 15u) >> 4, jl = (g.n + g.a) >> 4;
+    const bool edge = j == 0 || j < jf || j >= jl;
+    const bool slow = act && (edge || x != 0u || prev_ne);
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
+    if (mask) {
+        if (slow) {
+            const uint32_t slot = qn + __popc(mask & ((1u << lane) - 1u));
+            Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
+            Q[4][slot] = qw0; Q[5][slot] = qw1; Q[6][slot] = qw2; Q[7][slot] = qw3;
+            Q[8][slot] = j == 0 ? g.first_prev : ((1u << 16) | pb);
+            uint32_t f0 = 0, t0 = 16, t1 = 16;
+            if (edge) {
+                const int64_t lo = (int64_t)g.a - 16ll * j, hi = (int64_t)g.n + (int64_t)g.a - 16ll * j;
+                f0 = clamp16(lo);
+                t0 = clamp16(hi);
+                t1 = clamp16(hi + (int64_t)g.tail);  // columns of the next item are context only
             }
+            Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | ((g.seg == 0 ? 1u : 0u) << 15) | ((16u * j + 16u - g.a) << 16);
+            Q[10][slot] = g.item;
+            Q[11][slot] = g.rec;
         }
-        uint32_t w0, w1, w2, w3, w4;
-        if (WS == 0) { w0 = q0.x; w1 = q0.y; w2 = q0.z; w3 = q0.w; w4 = q1.x; }
-        else if (WS == 1) { w0 = q0.y; w1 = q0.z; w2 = q0.w; w3 = q1.x; w4 = q1.y; }
-        else if (WS == 2) { w0 = q0.z; w1 = q0.w; w2 = q1.x; w3 = q1.y; w4 = q1.z; }
-        else { w0 = q0.w; w1 = q1.x; w2 = q1.y; w3 = q1.z; w4 = q1.w; }
-        const uint32_t sh = bs * 8;
-        const uint32_t qw0 = __funnelshift_r(w0, w1, sh), qw1 = __funnelshift_r(w1, w2, sh),
-                       qw2 = __funnelshift_r(w2, w3, sh), qw3 = __funnelshift_r(w3, w4, sh);
-        // last column of this chunk -> neighbour lane (previous column of the next chunk)
-        const uint32_t lastb = act ? ((tv.w >> 24) | ((qw3 >> 24) << 8)) : 0u;
-        uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, lastb, 1);
-        if (lane == 0) pb = carry;
-        carry = __shfl_sync(0xFFFFFFFFu, lastb, 31);
-        uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | (tv.w ^ qw3);
-        bool prev_ne = (pb & 0xFFu) != (pb >> 8);
-        if (CALLER) {
-            x |= has_zero_byte(tv.x ^ kGap4) | has_zero_byte(tv.y ^ kGap4) | has_zero_byte(tv.z ^ kGap4) |
-                 has_zero_byte(tv.w ^ kGap4);
-            prev_ne |= (pb & 0xFFu) == '-';
-        }
-        const bool edge = j == 0 || j < jf || j >= jl;
-        const bool slow = act && (edge || x != 0u || prev_ne);
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
-        if (mask) {
-            if (slow) {
-                const uint32_t slot = qn + __popc(mask & lt_mask);
-                Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
-                Q[4][slot] = qw0; Q[5][slot] = qw1; Q[6][slot] = qw2; Q[7][slot] = qw3;
-                Q[8][slot] = j == 0 ? first_prev : ((1u << 16) | pb);
-                uint32_t f0 = 0, t0 = 16, t1 = 16;
-                if (edge) {
-                    const int64_t lo = (int64_t)a - 16ll * j, hi = (int64_t)n + (int64_t)a - 16ll * j;
-                    f0 = clamp16(lo);
-                    t0 = clamp16(hi);
-                    t1 = clamp16(hi + (int64_t)tail);  // columns of the next item are context only
-                }
-                Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | ((seg == 0 ? 1u : 0u) << 15) | ((16u * j + 16u - a) << 16);
-                Q[10][slot] = item;
-                Q[11][slot] = rec;
-            }
-            qn += __popc(mask);
+        qn += __popc(mask);
+        __syncwarp();
+        if (qn >= 32) {
+            walk_batch<MODE>(A, Q, 32, lane, E);
             __syncwarp();
-            if (qn >= 32) {
-                walk_batch<MODE>(A, Q, 32, lane, E);
-                __syncwarp();
-                qn -= 32;
-                uint32_t mv[12];
-                if (lane < qn) {
+            qn -= 32;
+            uint32_t mv[12];
+            if (lane < qn) {
 #pragma unroll
-                    for (int f = 0; f < 12; ++f) mv[f] = Q[f][lane + 32];
-                }
-                __syncwarp();
-                if (lane < qn) {
-#pragma unroll
-                    for (int f = 0; f < 12; ++f) Q[f][lane] = mv[f];
-                }
-                __syncwarp();
+                for (int f = 0; f < 12; ++f) mv[f] = Q[f][lane + 32];
             }
+            __syncwarp();
+            if (lane < qn) {
+#pragma unroll
+                for (int f = 0; f < 12; ++f) Q[f][lane] = mv[f];
+            }
+            __syncwarp();
         }
-        tv = ntv; q0 = nq0; q1 = nq1;
     }
 }
 
@@ -307,29 +337,63 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs 
     E.open_item = 0xFFFFFFFFu;
     E.open_count = 0;
 
-    for (uint64_t item = (uint64_t)blockIdx.x * kWalkWarps + wid; item < A.n_items; item += n_warps) {
+    // Dynamic scheduling: warps grab batches of kGrab consecutive items from a global counter (record lengths are
+    // log-normal, a static split leaves a 30-50 % tail).  The next batch is always requested one batch ahead.
+    // Software pipeline across items: the descriptor of the item after next and the first vectors of the next
+    // item are requested while the current item is being walked.
+    constexpr uint32_t kGrab = 8;
+    const uint32_t n_items = (uint32_t)A.n_items;
+    uint32_t s_it = 0, s_end = 0, nb_raw = 0;  // scheduler: last handed-out item, end of its batch, next batch (lane 0)
+    if (lane == 0) {
+        s_it = atomicAdd(A.sched, kGrab);
+        nb_raw = atomicAdd(A.sched, kGrab);
+    }
+    s_it = __shfl_sync(0xFFFFFFFFu, s_it, 0);
+    s_end = s_it + kGrab < n_items ? s_it + kGrab : n_items;
+    auto advance = [&]() -> bool {  // moves (s_it) to the next item of this warp; false when the work is exhausted
+        ++s_it;
+        if (s_it < s_end) return true;
+        const uint32_t nb = __shfl_sync(0xFFFFFFFFu, nb_raw, 0);
+        if (nb >= n_items) { s_it = n_items; return false; }
+        s_it = nb;
+        s_end = nb + kGrab < n_items ? nb + kGrab : n_items;
+        if (lane == 0) nb_raw = atomicAdd(A.sched, kGrab);
+        return true;
+    };
+    if (s_it < n_items) {
+        const uint32_t item = s_it;
         const uint4 *dp = reinterpret_cast<const uint4 *>(A.items + item);
-        const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
-        const uint64_t t_off = ((uint64_t)d0.y << 32) | d0.x, q_off = ((uint64_t)d0.w << 32) | d0.z;
-        const uint32_t n = d1.z, rec = d1.w, seg = d2.x, tail = d2.y;
-        const uint8_t *tp = A.text + t_off;
-        const uint8_t *qp = A.text + q_off;
-        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(tp) & 15u);
-        const uint8_t *tbase = tp - a;  // 16-byte aligned; chunk j covers item columns [16j-a, 16j-a+16)
-        const uint8_t *qv = qp - a;     // query byte stream in the same column frame
-        const uint32_t s = (uint32_t)(reinterpret_cast<uintptr_t>(qv) & 15u);
-        const uint8_t *qbase = qv - s;
-        const uint32_t nch = (n + a + 15u) >> 4;
-        const uint32_t q_last = (s + n + a - 1u) >> 4;  // last query vector holding a needed byte
-        // column preceding chunk 0 (only matters when a == 0; otherwise it sits inside chunk 0)
-        uint32_t first_prev = 0;
-        if (a == 0 && seg > 0) first_prev = (1u << 16) | ((uint32_t)qp[-1] << 8) | (uint32_t)tp[-1];
-        const uint32_t it32 = (uint32_t)item;
-        switch (s >> 2) {
-            case 0: walk_item<MODE, 0>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, s != 0, a, n, nch, q_last, first_prev, rec, seg, tail); break;
-            case 1: walk_item<MODE, 1>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, true, a, n, nch, q_last, first_prev, rec, seg, tail); break;
-            case 2: walk_item<MODE, 2>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, true, a, n, nch, q_last, first_prev, rec, seg, tail); break;
-            default: walk_item<MODE, 3>(A, Q, qn, E, lane, it32, tbase, qbase, s & 3u, true, a, n, nch, q_last, first_prev, rec, seg, tail); break;
+        Geom cur = make_geom(A, __ldg(dp), __ldg(dp + 1), __ldg(dp + 2), item);
+        bool has2 = advance();
+        uint32_t item2 = s_it;
+        uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0, e2 = e0;
+        if (has2) {
+            const uint4 *ep = reinterpret_cast<const uint4 *>(A.items + item2);
+            e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2);
+        }
+        Vec3 v = load_vec(cur, lane);
+        for (;;) {
+            Geom nxt = cur;
+            if (has2) nxt = make_geom(A, e0, e1, e2, item2);
+            const bool has3 = has2 && advance();
+            const uint32_t item3 = s_it;
+            if (has3) {
+                const uint4 *ep = reinterpret_cast<const uint4 *>(A.items + item3);
+                e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2);
+            }
+            uint32_t carry = 0;  // (t,q) bytes of the column before this step's first chunk: t | q<<8
+            for (uint32_t j0 = 0; j0 < cur.nch; j0 += 32) {
+                Vec3 nv;
+                if (j0 + 32 < cur.nch) nv = load_vec(cur, j0 + 32 + lane);
+                else if (has2) nv = load_vec(nxt, lane);
+                else { nv.t = make_uint4(0, 0, 0, 0); nv.q0 = nv.t; nv.q1 = nv.t; }
+                walk_step<MODE>(A, Q, qn, E, lane, cur, j0, v, carry);
+                v = nv;
+            }
+            if (!has2) break;
+            cur = nxt;
+            item2 = item3;
+            has2 = has3;
         }
     }
     if (qn) {

@@ -338,10 +338,10 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
         LAUNCH(ctx, k_fill_item_desc, grid_for(n_rec, 256), 256, n_rec, P.rc.n_items, P.item_base, P.rc.t_off, P.rc.q_off,
                P.rc.ncols, (const uint64_t *)slot_base, shift, P.items);
         WGA_CK(cudaMemsetAsync(nheads, 0, (n_items + 1) * 4, ctx->stream));
-        WGA_CK(cudaMemsetAsync(ovf, 0, 4, ctx->stream));
+        WGA_CK(cudaMemsetAsync(ovf, 0, 8, ctx->stream));
         WalkArgs A;
         A.text = ctx->d_text; A.items = P.items; A.n_items = n_items; A.rec_cnt = rec_cnt;
-        A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf;
+        A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf; A.sched = ovf + 1;
         auto kern = k_walk<MODE>;
         WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
         LAUNCH(ctx, kern, walk_grid(ctx, n_items), kWalkThreads, A);
