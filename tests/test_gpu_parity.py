@@ -373,3 +373,63 @@ def test_cli_matches_oracle(w, ctx, tmp_path):
     assert r.returncode == 0 and r.stdout == orc.call_maf(text, snp=True, svlen=0, sample="hg1")
     r = run("m2p", str(maf), "-q", "nope")
     assert r.returncode == 1 and b"Query name:nope not found in MAF" in r.stderr
+
+
+# ------------------------------------------------------------------------------------- stat -f paf
+TEST_PAF = open(os.path.join(G, "ref_testdotplot.paf"), "rb").read()
+
+
+def statp(w, ctx, text, each=False):
+    return w.run_bytes(w.stat_paf, w.PAFReader(text), each, ctx=ctx)
+
+
+def check_paf(w, ctx, text):
+    assert statp(w, ctx, text) == orc.stat_paf(text)
+    assert statp(w, ctx, text, True) == orc.stat_paf(text, True)
+
+
+def test_paf_stat_golden(w, ctx):
+    out = statp(w, ctx, TEST_PAF).decode().splitlines()
+    assert out[1].split("\t") == "B 300 0 A 300 0 250 50 0.84 0.84 210 0 2 2 30 30 1 50.0 1 10 1 10".split()
+    check_paf(w, ctx, TEST_PAF)
+
+
+def _pafline(cg, strand="+", q="q1", t="t1", extra=("NM:i:3",), ints=(1000, 10, 200, 2000, 50, 400, 180, 200, 60)):
+    f = [q, str(ints[0]), str(ints[1]), str(ints[2]), strand, t, str(ints[3]), str(ints[4]), str(ints[5]), str(ints[6]),
+         str(ints[7]), str(ints[8])] + list(extra) + ([f"cg:Z:{cg}"] if cg is not None else [])
+    return "\t".join(f).encode()
+
+
+def test_paf_stat_quirks_and_errors(w, ctx):
+    ok = [
+        b"#comment\n" + _pafline("10M2I3D5X4=") + b"\n\n" + _pafline("7=", "-", "q2") + b"\r\n" + _pafline("3=1X", "-"),
+        _pafline("100M") + b"\n" + _pafline("5=", extra=("tp:A:P", "cg:Z:9=")) + b"\n",  # first cg:Z: tag wins
+        "\t".join(["q", "0x10", "1", "2", "+", "t", "0x20", "3", "4", "1", "1", "0", "cg:Z:1="]).encode(),  # csv hex ints
+        _pafline("18446744073709551615=1X"),
+    ]
+    for t in ok:
+        check_paf(w, ctx, t)
+    bad = [(_pafline("10S5M"), 5), (_pafline("5H"), 5), (_pafline("10MM"), 5), (_pafline("M"), 1), (_pafline("12"), 5),
+           (_pafline("99999999999999999999999M"), 1), (_pafline(None), 6), (_pafline(""), 8),
+           (b"q\t1\t2\n", 9), (_pafline("5=", strand="*"), 9), (_pafline("5=", ints=(1000, "x", 200, 2000, 50, 400, 180, 200, 60)), 9),
+           (_pafline("5=") + b"\n" + _pafline("3=2Q1=") + b"\n" + _pafline("M"), 5),   # first bad record wins
+           (_pafline("5=") + b"\n" + _pafline("3=Q") + b"\n" + b"q\t1\n", 1)]           # "3=Q": op ok? no: 'Q' has no digits
+    for text, code in bad:
+        with pytest.raises(orc.OracleError) as eo:
+            orc.stat_paf(text)
+        with pytest.raises(w.WGAError) as eg:
+            statp(w, ctx, text)
+        assert eo.value.code == eg.value.code, (text, eo.value.code, eg.value.code, eo.value.msg)
+        if eo.value.code in (1, 5, 6):
+            assert str(eg.value) == eo.value.msg, text
+    check_paf(w, ctx, TEST_PAF)
+
+
+@pytest.mark.parametrize("seed,kw", [(1, {}), (2, dict(m_only=1)), (3, dict(ops_median=4000.0, ops_sigma=1.0)),
+                                     (4, dict(ops_median=3.0, ops_sigma=0.8, n_genomes=3, n_chr=2))])
+def test_paf_stat_synthetic(w, ctx, seed, kw):
+    n = 3000 if kw.get("ops_median", 150) < 1000 else 300
+    text = bs.gen_paf(bs.paf_params(n, seed=seed, **kw))
+    check_paf(w, ctx, text)
+    cnt = ctx.last_record_counts()
+    assert len(cnt) == n

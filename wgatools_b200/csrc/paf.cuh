@@ -1,0 +1,197 @@
+// paf.cuh -- `stat -f paf`: on-device PAF tokenisation + CIGAR counters.
+//
+// Replaces src/parser/paf.rs:22-31 (csv reader: tab-delimited, no header, flexible, '#' comments),
+// :48-65 PafRecord (12 typed columns + tags), :122-140 get_cigar_string (first cg:Z: tag), and
+// src/parser/cigar.rs:43-75 (tokenizer) + :629-707 parse_paf_to_cigar (M,= -> matched; X; I/D by strand; any
+// other op is CigarOpInvalid).
+//
+// The delimiter index ('\t', '\n') reuses the single-pass slot scan of tokenize.cuh with a PAF byte class.
+// CIGAR text is walked one record per thread with 16-byte loads (records are short -- a few hundred ops --
+// and the per-op work, a decimal parse, dominates; see DESIGN.md for the bound).
+// Not supported (reported, never silently wrong): quoted csv fields, a lone '\r' as record terminator, cs:Z:.
+#pragma once
+#include "ctx.cuh"
+#include "stat.cuh"
+#include "tokenize.cuh"
+
+namespace wga {
+
+struct PafRecs {
+    uint64_t *q_name_off, *t_name_off, *cig_off, *cig_len;
+    uint32_t *q_name_len, *t_name_len;
+    uint64_t *q_size, *t_size, *q_start, *t_start;
+    uint8_t *neg;
+};
+
+// flags: bit0 = record line (non-empty, not a '#' comment)
+__global__ void k_paf_line_flags(LineView lv, uint8_t *__restrict__ flags, uint32_t *__restrict__ isrec) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > lv.n_lines) return;
+    if (k == lv.n_lines) { isrec[k] = 0; return; }
+    uint64_t s = lv.start(k), e = lv.end(k);
+    if (e > s && lv.text[e - 1] == '\r') --e;  // CRLF
+    bool rec = e > s && lv.text[s] != '#';     // csv: empty lines skipped, comment(Some(b'#'))
+    flags[k] = rec ? 1 : 0;
+    isrec[k] = rec ? 1u : 0u;
+}
+
+// csv deserializer integer rule (csv 1.2.2 deserializer.rs): "0x" prefix => radix 16, else str::parse::<u64>()
+__device__ __forceinline__ bool csv_u64(const uint8_t *p, uint64_t n, uint64_t *out) {
+    if (n >= 2 && p[0] == '0' && p[1] == 'x') {
+        if (n == 2) return false;
+        uint64_t i = 2, v = 0;
+        if (p[i] == '+') { ++i; if (i == n) return false; }
+        for (; i < n; ++i) {
+            uint8_t c = p[i];
+            uint32_t d = c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : 99u;
+            if (d > 15 || (v >> 60)) return false;
+            v = v * 16 + d;
+        }
+        *out = v;
+        return true;
+    }
+    return parse_u64_bytes(p, n, out);
+}
+
+// err key: record index << 32 | position (24 bits) << 8 | code   (lowest record, then earliest position wins)
+__device__ __forceinline__ void paf_report(unsigned long long *err_key, uint64_t rec, uint64_t pos, int code) {
+    if (pos > 0xFFFFFFull) pos = 0xFFFFFFull;
+    atomicMin(err_key, (unsigned long long)((rec << 32) | (pos << 8) | (uint64_t)code));
+}
+
+// one PAF line -> 12 typed columns + cg:Z: span (paf.rs:48-65,122-140)
+__global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, const uint32_t *__restrict__ rec_scan,
+                            PafRecs R, unsigned long long *err_key) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= lv.n_lines || !flags[k]) return;
+    const uint64_t r = rec_scan[k];
+    uint64_t S = lv.start(k), E = lv.end(k);
+    if (E > S && lv.text[E - 1] == '\r') --E;
+    uint64_t wlo = k == 0 ? 0 : lv.nl_ws_idx[k - 1] + 1;
+    uint64_t whi = k < lv.n_nl ? lv.nl_ws_idx[k] : lv.n_ws;
+    // fields 0..11, then tags
+    uint64_t fb = S, w = wlo;
+    uint64_t v[12];
+    uint8_t neg = 0;
+    int code = 0;
+    uint64_t cg_off = 0, cg_len = 0;
+    bool have_cg = false, have_cs = false, quoted = false;
+    uint64_t nf = 0;
+    for (;; ++nf) {
+        uint64_t fe = w < whi ? (lv.ws_ent[w] & kPosMask) : E;
+        if (fe > E) fe = E;
+        const uint8_t *f = lv.text + fb;
+        const uint64_t fl = fe - fb;
+        if (fl && f[0] == '"') quoted = true;
+        if (nf < 12) {
+            if (nf == 0) { R.q_name_off[r] = fb; R.q_name_len[r] = (uint32_t)fl; }
+            else if (nf == 5) { R.t_name_off[r] = fb; R.t_name_len[r] = (uint32_t)fl; }
+            else if (nf == 4) {
+                if (fl == 1 && f[0] == '+') neg = 0;
+                else if (fl == 1 && f[0] == '-') neg = 1;
+                else if (!code) code = WGA_E_CSV;
+            } else if (!csv_u64(f, fl, &v[nf])) { if (!code) code = WGA_E_CSV; }
+        } else if (!have_cg && fl >= 5 && f[0] == 'c' && f[2] == ':' && f[3] == 'Z' && f[4] == ':') {
+            if (f[1] == 'g') { have_cg = true; cg_off = fb + 5; cg_len = fl - 5; }
+            else if (f[1] == 's') have_cs = true;
+        }
+        if (w >= whi) { ++nf; break; }
+        fb = fe + 1;
+        ++w;
+    }
+    if (quoted) { paf_report(err_key, r, 0, WGA_E_UNSUPPORTED); code = WGA_E_UNSUPPORTED; }
+    if (!code && nf < 12) code = WGA_E_CSV;
+    if (code) {
+        if (code != WGA_E_UNSUPPORTED) paf_report(err_key, r, 0, code);
+        R.cig_len[r] = 0; R.cig_off[r] = 0; R.neg[r] = 0;
+        R.q_size[r] = R.t_size[r] = R.q_start[r] = R.t_start[r] = 0;
+        return;
+    }
+    R.q_size[r] = v[1]; R.q_start[r] = v[2];
+    R.t_size[r] = v[6]; R.t_start[r] = v[7];
+    R.neg[r] = neg;
+    if (!have_cg) {  // cs:Z: conversion (paf.rs:159-218) is not accelerated; no tag at all is the reference's error
+        paf_report(err_key, r, 1, have_cs ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
+        cg_len = 0;
+        cg_off = 0;
+        R.neg[r] = 2;  // marks "no cigar"
+    }
+    R.cig_off[r] = cg_off;
+    R.cig_len[r] = cg_len;
+}
+
+// CIGAR text -> the 11 counters of struct Cigar (cigar.rs:16-29).  One record per thread.
+__global__ void k_paf_cigar_counts(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
+                                   unsigned long long *__restrict__ cnt11, unsigned long long *err_key) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    unsigned long long *o = cnt11 + r * 11;
+    unsigned long long c_m = 0, c_x = 0, c_ie = 0, c_i = 0, c_de = 0, c_d = 0;
+    const uint8_t negf = R.neg[r];
+    const uint64_t len = R.cig_len[r];
+    const uint8_t *p = text + R.cig_off[r];
+    if (negf == 2) { for (int i = 0; i < 11; ++i) o[i] = 0; return; }
+    if (len == 0) {  // fold_many1 on "" -> nom error -> e.input[..10] panics (errors.rs:88-97)
+        paf_report(err_key, r, 2, WGA_E_REF_PANIC);
+        for (int i = 0; i < 11; ++i) o[i] = 0;
+        return;
+    }
+    uint64_t val = 0;
+    uint32_t nd = 0;        // digits in the current number
+    bool ovf = false;
+    uint32_t op_run = 0;    // non-digit chars since the last digit
+    uint8_t op = 0;
+    int code = 0;
+    uint64_t epos = 0;
+    // tokens: digits* then nondigits*; a token is closed when a digit follows a non-digit or at the end
+    auto close_token = [&](uint64_t pos) {
+        if (code) return;
+        if (op_run != 1) { code = WGA_E_CIGAR_OP_INVALID; epos = pos; return; }     // cst2cu: op must be one char
+        if (nd == 0 || ovf) { code = WGA_E_PARSE_INT; epos = pos; return; }          // parse_str2u64
+        switch (op) {
+            case 'M': case '=': c_m += val; break;
+            case 'X': c_x += val; break;
+            case 'I': c_ie += 1; c_i += val; break;
+            case 'D': c_de += 1; c_d += val; break;
+            default: code = WGA_E_CIGAR_OP_INVALID; epos = pos; break;
+        }
+    };
+    const uint64_t a = reinterpret_cast<uintptr_t>(p) & 15u;
+    const uint8_t *base = p - a;
+    const uint64_t nvec = (a + len + 15) >> 4;
+    bool in_op = false;
+    for (uint64_t vi = 0; vi < nvec && !code; ++vi) {
+        uint4 vv = ldg16(base + 16 * vi);
+        uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int64_t idx = (int64_t)(16 * vi + k) - (int64_t)a;
+            if (idx < 0 || (uint64_t)idx >= len) continue;
+            const uint8_t ch = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+            const bool dig = ch >= '0' && ch <= '9';
+            if (dig) {
+                if (in_op) {  // a new token starts: close the previous one
+                    close_token((uint64_t)idx);
+                    val = 0; nd = 0; ovf = false; op_run = 0; in_op = false;
+                }
+                const uint32_t d = ch - '0';
+                if (val > (0xFFFFFFFFFFFFFFFFull - d) / 10) ovf = true;
+                val = val * 10 + d;
+                ++nd;
+            } else {
+                in_op = true;
+                ++op_run;
+                op = ch;
+            }
+        }
+    }
+    if (!code) close_token(len);  // last token (digits with no op char -> op_run == 0 -> CigarOpInvalid(""))
+    if (code) paf_report(err_key, r, 3 + epos, code);
+    const bool neg = negf == 1;
+    o[0] = c_m; o[1] = c_x;
+    o[2] = neg ? 0 : c_ie; o[3] = neg ? 0 : c_i; o[4] = neg ? 0 : c_de; o[5] = neg ? 0 : c_d;
+    o[6] = neg ? c_ie : 0; o[7] = neg ? c_i : 0; o[8] = neg ? c_de : 0; o[9] = neg ? c_d : 0;
+    o[10] = neg ? 1 : 0;
+}
+
+}  // namespace wga

@@ -17,6 +17,12 @@ constexpr int kWsThreads = 256;
 constexpr uint32_t kSeg = 16384;  // columns per work item of the column walk
 
 // ---------------------------------------------------------------- 1. whitespace index
+// CLS 0: ASCII whitespace (MAF, split_whitespace); CLS 1: PAF delimiters '\t' and '\n' (csv reader, paf.rs:22-31)
+template <int CLS>
+__device__ __forceinline__ uint32_t delim_bytes(uint32_t w) {
+    return CLS == 0 ? ws_bytes(w) : (zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au));
+}
+template <int CLS>
 __device__ __forceinline__ void ws_flags16(const uint8_t *text, uint64_t off, uint64_t len, uint32_t ws[4],
                                            uint32_t nl[4]) {
     uint4 v = ldg16(text + off);
@@ -25,11 +31,12 @@ __device__ __forceinline__ void ws_flags16(const uint8_t *text, uint64_t off, ui
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         uint32_t valid = rem >= 4 * (k + 1) ? kHi : range_flags(0, (int)(rem - 4 * k));
-        ws[k] = ws_bytes(w[k]) & valid;
+        ws[k] = delim_bytes<CLS>(w[k]) & valid;
         nl[k] = nl_bytes(w[k]) & valid;
     }
 }
 
+template <int CLS>
 __global__ void __launch_bounds__(kWsThreads) k_ws_count(const uint8_t *__restrict__ text, uint64_t len,
                                                          uint64_t *__restrict__ tile_ws,
                                                          uint64_t *__restrict__ tile_nl) {
@@ -39,7 +46,7 @@ __global__ void __launch_bounds__(kWsThreads) k_ws_count(const uint8_t *__restri
         uint64_t off = base + (uint64_t)i * 16;
         if (off >= len) break;
         uint32_t ws[4], nl[4];
-        ws_flags16(text, off, len, ws, nl);
+        ws_flags16<CLS>(text, off, len, ws, nl);
         cw += __popc(ws[0]) + __popc(ws[1]) + __popc(ws[2]) + __popc(ws[3]);
         cn += __popc(nl[0]) + __popc(nl[1]) + __popc(nl[2]) + __popc(nl[3]);
     }
@@ -78,6 +85,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp
     return off + pre;
 }
 
+template <int CLS>
 __global__ void __launch_bounds__(kWsThreads) k_ws_fill(const uint8_t *__restrict__ text, uint64_t len,
                                                         const uint64_t *__restrict__ tile_ws_off,
                                                         const uint64_t *__restrict__ tile_nl_off,
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(kWsThreads) k_ws_fill(const uint8_t *__restric
     for (int it = 0; it < kWsTile / 16 / kWsThreads; ++it) {
         uint64_t off = base + ((uint64_t)it * kWsThreads + threadIdx.x) * 16;
         uint32_t ws[4] = {0, 0, 0, 0}, nl[4] = {0, 0, 0, 0};
-        if (off < len) ws_flags16(text, off, len, ws, nl);
+        if (off < len) ws_flags16<CLS>(text, off, len, ws, nl);
         uint32_t cw = __popc(ws[0]) + __popc(ws[1]) + __popc(ws[2]) + __popc(ws[3]);
         uint32_t cn = __popc(nl[0]) + __popc(nl[1]) + __popc(nl[2]) + __popc(nl[3]);
         uint32_t tw, tn;
@@ -122,75 +130,92 @@ __global__ void __launch_bounds__(kWsThreads) k_ws_fill(const uint8_t *__restric
 // per tile; a sparse pass then compacts the slots into ws_ent / nl_ws_idx.  A tile with more than kTokCap
 // whitespace bytes raises the overflow flag and the caller falls back to the exact two-pass kernels.
 constexpr int kTokTile = 4096;
-constexpr int kTokCap = 128;
+constexpr int kTokCap = 128;     // MAF: whitespace slots per 4 KiB tile
+constexpr int kTokCapPaf = 512;  // PAF: tab/newline slots per 4 KiB tile
 constexpr int kTokWarps = 8;
 
+// 0x80 in every byte below 0x21 (control characters and space): the superset of all delimiter classes
+__device__ __forceinline__ uint32_t lt21_bytes(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w) & kHi; }
+template <int CLS>
+__device__ __forceinline__ bool is_delim(uint32_t ch) {
+    return CLS == 0 ? (ch == 0x20u || (ch - 9u) < 5u) : (ch == 9u || ch == 10u);
+}
+
+template <int CLS, int CAP>
 __global__ void __launch_bounds__(kTokWarps * 32) k_ws_scan(const uint8_t *__restrict__ text, uint64_t len, uint64_t n_tiles,
                                                             uint64_t *__restrict__ tile_ws, uint64_t *__restrict__ tile_nl,
                                                             uint16_t *__restrict__ slots, uint32_t *__restrict__ overflow) {
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ uint32_t s_cnt[kTokWarps][2];  // per warp: delimiters, newlines of the current tile
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint64_t n_warps = (uint64_t)gridDim.x * kTokWarps;
-    for (uint64_t tile = (uint64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5); tile < n_tiles; tile += n_warps) {
+    for (uint64_t tile = (uint64_t)blockIdx.x * kTokWarps + wid; tile < n_tiles; tile += n_warps) {
         const uint64_t base = tile * kTokTile;
         uint4 v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             uint64_t off = base + (uint64_t)k * 512 + lane * 16;
-            v[k] = off < len ? ldg16(text + off) : make_uint4(0, 0, 0, 0);
+            v[k] = off < len ? ldg16(text + off) : make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
         }
-        uint32_t cw = 0, cn = 0;
-        uint16_t *slot = slots + tile * kTokCap;
+        if (lane == 0) { s_cnt[wid][0] = 0; s_cnt[wid][1] = 0; }
+        __syncwarp();
+        uint16_t *slot = slots + tile * CAP;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint64_t off = base + (uint64_t)k * 512 + lane * 16;
-            uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, ws[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ws[i] = ws_bytes(w[i]);
-            if (off + 16 > len) {  // the vector straddles the end of the text: mask the bytes past it
-                const int64_t rem = (int64_t)len - (int64_t)off;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ws[i] &= rem > 4 * i ? range_flags(0, (int)(rem - 4 * i)) : 0u;
-            }
-            const uint32_t c = __popc(ws[0]) + __popc(ws[1]) + __popc(ws[2]) + __popc(ws[3]);
-            if (__ballot_sync(0xFFFFFFFFu, c != 0)) {
-                uint32_t tot;
-                uint32_t idx = cw + warp_excl_scan(c, &tot);
+            // dense part: 3 ops per word.  Delimiters are sparse, the exact test runs per candidate byte only;
+            // entries of one step land in arbitrary order (shared atomic), k_ws_compact sorts the tile's few entries
+            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+            const uint32_t c0 = lt21_bytes(w[0]), c1 = lt21_bytes(w[1]), c2 = lt21_bytes(w[2]), c3 = lt21_bytes(w[3]);
+            if (c0 | c1 | c2 | c3) {
+                const uint32_t cand[4] = {c0, c1, c2, c3};
+                const uint32_t rel0 = (uint32_t)k * 512u + lane * 16u;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    uint32_t m = ws[i];
+                    uint32_t m = cand[i];
                     while (m) {
-                        int bit = __ffs(m) - 1;
+                        const int bit = __ffs(m) - 1;
                         m &= m - 1;
                         const uint32_t byte = (uint32_t)(bit >> 3);
-                        const uint32_t isnl = ((w[i] >> (8 * byte)) & 0xFFu) == 0x0Au;  // newline among the whitespace
-                        const uint32_t rel = (uint32_t)k * 512u + lane * 16u + 4u * i + byte;
-                        if (idx < (uint32_t)kTokCap) slot[idx] = (uint16_t)(rel | (isnl << 15));
-                        cn += isnl;
-                        ++idx;
+                        const uint32_t ch = (w[i] >> (8 * byte)) & 0xFFu;
+                        const uint32_t rel = rel0 + 4u * i + byte;
+                        if (is_delim<CLS>(ch) && base + rel < len) {
+                            const uint32_t isnl = ch == 0x0Au;
+                            const uint32_t idx = atomicAdd(&s_cnt[wid][0], 1u);
+                            if (isnl) atomicAdd(&s_cnt[wid][1], 1u);
+                            if (idx < (uint32_t)CAP) slot[idx] = (uint16_t)(rel | (isnl << 15));
+                        }
                     }
                 }
-                cw += tot;
             }
         }
-        cn = warp_sum(cn);
+        __syncwarp();
         if (lane == 0) {
+            const uint32_t cw = s_cnt[wid][0];
             tile_ws[tile] = cw;
-            tile_nl[tile] = cn;
-            if (cw > (uint32_t)kTokCap) atomicOr(overflow, 1u);
+            tile_nl[tile] = s_cnt[wid][1];
+            if (cw > (uint32_t)CAP) atomicOr(overflow, 1u);
         }
+        __syncwarp();
     }
 }
 
+template <int CAP>
 __global__ void k_ws_compact(uint64_t n_tiles, const uint64_t *__restrict__ tile_ws, const uint64_t *__restrict__ ws_off,
-                             const uint64_t *__restrict__ nl_off, const uint16_t *__restrict__ slots,
+                             const uint64_t *__restrict__ nl_off, uint16_t *__restrict__ slots,
                              uint64_t *__restrict__ ws_ent, uint64_t *__restrict__ nl_ws_idx) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     uint32_t c = (uint32_t)tile_ws[t];
-    if (c > (uint32_t)kTokCap) c = kTokCap;  // overflow: the caller discards this index
+    if (c > (uint32_t)CAP) c = CAP;  // overflow: the caller discards this index
     uint64_t wo = ws_off[t], no = nl_off[t];
     const uint64_t base = t * kTokTile;
-    const uint16_t *slot = slots + t * kTokCap;
+    uint16_t *slot = slots + t * CAP;
+    // entries arrive ordered step by step, unordered inside a step: insertion sort on tile-relative offset
+    for (uint32_t i = 1; i < c; ++i) {
+        const uint16_t e = slot[i];
+        uint32_t j = i;
+        while (j > 0 && (slot[j - 1] & 0x7FFFu) > (e & 0x7FFFu)) { slot[j] = slot[j - 1]; --j; }
+        slot[j] = e;
+    }
     for (uint32_t i = 0; i < c; ++i) {
         uint32_t e = slot[i];
         bool isnl = e >> 15;

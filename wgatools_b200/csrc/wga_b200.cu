@@ -166,33 +166,27 @@ int resolve_error(wga_ctx *ctx, const Prep &P, uint64_t key, const char *qname) 
     return code;
 }
 
-// tokenise the slab: whitespace index -> lines -> s-lines -> records -> work items
-int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep *P) {
-    const uint64_t len = ctx->text_len;
-    const uint8_t *text = ctx->d_text;
-    ctx->n_rec = ctx->n_items = ctx->n_runs = 0;
-    P->err_key = ctx->buf<unsigned long long>(B_ERR, 1);
-    if (!P->err_key) return ctx->err_code;
-    LAUNCH(ctx, k_init_u64, 1, 1, P->err_key, 1, kNoErr);
-    if (len == 0) return WGA_OK;
-
-    // 1. whitespace index: single-pass fast path, exact two-pass fallback when a tile overflows
+// delimiter index of the slab: single-pass fast path, exact two-pass fallback when a 4 KiB tile overflows its slots.
+// CLS 0 = ASCII whitespace (MAF), CLS 1 = tab/newline (PAF).  Leaves the last text byte in ctx->h_scal[8].
+template <int CLS, int CAP>
+int build_delim_index(wga_ctx *ctx, const uint8_t *text, uint64_t len, uint64_t *p_n_ws, uint64_t *p_n_nl, uint64_t **p_ws_ent,
+                      uint64_t **p_nl_idx) {
     uint64_t n_ws = 0, n_nl = 0;
     uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
-    uint8_t last_byte = 0;
     bool indexed = false;
     {
         const uint64_t n_tiles = (len + kTokTile - 1) / kTokTile;
         uint64_t *tile_ws = ctx->buf<uint64_t>(B_TILE_WS, n_tiles + 1), *tile_nl = ctx->buf<uint64_t>(B_TILE_NL, n_tiles + 1);
         uint64_t *ws_off = ctx->buf<uint64_t>(B_TILE_WS_OFF, n_tiles + 1), *nl_off = ctx->buf<uint64_t>(B_TILE_NL_OFF, n_tiles + 1);
-        uint16_t *slots = ctx->buf<uint16_t>(B_PAF_A, n_tiles * kTokCap);
+        uint16_t *slots = ctx->buf<uint16_t>(B_PAF_A, n_tiles * CAP);
         uint32_t *ovf = ctx->buf<uint32_t>(B_SCALARS, 16);
         if (!tile_ws || !tile_nl || !ws_off || !nl_off || !slots || !ovf) return ctx->err_code;
         WGA_CK(cudaMemsetAsync(tile_ws + n_tiles, 0, 8, ctx->stream));
         WGA_CK(cudaMemsetAsync(tile_nl + n_tiles, 0, 8, ctx->stream));
         WGA_CK(cudaMemsetAsync(ovf, 0, 4, ctx->stream));
         uint64_t want = (n_tiles + kTokWarps - 1) / kTokWarps, cap = (uint64_t)ctx->n_sm * 8;
-        LAUNCH(ctx, k_ws_scan, (unsigned)(want < cap ? want : cap), kTokWarps * 32, text, len, n_tiles, tile_ws, tile_nl, slots, ovf);
+        auto k_scan = k_ws_scan<CLS, CAP>;
+        LAUNCH(ctx, k_scan, (unsigned)(want < cap ? want : cap), kTokWarps * 32, text, len, n_tiles, tile_ws, tile_nl, slots, ovf);
         WGA_TRY(exclusive_sum(ctx, tile_ws, ws_off, n_tiles + 1));
         WGA_TRY(exclusive_sum(ctx, tile_nl, nl_off, n_tiles + 1));
         WGA_CK(cudaMemcpyAsync(ctx->h_scal + 8, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
@@ -202,7 +196,8 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
             n_ws = tot[0]; n_nl = tot[1];
             ws_ent = ctx->buf<uint64_t>(B_WS, n_ws + 1); nl_idx = ctx->buf<uint64_t>(B_NLIDX, n_nl + 1);
             if (!ws_ent || !nl_idx) return ctx->err_code;
-            LAUNCH(ctx, k_ws_compact, grid_for(n_tiles, 256), 256, n_tiles, tile_ws, ws_off, nl_off, slots, ws_ent, nl_idx);
+            auto k_comp = k_ws_compact<CAP>;
+            LAUNCH(ctx, k_comp, grid_for(n_tiles, 256), 256, n_tiles, tile_ws, ws_off, nl_off, slots, ws_ent, nl_idx);
             indexed = true;
         }
     }
@@ -213,7 +208,8 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
         if (!tile_ws || !tile_nl || !ws_off || !nl_off) return ctx->err_code;
         WGA_CK(cudaMemsetAsync(tile_ws + n_tiles, 0, 8, ctx->stream));
         WGA_CK(cudaMemsetAsync(tile_nl + n_tiles, 0, 8, ctx->stream));
-        LAUNCH(ctx, k_ws_count, (unsigned)n_tiles, kWsThreads, text, len, tile_ws, tile_nl);
+        auto k_cnt = k_ws_count<CLS>;
+        LAUNCH(ctx, k_cnt, (unsigned)n_tiles, kWsThreads, text, len, tile_ws, tile_nl);
         WGA_TRY(exclusive_sum(ctx, tile_ws, ws_off, n_tiles + 1));
         WGA_TRY(exclusive_sum(ctx, tile_nl, nl_off, n_tiles + 1));
         uint64_t tot[2];
@@ -221,10 +217,30 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
         n_ws = tot[0]; n_nl = tot[1];
         ws_ent = ctx->buf<uint64_t>(B_WS, n_ws + 1); nl_idx = ctx->buf<uint64_t>(B_NLIDX, n_nl + 1);
         if (!ws_ent || !nl_idx) return ctx->err_code;
-        LAUNCH(ctx, k_ws_fill, (unsigned)n_tiles, kWsThreads, text, len, ws_off, nl_off, ws_ent, nl_idx);
+        auto k_fill = k_ws_fill<CLS>;
+        LAUNCH(ctx, k_fill, (unsigned)n_tiles, kWsThreads, text, len, ws_off, nl_off, ws_ent, nl_idx);
         WGA_CK(cudaMemcpyAsync(ctx->h_scal + 8, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
         WGA_TRY(sync_check(ctx));
     }
+    *p_n_ws = n_ws; *p_n_nl = n_nl; *p_ws_ent = ws_ent; *p_nl_idx = nl_idx;
+    return WGA_OK;
+}
+
+// tokenise the slab: whitespace index -> lines -> s-lines -> records -> work items
+int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep *P) {
+    const uint64_t len = ctx->text_len;
+    const uint8_t *text = ctx->d_text;
+    ctx->n_rec = ctx->n_items = ctx->n_runs = 0;
+    P->err_key = ctx->buf<unsigned long long>(B_ERR, 1);
+    if (!P->err_key) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, P->err_key, 1, kNoErr);
+    if (len == 0) return WGA_OK;
+
+    // 1. whitespace index
+    uint64_t n_ws = 0, n_nl = 0;
+    uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
+    uint8_t last_byte = 0;
+    WGA_TRY((build_delim_index<0, kTokCap>(ctx, text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
     last_byte = *(uint8_t *)(ctx->h_scal + 8);
     const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
     ctx->n_ws = n_ws; ctx->n_nl = n_nl; ctx->n_lines = n_lines;
@@ -854,6 +870,110 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (!d_out) return ctx->err_code;
     LAUNCH(ctx, k_vcf_rows<1>, grid_for(n_rows, 128), 128, V, n_rows, rowbase, row_len, row_off, d_out, P.err_key);
     return finish_output(ctx, d_out, sc[0], mem, out);
+}
+#endif
+
+#ifdef WGA_WITH_PAF
+}  // extern "C"
+namespace {
+// host restatement of the tokenizer's error wording (cigar.rs:43-75, errors.rs) for one CIGAR string
+std::string paf_cigar_error_text(const std::string &cg, int code) {
+    size_t i = 0;
+    while (i < cg.size()) {
+        size_t d0 = i;
+        while (i < cg.size() && cg[i] >= '0' && cg[i] <= '9') ++i;
+        size_t o0 = i;
+        while (i < cg.size() && !(cg[i] >= '0' && cg[i] <= '9')) ++i;
+        std::string digits = cg.substr(d0, o0 - d0), op = cg.substr(o0, i - o0);
+        if (op.size() != 1) return "CIGAR OP `" + op + "` invalid";
+        uint64_t v;
+        if (!parse_u64_bytes((const unsigned char *)digits.data(), digits.size(), &v)) return "Parse `" + digits + "` Into Integer Error";
+        if (std::string("M=XID").find(op[0]) == std::string::npos) return "CIGAR OP `" + op + "` invalid";
+    }
+    return "CIGAR error code " + std::to_string(code);
+}
+}  // namespace
+extern "C" {
+
+// ---------------------------------------------------------------- stat -f paf
+int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_stat_acc *acc) {
+    (void)flags;
+    if (!ctx || !acc || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    ctx->n_rec = 0;
+    if (len == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    unsigned long long *err_key = ctx->buf<unsigned long long>(B_ERR, 1);
+    if (!err_key) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, err_key, 1, kNoErr);
+    uint64_t n_ws = 0, n_nl = 0;
+    uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
+    WGA_TRY((build_delim_index<1, kTokCapPaf>(ctx, d_text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
+    const uint8_t last_byte = *(uint8_t *)(ctx->h_scal + 8);
+    const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
+    LineView lv;
+    lv.text = d_text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
+    lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = 0;
+    uint8_t *lflags = ctx->buf<uint8_t>(B_LINE_FLAGS, n_lines + 1);
+    uint32_t *isrec = ctx->buf<uint32_t>(B_LINE_HEAD, n_lines + 1), *rscan = ctx->buf<uint32_t>(B_LINE_REC, n_lines + 1);
+    if (!lflags || !isrec || !rscan) return ctx->err_code;
+    LAUNCH(ctx, k_paf_line_flags, grid_for(n_lines + 1, 256), 256, lv, lflags, isrec);
+    WGA_TRY(exclusive_sum(ctx, isrec, rscan, n_lines + 1));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal, rscan + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    const uint64_t n_rec = *(uint32_t *)ctx->h_scal;
+    ctx->n_rec = n_rec;
+    if (n_rec == 0) return WGA_OK;
+    PafRecs R;
+    R.q_name_off = ctx->buf<uint64_t>(B_PAF_B, n_rec); R.t_name_off = ctx->buf<uint64_t>(B_PAF_C, n_rec);
+    R.cig_off = ctx->buf<uint64_t>(B_PAF_D, n_rec); R.cig_len = ctx->buf<uint64_t>(B_PAF_E, n_rec);
+    R.q_name_len = ctx->buf<uint32_t>(B_PAF_F, n_rec); R.t_name_len = ctx->buf<uint32_t>(B_PAF_G, n_rec);
+    uint64_t *m4 = ctx->buf<uint64_t>(B_PAF_H, 4 * n_rec);
+    R.neg = ctx->buf<uint8_t>(B_PAF_I, n_rec);
+    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
+    if (!R.q_name_off || !R.t_name_off || !R.cig_off || !R.cig_len || !R.q_name_len || !R.t_name_len || !m4 || !R.neg || !cnt11)
+        return ctx->err_code;
+    R.q_size = m4; R.t_size = m4 + n_rec; R.q_start = m4 + 2 * n_rec; R.t_start = m4 + 3 * n_rec;
+    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key);
+    WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key);
+    WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    uint64_t key;
+    WGA_TRY(read_scalars(ctx, {err_key}, &key));
+    {
+        float ms = 0.f;
+        WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->walk_ms = ms; ctx->walk_launches = 1; ctx->walk_bytes = len;
+    }
+    if (key != kNoErr) {
+        const int code = (int)(key & 0xFF);
+        const uint64_t rec = key >> 32;
+        std::string msg;
+        if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+        else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on an empty cg:Z: tag";
+        else {
+            uint64_t oc[2];
+            WGA_TRY(read_scalars(ctx, {R.cig_off + rec, R.cig_len + rec}, oc));
+            std::string cg((size_t)std::min<uint64_t>(oc[1], 1u << 20), '\0');
+            if (!cg.empty()) WGA_CK(cudaMemcpy(&cg[0], d_text + oc[0], cg.size(), cudaMemcpyDeviceToHost));
+            msg = paf_cigar_error_text(cg, code);
+        }
+        ctx->set_error(code, rec, msg);
+        return code;
+    }
+    RecMeta M;
+    M.text = d_text;
+    M.t_name_off = R.t_name_off; M.q_name_off = R.q_name_off; M.t_name_len = R.t_name_len; M.q_name_len = R.q_name_len;
+    M.t_size = R.t_size; M.q_size = R.q_size; M.t_start = R.t_start; M.q_start = R.q_start;
+    M.neg = R.neg; M.skip = nullptr;
+    int rc = stat_reduce(ctx, n_rec, M, cnt11, err_key, acc);
+    if (rc) return rc;
+    ctx->last_counts_valid = true;
+    return WGA_OK;
 }
 #endif
 
