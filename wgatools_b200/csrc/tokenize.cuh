@@ -210,6 +210,24 @@ __global__ void k_ws_compact(uint64_t n_tiles, const uint64_t *__restrict__ tile
     const uint64_t base = t * kTokTile;
     uint16_t *slot = slots + t * CAP;
     // entries arrive ordered step by step, unordered inside a step: insertion sort on tile-relative offset
+    constexpr int kLocal = 48;
+    if (c <= (uint32_t)kLocal) {  // the common case: a handful of entries, sorted in thread-local storage
+        uint16_t e[kLocal];
+        for (uint32_t i = 0; i < c; ++i) e[i] = slot[i];
+        for (uint32_t i = 1; i < c; ++i) {
+            const uint16_t v = e[i];
+            uint32_t j = i;
+            while (j > 0 && (e[j - 1] & 0x7FFFu) > (v & 0x7FFFu)) { e[j] = e[j - 1]; --j; }
+            e[j] = v;
+        }
+        for (uint32_t i = 0; i < c; ++i) {
+            const uint32_t v = e[i];
+            const bool isnl = v >> 15;
+            ws_ent[wo + i] = (base + (v & 0x7FFFu)) | (isnl ? ~kPosMask : 0ull);
+            if (isnl) nl_ws_idx[no++] = wo + i;
+        }
+        return;
+    }
     for (uint32_t i = 1; i < c; ++i) {
         const uint16_t e = slot[i];
         uint32_t j = i;

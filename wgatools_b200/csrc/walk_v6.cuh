@@ -37,7 +37,7 @@ constexpr uint32_t kSlotPad = 16;
 struct __align__(16) ItemDesc {  // one work item: columns [seg*kSeg, seg*kSeg+n) of record rec
     uint64_t t_off, q_off;       // byte offsets of the item's first column in target / query
     uint32_t n, rec, seg, tail;  // tail: columns of the record after this item, clipped to 16
-    uint64_t slot_base;          // first slot of the item's run-head region (cold: read when heads are emitted)
+    uint64_t slot_base;          // first slot of the item's run-head region (cold: only read when heads are emitted)
     uint64_t pad;
 };
 static_assert(sizeof(ItemDesc) == 48, "ItemDesc is read as three 16-byte vectors");
@@ -208,198 +208,230 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
     }
 }
 
-// geometry of one work item in the 16-byte frame of its target stream (only what the streaming loop needs; the
-// record id, the slot base and the column preceding the item are re-read from the descriptor on the cold path)
-struct Geom {
-    const uint8_t *tbase, *qbase;  // 16-byte aligned; chunk j covers item columns [16j-a, 16j-a+16)
-    uint32_t a, s, n, item, ts;    // ts = tail | (seg == 0) << 8
-    __device__ __forceinline__ uint32_t nch() const { return (n + a + 15u) >> 4; }
-    __device__ __forceinline__ uint32_t q_last() const { return (s + n + a - 1u) >> 4; }  // last query vector needed
-};
+// push the slow chunks of one step into the warp queue and run a batch when 32 are queued (cold path: kept out of
+// line so that the four word-shift instantiations of the streaming loop stay small)
+// run one batch of 32 queued chunks and shift the remainder of the queue down (out of line: it runs once per 32
+// slow chunks, and keeping it out of the streaming loop keeps that loop's register footprint small)
+template <int MODE>
+__device__ __noinline__ uint3 walk_flush(const WalkArgs &A, uint32_t (*Q)[64], uint32_t qn, uint32_t open_item, uint32_t open_count) {
+    const uint32_t lane = threadIdx.x & 31;
+    WarpEmit E;
+    E.open_item = open_item;
+    E.open_count = open_count;
+    walk_batch<MODE>(A, Q, 32, lane, E);
+    __syncwarp();
+    qn -= 32;
+    uint32_t mv[11];
+    if (lane < qn) {
+#pragma unroll
+        for (int f = 0; f < 11; ++f) mv[f] = Q[f][lane + 32];
+    }
+    __syncwarp();
+    if (lane < qn) {
+#pragma unroll
+        for (int f = 0; f < 11; ++f) Q[f][lane] = mv[f];
+    }
+    __syncwarp();
+    return make_uint3(qn, E.open_item, E.open_count);
+}
 
-__device__ __forceinline__ Geom make_geom(const WalkArgs &A, const uint4 &d0, const uint4 &d1, uint32_t item) {
-    Geom g;
+// geometry of one work item in the 16-byte frame of its target stream (hot fields only: the record id, the slot
+// base and the column preceding the item are re-read from the descriptor on the cold path)
+struct G {
+    const uint8_t *tptr, *qptr;  // lane-adjusted pointers to chunk `lane` (16-byte aligned)
+    uint32_t a, s, n, item, ts;  // ts = tail | (seg == 0) << 8
+};
+__device__ __forceinline__ G make_g(const WalkArgs &A, const uint4 &d0, const uint4 &d1, uint32_t item, uint32_t lane) {
+    G g;
     const uint64_t t_off = ((uint64_t)d0.y << 32) | d0.x, q_off = ((uint64_t)d0.w << 32) | d0.z;
     g.n = d1.x; g.item = item;
     g.ts = d1.w | ((d1.z == 0 ? 1u : 0u) << 8);
     const uint8_t *tp = A.text + t_off, *qp = A.text + q_off;
     g.a = (uint32_t)(reinterpret_cast<uintptr_t>(tp) & 15u);
-    g.tbase = tp - g.a;
-    const uint8_t *qv = qp - g.a;  // query byte stream in the same column frame
+    const uint8_t *qv = qp - g.a;  // query byte stream in the column frame of the aligned target stream
     g.s = (uint32_t)(reinterpret_cast<uintptr_t>(qv) & 15u);
-    g.qbase = qv - g.s;
+    g.tptr = tp - g.a + 16u * lane;  // chunk j covers item columns [16j-a, 16j-a+16)
+    g.qptr = qv - g.s + 16u * lane;
     return g;
 }
-
-struct Vec3 { uint4 t, q0, q1; };
-__device__ __forceinline__ Vec3 load_vec(const Geom &g, uint32_t j) {
-    Vec3 v;
-    v.t = make_uint4(0, 0, 0, 0); v.q0 = v.t; v.q1 = v.t;
-    if (j < g.nch()) {
-        v.t = ldg16(g.tbase + 16ull * j);
-        v.q0 = ldg16(g.qbase + 16ull * j);
-        if (g.s != 0 && j + 1 <= g.q_last()) v.q1 = ldg16(g.qbase + 16ull * (j + 1));
+__device__ __forceinline__ void load_first(const G &g, uint32_t lane, uint4 &tv, uint4 &q0, uint4 &q1) {
+    const int jrem = (int)((g.n + g.a + 15u) >> 4) - (int)lane, qrem = (int)((g.s + g.n + g.a - 1u) >> 4) - (int)lane;
+    tv = make_uint4(0, 0, 0, 0); q0 = tv; q1 = tv;
+    if (jrem > 0) {
+        tv = ldg16(g.tptr);
+        q0 = ldg16(g.qptr);
+        if (g.s != 0 && qrem > 0) q1 = ldg16(g.qptr + 16);
     }
-    return v;
 }
 
-template <int WS>
-__device__ __forceinline__ void realign(const uint4 &q0, const uint4 &q1, uint32_t sh, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
-    uint32_t w0, w1, w2, w3, w4;
-    if (WS == 0) { w0 = q0.x; w1 = q0.y; w2 = q0.z; w3 = q0.w; w4 = q1.x; }
-    else if (WS == 1) { w0 = q0.y; w1 = q0.z; w2 = q0.w; w3 = q1.x; w4 = q1.y; }
-    else if (WS == 2) { w0 = q0.z; w1 = q0.w; w2 = q1.x; w3 = q1.y; w4 = q1.z; }
-    else { w0 = q0.w; w1 = q1.x; w2 = q1.y; w3 = q1.z; w4 = q1.w; }
-    o0 = __funnelshift_r(w0, w1, sh); o1 = __funnelshift_r(w1, w2, sh);
-    o2 = __funnelshift_r(w2, w3, sh); o3 = __funnelshift_r(w3, w4, sh);
+// descriptor prefetch through shared memory (cp.async keeps the 32 hot bytes out of the register file)
+__device__ __forceinline__ void desc_prefetch(uint32_t *dst_smem, const ItemDesc *src, uint32_t lane) {
+    if (lane < 2) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem + 4 * lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(reinterpret_cast<const uint4 *>(src) + lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void desc_wait() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
 }
 
-// one step (32 chunks) of the current item: 128-bit compare, push the slow chunks, run a batch when 32 are queued
-template <int MODE>
-__device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane,
-                                          const Geom &g, uint32_t j0, const Vec3 &v, uint32_t &carry) {
+struct Sched {  // dynamic work distribution: batches of kGrab consecutive items from a global counter
+    uint32_t it, end, nb_raw;
+};
+constexpr uint32_t kGrab = 8;
+__device__ __forceinline__ bool sched_next(const WalkArgs &A, Sched &S, uint32_t n_items, uint32_t lane) {
+    ++S.it;
+    if (S.it < S.end) return true;
+    const uint32_t nb = __shfl_sync(0xFFFFFFFFu, S.nb_raw, 0);
+    if (nb >= n_items) { S.it = n_items; return false; }
+    S.it = nb;
+    S.end = nb + kGrab < n_items ? nb + kGrab : n_items;
+    if (lane == 0) S.nb_raw = atomicAdd(A.sched, kGrab);  // requested one batch ahead
+    return true;
+}
+
+// stream one item.  WS = word part of the query misalignment (compile-time word select).
+// On its last step the warp turns the prefetched descriptor of its next item into a geometry, requests that
+// item's first vectors and starts the descriptor prefetch of the item after it.
+template <int MODE, int WS>
+__device__ __forceinline__ void walk_item(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane, G &g,
+                                          uint4 &tv, uint4 &q0, uint4 &q1, bool &have_next, uint32_t *dslot, uint32_t &dpar,
+                                          Sched &S, uint32_t n_items) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
-    const uint32_t j = j0 + lane;
-    const bool act = j < g.nch();
-    const uint4 tv = v.t;
-    uint32_t qw0, qw1, qw2, qw3;
-    const uint32_t sh = (g.s & 3u) * 8u;
-    switch (g.s >> 2) {  // warp-uniform
-        case 0: realign<0>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
-        case 1: realign<1>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
-        case 2: realign<2>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
-        default: realign<3>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
-    }
-    // last column of this chunk -> neighbour lane (previous column of the next chunk)
-    const uint32_t lastb = act ? ((tv.w >> 24) | ((qw3 >> 24) << 8)) : 0u;
-    uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, lastb, 1);
-    if (lane == 0) pb = carry;
-    carry = __shfl_sync(0xFFFFFFFFu, lastb, 31);
-    uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | (tv.w ^ qw3);
-    bool prev_ne = (pb & 0xFFu) != (pb >> 8);
-    if (CALLER) {
-        x |= has_zero_byte(tv.x ^ kGap4) | has_zero_byte(tv.y ^ kGap4) | has_zero_byte(tv.z ^ kGap4) |
-             has_zero_byte(tv.w ^ kGap4);
-        prev_ne |= (pb & 0xFFu) == '-';
-    }
+    const uint32_t a = g.a, n = g.n;
+    const uint32_t nch = (n + a + 15u) >> 4, q_last = (g.s + n + a - 1u) >> 4;
+    const uint32_t bs8 = (g.s & 3u) * 8u;
+    const bool two = g.s != 0;
     // interior chunks: fully inside the item -> 16j >= a and 16j+16 <= n+a
-    const uint32_t jf = (g.a + 15u) >> 4, jl = (g.n + g.a) >> 4;
-    const bool edge = j == 0 || j < jf || j >= jl;
-    const bool slow = act && (edge || x != 0u || prev_ne);
-    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
-    if (mask) {
-        if (slow) {
-            const uint32_t slot = qn + __popc(mask & ((1u << lane) - 1u));
-            Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
-            Q[4][slot] = qw0; Q[5][slot] = qw1; Q[6][slot] = qw2; Q[7][slot] = qw3;
+    const uint32_t jf = (a + 15u) >> 4, jl = (n + a) >> 4;
+    const uint8_t *tptr = g.tptr, *qptr = g.qptr;
+    int jrem = (int)nch - (int)lane;     // chunk j = j0+lane exists iff jrem > 0
+    int qrem = (int)q_last - (int)lane;  // its second query vector is needed iff qrem > 0
+    uint32_t carry = 0;                  // (t,q) bytes of the column before this step's first chunk: t | q<<8
+    uint32_t j = lane;
+    G nxt = g;
+    for (;;) {
+        const bool act = jrem > 0;
+        const bool more = j + 32 - lane < nch;  // warp-uniform: this item has another step
+        tptr += 512; qptr += 512; jrem -= 32; qrem -= 32;
+        uint4 ntv = make_uint4(0, 0, 0, 0), nq0 = ntv, nq1 = ntv;
+        if (more) {
+            if (jrem > 0) {
+                ntv = ldg16(tptr);
+                nq0 = ldg16(qptr);
+                if (two && qrem > 0) nq1 = ldg16(qptr + 16);
+            }
+        } else if (have_next) {
+            desc_wait();
+            const uint4 e0 = *reinterpret_cast<const uint4 *>(dslot + 8 * dpar);
+            const uint4 e1 = *reinterpret_cast<const uint4 *>(dslot + 8 * dpar + 4);
+            nxt = make_g(A, e0, e1, S.it, lane);
+            load_first(nxt, lane, ntv, nq0, nq1);
+            have_next = sched_next(A, S, n_items, lane);
+            dpar ^= 1u;
+            __syncwarp();
+            if (have_next) desc_prefetch(dslot + 8 * dpar, A.items + S.it, lane);
+            have_next = true | have_next;  // (the item just turned into `nxt` exists; S.it now names the one after)
+        }
+        uint32_t w0, w1, w2, w3, w4;
+        if (WS == 0) { w0 = q0.x; w1 = q0.y; w2 = q0.z; w3 = q0.w; w4 = q1.x; }
+        else if (WS == 1) { w0 = q0.y; w1 = q0.z; w2 = q0.w; w3 = q1.x; w4 = q1.y; }
+        else if (WS == 2) { w0 = q0.z; w1 = q0.w; w2 = q1.x; w3 = q1.y; w4 = q1.z; }
+        else { w0 = q0.w; w1 = q1.x; w2 = q1.y; w3 = q1.z; w4 = q1.w; }
+        const uint32_t qw0 = __funnelshift_r(w0, w1, bs8), qw1 = __funnelshift_r(w1, w2, bs8),
+                       qw2 = __funnelshift_r(w2, w3, bs8), qw3 = __funnelshift_r(w3, w4, bs8);
+        // last column of this chunk -> neighbour lane (previous column of the next chunk)
+        const uint32_t lastb = act ? __byte_perm(tv.w, qw3, 0x4473) & 0xFFFFu : 0u;  // t[15] | q[15]<<8
+        uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, lastb, 1);
+        if (lane == 0) pb = carry;
+        carry = __shfl_sync(0xFFFFFFFFu, lastb, 31);
+        uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | (tv.w ^ qw3);
+        bool prev_ne = (pb & 0xFFu) != (pb >> 8);
+        if (CALLER) {
+            x |= has_zero_byte(tv.x ^ kGap4) | has_zero_byte(tv.y ^ kGap4) | has_zero_byte(tv.z ^ kGap4) |
+                 has_zero_byte(tv.w ^ kGap4);
+            prev_ne |= (pb & 0xFFu) == '-';
+        }
+        const bool edge = j == 0 || j < jf || j >= jl;
+        const bool slow = act && (edge || x != 0u || prev_ne);
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
+        if (mask) {
             const uint32_t seg0 = g.ts >> 8;
-            uint32_t prev = (1u << 16) | pb;
-            if (j == 0) {  // column preceding chunk 0 (only matters when a == 0; otherwise it sits inside chunk 0)
-                prev = 0;
-                if (g.a == 0 && !seg0)
-                    prev = (1u << 16) | ((uint32_t)g.qbase[(int)g.s - 1] << 8) | (uint32_t)g.tbase[-1];
+            uint32_t f0 = 0, t0 = 16, t1 = 16, prev = (1u << 16) | pb;
+            if (slow) {
+                if (edge) {
+                    const int64_t lo = (int64_t)a - 16ll * j, hi = (int64_t)n + (int64_t)a - 16ll * j;
+                    f0 = clamp16(lo);
+                    t0 = clamp16(hi);
+                    t1 = clamp16(hi + (int64_t)(g.ts & 0xFFu));  // columns of the next item are context only
+                }
+                if (j == 0) {  // column preceding chunk 0 (only matters when a == 0; otherwise it sits inside chunk 0)
+                    prev = 0;
+                    if (a == 0 && !seg0) prev = (1u << 16) | ((uint32_t)g.qptr[(int)g.s - 1] << 8) | (uint32_t)g.tptr[-1];
+                }
             }
-            Q[8][slot] = prev;
-            uint32_t f0 = 0, t0 = 16, t1 = 16;
-            if (edge) {
-                const int64_t lo = (int64_t)g.a - 16ll * j, hi = (int64_t)g.n + (int64_t)g.a - 16ll * j;
-                f0 = clamp16(lo);
-                t0 = clamp16(hi);
-                t1 = clamp16(hi + (int64_t)(g.ts & 0xFFu));  // columns of the next item are context only
+            const uint32_t meta = f0 | (t0 << 5) | (t1 << 10) | (seg0 << 15) | ((16u * j + 16u - a) << 16);
+            if (slow) {
+                const uint32_t slot = qn + __popc(mask & ((1u << lane) - 1u));
+                Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
+                Q[4][slot] = qw0; Q[5][slot] = qw1; Q[6][slot] = qw2; Q[7][slot] = qw3;
+                Q[8][slot] = prev; Q[9][slot] = meta; Q[10][slot] = g.item;
             }
-            Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | (seg0 << 15) | ((16u * j + 16u - g.a) << 16);
-            Q[10][slot] = g.item;
+            qn += __popc(mask);
+            __syncwarp();
+            if (qn >= 32) {
+                const uint3 st = walk_flush<MODE>(A, Q, qn, E.open_item, E.open_count);
+                qn = st.x; E.open_item = st.y; E.open_count = st.z;
+            }
         }
-        qn += __popc(mask);
-        __syncwarp();
-        if (qn >= 32) {
-            walk_batch<MODE>(A, Q, 32, lane, E);
-            __syncwarp();
-            qn -= 32;
-            uint32_t mv[11];
-            if (lane < qn) {
-#pragma unroll
-                for (int f = 0; f < 11; ++f) mv[f] = Q[f][lane + 32];
-            }
-            __syncwarp();
-            if (lane < qn) {
-#pragma unroll
-                for (int f = 0; f < 11; ++f) Q[f][lane] = mv[f];
-            }
-            __syncwarp();
-        }
+        j += 32;
+        tv = ntv; q0 = nq0; q1 = nq1;
+        if (!more) break;
     }
+    g = nxt;
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs A) {
     constexpr bool RUNS = MODE != MODE_STAT;
-    __shared__ uint32_t s_queue[kWalkWarps][11][64];  // per warp, SoA, 64 slots
+    __shared__ uint32_t s_queue[kWalkWarps][11][64];          // per warp, SoA, 64 slots
+    __shared__ __align__(16) uint32_t s_desc[kWalkWarps][16];  // per warp: two 32-byte descriptor slots
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t (*Q)[64] = s_queue[wid];
-    uint32_t qn = 0;
+    uint32_t *dslot = s_desc[wid];
+    uint32_t qn = 0, dpar = 0;
     WarpEmit E;
     E.open_item = 0xFFFFFFFFu;
     E.open_count = 0;
-
-    // Dynamic scheduling: warps grab batches of kGrab consecutive items from a global counter (record lengths are
-    // log-normal, a static split leaves a 30-50 % tail).  The next batch is always requested one batch ahead.
-    // Software pipeline across items: the descriptor of the item after next and the first vectors of the next
-    // item are requested while the current item is being walked.
-    constexpr uint32_t kGrab = 8;
     const uint32_t n_items = (uint32_t)A.n_items;
-    uint32_t s_it = 0, s_end = 0, nb_raw = 0;  // scheduler: last handed-out item, end of its batch, next batch (lane 0)
+    Sched S;
+    S.it = 0; S.end = 0; S.nb_raw = 0;
     if (lane == 0) {
-        s_it = atomicAdd(A.sched, kGrab);
-        nb_raw = atomicAdd(A.sched, kGrab);
+        S.it = atomicAdd(A.sched, kGrab);
+        S.nb_raw = atomicAdd(A.sched, kGrab);
     }
-    s_it = __shfl_sync(0xFFFFFFFFu, s_it, 0);
-    s_end = s_it + kGrab < n_items ? s_it + kGrab : n_items;
-    auto advance = [&]() -> bool {  // moves (s_it) to the next item of this warp; false when the work is exhausted
-        ++s_it;
-        if (s_it < s_end) return true;
-        const uint32_t nb = __shfl_sync(0xFFFFFFFFu, nb_raw, 0);
-        if (nb >= n_items) { s_it = n_items; return false; }
-        s_it = nb;
-        s_end = nb + kGrab < n_items ? nb + kGrab : n_items;
-        if (lane == 0) nb_raw = atomicAdd(A.sched, kGrab);
-        return true;
-    };
-    if (s_it < n_items) {
-        const uint32_t item = s_it;
-        const uint4 *dp = reinterpret_cast<const uint4 *>(A.items + item);
-        Geom cur = make_geom(A, __ldg(dp), __ldg(dp + 1), item);
-        bool has2 = advance();
-        uint32_t item2 = s_it;
-        uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
-        if (has2) {
-            const uint4 *ep = reinterpret_cast<const uint4 *>(A.items + item2);
-            e0 = __ldg(ep); e1 = __ldg(ep + 1);
-        }
-        Vec3 v = load_vec(cur, lane);
+    S.it = __shfl_sync(0xFFFFFFFFu, S.it, 0);
+    S.end = S.it + kGrab < n_items ? S.it + kGrab : n_items;
+    if (S.it < n_items) {
+        const uint4 *dp = reinterpret_cast<const uint4 *>(A.items + S.it);
+        G cur = make_g(A, __ldg(dp), __ldg(dp + 1), S.it, lane);
+        uint4 tv, q0, q1;
+        load_first(cur, lane, tv, q0, q1);
+        bool have_next = sched_next(A, S, n_items, lane);  // S.it = the warp's next item
+        if (have_next) desc_prefetch(dslot + 8 * dpar, A.items + S.it, lane);
         for (;;) {
-            Geom nxt = cur;
-            if (has2) nxt = make_geom(A, e0, e1, item2);
-            const bool has3 = has2 && advance();
-            const uint32_t item3 = s_it;
-            if (has3) {
-                const uint4 *ep = reinterpret_cast<const uint4 *>(A.items + item3);
-                e0 = __ldg(ep); e1 = __ldg(ep + 1);
+            const bool had_next = have_next;
+            bool hn = have_next;
+            switch (cur.s >> 2) {  // warp-uniform
+                case 0: walk_item<MODE, 0>(A, Q, qn, E, lane, cur, tv, q0, q1, hn, dslot, dpar, S, n_items); break;
+                case 1: walk_item<MODE, 1>(A, Q, qn, E, lane, cur, tv, q0, q1, hn, dslot, dpar, S, n_items); break;
+                case 2: walk_item<MODE, 2>(A, Q, qn, E, lane, cur, tv, q0, q1, hn, dslot, dpar, S, n_items); break;
+                default: walk_item<MODE, 3>(A, Q, qn, E, lane, cur, tv, q0, q1, hn, dslot, dpar, S, n_items); break;
             }
-            uint32_t carry = 0;  // (t,q) bytes of the column before this step's first chunk: t | q<<8
-            const uint32_t cur_nch = cur.nch();
-            for (uint32_t j0 = 0; j0 < cur_nch; j0 += 32) {
-                Vec3 nv;
-                if (j0 + 32 < cur_nch) nv = load_vec(cur, j0 + 32 + lane);
-                else if (has2) nv = load_vec(nxt, lane);
-                else { nv.t = make_uint4(0, 0, 0, 0); nv.q0 = nv.t; nv.q1 = nv.t; }
-                walk_step<MODE>(A, Q, qn, E, lane, cur, j0, v, carry);
-                v = nv;
-            }
-            if (!has2) break;
-            cur = nxt;
-            item2 = item3;
-            has2 = has3;
+            if (!had_next) break;   // the item just walked was the warp's last
+            have_next = S.it < n_items;  // is there an item after the one now in `cur`?
         }
     }
     if (qn) {

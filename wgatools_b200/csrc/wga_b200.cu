@@ -7,7 +7,11 @@
 #include "stat.cuh"
 #include "stat_acc.hpp"
 #include "tokenize.cuh"
+#ifdef WGA_WALK_V6
+#include "walk_v6.cuh"
+#else
 #include "walk.cuh"
+#endif
 #ifdef WGA_WITH_CALL
 #include "call.cuh"
 #endif
