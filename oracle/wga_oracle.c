@@ -1333,3 +1333,162 @@ int orc_stat_maf_mt(const char *text, size_t len, int each, const char *query_na
     free(v.r);
     return rc;
 }
+
+/* ======================================================================================
+ * paf2maf  (src/converter.rs:176-265) with the FASTA access of rust-htslib 0.44 / htslib faidx
+ * (un-vendored; restated from the published htslib faidx.c: faidx_adjust_position + fai_retrieve).
+ * ====================================================================================== */
+typedef struct { sv name; uint64_t len, offset, linebases, linewidth; } fai_ent;
+typedef struct { fai_ent *e; size_t n; const char *fa; size_t fa_len; } faidx;
+
+static int fai_parse(const char *fai, size_t fai_len, const char *fa, size_t fa_len, faidx *out) {
+    out->e = NULL; out->n = 0; out->fa = fa; out->fa_len = fa_len;
+    size_t cap = 0, i = 0;
+    while (i < fai_len) {
+        size_t j = i;
+        while (j < fai_len && fai[j] != '\n') j++;
+        sv f[5]; int nf = 0; size_t b = i;
+        for (size_t k = i; k <= j && nf < 5; k++)
+            if (k == j || fai[k] == '\t') { f[nf].p = fai + b; f[nf].n = k - b; nf++; b = k + 1; }
+        if (nf == 5) {
+            if (out->n == cap) { cap = cap ? cap * 2 : 64; out->e = (fai_ent *)realloc(out->e, cap * sizeof(fai_ent)); }
+            fai_ent *e = &out->e[out->n];
+            e->name = f[0];
+            if (!parse_u64(f[1], &e->len) || !parse_u64(f[2], &e->offset) || !parse_u64(f[3], &e->linebases) ||
+                !parse_u64(f[4], &e->linewidth)) return -1;
+            out->n++;
+        }
+        i = j + 1;
+    }
+    return 0;
+}
+
+/* faidx_fetch_seq64(name, beg, end) with end INCLUSIVE; returns 0 and appends the bases, -1 if name is unknown */
+static int fai_fetch(const faidx *fx, sv name, uint64_t beg_u, uint64_t end_u, orc_buf *out) {
+    const fai_ent *e = NULL;
+    for (size_t i = 0; i < fx->n; i++)
+        if (sv_eq(fx->e[i].name, name)) { e = &fx->e[i]; break; }
+    if (!e) return -1;
+    int64_t beg = (int64_t)beg_u, end = (int64_t)end_u, len = (int64_t)e->len;
+    /* faidx_adjust_position(end_adjust = 1) */
+    if (end < beg) beg = end;
+    if (beg < 0) beg = 0; else if (len <= beg) beg = len;
+    if (end < 0) end = 0; else if (len <= end) end = len - 1;
+    /* fai_retrieve(offset, beg, end + 1): seek, then take isgraph() bytes until the count is reached */
+    int64_t want = end + 1 - beg;
+    if (want <= 0 || e->linebases == 0) return 0;
+    uint64_t pos = e->offset + (uint64_t)beg / e->linebases * e->linewidth + (uint64_t)beg % e->linebases;
+    int64_t l = 0;
+    while (l < want && pos < fx->fa_len) {
+        unsigned char c = (unsigned char)fx->fa[pos++];
+        if (c > 32 && c < 127) { buf_putc(out, (char)c); l++; }
+    }
+    return 0;
+}
+
+/* utils.rs:83-101 reverse_complement; returns the offending char or 0 */
+static char revcomp_inplace(char *s, size_t n) {
+    for (size_t i = 0; i < n; i++) { /* validate in the reference's iteration order: from the END of the input */
+        char c = s[n - 1 - i];
+        if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N' || c == 'a' || c == 'c' || c == 'g' || c == 't' || c == 'n'))
+            return c;
+    }
+    for (size_t i = 0; i < n / 2; i++) { char t = s[i]; s[i] = s[n - 1 - i]; s[n - 1 - i] = t; }
+    for (size_t i = 0; i < n; i++) {
+        switch (s[i]) {
+        case 'A': s[i] = 'T'; break; case 'C': s[i] = 'G'; break; case 'G': s[i] = 'C'; break; case 'T': s[i] = 'A'; break;
+        case 'a': s[i] = 't'; break; case 'c': s[i] = 'g'; break; case 'g': s[i] = 'c'; break; case 't': s[i] = 'a'; break;
+        default: break;
+        }
+    }
+    return 0;
+}
+
+/* String::insert_str(idx, "-" * n) on an orc_buf */
+static int buf_insert_gaps(orc_buf *b, uint64_t idx, uint64_t n) {
+    if (idx > b->n) return -1; /* insert_str panics when idx is past the end */
+    buf_reserve(b, n);
+    memmove(b->p + idx + n, b->p + idx, b->n - idx);
+    memset(b->p + idx, '-', n);
+    b->n += n;
+    return 0;
+}
+
+int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_len, const char *t_fai, size_t t_fai_len,
+                const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, const char *t_path,
+                const char *q_path, orc_buf *out, char *err, size_t errcap) {
+    faidx tf, qf;
+    if (fai_parse(t_fai, t_fai_len, t_fa, t_fa_len, &tf) || fai_parse(q_fai, q_fai_len, q_fa, q_fa_len, &qf)) {
+        set_err(err, errcap, "HTS library error by bad .fai");
+        return ORC_E_CSV;
+    }
+    /* converter.rs:190-195 header */
+    buf_puts(out, "#maf version=1.6 convert_from=paf t_seq_path=");
+    buf_puts(out, t_path);
+    buf_puts(out, " q_seq_path=");
+    buf_puts(out, q_path);
+    buf_putc(out, '\n');
+    size_t pos = 0;
+    pafrow row = {0};
+    orc_buf ts = {0}, qs = {0};
+    int rc = ORC_OK;
+    while (rc == ORC_OK && paf_next(paf, paf_len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int neg = 0, bad = row.n < 12;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) { if (sv_eq_c(row.f[4], "+")) neg = 0; else if (sv_eq_c(row.f[4], "-")) neg = 1; else bad = 1; continue; }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+        sv qname = row.f[0], tname = row.f[5];
+        uint64_t q_size = u[1], q_st = u[2], q_en = u[3], t_size = u[6], t_st = u[7], t_en = u[8], mapq = u[11];
+        uint64_t q_start_maf = neg ? q_size - q_en : q_st; /* converter.rs:213-216 */
+        ts.n = 0; qs.n = 0;
+        if (fai_fetch(&tf, tname, t_st, t_en - 1, &ts) || fai_fetch(&qf, qname, q_st, q_en - 1, &qs)) {
+            set_err(err, errcap, "HTS library error by sequence not found");
+            rc = ORC_E_NOM; break;
+        }
+        if (neg) {
+            char c = revcomp_inplace(qs.p, qs.n);
+            if (c) { set_err(err, errcap, "Invalid Base: `%c`", c); rc = ORC_E_VCF_BASE; break; }
+        }
+        /* cigar.rs:492-551 parse_cigar_to_insert */
+        sv cg = {0, 0}; int have = 0;
+        for (size_t k = 12; k < row.n && !have; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
+        if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
+        if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
+        uint64_t off = 0;
+        size_t i = 0;
+        while (i < cg.n && rc == ORC_OK) {
+            size_t d0 = i;
+            while (i < cg.n && cg.p[i] >= '0' && cg.p[i] <= '9') i++;
+            size_t o0 = i;
+            while (i < cg.n && !(cg.p[i] >= '0' && cg.p[i] <= '9')) i++;
+            sv digits = {cg.p + d0, o0 - d0}, op = {cg.p + o0, i - o0};
+            uint64_t cnt;
+            if (op.n != 1) { set_err(err, errcap, "CIGAR OP `%.*s` invalid", (int)op.n, op.p); rc = ORC_E_CIGAR_OP_INVALID; break; }
+            if (!parse_u64(digits, &cnt)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)digits.n, digits.p); rc = ORC_E_PARSE_INT; break; }
+            switch (op.p[0]) {
+            case 'M': case '=': case 'X': off += cnt; break;
+            case 'I': if (buf_insert_gaps(&ts, off, cnt)) { set_err(err, errcap, "panic: insert_str index out of range"); rc = ORC_E_PANIC; } off += cnt; break;
+            case 'D': if (buf_insert_gaps(&qs, off, cnt)) { set_err(err, errcap, "panic: insert_str index out of range"); rc = ORC_E_PANIC; } off += cnt; break;
+            default: set_err(err, errcap, "CIGAR OP `%c` invalid", op.p[0]); rc = ORC_E_CIGAR_OP_INVALID; break;
+            }
+        }
+        if (rc) break;
+        /* maf.rs:566-581 MAFWriter::write_record */
+        buf_puts(out, "a score="); buf_putu(out, mapq); buf_putc(out, '\n');
+        buf_puts(out, "s\t"); buf_put(out, tname.p, tname.n); buf_putc(out, '\t'); buf_putu(out, t_st); buf_putc(out, '\t');
+        buf_putu(out, t_en - t_st); buf_puts(out, "\t+\t"); buf_putu(out, t_size); buf_putc(out, '\t');
+        buf_put(out, ts.p, ts.n); buf_putc(out, '\n');
+        buf_puts(out, "s\t"); buf_put(out, qname.p, qname.n); buf_putc(out, '\t'); buf_putu(out, q_start_maf); buf_putc(out, '\t');
+        buf_putu(out, q_en - q_st); buf_putc(out, '\t'); buf_putc(out, neg ? '-' : '+'); buf_putc(out, '\t'); buf_putu(out, q_size);
+        buf_putc(out, '\t'); buf_put(out, qs.p, qs.n); buf_putc(out, '\n');
+        buf_putc(out, '\n');
+    }
+    free(row.f); free(row.scratch); free(tf.e); free(qf.e);
+    orc_buf_free(&ts); orc_buf_free(&qs);
+    return rc;
+}

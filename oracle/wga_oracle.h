@@ -88,6 +88,13 @@ int orc_maf2paf_mt(const char *text, size_t len, const char *query_name, int thr
 int orc_stat_maf_mt(const char *text, size_t len, int each, const char *query_name, int threads, orc_buf *out,
                     char *err, size_t errcap);
 
+/* src/converter.rs:176-265 paf2maf; FASTA access = htslib faidx_fetch_seq64 (inclusive end, clipped to the sequence).
+ * The header (and every block before a failing record) would already have been written by the reference; on error the
+ * buffer holds that partial output. */
+int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_len, const char *t_fai, size_t t_fai_len,
+                const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, const char *t_path,
+                const char *q_path, orc_buf *out, char *err, size_t errcap);
+
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */
 void orc_fmt_f32(float v, char *dst /* >= 32 bytes */);      /* ryu 1.0.14 Buffer::format(f32) */

@@ -54,6 +54,8 @@ def lib():
                                      ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_stat_maf_mt.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
                                       ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_paf2maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 5 + [ctypes.c_char_p, ctypes.c_char_p,
+                                                                             ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -114,6 +116,37 @@ def call_maf(text: bytes, snp=False, inv=False, svlen=50, sample="sample", query
              chunk_size=1000000) -> bytes:
     return _run(lib().orc_call_maf, text, len(text), int(snp), int(inv), svlen, _opt(sample),
                 _opt(query_name), chunk_size)
+
+
+def paf2maf(paf: bytes, t_fa: bytes, t_fai: bytes, q_fa: bytes, q_fai: bytes, t_path="t.fa", q_path="q.fa") -> bytes:
+    return _run(lib().orc_paf2maf, paf, len(paf), t_fa, len(t_fa), t_fai, len(t_fai), q_fa, len(q_fa), q_fai, len(q_fai),
+                _opt(t_path), _opt(q_path))
+
+
+def make_fai(fa: bytes) -> bytes:
+    """samtools-faidx-style index of an in-memory FASTA (uniform line width per record assumed)"""
+    out, pos = [], 0
+    lines = fa.split(b"\n")
+    i = 0
+    while i < len(lines):
+        l = lines[i]
+        if l.startswith(b">"):
+            name = l[1:].split()[0]
+            pos += len(l) + 1
+            off, n, lb, lw = pos, 0, 0, 0
+            i += 1
+            while i < len(lines) and not lines[i].startswith(b">"):
+                if lines[i]:
+                    if lb == 0:
+                        lb, lw = len(lines[i]), len(lines[i]) + 1
+                    n += len(lines[i])
+                pos += len(lines[i]) + 1
+                i += 1
+            out.append(b"%s\t%d\t%d\t%d\t%d" % (name, n, off, lb, lw))
+        else:
+            pos += len(l) + 1
+            i += 1
+    return b"\n".join(out) + b"\n"
 
 
 def paf_cigar_counts(cg: bytes, neg=False):

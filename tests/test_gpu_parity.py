@@ -433,3 +433,43 @@ def test_paf_stat_synthetic(w, ctx, seed, kw):
     check_paf(w, ctx, text)
     cnt = ctx.last_record_counts()
     assert len(cnt) == n
+
+
+# ------------------------------------------------------------------------- larger inputs (seconds of oracle time)
+def test_large_config2_exact(w, ctx):
+    """100 k blocks (0.67 GB) of the bench workload: all three commands byte-identical to the oracle."""
+    text = bs.gen_maf(bs.maf_params(100_000, seed=20260926))
+    assert paf(w, ctx, text) == orc.maf2paf(text)
+    assert stat(w, ctx, text) == orc.stat_maf(text)
+    assert vcf(w, ctx, text, snp=True, svlen=0) == orc.call_maf(text, snp=True, svlen=0)
+    assert vcf(w, ctx, text) == orc.call_maf(text)
+
+
+def test_large_config3_long_records_exact(w, ctx):
+    """human-vs-human shape (SURVEY 8(d) cfg 3): blocks up to 5 M columns so that the 1 M-column chunk grid, SVs and
+    multi-item records are all exercised; default call and call -s -l0 --inv."""
+    text = bs.gen_maf(bs.maf_params(400, seed=31, config=3, p_neg=0.2))
+    assert len(text) > 50_000_000
+    assert paf(w, ctx, text) == orc.maf2paf(text)
+    assert stat(w, ctx, text) == orc.stat_maf(text)
+    assert vcf(w, ctx, text, inv=True) == orc.call_maf(text, inv=True)
+    assert vcf(w, ctx, text, snp=True, svlen=0, inv=True) == orc.call_maf(text, snp=True, svlen=0, inv=True)
+
+
+def test_full_size_properties(w, ctx):
+    """size-independent invariants on a 1.3 GB slab (too big to diff comfortably): one PAF row per record, NM and
+    block length consistent with the per-record counters, stat totals = column sums, one SNP row per mismatch."""
+    text = bs.gen_maf(bs.maf_params(200_000, seed=5))
+    out = paf(w, ctx, text)
+    cnt = ctx.last_record_counts().astype(np.int64)
+    rows = out.split(b"\n")[:-1]
+    assert len(rows) == len(cnt) == 200_000
+    f = np.array([[int(r.split(b"\t")[9]), int(r.split(b"\t")[10]), int(r.split(b"\t")[12][5:])] for r in rows[::97]])
+    c = cnt[::97]
+    assert (f[:, 0] == c[:, 0]).all() and (f[:, 1] == c[:, [0, 1, 3, 5, 7, 9]].sum(1)).all() and (f[:, 2] == f[:, 1] - f[:, 0]).all()
+    st = stat(w, ctx, text).decode().splitlines()[1:]
+    tot = np.array([[int(x) for i, x in enumerate(l.split("\t")) if i in (10, 11, 12, 13, 14, 15, 18, 19, 20, 21)] for l in st]).sum(0)
+    want = cnt[:, [0, 1, 2, 4, 3, 5, 6, 7, 8, 9]].sum(0)
+    assert (tot == want).all()
+    v = vcf(w, ctx, text, snp=True, svlen=10**9)
+    assert v.count(b"\n") - 8 == int(cnt[:, 1].sum())  # only SNP rows when no indel passes the cutoff

@@ -31,6 +31,7 @@ namespace wga {
         if (rc__) return rc__;   \
     } while (0)
 
+constexpr uint32_t kSeg = 16384;  // columns per work item of the column walk
 constexpr uint64_t kNoErr = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kPosMask = 0x7FFFFFFFFFFFFFFFull;  // ws entry: bit 63 = newline
 

@@ -14,7 +14,6 @@ namespace wga {
 
 constexpr int kWsTile = 32768;    // bytes per CTA in the whitespace-index kernels
 constexpr int kWsThreads = 256;
-constexpr uint32_t kSeg = 16384;  // columns per work item of the column walk
 
 // ---------------------------------------------------------------- 1. whitespace index
 // CLS 0: ASCII whitespace (MAF, split_whitespace); CLS 1: PAF delimiters '\t' and '\n' (csv reader, paf.rs:22-31)

@@ -4,7 +4,7 @@
 // cigar_cat_ext :298-308) and of src/tools/caller.rs:442-446 (classifier cigar_cat_ext_caller,
 // cigar.rs:314-328).
 //
-// Shape (v3).  Persistent warps; a warp walks one work item (<= kSeg columns of one record) at a time.
+// Shape (v4).  Persistent warps; a warp walks one work item (<= kSeg columns of one record) at a time.
 // Lane i of step k owns the 16 columns of chunk j = 32k+i: one aligned 16-byte load of the target and a
 // funnel-shifted pair of 16-byte loads of the query (the two streams are misaligned against each other by
 // an arbitrary number of bytes).  Alignments are >99 % identical columns, so the dense part of the kernel
@@ -17,44 +17,13 @@
 //   - run heads (class changes) -> (column-in-item, class) entries appended, in column order, to the
 //     item's slot region (capacity n/8+16 by default; an overflow is reported and the caller re-runs with
 //     worst-case capacity), so maf2paf / call need ONE dense pass; a sparse kernel compacts the slots.
+// Work distribution is dynamic (batches of 8 items from a global counter) and the warp requests the first vectors
+// of its next item during the last step of the current one.
 // Algorithmic traffic: 2 bytes per column (+ 48 B of item descriptor).
 #pragma once
-#include "ctx.cuh"
-#include "tokenize.cuh"
+#include "walk_types.cuh"
 
 namespace wga {
-
-enum { MODE_STAT = 0, MODE_RUNS_EXT = 1, MODE_RUNS_CALLER = 2 };
-constexpr int kWalkThreads = 256;
-constexpr int kWalkWarps = kWalkThreads / 32;
-#ifndef WGA_WALK_CTAS
-#define WGA_WALK_CTAS 3
-#endif
-constexpr int kWalkCtasPerSm = WGA_WALK_CTAS;
-constexpr int kQWords = 14;  // queue entry: t[4] q[4] prev meta item rec col_lo col_hi
-constexpr uint32_t kSlotPad = 16;
-
-struct __align__(16) ItemDesc {  // one work item: columns [seg*kSeg, seg*kSeg+n) of record rec
-    uint64_t t_off, q_off;       // byte offsets of the item's first column in target / query
-    uint32_t n, rec, seg, tail;  // tail: columns of the record after this item, clipped to 16
-    uint64_t slot_base;          // first slot of the item's run-head region (cold: read when heads are emitted)
-    uint64_t pad;
-};
-static_assert(sizeof(ItemDesc) == 48, "ItemDesc is read as three 16-byte vectors");
-
-struct WalkArgs {
-    const uint8_t *text;
-    const ItemDesc *items;
-    uint64_t n_items;
-    unsigned long long *rec_cnt;  // [n_rec][5]: X, I_events, I_cols, D_events, D_cols (zero-initialised)
-    uint32_t *item_nheads;        // [n_items] zero-initialised
-    uint32_t *slots;              // run-head slots
-    uint32_t cap_shift;           // slot capacity of an item = (n >> cap_shift) + kSlotPad
-    uint32_t *overflow;
-    unsigned int *sched;          // dynamic work counter (zero-initialised)
-};
-
-__device__ __host__ __forceinline__ uint64_t slot_cap(uint64_t n, uint32_t shift) { return (n >> shift) + kSlotPad; }
 
 // rec_slot_base: exclusive scan over records of the summed capacities of their items
 __global__ void k_rec_slot_need(uint64_t n_rec, const uint32_t *__restrict__ n_items, const uint64_t *__restrict__ ncols,
@@ -90,7 +59,7 @@ __global__ void k_fill_item_desc(uint64_t n_rec, const uint32_t *__restrict__ n_
         d.rec = (uint32_t)r;
         d.seg = s;
         d.tail = (uint32_t)(tail > 16 ? 16 : tail);
-        d.pad = 0;
+        d.pad0 = d.pad1 = 0;
         items[b + s] = d;
     }
 }
@@ -147,8 +116,7 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
             p_eq = F[k].eq; p_x = F[k].x; p_i = F[k].i; p_d = F[k].d; p_w = F[k].w;
         }
         if (COUNTS && (cX | cI | cD)) {
-            const uint32_t rec = __ldg(reinterpret_cast<const uint4 *>(A.items + item) + 1).y;
-            unsigned long long *c = A.rec_cnt + (uint64_t)rec * 5;
+            unsigned long long *c = A.rec_cnt + (uint64_t)Q[11][lane] * 5;
             if (cX) atomicAdd(c + 0, (unsigned long long)cX);
             if (eI) atomicAdd(c + 1, (unsigned long long)eI);
             if (cI) atomicAdd(c + 2, (unsigned long long)cI);
@@ -177,9 +145,9 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
         const uint32_t incl = carry + x;  // heads of this item up to and including this lane
         if (act) {
             const uint4 *dp = reinterpret_cast<const uint4 *>(A.items + item);
-            const uint4 d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
-            const uint64_t sbase = ((uint64_t)d2.y << 32) | d2.x;
-            const uint32_t cap = (uint32_t)slot_cap(d1.x, A.cap_shift);
+            const uint4 d1 = __ldg(dp + 1);
+            const uint64_t sbase = ((uint64_t)d1.y << 32) | d1.x;
+            const uint32_t cap = (uint32_t)slot_cap(d1.z, A.cap_shift);
             uint32_t o = incl - hc;
             if (incl > cap) {
                 atomicOr(A.overflow, 1u);
@@ -208,26 +176,27 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
     }
 }
 
-// geometry of one work item in the 16-byte frame of its target stream (only what the streaming loop needs; the
-// record id, the slot base and the column preceding the item are re-read from the descriptor on the cold path)
+// geometry of one work item in the 16-byte frame of its target stream
 struct Geom {
     const uint8_t *tbase, *qbase;  // 16-byte aligned; chunk j covers item columns [16j-a, 16j-a+16)
-    uint32_t a, s, n, item, ts;    // ts = tail | (seg == 0) << 8
-    __device__ __forceinline__ uint32_t nch() const { return (n + a + 15u) >> 4; }
-    __device__ __forceinline__ uint32_t q_last() const { return (s + n + a - 1u) >> 4; }  // last query vector needed
+    uint32_t a, s, n, nch, q_last, rec, seg, tail, item, first_prev;
 };
 
-__device__ __forceinline__ Geom make_geom(const WalkArgs &A, const uint4 &d0, const uint4 &d1, uint32_t item) {
+__device__ __forceinline__ Geom make_geom(const WalkArgs &A, const uint4 &d0, const uint4 &d1, const uint4 &d2, uint32_t item) {
     Geom g;
     const uint64_t t_off = ((uint64_t)d0.y << 32) | d0.x, q_off = ((uint64_t)d0.w << 32) | d0.z;
-    g.n = d1.x; g.item = item;
-    g.ts = d1.w | ((d1.z == 0 ? 1u : 0u) << 8);
+    g.n = d1.z; g.rec = d1.w; g.seg = d2.x; g.tail = d2.y; g.item = item;
     const uint8_t *tp = A.text + t_off, *qp = A.text + q_off;
     g.a = (uint32_t)(reinterpret_cast<uintptr_t>(tp) & 15u);
     g.tbase = tp - g.a;
     const uint8_t *qv = qp - g.a;  // query byte stream in the same column frame
     g.s = (uint32_t)(reinterpret_cast<uintptr_t>(qv) & 15u);
     g.qbase = qv - g.s;
+    g.nch = (g.n + g.a + 15u) >> 4;
+    g.q_last = (g.s + g.n + g.a - 1u) >> 4;  // last query vector holding a needed byte
+    // column preceding chunk 0 (only matters when a == 0; otherwise it sits inside chunk 0)
+    g.first_prev = 0;
+    if (g.a == 0 && g.seg > 0) g.first_prev = (1u << 16) | ((uint32_t)qp[-1] << 8) | (uint32_t)tp[-1];
     return g;
 }
 
@@ -235,10 +204,10 @@ struct Vec3 { uint4 t, q0, q1; };
 __device__ __forceinline__ Vec3 load_vec(const Geom &g, uint32_t j) {
     Vec3 v;
     v.t = make_uint4(0, 0, 0, 0); v.q0 = v.t; v.q1 = v.t;
-    if (j < g.nch()) {
+    if (j < g.nch) {
         v.t = ldg16(g.tbase + 16ull * j);
         v.q0 = ldg16(g.qbase + 16ull * j);
-        if (g.s != 0 && j + 1 <= g.q_last()) v.q1 = ldg16(g.qbase + 16ull * (j + 1));
+        if (g.s != 0 && j + 1 <= g.q_last) v.q1 = ldg16(g.qbase + 16ull * (j + 1));
     }
     return v;
 }
@@ -260,7 +229,7 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
                                           const Geom &g, uint32_t j0, const Vec3 &v, uint32_t &carry) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
     const uint32_t j = j0 + lane;
-    const bool act = j < g.nch();
+    const bool act = j < g.nch;
     const uint4 tv = v.t;
     uint32_t qw0, qw1, qw2, qw3;
     const uint32_t sh = (g.s & 3u) * 8u;
@@ -292,23 +261,17 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
             const uint32_t slot = qn + __popc(mask & ((1u << lane) - 1u));
             Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
             Q[4][slot] = qw0; Q[5][slot] = qw1; Q[6][slot] = qw2; Q[7][slot] = qw3;
-            const uint32_t seg0 = g.ts >> 8;
-            uint32_t prev = (1u << 16) | pb;
-            if (j == 0) {  // column preceding chunk 0 (only matters when a == 0; otherwise it sits inside chunk 0)
-                prev = 0;
-                if (g.a == 0 && !seg0)
-                    prev = (1u << 16) | ((uint32_t)g.qbase[(int)g.s - 1] << 8) | (uint32_t)g.tbase[-1];
-            }
-            Q[8][slot] = prev;
+            Q[8][slot] = j == 0 ? g.first_prev : ((1u << 16) | pb);
             uint32_t f0 = 0, t0 = 16, t1 = 16;
             if (edge) {
                 const int64_t lo = (int64_t)g.a - 16ll * j, hi = (int64_t)g.n + (int64_t)g.a - 16ll * j;
                 f0 = clamp16(lo);
                 t0 = clamp16(hi);
-                t1 = clamp16(hi + (int64_t)(g.ts & 0xFFu));  // columns of the next item are context only
+                t1 = clamp16(hi + (int64_t)g.tail);  // columns of the next item are context only
             }
-            Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | (seg0 << 15) | ((16u * j + 16u - g.a) << 16);
+            Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | ((g.seg == 0 ? 1u : 0u) << 15) | ((16u * j + 16u - g.a) << 16);
             Q[10][slot] = g.item;
+            Q[11][slot] = g.rec;
         }
         qn += __popc(mask);
         __syncwarp();
@@ -316,15 +279,15 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
             walk_batch<MODE>(A, Q, 32, lane, E);
             __syncwarp();
             qn -= 32;
-            uint32_t mv[11];
+            uint32_t mv[12];
             if (lane < qn) {
 #pragma unroll
-                for (int f = 0; f < 11; ++f) mv[f] = Q[f][lane + 32];
+                for (int f = 0; f < 12; ++f) mv[f] = Q[f][lane + 32];
             }
             __syncwarp();
             if (lane < qn) {
 #pragma unroll
-                for (int f = 0; f < 11; ++f) Q[f][lane] = mv[f];
+                for (int f = 0; f < 12; ++f) Q[f][lane] = mv[f];
             }
             __syncwarp();
         }
@@ -334,7 +297,7 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
 template <int MODE>
 __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs A) {
     constexpr bool RUNS = MODE != MODE_STAT;
-    __shared__ uint32_t s_queue[kWalkWarps][11][64];  // per warp, SoA, 64 slots
+    __shared__ uint32_t s_queue[kWalkWarps][12][64];  // per warp, SoA, 64 slots
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t (*Q)[64] = s_queue[wid];
     uint32_t qn = 0;
@@ -368,29 +331,28 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs 
     if (s_it < n_items) {
         const uint32_t item = s_it;
         const uint4 *dp = reinterpret_cast<const uint4 *>(A.items + item);
-        Geom cur = make_geom(A, __ldg(dp), __ldg(dp + 1), item);
+        Geom cur = make_geom(A, __ldg(dp), __ldg(dp + 1), __ldg(dp + 2), item);
         bool has2 = advance();
         uint32_t item2 = s_it;
-        uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
+        uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0, e2 = e0;
         if (has2) {
             const uint4 *ep = reinterpret_cast<const uint4 *>(A.items + item2);
-            e0 = __ldg(ep); e1 = __ldg(ep + 1);
+            e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2);
         }
         Vec3 v = load_vec(cur, lane);
         for (;;) {
             Geom nxt = cur;
-            if (has2) nxt = make_geom(A, e0, e1, item2);
+            if (has2) nxt = make_geom(A, e0, e1, e2, item2);
             const bool has3 = has2 && advance();
             const uint32_t item3 = s_it;
             if (has3) {
                 const uint4 *ep = reinterpret_cast<const uint4 *>(A.items + item3);
-                e0 = __ldg(ep); e1 = __ldg(ep + 1);
+                e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2);
             }
             uint32_t carry = 0;  // (t,q) bytes of the column before this step's first chunk: t | q<<8
-            const uint32_t cur_nch = cur.nch();
-            for (uint32_t j0 = 0; j0 < cur_nch; j0 += 32) {
+            for (uint32_t j0 = 0; j0 < cur.nch; j0 += 32) {
                 Vec3 nv;
-                if (j0 + 32 < cur_nch) nv = load_vec(cur, j0 + 32 + lane);
+                if (j0 + 32 < cur.nch) nv = load_vec(cur, j0 + 32 + lane);
                 else if (has2) nv = load_vec(nxt, lane);
                 else { nv.t = make_uint4(0, 0, 0, 0); nv.q0 = nv.t; nv.q1 = nv.t; }
                 walk_step<MODE>(A, Q, qn, E, lane, cur, j0, v, carry);

@@ -7,11 +7,7 @@
 #include "stat.cuh"
 #include "stat_acc.hpp"
 #include "tokenize.cuh"
-#ifdef WGA_WALK_V6
-#include "walk_v6.cuh"
-#else
-#include "walk.cuh"
-#endif
+#include "walk_types.cuh"
 #ifdef WGA_WITH_CALL
 #include "call.cuh"
 #endif
@@ -348,23 +344,25 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
             uint64_t *need = ctx->buf<uint64_t>(B_GEN_H, n_rec + 1);
             slot_base = ctx->buf<uint64_t>(B_RUN_BASE, n_rec + 1);
             if (!need || !slot_base) return ctx->err_code;
-            LAUNCH(ctx, k_rec_slot_need, grid_for(n_rec + 1, 256), 256, n_rec, P.rc.n_items, P.rc.ncols, shift, need);
+            launch_rec_slot_need(grid_for(n_rec + 1, 256), 256, ctx->stream, n_rec, P.rc.n_items, P.rc.ncols, shift, need);
+            ctx->n_own++;
             WGA_TRY(exclusive_sum(ctx, need, slot_base, n_rec + 1));
             uint64_t total;
             WGA_TRY(read_scalars(ctx, {slot_base + n_rec}, &total));
             slots = ctx->buf<uint32_t>(B_PAF_B, total + 1);
             if (!slots) return ctx->err_code;
         }
-        LAUNCH(ctx, k_fill_item_desc, grid_for(n_rec, 256), 256, n_rec, P.rc.n_items, P.item_base, P.rc.t_off, P.rc.q_off,
-               P.rc.ncols, (const uint64_t *)slot_base, shift, P.items);
+        launch_fill_item_desc(grid_for(n_rec, 256), 256, ctx->stream, n_rec, P.rc.n_items, P.item_base, P.rc.t_off, P.rc.q_off,
+                              P.rc.ncols, (const uint64_t *)slot_base, shift, P.items);
+        ctx->n_own++;
         WGA_CK(cudaMemsetAsync(nheads, 0, (n_items + 1) * 4, ctx->stream));
         WGA_CK(cudaMemsetAsync(ovf, 0, 8, ctx->stream));
         WalkArgs A;
         A.text = ctx->d_text; A.items = P.items; A.n_items = n_items; A.rec_cnt = rec_cnt;
         A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf; A.sched = ovf + 1;
-        auto kern = k_walk<MODE>;
         WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        LAUNCH(ctx, kern, walk_grid(ctx, n_items), kWalkThreads, A);
+        launch_walk(MODE, walk_grid(ctx, n_items), ctx->stream, A);
+        ctx->n_own++;
         WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
         ctx->walk_launches++;
         ctx->walk_bytes += 2 * P.total_cols + 48 * n_items;
@@ -388,8 +386,9 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
         R->run_rec = ctx->buf<uint32_t>(B_RUN_REC, n_runs + 1);
         R->run_cls = ctx->buf<uint8_t>(B_RUN_CLS, n_runs + 1);
         if (!R->run_pos || !R->run_rec || !R->run_cls) return ctx->err_code;
-        LAUNCH(ctx, k_runs_compact, grid_for(n_items * 32, 256), 256, n_items, P.items, nheads, R->run_base, slots, R->run_pos,
-               R->run_rec, R->run_cls);
+        launch_runs_compact(grid_for(n_items * 32, 256), 256, ctx->stream, n_items, P.items, nheads, R->run_base, slots, R->run_pos,
+                            R->run_rec, R->run_cls);
+        ctx->n_own++;
         return WGA_OK;
     }
 }
