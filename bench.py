@@ -51,6 +51,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def walk_traffic(blocks):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_walk launch from the committed ncu --set full capture of this
+    workload (profiles/walk_traffic.json); null when the capture was taken on another workload size"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json")))
+        return t["dram_bytes_per_launch"] if int(t["workload_blocks"]) == int(blocks) else None
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -291,7 +301,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_walk (dense column walk, all launches of the timed steps)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": walk_traffic(args.blocks),
                          "launches": walk["launches"], "avg_launch_ms": walk["ms"] / max(walk["launches"], 1),
                          "alg_bytes_per_launch": walk["bytes"] / max(walk["launches"], 1)},
             "input_bytes_per_gpu": nbytes, "columns_per_gpu": ncols, "gen_seconds": t_gen}

@@ -130,6 +130,20 @@ int wga_vcf_header(wga_ctx *ctx, const char *sample, wga_span *out);
 int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags,
                  const wga_call_opts *opts, wga_span *out);
 
+/* ---- paf2maf: src/converter.rs:176-265 (second wave, config 5) ------------------------------------- */
+/* A FASTA resident in HBM (rust-htslib faidx::Reader stand-in): `fa` = file bytes, `fai` = its samtools .fai text
+ * (the reference refuses to run without the .fai, utils.rs:480-492).  Host buffers.  Well-formed FASTA assumed
+ * (uniform line width per record, which is what a .fai describes). */
+typedef struct wga_fasta wga_fasta;
+int wga_fasta_load(wga_ctx *ctx, const void *fa, uint64_t fa_len, const void *fai, uint64_t fai_len, wga_fasta **out);
+void wga_fasta_free(wga_fasta *fa);
+/* "#maf version=1.6 convert_from=paf t_seq_path=.. q_seq_path=..\n" (converter.rs:190-195) */
+int wga_paf2maf_header(wga_ctx *ctx, const char *t_fa_path, const char *q_fa_path, wga_span *out);
+/* MAF blocks of one slab of PAF lines, file order: fetch [t_start,t_end-1] / [q_start,q_end-1], reverse-complement
+ * '-' queries (utils.rs:83-101), expand the CIGAR into gapped rows (cigar.rs:492-551), maf.rs:566-581 text. */
+int wga_paf2maf(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *target,
+                const wga_fasta *query, wga_span *out);
+
 /* ---- AlignRecord-level batch access (common.rs:142-176 get_stat / get_cigar_string) --------- */
 /* per-record counters of the last wga_maf2paf / wga_maf_stat / wga_paf_stat call, struct Cigar order
  * (cigar.rs:16-29): match, mismatch, ins_event, ins, del_event, del, inv_ins_event, inv_ins,

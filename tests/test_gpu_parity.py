@@ -473,3 +473,112 @@ def test_full_size_properties(w, ctx):
     assert (tot == want).all()
     v = vcf(w, ctx, text, snp=True, svlen=10**9)
     assert v.count(b"\n") - 8 == int(cnt[:, 1].sum())  # only SNP rows when no indel passes the cutoff
+
+
+# ----------------------------------------------------------------------------------------- paf2maf
+def _revcomp(s):
+    return s.translate(bytes.maketrans(b"ACGTacgtNn", b"TGCAtgcaNn"))[::-1]
+
+
+def _wrap(name, seq, width):
+    return b">" + name + b" some description\n" + b"\n".join(seq[i:i + width] for i in range(0, len(seq), width)) + b"\n"
+
+
+def make_paf2maf_case(rng, n_rec=40, n_tchr=3, n_qchr=4, width_t=60, width_q=70, soft=True):
+    """target genome + query genome assembled from mutated (and for '-' records reverse-complemented) target segments,
+    with a PAF whose cg:Z: strings are consistent with both FASTAs"""
+    alpha = b"ACGT"
+    tch = [bytes(rng.choice(alpha) for _ in range(rng.randrange(3000, 9000))) for _ in range(n_tchr)]
+    if soft:
+        tch = [c[:500] + c[500:900].lower() + c[900:] for c in tch]
+    qparts = [[] for _ in range(n_qchr)]
+    recs = []
+    for r in range(n_rec):
+        ti = rng.randrange(n_tchr)
+        L = rng.randrange(1, 1500)
+        ts = rng.randrange(0, len(tch[ti]) - L)
+        tseg = tch[ti][ts:ts + L]
+        q = bytearray()
+        ops = []
+        i = 0
+        while i < L:
+            u = rng.random()
+            n = min(L - i, rng.randrange(1, 60))
+            if u < 0.6:
+                ops.append((b"=", n)); q += tseg[i:i + n]; i += n
+            elif u < 0.75:
+                n = min(n, 3)
+                for k in range(n):
+                    c = tseg[i + k:i + k + 1].upper()
+                    q += bytes([rng.choice([x for x in alpha if bytes([x]) != c])])
+                ops.append((b"X", n)); i += n
+            elif u < 0.88:
+                ops.append((b"D", n)); i += n
+            else:
+                ops.append((b"I", n)); q += bytes(rng.choice(alpha) for _ in range(n))
+        if rng.random() < 0.3:
+            ops = [(b"M" if o in b"=X" else o, n) for o, n in ops]  # M-only spelling
+        merged = []
+        for o, n in ops:
+            if merged and merged[-1][0] == o:
+                merged[-1][1] += n
+            else:
+                merged.append([o, n])
+        neg = rng.random() < 0.4
+        qi = rng.randrange(n_qchr)
+        spacer = bytes(rng.choice(alpha) for _ in range(rng.randrange(0, 50)))
+        qparts[qi].append(spacer)
+        qs = sum(len(p) for p in qparts[qi])
+        qparts[qi].append(_revcomp(bytes(q)) if neg else bytes(q))
+        recs.append((qi, qs, qs + len(q), neg, ti, ts, ts + L, b"".join(b"%d%s" % (n, o) for o, n in merged)))
+    qch = [b"".join(p) + b"ACGT" for p in qparts]
+    t_fa = b"".join(_wrap(b"tgt.chr%d" % i, c, width_t) for i, c in enumerate(tch))
+    q_fa = b"".join(_wrap(b"qry#%d" % i, c, width_q) for i, c in enumerate(qch))
+    paf = b"".join(b"qry#%d\t%d\t%d\t%d\t%s\ttgt.chr%d\t%d\t%d\t%d\t%d\t%d\t%d\ttp:A:P\tcg:Z:%s\n" %
+                   (qi, len(qch[qi]), qs, qe, b"-" if neg else b"+", ti, len(tch[ti]), ts, te, 1, 2, rng.randrange(0, 61), cg)
+                   for (qi, qs, qe, neg, ti, ts, te, cg) in recs)
+    return paf, t_fa, orc.make_fai(t_fa), q_fa, orc.make_fai(q_fa)
+
+
+def p2m(w, ctx, paf, t_fa, t_fai, q_fa, q_fai):
+    out = io.BytesIO()
+    w.paf2maf(w.PAFReader(paf), out, "t.fa", "q.fa", ctx=ctx, target=w.Fasta(ctx, t_fa, t_fai), query=w.Fasta(ctx, q_fa, q_fai))
+    return out.getvalue()
+
+
+def test_paf2maf_parity(w, ctx):
+    rng = random.Random(2026)
+    for it in range(6):
+        case = make_paf2maf_case(rng, n_rec=60, width_t=rng.choice([50, 60, 80]), width_q=rng.choice([60, 61, 100]), soft=it % 2 == 0)
+        want = orc.paf2maf(*case)
+        got = p2m(w, ctx, *case)
+        assert got == want
+        # the result is a MAF whose maf2paf round-trips the alignment counters of the PAF CIGARs
+        back = orc.maf2paf(got)
+        assert back.count(b"\n") == case[0].count(b"\n")
+
+
+def test_paf2maf_edges_and_errors(w, ctx):
+    t_fa = b">chrT desc\nACGTACGTAC\nGGGGCCCCAA\nTTTT\n>other\nAAAA\n"
+    q_fa = b">chrQ\nACGTACGTACGGCCCCAATT\nTTAA\n>bad\nACGTRYAC\n"
+    ti, qi = orc.make_fai(t_fa), orc.make_fai(q_fa)
+    def line(cg, strand=b"+", q=b"chrQ", t=b"chrT", qs=1, qe=13, ts=2, te=14, tag=True):
+        return b"\t".join([q, b"24", b"%d" % qs, b"%d" % qe, strand, t, b"24", b"%d" % ts, b"%d" % te, b"9", b"14", b"60"] +
+                          ([b"cg:Z:" + cg] if tag else [])) + b"\n"
+    ok = [line(b"4=1X2I3=2D2="), line(b"4=1X2I3=2D2=", b"-"), line(b"5M"),           # CIGAR shorter than the spans
+          line(b"3M2I20M"), line(b"12M3D"), line(b"2I12M", ts=20, te=30),            # spans clipped at the sequence end
+          b"#c\n" + line(b"12=") + b"\n" + line(b"6=6X", b"-"), line(b"1=", qs=0, qe=1, ts=0, te=1)]
+    for paf in ok:
+        assert p2m(w, ctx, paf, t_fa, ti, q_fa, qi) == orc.paf2maf(paf, t_fa, ti, q_fa, qi), paf
+    bad = [(line(b"10S2M"), 5), (line(b"10MM"), 5), (line(b"M"), 1), (line(b""), 8), (line(b"5=", tag=False), 6),
+           (line(b"5=", t=b"nope"), 11), (line(b"5=", q=b"nope"), 11), (line(b"8=", b"-", q=b"bad", qs=0, qe=8), 10),
+           (line(b"20M2I"), 8), (line(b"3=20D1="), 8), (b"a\tb\n", 9),
+           (line(b"12=") + line(b"3=2Q") + line(b"M"), 5)]
+    for paf, code in bad:
+        with pytest.raises(orc.OracleError) as eo:
+            orc.paf2maf(paf, t_fa, ti, q_fa, qi)
+        with pytest.raises(w.WGAError) as eg:
+            p2m(w, ctx, paf, t_fa, ti, q_fa, qi)
+        assert eo.value.code == code == eg.value.code, (paf, eo.value.code, eg.value.code, eo.value.msg)
+        if code in (1, 5, 6, 10):
+            assert str(eg.value) == eo.value.msg, paf

@@ -48,6 +48,12 @@ ABI = {
     "wga_vcf_header": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _P(Span)]),
     "wga_maf_call": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
                                    _P(CallOpts), _P(Span)]),
+    "wga_fasta_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                                     _P(ctypes.c_void_p)]),
+    "wga_fasta_free": (None, [ctypes.c_void_p]),
+    "wga_paf2maf_header": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, _P(Span)]),
+    "wga_paf2maf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
+                                  ctypes.c_void_p, ctypes.c_void_p, _P(Span)]),
     "wga_last_record_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, _P(ctypes.c_uint64)]),
 }
 

@@ -99,6 +99,33 @@ class Context:
         return out
 
 
+class Fasta:
+    """FASTA resident in HBM (stands in for rust_htslib::faidx::Reader, src/converter.rs:183-184)"""
+
+    def __init__(self, ctx, fa: bytes, fai: bytes):
+        self.ctx = ctx
+        h = ctypes.c_void_p()
+        ctx._check(ctx.L.wga_fasta_load(ctx.h, fa, len(fa), fai, len(fai), ctypes.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_path(cls, ctx, path):
+        # utils.rs:470-492: both the FASTA and its .fai must exist
+        for p in (path, path + ".fai"):
+            if not os.path.exists(p):
+                raise WGAError(-1, f"File path `{p}` not exist")
+        with open(path, "rb") as f, open(path + ".fai", "rb") as g:
+            return cls(ctx, f.read(), g.read())
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.ctx.L.wga_fasta_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class StatAcc:
     def __init__(self, each=False):
         self.L = _lib.load()
@@ -249,6 +276,21 @@ def call_var_maf(mafreader: MAFReader, mafindex, writer, if_snp=False, if_inv=Fa
         ptr, ln = ctx.maf_call_raw(ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags, opts)
         if ln:
             writer.write(ctypes.string_at(ptr, ln))
+
+
+def paf2maf(pafreader: PAFReader, writer, t_fa_path, q_fa_path, ctx=None, target=None, query=None):
+    """src/converter.rs:176-265.  target/query: preloaded Fasta objects (else loaded from the two paths)."""
+    ctx = ctx or default_context()
+    target = target or Fasta.from_path(ctx, t_fa_path)
+    query = query or Fasta.from_path(ctx, q_fa_path)
+    sp = Span()
+    ctx._check(ctx.L.wga_paf2maf_header(ctx.h, _opt(t_fa_path), _opt(q_fa_path), ctypes.byref(sp)))
+    writer.write(ctypes.string_at(sp.data, sp.len))
+    keep, base = _host_ptr(pafreader.data)
+    ctx._check(ctx.L.wga_paf2maf(ctx.h, ctypes.c_void_p(base), len(pafreader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, target.h,
+                                 query.h, ctypes.byref(sp)))
+    if sp.len:
+        writer.write(ctypes.string_at(sp.data, sp.len))
 
 
 def run_bytes(fn, *args, **kw) -> bytes:

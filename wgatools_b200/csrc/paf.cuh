@@ -111,7 +111,7 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
     R.t_size[r] = v[6]; R.t_start[r] = v[7];
     R.neg[r] = neg;
     if (!have_cg) {  // cs:Z: conversion (paf.rs:159-218) is not accelerated; no tag at all is the reference's error
-        paf_report(err_key, r, 1, have_cs ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
+        paf_report(err_key, r, 0x800000, have_cs ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
         cg_len = 0;
         cg_off = 0;
         R.neg[r] = 2;  // marks "no cigar"
@@ -132,7 +132,7 @@ __global__ void k_paf_cigar_counts(uint64_t n_rec, const uint8_t *__restrict__ t
     const uint8_t *p = text + R.cig_off[r];
     if (negf == 2) { for (int i = 0; i < 11; ++i) o[i] = 0; return; }
     if (len == 0) {  // fold_many1 on "" -> nom error -> e.input[..10] panics (errors.rs:88-97)
-        paf_report(err_key, r, 2, WGA_E_REF_PANIC);
+        paf_report(err_key, r, 0x800001, WGA_E_REF_PANIC);
         for (int i = 0; i < 11; ++i) o[i] = 0;
         return;
     }
@@ -186,7 +186,7 @@ __global__ void k_paf_cigar_counts(uint64_t n_rec, const uint8_t *__restrict__ t
         }
     }
     if (!code) close_token(len);  // last token (digits with no op char -> op_run == 0 -> CigarOpInvalid(""))
-    if (code) paf_report(err_key, r, 3 + epos, code);
+    if (code) paf_report(err_key, r, 0x800002 + (epos > 0x7FFFF0ull ? 0x7FFFF0ull : epos), code);
     const bool neg = negf == 1;
     o[0] = c_m; o[1] = c_x;
     o[2] = neg ? 0 : c_ie; o[3] = neg ? 0 : c_i; o[4] = neg ? 0 : c_de; o[5] = neg ? 0 : c_d;

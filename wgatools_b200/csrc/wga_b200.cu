@@ -13,6 +13,7 @@
 #endif
 #ifdef WGA_WITH_PAF
 #include "paf.cuh"
+#include "paf2maf.cuh"
 #endif
 
 using namespace wga;
@@ -980,11 +981,240 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
 }
 #endif
 
+#ifdef WGA_WITH_PAF
+// ---------------------------------------------------------------- paf2maf
+int wga_fasta_load(wga_ctx *ctx, const void *fa, uint64_t fa_len, const void *fai, uint64_t fai_len, wga_fasta **out) {
+    if (!ctx || !out || !fa || !fai) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    // .fai: name \t length \t offset \t linebases \t linewidth
+    struct Ent { std::string name; uint64_t len, off, lb, lw, hash; };
+    std::vector<Ent> ents;
+    const char *p = (const char *)fai, *end = p + fai_len;
+    while (p < end) {
+        const char *nl = (const char *)memchr(p, '\n', end - p);
+        const char *le = nl ? nl : end;
+        std::vector<std::string> f;
+        const char *b = p;
+        for (const char *c = p; c <= le; ++c)
+            if (c == le || *c == '\t') { f.emplace_back(b, c - b); b = c + 1; }
+        if (f.size() >= 5) {
+            Ent e;
+            e.name = f[0];
+            bool ok = parse_u64_bytes((const unsigned char *)f[1].data(), f[1].size(), &e.len) &&
+                      parse_u64_bytes((const unsigned char *)f[2].data(), f[2].size(), &e.off) &&
+                      parse_u64_bytes((const unsigned char *)f[3].data(), f[3].size(), &e.lb) &&
+                      parse_u64_bytes((const unsigned char *)f[4].data(), f[4].size(), &e.lw);
+            if (!ok) { ctx->set_error(WGA_E_INVALID_ARG, ents.size(), "malformed .fai line"); return WGA_E_INVALID_ARG; }
+            uint64_t h = 0xCBF29CE484222325ull;
+            for (unsigned char ch : e.name) h = (h ^ ch) * 0x100000001B3ull;
+            e.hash = h;
+            ents.push_back(std::move(e));
+        }
+        p = le + 1;
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.hash < b.hash; });
+    const uint64_t n = ents.size();
+    std::vector<uint64_t> meta(n * kFaMeta + 1), unwrap(n * 5 + 1);
+    std::string names;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        meta[i * kFaMeta] = ents[i].hash; meta[i * kFaMeta + 1] = names.size(); meta[i * kFaMeta + 2] = ents[i].name.size();
+        meta[i * kFaMeta + 3] = total; meta[i * kFaMeta + 4] = ents[i].len;
+        unwrap[i * 5] = ents[i].off; unwrap[i * 5 + 1] = ents[i].lb; unwrap[i * 5 + 2] = ents[i].lw; unwrap[i * 5 + 3] = total;
+        unwrap[i * 5 + 4] = ents[i].len;
+        names += ents[i].name;
+        total += ents[i].len;
+    }
+    wga_fasta *F = new wga_fasta();
+    F->device = ctx->device; F->n_seq = n; F->total = total;
+    uint8_t *d_fa = nullptr;
+    uint64_t *d_unwrap = nullptr;
+    auto fail = [&](const char *msg) {
+        if (d_fa) cudaFree(d_fa);
+        if (d_unwrap) cudaFree(d_unwrap);
+        wga_fasta_free(F);
+        ctx->set_error(WGA_E_NOMEM, 0, msg);
+        return WGA_E_NOMEM;
+    };
+    if (cudaMalloc(&F->d_seq, total + 64) != cudaSuccess || cudaMalloc(&F->d_names, names.size() + 16) != cudaSuccess ||
+        cudaMalloc(&F->d_meta, (n * kFaMeta + 1) * 8) != cudaSuccess || cudaMalloc(&d_fa, fa_len + 64) != cudaSuccess ||
+        cudaMalloc(&d_unwrap, (n * 5 + 1) * 8) != cudaSuccess)
+        return fail("cudaMalloc failed while loading a FASTA");
+    WGA_CK(cudaMemcpyAsync(d_fa, fa, fa_len, cudaMemcpyHostToDevice, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(F->d_names, names.data(), names.size(), cudaMemcpyHostToDevice, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(F->d_meta, meta.data(), n * kFaMeta * 8, cudaMemcpyHostToDevice, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(d_unwrap, unwrap.data(), n * 5 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t s0 = 0; s0 < n; s0 += 32768) {
+        const uint64_t cnt = std::min<uint64_t>(32768, n - s0);
+        dim3 grid(64, (unsigned)cnt);
+        k_fasta_unwrap<<<grid, 256, 0, ctx->stream>>>(cnt, d_fa, fa_len, d_unwrap + s0 * 5, F->d_seq);
+        ctx->n_own++;
+    }
+    int rc = sync_check(ctx);
+    cudaFree(d_fa);
+    cudaFree(d_unwrap);
+    if (rc) { wga_fasta_free(F); return rc; }
+    *out = F;
+    return WGA_OK;
+}
+
+void wga_fasta_free(wga_fasta *F) {
+    if (!F) return;
+    cudaSetDevice(F->device);
+    if (F->d_seq) cudaFree(F->d_seq);
+    if (F->d_names) cudaFree(F->d_names);
+    if (F->d_meta) cudaFree(F->d_meta);
+    delete F;
+}
+
+int wga_paf2maf_header(wga_ctx *ctx, const char *t_fa_path, const char *q_fa_path, wga_span *out) {
+    if (!ctx || !out || !t_fa_path || !q_fa_path) return WGA_E_INVALID_ARG;
+    static thread_local std::string hdr;
+    hdr = std::string("#maf version=1.6 convert_from=paf t_seq_path=") + t_fa_path + " q_seq_path=" + q_fa_path + "\n";
+    out->data = hdr.data();
+    out->len = hdr.size();
+    return WGA_OK;
+}
+
+int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
+                wga_span *out) {
+    (void)flags;
+    if (!ctx || !out || !TF || !QF || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    ctx->n_rec = 0;
+    if (len == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    unsigned long long *err_key = ctx->buf<unsigned long long>(B_ERR, 1);
+    if (!err_key) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, err_key, 1, kNoErr);
+    uint64_t n_ws = 0, n_nl = 0;
+    uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
+    WGA_TRY((build_delim_index<1, kTokCapPaf>(ctx, d_text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
+    const uint8_t last_byte = *(uint8_t *)(ctx->h_scal + 8);
+    const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
+    LineView lv;
+    lv.text = d_text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
+    lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = 0;
+    uint8_t *lflags = ctx->buf<uint8_t>(B_LINE_FLAGS, n_lines + 1);
+    uint32_t *isrec = ctx->buf<uint32_t>(B_LINE_HEAD, n_lines + 1), *rscan = ctx->buf<uint32_t>(B_LINE_REC, n_lines + 1);
+    if (!lflags || !isrec || !rscan) return ctx->err_code;
+    LAUNCH(ctx, k_paf_line_flags, grid_for(n_lines + 1, 256), 256, lv, lflags, isrec);
+    WGA_TRY(exclusive_sum(ctx, isrec, rscan, n_lines + 1));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal, rscan + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    const uint64_t n_rec = *(uint32_t *)ctx->h_scal;
+    ctx->n_rec = n_rec;
+    if (n_rec == 0) return WGA_OK;
+    PafRecs R;
+    R.q_name_off = ctx->buf<uint64_t>(B_PAF_B, n_rec); R.t_name_off = ctx->buf<uint64_t>(B_PAF_C, n_rec);
+    R.cig_off = ctx->buf<uint64_t>(B_PAF_D, n_rec); R.cig_len = ctx->buf<uint64_t>(B_PAF_E, n_rec);
+    R.q_name_len = ctx->buf<uint32_t>(B_PAF_F, n_rec); R.t_name_len = ctx->buf<uint32_t>(B_PAF_G, n_rec);
+    uint64_t *m4 = ctx->buf<uint64_t>(B_PAF_H, 4 * n_rec);
+    R.neg = ctx->buf<uint8_t>(B_PAF_I, n_rec);
+    uint64_t *x7 = ctx->buf<uint64_t>(B_PAF_J, 7 * n_rec);
+    uint64_t *n_ops = ctx->buf<uint64_t>(B_GEN_A, n_rec + 1), *op_base = ctx->buf<uint64_t>(B_GEN_B, n_rec + 1);
+    if (!R.q_name_off || !R.t_name_off || !R.cig_off || !R.cig_len || !R.q_name_len || !R.t_name_len || !m4 || !R.neg || !x7 ||
+        !n_ops || !op_base)
+        return ctx->err_code;
+    R.q_size = m4; R.t_size = m4 + n_rec; R.q_start = m4 + 2 * n_rec; R.t_start = m4 + 3 * n_rec;
+    P2mRecs X;
+    X.q_end = x7; X.t_end = x7 + n_rec; X.mapq = x7 + 2 * n_rec; X.t_src = x7 + 3 * n_rec; X.q_src = x7 + 4 * n_rec;
+    X.LT = x7 + 5 * n_rec; X.LQ = x7 + 6 * n_rec; X.n_ops = n_ops;
+    FaView T{TF->d_seq, TF->d_names, TF->d_meta, TF->n_seq}, Q{QF->d_seq, QF->d_names, QF->d_meta, QF->n_seq};
+    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key);
+    LAUNCH(ctx, k_p2m_spans, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, X, T, Q, err_key);
+    LAUNCH(ctx, k_p2m_revcomp_check, (unsigned)n_rec, 128, n_rec, R, X, QF->d_seq, err_key);
+    LAUNCH(ctx, k_p2m_ops<0>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+           (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key);
+    WGA_TRY(exclusive_sum(ctx, n_ops, op_base, n_rec + 1));
+    uint64_t sc[2];
+    WGA_TRY(read_scalars(ctx, {op_base + n_rec, err_key}, sc));
+    const uint64_t n_opsT = sc[0];
+    uint64_t key = sc[1];
+    uint64_t *op_len = ctx->buf<uint64_t>(B_RUN_POS, n_opsT + 1), *c_all = ctx->buf<uint64_t>(B_GEN_C, n_opsT + 1);
+    uint64_t *c_i = ctx->buf<uint64_t>(B_GEN_D, n_opsT + 1), *c_d = ctx->buf<uint64_t>(B_GEN_E, n_opsT + 1);
+    uint64_t *S_all = ctx->buf<uint64_t>(B_GEN_F, n_opsT + 1), *S_i = ctx->buf<uint64_t>(B_GEN_G, n_opsT + 1);
+    uint64_t *S_d = ctx->buf<uint64_t>(B_GEN_H, n_opsT + 1);
+    uint8_t *op_type = ctx->buf<uint8_t>(B_RUN_CLS, n_opsT + 1);
+    uint32_t *op_rec = ctx->buf<uint32_t>(B_RUN_REC, n_opsT + 1), *op_pos = ctx->buf<uint32_t>(B_RUN_DL, n_opsT + 1);
+    uint64_t *blk_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *blk_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
+    uint32_t *fix_t = ctx->buf<uint32_t>(B_ROW_FIXED, n_rec + 1), *fix_q = ctx->buf<uint32_t>(B_NAME_LEN, n_rec + 1);
+    if (!op_len || !c_all || !c_i || !c_d || !S_all || !S_i || !S_d || !op_type || !op_rec || !op_pos || !blk_len || !blk_off ||
+        !fix_t || !fix_q)
+        return ctx->err_code;
+    P2mView V;
+    V.n_rec = n_rec; V.n_ops = n_opsT; V.text = d_text; V.R = R; V.X = X; V.op_base = op_base; V.op_len = op_len; V.op_type = op_type;
+    V.op_rec = op_rec; V.op_pos = op_pos; V.S_all = S_all; V.S_i = S_i; V.S_d = S_d; V.tseq = TF->d_seq; V.qseq = QF->d_seq;
+    V.blk_len = blk_len; V.blk_off = blk_off; V.fix_t = fix_t; V.fix_q = fix_q; V.out = nullptr;
+    if (key == kNoErr) {
+        LAUNCH(ctx, k_p2m_ops<1>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)op_base, op_len, op_type,
+               op_rec, op_pos, err_key);
+        LAUNCH(ctx, k_p2m_contrib, grid_for(n_opsT + 1, 256), 256, n_opsT, op_len, op_type, c_all, c_i, c_d);
+        WGA_TRY(exclusive_sum(ctx, c_all, S_all, n_opsT + 1));
+        WGA_TRY(exclusive_sum(ctx, c_i, S_i, n_opsT + 1));
+        WGA_TRY(exclusive_sum(ctx, c_d, S_d, n_opsT + 1));
+        if (n_opsT) LAUNCH(ctx, k_p2m_check, grid_for(n_opsT, 256), 256, V, err_key);
+        LAUNCH(ctx, k_p2m_blocks<0>, grid_for(n_rec + 1, 256), 256, V);
+        WGA_TRY(exclusive_sum(ctx, blk_len, blk_off, n_rec + 1));
+        WGA_TRY(read_scalars(ctx, {blk_off + n_rec, err_key}, sc));
+        key = sc[1];
+    }
+    if (key != kNoErr) {
+        const int code = (int)(key & 0xFF);
+        const uint64_t rec = key >> 32, pos = (key >> 8) & 0xFFFFFF;
+        std::string msg;
+        if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+        else if (code == WGA_E_NOM) msg = "HTS library error by sequence of record " + std::to_string(rec) + " not found in the FASTA index";
+        else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR, or an insert past the end of the fetched sequence)";
+        else if (code == WGA_E_VCF_BASE) {
+            uint64_t ql[2];
+            WGA_TRY(read_scalars(ctx, {X.q_src + rec, X.LQ + rec}, ql));
+            char c = '?';
+            if (pos >= 2 && ql[1] > pos - 2) WGA_CK(cudaMemcpy(&c, QF->d_seq + ql[0] + ql[1] - 1 - (pos - 2), 1, cudaMemcpyDeviceToHost));
+            msg = std::string("Invalid Base: `") + c + "`";
+        } else {
+            uint64_t oc[2];
+            WGA_TRY(read_scalars(ctx, {R.cig_off + rec, R.cig_len + rec}, oc));
+            std::string cg((size_t)std::min<uint64_t>(oc[1], 1u << 20), '\0');
+            if (!cg.empty()) WGA_CK(cudaMemcpy(&cg[0], d_text + oc[0], cg.size(), cudaMemcpyDeviceToHost));
+            msg = paf_cigar_error_text(cg, code);
+        }
+        ctx->set_error(code, rec, msg);
+        return code;
+    }
+    const uint64_t total = sc[0];
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    V.out = d_out;
+    LAUNCH(ctx, k_p2m_blocks<1>, grid_for(n_rec + 1, 256), 256, V);
+    WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    LAUNCH(ctx, k_p2m_rows, grid_for((n_opsT + n_rec) * 32, 256), 256, V);
+    WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    int rc = finish_output(ctx, d_out, total, mem, out);
+    if (rc) return rc;
+    float ms = 0.f;
+    WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->walk_ms = ms; ctx->walk_launches = 1; ctx->walk_bytes = total;  // expansion kernel: output-bound
+    return WGA_OK;
+}
+#endif
+
 #ifndef WGA_WITH_PAF
 int wga_paf_stat(wga_ctx *ctx, const void *, uint64_t, int, uint32_t, wga_stat_acc *) {
     if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "paf stat not built");
     return WGA_E_UNSUPPORTED;
 }
+int wga_fasta_load(wga_ctx *, const void *, uint64_t, const void *, uint64_t, wga_fasta **) { return WGA_E_UNSUPPORTED; }
+void wga_fasta_free(wga_fasta *) {}
+int wga_paf2maf_header(wga_ctx *, const char *, const char *, wga_span *) { return WGA_E_UNSUPPORTED; }
+int wga_paf2maf(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const wga_fasta *, wga_span *) { return WGA_E_UNSUPPORTED; }
 #endif
 #ifndef WGA_WITH_CALL
 int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
