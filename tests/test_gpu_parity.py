@@ -460,7 +460,12 @@ def test_full_size_properties(w, ctx):
     """size-independent invariants on a 1.3 GB slab (too big to diff comfortably): one PAF row per record, NM and
     block length consistent with the per-record counters, stat totals = column sums, one SNP row per mismatch."""
     text = bs.gen_maf(bs.maf_params(200_000, seed=5))
-    out = paf(w, ctx, text)
+    old_slab = w.api.SLAB_BYTES
+    w.api.SLAB_BYTES = 1 << 40  # one slab, so that last_record_counts covers the whole file
+    try:
+        out = paf(w, ctx, text)
+    finally:
+        w.api.SLAB_BYTES = old_slab
     cnt = ctx.last_record_counts().astype(np.int64)
     rows = out.split(b"\n")[:-1]
     assert len(rows) == len(cnt) == 200_000
@@ -567,12 +572,13 @@ def test_paf2maf_edges_and_errors(w, ctx):
                           ([b"cg:Z:" + cg] if tag else [])) + b"\n"
     ok = [line(b"4=1X2I3=2D2="), line(b"4=1X2I3=2D2=", b"-"), line(b"5M"),           # CIGAR shorter than the spans
           line(b"3M2I20M"), line(b"12M3D"), line(b"2I12M", ts=20, te=30),            # spans clipped at the sequence end
-          b"#c\n" + line(b"12=") + b"\n" + line(b"6=6X", b"-"), line(b"1=", qs=0, qe=1, ts=0, te=1)]
+          b"#c\n" + line(b"12=") + b"\n" + line(b"6=6X", b"-"), line(b"1=", qs=0, qe=1, ts=0, te=1), line(b"3=20D1="),
+          line(b"3=20D1=", b"-"), line(b"2I3D2I8=")]
     for paf in ok:
         assert p2m(w, ctx, paf, t_fa, ti, q_fa, qi) == orc.paf2maf(paf, t_fa, ti, q_fa, qi), paf
     bad = [(line(b"10S2M"), 5), (line(b"10MM"), 5), (line(b"M"), 1), (line(b""), 8), (line(b"5=", tag=False), 6),
            (line(b"5=", t=b"nope"), 11), (line(b"5=", q=b"nope"), 11), (line(b"8=", b"-", q=b"bad", qs=0, qe=8), 10),
-           (line(b"20M2I"), 8), (line(b"3=20D1="), 8), (b"a\tb\n", 9),
+           (line(b"20M2I"), 8), (line(b"20M2D"), 8), (b"a\tb\n", 9),
            (line(b"12=") + line(b"3=2Q") + line(b"M"), 5)]
     for paf, code in bad:
         with pytest.raises(orc.OracleError) as eo:

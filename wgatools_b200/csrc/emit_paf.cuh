@@ -66,6 +66,9 @@ struct PafRowArgs {
     uint32_t *row_fixed; // bytes before the CIGAR text
     const uint64_t *row_off;
     char *out;
+    const uint64_t *run_len;   // PASS 1: the CIGAR tokens are written by the row's own thread
+    const uint32_t *run_dl;
+    const uint8_t *run_cls;
 };
 
 // forward-strand query coordinates (maf.rs:433-450), wrapping like release Rust
@@ -75,13 +78,34 @@ __device__ __forceinline__ void query_fwd(const SLines &sl, uint64_t ql, uint64_
     else { *qs = st; *qe = st + al; }
 }
 
-// pass 0: row lengths; pass 1: write everything but the CIGAR tokens
+constexpr int kPafThreads = 128;
+constexpr int kPafSpan = 8192;  // bytes of output one warp (32 consecutive rows) may stage in shared memory
+
+// pass 0: row lengths.  pass 1: one thread per record formats its whole row (fixed fields + CIGAR tokens); the 32 rows
+// of a warp are consecutive in the output, so they are built in one shared-memory span and copied out with aligned
+// word stores (a span longer than kPafSpan -- records with thousands of runs -- is written directly).
 template <int PASS>
-__global__ void k_paf_rows(PafRowArgs A) {
+__global__ void __launch_bounds__(kPafThreads) k_paf_rows(PafRowArgs A) {
+    __shared__ __align__(16) char s_span[PASS == 1 ? kPafThreads / 32 : 1][PASS == 1 ? kPafSpan + 16 : 16];
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > A.n_rec) return;
-    if (r == A.n_rec) { if (PASS == 0) A.row_len[r] = 0; return; }
-    if (A.skip[r]) { if (PASS == 0) { A.row_len[r] = 0; A.row_fixed[r] = 0; } return; }
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t span_lo = 0, span_hi = 0;
+    bool staged = false;
+    if (PASS == 1) {
+        const uint64_t first = r - lane;
+        if (first < A.n_rec) {
+            const uint64_t lastp1 = first + 32 < A.n_rec ? first + 32 : A.n_rec;
+            span_lo = A.row_off[first];
+            span_hi = A.row_off[lastp1];
+            staged = span_hi - span_lo <= (uint64_t)kPafSpan;
+        }
+    }
+    if (PASS == 0) {
+        if (r > A.n_rec) return;
+        if (r == A.n_rec) { A.row_len[r] = 0; return; }
+        if (A.skip[r]) { A.row_len[r] = 0; A.row_fixed[r] = 0; return; }
+    }
+    if (r < A.n_rec && !A.skip[r]) {
     uint64_t tl = A.tl[r], ql = A.ql[r], n = A.ncols[r];
     const unsigned long long *c = A.rec_cnt + r * 5;
     uint64_t match = n - c[0] - c[2] - c[4];
@@ -90,7 +114,8 @@ __global__ void k_paf_rows(PafRowArgs A) {
     uint64_t ts = A.sl.start[tl], te = ts + A.sl.ali[tl];
     const uint8_t *qn = A.text + A.sl.name_off[ql], *tn = A.text + A.sl.name_off[tl];
     uint32_t qnl = A.sl.name_len[ql], tnl = A.sl.name_len[tl];
-    uint64_t cig = A.cig_off[A.rec_run_first[r + 1]] - A.cig_off[A.rec_run_first[r]];
+    const uint64_t j0 = A.rec_run_first[r], j1 = A.rec_run_first[r + 1];
+    uint64_t cig = A.cig_off[j1] - A.cig_off[j0];
     if (PASS == 0) {
         // q_name q_size q_start q_end strand t_name t_size t_start t_end matches block_len 255 NM:i:x cg:Z:...
         uint32_t fixed = csv_name_len(qn, qnl) + 1 + ndigits_u64(A.sl.src[ql]) + 1 + ndigits_u64(qs) + 1 +
@@ -100,7 +125,7 @@ __global__ void k_paf_rows(PafRowArgs A) {
         A.row_fixed[r] = fixed;
         A.row_len[r] = (uint64_t)fixed + cig + 1;
     } else {
-        char *o = A.out + A.row_off[r];
+        char *o = staged ? s_span[threadIdx.x >> 5] + (span_lo & 3u) + (A.row_off[r] - span_lo) : A.out + A.row_off[r];
         o = csv_name_put(o, qn, qnl); *o++ = '\t';
         o = put_u64(o, A.sl.src[ql]); *o++ = '\t';
         o = put_u64(o, qs); *o++ = '\t';
@@ -116,7 +141,33 @@ __global__ void k_paf_rows(PafRowArgs A) {
         *o++ = 'N'; *o++ = 'M'; *o++ = ':'; *o++ = 'i'; *o++ = ':';
         o = put_u64(o, n - match); *o++ = '\t';
         *o++ = 'c'; *o++ = 'g'; *o++ = ':'; *o++ = 'Z'; *o++ = ':';
-        A.out[A.row_off[r] + A.row_fixed[r] + cig] = '\n';
+        for (uint64_t j = j0; j < j1; ++j) {  // "<len><op>" per run (cigar.rs:409-410)
+            const int nd = (int)A.run_dl[j] - 1;
+            write_u64(o, A.run_len[j], nd);
+            o[nd] = kClsChar[A.run_cls[j]];
+            o += nd + 1;
+        }
+        *o = '\n';
+    }
+    }
+    if (PASS == 1) {
+        __syncwarp();
+        if (staged) {
+            const char *sp = s_span[threadIdx.x >> 5];
+            const uint32_t al = (uint32_t)(span_lo & 3u);
+            const uint64_t nbytes = span_hi - span_lo;
+            char *gbase = A.out + (span_lo - al);  // 4-byte aligned (out comes from cudaMalloc)
+            const uint64_t nwords = (al + nbytes + 3) >> 2;
+            for (uint64_t wi = lane; wi < nwords; wi += 32) {
+                const uint64_t b0 = wi * 4;
+                if (b0 >= al && b0 + 4 <= al + nbytes) {
+                    *reinterpret_cast<uint32_t *>(gbase + b0) = *reinterpret_cast<const uint32_t *>(sp + b0);
+                } else {
+                    for (uint64_t b = b0; b < b0 + 4; ++b)
+                        if (b >= al && b < al + nbytes) gbase[b] = sp[b];
+                }
+            }
+        }
     }
 }
 

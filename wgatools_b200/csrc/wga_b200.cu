@@ -531,16 +531,15 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     R.n_rec = n_rec; R.text = ctx->d_text; R.sl = P.sl; R.tl = P.rc.tl; R.ql = P.rc.ql; R.ncols = P.rc.ncols;
     R.skip = P.rc.skip; R.rec_cnt = rec_cnt; R.rec_run_first = rec_run_first; R.cig_off = cig_off;
     R.row_len = row_len; R.row_fixed = row_fixed; R.row_off = row_off; R.out = nullptr;
-    LAUNCH(ctx, k_paf_rows<0>, grid_for(n_rec + 1, 256), 256, R);
+    R.run_len = run_len; R.run_dl = run_dl; R.run_cls = run_cls;
+    LAUNCH(ctx, k_paf_rows<0>, grid_for(n_rec + 1, kPafThreads), kPafThreads, R);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
     WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
     char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_out) return ctx->err_code;
     R.out = d_out;
-    LAUNCH(ctx, k_paf_rows<1>, grid_for(n_rec + 1, 256), 256, R);
-    LAUNCH(ctx, k_paf_cigar, grid_for(n_runs, 256), 256, n_runs, run_rec, run_cls, run_len, run_dl, cig_off, rec_run_first,
-           row_off, row_fixed, d_out);
+    LAUNCH(ctx, k_paf_rows<1>, grid_for(n_rec, kPafThreads), kPafThreads, R);
     // per-record 11 counters stay available for wga_last_record_counts
     unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
     if (!cnt11) return ctx->err_code;
