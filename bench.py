@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample-mb", type=float, default=float(os.environ.get("WGA_BENCH_CPU_MB", 1500)))
     ap.add_argument("--no-call", action="store_true")
+    ap.add_argument("--slab-mb", type=int, default=int(os.environ.get("WGA_BENCH_SLAB_MB", 256)))
     return ap.parse_args()
 
 
@@ -272,11 +273,33 @@ def main():
     own0, cub0 = ctx.launch_counts()
     ms_dev = timed(1, d_text.data_ptr(), args.steps, True)
     own1, cub1 = ctx.launch_counts()
-    # e2e: host buffers, copies inside the timed region
+    # e2e: host buffers, copies inside the timed region.
+    # (1) the public pipeline: ONE asynchronous slab-wise upload per step (ResidentMaf = wga_text_open), the three
+    #     commands run on every slab as it arrives, outputs copied back to pinned host memory inside each call;
+    # (2) three independent host-buffer calls (the file crosses PCIe three times), kept as e2e_separate_calls.
+    d2h = {"n": 0}
+
+    def step_resident(_mem, ptr, _collect=False):
+        acc = w.StatAcc(False)
+        tot = 0
+        with w.ResidentMaf((ptr, nbytes), ctx, args.slab_mb << 20) as rm:
+            for p, n, fl in rm.slabs():
+                tot += ctx.maf2paf_raw(p, n, 1, fl)[1]
+                ctx.maf_stat_raw(p, n, 1, fl, acc)
+                if do_call:
+                    tot += ctx.maf_call_raw(p, n, 1, fl, opts)[1]
+        d2h["n"] = tot
+        return acc
+
+    e2e_steps = max(1, min(args.steps, 3))
+    _step = step
+    step = step_resident
     for _ in range(2):
         step(0, host_ptr)
-    e2e_steps = max(1, min(args.steps, 3))
     ms_e2e = timed(0, host_ptr, e2e_steps, False)
+    step = _step
+    step(0, host_ptr)
+    ms_e2e_sep = timed(0, host_ptr, e2e_steps, False)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -294,9 +317,14 @@ def main():
     line = {"metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "GB/s",
-                    "h2d_bytes_per_step": nbytes * (3 if do_call else 2),
-                    "d2h_bytes_per_step": out_bytes["paf"] + out_bytes["vcf"], "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h["n"],
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                    "mode": f"ResidentMaf: one async upload per step in {args.slab_mb} MiB slabs, the three commands run "
+                            "per slab while the next slab uploads; outputs D2H inside every call"},
+            "e2e_separate_calls": {"value": world * nbytes / (ms_e2e_sep / e2e_steps * 1e-3) / 1e9, "unit": "GB/s",
+                                   "h2d_bytes_per_step": nbytes * (3 if do_call else 2),
+                                   "d2h_bytes_per_step": out_bytes["paf"] + out_bytes["vcf"],
+                                   "mode": "three independent host-buffer calls (file uploaded three times)"},
             "gpu_launches": own1 - own0, "cub_scan_calls": cub1 - cub0,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_walk (dense column walk, all launches of the timed steps)",

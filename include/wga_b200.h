@@ -19,8 +19,9 @@
  *     outputs are library-owned and valid until the next call on the same ctx.
  *   - one ctx per (host thread, GPU); a ctx is not thread-safe; different ctxs may run concurrently.
  *   - there is NO CPU fallback: without a CUDA device wga_ctx_create fails with WGA_E_CUDA.
- *   - device-resident inputs (mem == WGA_MEM_DEVICE) must be 16-byte aligned and readable up to
- *     the next multiple of 16 past `len` (true for any cudaMalloc'ed / torch buffer).
+ *   - device-resident inputs (mem == WGA_MEM_DEVICE) must be readable up to the next multiple of 16
+ *     past `len` (true for any cudaMalloc'ed / torch buffer); a pointer that is not 16-byte aligned
+ *     costs one device-to-device copy of the slab.
  */
 #ifndef WGA_B200_H
 #define WGA_B200_H
@@ -58,12 +59,16 @@ enum { WGA_MEM_HOST = 0, WGA_MEM_DEVICE = 1 };
 /* the slab starts at byte 0 of the file: its first line is the header MAFReader::new swallows
  * unconditionally (src/parser/maf.rs:25-36).  Slabs of one file must be cut before a line that
  * does not start with 's' (wga_maf_safe_cut) so that s-line groups are never split. */
-enum { WGA_F_FIRST_SLAB = 1u };
+enum {
+    WGA_F_FIRST_SLAB = 1u,
+    /* with mem == WGA_MEM_DEVICE: still hand the output back in (pinned) host memory */
+    WGA_F_OUT_HOST = 2u
+};
 
 typedef struct wga_ctx wga_ctx;
 
 typedef struct {
-    const void *data; /* same memory kind as the input text (pinned host or device) */
+    const void *data; /* same memory kind as the input text (pinned host or device); host with WGA_F_OUT_HOST */
     uint64_t len;
 } wga_span;
 
@@ -87,6 +92,22 @@ void wga_host_free(void *p);
 /* offset of the last line in text[0..len) (other than the first) that does not start with 's':
  * cutting a file there never splits an s-line group (maf.rs:395-413).  0 if there is none. */
 uint64_t wga_maf_safe_cut(const char *text, uint64_t len);
+
+/* ---- resident text: one upload, several commands ------------------------------------------------
+ * The reference runs maf2paf / stat / call as separate passes over the same file (each re-reads it,
+ * src/parser/maf.rs:15-44).  Here the file is uploaded ONCE, asynchronously and slab by slab on a
+ * private copy stream; wga_text_slab() makes the ctx stream wait for slab k only, so the commands
+ * run on slab k while slab k+1 is still crossing PCIe.  Slabs are cut with wga_maf_safe_cut and lie
+ * contiguously in HBM, so after the last slab the whole text can also be used in one call.
+ * host_text must stay valid until wga_text_close (pinned memory gives full PCIe rate).  One resident
+ * text per ctx at a time; slab_bytes == 0 picks 256 MiB. */
+typedef struct wga_text wga_text;
+int wga_text_open(wga_ctx *ctx, const void *host_text, uint64_t len, uint64_t slab_bytes, wga_text **out);
+uint32_t wga_text_slabs(const wga_text *t);
+/* device pointer / length / WGA_F_FIRST_SLAB flag of slab k, to be passed with WGA_MEM_DEVICE */
+int wga_text_slab(wga_text *t, uint32_t k, const void **dev, uint64_t *len, uint32_t *flags);
+int wga_text_whole(wga_text *t, const void **dev, uint64_t *len);
+void wga_text_close(wga_text *t);
 
 /* ---- maf2paf: src/converter.rs:29-54 + MAFRecord::convert2paf src/parser/maf.rs:484-520 ------ */
 /* out = PAF rows (14 tab-separated fields, '\n'-terminated), one per MAF record, file order.

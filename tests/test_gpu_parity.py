@@ -216,6 +216,42 @@ def test_multi_slab_matches_single(w, ctx):
         w.api.SLAB_BYTES = old
 
 
+def test_resident_maf_pipeline(w, ctx):
+    """one upload, three commands, small slabs (unaligned slab starts -> realign copy), slab-major and command-major"""
+    text = bs.gen_maf(bs.maf_params(1500, seed=35, p_neg=0.3))
+    want_paf, want_stat = orc.maf2paf(text), orc.stat_maf(text)
+    want_vcf = orc.call_maf(text, snp=True, svlen=0)
+    for slab in (70_000, 1 << 20, 0):
+        with w.ResidentMaf(text, ctx, slab) as rm:
+            if slab == 70_000:
+                assert ctx.L.wga_text_slabs(rm.h) > 10
+            # command-major through the reference-shaped functions
+            assert w.run_bytes(w.maf2paf, rm, ctx=ctx) == want_paf
+            assert w.run_bytes(w.stat_maf, rm, ctx=ctx) == want_stat
+            assert w.run_bytes(w.call_var_maf, rm, None, True, False, 0, ctx=ctx) == want_vcf
+            # slab-major through the raw calls
+            from wgatools_b200._lib import CallOpts
+            opts = CallOpts(snp=1, inv=0, svlen_cutoff=0, chunk_size=1000000, query_name=None)
+            acc = w.StatAcc(False)
+            out_paf, out_vcf = [], [ctx.vcf_header("sample")]
+            for p, n, fl in rm.slabs():
+                ptr, ln = ctx.maf2paf_raw(p, n, 1, fl)
+                out_paf.append(ctypes.string_at(ptr, ln) if ln else b"")
+                ctx.maf_stat_raw(p, n, 1, fl, acc)
+                ptr, ln = ctx.maf_call_raw(p, n, 1, fl, opts)
+                out_vcf.append(ctypes.string_at(ptr, ln) if ln else b"")
+            assert b"".join(out_paf) == want_paf
+            assert acc.write() == want_stat
+            assert b"".join(out_vcf) == want_vcf
+            # the whole text in one call once everything has arrived
+            p, n, fl = rm.whole()
+            ptr, ln = ctx.maf2paf_raw(p, n, 1, fl)
+            assert ctypes.string_at(ptr, ln) == want_paf
+    # empty text
+    with w.ResidentMaf(b"", ctx) as rm:
+        assert w.run_bytes(w.maf2paf, rm, ctx=ctx) == b""
+
+
 def test_stat_export_import_roundtrip(w, ctx):
     text = bs.gen_maf(bs.maf_params(600, seed=44, p_neg=0.4))
     L = ctx.L

@@ -11,6 +11,7 @@ SO_PATH = os.environ.get("WGA_B200_LIB") or os.path.join(_DIR, "libwga_b200.so")
 
 WGA_MEM_HOST, WGA_MEM_DEVICE = 0, 1
 WGA_F_FIRST_SLAB = 1
+WGA_F_OUT_HOST = 2
 
 
 class Span(ctypes.Structure):
@@ -33,6 +34,12 @@ ABI = {
     "wga_host_alloc": (ctypes.c_void_p, [ctypes.c_uint64]),
     "wga_host_free": (None, [ctypes.c_void_p]),
     "wga_maf_safe_cut": (ctypes.c_uint64, [ctypes.c_void_p, ctypes.c_uint64]),
+    "wga_text_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, _P(ctypes.c_void_p)]),
+    "wga_text_slabs": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "wga_text_slab": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, _P(ctypes.c_void_p), _P(ctypes.c_uint64),
+                                    _P(ctypes.c_uint32)]),
+    "wga_text_whole": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_void_p), _P(ctypes.c_uint64)]),
+    "wga_text_close": (None, [ctypes.c_void_p]),
     "wga_maf2paf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
                                   ctypes.c_char_p, _P(Span)]),
     "wga_stat_acc_create": (ctypes.c_void_p, [ctypes.c_int]),

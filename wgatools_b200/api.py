@@ -14,7 +14,7 @@ import io
 import os
 
 from . import _lib
-from ._lib import WGA_F_FIRST_SLAB, WGA_MEM_DEVICE, WGA_MEM_HOST, CallOpts, Span
+from ._lib import WGA_F_FIRST_SLAB, WGA_F_OUT_HOST, WGA_MEM_DEVICE, WGA_MEM_HOST, CallOpts, Span
 
 SLAB_BYTES = 1 << 30  # host inputs larger than this are cut into slabs at s-line-group boundaries
 
@@ -206,6 +206,71 @@ class PAFReader:
         self.data = _read_all(reader)
 
 
+class ResidentMaf:
+    """A MAF uploaded ONCE for several commands (the reference re-reads the file per command).
+
+    The upload is asynchronous and slab-wise (include/wga_b200.h, wga_text_open): iterating `slabs()` hands out
+    each slab as soon as it has arrived, so commands on slab k overlap the PCIe transfer of slab k+1.
+    maf2paf / stat_maf / call_var_maf accept a ResidentMaf wherever they take a MAFReader.
+    `data`: bytes-like, or (host_address, length) of caller-owned (ideally pinned) memory."""
+
+    def __init__(self, data, ctx=None, slab_bytes=0):
+        self.ctx = ctx or default_context()
+        if isinstance(data, tuple):
+            self._keep, base, n = None, int(data[0]), int(data[1])
+        else:
+            data = _read_all(data)
+            self._keep, base = _host_ptr(data)
+            n = len(data)
+        h = ctypes.c_void_p()
+        self.ctx._check(self.ctx.L.wga_text_open(self.ctx.h, ctypes.c_void_p(base), n, int(slab_bytes), ctypes.byref(h)))
+        self.h = h
+        self.nbytes = n
+
+    def slabs(self):
+        """yield (device_ptr, length, flags); flags carry WGA_F_OUT_HOST so outputs come back in host memory"""
+        L = self.ctx.L
+        for k in range(L.wga_text_slabs(self.h)):
+            dev, ln, fl = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_uint32()
+            self.ctx._check(L.wga_text_slab(self.h, k, ctypes.byref(dev), ctypes.byref(ln), ctypes.byref(fl)))
+            yield ctypes.c_void_p(dev.value), ln.value, fl.value | WGA_F_OUT_HOST
+
+    def whole(self):
+        dev, ln = ctypes.c_void_p(), ctypes.c_uint64()
+        self.ctx._check(self.ctx.L.wga_text_whole(self.h, ctypes.byref(dev), ctypes.byref(ln)))
+        return ctypes.c_void_p(dev.value), ln.value, WGA_F_FIRST_SLAB | WGA_F_OUT_HOST
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.wga_text_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _maf_slabs(src, ctx):
+    """(ptr, length, mem, flags) of every slab of a MAFReader (host, cut here) or a ResidentMaf (device)"""
+    if isinstance(src, ResidentMaf):
+        if src.ctx is not ctx:
+            raise WGAError(101, "ResidentMaf belongs to another Context")
+        for ptr, n, flags in src.slabs():
+            yield ptr, n, WGA_MEM_DEVICE, flags
+        return
+    keep, base = _host_ptr(src.data)
+    for off, n, flags in _slabs(src.data, ctx.L):
+        yield ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags
+
+
 def _slabs(data: bytes, L):
     """yield (offset, length, flags): slabs cut right before a line that is not an s-line"""
     n = len(data)
@@ -236,9 +301,8 @@ def _host_ptr(data: bytes):
 def maf2paf(mafreader: MAFReader, writer, query_name=None, ctx=None):
     """src/converter.rs:29-54: every MAF record -> one PAF row (file order, i.e. the `-t 1` order)."""
     ctx = ctx or default_context()
-    keep, base = _host_ptr(mafreader.data)
-    for off, n, flags in _slabs(mafreader.data, ctx.L):
-        ptr, ln = ctx.maf2paf_raw(ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags, query_name)
+    for p, n, mem, flags in _maf_slabs(mafreader, ctx):
+        ptr, ln = ctx.maf2paf_raw(p, n, mem, flags, query_name)
         if ln:
             writer.write(ctypes.string_at(ptr, ln))
 
@@ -247,9 +311,8 @@ def stat_maf(reader: MAFReader, writer, each=False, query_name=None, ctx=None):
     """src/tools/stat.rs:61-84"""
     ctx = ctx or default_context()
     acc = StatAcc(each)
-    keep, base = _host_ptr(reader.data)
-    for off, n, flags in _slabs(reader.data, ctx.L):
-        ctx.maf_stat_raw(ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags, acc, query_name)
+    for p, n, mem, flags in _maf_slabs(reader, ctx):
+        ctx.maf_stat_raw(p, n, mem, flags, acc, query_name)
     writer.write(acc.write())
 
 
@@ -271,9 +334,8 @@ def call_var_maf(mafreader: MAFReader, mafindex, writer, if_snp=False, if_inv=Fa
     writer.write(ctx.vcf_header(sample or "sample"))
     opts = CallOpts(snp=int(bool(if_snp)), inv=int(bool(if_inv)), svlen_cutoff=int(svlen_cutoff),
                     chunk_size=int(1000000 if chunk_size is None else chunk_size), query_name=_opt(query_name))
-    keep, base = _host_ptr(mafreader.data)
-    for off, n, flags in _slabs(mafreader.data, ctx.L):
-        ptr, ln = ctx.maf_call_raw(ctypes.c_void_p(base + off), n, WGA_MEM_HOST, flags, opts)
+    for p, n, mem, flags in _maf_slabs(mafreader, ctx):
+        ptr, ln = ctx.maf_call_raw(p, n, mem, flags, opts)
         if ln:
             writer.write(ctypes.string_at(ptr, ln))
 

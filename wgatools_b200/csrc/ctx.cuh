@@ -47,6 +47,7 @@ enum BufId {
     B_PT_KEYS, B_PT_FIRST, B_PT_VALS, B_REC_SLOT, B_PT_FLAG, B_PT_IDX, B_PAIR_FIRST, B_PAIR_VALS,
     B_NAME_LEN, B_NAME_OFF, B_NAME_BUF, B_INV_FLAG, B_INV_IDX, B_INV_PAIR, B_INV_NUM,
     B_GEN_A, B_GEN_B, B_GEN_C, B_GEN_D, B_GEN_E, B_GEN_F, B_GEN_G, B_GEN_H,
+    B_TEXT_RES,
     B_PAF_A, B_PAF_B, B_PAF_C, B_PAF_D, B_PAF_E, B_PAF_F, B_PAF_G, B_PAF_H, B_PAF_I, B_PAF_J,
     B_COUNT_
 };

@@ -144,6 +144,7 @@ template <int CLS, int CAP>
 __global__ void __launch_bounds__(kTokWarps * 32) k_ws_scan(const uint8_t *__restrict__ text, uint64_t len, uint64_t n_tiles,
                                                             uint64_t *__restrict__ tile_ws, uint64_t *__restrict__ tile_nl,
                                                             uint16_t *__restrict__ slots, uint32_t *__restrict__ overflow) {
+    __shared__ uint32_t s_cnt[kTokWarps][2];  // per warp: delimiters, newlines of the current tile
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint64_t n_warps = (uint64_t)gridDim.x * kTokWarps;
     for (uint64_t tile = (uint64_t)blockIdx.x * kTokWarps + wid; tile < n_tiles; tile += n_warps) {
@@ -154,86 +155,90 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_ws_scan(const uint8_t *__res
             uint64_t off = base + (uint64_t)k * 512 + lane * 16;
             v[k] = off < len ? ldg16(text + off) : make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
         }
-        uint32_t cw = 0, cn = 0;
+        if (lane == 0) { s_cnt[wid][0] = 0; s_cnt[wid][1] = 0; }
+        __syncwarp();
         uint16_t *slot = slots + tile * CAP;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            // dense part: 3 ops per word find candidate bytes (< 0x21).  Delimiters are sparse: only the few lanes that
-            // hold a candidate run the exact test, and their counts are combined with one shuffle per such lane, so the
-            // slots are written in text order without a full warp scan.
+            // dense part: 3 ops per word.  Delimiters are sparse, the exact test runs per candidate byte only;
+            // entries of one step land in arbitrary order (shared atomic), k_ws_compact sorts the tile's few entries
             const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
             const uint32_t c0 = lt21_bytes(w[0]), c1 = lt21_bytes(w[1]), c2 = lt21_bytes(w[2]), c3 = lt21_bytes(w[3]);
-            const bool cand = (c0 | c1 | c2 | c3) != 0u;
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, cand);
-            if (m) {
+            if (c0 | c1 | c2 | c3) {
+                const uint32_t cand[4] = {c0, c1, c2, c3};
                 const uint32_t rel0 = (uint32_t)k * 512u + lane * 16u;
-                uint32_t flags[4] = {0, 0, 0, 0}, cnt = 0;
-                if (cand) {
-                    const uint32_t cd[4] = {c0, c1, c2, c3};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t mm = cd[i];
-                        while (mm) {
-                            const int bit = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const uint32_t byte = (uint32_t)(bit >> 3);
-                            const uint32_t ch = (w[i] >> (8 * byte)) & 0xFFu;
-                            if (is_delim<CLS>(ch) && base + rel0 + 4u * i + byte < len) { flags[i] |= 1u << bit; ++cnt; }
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t m = cand[i];
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t byte = (uint32_t)(bit >> 3);
+                        const uint32_t ch = (w[i] >> (8 * byte)) & 0xFFu;
+                        const uint32_t rel = rel0 + 4u * i + byte;
+                        if (is_delim<CLS>(ch) && base + rel < len) {
+                            const uint32_t isnl = ch == 0x0Au;
+                            const uint32_t idx = atomicAdd(&s_cnt[wid][0], 1u);
+                            if (isnl) atomicAdd(&s_cnt[wid][1], 1u);
+                            if (idx < (uint32_t)CAP) slot[idx] = (uint16_t)(rel | (isnl << 15));
                         }
                     }
                 }
-                uint32_t pre = 0, tot = 0;
-                while (m) {  // warp-uniform: one iteration per candidate lane
-                    const int L = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t cL = __shfl_sync(0xFFFFFFFFu, cnt, L);
-                    if ((uint32_t)L < lane) pre += cL;
-                    tot += cL;
-                }
-                if (cnt) {
-                    uint32_t idx = cw + pre;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t mm = flags[i];
-                        while (mm) {
-                            const int bit = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const uint32_t byte = (uint32_t)(bit >> 3);
-                            const uint32_t isnl = ((w[i] >> (8 * byte)) & 0xFFu) == 0x0Au;
-                            if (idx < (uint32_t)CAP) slot[idx] = (uint16_t)((rel0 + 4u * i + byte) | (isnl << 15));
-                            cn += isnl;
-                            ++idx;
-                        }
-                    }
-                }
-                cw += tot;
             }
         }
-        cn = warp_sum(cn);
+        __syncwarp();
         if (lane == 0) {
+            const uint32_t cw = s_cnt[wid][0];
             tile_ws[tile] = cw;
-            tile_nl[tile] = cn;
+            tile_nl[tile] = s_cnt[wid][1];
             if (cw > (uint32_t)CAP) atomicOr(overflow, 1u);
         }
+        __syncwarp();
     }
 }
 
+// one warp per tile: the slots of a tile arrive ordered step by step but unordered inside a step (shared atomics), so
+// every entry computes its rank among the tile's (few) entries with shuffles and is written straight to its place
 template <int CAP>
 __global__ void k_ws_compact(uint64_t n_tiles, const uint64_t *__restrict__ tile_ws, const uint64_t *__restrict__ ws_off,
                              const uint64_t *__restrict__ nl_off, const uint16_t *__restrict__ slots,
                              uint64_t *__restrict__ ws_ent, uint64_t *__restrict__ nl_ws_idx) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     if (t >= n_tiles) return;
     uint32_t c = (uint32_t)tile_ws[t];
     if (c > (uint32_t)CAP) c = CAP;  // overflow: the caller discards this index
-    uint64_t wo = ws_off[t], no = nl_off[t];
-    const uint64_t base = t * kTokTile;
+    if (c == 0) return;
+    const uint64_t wo = ws_off[t], no = nl_off[t], base = t * kTokTile;
     const uint16_t *slot = slots + t * CAP;
-    for (uint32_t i = 0; i < c; ++i) {  // slots are already in text order
-        const uint32_t e = slot[i];
-        const bool isnl = e >> 15;
-        ws_ent[wo + i] = (base + (e & 0x7FFFu)) | (isnl ? ~kPosMask : 0ull);
-        if (isnl) nl_ws_idx[no++] = wo + i;
+    if (c <= 32) {
+        const uint32_t e = lane < c ? slot[lane] : 0xFFFFu;
+        const uint32_t rel = e & 0x7FFFu, isnl = lane < c ? (e >> 15) : 0u;
+        uint32_t rank = 0, nlrank = 0;
+        for (uint32_t j = 0; j < c; ++j) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, e, j);
+            const bool before = (v & 0x7FFFu) < rel;
+            rank += before;
+            nlrank += before && (v >> 15);
+        }
+        if (lane < c) {
+            ws_ent[wo + rank] = (base + rel) | (isnl ? ~kPosMask : 0ull);
+            if (isnl) nl_ws_idx[no + nlrank] = wo + rank;
+        }
+        return;
+    }
+    // many delimiters in one tile (rare): ranks by a cooperative O(c^2) count over the slot array
+    for (uint32_t i = lane; i < c; i += 32) {
+        const uint32_t e = slot[i], rel = e & 0x7FFFu;
+        uint32_t rank = 0, nlrank = 0;
+        for (uint32_t j = 0; j < c; ++j) {
+            const uint32_t v = slot[j];
+            const bool before = (v & 0x7FFFu) < rel;
+            rank += before;
+            nlrank += before && (v >> 15);
+        }
+        ws_ent[wo + rank] = (base + rel) | ((e >> 15) ? ~kPosMask : 0ull);
+        if (e >> 15) nl_ws_idx[no + nlrank] = wo + rank;
     }
 }
 

@@ -111,9 +111,13 @@ int stage_text(wga_ctx *ctx, const void *text, uint64_t len, int mem) {
     ctx->text_len = len;
     ctx->h_text = nullptr;
     if (mem == WGA_MEM_DEVICE) {
-        if (reinterpret_cast<uintptr_t>(text) & 15u) {
-            ctx->set_error(WGA_E_INVALID_ARG, 0, "device text must be 16-byte aligned");
-            return WGA_E_INVALID_ARG;
+        if (reinterpret_cast<uintptr_t>(text) & 15u) {  // e.g. a slab of a resident text: realign with one D2D copy
+            uint8_t *d = (uint8_t *)ctx->ensure(B_TEXT, len + 64);
+            if (!d) return ctx->err_code;
+            if (len) WGA_CK(cudaMemcpyAsync(d, text, len, cudaMemcpyDeviceToDevice, ctx->stream));
+            WGA_CK(cudaMemsetAsync(d + len, 0, 64, ctx->stream));
+            ctx->d_text = d;
+            return WGA_OK;
         }
         ctx->d_text = (const uint8_t *)text;
         return WGA_OK;
@@ -198,7 +202,7 @@ int build_delim_index(wga_ctx *ctx, const uint8_t *text, uint64_t len, uint64_t 
             ws_ent = ctx->buf<uint64_t>(B_WS, n_ws + 1); nl_idx = ctx->buf<uint64_t>(B_NLIDX, n_nl + 1);
             if (!ws_ent || !nl_idx) return ctx->err_code;
             auto k_comp = k_ws_compact<CAP>;
-            LAUNCH(ctx, k_comp, grid_for(n_tiles, 256), 256, n_tiles, tile_ws, ws_off, nl_off, slots, ws_ent, nl_idx);
+            LAUNCH(ctx, k_comp, grid_for(n_tiles * 32, 256), 256, n_tiles, tile_ws, ws_off, nl_off, slots, ws_ent, nl_idx);
             indexed = true;
         }
     }
@@ -395,8 +399,8 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
 }
 
 // hand the command's output back in the caller's memory kind
-int finish_output(wga_ctx *ctx, const void *d_out, uint64_t n, int mem, wga_span *out) {
-    if (mem == WGA_MEM_DEVICE || n == 0) {
+int finish_output(wga_ctx *ctx, const void *d_out, uint64_t n, int mem, uint32_t flags, wga_span *out) {
+    if ((mem == WGA_MEM_DEVICE && !(flags & WGA_F_OUT_HOST)) || n == 0) {
         out->data = n ? d_out : nullptr;
         out->len = n;
         return sync_check(ctx);
@@ -494,6 +498,104 @@ uint64_t wga_maf_safe_cut(const char *text, uint64_t len) {
     return 0;
 }
 
+// ---------------------------------------------------------------- resident text
+struct wga_text {
+    wga_ctx *ctx = nullptr;
+    uint8_t *d = nullptr;
+    uint64_t len = 0;
+    std::vector<uint64_t> off;  // n_slabs + 1
+    std::vector<cudaEvent_t> ev;
+    cudaStream_t copy = nullptr;
+};
+
+int wga_text_open(wga_ctx *ctx, const void *host_text, uint64_t len, uint64_t slab_bytes, wga_text **out) {
+    if (!ctx || !out || (!host_text && len)) return WGA_E_INVALID_ARG;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    if (slab_bytes == 0) slab_bytes = 256ull << 20;
+    if (slab_bytes < 4096) slab_bytes = 4096;
+    const char *h = (const char *)host_text;
+    // the previous resident text (same buffer) may still be read by work on the ctx stream
+    WGA_CK(cudaStreamSynchronize(ctx->stream));
+    uint8_t *d = (uint8_t *)ctx->ensure(B_TEXT_RES, len + 64);
+    if (!d) return ctx->err_code;
+    wga_text *t = new wga_text();
+    t->ctx = ctx;
+    t->d = d;
+    t->len = len;
+    if (cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking) != cudaSuccess) {
+        delete t;
+        ctx->set_error(WGA_E_CUDA, 0, "cudaStreamCreate failed");
+        return WGA_E_CUDA;
+    }
+    uint64_t off = 0;
+    t->off.push_back(0);
+    while (off < len) {
+        uint64_t want = std::min<uint64_t>(slab_bytes, len - off), cut = want;
+        while (off + want < len) {  // cut before a line that is not an s-line; widen the window until one exists
+            cut = wga_maf_safe_cut(h + off, want);
+            if (cut) break;
+            want = std::min<uint64_t>(want * 2, len - off);
+            cut = want;
+        }
+        cudaEvent_t e = nullptr;
+        if (cudaMemcpyAsync(d + off, h + off, cut, cudaMemcpyHostToDevice, t->copy) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(e, t->copy) != cudaSuccess) {
+            if (e) cudaEventDestroy(e);
+            wga_text_close(t);
+            ctx->set_error(WGA_E_CUDA, 0, "asynchronous upload failed");
+            return WGA_E_CUDA;
+        }
+        t->ev.push_back(e);
+        off += cut;
+        t->off.push_back(off);
+    }
+    if (t->ev.empty()) {  // empty text: one empty slab
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEventRecord(e, t->copy);
+        t->ev.push_back(e);
+        t->off.push_back(0);
+    }
+    cudaMemsetAsync(d + len, 0, 64, t->copy);
+    cudaEventRecord(t->ev.back(), t->copy);  // the last slab also covers the zero tail
+    *out = t;
+    return WGA_OK;
+}
+
+uint32_t wga_text_slabs(const wga_text *t) { return t ? (uint32_t)t->ev.size() : 0; }
+
+int wga_text_slab(wga_text *t, uint32_t k, const void **dev, uint64_t *len, uint32_t *flags) {
+    if (!t || k >= t->ev.size() || !dev || !len) return WGA_E_INVALID_ARG;
+    wga_ctx *ctx = t->ctx;
+    cudaSetDevice(ctx->device);
+    WGA_CK(cudaStreamWaitEvent(ctx->stream, t->ev[k], 0));
+    *dev = t->d + t->off[k];
+    *len = t->off[k + 1] - t->off[k];
+    if (flags) *flags = k == 0 ? WGA_F_FIRST_SLAB : 0u;
+    return WGA_OK;
+}
+
+int wga_text_whole(wga_text *t, const void **dev, uint64_t *len) {
+    if (!t || !dev || !len) return WGA_E_INVALID_ARG;
+    wga_ctx *ctx = t->ctx;
+    cudaSetDevice(ctx->device);
+    WGA_CK(cudaStreamWaitEvent(ctx->stream, t->ev.back(), 0));
+    *dev = t->d;
+    *len = t->len;
+    return WGA_OK;
+}
+
+void wga_text_close(wga_text *t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    if (t->copy) cudaStreamSynchronize(t->copy);
+    for (cudaEvent_t e : t->ev) cudaEventDestroy(e);
+    if (t->copy) cudaStreamDestroy(t->copy);
+    delete t;
+}
+
 // ---------------------------------------------------------------- maf2paf
 int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name,
                 wga_span *out) {
@@ -545,7 +647,7 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     if (!cnt11) return ctx->err_code;
     LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
     ctx->last_counts_valid = true;
-    return finish_output(ctx, d_out, total, mem, out);
+    return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
 // ---------------------------------------------------------------- stat
@@ -872,7 +974,7 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     char *d_out = (char *)ctx->ensure(B_OUT, sc[0] + 16);
     if (!d_out) return ctx->err_code;
     LAUNCH(ctx, k_vcf_rows<1>, grid_for(n_rows, 128), 128, V, n_rows, rowbase, row_len, row_off, d_out, P.err_key);
-    return finish_output(ctx, d_out, sc[0], mem, out);
+    return finish_output(ctx, d_out, sc[0], mem, flags, out);
 }
 #endif
 
@@ -1196,7 +1298,7 @@ int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     LAUNCH(ctx, k_p2m_rows, grid_for((n_opsT + n_rec) * 32, 256), 256, V);
     WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    int rc = finish_output(ctx, d_out, total, mem, out);
+    int rc = finish_output(ctx, d_out, total, mem, flags, out);
     if (rc) return rc;
     float ms = 0.f;
     WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
