@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample-mb", type=float, default=float(os.environ.get("WGA_BENCH_CPU_MB", 1500)))
     ap.add_argument("--no-call", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer legs")
     ap.add_argument("--slab-mb", type=int, default=int(os.environ.get("WGA_BENCH_SLAB_MB", 256)))
     return ap.parse_args()
 
@@ -292,14 +293,16 @@ def main():
         return acc
 
     e2e_steps = max(1, min(args.steps, 3))
-    _step = step
-    step = step_resident
-    for _ in range(2):
+    ms_e2e = ms_e2e_sep = float("nan")
+    if not args.no_e2e:
+        _step = step
+        step = step_resident
+        for _ in range(2):
+            step(0, host_ptr)
+        ms_e2e = timed(0, host_ptr, e2e_steps, False)
+        step = _step
         step(0, host_ptr)
-    ms_e2e = timed(0, host_ptr, e2e_steps, False)
-    step = _step
-    step(0, host_ptr)
-    ms_e2e_sep = timed(0, host_ptr, e2e_steps, False)
+        ms_e2e_sep = timed(0, host_ptr, e2e_steps, False)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
