@@ -165,6 +165,15 @@ int wga_paf2maf_header(wga_ctx *ctx, const char *t_fa_path, const char *q_fa_pat
 int wga_paf2maf(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *target,
                 const wga_fasta *query, wga_span *out);
 
+/* ---- call -f paf: src/tools/caller.rs:268-302 call_var_paf + :610-822 call_within_var_paf -------------------- */
+/* VCF body rows of one slab of PAF lines, file order (the header comes from wga_vcf_header).  Sequences are
+ * fetched as [start, end] INCLUSIVE (paf.rs:221-237), '-' queries are not reverse-complemented, every '-' record
+ * gets an <INV> row, and a failing CIGAR token / VCF row silently ends its record (the reference discards the
+ * fold closure's Result, caller.rs:673-815).  The reference buffers all rows and writes the header last, so on
+ * any error there is no output at all. */
+int wga_paf_call(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *target,
+                 const wga_fasta *query, int snp, uint64_t svlen_cutoff, wga_span *out);
+
 /* ---- AlignRecord-level batch access (common.rs:142-176 get_stat / get_cigar_string) --------- */
 /* per-record counters of the last wga_maf2paf / wga_maf_stat / wga_paf_stat call, struct Cigar order
  * (cigar.rs:16-29): match, mismatch, ins_event, ins, del_event, del, inv_ins_event, inv_ins,

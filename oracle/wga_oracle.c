@@ -1492,3 +1492,135 @@ int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_l
     orc_buf_free(&ts); orc_buf_free(&qs);
     return rc;
 }
+
+/* ------------------------------------------------------------- call -f paf */
+/* src/tools/caller.rs:268-302 call_var_paf + :610-822 call_within_var_paf.
+ * Sequences come from faidx with an INCLUSIVE end (paf.rs:221-237: [start, end], one base more than the
+ * alignment -- Q13); the query is NOT reverse-complemented for '-' (Q12); the <INV> row is not gated (Q12).
+ * The fold closure's Result is discarded (caller.rs:673-815: `let (_, _) = fold_many1(..)(cigar)?`), so the
+ * first failing token / row of a record silently ENDS that record (rows before it are kept) -- Q15.
+ * Slices past the fetched strings and `pos - start - 1` underflows are panics.  All rows are buffered and
+ * the header is written after the loop (caller.rs:283-299), so any error leaves the output empty. */
+int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_len, const char *t_fai, size_t t_fai_len,
+                 const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, int snp, uint64_t svlen_cutoff,
+                 const char *sample, orc_buf *out, char *err, size_t errcap) {
+    faidx tf, qf;
+    if (fai_parse(t_fai, t_fai_len, t_fa, t_fa_len, &tf) || fai_parse(q_fai, q_fai_len, q_fa, q_fa_len, &qf)) {
+        set_err(err, errcap, "HTS library error by bad .fai");
+        return ORC_E_CSV;
+    }
+    size_t pos = 0;
+    pafrow row = {0};
+    orc_buf ts = {0}, qs = {0}, body = {0}, conv = {0}, rowb = {0};
+    int rc = ORC_OK;
+    char info[256], tail[1200], dis[64];
+    while (rc == ORC_OK && paf_next(paf, paf_len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int neg = 0, bad = row.n < 12;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) { if (sv_eq_c(row.f[4], "+")) neg = 0; else if (sv_eq_c(row.f[4], "-")) neg = 1; else bad = 1; continue; }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+        sv qname = row.f[0], tname = row.f[5];
+        const uint64_t q_st = u[2], q_en = u[3], t_st = u[7], t_en = u[8];
+        ts.n = 0; qs.n = 0;
+        if (fai_fetch(&tf, tname, t_st, t_en, &ts) || fai_fetch(&qf, qname, q_st, q_en, &qs)) {
+            set_err(err, errcap, "HTS library error by sequence not found");
+            rc = ORC_E_NOM; break;
+        }
+        const char sfx = neg ? 'N' : 'P';
+        if (qname.n > 1000) { set_err(err, errcap, "oracle: query name too long"); rc = ORC_E_PANIC; break; }
+        if (neg) { /* caller.rs:641-658 */
+            if (ts.n < 1) { set_err(err, errcap, "panic: byte index 1 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
+            snprintf(info, sizeof info, "SVTYPE=INV;END=%llu", (unsigned long long)t_en);
+            snprintf(tail, sizeof tail, "%.*s@%llu@%llu@%c", (int)qname.n, qname.p, (unsigned long long)q_st,
+                     (unsigned long long)q_en, sfx);
+            rc = vcf_row(&body, tname, t_st + 1, ts.p, 1, "<INV>", 5, 1, info, tail, err, errcap);
+            if (rc) break;
+        }
+        /* paf.rs:122-140 get_cigar_string */
+        sv cg = {0, 0};
+        int have = 0;
+        for (size_t k = 12; k < row.n && !have; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
+        if (!have)
+            for (size_t k = 12; k < row.n && !have; k++)
+                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
+                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
+                    conv.n = 0;
+                    cs_to_cigar(cs, &conv);
+                    cg.p = conv.p; cg.n = conv.n; have = 1;
+                }
+        if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
+        if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
+        uint64_t t_pos = t_st, q_pos = q_st;
+        int after_m = 0, stopped = 0;
+        size_t i = 0;
+        while (i < cg.n && !stopped && rc == ORC_OK) {
+            size_t d0 = i;
+            while (i < cg.n && cg.p[i] >= '0' && cg.p[i] <= '9') i++;
+            size_t o0 = i;
+            while (i < cg.n && !(cg.p[i] >= '0' && cg.p[i] <= '9')) i++;
+            sv digits = {cg.p + d0, o0 - d0}, op = {cg.p + o0, i - o0};
+            uint64_t len;
+            if (op.n != 1 || !parse_u64(digits, &len)) { stopped = 1; break; } /* cst2cu error, discarded */
+            switch (op.p[0]) {
+            case 'M': case '=': t_pos += len; q_pos += len; after_m = 1; break;
+            case 'X':
+                if (snp) {
+                    for (uint64_t k = 0; k < len; k++) {
+                        const uint64_t a = t_pos - t_st, b = q_pos - q_st;
+                        if (a + 1 > ts.n || b + 1 > qs.n) { set_err(err, errcap, "panic: byte index out of range"); rc = ORC_E_PANIC; break; }
+                        snprintf(tail, sizeof tail, "%.*s@%llu@%c", (int)qname.n, qname.p, (unsigned long long)q_pos, sfx);
+                        rowb.n = 0;
+                        if (vcf_row(&rowb, tname, t_pos + 1, ts.p + a, 1, qs.p + b, 1, 0, NULL, tail, dis, sizeof dis)) { stopped = 1; break; }
+                        buf_put(&body, rowb.p, rowb.n);
+                        t_pos++; q_pos++;
+                    }
+                } else { t_pos += len; q_pos += len; }
+                after_m = 1;
+                break;
+            case 'I':
+                if (len > svlen_cutoff && after_m) {
+                    if (t_pos == t_st || q_pos == q_st) { set_err(err, errcap, "panic: attempt to subtract with overflow"); rc = ORC_E_PANIC; break; }
+                    const uint64_t a = t_pos - t_st - 1, b = q_pos - q_st - 1;
+                    if (a + 1 > ts.n || len > qs.n || b + len + 1 > qs.n) { set_err(err, errcap, "panic: byte index out of range"); rc = ORC_E_PANIC; break; }
+                    snprintf(info, sizeof info, "%sSVTYPE=INS;SVLEN=%llu;END=%llu", neg ? "INV_NEST=TRUE;" : "",
+                             (unsigned long long)len, (unsigned long long)t_pos);
+                    snprintf(tail, sizeof tail, "%.*s@%llu@%llu@%c", (int)qname.n, qname.p, (unsigned long long)q_pos,
+                             (unsigned long long)(q_pos + len), sfx);
+                    rowb.n = 0;
+                    if (vcf_row(&rowb, tname, t_pos, ts.p + a, 1, qs.p + b, len + 1, 0, info, tail, dis, sizeof dis)) { stopped = 1; break; }
+                    buf_put(&body, rowb.p, rowb.n);
+                }
+                q_pos += len; after_m = 0;
+                break;
+            case 'D':
+                if (len > svlen_cutoff && after_m) {
+                    if (t_pos == t_st || q_pos == q_st) { set_err(err, errcap, "panic: attempt to subtract with overflow"); rc = ORC_E_PANIC; break; }
+                    const uint64_t a = t_pos - t_st - 1, b = q_pos - q_st - 1;
+                    if (len > ts.n || a + len + 1 > ts.n || b + 1 > qs.n) { set_err(err, errcap, "panic: byte index out of range"); rc = ORC_E_PANIC; break; }
+                    snprintf(info, sizeof info, "%sSVTYPE=DEL;SVLEN=%llu;END=%llu", neg ? "INV_NEST=TRUE;" : "",
+                             (unsigned long long)len, (unsigned long long)(t_pos + len));
+                    snprintf(tail, sizeof tail, "%.*s@%llu@%llu@%c", (int)qname.n, qname.p, (unsigned long long)q_pos,
+                             (unsigned long long)q_pos, sfx);
+                    rowb.n = 0;
+                    if (vcf_row(&rowb, tname, t_pos, ts.p + a, len + 1, qs.p + b, 1, 0, info, tail, dis, sizeof dis)) { stopped = 1; break; }
+                    buf_put(&body, rowb.p, rowb.n);
+                }
+                t_pos += len; after_m = 0;
+                break;
+            default: stopped = 1; break; /* CigarOpInvalid, discarded */
+            }
+        }
+    }
+    if (rc == ORC_OK) { /* caller.rs:294-299 */
+        vcf_header(out, sample ? sample : "sample");
+        buf_put(out, body.p, body.n);
+    }
+    free(row.f); free(row.scratch); free(tf.e); free(qf.e);
+    orc_buf_free(&ts); orc_buf_free(&qs); orc_buf_free(&body); orc_buf_free(&conv); orc_buf_free(&rowb);
+    return rc;
+}

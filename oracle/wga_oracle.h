@@ -95,6 +95,12 @@ int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_l
                 const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, const char *t_path,
                 const char *q_path, orc_buf *out, char *err, size_t errcap);
 
+/* src/tools/caller.rs:268-302,610-822 call_var_paf (`call -f paf`): PAF + 2 FASTA -> VCF.  Any error leaves out empty
+ * (the reference buffers every row and writes the header last). */
+int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_len, const char *t_fai, size_t t_fai_len,
+                 const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, int snp, uint64_t svlen_cutoff,
+                 const char *sample, orc_buf *out, char *err, size_t errcap);
+
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */
 void orc_fmt_f32(float v, char *dst /* >= 32 bytes */);      /* ryu 1.0.14 Buffer::format(f32) */

@@ -56,6 +56,8 @@ def lib():
                                       ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_paf2maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 5 + [ctypes.c_char_p, ctypes.c_char_p,
                                                                              ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_call_paf.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 5 + [ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p,
+                                                                              ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -121,6 +123,11 @@ def call_maf(text: bytes, snp=False, inv=False, svlen=50, sample="sample", query
 def paf2maf(paf: bytes, t_fa: bytes, t_fai: bytes, q_fa: bytes, q_fai: bytes, t_path="t.fa", q_path="q.fa") -> bytes:
     return _run(lib().orc_paf2maf, paf, len(paf), t_fa, len(t_fa), t_fai, len(t_fai), q_fa, len(q_fa), q_fai, len(q_fai),
                 _opt(t_path), _opt(q_path))
+
+
+def call_paf(paf: bytes, t_fa: bytes, t_fai: bytes, q_fa: bytes, q_fai: bytes, snp=False, svlen=50, sample="sample") -> bytes:
+    return _run(lib().orc_call_paf, paf, len(paf), t_fa, len(t_fa), t_fai, len(t_fai), q_fa, len(q_fa), q_fai, len(q_fai),
+                int(snp), int(svlen), _opt(sample))
 
 
 def make_fai(fa: bytes) -> bytes:

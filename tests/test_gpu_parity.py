@@ -624,3 +624,56 @@ def test_paf2maf_edges_and_errors(w, ctx):
         assert eo.value.code == code == eg.value.code, (paf, eo.value.code, eg.value.code, eo.value.msg)
         if code in (1, 5, 6, 10):
             assert str(eg.value) == eo.value.msg, paf
+
+
+# ---------------------------------------------------------------- call -f paf (row a15)
+def cpaf(w, ctx, paf, t_fa, t_fai, q_fa, q_fai, snp=False, svlen=50, sample=None):
+    out = io.BytesIO()
+    w.call_var_paf(w.PAFReader(paf), "t.fa", "q.fa", out, snp, svlen, False, sample, ctx=ctx,
+                   target=w.Fasta(ctx, t_fa, t_fai), query=w.Fasta(ctx, q_fa, q_fai))
+    return out.getvalue()
+
+
+def test_call_paf_parity(w, ctx):
+    rng = random.Random(77)
+    for it in range(6):
+        case = make_paf2maf_case(rng, n_rec=80, width_t=rng.choice([50, 60, 80]), width_q=rng.choice([60, 61, 100]), soft=it % 2 == 0)
+        for snp, svlen in ((True, 0), (False, 0), (True, 5), (False, 50)):
+            want = orc.call_paf(*case, snp=snp, svlen=svlen, sample="s1")
+            got = cpaf(w, ctx, *case, snp=snp, svlen=svlen, sample="s1")
+            assert got == want, (it, snp, svlen)
+            if snp and svlen == 0:
+                assert want.count(b"\n") > 200
+
+
+def test_call_paf_edges_and_errors(w, ctx):
+    t_fa = b">chrT\nACGTACGTACGGGGCCCCAATTTT\n>rT\nRCGTACGTAC\n"
+    q_fa = b">chrQ\nACGTACGTACGGCCCCAATTTTAA\n>yQ\nACGTAYGTACGG\n"
+    ti, qi = orc.make_fai(t_fa), orc.make_fai(q_fa)
+
+    def line(cg, strand=b"+", q=b"chrQ", t=b"chrT", qs=1, qe=13, ts=2, te=14, tag=True):
+        return b"\t".join([q, b"24", b"%d" % qs, b"%d" % qe, strand, t, b"24", b"%d" % ts, b"%d" % te, b"9", b"14", b"60"] +
+                          ([b"cg:Z:" + cg] if tag else [])) + b"\n"
+    ok = [line(b"4=1X2I3=2D2="), line(b"4=1X2I3=2D2=", b"-"), line(b"2I4=2D3I2="), line(b"4=1X3S2I3=") + line(b"4=1X"),
+          line(b"4=1X2II3=") + line(b"2=2X", b"-"), line(b"4=X2=") + line(b"3=1X"), line(b"3=99999999999999999999X") + line(b"3=1X"),
+          line(b"2=3X3=", q=b"yQ", qs=2, qe=10),           # ALT 'Y' ends the record after one SNP row
+          line(b"2=3X3=", b"-", q=b"yQ", qs=2, qe=10) + line(b"1=2X"),
+          line(b"2X3D", t=b"rT", ts=1, te=8), b"#c\n\n" + line(b"12M"), line(b"11=1X"), line(b"12=1X"),   # the inclusive extra base
+          line(b"8=4D", ts=10, te=22) + line(b"8=5I", qs=10, qe=23), line(b"0M5X")]
+    for paf in ok:
+        for snp, svlen in ((True, 0), (False, 0), (True, 1), (False, 2)):
+            assert cpaf(w, ctx, paf, t_fa, ti, q_fa, qi, snp, svlen) == orc.call_paf(paf, t_fa, ti, q_fa, qi, snp=snp, svlen=svlen), (paf, snp, svlen)
+    bad = [(line(b"4=1X") + line(b"4=20D"), 8), (line(b"12=3X"), 8), (line(b"0=2I"), 8), (line(b"0=2D"), 8), (line(b""), 8),
+           (line(b"5=", tag=False), 6), (line(b"5=", b"-", t=b"rT", ts=0, te=5, tag=False), 10), (line(b"5=", b"-", t=b"rT", ts=0, te=5), 10),
+           (line(b"5=", t=b"nope"), 11), (line(b"5=", q=b"nope"), 11), (b"a\tb\n", 9), (line(b"5=", b"-", ts=30, te=40), 8),
+           (line(b"8=6D", ts=10, te=22), 8), (line(b"4=") + line(b"13=1X") + line(b"", tag=False), 8)]
+    for paf, code in bad:
+        with pytest.raises(orc.OracleError) as eo:
+            orc.call_paf(paf, t_fa, ti, q_fa, qi, snp=True, svlen=0)
+        with pytest.raises(w.WGAError) as eg:
+            cpaf(w, ctx, paf, t_fa, ti, q_fa, qi, True, 0)
+        assert eo.value.code == code == eg.value.code, (paf, eo.value.code, eg.value.code, eo.value.msg)
+        if code in (6, 10):
+            assert str(eg.value) == eo.value.msg, paf
+    # errors that only exist with --snp do not fire without it
+    assert cpaf(w, ctx, line(b"12=3X"), t_fa, ti, q_fa, qi, False, 0) == orc.call_paf(line(b"12=3X"), t_fa, ti, q_fa, qi, snp=False, svlen=0)

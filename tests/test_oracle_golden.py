@@ -208,3 +208,36 @@ def test_chunk_grid_inv_rows(t, C, K, data):
     grid = pyspec.chunk_grid(t, q, C, K)
     want = sum(1 for (s, e) in grid if any(ch != "-" for ch in t[s:e]))
     assert sum("<INV>" in r for r in rows) == want
+
+
+def test_call_paf_hand_derived():
+    """caller.rs:610-822 on a hand-walked record (inclusive faidx end, no revcomp, ungated <INV>, Q12/Q13/Q15)"""
+    t_fa = b">chrT\nACGTACGTACGGGGCCCCAATTTT\n"
+    q_fa = b">chrQ\nACGTACGTACGGCCCCAATTTTAA\n"
+    ti, qi = orc.make_fai(t_fa), orc.make_fai(q_fa)
+
+    def line(cg, strand=b"+"):
+        return b"\t".join([b"chrQ", b"24", b"1", b"13", strand, b"chrT", b"24", b"2", b"14", b"9", b"14", b"60", b"cg:Z:" + cg]) + b"\n"
+    hdr = orc.call_maf(b"##maf version=1\n", snp=True, svlen=0)  # header only
+    got = orc.call_paf(line(b"4=1X2I3=2D2="), t_fa, ti, q_fa, qi, snp=True, svlen=0)
+    assert got == hdr + (
+        b"chrT\t7\t.\tG\tC\t.\t.\t.\tGT:QI\t1|1:chrQ@5@P\n"
+        b"chrT\t7\t.\tG\tCGT\t.\t.\tSVTYPE=INS;SVLEN=2;END=7\tGT:QI\t1|1:chrQ@6@8@P\n"
+        b"chrT\t10\t.\tCGG\tG\t.\t.\tSVTYPE=DEL;SVLEN=2;END=12\tGT:QI\t1|1:chrQ@11@11@P\n")
+    got = orc.call_paf(line(b"4=1X2I3=2D2=", b"-"), t_fa, ti, q_fa, qi, snp=False, svlen=1)
+    assert got == hdr + (
+        b"chrT\t3\t.\tG\t<INV>\t.\t.\tSVTYPE=INV;END=14\tGT:QI\t1|1:chrQ@1@13@N\n"
+        b"chrT\t7\t.\tG\tCGT\t.\t.\tINV_NEST=TRUE;SVTYPE=INS;SVLEN=2;END=7\tGT:QI\t1|1:chrQ@6@8@N\n"
+        b"chrT\t10\t.\tCGG\tG\t.\t.\tINV_NEST=TRUE;SVTYPE=DEL;SVLEN=2;END=12\tGT:QI\t1|1:chrQ@11@11@N\n")
+    # svlen cutoff is strict (>), leading indel has no anchor (after_m false), I right after D is skipped too
+    assert orc.call_paf(line(b"4=1X2I3=2D2="), t_fa, ti, q_fa, qi, snp=False, svlen=2) == hdr
+    assert orc.call_paf(line(b"2I4=2D3I2="), t_fa, ti, q_fa, qi, snp=False, svlen=0) == hdr + (
+        b"chrT\t6\t.\tCGT\tG\t.\t.\tSVTYPE=DEL;SVLEN=2;END=8\tGT:QI\t1|1:chrQ@7@7@P\n")
+    # a failing token silently ends the record (rows before it are kept); the next record is still processed
+    two = line(b"4=1X3S2I3=") + line(b"4=1X")
+    assert orc.call_paf(two, t_fa, ti, q_fa, qi, snp=True, svlen=0) == hdr + 2 * b"chrT\t7\t.\tG\tC\t.\t.\t.\tGT:QI\t1|1:chrQ@5@P\n"
+    # slices past the fetched strings are panics; nothing is written
+    for cg in (b"4=20D", b"12=3X", b"0=2I"):
+        with pytest.raises(orc.OracleError) as e:
+            orc.call_paf(line(b"4=1X") + line(cg), t_fa, ti, q_fa, qi, snp=True, svlen=0)
+        assert e.value.code == 8

@@ -355,10 +355,26 @@ def paf2maf(pafreader: PAFReader, writer, t_fa_path, q_fa_path, ctx=None, target
         writer.write(ctypes.string_at(sp.data, sp.len))
 
 
+def call_var_paf(pafreader: PAFReader, t_fa_path, q_fa_path, writer, if_snp=False, svlen_cutoff=50, _between=False,
+                 sample=None, ctx=None, target=None, query=None):
+    """src/tools/caller.rs:268-302.  Nothing is written when the call fails (the reference writes the header after
+    all records were processed).  target/query: preloaded Fasta objects (else loaded from the two paths)."""
+    ctx = ctx or default_context()
+    target = target or Fasta.from_path(ctx, t_fa_path)
+    query = query or Fasta.from_path(ctx, q_fa_path)
+    keep, base = _host_ptr(pafreader.data)
+    sp = Span()
+    ctx._check(ctx.L.wga_paf_call(ctx.h, ctypes.c_void_p(base), len(pafreader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, target.h,
+                                  query.h, int(bool(if_snp)), int(svlen_cutoff), ctypes.byref(sp)))
+    body = ctypes.string_at(sp.data, sp.len) if sp.len else b""
+    writer.write(ctx.vcf_header(sample or "sample"))
+    writer.write(body)
+
+
 def run_bytes(fn, *args, **kw) -> bytes:
     """convenience: run one of the functions above into a bytes object (the writer argument is inserted
-    where the reference signature has it: 2nd for maf2paf/stat_*, 3rd for call_var_maf)"""
+    where the reference signature has it: 2nd for maf2paf/stat_*, 3rd for call_var_maf, 4th for call_var_paf)"""
     w = io.BytesIO()
-    pos = 2 if fn is call_var_maf else 1
+    pos = 2 if fn is call_var_maf else 3 if fn is call_var_paf else 1
     fn(*args[:pos], w, *args[pos:], **kw)
     return w.getvalue()

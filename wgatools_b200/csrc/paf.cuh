@@ -114,7 +114,7 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
         paf_report(err_key, r, 0x800000, have_cs ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
         cg_len = 0;
         cg_off = 0;
-        R.neg[r] = 2;  // marks "no cigar"
+        R.neg[r] = neg | 2;  // bit 1 marks "no cigar" (bit 0 stays the strand)
     }
     R.cig_off[r] = cg_off;
     R.cig_len[r] = cg_len;
@@ -130,7 +130,7 @@ __global__ void k_paf_cigar_counts(uint64_t n_rec, const uint8_t *__restrict__ t
     const uint8_t negf = R.neg[r];
     const uint64_t len = R.cig_len[r];
     const uint8_t *p = text + R.cig_off[r];
-    if (negf == 2) { for (int i = 0; i < 11; ++i) o[i] = 0; return; }
+    if (negf & 2) { for (int i = 0; i < 11; ++i) o[i] = 0; return; }
     if (len == 0) {  // fold_many1 on "" -> nom error -> e.input[..10] panics (errors.rs:88-97)
         paf_report(err_key, r, 0x800001, WGA_E_REF_PANIC);
         for (int i = 0; i < 11; ++i) o[i] = 0;

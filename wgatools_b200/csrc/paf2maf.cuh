@@ -85,8 +85,9 @@ struct P2mRecs {  // per PAF record
 };
 
 // extra typed columns + FASTA spans (converter.rs:196-225)
+// end_adj: 1 = paf2maf / pafpseudo fetch [start, end-1]; 0 = `call -f paf` fetches [start, end] (paf.rs:221-237, Q13)
 __global__ void k_p2m_spans(LineView lv, const uint8_t *__restrict__ flags, const uint32_t *__restrict__ rec_scan, PafRecs R,
-                            P2mRecs X, FaView T, FaView Q, unsigned long long *err_key) {
+                            P2mRecs X, FaView T, FaView Q, uint64_t end_adj, unsigned long long *err_key) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= lv.n_lines || !flags[k]) return;
     const uint64_t r = rec_scan[k];
@@ -111,10 +112,10 @@ __global__ void k_p2m_spans(LineView lv, const uint8_t *__restrict__ flags, cons
     const uint64_t qi = ti == ~0ull ? ~0ull : fa_find(Q, lv.text + R.q_name_off[r], R.q_name_len[r]);
     if (ti == ~0ull || qi == ~0ull) { paf_report(err_key, r, 1, WGA_E_NOM); return; }  // faidx: sequence not found
     uint64_t first, count;
-    fa_clip(T.meta[ti * kFaMeta + 4], R.t_start[r], v8 - 1, &first, &count);
+    fa_clip(T.meta[ti * kFaMeta + 4], R.t_start[r], v8 - end_adj, &first, &count);
     X.t_src[r] = T.meta[ti * kFaMeta + 3] + first;
     X.LT[r] = count;
-    fa_clip(Q.meta[qi * kFaMeta + 4], R.q_start[r], v3 - 1, &first, &count);
+    fa_clip(Q.meta[qi * kFaMeta + 4], R.q_start[r], v3 - end_adj, &first, &count);
     X.q_src[r] = Q.meta[qi * kFaMeta + 3] + first;
     X.LQ[r] = count;
 }
@@ -123,7 +124,7 @@ __global__ void k_p2m_spans(LineView lv, const uint8_t *__restrict__ flags, cons
 __global__ void k_p2m_revcomp_check(uint64_t n_rec, PafRecs R, P2mRecs X, const uint8_t *__restrict__ qseq,
                                     unsigned long long *err_key) {
     const uint64_t r = blockIdx.x;
-    if (r >= n_rec || R.neg[r] != 1) return;
+    if (r >= n_rec || !(R.neg[r] & 1)) return;
     const uint8_t *p = qseq + X.q_src[r];
     const uint64_t n = X.LQ[r];
     for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -144,10 +145,10 @@ __global__ void k_p2m_ops(uint64_t n_rec, const uint8_t *__restrict__ text, PafR
     if (r == n_rec) { if (PASS == 0) n_ops[r] = 0; return; }
     const uint64_t len = R.cig_len[r];
     const uint8_t *p = text + R.cig_off[r];
-    if (R.neg[r] == 2 || len == 0) {
+    if ((R.neg[r] & 2) || len == 0) {
         if (PASS == 0) {
             n_ops[r] = 0;
-            if (R.neg[r] != 2 && len == 0) paf_report(err_key, r, 0x800001, WGA_E_REF_PANIC);  // fold_many1 on "" (errors.rs:88-97)
+            if (!(R.neg[r] & 2) && len == 0) paf_report(err_key, r, 0x800001, WGA_E_REF_PANIC);  // fold_many1 on "" (errors.rs:88-97)
         }
         return;
     }

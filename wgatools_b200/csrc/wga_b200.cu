@@ -14,6 +14,7 @@
 #ifdef WGA_WITH_PAF
 #include "paf.cuh"
 #include "paf2maf.cuh"
+#include "call_paf.cuh"
 #endif
 
 using namespace wga;
@@ -1178,15 +1179,16 @@ int wga_paf2maf_header(wga_ctx *ctx, const char *t_fa_path, const char *q_fa_pat
     return WGA_OK;
 }
 
-int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
-                wga_span *out) {
-    (void)flags;
-    if (!ctx || !out || !TF || !QF || (!text && len)) return WGA_E_INVALID_ARG;
-    cudaSetDevice(ctx->device);
-    out->data = nullptr;
-    out->len = 0;
-    walk_begin(ctx);
-    WGA_TRY(stage_text(ctx, text, len, mem));
+// PAF text -> typed records + FASTA spans (shared by paf2maf and call -f paf)
+struct PafPrep {
+    LineView lv;
+    PafRecs R;
+    P2mRecs X;
+    uint64_t n_rec = 0;
+    unsigned long long *err_key = nullptr;
+    uint64_t *n_ops = nullptr, *op_base = nullptr;
+};
+static int paf_fasta_prepare(wga_ctx *ctx, uint64_t len, const wga_fasta *TF, const wga_fasta *QF, uint64_t end_adj, PafPrep *PP) {
     ctx->n_rec = 0;
     if (len == 0) return WGA_OK;
     const uint8_t *d_text = ctx->d_text;
@@ -1228,7 +1230,29 @@ int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     X.LT = x7 + 5 * n_rec; X.LQ = x7 + 6 * n_rec; X.n_ops = n_ops;
     FaView T{TF->d_seq, TF->d_names, TF->d_meta, TF->n_seq}, Q{QF->d_seq, QF->d_names, QF->d_meta, QF->n_seq};
     LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key);
-    LAUNCH(ctx, k_p2m_spans, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, X, T, Q, err_key);
+    LAUNCH(ctx, k_p2m_spans, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, X, T, Q, end_adj, err_key);
+    PP->lv = lv; PP->R = R; PP->X = X; PP->n_rec = n_rec; PP->err_key = err_key; PP->n_ops = n_ops; PP->op_base = op_base;
+    return WGA_OK;
+}
+
+int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
+                wga_span *out) {
+    (void)flags;
+    if (!ctx || !out || !TF || !QF || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    PafPrep PP;
+    WGA_TRY(paf_fasta_prepare(ctx, len, TF, QF, 1, &PP));
+    const uint64_t n_rec = PP.n_rec;
+    if (n_rec == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    PafRecs R = PP.R;
+    P2mRecs X = PP.X;
+    unsigned long long *err_key = PP.err_key;
+    uint64_t *n_ops = PP.n_ops, *op_base = PP.op_base;
     LAUNCH(ctx, k_p2m_revcomp_check, (unsigned)n_rec, 128, n_rec, R, X, QF->d_seq, err_key);
     LAUNCH(ctx, k_p2m_ops<0>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
            (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key);
@@ -1305,6 +1329,98 @@ int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     ctx->walk_ms = ms; ctx->walk_launches = 1; ctx->walk_bytes = total;  // expansion kernel: output-bound
     return WGA_OK;
 }
+
+// ---------------------------------------------------------------- call -f paf (caller.rs:268-302,610-822)
+int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
+                 int snp, uint64_t svlen_cutoff, wga_span *out) {
+    if (!ctx || !out || !TF || !QF || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    PafPrep PP;
+    WGA_TRY(paf_fasta_prepare(ctx, len, TF, QF, 0, &PP));
+    const uint64_t n_rec = PP.n_rec;
+    if (n_rec == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    PafRecs R = PP.R;
+    P2mRecs X = PP.X;
+    unsigned long long *err_key = PP.err_key;
+    uint64_t *n_ops = PP.n_ops, *op_base = PP.op_base;
+    LAUNCH(ctx, k_cp_ops<0>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+           (uint8_t *)nullptr, (uint32_t *)nullptr, err_key);
+    WGA_TRY(exclusive_sum(ctx, n_ops, op_base, n_rec + 1));
+    uint64_t sc[2];
+    WGA_TRY(read_scalars(ctx, {op_base + n_rec, err_key}, sc));
+    const uint64_t n_opsT = sc[0];
+    uint64_t key = sc[1];
+    uint64_t total = 0, n_rows = 0;
+    uint64_t *row_len = nullptr, *row_off = nullptr;
+    uint32_t *rec_bad = nullptr;
+    CpView V;
+    if (key == kNoErr && n_opsT) {
+        uint64_t *op_len = ctx->buf<uint64_t>(B_RUN_POS, n_opsT + 1), *tcon = ctx->buf<uint64_t>(B_GEN_C, n_opsT + 1);
+        uint64_t *qcon = ctx->buf<uint64_t>(B_GEN_D, n_opsT + 1), *rows = ctx->buf<uint64_t>(B_GEN_E, n_opsT + 1);
+        uint64_t *St = ctx->buf<uint64_t>(B_GEN_F, n_opsT + 1), *Sq = ctx->buf<uint64_t>(B_GEN_G, n_opsT + 1);
+        uint64_t *rowbase = ctx->buf<uint64_t>(B_GEN_H, n_opsT + 1);
+        uint8_t *op_type = ctx->buf<uint8_t>(B_RUN_CLS, n_opsT + 1);
+        uint32_t *op_rec = ctx->buf<uint32_t>(B_RUN_REC, n_opsT + 1);
+        rec_bad = ctx->buf<uint32_t>(B_ROW_FIXED, 2 * n_rec);
+        if (!op_len || !tcon || !qcon || !rows || !St || !Sq || !rowbase || !op_type || !op_rec || !rec_bad) return ctx->err_code;
+        uint32_t *rec_panic = rec_bad + n_rec;
+        WGA_CK(cudaMemsetAsync(rec_bad, 0xFF, 2 * n_rec * sizeof(uint32_t), ctx->stream));
+        LAUNCH(ctx, k_cp_ops<1>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)op_base, op_len, op_type,
+               op_rec, err_key);
+        LAUNCH(ctx, k_cp_contrib, grid_for(n_opsT + 1, 256), 256, n_opsT, op_len, op_type, op_rec, op_base, svlen_cutoff, snp, tcon,
+               qcon, rows);
+        WGA_TRY(exclusive_sum(ctx, tcon, St, n_opsT + 1));
+        WGA_TRY(exclusive_sum(ctx, qcon, Sq, n_opsT + 1));
+        WGA_TRY(exclusive_sum(ctx, rows, rowbase, n_opsT + 1));
+        WGA_TRY(read_scalars(ctx, {rowbase + n_opsT}, &n_rows));
+        V.n_rec = n_rec; V.n_ops = n_opsT; V.text = d_text; V.R = R; V.X = X; V.op_base = op_base; V.op_len = op_len;
+        V.op_type = op_type; V.op_rec = op_rec; V.St = St; V.Sq = Sq; V.rowbase = rowbase; V.tseq = TF->d_seq; V.qseq = QF->d_seq;
+        V.svlen = svlen_cutoff; V.snp = snp;
+        if (n_rows) {
+            row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rows + 1);
+            row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rows + 1);
+            if (!row_len || !row_off) return ctx->err_code;
+            LAUNCH(ctx, k_cp_rows<0>, grid_for(n_rows + 1, 128), 128, V, n_rows, row_len, (const uint64_t *)nullptr, rec_bad, rec_panic,
+                   (char *)nullptr, err_key);
+            LAUNCH(ctx, k_cp_resolve, grid_for(n_rows, 256), 256, V, n_rows, row_len, (const uint32_t *)rec_bad,
+                   (const uint32_t *)rec_panic, err_key);
+            WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rows + 1));
+            WGA_TRY(read_scalars(ctx, {row_off + n_rows, err_key}, sc));
+            total = sc[0];
+            key = sc[1];
+        }
+    }
+    if (key != kNoErr) {
+        const int code = (int)(key & 0xFF);
+        const uint64_t rec = key >> 32, pos = (key >> 8) & 0xFFFFFF;
+        std::string msg;
+        if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+        else if (code == WGA_E_NOM) msg = "HTS library error by sequence of record " + std::to_string(rec) + " not found in the FASTA index";
+        else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+        else if (code == WGA_E_VCF_BASE) {
+            uint64_t ts;
+            WGA_TRY(read_scalars(ctx, {X.t_src + rec}, &ts));
+            char c = '?';
+            WGA_CK(cudaMemcpy(&c, TF->d_seq + ts, 1, cudaMemcpyDeviceToHost));
+            msg = std::string("invalid VCF base `") + c + "`";
+        } else msg = pos == 0x800001 ? "the reference panics on this record (empty CIGAR)"
+                                     : "the reference panics on this record (slice past the fetched sequence)";
+        ctx->set_error(code, rec, msg);
+        return code;
+    }
+    if (total == 0) return sync_check(ctx);
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    LAUNCH(ctx, k_cp_rows<1>, grid_for(n_rows, 128), 128, V, n_rows, row_len, (const uint64_t *)row_off, rec_bad, rec_bad + n_rec, d_out,
+           err_key);
+    return finish_output(ctx, d_out, total, mem, flags, out);
+}
 #endif
 
 #ifndef WGA_WITH_PAF
@@ -1316,6 +1432,9 @@ int wga_fasta_load(wga_ctx *, const void *, uint64_t, const void *, uint64_t, wg
 void wga_fasta_free(wga_fasta *) {}
 int wga_paf2maf_header(wga_ctx *, const char *, const char *, wga_span *) { return WGA_E_UNSUPPORTED; }
 int wga_paf2maf(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const wga_fasta *, wga_span *) { return WGA_E_UNSUPPORTED; }
+int wga_paf_call(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const wga_fasta *, int, uint64_t, wga_span *) {
+    return WGA_E_UNSUPPORTED;
+}
 #endif
 #ifndef WGA_WITH_CALL
 int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
