@@ -72,6 +72,16 @@ __global__ void k_cp_ops(uint64_t n_rec, const uint8_t *__restrict__ text, PafRe
     if (PASS == 0) n_ops[r] = cnt;
 }
 
+// the <INV> row is built before the CIGAR is even looked up (caller.rs:641-660): its failures are real errors and precede
+// CigarTagNotFound / the tokenizer's
+__global__ void k_cp_inv_check(uint64_t n_rec, PafRecs R, P2mRecs X, const uint8_t *__restrict__ tseq, unsigned long long *err_key) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec || !(R.neg[r] & 1)) return;
+    char c;
+    if (X.LT[r] < 1) paf_report(err_key, r, 2, WGA_E_REF_PANIC);  // &t_seq_string[0..1] on ""
+    else if (!vcf_base(tseq[X.t_src[r]], &c)) paf_report(err_key, r, 2, WGA_E_VCF_BASE);
+}
+
 struct CpView {
     uint64_t n_rec, n_ops;
     const uint8_t *text;

@@ -1348,6 +1348,7 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     P2mRecs X = PP.X;
     unsigned long long *err_key = PP.err_key;
     uint64_t *n_ops = PP.n_ops, *op_base = PP.op_base;
+    LAUNCH(ctx, k_cp_inv_check, grid_for(n_rec, 256), 256, n_rec, R, X, (const uint8_t *)TF->d_seq, err_key);
     LAUNCH(ctx, k_cp_ops<0>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
            (uint8_t *)nullptr, (uint32_t *)nullptr, err_key);
     WGA_TRY(exclusive_sum(ctx, n_ops, op_base, n_rec + 1));
