@@ -1624,3 +1624,182 @@ int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_
     orc_buf_free(&ts); orc_buf_free(&qs); orc_buf_free(&body); orc_buf_free(&conv); orc_buf_free(&rowb);
     return rc;
 }
+
+/* ---------------------------------------------------------------- pafpseudo */
+/* src/tools/pseudomaf.rs:18-237 generate_pesudo_maf / write_pmaf / get_sline_seq and
+ * src/parser/cigar.rs:744-804 gen_pesudo_maf_by_cigar.
+ * Iteration order of the two HashMaps (targets; queries inside a target) is nondeterministic in the reference; here
+ * it is FIRST-OCCURRENCE order (the same convention as the stat rows).  Records with equal target_start
+ * inside one (target, query) group are placed by slice::binary_search_by's tie behaviour (pseudomaf.rs:91-94); this
+ * restates the classic three-way loop of std (1.52-1.8x) -- parity unpinned, and the CUDA path refuses such inputs.
+ * out = the files' bytes concatenated in target order; index = one line "{target}\t{bytes}\n" per file
+ * ({out_dir}/{target}.maf).  On error nothing is returned (the reference may leave other targets' files behind). */
+typedef struct {
+    sv qname, tname, cg;
+    uint64_t q_size, q_st, q_en, t_size, t_st, t_en;
+    int neg, have_cg;
+} pprec;
+
+static int pp_project(const pprec *r, orc_buf *q, int base, char *err, size_t errcap) {
+    /* cigar.rs:744-804 */
+    if (!r->have_cg) { set_err(err, errcap, "CIGAR start tag not found"); return ORC_E_CIGAR_TAG_NOT_FOUND; }
+    sv cg = r->cg;
+    if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); return ORC_E_PANIC; }
+    uint64_t off = 0;
+    size_t i = 0;
+    while (i < cg.n) {
+        size_t d0 = i;
+        while (i < cg.n && cg.p[i] >= '0' && cg.p[i] <= '9') i++;
+        size_t o0 = i;
+        while (i < cg.n && !(cg.p[i] >= '0' && cg.p[i] <= '9')) i++;
+        sv digits = {cg.p + d0, o0 - d0}, op = {cg.p + o0, i - o0};
+        uint64_t len;
+        if (op.n != 1) { set_err(err, errcap, "CIGAR OP `%.*s` invalid", (int)op.n, op.p); return ORC_E_CIGAR_OP_INVALID; }
+        if (!parse_u64(digits, &len)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)digits.n, digits.p); return ORC_E_PARSE_INT; }
+        switch (op.p[0]) {
+        case 'M': case '=':
+            if (base) off += len; else { buf_reserve(q, len); memset(q->p + q->n, '1', len); q->n += len; }
+            break;
+        case 'X':
+            if (base) off += len; else { buf_reserve(q, len); memset(q->p + q->n, '0', len); q->n += len; }
+            break;
+        case 'I': case 'S':
+            if (base) { /* String::drain(off..off+len) */
+                if (len > q->n || off > q->n - len) { set_err(err, errcap, "panic: drain range out of bounds"); return ORC_E_PANIC; }
+                memmove(q->p + off, q->p + off + len, q->n - off - len);
+                q->n -= len;
+            }
+            break;
+        case 'D':
+            if (base) {
+                if (buf_insert_gaps(q, off, len)) { set_err(err, errcap, "panic: insert_str index out of range"); return ORC_E_PANIC; }
+                off += len;
+            } else { buf_reserve(q, len); memset(q->p + q->n, '-', len); q->n += len; }
+            break;
+        default: break; /* other ops are ignored (cigar.rs:797) */
+        }
+    }
+    return ORC_OK;
+}
+
+int orc_paf_pseudo(const char *paf, size_t paf_len, const char *fa, size_t fa_len, const char *fai, size_t fai_len,
+                   const char *target, orc_buf *out, orc_buf *index, char *err, size_t errcap) {
+    const int base = fa != NULL;
+    faidx fx = {0};
+    if (base && fai_parse(fai, fai_len, fa, fa_len, &fx)) { set_err(err, errcap, "HTS library error by bad .fai"); return ORC_E_CSV; }
+    size_t pos = 0;
+    pafrow row = {0};
+    pprec *recs = NULL;
+    size_t n = 0, cap = 0;
+    int rc = ORC_OK;
+    /* pseudomaf.rs:24-43: read everything (csv errors first) */
+    while (paf_next(paf, paf_len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int neg = 0, bad = row.n < 12;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) { if (sv_eq_c(row.f[4], "+")) neg = 0; else if (sv_eq_c(row.f[4], "-")) neg = 1; else bad = 1; continue; }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+        if (target && !sv_eq_c(row.f[5], target)) continue;
+        if (n == cap) { cap = cap ? cap * 2 : 256; recs = (pprec *)realloc(recs, cap * sizeof(pprec)); }
+        pprec *r = &recs[n++];
+        r->qname = row.f[0]; r->tname = row.f[5];
+        r->q_size = u[1]; r->q_st = u[2]; r->q_en = u[3]; r->t_size = u[6]; r->t_st = u[7]; r->t_en = u[8];
+        r->neg = neg; r->have_cg = 0; r->cg.p = NULL; r->cg.n = 0;
+        for (size_t k = 12; k < row.n && !r->have_cg; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { r->cg.p = row.f[k].p + 5; r->cg.n = row.f[k].n - 5; r->have_cg = 1; }
+        /* cs:Z: conversion is not restated for this command (the CUDA path reports it as unsupported) */
+    }
+    uint8_t *done = (uint8_t *)calloc(n ? n : 1, 1);
+    size_t *grp = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
+    orc_buf q = {0};
+    for (size_t a = 0; a < n && rc == ORC_OK; a++) { /* targets in first-occurrence order */
+        if (done[a] & 1) continue;
+        const sv tname = recs[a].tname;
+        const size_t file_start = out->n;
+        buf_puts(out, "a score=0\n");
+        int first_flag = 1;
+        uint64_t target_size = 0;
+        for (size_t b = a; b < n && rc == ORC_OK; b++) { /* queries of this target in first-occurrence order */
+            if ((done[b] & 1) || !sv_eq(recs[b].tname, tname)) continue;
+            const sv qname = recs[b].qname;
+            size_t m = 0;
+            for (size_t c = b; c < n; c++) {
+                if ((done[c] & 1) || !sv_eq(recs[c].tname, tname) || !sv_eq(recs[c].qname, qname)) continue;
+                done[c] |= 1;
+                /* pseudomaf.rs:91-94 binary_search_by(target_start) + insert */
+                size_t size = m, left = 0, right = m, idx;
+                int found = 0;
+                while (left < right) {
+                    size_t mid = left + size / 2;
+                    uint64_t pv = recs[grp[mid]].t_st, kv = recs[c].t_st;
+                    if (pv < kv) left = mid + 1; else if (pv > kv) right = mid; else { idx = mid; found = 1; break; }
+                    size = right - left;
+                }
+                if (!found) idx = left;
+                memmove(grp + idx + 1, grp + idx, (m - idx) * sizeof(size_t));
+                grp[idx] = c;
+                m++;
+            }
+            int first_query_flag = 1;
+            uint64_t last_target_end = 0;
+            for (size_t k = 0; k < m && rc == ORC_OK; k++) {
+                const pprec *r = &recs[grp[k]];
+                target_size = r->t_size;
+                if (first_flag) { /* pseudomaf.rs:121-132 */
+                    buf_puts(out, "s\t"); buf_put(out, tname.p, tname.n); buf_puts(out, "\t0\t"); buf_putu(out, target_size);
+                    buf_puts(out, "\t+\t"); buf_putu(out, target_size); buf_putc(out, '\t');
+                    if (base) {
+                        if (target_size == 0) { set_err(err, errcap, "panic: attempt to subtract with overflow"); rc = ORC_E_PANIC; break; }
+                        if (fai_fetch(&fx, tname, 0, target_size - 1, out)) { set_err(err, errcap, "HTS library error by sequence not found"); rc = ORC_E_NOM; break; }
+                    } else { buf_reserve(out, target_size); memset(out->p + out->n, 'N', target_size); out->n += target_size; }
+                    buf_putc(out, '\n');
+                    first_flag = 0;
+                }
+                if (first_query_flag) {
+                    buf_puts(out, "s\t"); buf_put(out, r->qname.p, r->qname.n); buf_puts(out, "\t0\t"); buf_putu(out, r->q_size);
+                    buf_puts(out, "\t+\t"); buf_putu(out, r->q_size); buf_putc(out, '\t');
+                }
+                uint64_t overlap = 0;
+                if (r->t_st > last_target_end) {
+                    uint64_t gap = r->t_st - last_target_end;
+                    buf_reserve(out, gap); memset(out->p + out->n, '-', gap); out->n += gap;
+                } else {
+                    if (last_target_end > r->t_en) continue; /* contained: skipped (first_query_flag stays) */
+                    overlap = last_target_end - r->t_st;
+                }
+                last_target_end = r->t_en;
+                q.n = 0;
+                if (base) { /* get_sline_seq: [q_start, q_end - 1] */
+                    if (r->q_en == 0) { set_err(err, errcap, "panic: attempt to subtract with overflow"); rc = ORC_E_PANIC; break; }
+                    if (fai_fetch(&fx, qname, r->q_st, r->q_en - 1, &q)) { set_err(err, errcap, "HTS library error by sequence not found"); rc = ORC_E_NOM; break; }
+                }
+                if (r->neg) {
+                    char c = revcomp_inplace(q.p, q.n);
+                    if (c) { set_err(err, errcap, "Invalid Base: `%c`", c); rc = ORC_E_VCF_BASE; break; }
+                }
+                rc = pp_project(r, &q, base, err, errcap);
+                if (rc) break;
+                if (overlap > 0) {
+                    if (overlap > q.n) { set_err(err, errcap, "panic: drain range out of bounds"); rc = ORC_E_PANIC; break; }
+                    buf_put(out, q.p + overlap, q.n - overlap);
+                } else buf_put(out, q.p, q.n);
+                first_query_flag = 0;
+            }
+            if (rc) break;
+            if (last_target_end > target_size) { set_err(err, errcap, "panic: attempt to subtract with overflow"); rc = ORC_E_PANIC; break; }
+            uint64_t tail = target_size - last_target_end;
+            buf_reserve(out, tail); memset(out->p + out->n, '-', tail); out->n += tail;
+            buf_putc(out, '\n');
+        }
+        if (rc) break;
+        buf_putc(out, '\n');
+        buf_put(index, tname.p, tname.n); buf_putc(index, '\t'); buf_putu(index, out->n - file_start); buf_putc(index, '\n');
+    }
+    if (rc) { out->n = 0; index->n = 0; }
+    free(done); free(grp); free(recs); free(row.f); free(row.scratch); free(fx.e);
+    orc_buf_free(&q);
+    return rc;
+}

@@ -101,6 +101,12 @@ int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_
                  const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, int snp, uint64_t svlen_cutoff,
                  const char *sample, orc_buf *out, char *err, size_t errcap);
 
+/* src/tools/pseudomaf.rs:18-237 + src/parser/cigar.rs:744-804 (`pafpseudo`).  fa/fai NULL = no FASTA ('N' target row,
+ * 1/0/- query rows); target NULL = all targets.  out = files concatenated in first-occurrence target order,
+ * index = "{target}\t{bytes}\n" per file. */
+int orc_paf_pseudo(const char *paf, size_t paf_len, const char *fa, size_t fa_len, const char *fai, size_t fai_len,
+                   const char *target, orc_buf *out, orc_buf *index, char *err, size_t errcap);
+
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */
 void orc_fmt_f32(float v, char *dst /* >= 32 bytes */);      /* ryu 1.0.14 Buffer::format(f32) */

@@ -58,6 +58,8 @@ def lib():
                                                                              ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_call_paf.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 5 + [ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p,
                                                                               ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_paf_pseudo.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 3 + [ctypes.c_char_p, ctypes.POINTER(OrcBuf),
+                                                                                ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -128,6 +130,23 @@ def paf2maf(paf: bytes, t_fa: bytes, t_fai: bytes, q_fa: bytes, q_fai: bytes, t_
 def call_paf(paf: bytes, t_fa: bytes, t_fai: bytes, q_fa: bytes, q_fai: bytes, snp=False, svlen=50, sample="sample") -> bytes:
     return _run(lib().orc_call_paf, paf, len(paf), t_fa, len(t_fa), t_fai, len(t_fai), q_fa, len(q_fa), q_fai, len(q_fai),
                 int(snp), int(svlen), _opt(sample))
+
+
+def paf_pseudo(paf: bytes, fa: bytes = None, fai: bytes = None, target=None) -> dict:
+    """{target name: bytes of {out_dir}/{target}.maf}, in first-occurrence order"""
+    out, index = OrcBuf(), OrcBuf()
+    err = ctypes.create_string_buffer(512)
+    rc = lib().orc_paf_pseudo(paf, len(paf), fa, len(fa) if fa is not None else 0, fai, len(fai) if fai is not None else 0,
+                              _opt(target), ctypes.byref(out), ctypes.byref(index), err, 512)
+    data, idx = _take(out), _take(index)
+    if rc != 0:
+        raise OracleError(rc, err.value.decode("utf-8", "replace"))
+    files, pos = {}, 0
+    for line in idx.splitlines():
+        name, n = line.rsplit(b"\t", 1)
+        files[name] = data[pos:pos + int(n)]
+        pos += int(n)
+    return files
 
 
 def make_fai(fa: bytes) -> bytes:

@@ -241,3 +241,38 @@ def test_call_paf_hand_derived():
         with pytest.raises(orc.OracleError) as e:
             orc.call_paf(line(b"4=1X") + line(cg), t_fa, ti, q_fa, qi, snp=True, svlen=0)
         assert e.value.code == 8
+
+
+def test_paf_pseudo_hand_derived():
+    """pseudomaf.rs:78-205 + cigar.rs:744-804 on hand-walked records: gap fill, head-overlap trim, contained record
+    skipped, '-' strand reverse-complemented, I deleted / D gap-inserted, and the FASTA-less 1/0/- spelling"""
+    fa = b">chrT\nACGTACGTACGGGGCCCCAATTTT\n>chrQ\nACGTACGTACGGCCCCAATTTTAA\n>q2\nTTTTGGGGCCCCAAAA\n"
+    fai = orc.make_fai(fa)
+
+    def line(cg, strand=b"+", q=b"chrQ", t=b"chrT", qs=1, qe=13, ts=2, te=14, qsz=24):
+        return b"\t".join([q, b"%d" % qsz, b"%d" % qs, b"%d" % qe, strand, t, b"24", b"%d" % ts, b"%d" % te, b"9", b"14", b"60",
+                           b"cg:Z:" + cg]) + b"\n"
+    paf = (line(b"4=1X2I3=2D2=") + line(b"4=", q=b"q2", qs=0, qe=4, ts=16, te=20, qsz=16) +
+           line(b"3=1D2=", b"-", q=b"q2", qs=4, qe=9, ts=4, te=10, qsz=16) +
+           line(b"6=", qs=14, qe=20, ts=10, te=16) + line(b"4=", qs=3, qe=7, ts=11, te=15))
+    got = orc.paf_pseudo(paf, fa, fai)
+    assert list(got) == [b"chrT"]
+    assert got[b"chrT"] == (b"a score=0\n"
+                            b"s\tchrT\t0\t24\t+\t24\tACGTACGTACGGGGCCCCAATTTT\n"
+                            b"s\tchrQ\t0\t24\t+\t24\t--CGTACACG--GCTT--------\n"
+                            b"s\tq2\t0\t16\t+\t16\t----GCC-CC------TTTT----\n\n")
+    assert orc.paf_pseudo(paf)[b"chrT"] == (b"a score=0\n"
+                                            b"s\tchrT\t0\t24\t+\t24\tNNNNNNNNNNNNNNNNNNNNNNNN\n"
+                                            b"s\tchrQ\t0\t24\t+\t24\t--11110111--1111--------\n"
+                                            b"s\tq2\t0\t16\t+\t16\t----111-11------1111----\n\n")
+    # --target filter, several targets in first-occurrence order, ops outside M=XIDS are ignored (Q4)
+    paf2 = line(b"2H4=2N", t=b"other", ts=0, te=4, qs=0, qe=4) + paf
+    assert list(orc.paf_pseudo(paf2)) == [b"other", b"chrT"]
+    assert orc.paf_pseudo(paf2)[b"other"] == b"a score=0\ns\tother\t0\t24\t+\t24\t" + b"N" * 24 + b"\ns\tchrQ\t0\t24\t+\t24\t1111" + b"-" * 20 + b"\n\n"
+    assert list(orc.paf_pseudo(paf2, target="chrT")) == [b"chrT"]
+    assert orc.paf_pseudo(paf2, target="nope") == {}
+    for bad, code in ((line(b"4=9I"), 8), (line(b"20=3D"), 8), (line(b"5MM"), 5), (line(b"M"), 1), (line(b""), 8),
+                      (line(b"4=", q=b"zz"), 11), (line(b"12=") + line(b"2=", ts=4, te=20, qs=0, qe=2), 8)):
+        with pytest.raises(orc.OracleError) as e:
+            orc.paf_pseudo(bad, fa, fai)
+        assert e.value.code == code, (bad, e.value.code, e.value.msg)

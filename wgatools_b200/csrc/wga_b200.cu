@@ -1360,7 +1360,7 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     uint64_t *row_len = nullptr, *row_off = nullptr;
     uint32_t *rec_bad = nullptr;
     CpView V;
-    if (key == kNoErr && n_opsT) {
+    if (n_opsT) {  // also when an error is already known: a lower record may still fail at row level
         uint64_t *op_len = ctx->buf<uint64_t>(B_RUN_POS, n_opsT + 1), *tcon = ctx->buf<uint64_t>(B_GEN_C, n_opsT + 1);
         uint64_t *qcon = ctx->buf<uint64_t>(B_GEN_D, n_opsT + 1), *rows = ctx->buf<uint64_t>(B_GEN_E, n_opsT + 1);
         uint64_t *St = ctx->buf<uint64_t>(B_GEN_F, n_opsT + 1), *Sq = ctx->buf<uint64_t>(B_GEN_G, n_opsT + 1);
