@@ -174,6 +174,16 @@ int wga_paf2maf(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t f
 int wga_paf_call(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *target,
                  const wga_fasta *query, int snp, uint64_t svlen_cutoff, wga_span *out);
 
+/* ---- pafpseudo: src/tools/pseudomaf.rs:18-237 + src/parser/cigar.rs:744-804 gen_pesudo_maf_by_cigar ------------ */
+/* One pseudo-MAF per target: `out` = the files' bytes concatenated, `index` (always host memory) = one line
+ * "{target}\t{bytes}\n" per file, i.e. what the reference writes to {out_dir}/{target}.maf.  fa = the FASTA holding
+ * targets and queries, or NULL ('N' target row, 1/0/- query rows); target = --target filter or NULL.
+ * Targets, and queries inside a target, come in first-occurrence order (the reference iterates HashMaps).  Records of
+ * one (target, query) group with equal target_start are refused with WGA_E_UNSUPPORTED: their order depends on the
+ * tie behaviour of std's binary_search (pseudomaf.rs:91-94).  On error nothing is returned. */
+int wga_paf_pseudo(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *fa,
+                   const char *target, wga_span *out, wga_span *index);
+
 /* ---- AlignRecord-level batch access (common.rs:142-176 get_stat / get_cigar_string) --------- */
 /* per-record counters of the last wga_maf2paf / wga_maf_stat / wga_paf_stat call, struct Cigar order
  * (cigar.rs:16-29): match, mismatch, ins_event, ins, del_event, del, inv_ins_event, inv_ins,

@@ -677,3 +677,77 @@ def test_call_paf_edges_and_errors(w, ctx):
             assert str(eg.value) == eo.value.msg, paf
     # errors that only exist with --snp do not fire without it
     assert cpaf(w, ctx, line(b"12=3X"), t_fa, ti, q_fa, qi, False, 0) == orc.call_paf(line(b"12=3X"), t_fa, ti, q_fa, qi, snp=False, svlen=0)
+
+
+# ---------------------------------------------------------------- pafpseudo (row a17)
+def _dedupe_starts(paf):
+    seen, out = set(), []
+    for l in paf.splitlines(keepends=True):
+        f = l.split(b"\t")
+        k = (f[0], f[5], f[7])
+        if k not in seen:
+            seen.add(k)
+            out.append(l)
+    return b"".join(out)
+
+
+def test_paf_pseudo_parity(w, ctx):
+    rng = random.Random(99)
+    for it in range(5):
+        paf, t_fa, _, q_fa, _ = make_paf2maf_case(rng, n_rec=120, width_t=rng.choice([50, 60, 80]), width_q=rng.choice([60, 61, 100]),
+                                                  soft=it % 2 == 0)
+        paf = _dedupe_starts(paf)
+        fa = t_fa + q_fa
+        fai = orc.make_fai(fa)
+        F = w.Fasta(ctx, fa, fai)
+        want = orc.paf_pseudo(paf, fa, fai)
+        got = w.pseudo_maf_files(w.PAFReader(paf), F, ctx=ctx)
+        assert list(got) == list(want)
+        for k in want:
+            assert got[k] == want[k], (it, k)
+        want = orc.paf_pseudo(paf)
+        got = w.pseudo_maf_files(w.PAFReader(paf), None, ctx=ctx)
+        assert list(got) == list(want) and all(got[k] == want[k] for k in want)
+        one = list(want)[-1]
+        assert w.pseudo_maf_files(w.PAFReader(paf), F, one.decode(), ctx=ctx) == orc.paf_pseudo(paf, fa, fai, target=one.decode())
+
+
+def test_paf_pseudo_edges_and_errors(w, ctx, tmp_path):
+    fa = b">chrT\nACGTACGTACGGGGCCCCAATTTT\n>chrQ\nACGTACGTACGGCCCCAATTTTAA\n>q2\nTTTTGGGGCCCCAAAA\n>other\nACGTACGTACGTACGTACGTACGT\n>bad\nACGTRYACGT\n"
+    fai = orc.make_fai(fa)
+    F = w.Fasta(ctx, fa, fai)
+
+    def line(cg, strand=b"+", q=b"chrQ", t=b"chrT", qs=1, qe=13, ts=2, te=14, qsz=24, tag=True):
+        return b"\t".join([q, b"%d" % qsz, b"%d" % qs, b"%d" % qe, strand, t, b"24", b"%d" % ts, b"%d" % te, b"9", b"14", b"60"] +
+                          ([b"cg:Z:" + cg] if tag else [])) + b"\n"
+    paf = (line(b"4=1X2I3=2D2=") + line(b"4=", q=b"q2", qs=0, qe=4, ts=16, te=20, qsz=16) +
+           line(b"3=1D2=", b"-", q=b"q2", qs=4, qe=9, ts=4, te=10, qsz=16) +
+           line(b"6=", qs=14, qe=20, ts=10, te=16) + line(b"4=", qs=3, qe=7, ts=11, te=15))
+    paf2 = line(b"2H4=2N", t=b"other", ts=0, te=4, qs=0, qe=4) + paf
+    ok = [paf, paf2, b"#x\n\n" + line(b"5M3S4M"), line(b"4=9I", qs=0, qe=20), line(b"3M") + line(b"20M", ts=0, te=1),
+          line(b"12=") + line(b"", ts=3, te=9) + line(b"M", ts=4, te=8, tag=False)]     # contained records are never looked at
+    for p in ok:
+        for f, ff, ffi in ((F, fa, fai), (None, None, None)):
+            want = orc.paf_pseudo(p, ff, ffi)
+            got = w.pseudo_maf_files(w.PAFReader(p), f, ctx=ctx)
+            assert list(got) == list(want) and all(got[k] == want[k] for k in want), (p, f is None)
+    assert w.pseudo_maf_files(w.PAFReader(paf2), F, "nope", ctx=ctx) == {}
+    assert w.pseudo_maf_files(w.PAFReader(b""), F, ctx=ctx) == {}
+    # the reference-shaped entry writes {out_dir}/{target}.maf
+    w.generate_pesudo_maf(w.PAFReader(paf2), str(tmp_path), None, None, ctx=ctx, fa=F)
+    assert sorted(os.listdir(tmp_path)) == ["chrT.maf", "other.maf"]
+    assert (tmp_path / "chrT.maf").read_bytes() == orc.paf_pseudo(paf2, fa, fai)[b"chrT"]
+    bad = [(line(b"4=9I"), 8), (line(b"20=3D"), 8), (line(b"5MM"), 5), (line(b"M"), 1), (line(b""), 8), (line(b"4=", q=b"zz"), 11),
+           (line(b"4=", t=b"zz"), 11), (line(b"12=") + line(b"2=", ts=4, te=20, qs=0, qe=2), 8), (line(b"4=", tag=False), 6),
+           (line(b"8=", b"-", q=b"bad", qs=0, qe=8, qsz=10), 10), (b"a\tb\n" + line(b"4="), 9), (line(b"4=", ts=30, te=40), 8),
+           (line(b"4=", t=b"other") + line(b"4=", q=b"zz", ts=3, te=5, t=b"other"), 11)]
+    for p, code in bad:
+        with pytest.raises(orc.OracleError) as eo:
+            orc.paf_pseudo(p, fa, fai)
+        with pytest.raises(w.WGAError) as eg:
+            w.pseudo_maf_files(w.PAFReader(p), F, ctx=ctx)
+        assert eo.value.code == code == eg.value.code, (p, eo.value.code, eg.value.code, eo.value.msg)
+    # equal target_start inside one (target, query) group: order is unspecified in the reference -> refused
+    with pytest.raises(w.WGAError) as e:
+        w.pseudo_maf_files(w.PAFReader(line(b"4=") + line(b"5=")), F, ctx=ctx)
+    assert e.value.code == 102

@@ -1,8 +1,9 @@
 """wgatools_b200 -- B200-native hot path of wgatools (maf2paf / stat / call): hand-written sm_100a CUDA
 kernels behind a C ABI (include/wga_b200.h) with a host-side mirror of the reference's operator
 interface (wgatools_b200.api).  No CPU fallback."""
-from .api import (Context, Fasta, MAFReader, PAFReader, ResidentMaf, StatAcc, WGAError, call_var_maf, call_var_paf, default_context, maf2paf,
+from .api import (Context, Fasta, MAFReader, PAFReader, ResidentMaf, StatAcc, WGAError, call_var_maf, call_var_paf, default_context, generate_pesudo_maf,
+                  maf2paf, pseudo_maf_files,
                   paf2maf, run_bytes, stat_maf, stat_paf)
 
-__all__ = ["Context", "MAFReader", "PAFReader", "StatAcc", "WGAError", "call_var_maf", "call_var_paf", "default_context",
+__all__ = ["Context", "MAFReader", "PAFReader", "StatAcc", "WGAError", "call_var_maf", "call_var_paf", "default_context", "generate_pesudo_maf", "pseudo_maf_files",
            "maf2paf", "paf2maf", "Fasta", "ResidentMaf", "run_bytes", "stat_maf", "stat_paf"]

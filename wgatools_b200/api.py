@@ -371,6 +371,32 @@ def call_var_paf(pafreader: PAFReader, t_fa_path, q_fa_path, writer, if_snp=Fals
     writer.write(body)
 
 
+def pseudo_maf_files(reader: PAFReader, fa=None, target=None, ctx=None) -> dict:
+    """{target name (bytes): bytes of {out_dir}/{target}.maf} in first-occurrence order; fa: a Fasta or None"""
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(reader.data)
+    out, index = Span(), Span()
+    ctx._check(ctx.L.wga_paf_pseudo(ctx.h, ctypes.c_void_p(base), len(reader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB,
+                                    fa.h if fa is not None else None, _opt(target), ctypes.byref(out), ctypes.byref(index)))
+    files, pos = {}, 0
+    idx = ctypes.string_at(index.data, index.len) if index.len else b""
+    for line in idx.splitlines():
+        name, n = line.rsplit(b"\t", 1)
+        files[name] = ctypes.string_at(out.data + pos, int(n))
+        pos += int(n)
+    return files
+
+
+def generate_pesudo_maf(reader: PAFReader, out_dir, fa_path=None, target=None, ctx=None, fa=None):
+    """src/tools/pseudomaf.rs:18-75 (sic): one file {out_dir}/{target}.maf per target"""
+    ctx = ctx or default_context()
+    if fa is None and fa_path is not None:
+        fa = Fasta.from_path(ctx, fa_path)
+    for name, data in pseudo_maf_files(reader, fa, target, ctx).items():
+        with open(os.path.join(out_dir, name.decode("utf-8", "replace") + ".maf"), "wb") as f:
+            f.write(data)
+
+
 def run_bytes(fn, *args, **kw) -> bytes:
     """convenience: run one of the functions above into a bytes object (the writer argument is inserted
     where the reference signature has it: 2nd for maf2paf/stat_*, 3rd for call_var_maf, 4th for call_var_paf)"""

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/wga_b200.h"
@@ -48,6 +49,8 @@ enum BufId {
     B_NAME_LEN, B_NAME_OFF, B_NAME_BUF, B_INV_FLAG, B_INV_IDX, B_INV_PAIR, B_INV_NUM,
     B_GEN_A, B_GEN_B, B_GEN_C, B_GEN_D, B_GEN_E, B_GEN_F, B_GEN_G, B_GEN_H,
     B_TEXT_RES,
+    B_PP_A, B_PP_B, B_PP_C, B_PP_D, B_PP_E, B_PP_F, B_PP_G, B_PP_H, B_PP_I, B_PP_J, B_PP_K, B_PP_L, B_PP_M, B_PP_N, B_PP_O, B_PP_P,
+    B_PP_Q, B_PP_R, B_PP_S, B_PP_T,
     B_PAF_A, B_PAF_B, B_PAF_C, B_PAF_D, B_PAF_E, B_PAF_F, B_PAF_G, B_PAF_H, B_PAF_I, B_PAF_J,
     B_COUNT_
 };
@@ -73,6 +76,7 @@ struct wga_ctx {
     int err_code = 0;
     uint64_t err_where = 0;
     std::string err_msg;
+    std::string pseudo_index;  // host text of the last wga_paf_pseudo file index
     // accounting
     uint64_t n_own = 0, n_cub = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -151,6 +155,18 @@ static int exclusive_sum(wga_ctx *ctx, const InT *in, OutT *out, uint64_t n) {
     void *t = ctx->ensure(B_CUBTMP, tmp);
     if (!t) return ctx->err_code;
     WGA_CK(cub::DeviceScan::ExclusiveSum(t, tmp, in, out, (int64_t)n, ctx->stream));
+    ctx->n_cub++;
+    return WGA_OK;
+}
+
+// stable LSD radix sort of (key, value) pairs (utility: orders the small per-record index arrays of pafpseudo)
+static int sort_pairs_u64(wga_ctx *ctx, const uint64_t *k_in, uint64_t *k_out, const uint64_t *v_in, uint64_t *v_out, uint64_t n) {
+    if (n == 0) return WGA_OK;
+    size_t tmp = 0;
+    WGA_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int64_t)n, 0, 64, ctx->stream));
+    void *t = ctx->ensure(B_CUBTMP, tmp);
+    if (!t) return ctx->err_code;
+    WGA_CK(cub::DeviceRadixSort::SortPairs(t, tmp, k_in, k_out, v_in, v_out, (int64_t)n, 0, 64, ctx->stream));
     ctx->n_cub++;
     return WGA_OK;
 }

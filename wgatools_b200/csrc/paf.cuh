@@ -60,8 +60,9 @@ __device__ __forceinline__ void paf_report(unsigned long long *err_key, uint64_t
 }
 
 // one PAF line -> 12 typed columns + cg:Z: span (paf.rs:48-65,122-140)
+// tag_key: where a missing cg:Z: tag is reported (== err_key for commands that look every record's CIGAR up in file order)
 __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, const uint32_t *__restrict__ rec_scan,
-                            PafRecs R, unsigned long long *err_key) {
+                            PafRecs R, unsigned long long *err_key, unsigned long long *tag_key) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= lv.n_lines || !flags[k]) return;
     const uint64_t r = rec_scan[k];
@@ -111,10 +112,10 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
     R.t_size[r] = v[6]; R.t_start[r] = v[7];
     R.neg[r] = neg;
     if (!have_cg) {  // cs:Z: conversion (paf.rs:159-218) is not accelerated; no tag at all is the reference's error
-        paf_report(err_key, r, 0x800000, have_cs ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
+        paf_report(tag_key, r, 0x800000, have_cs ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
         cg_len = 0;
         cg_off = 0;
-        R.neg[r] = neg | 2;  // bit 1 marks "no cigar" (bit 0 stays the strand)
+        R.neg[r] = neg | 2 | (have_cs ? 4 : 0);  // bit 1 marks "no cg:Z:" (bit 0 stays the strand), bit 2 "but a cs:Z:"
     }
     R.cig_off[r] = cg_off;
     R.cig_len[r] = cg_len;

@@ -87,7 +87,7 @@ struct P2mRecs {  // per PAF record
 // extra typed columns + FASTA spans (converter.rs:196-225)
 // end_adj: 1 = paf2maf / pafpseudo fetch [start, end-1]; 0 = `call -f paf` fetches [start, end] (paf.rs:221-237, Q13)
 __global__ void k_p2m_spans(LineView lv, const uint8_t *__restrict__ flags, const uint32_t *__restrict__ rec_scan, PafRecs R,
-                            P2mRecs X, FaView T, FaView Q, uint64_t end_adj, unsigned long long *err_key) {
+                            P2mRecs X, FaView T, FaView Q, uint64_t end_adj, int lookup, unsigned long long *err_key) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= lv.n_lines || !flags[k]) return;
     const uint64_t r = rec_scan[k];
@@ -108,6 +108,7 @@ __global__ void k_p2m_spans(LineView lv, const uint8_t *__restrict__ flags, cons
     }
     X.q_end[r] = v3; X.t_end[r] = v8; X.mapq[r] = v11;
     X.LT[r] = X.LQ[r] = X.t_src[r] = X.q_src[r] = 0;
+    if (!lookup) return;  // pafpseudo looks sequences up later, for the records it keeps
     const uint64_t ti = fa_find(T, lv.text + R.t_name_off[r], R.t_name_len[r]);
     const uint64_t qi = ti == ~0ull ? ~0ull : fa_find(Q, lv.text + R.q_name_off[r], R.q_name_len[r]);
     if (ti == ~0ull || qi == ~0ull) { paf_report(err_key, r, 1, WGA_E_NOM); return; }  // faidx: sequence not found

@@ -15,6 +15,7 @@
 #include "paf.cuh"
 #include "paf2maf.cuh"
 #include "call_paf.cuh"
+#include "pafpseudo.cuh"
 #endif
 
 using namespace wga;
@@ -1042,7 +1043,7 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (!R.q_name_off || !R.t_name_off || !R.cig_off || !R.cig_len || !R.q_name_len || !R.t_name_len || !m4 || !R.neg || !cnt11)
         return ctx->err_code;
     R.q_size = m4; R.t_size = m4 + n_rec; R.q_start = m4 + 2 * n_rec; R.t_start = m4 + 3 * n_rec;
-    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key);
+    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key, err_key);
     WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key);
     WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1188,7 +1189,8 @@ struct PafPrep {
     unsigned long long *err_key = nullptr;
     uint64_t *n_ops = nullptr, *op_base = nullptr;
 };
-static int paf_fasta_prepare(wga_ctx *ctx, uint64_t len, const wga_fasta *TF, const wga_fasta *QF, uint64_t end_adj, PafPrep *PP) {
+static int paf_fasta_prepare(wga_ctx *ctx, uint64_t len, const wga_fasta *TF, const wga_fasta *QF, uint64_t end_adj, PafPrep *PP,
+                             bool with_spans = true, unsigned long long *tag_key = nullptr) {
     ctx->n_rec = 0;
     if (len == 0) return WGA_OK;
     const uint8_t *d_text = ctx->d_text;
@@ -1228,9 +1230,11 @@ static int paf_fasta_prepare(wga_ctx *ctx, uint64_t len, const wga_fasta *TF, co
     P2mRecs X;
     X.q_end = x7; X.t_end = x7 + n_rec; X.mapq = x7 + 2 * n_rec; X.t_src = x7 + 3 * n_rec; X.q_src = x7 + 4 * n_rec;
     X.LT = x7 + 5 * n_rec; X.LQ = x7 + 6 * n_rec; X.n_ops = n_ops;
-    FaView T{TF->d_seq, TF->d_names, TF->d_meta, TF->n_seq}, Q{QF->d_seq, QF->d_names, QF->d_meta, QF->n_seq};
-    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key);
-    LAUNCH(ctx, k_p2m_spans, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, X, T, Q, end_adj, err_key);
+    FaView T{nullptr, nullptr, nullptr, 0}, Q{nullptr, nullptr, nullptr, 0};
+    if (TF) T = FaView{TF->d_seq, TF->d_names, TF->d_meta, TF->n_seq};
+    if (QF) Q = FaView{QF->d_seq, QF->d_names, QF->d_meta, QF->n_seq};
+    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key, tag_key ? tag_key : err_key);
+    LAUNCH(ctx, k_p2m_spans, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, X, T, Q, end_adj, with_spans ? 1 : 0, err_key);
     PP->lv = lv; PP->R = R; PP->X = X; PP->n_rec = n_rec; PP->err_key = err_key; PP->n_ops = n_ops; PP->op_base = op_base;
     return WGA_OK;
 }
@@ -1422,6 +1426,201 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
            err_key);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
+
+// ---------------------------------------------------------------- pafpseudo (pseudomaf.rs:18-237, cigar.rs:744-804)
+int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *FA, const char *target,
+                   wga_span *out, wga_span *index) {
+    if (!ctx || !out || !index || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr; out->len = 0;
+    index->data = nullptr; index->len = 0;
+    ctx->pseudo_index.clear();
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    unsigned long long *tag_key = ctx->buf<unsigned long long>(B_PP_T, 1);
+    if (!tag_key) return ctx->err_code;
+    PafPrep PP;
+    WGA_TRY(paf_fasta_prepare(ctx, len, nullptr, nullptr, 1, &PP, false, tag_key));
+    const uint64_t n_rec = PP.n_rec;
+    if (n_rec == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    PafRecs R = PP.R;
+    P2mRecs X = PP.X;
+    unsigned long long *err_key = PP.err_key;
+    const int base = FA != nullptr;
+    uint64_t key;
+    WGA_TRY(read_scalars(ctx, {err_key}, &key));  // csv-level errors come first: the reference reads every record up front
+    auto fail = [&](uint64_t k) {
+        const int code = (int)(k & 0xFF);
+        const uint64_t rec = k >> 32;
+        std::string msg;
+        if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+        else if (code == WGA_E_NOM) msg = "HTS library error by sequence not found in the FASTA index";
+        else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported input: quoted csv field, cs:Z: without cg:Z:, or records of one (target, query) group with equal target_start";
+        else if (code == WGA_E_VCF_BASE) msg = "Invalid Base in a '-' strand query";
+        else if (code == WGA_E_CIGAR_OP_INVALID) msg = "CIGAR OP invalid";
+        else if (code == WGA_E_PARSE_INT) msg = "Parse Into Integer Error";
+        else if (code == WGA_E_INTERNAL) msg = "name hash collision";
+        else msg = "the reference panics on this input (drain / insert_str / slice past the end, or an underflowing subtraction)";
+        ctx->set_error(code, rec, msg);
+        return code;
+    };
+    if (key != kNoErr) return fail(key);
+
+    // ---- group keys, first-occurrence ranks, sorted order
+    uint64_t *kt = ctx->buf<uint64_t>(B_PP_A, n_rec), *kp = ctx->buf<uint64_t>(B_PP_B, n_rec);
+    uint64_t *ft = ctx->buf<uint64_t>(B_PP_C, n_rec), *fp = ctx->buf<uint64_t>(B_PP_D, n_rec);
+    uint64_t *slot_of = ctx->buf<uint64_t>(B_PP_E, n_rec);
+    uint64_t cap = 64;
+    while (cap < 2 * n_rec) cap <<= 1;
+    unsigned long long *tkeys = ctx->buf<unsigned long long>(B_PT_KEYS, cap), *tfirst = ctx->buf<unsigned long long>(B_PT_FIRST, cap);
+    uint8_t *d_filter = nullptr;
+    const uint32_t flen = target ? (uint32_t)strlen(target) : 0;
+    if (target) {
+        d_filter = (uint8_t *)ctx->ensure(B_QNAME, flen + 1);
+        if (!d_filter) return ctx->err_code;
+        WGA_CK(cudaMemcpyAsync(d_filter, target, flen, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!kt || !kp || !ft || !fp || !slot_of || !tkeys || !tfirst) return ctx->err_code;
+    LAUNCH(ctx, k_pp_keys, grid_for(n_rec, 256), 256, n_rec, d_text, R, (const uint8_t *)d_filter, flen, target ? 1 : 0, kt, kp);
+    for (int pass = 0; pass < 2; ++pass) {
+        WGA_CK(cudaMemsetAsync(tkeys, 0, cap * 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(tfirst, 0xFF, cap * 8, ctx->stream));
+        LAUNCH(ctx, k_pp_first_insert, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)(pass ? kp : kt), cap - 1, tkeys, tfirst, slot_of);
+        LAUNCH(ctx, k_pp_first_read, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)slot_of, (const unsigned long long *)tfirst,
+               pass ? fp : ft);
+    }
+    LAUNCH(ctx, k_pp_verify, grid_for(n_rec, 256), 256, n_rec, d_text, R, (const uint64_t *)ft, (const uint64_t *)fp, err_key);
+    uint64_t *ka = ctx->buf<uint64_t>(B_PP_F, n_rec), *kb = ctx->buf<uint64_t>(B_PP_G, n_rec);
+    uint64_t *va = ctx->buf<uint64_t>(B_PP_H, n_rec), *vb = ctx->buf<uint64_t>(B_PP_I, n_rec);
+    if (!ka || !kb || !va || !vb) return ctx->err_code;
+    LAUNCH(ctx, k_pp_iota, grid_for(n_rec, 256), 256, n_rec, va);
+    WGA_TRY(sort_pairs_u64(ctx, R.t_start, kb, va, vb, n_rec));                       // by target_start
+    LAUNCH(ctx, k_pp_gather_u64, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)fp, (const uint64_t *)vb, ka);
+    WGA_TRY(sort_pairs_u64(ctx, ka, kb, vb, va, n_rec));                              // then by query group
+    LAUNCH(ctx, k_pp_gather_u64, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)ft, (const uint64_t *)va, ka);
+    WGA_TRY(sort_pairs_u64(ctx, ka, kb, va, vb, n_rec));                              // then by target
+    const uint64_t *ord = vb;   // sorted position -> file-order record; dropped records (key ~0) are last
+    // number of used records = first sorted position whose target key is "dropped"
+    uint64_t n = n_rec;
+    if (target) {
+        uint32_t *usedf = ctx->buf<uint32_t>(B_PP_J, n_rec + 1), *useds = ctx->buf<uint32_t>(B_PP_K, n_rec + 1);
+        if (!usedf || !useds) return ctx->err_code;
+        LAUNCH(ctx, k_pp_used, grid_for(n_rec + 1, 256), 256, n_rec, (const uint64_t *)ft, usedf);
+        WGA_TRY(exclusive_sum(ctx, usedf, useds, n_rec + 1));
+        WGA_CK(cudaMemcpyAsync(ctx->h_scal, useds + n_rec, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_TRY(sync_check(ctx));
+        n = *(uint32_t *)ctx->h_scal;
+    }
+    if (n == 0) return WGA_OK;
+
+    // ---- group structure + the sequential last_target_end state
+    PpRecs S;
+    S.rec = const_cast<uint64_t *>(ord);
+    S.flags = ctx->buf<uint32_t>(B_PP_J, n + 1);
+    uint32_t *ghead = ctx->buf<uint32_t>(B_PP_K, n + 1), *gid = ctx->buf<uint32_t>(B_PP_L, n + 1);
+    uint64_t *p8 = ctx->buf<uint64_t>(B_PP_M, 10 * (n + 1));
+    if (!S.flags || !ghead || !gid || !p8) return ctx->err_code;
+    S.gap = p8; S.overlap = p8 + (n + 1); S.tail = p8 + 2 * (n + 1); S.q_src = p8 + 3 * (n + 1); S.LQ = p8 + 4 * (n + 1);
+    S.P = p8 + 5 * (n + 1); S.seg_len = p8 + 6 * (n + 1); S.seg_off = p8 + 7 * (n + 1);
+    uint64_t *t_src = p8 + 8 * (n + 1), *t_cnt = p8 + 9 * (n + 1);
+    LAUNCH(ctx, k_pp_flags, grid_for(n + 1, 256), 256, n, ord, (const uint64_t *)ft, (const uint64_t *)fp, (const uint64_t *)R.t_start, S.flags,
+           ghead, err_key);
+    WGA_TRY(exclusive_sum(ctx, ghead, gid, n + 1));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal, gid + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    const uint64_t n_groups = *(uint32_t *)ctx->h_scal;
+    uint64_t *gstart = ctx->buf<uint64_t>(B_PP_N, n_groups + 1);
+    if (!gstart) return ctx->err_code;
+    LAUNCH(ctx, k_pp_group_starts, grid_for(n + 1, 256), 256, n, (const uint32_t *)ghead, (const uint32_t *)gid, gstart, n_groups);
+    LAUNCH(ctx, k_pp_groups, grid_for(n_groups, 128), 128, n_groups, (const uint64_t *)gstart, ord, R, X, S, err_key);
+    // target heads
+    uint32_t *tflag = ghead, *tid = gid;  // reuse
+    LAUNCH(ctx, k_pp_thead_flag, grid_for(n + 1, 256), 256, n, (const uint32_t *)S.flags, tflag);
+    WGA_TRY(exclusive_sum(ctx, tflag, tid, n + 1));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal, tid + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    const uint64_t n_targets = *(uint32_t *)ctx->h_scal;
+    uint64_t *thead_pos = ctx->buf<uint64_t>(B_PP_O, n_targets + 1), *finfo = ctx->buf<uint64_t>(B_PP_P, 4 * n_targets + 4);
+    if (!thead_pos || !finfo) return ctx->err_code;
+    LAUNCH(ctx, k_pp_thead_pos, grid_for(n, 256), 256, n, (const uint32_t *)S.flags, (const uint32_t *)tid, thead_pos);
+
+    // ---- FASTA spans, CIGAR ops, layout
+    FaView F{nullptr, nullptr, nullptr, 0};
+    if (FA) F = FaView{FA->d_seq, FA->d_names, FA->d_meta, FA->n_seq};
+    LAUNCH(ctx, k_pp_spans, grid_for(n, 256), 256, n, d_text, ord, R, X, S, F, base, t_src, t_cnt, err_key);
+    if (base) LAUNCH(ctx, k_pp_revcomp_check, (unsigned)std::min<uint64_t>(n, 0x7FFFFFFFull), 128, n, ord, R, S, (const uint8_t *)FA->d_seq, err_key);
+    uint64_t *n_ops = ctx->buf<uint64_t>(B_PP_Q, n + 1), *op_base = ctx->buf<uint64_t>(B_PP_R, n + 1);
+    if (!n_ops || !op_base) return ctx->err_code;
+    LAUNCH(ctx, k_pp_ops<0>, grid_for(n + 1, 128), 128, n, d_text, ord, R, S, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+           (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key);
+    WGA_TRY(exclusive_sum(ctx, n_ops, op_base, n + 1));
+    uint64_t sc[2];
+    WGA_TRY(read_scalars(ctx, {op_base + n, err_key}, sc));
+    const uint64_t n_opsT = sc[0];
+    uint64_t *op_len = ctx->buf<uint64_t>(B_RUN_POS, n_opsT + 1), *c_out = ctx->buf<uint64_t>(B_GEN_C, n_opsT + 1);
+    uint64_t *c_src = ctx->buf<uint64_t>(B_GEN_D, n_opsT + 1), *S_out = ctx->buf<uint64_t>(B_GEN_E, n_opsT + 1);
+    uint64_t *S_src = ctx->buf<uint64_t>(B_GEN_F, n_opsT + 1);
+    uint8_t *op_type = ctx->buf<uint8_t>(B_RUN_CLS, n_opsT + 1);
+    uint32_t *op_rec = ctx->buf<uint32_t>(B_RUN_REC, n_opsT + 1), *op_pos = ctx->buf<uint32_t>(B_RUN_DL, n_opsT + 1);
+    if (!op_len || !c_out || !c_src || !S_out || !S_src || !op_type || !op_rec || !op_pos) return ctx->err_code;
+    LAUNCH(ctx, k_pp_ops<1>, grid_for(n + 1, 128), 128, n, d_text, ord, R, S, n_ops, (const uint64_t *)op_base, op_len, op_type, op_rec, op_pos,
+           err_key);
+    LAUNCH(ctx, k_pp_contrib, grid_for(n_opsT + 1, 256), 256, n_opsT, (const uint64_t *)op_len, (const uint8_t *)op_type, c_out, c_src);
+    WGA_TRY(exclusive_sum(ctx, c_out, S_out, n_opsT + 1));
+    WGA_TRY(exclusive_sum(ctx, c_src, S_src, n_opsT + 1));
+    PpView V;
+    V.n = n; V.n_ops = n_opsT; V.text = d_text; V.ord = ord; V.R = R; V.X = X; V.S = S; V.op_base = op_base; V.op_len = op_len;
+    V.op_type = op_type; V.op_rec = op_rec; V.op_pos = op_pos; V.S_out = S_out; V.S_src = S_src; V.seq = FA ? FA->d_seq : nullptr;
+    V.t_src = t_src; V.t_cnt = t_cnt; V.base = base; V.out = nullptr;
+    if (n_opsT) LAUNCH(ctx, k_pp_check, grid_for(n_opsT, 256), 256, V, err_key);
+    LAUNCH(ctx, k_pp_layout, grid_for(n + 1, 256), 256, V, err_key);
+    WGA_TRY(exclusive_sum(ctx, S.seg_len, S.seg_off, n + 1));
+    WGA_TRY(read_scalars(ctx, {S.seg_off + n, err_key}, sc));
+    if (sc[1] != kNoErr) return fail(sc[1]);
+    const uint64_t total = sc[0];
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    V.out = d_out;
+    WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    WGA_CK(cudaMemsetAsync(d_out, '-', total, ctx->stream));
+    LAUNCH(ctx, k_pp_fixed, grid_for(n, 256), 256, V);
+    {
+        const uint64_t per = 256ull * 64;
+        uint64_t gx = 1;
+        // enough blocks per target for the longest sequence; grid-stride covers the rest
+        gx = std::min<uint64_t>(2048, std::max<uint64_t>(1, (total / std::max<uint64_t>(n_targets, 1) + per - 1) / per));
+        dim3 grid((unsigned)gx, (unsigned)std::min<uint64_t>(n_targets, 65535));
+        if (n_targets > 65535) { ctx->set_error(WGA_E_UNSUPPORTED, 0, "more than 65535 targets in one call"); return WGA_E_UNSUPPORTED; }
+        k_pp_target_rows<<<grid, 256, 0, ctx->stream>>>(V, (const uint64_t *)thead_pos, n_targets);
+        ctx->n_own++;
+    }
+    LAUNCH(ctx, k_pp_rows, grid_for((n_opsT + n) * 32, 256), 256, V);
+    WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    LAUNCH(ctx, k_pp_files, grid_for(n_targets, 128), 128, V, (const uint64_t *)thead_pos, n_targets, total, finfo);
+    // index: "{target}\t{bytes}\n" per file, built on the host from the (tiny) per-file table
+    std::vector<uint64_t> info(4 * n_targets);
+    WGA_CK(cudaMemcpyAsync(info.data(), finfo, info.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    std::string &idx = ctx->pseudo_index;
+    for (uint64_t t = 0; t < n_targets; ++t) {
+        std::string name((size_t)info[4 * t + 1], '\0');
+        if (!name.empty()) WGA_CK(cudaMemcpy(&name[0], d_text + info[4 * t], name.size(), cudaMemcpyDeviceToHost));
+        idx += name;
+        idx += '\t';
+        idx += std::to_string(info[4 * t + 3]);
+        idx += '\n';
+    }
+    index->data = idx.data();
+    index->len = idx.size();
+    int rc = finish_output(ctx, d_out, total, mem, flags, out);
+    if (rc) return rc;
+    float ms = 0.f;
+    WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->walk_ms = ms; ctx->walk_launches = 1; ctx->walk_bytes = total;  // expansion: output-bound
+    return WGA_OK;
+}
 #endif
 
 #ifndef WGA_WITH_PAF
@@ -1434,6 +1633,9 @@ void wga_fasta_free(wga_fasta *) {}
 int wga_paf2maf_header(wga_ctx *, const char *, const char *, wga_span *) { return WGA_E_UNSUPPORTED; }
 int wga_paf2maf(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const wga_fasta *, wga_span *) { return WGA_E_UNSUPPORTED; }
 int wga_paf_call(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const wga_fasta *, int, uint64_t, wga_span *) {
+    return WGA_E_UNSUPPORTED;
+}
+int wga_paf_pseudo(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const char *, wga_span *, wga_span *) {
     return WGA_E_UNSUPPORTED;
 }
 #endif
