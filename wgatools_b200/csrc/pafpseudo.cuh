@@ -10,7 +10,7 @@
 // I/S delete query bases, D inserts '-'; without FASTA M/= -> '1', X -> '0', D -> '-'; other ops are ignored.
 //
 // The reference's two HashMaps iterate in arbitrary order; here targets, and queries inside a target, come in
-// first-occurrence order (the oracle's convention).  The reference edits Strings (drain / insert_str, O(L) per
+// first-occurrence order (the convention of the stat rows).  The reference edits Strings (drain / insert_str, O(L) per
 // indel); here the whole output is laid out by prefix sums, filled with '-' once, and every CIGAR op writes its own
 // slice.  Records of one group with EQUAL target_start are ordered by std's binary_search tie behaviour in the
 // reference (pseudomaf.rs:91-94), which is not specified: such inputs are refused (WGA_E_UNSUPPORTED).
