@@ -530,7 +530,7 @@ typedef struct {
     uint64_t inv_ins_event, inv_ins_size, inv_del_event, inv_del_size;
 } statrow;
 
-typedef struct { statrow *r; size_t n, cap; } statvec;
+typedef struct { statrow *r; size_t n, cap; size_t *ht; size_t ht_cap; } statvec; /* ht: Pair -> row (the HashMap) */
 static statrow *statvec_push(statvec *v) {
     if (v->n == v->cap) {
         v->cap = v->cap ? v->cap * 2 : 64;
@@ -547,18 +547,46 @@ static void stat_accumulate(statvec *v, int each, sv ref_name, uint64_t ref_size
                             sv query_name, uint64_t query_size, uint64_t query_start,
                             const recstat *rs) {
     statrow *s = NULL;
-    if (!each) {
-        for (size_t i = 0; i < v->n; i++) { /* HashMap<Pair,..>: linear probe keeps first-seen order */
-            statrow *c = &v->r[i];
+    size_t slot = 0;
+    if (!each) { /* HashMap<Pair,..> (stat.rs:170-176); rows keep first-seen order */
+        if ((v->n + 1) * 2 > v->ht_cap) { /* grow + rehash */
+            size_t nc = v->ht_cap ? v->ht_cap * 2 : 1024;
+            size_t *nh = (size_t *)malloc(nc * sizeof(size_t));
+            for (size_t i = 0; i < nc; i++) nh[i] = (size_t)-1;
+            for (size_t i = 0; i < v->n; i++) {
+                const statrow *c = &v->r[i];
+                uint64_t h = 1469598103934665603ull;
+                for (size_t k = 0; k < c->ref_name.n; k++) h = (h ^ (unsigned char)c->ref_name.p[k]) * 1099511628211ull;
+                h = (h ^ c->ref_size) * 1099511628211ull;
+                for (size_t k = 0; k < c->query_name.n; k++) h = (h ^ (unsigned char)c->query_name.p[k]) * 1099511628211ull;
+                h = (h ^ c->query_size) * 1099511628211ull;
+                size_t sl = (size_t)(h ^ (h >> 29)) & (nc - 1);
+                while (nh[sl] != (size_t)-1) sl = (sl + 1) & (nc - 1);
+                nh[sl] = i;
+            }
+            free(v->ht);
+            v->ht = nh;
+            v->ht_cap = nc;
+        }
+        uint64_t h = 1469598103934665603ull;
+        for (size_t k = 0; k < ref_name.n; k++) h = (h ^ (unsigned char)ref_name.p[k]) * 1099511628211ull;
+        h = (h ^ ref_size) * 1099511628211ull;
+        for (size_t k = 0; k < query_name.n; k++) h = (h ^ (unsigned char)query_name.p[k]) * 1099511628211ull;
+        h = (h ^ query_size) * 1099511628211ull;
+        slot = (size_t)(h ^ (h >> 29)) & (v->ht_cap - 1);
+        while (v->ht[slot] != (size_t)-1) {
+            statrow *c = &v->r[v->ht[slot]];
             if (c->ref_size == ref_size && c->query_size == query_size && sv_eq(c->ref_name, ref_name) &&
                 sv_eq(c->query_name, query_name)) {
                 s = c;
                 break;
             }
+            slot = (slot + 1) & (v->ht_cap - 1);
         }
     }
     if (!s) {
         s = statvec_push(v);
+        if (!each) v->ht[slot] = v->n - 1;
         s->ref_name = ref_name; s->ref_size = ref_size;
         s->query_name = query_name; s->query_size = query_size;
         if (each) { s->ref_start = ref_start; s->query_start = query_start; }
@@ -667,7 +695,7 @@ int orc_stat_maf(const char *text, size_t len, int each, const char *query_name,
     }
     if (rc == 0) stat_write(&v, each, out);
     free(rec.s);
-    free(v.r);
+    free(v.r); free(v.ht);
     return rc < 0 ? -rc : ORC_OK;
 }
 
@@ -891,7 +919,7 @@ int orc_stat_paf(const char *text, size_t len, int each, orc_buf *out, char *err
     /* names reference row scratch only for quoted fields; copy-free path is the norm.  To be
      * safe for quoted names we would need owned copies; quoted names are not generated by tests. */
     if (rc == ORC_OK) stat_write(&v, each, out);
-    free(row.f); free(row.scratch); free(v.r);
+    free(row.f); free(row.scratch); free(v.r); free(v.ht);
     orc_buf_free(&conv);
     return rc;
 }
@@ -1330,7 +1358,7 @@ int orc_stat_maf_mt(const char *text, size_t len, int each, const char *query_na
     }
     for (size_t i = 0; i < ps.next_idx; i++) free(ps.st[i].own);
     free(ps.st);
-    free(v.r);
+    free(v.r); free(v.ht);
     return rc;
 }
 

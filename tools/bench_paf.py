@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--fa-records", type=int, default=50_000, help="config-5 PAF records against the FASTA")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--cpu-mb", type=float, default=60.0)
+    ap.add_argument("--only", default="", help="stat | fasta : run one half only (profiling)")
     args = ap.parse_args()
 
     import torch
@@ -115,6 +116,8 @@ def main():
         print(json.dumps(line), flush=True)
 
     # ---------------- config 4 (scaled): stat -f paf
+    if args.only == "fasta":
+        args.records = 1000
     paf = bs.gen_paf(bs.paf_params(args.records, seed=20260928))
     d = resident(paf)
     buf, hp = ctypes.c_char_p(paf), None
@@ -136,6 +139,8 @@ def main():
     cpu = len(smp) / (time.perf_counter() - t0) / 1e9
     report("stat -f paf (config 4 shape)", len(paf), ms_dev, ms_e2e, 0, cpu, len(smp), {"records": args.records})
     del d
+    if args.only == "stat":
+        return
 
     # ---------------- config 5 (scaled): FASTA-backed commands
     chr_size = int(args.chr_mbp * 1e6)
@@ -162,7 +167,7 @@ def main():
                 ctx._check(L.wga_paf_pseudo(ctx.h, ptr, len(paf5), mem, 1, F.h, None, ctypes.byref(sp), ctypes.byref(sp2)))
             outn[fn_name] = sp.len
         return run
-    smp5 = sample_lines(paf5, min(args.cpu_mb, 20.0))
+    smp5 = sample_lines(paf5, min(args.cpu_mb, 4.0))  # paf2maf writes ~80x its input
     for name, label, cpu_fn in (("paf2maf", "paf2maf (config 5 shape)", lambda s: orc.paf2maf(s, fa, fai, fa, fai)),
                                 ("call", "call -f paf -s -l0", lambda s: orc.call_paf(s, fa, fai, fa, fai, snp=True, svlen=0)),
                                 ("pseudo", "pafpseudo -f all.fa", lambda s: orc.paf_pseudo(s, fa, fai))):
