@@ -121,11 +121,110 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
     R.cig_len[r] = cg_len;
 }
 
-// CIGAR text -> the 11 counters of struct Cigar (cigar.rs:16-29).  One record per thread.
+// CIGAR text -> the 11 counters of struct Cigar (cigar.rs:16-29), fast path: one WARP per record, lane i of a step
+// owns the aligned 16-byte piece 32*step+i.  A token belongs to the piece that holds its op char; its digits may start
+// in the previous piece, which arrives by shuffle (lane 0: the last piece of the previous step).  Anything that is not
+// `digits+ one-of(M=XID)` -- i.e. every input on which the reference raises an error, plus numbers of 17+ digits --
+// only sets slow[r]; those records are redone by the exact one-thread kernel below, which owns all error reporting.
+__global__ void __launch_bounds__(256) k_paf_cigar_counts_warp(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
+                                                               unsigned long long *__restrict__ cnt11, uint8_t *__restrict__ slow) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (r >= n_rec) return;
+    const uint8_t negf = R.neg[r];
+    const uint64_t len = R.cig_len[r];
+    if ((negf & 2) || len == 0) { if (lane == 0) slow[r] = 1; return; }
+    const uint8_t *p = text + R.cig_off[r];
+    const uint64_t a = reinterpret_cast<uintptr_t>(p) & 15u;
+    const uint8_t *base = p - a;
+    const uint64_t nvec = (a + len + 15) >> 4;
+    unsigned long long c_m = 0, c_x = 0, c_i = 0, c_d = 0, e_i = 0, e_d = 0;
+    bool bad = false;
+    const uint4 colons = make_uint4(0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au);
+    uint4 carry = colons;  // the byte before a CIGAR is the ':' of "cg:Z:"
+    for (uint64_t v0 = 0; v0 < nvec; v0 += 32) {
+        const uint64_t vi = v0 + lane;
+        const bool have = vi < nvec;
+        const uint4 cur = have ? ldg16(base + 16 * vi) : colons;
+        uint4 prev;
+        prev.x = __shfl_up_sync(0xFFFFFFFFu, cur.x, 1); prev.y = __shfl_up_sync(0xFFFFFFFFu, cur.y, 1);
+        prev.z = __shfl_up_sync(0xFFFFFFFFu, cur.z, 1); prev.w = __shfl_up_sync(0xFFFFFFFFu, cur.w, 1);
+        if (lane == 0) prev = carry;
+        carry.x = __shfl_sync(0xFFFFFFFFu, cur.x, 31); carry.y = __shfl_sync(0xFFFFFFFFu, cur.y, 31);
+        carry.z = __shfl_sync(0xFFFFFFFFu, cur.z, 31); carry.w = __shfl_sync(0xFFFFFFFFu, cur.w, 31);
+        if (!have) continue;
+        const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;  // CIGAR index of byte 0 of this piece
+        unsigned long long val = 0;
+        uint32_t nd = 0;
+        if (idx0 > 0) {  // digits at the end of the previous piece belong to the first token that closes here
+            const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+            bool run = true;
+#pragma unroll
+            for (int j = 15; j >= 0; --j) {
+                const uint32_t ch = (pw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                run = run && (ch - '0') <= 9u;
+                nd += run ? 1u : 0u;
+            }
+            if (nd == 16) bad = true;  // the number started even earlier
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t ch = (pw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                if (j >= 16 - (int)nd) val = val * 10 + (ch - '0');
+            }
+        }
+        bool prev_nondigit = nd == 0;
+        const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int64_t idx = idx0 + k;
+            if (idx < 0 || (uint64_t)idx >= len) continue;
+            const uint32_t ch = (cw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            if ((ch - '0') <= 9u) {
+                val = val * 10 + (ch - '0');
+                ++nd;
+                prev_nondigit = false;
+                if ((uint64_t)idx == len - 1) bad = true;  // the CIGAR ends inside a number
+            } else {
+                if (prev_nondigit || nd > 18) bad = true;  // op of 2+ chars, missing length, or a 19+ digit length
+                if (ch == 'M' || ch == '=') c_m += val;
+                else if (ch == 'X') c_x += val;
+                else if (ch == 'I') { c_i += val; ++e_i; }
+                else if (ch == 'D') { c_d += val; ++e_d; }
+                else bad = true;
+                val = 0;
+                nd = 0;
+                prev_nondigit = true;
+            }
+        }
+    }
+    bad = __any_sync(0xFFFFFFFFu, bad);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        c_m += __shfl_xor_sync(0xFFFFFFFFu, c_m, d); c_x += __shfl_xor_sync(0xFFFFFFFFu, c_x, d);
+        c_i += __shfl_xor_sync(0xFFFFFFFFu, c_i, d); c_d += __shfl_xor_sync(0xFFFFFFFFu, c_d, d);
+        e_i += __shfl_xor_sync(0xFFFFFFFFu, e_i, d); e_d += __shfl_xor_sync(0xFFFFFFFFu, e_d, d);
+    }
+    if (lane == 0) {
+        slow[r] = bad ? 1 : 0;
+        if (!bad) {
+            const bool neg = negf == 1;
+            unsigned long long *o = cnt11 + r * 11;
+            o[0] = c_m; o[1] = c_x;
+            o[2] = neg ? 0 : e_i; o[3] = neg ? 0 : c_i; o[4] = neg ? 0 : e_d; o[5] = neg ? 0 : c_d;
+            o[6] = neg ? e_i : 0; o[7] = neg ? c_i : 0; o[8] = neg ? e_d : 0; o[9] = neg ? c_d : 0;
+            o[10] = neg ? 1 : 0;
+        }
+    }
+}
+
+// Exact path, one record per thread: the tokenizer of cigar.rs:43-75 with the reference's errors.  only != nullptr:
+// just the records the warp kernel flagged.
 __global__ void k_paf_cigar_counts(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
-                                   unsigned long long *__restrict__ cnt11, unsigned long long *err_key) {
+                                   unsigned long long *__restrict__ cnt11, unsigned long long *err_key,
+                                   const uint8_t *__restrict__ only) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
+    if (only && !only[r]) return;
     unsigned long long *o = cnt11 + r * 11;
     unsigned long long c_m = 0, c_x = 0, c_ie = 0, c_i = 0, c_de = 0, c_d = 0;
     const uint8_t negf = R.neg[r];

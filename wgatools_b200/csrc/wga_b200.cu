@@ -1045,7 +1045,10 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     R.q_size = m4; R.t_size = m4 + n_rec; R.q_start = m4 + 2 * n_rec; R.t_start = m4 + 3 * n_rec;
     LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key, err_key);
     WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key);
+    uint8_t *slow = ctx->buf<uint8_t>(B_RUN_CLS, n_rec);
+    if (!slow) return ctx->err_code;
+    LAUNCH(ctx, k_paf_cigar_counts_warp, grid_for(n_rec * 32, 256), 256, n_rec, d_text, R, cnt11, slow);
+    LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key, (const uint8_t *)slow);
     WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     uint64_t key;
     WGA_TRY(read_scalars(ctx, {err_key}, &key));
