@@ -471,6 +471,44 @@ def test_paf_stat_synthetic(w, ctx, seed, kw):
     assert len(cnt) == n
 
 
+def test_paf_stat_long_numbers_all_alignments(w, ctx):
+    """lengths of 1..20 digits crossing the 16-byte pieces of the warp kernel at every alignment; 10+ digit lengths,
+    malformed tokens and overflowing numbers take the exact path (per-record counters compared too)"""
+    rng = random.Random(5)
+    lines, cgs = [], []
+    for i in range(600):
+        ops = []
+        for _ in range(rng.randrange(1, 40)):
+            nd = rng.choice([1, 1, 2, 3, 5, 8, 9, 10, 12, 15, 16, 17, 19])
+            v = rng.randrange(10 ** (nd - 1), 10 ** nd) if nd < 19 else rng.randrange(10 ** 18, 2 ** 62)
+            if rng.random() < 0.3:
+                v = b"%0*d" % (rng.randrange(nd, nd + 8), v)   # leading zeros
+            else:
+                v = b"%d" % v
+            ops.append(v + bytes([rng.choice(b"M=XID")]))
+        cg = b"".join(ops)
+        cgs.append(cg)
+        pad = b"q" * rng.randrange(1, 33)                       # shifts the CIGAR's alignment
+        lines.append(b"\t".join([pad, b"100", b"0", b"50", rng.choice([b"+", b"-"]), b"t%d" % (i % 3), b"100", b"0", b"50", b"1", b"2",
+                                 b"60", b"cg:Z:" + cg]) + b"\n")
+    text = b"".join(lines)
+    acc = w.StatAcc(True)
+    buf = ctypes.c_char_p(text)
+    ctx.paf_stat_raw(ctypes.cast(buf, ctypes.c_void_p), len(text), 0, 1, acc)
+    cnt = ctx.last_record_counts()
+    for i, cg in enumerate(cgs):
+        want = orc.paf_cigar_counts(cg, lines[i].split(b"\t")[4] == b"-")
+        assert [int(x) & (2 ** 64 - 1) for x in cnt[i]] == [int(x) & (2 ** 64 - 1) for x in want], (i, cg)
+    # one malformed token anywhere -> the reference's error, from the lowest record
+    for badcg in (b"12MM3=", b"5=7", b"3=Q4M", b"5=99999999999999999999M", b"4=5S"):
+        t2 = b"".join(lines[:7]) + lines[7].replace(b"cg:Z:" + cgs[7], b"cg:Z:" + cgs[7] + badcg) + b"".join(lines[8:20])
+        with pytest.raises(orc.OracleError) as eo:
+            orc.stat_paf(t2)
+        with pytest.raises(w.WGAError) as eg:
+            w.run_bytes(w.stat_paf, w.PAFReader(t2), ctx=ctx)
+        assert eo.value.code == eg.value.code and str(eg.value) == eo.value.msg, badcg
+
+
 # ------------------------------------------------------------------------- larger inputs (seconds of oracle time)
 def test_large_config2_exact(w, ctx):
     """100 k blocks (0.67 GB) of the bench workload: all three commands byte-identical to the oracle."""

@@ -122,10 +122,17 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
 }
 
 // CIGAR text -> the 11 counters of struct Cigar (cigar.rs:16-29), fast path: one WARP per record, lane i of a step
-// owns the aligned 16-byte piece 32*step+i.  A token belongs to the piece that holds its op char; its digits may start
-// in the previous piece, which arrives by shuffle (lane 0: the last piece of the previous step).  Anything that is not
-// `digits+ one-of(M=XID)` -- i.e. every input on which the reference raises an error, plus numbers of 17+ digits --
+// owns the aligned 16-byte piece 32*step+i.  A token belongs to the piece that holds its op char; the digits it may
+// have in the previous piece arrive afterwards as that lane's trailing (value, digit count) by shuffle (lane 0: from
+// lane 31 of the previous step) and are spliced in front of the piece's first token.  Anything that is not
+// `digits+ one-of(M=XID)` -- i.e. every input on which the reference raises an error -- and any length of 10+ digits
 // only sets slow[r]; those records are redone by the exact one-thread kernel below, which owns all error reporting.
+__device__ __forceinline__ uint32_t pow10_u32(uint32_t n) {  // n <= 9
+    uint32_t p = 1;
+#pragma unroll
+    for (uint32_t i = 0; i < 9; ++i) p *= i < n ? 10u : 1u;
+    return p;
+}
 __global__ void __launch_bounds__(256) k_paf_cigar_counts_warp(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
                                                                unsigned long long *__restrict__ cnt11, uint8_t *__restrict__ slow) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -138,80 +145,76 @@ __global__ void __launch_bounds__(256) k_paf_cigar_counts_warp(uint64_t n_rec, c
     const uint64_t a = reinterpret_cast<uintptr_t>(p) & 15u;
     const uint8_t *base = p - a;
     const uint64_t nvec = (a + len + 15) >> 4;
-    unsigned long long c_m = 0, c_x = 0, c_i = 0, c_d = 0, e_i = 0, e_d = 0;
+    unsigned long long c[4] = {0, 0, 0, 0};  // M/=, X, I, D lengths
+    uint32_t e_i = 0, e_d = 0;
     bool bad = false;
-    const uint4 colons = make_uint4(0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au);
-    uint4 carry = colons;  // the byte before a CIGAR is the ':' of "cg:Z:"
+    uint32_t carry_val = 0, carry_nd = 0;  // trailing digits of the previous step's last piece
     for (uint64_t v0 = 0; v0 < nvec; v0 += 32) {
         const uint64_t vi = v0 + lane;
         const bool have = vi < nvec;
-        const uint4 cur = have ? ldg16(base + 16 * vi) : colons;
-        uint4 prev;
-        prev.x = __shfl_up_sync(0xFFFFFFFFu, cur.x, 1); prev.y = __shfl_up_sync(0xFFFFFFFFu, cur.y, 1);
-        prev.z = __shfl_up_sync(0xFFFFFFFFu, cur.z, 1); prev.w = __shfl_up_sync(0xFFFFFFFFu, cur.w, 1);
-        if (lane == 0) prev = carry;
-        carry.x = __shfl_sync(0xFFFFFFFFu, cur.x, 31); carry.y = __shfl_sync(0xFFFFFFFFu, cur.y, 31);
-        carry.z = __shfl_sync(0xFFFFFFFFu, cur.z, 31); carry.w = __shfl_sync(0xFFFFFFFFu, cur.w, 31);
-        if (!have) continue;
-        const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;  // CIGAR index of byte 0 of this piece
-        unsigned long long val = 0;
-        uint32_t nd = 0;
-        if (idx0 > 0) {  // digits at the end of the previous piece belong to the first token that closes here
-            const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
-            bool run = true;
+        uint32_t val = 0, nd = 0;            // the number being read
+        uint32_t first_val = 0, first_nd = 0, first_cls = 4;  // first token that closes in this piece (4 = none)
+        if (have) {
+            const uint4 cur = ldg16(base + 16 * vi);
+            const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
+            const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;  // CIGAR index of byte 0 of this piece
+            bool prev_op = false;  // the previous byte of this piece was an op char
 #pragma unroll
-            for (int j = 15; j >= 0; --j) {
-                const uint32_t ch = (pw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                run = run && (ch - '0') <= 9u;
-                nd += run ? 1u : 0u;
-            }
-            if (nd == 16) bad = true;  // the number started even earlier
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t ch = (pw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                if (j >= 16 - (int)nd) val = val * 10 + (ch - '0');
+            for (int k = 0; k < 16; ++k) {
+                const int64_t idx = idx0 + k;
+                if (idx < 0 || (uint64_t)idx >= len) continue;
+                const uint32_t ch = (cw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                const uint32_t dg = ch - '0';
+                if (dg <= 9u) {
+                    val = val * 10 + dg;
+                    ++nd;
+                    prev_op = false;
+                    if ((uint64_t)idx == len - 1) bad = true;  // the CIGAR ends inside a number
+                } else {
+                    const uint32_t cls = (ch == 'M' || ch == '=') ? 0u : ch == 'X' ? 1u : ch == 'I' ? 2u : ch == 'D' ? 3u : 4u;
+                    if (cls == 4u || prev_op || nd > 9u || (nd == 0 && idx == 0)) bad = true;
+                    if (first_cls == 4u) { first_val = val; first_nd = nd; first_cls = cls; }
+                    else {
+                        c[0] += cls == 0u ? val : 0u; c[1] += cls == 1u ? val : 0u;
+                        c[2] += cls == 2u ? val : 0u; c[3] += cls == 3u ? val : 0u;
+                    }
+                    e_i += cls == 2u; e_d += cls == 3u;
+                    val = 0; nd = 0;
+                    prev_op = true;
+                }
             }
         }
-        bool prev_nondigit = nd == 0;
-        const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int64_t idx = idx0 + k;
-            if (idx < 0 || (uint64_t)idx >= len) continue;
-            const uint32_t ch = (cw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            if ((ch - '0') <= 9u) {
-                val = val * 10 + (ch - '0');
-                ++nd;
-                prev_nondigit = false;
-                if ((uint64_t)idx == len - 1) bad = true;  // the CIGAR ends inside a number
-            } else {
-                if (prev_nondigit || nd > 18) bad = true;  // op of 2+ chars, missing length, or a 19+ digit length
-                if (ch == 'M' || ch == '=') c_m += val;
-                else if (ch == 'X') c_x += val;
-                else if (ch == 'I') { c_i += val; ++e_i; }
-                else if (ch == 'D') { c_d += val; ++e_d; }
-                else bad = true;
-                val = 0;
-                nd = 0;
-                prev_nondigit = true;
-            }
+        // trailing digits of the piece to the left
+        uint32_t lv = __shfl_up_sync(0xFFFFFFFFu, val, 1), ln = __shfl_up_sync(0xFFFFFFFFu, nd, 1);
+        if (lane == 0) { lv = carry_val; ln = carry_nd; }
+        carry_val = __shfl_sync(0xFFFFFFFFu, val, 31);
+        carry_nd = __shfl_sync(0xFFFFFFFFu, nd, 31);
+        if (have) {
+            if (first_cls != 4u) {
+                // no digits on either side of the boundary (op after op), or a length of 10+ digits
+                if (first_nd + ln == 0 || first_nd + ln > 9u) bad = true;
+                const unsigned long long full = (unsigned long long)lv * pow10_u32(first_nd > 9u ? 9u : first_nd) + first_val;
+                c[0] += first_cls == 0u ? full : 0ull; c[1] += first_cls == 1u ? full : 0ull;
+                c[2] += first_cls == 2u ? full : 0ull; c[3] += first_cls == 3u ? full : 0ull;
+            } else if (ln) bad = true;  // a number of 17+ digits runs through this piece
         }
     }
     bad = __any_sync(0xFFFFFFFFu, bad);
+    unsigned long long ei = e_i, ed = e_d;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
-        c_m += __shfl_xor_sync(0xFFFFFFFFu, c_m, d); c_x += __shfl_xor_sync(0xFFFFFFFFu, c_x, d);
-        c_i += __shfl_xor_sync(0xFFFFFFFFu, c_i, d); c_d += __shfl_xor_sync(0xFFFFFFFFu, c_d, d);
-        e_i += __shfl_xor_sync(0xFFFFFFFFu, e_i, d); e_d += __shfl_xor_sync(0xFFFFFFFFu, e_d, d);
+        c[0] += __shfl_xor_sync(0xFFFFFFFFu, c[0], d); c[1] += __shfl_xor_sync(0xFFFFFFFFu, c[1], d);
+        c[2] += __shfl_xor_sync(0xFFFFFFFFu, c[2], d); c[3] += __shfl_xor_sync(0xFFFFFFFFu, c[3], d);
+        ei += __shfl_xor_sync(0xFFFFFFFFu, ei, d); ed += __shfl_xor_sync(0xFFFFFFFFu, ed, d);
     }
     if (lane == 0) {
         slow[r] = bad ? 1 : 0;
         if (!bad) {
             const bool neg = negf == 1;
             unsigned long long *o = cnt11 + r * 11;
-            o[0] = c_m; o[1] = c_x;
-            o[2] = neg ? 0 : e_i; o[3] = neg ? 0 : c_i; o[4] = neg ? 0 : e_d; o[5] = neg ? 0 : c_d;
-            o[6] = neg ? e_i : 0; o[7] = neg ? c_i : 0; o[8] = neg ? e_d : 0; o[9] = neg ? c_d : 0;
+            o[0] = c[0]; o[1] = c[1];
+            o[2] = neg ? 0 : ei; o[3] = neg ? 0 : c[2]; o[4] = neg ? 0 : ed; o[5] = neg ? 0 : c[3];
+            o[6] = neg ? ei : 0; o[7] = neg ? c[2] : 0; o[8] = neg ? ed : 0; o[9] = neg ? c[3] : 0;
             o[10] = neg ? 1 : 0;
         }
     }
