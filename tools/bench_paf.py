@@ -120,8 +120,11 @@ def main():
         args.records = 1000
     paf = bs.gen_paf(bs.paf_params(args.records, seed=20260928))
     d = resident(paf)
-    buf, hp = ctypes.c_char_p(paf), None
-    hp = ctypes.cast(buf, ctypes.c_void_p).value
+    def pinned_copy(data):  # pinned host memory: the e2e leg should see PCIe, not a pageable staging copy
+        ptr = L.wga_host_alloc(len(data) + 64)
+        ctypes.memmove(ptr, data, len(data))
+        return ptr
+    hp = pinned_copy(paf)
 
     def st_dev():
         acc = w.StatAcc(False)
@@ -150,8 +153,7 @@ def main():
                                     ops_median=150.0, ops_max=2000))
     paf5 = dedupe_ties(paf5)
     d5 = resident(paf5)
-    buf5 = ctypes.c_char_p(paf5)
-    hp5 = ctypes.cast(buf5, ctypes.c_void_p).value
+    hp5 = pinned_copy(paf5)
     sp, sp2 = w.api.Span(), w.api.Span()
     outn = {}
 

@@ -122,16 +122,15 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
 }
 
 // CIGAR text -> the 11 counters of struct Cigar (cigar.rs:16-29), fast path: one WARP per record, lane i of a step
-// owns the aligned 16-byte piece 32*step+i.  A token belongs to the piece that holds its op char; the digits it may
-// have in the previous piece arrive afterwards as that lane's trailing (value, digit count) by shuffle (lane 0: from
-// lane 31 of the previous step) and are spliced in front of the piece's first token.  Anything that is not
-// `digits+ one-of(M=XID)` -- i.e. every input on which the reference raises an error -- and any length of 10+ digits
+// owns the aligned 16-byte piece 32*step+i.  A token belongs to the piece that holds its op char.  Phase 1 (SWAR):
+// every lane parses the digit run at the END of its piece (<= 8 digits: flag words + the 3-multiply 8-digit parse)
+// and hands (value, digits) to the lane on its right by shuffle (lane 31 -> lane 0 of the next step).  Phase 2: a
+// branch-free pass over the 16 bytes that starts from the left neighbour's trailing number.  Anything that is not
+// `digits+ one-of(M=XID)` -- i.e. every input on which the reference raises an error -- and any length of 9+ digits
 // only sets slow[r]; those records are redone by the exact one-thread kernel below, which owns all error reporting.
-__device__ __forceinline__ uint32_t pow10_u32(uint32_t n) {  // n <= 9
-    uint32_t p = 1;
-#pragma unroll
-    for (uint32_t i = 0; i < 9; ++i) p *= i < n ? 10u : 1u;
-    return p;
+__device__ __forceinline__ uint32_t digit_flags(uint32_t w) {  // bit 7 of every byte in '0'..'9'
+    const uint32_t x = w ^ 0x30303030u;
+    return ~(((x & 0x7F7F7F7Fu) + 0x76767676u) | x) & 0x80808080u;
 }
 __global__ void __launch_bounds__(256) k_paf_cigar_counts_warp(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
                                                                unsigned long long *__restrict__ cnt11, uint8_t *__restrict__ slow) {
@@ -145,66 +144,66 @@ __global__ void __launch_bounds__(256) k_paf_cigar_counts_warp(uint64_t n_rec, c
     const uint64_t a = reinterpret_cast<uintptr_t>(p) & 15u;
     const uint8_t *base = p - a;
     const uint64_t nvec = (a + len + 15) >> 4;
-    unsigned long long c[4] = {0, 0, 0, 0};  // M/=, X, I, D lengths
+    unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;  // M/=, X, I, D lengths
     uint32_t e_i = 0, e_d = 0;
     bool bad = false;
-    uint32_t carry_val = 0, carry_nd = 0;  // trailing digits of the previous step's last piece
+    uint32_t carry_val = 0, carry_nd = 0;  // trailing number of the previous step's last piece
     for (uint64_t v0 = 0; v0 < nvec; v0 += 32) {
         const uint64_t vi = v0 + lane;
         const bool have = vi < nvec;
-        uint32_t val = 0, nd = 0;            // the number being read
-        uint32_t first_val = 0, first_nd = 0, first_cls = 4;  // first token that closes in this piece (4 = none)
-        if (have) {
-            const uint4 cur = ldg16(base + 16 * vi);
-            const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
-            const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;  // CIGAR index of byte 0 of this piece
-            bool prev_op = false;  // the previous byte of this piece was an op char
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int64_t idx = idx0 + k;
-                if (idx < 0 || (uint64_t)idx >= len) continue;
-                const uint32_t ch = (cw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-                const uint32_t dg = ch - '0';
-                if (dg <= 9u) {
-                    val = val * 10 + dg;
-                    ++nd;
-                    prev_op = false;
-                    if ((uint64_t)idx == len - 1) bad = true;  // the CIGAR ends inside a number
-                } else {
-                    const uint32_t cls = (ch == 'M' || ch == '=') ? 0u : ch == 'X' ? 1u : ch == 'I' ? 2u : ch == 'D' ? 3u : 4u;
-                    if (cls == 4u || prev_op || nd > 9u || (nd == 0 && idx == 0)) bad = true;
-                    if (first_cls == 4u) { first_val = val; first_nd = nd; first_cls = cls; }
-                    else {
-                        c[0] += cls == 0u ? val : 0u; c[1] += cls == 1u ? val : 0u;
-                        c[2] += cls == 2u ? val : 0u; c[3] += cls == 3u ? val : 0u;
-                    }
-                    e_i += cls == 2u; e_d += cls == 3u;
-                    val = 0; nd = 0;
-                    prev_op = true;
-                }
+        uint4 cur = make_uint4(0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au);
+        if (have) cur = ldg16(base + 16 * vi);
+        // ---- phase 1: digit run at the end of the piece
+        uint32_t t_nd, t_val = 0;
+        {
+            const unsigned long long F = ((unsigned long long)digit_flags(cur.w) << 32) | digit_flags(cur.z);
+            const unsigned long long nF = ~F & 0x8080808080808080ull;
+            t_nd = nF ? (uint32_t)__clzll((long long)nF) >> 3 : 8u;
+            if (t_nd == 8u && (digit_flags(cur.y) & 0x80000000u)) t_nd = 9u;  // longer than the window: flagged by the consumer
+            if (t_nd) {
+                const unsigned long long H = ((unsigned long long)cur.w << 32) | cur.z;
+                const unsigned long long keep = t_nd >= 8u ? ~0ull : ~0ull << (8u * (8u - t_nd));
+                unsigned long long v = ((H & keep) | (0x3030303030303030ull & ~keep)) - 0x3030303030303030ull;
+                v = v * 10 + (v >> 8);
+                v = (((v & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((v >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
+                t_val = (uint32_t)v;
             }
         }
-        // trailing digits of the piece to the left
-        uint32_t lv = __shfl_up_sync(0xFFFFFFFFu, val, 1), ln = __shfl_up_sync(0xFFFFFFFFu, nd, 1);
-        if (lane == 0) { lv = carry_val; ln = carry_nd; }
-        carry_val = __shfl_sync(0xFFFFFFFFu, val, 31);
-        carry_nd = __shfl_sync(0xFFFFFFFFu, nd, 31);
-        if (have) {
-            if (first_cls != 4u) {
-                // no digits on either side of the boundary (op after op), or a length of 10+ digits
-                if (first_nd + ln == 0 || first_nd + ln > 9u) bad = true;
-                const unsigned long long full = (unsigned long long)lv * pow10_u32(first_nd > 9u ? 9u : first_nd) + first_val;
-                c[0] += first_cls == 0u ? full : 0ull; c[1] += first_cls == 1u ? full : 0ull;
-                c[2] += first_cls == 2u ? full : 0ull; c[3] += first_cls == 3u ? full : 0ull;
-            } else if (ln) bad = true;  // a number of 17+ digits runs through this piece
+        uint32_t val = __shfl_up_sync(0xFFFFFFFFu, t_val, 1), nd = __shfl_up_sync(0xFFFFFFFFu, t_nd, 1);
+        if (lane == 0) { val = carry_val; nd = carry_nd; }
+        carry_val = __shfl_sync(0xFFFFFFFFu, t_val, 31);
+        carry_nd = __shfl_sync(0xFFFFFFFFu, t_nd, 31);
+        if (!have) continue;
+        // ---- phase 2: the 16 bytes, branch-free
+        const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;  // CIGAR index of byte 0 of this piece
+        const int klo = idx0 < 0 ? (int)-idx0 : 0;
+        const int khi = (uint64_t)(idx0 + 16) > len ? (int)((int64_t)len - idx0) : 16;
+        if (idx0 <= 0) { val = 0; nd = 0; }  // nothing belongs to the CIGAR on the left of its first piece
+        const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
+        uint32_t am = 0, ax = 0, ai = 0, ad = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t ch = (cw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            const uint32_t dg = ch - '0';
+            const bool in = k >= klo && k < khi;
+            const bool isd = in && dg <= 9u, iso = in && dg > 9u;
+            const bool m = ch == 'M' || ch == '=', x = ch == 'X', ii = ch == 'I', dd = ch == 'D';
+            bad = bad || (iso && (nd == 0u || nd > 8u || !(m || x || ii || dd)));
+            am += (iso && m) ? val : 0u; ax += (iso && x) ? val : 0u;
+            ai += (iso && ii) ? val : 0u; ad += (iso && dd) ? val : 0u;
+            e_i += (iso && ii) ? 1u : 0u; e_d += (iso && dd) ? 1u : 0u;
+            val = isd ? val * 10u + dg : (iso ? 0u : val);
+            nd = isd ? nd + 1u : (iso ? 0u : nd);
         }
+        if ((uint64_t)(idx0 + 16) >= len && nd != 0u) bad = true;  // the CIGAR ends inside a number
+        c0 += am; c1 += ax; c2 += ai; c3 += ad;
     }
     bad = __any_sync(0xFFFFFFFFu, bad);
     unsigned long long ei = e_i, ed = e_d;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
-        c[0] += __shfl_xor_sync(0xFFFFFFFFu, c[0], d); c[1] += __shfl_xor_sync(0xFFFFFFFFu, c[1], d);
-        c[2] += __shfl_xor_sync(0xFFFFFFFFu, c[2], d); c[3] += __shfl_xor_sync(0xFFFFFFFFu, c[3], d);
+        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, d); c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, d);
+        c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, d); c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, d);
         ei += __shfl_xor_sync(0xFFFFFFFFu, ei, d); ed += __shfl_xor_sync(0xFFFFFFFFu, ed, d);
     }
     if (lane == 0) {
@@ -212,9 +211,9 @@ __global__ void __launch_bounds__(256) k_paf_cigar_counts_warp(uint64_t n_rec, c
         if (!bad) {
             const bool neg = negf == 1;
             unsigned long long *o = cnt11 + r * 11;
-            o[0] = c[0]; o[1] = c[1];
-            o[2] = neg ? 0 : ei; o[3] = neg ? 0 : c[2]; o[4] = neg ? 0 : ed; o[5] = neg ? 0 : c[3];
-            o[6] = neg ? ei : 0; o[7] = neg ? c[2] : 0; o[8] = neg ? ed : 0; o[9] = neg ? c[3] : 0;
+            o[0] = c0; o[1] = c1;
+            o[2] = neg ? 0 : ei; o[3] = neg ? 0 : c2; o[4] = neg ? 0 : ed; o[5] = neg ? 0 : c3;
+            o[6] = neg ? ei : 0; o[7] = neg ? c2 : 0; o[8] = neg ? ed : 0; o[9] = neg ? c3 : 0;
             o[10] = neg ? 1 : 0;
         }
     }

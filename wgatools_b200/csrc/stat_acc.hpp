@@ -34,7 +34,25 @@ struct wga_stat_acc {
         k.append((const char *)&qs, 8);
         return k;
     }
+    // the key -> row map is only needed once a SECOND table is merged in (another slab, an imported blob); the first
+    // table is bulk-loaded without it
+    void ensure_index() {
+        if (index.size() == rows.size()) return;
+        index.clear();
+        index.reserve(rows.size() * 2);
+        for (uint32_t i = 0; i < rows.size(); ++i)
+            index.emplace(key_of(rows[i].ref_name, rows[i].ref_size, rows[i].query_name, rows[i].query_size), i);
+    }
+    uint32_t add_new(const char *rn, size_t lr, uint64_t rs, const char *qn, size_t lq, uint64_t qs) {
+        rows.emplace_back();
+        Row &r = rows.back();
+        r.ref_name.assign(rn, lr); r.query_name.assign(qn, lq); r.ref_size = rs; r.query_size = qs;
+        r.v[11] = rs;  // stat.rs:186,189: minima start at the sizes
+        r.v[12] = qs;
+        return (uint32_t)rows.size() - 1;
+    }
     uint32_t find_or_add(const std::string &rn, uint64_t rs, const std::string &qn, uint64_t qs) {
+        ensure_index();
         std::string k = key_of(rn, rs, qn, qs);
         auto it = index.find(k);
         if (it != index.end()) return it->second;

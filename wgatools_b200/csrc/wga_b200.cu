@@ -761,15 +761,21 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_first[a] < h_first[b]; });
         std::vector<uint64_t> name_pos(2 * n_pairs + 1, 0);
         for (uint64_t i = 0; i < 2 * n_pairs; ++i) name_pos[i + 1] = name_pos[i] + h_nlen[i];
+        const bool bulk = acc->rows.empty();  // first table: every pair is new, no key map needed
+        if (bulk) acc->rows.reserve(n_pairs);
         for (uint32_t p : order) {
-            std::string rn(h_names.data() + name_pos[2 * p], h_nlen[2 * p]);
-            std::string qn(h_names.data() + name_pos[2 * p + 1], h_nlen[2 * p + 1]);
-            map[p] = acc->find_or_add(rn, h_sizes[2 * p], qn, h_sizes[2 * p + 1]);
+            const char *rn = h_names.data() + name_pos[2 * p], *qn = h_names.data() + name_pos[2 * p + 1];
+            if (bulk) map[p] = acc->add_new(rn, h_nlen[2 * p], h_sizes[2 * p], qn, h_nlen[2 * p + 1], h_sizes[2 * p + 1]);
+            else map[p] = acc->find_or_add(std::string(rn, h_nlen[2 * p]), h_sizes[2 * p], std::string(qn, h_nlen[2 * p + 1]),
+                                           h_sizes[2 * p + 1]);
             acc->add_pair_vals(map[p], &h_vals[(uint64_t)p * kPairVals]);
         }
+        const size_t i0 = acc->inv_pair.size();
+        acc->inv_pair.resize(i0 + n_inv);
+        acc->inv_num.resize(i0 + n_inv);
         for (uint64_t i = 0; i < n_inv; ++i) {
-            acc->inv_pair.push_back(map[h_inv_pair[i]]);
-            acc->inv_num.push_back(h_inv_num[i]);
+            acc->inv_pair[i0 + i] = map[h_inv_pair[i]];
+            acc->inv_num[i0 + i] = h_inv_num[i];
         }
         return WGA_OK;
     }
