@@ -2,6 +2,10 @@
 #include <algorithm>
 #include <numeric>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "ctx.cuh"
 #include "emit_paf.cuh"
 #include "stat.cuh"
@@ -686,6 +690,14 @@ namespace {
 // shared tail of stat_maf / stat_paf: pair reduction on the device, merge into the host accumulator
 int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned long long *cnt11,
                 unsigned long long *err_key, wga_stat_acc *acc) {
+    static const bool dbg = getenv("WGA_DEBUG_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!dbg) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[stat_reduce] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     std::vector<uint64_t> h_first, h_vals, h_sizes, h_inv_num;
     std::vector<uint32_t> h_nlen, h_inv_pair;
     std::vector<char> h_names;
@@ -718,6 +730,7 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         WGA_CK(cudaMemcpyAsync(ctx->h_scal + 1, iidx + n_rec, 8, cudaMemcpyDeviceToHost, ctx->stream));
         WGA_CK(cudaMemcpyAsync(ctx->h_scal + 2, err_key, 8, cudaMemcpyDeviceToHost, ctx->stream));
         WGA_TRY(sync_check(ctx));
+        lap("table build + sync");
         n_pairs = *(uint32_t *)ctx->h_scal;
         n_inv = ctx->h_scal[1];
         if (ctx->h_scal[2] != kNoErr) {
@@ -755,12 +768,14 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
             WGA_CK(cudaMemcpyAsync(h_inv_num.data(), inv_num, n_inv * 8, cudaMemcpyDeviceToHost, ctx->stream));
         }
         WGA_TRY(sync_check(ctx));
+        lap("gather + D2H");
         // merge in first-occurrence order (the reference's HashMap order is unspecified; natord sort is stable)
         std::vector<uint32_t> order(n_pairs), map(n_pairs);
         std::iota(order.begin(), order.end(), 0u);
         std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_first[a] < h_first[b]; });
         std::vector<uint64_t> name_pos(2 * n_pairs + 1, 0);
         for (uint64_t i = 0; i < 2 * n_pairs; ++i) name_pos[i + 1] = name_pos[i] + h_nlen[i];
+        lap("order sort");
         const bool bulk = acc->rows.empty();  // first table: every pair is new, no key map needed
         if (bulk) acc->rows.reserve(n_pairs);
         for (uint32_t p : order) {
@@ -777,6 +792,7 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
             acc->inv_pair[i0 + i] = map[h_inv_pair[i]];
             acc->inv_num[i0 + i] = h_inv_num[i];
         }
+        lap("host merge");
         return WGA_OK;
     }
     // --each: one row per record (stat.rs:129-164)
