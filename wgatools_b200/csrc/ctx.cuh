@@ -128,6 +128,23 @@ struct wga_ctx {
     T *buf(wga::BufId id, size_t count) {
         return (T *)ensure(id, count * sizeof(T));
     }
+    // pinned scratch for table-sized D2H reads (pageable destinations go through a slow staging copy)
+    void *h_scratch = nullptr;
+    size_t h_scratch_cap = 0;
+    void *ensure_host_scratch(size_t bytes) {
+        if (h_scratch_cap >= bytes && h_scratch) return h_scratch;
+        if (h_scratch) cudaFreeHost(h_scratch);
+        h_scratch = nullptr;
+        size_t want = bytes + bytes / 4 + 4096;
+        if (cudaHostAlloc(&h_scratch, want, cudaHostAllocDefault) != cudaSuccess) {
+            h_scratch = nullptr;
+            h_scratch_cap = 0;
+            set_error(WGA_E_NOMEM, 0, "cudaHostAlloc failed for host scratch");
+            return nullptr;
+        }
+        h_scratch_cap = want;
+        return h_scratch;
+    }
     void *ensure_host_out(size_t bytes) {
         if (h_out_cap >= bytes && h_out) return h_out;
         if (h_out) cudaFreeHost(h_out);

@@ -458,6 +458,7 @@ void wga_ctx_destroy(wga_ctx *ctx) {
     for (auto &b : ctx->bufs)
         if (b.p) cudaFree(b.p);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -754,32 +755,48 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         if (!nbuf) return ctx->err_code;
         LAUNCH(ctx, k_pair_names, grid_for(2 * n_pairs, 256), 256, n_pairs, p_first, M, noff, nbuf);
         LAUNCH(ctx, k_inv_gather, grid_for(n_rec, 256), 256, n_rec, iflag, iidx, rec_slot, idx, cnt11, inv_pair, inv_num);
-        h_first.resize(n_pairs); h_vals.resize(n_pairs * kPairVals); h_sizes.resize(n_pairs * 2);
-        h_nlen.resize(2 * n_pairs); h_names.resize(name_total + 1); h_inv_pair.resize(n_inv); h_inv_num.resize(n_inv);
+        // pairs in first-occurrence order (the reference's HashMap order is unspecified; natord sort is stable):
+        // sort (first record, pair id) on the device, read everything back through pinned scratch
+        uint64_t *ord_k = ctx->buf<uint64_t>(B_PP_A, n_pairs + 1), *ord_v = ctx->buf<uint64_t>(B_PP_B, n_pairs + 1);
+        uint64_t *ord_i = ctx->buf<uint64_t>(B_PP_C, n_pairs + 1);
+        if (!ord_k || !ord_v || !ord_i) return ctx->err_code;
         if (n_pairs) {
-            WGA_CK(cudaMemcpyAsync(h_first.data(), p_first, n_pairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            WGA_CK(cudaMemcpyAsync(h_vals.data(), p_vals, n_pairs * kPairVals * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            WGA_CK(cudaMemcpyAsync(h_sizes.data(), p_sizes, n_pairs * 16, cudaMemcpyDeviceToHost, ctx->stream));
-            WGA_CK(cudaMemcpyAsync(h_nlen.data(), nlen, n_pairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            if (name_total) WGA_CK(cudaMemcpyAsync(h_names.data(), nbuf, name_total, cudaMemcpyDeviceToHost, ctx->stream));
+            LAUNCH(ctx, k_iota, grid_for(n_pairs, 256), 256, ord_i, n_pairs);
+            WGA_TRY(sort_pairs_u64(ctx, p_first, ord_k, ord_i, ord_v, n_pairs));
+        }
+        const size_t b_vals = n_pairs * kPairVals * 8, b_sizes = n_pairs * 16, b_nlen = n_pairs * 8, b_ord = n_pairs * 8;
+        const size_t b_invp = (n_inv * 4 + 7) & ~(size_t)7, b_invn = n_inv * 8;
+        const size_t o_vals = 0, o_sizes = o_vals + b_vals, o_nlen = o_sizes + b_sizes, o_ord = o_nlen + b_nlen, o_invp = o_ord + b_ord,
+                     o_invn = o_invp + b_invp, o_names = o_invn + b_invn;
+        char *hs = (char *)ctx->ensure_host_scratch(o_names + name_total + 8);
+        if (!hs) return ctx->err_code;
+        if (n_pairs) {
+            WGA_CK(cudaMemcpyAsync(hs + o_vals, p_vals, b_vals, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_sizes, p_sizes, b_sizes, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_nlen, nlen, b_nlen, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_ord, ord_v, b_ord, cudaMemcpyDeviceToHost, ctx->stream));
+            if (name_total) WGA_CK(cudaMemcpyAsync(hs + o_names, nbuf, name_total, cudaMemcpyDeviceToHost, ctx->stream));
         }
         if (n_inv) {
-            WGA_CK(cudaMemcpyAsync(h_inv_pair.data(), inv_pair, n_inv * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            WGA_CK(cudaMemcpyAsync(h_inv_num.data(), inv_num, n_inv * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_invp, inv_pair, n_inv * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_invn, inv_num, n_inv * 8, cudaMemcpyDeviceToHost, ctx->stream));
         }
         WGA_TRY(sync_check(ctx));
-        lap("gather + D2H");
-        // merge in first-occurrence order (the reference's HashMap order is unspecified; natord sort is stable)
-        std::vector<uint32_t> order(n_pairs), map(n_pairs);
-        std::iota(order.begin(), order.end(), 0u);
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_first[a] < h_first[b]; });
+        lap("gather + sort + D2H");
+        const uint64_t *h_vals = (const uint64_t *)(hs + o_vals), *h_sizes = (const uint64_t *)(hs + o_sizes);
+        const uint32_t *h_nlen = (const uint32_t *)(hs + o_nlen);
+        const uint64_t *order = (const uint64_t *)(hs + o_ord);
+        const uint32_t *h_inv_pair = (const uint32_t *)(hs + o_invp);
+        const uint64_t *h_inv_num = (const uint64_t *)(hs + o_invn);
+        const char *h_names = hs + o_names;
+        std::vector<uint32_t> map(n_pairs);
         std::vector<uint64_t> name_pos(2 * n_pairs + 1, 0);
         for (uint64_t i = 0; i < 2 * n_pairs; ++i) name_pos[i + 1] = name_pos[i] + h_nlen[i];
-        lap("order sort");
         const bool bulk = acc->rows.empty();  // first table: every pair is new, no key map needed
         if (bulk) acc->rows.reserve(n_pairs);
-        for (uint32_t p : order) {
-            const char *rn = h_names.data() + name_pos[2 * p], *qn = h_names.data() + name_pos[2 * p + 1];
+        for (uint64_t oi = 0; oi < n_pairs; ++oi) {
+            const uint32_t p = (uint32_t)order[oi];
+            const char *rn = h_names + name_pos[2 * p], *qn = h_names + name_pos[2 * p + 1];
             if (bulk) map[p] = acc->add_new(rn, h_nlen[2 * p], h_sizes[2 * p], qn, h_nlen[2 * p + 1], h_sizes[2 * p + 1]);
             else map[p] = acc->find_or_add(std::string(rn, h_nlen[2 * p]), h_sizes[2 * p], std::string(qn, h_nlen[2 * p + 1]),
                                            h_sizes[2 * p + 1]);
