@@ -103,6 +103,28 @@ def make_workload(blocks, seed, pinned_alloc):
     return keep, nbytes, ncols
 
 
+def bind_to_gpu_numa(dev):
+    """pin this rank to the CPUs of its GPU's NUMA node (so that the pinned MAF buffer is allocated and first touched
+    there): at N=8 every rank streams ~52 GB/s over PCIe and a remote-socket buffer would go through UPI.
+    Best effort: returns the node or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(dev)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_sample_len(host_ptr, nbytes, want, L=None):
     """largest safe cut <= want bytes (whole MAF blocks only)"""
     if want >= nbytes:
@@ -197,6 +219,8 @@ def main():
     import wgatools_b200 as w
     from wgatools_b200._lib import CallOpts
     dev = torch.cuda.current_device()
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(dev)   # pinned input buffers must live on the socket the GPU hangs off
     stream = torch.cuda.current_stream().cuda_stream
     ctx = w.Context(dev, stream)
     L = ctx.L
@@ -335,9 +359,10 @@ def main():
                          "frac": achieved / peak if peak else None, "traffic": walk_traffic(args.blocks),
                          "launches": walk["launches"], "avg_launch_ms": walk["ms"] / max(walk["launches"], 1),
                          "alg_bytes_per_launch": walk["bytes"] / max(walk["launches"], 1)},
-            "input_bytes_per_gpu": nbytes, "columns_per_gpu": ncols, "gen_seconds": t_gen}
+            "input_bytes_per_gpu": nbytes, "columns_per_gpu": ncols, "gen_seconds": t_gen, "numa_node": numa}
     if rank == 0:
         if world == 1:
+            os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core back
             cores = os.cpu_count() or 1
             gbs, n, dt = run_cpu(host_ptr, nbytes, args.cpu_sample_mb * 1e6, cores, do_call)
             line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",

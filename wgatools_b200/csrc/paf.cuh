@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t digit_flags(uint32_t w) {  // bit 7 of every
     const uint32_t x = w ^ 0x30303030u;
     return ~(((x & 0x7F7F7F7Fu) + 0x76767676u) | x) & 0x80808080u;
 }
-__global__ void __launch_bounds__(256) k_paf_cigar_counts_warp(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
+__global__ void __launch_bounds__(128, 8) k_paf_cigar_counts_warp(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
                                                                unsigned long long *__restrict__ cnt11, uint8_t *__restrict__ slow) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;

@@ -1086,7 +1086,7 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     uint8_t *slow = ctx->buf<uint8_t>(B_RUN_CLS, n_rec);
     if (!slow) return ctx->err_code;
-    LAUNCH(ctx, k_paf_cigar_counts_warp, grid_for(n_rec * 32, 256), 256, n_rec, d_text, R, cnt11, slow);
+    LAUNCH(ctx, k_paf_cigar_counts_warp, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, cnt11, slow);
     LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key, (const uint8_t *)slow);
     WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     uint64_t key;
