@@ -25,6 +25,7 @@
 
 namespace wga {
 
+#ifndef WGA_WALK_NO_SPARSE  // the non-template helper kernels are defined by walk_kernels.cu only
 // rec_slot_base: exclusive scan over records of the summed capacities of their items
 __global__ void k_rec_slot_need(uint64_t n_rec, const uint32_t *__restrict__ n_items, const uint64_t *__restrict__ ncols,
                                 uint32_t shift, uint64_t *__restrict__ need) {
@@ -64,6 +65,8 @@ __global__ void k_fill_item_desc(uint64_t n_rec, const uint32_t *__restrict__ n_
     }
 }
 
+#endif  // WGA_WALK_NO_SPARSE
+
 __device__ __forceinline__ uint32_t has_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & kHi; }
 __device__ __forceinline__ int clamp16(int64_t v) { return v < 0 ? 0 : (v > 16 ? 16 : (int)v); }
 
@@ -73,7 +76,9 @@ struct WarpEmit {  // run-head emission state of the warp: the item whose slot r
 };
 
 // classify one queued chunk per lane (lanes >= cnt idle); counts -> atomics, heads -> item slots in order
-template <int MODE>
+// RECQ: the record index travels in queue field 11 (false: it is read from the item descriptor instead, which
+// saves 256 B of shared memory per warp for the TMA-staged variant)
+template <int MODE, bool RECQ = true>
 __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64], uint32_t cnt, uint32_t lane, WarpEmit &E) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
     constexpr bool RUNS = MODE != MODE_STAT;
@@ -116,7 +121,8 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
             p_eq = F[k].eq; p_x = F[k].x; p_i = F[k].i; p_d = F[k].d; p_w = F[k].w;
         }
         if (COUNTS && (cX | cI | cD)) {
-            unsigned long long *c = A.rec_cnt + (uint64_t)Q[11][lane] * 5;
+            const uint32_t rec = RECQ ? Q[11][lane] : __ldg(&A.items[item].rec);
+            unsigned long long *c = A.rec_cnt + (uint64_t)rec * 5;
             if (cX) atomicAdd(c + 0, (unsigned long long)cX);
             if (eI) atomicAdd(c + 1, (unsigned long long)eI);
             if (cI) atomicAdd(c + 2, (unsigned long long)cI);
@@ -224,7 +230,7 @@ __device__ __forceinline__ void realign(const uint4 &q0, const uint4 &q1, uint32
 }
 
 // one step (32 chunks) of the current item: 128-bit compare, push the slow chunks, run a batch when 32 are queued
-template <int MODE>
+template <int MODE, bool RECQ = true>
 __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane,
                                           const Geom &g, uint32_t j0, const Vec3 &v, uint32_t &carry) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
@@ -271,23 +277,24 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
             }
             Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | ((g.seg == 0 ? 1u : 0u) << 15) | ((16u * j + 16u - g.a) << 16);
             Q[10][slot] = g.item;
-            Q[11][slot] = g.rec;
+            if (RECQ) Q[11][slot] = g.rec;
         }
         qn += __popc(mask);
         __syncwarp();
         if (qn >= 32) {
-            walk_batch<MODE>(A, Q, 32, lane, E);
+            walk_batch<MODE, RECQ>(A, Q, 32, lane, E);
             __syncwarp();
             qn -= 32;
-            uint32_t mv[12];
+            constexpr int NF = RECQ ? 12 : 11;
+            uint32_t mv[NF];
             if (lane < qn) {
 #pragma unroll
-                for (int f = 0; f < 12; ++f) mv[f] = Q[f][lane + 32];
+                for (int f = 0; f < NF; ++f) mv[f] = Q[f][lane + 32];
             }
             __syncwarp();
             if (lane < qn) {
 #pragma unroll
-                for (int f = 0; f < 12; ++f) Q[f][lane] = mv[f];
+                for (int f = 0; f < NF; ++f) Q[f][lane] = mv[f];
             }
             __syncwarp();
         }
@@ -371,6 +378,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs 
     if (RUNS && E.open_item != 0xFFFFFFFFu && lane == 0) A.item_nheads[E.open_item] = E.open_count;
 }
 
+#ifndef WGA_WALK_NO_SPARSE
 // sparse: item slot regions -> dense run arrays (run_base = exclusive scan of item_nheads)
 __global__ void k_runs_compact(uint64_t n_items, const ItemDesc *__restrict__ items, const uint32_t *__restrict__ item_nheads,
                                const uint64_t *__restrict__ run_base, const uint32_t *__restrict__ slots,
@@ -388,5 +396,6 @@ __global__ void k_runs_compact(uint64_t n_items, const ItemDesc *__restrict__ it
         run_cls[rb + i] = (uint8_t)(e & 7u);
     }
 }
+#endif  // WGA_WALK_NO_SPARSE
 
 }  // namespace wga

@@ -1,0 +1,197 @@
+// walk_tma.cuh -- TMA-staged variant of the dense column walk (same algorithm and outputs as k_walk, walk.cuh).
+//
+// k_walk keeps its operands in registers: one step of vectors is in flight per warp plus one prefetched step, i.e.
+// ~73 KB per SM -- about what Little's law asks for at 6.5 TB/s, so the kernel idles on `long_scoreboard`
+// (profiles/r01g_walk_full_ncu.md: 50-54 % of DRAM peak).  Here every warp owns a ring of kTmaStages shared-memory
+// windows of kTmaWin chunks (target bytes + query bytes of 2 steps); one lane fills them with 1-D bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) up to kTmaStages windows ahead -- across item boundaries --
+// and the warp reads its vectors with LDS.128.  Bytes in flight: 24 warps x 3 x 2 KB = 148 KB per SM, and the 24
+// prefetch registers of k_walk are gone.
+#pragma once
+#include "walk.cuh"
+
+namespace wga {
+
+constexpr int kTmaStages = 3;
+constexpr uint32_t kTmaWin = 64;                                  // chunks per window (2 steps)
+constexpr uint32_t kTmaStageBytes = kTmaWin * 16 + kTmaWin * 16 + 16;  // T | Q (+ one vector for the realign)
+constexpr int kTmaGeoms = 4;                                      // item geometries in flight per warp
+
+struct TmaWin { uint32_t gslot, j0, cnt, pad; };
+struct __align__(16) TmaWarp {
+    uint8_t stage[kTmaStages][kTmaStageBytes];
+    Geom geom[kTmaGeoms];
+    TmaWin win[kTmaStages];
+    unsigned long long bar[kTmaStages];
+};
+struct TmaSmem {
+    uint32_t queue[kWalkWarps][11][64];
+    TmaWarp w[kWalkWarps];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk_tma(WalkArgs A) {
+    constexpr bool RUNS = MODE != MODE_STAT;
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    TmaSmem &S = *reinterpret_cast<TmaSmem *>(s_raw);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t (*Q)[64] = S.queue[wid];
+    TmaWarp &W = S.w[wid];
+    uint32_t qn = 0;
+    WarpEmit E;
+    E.open_item = 0xFFFFFFFFu;
+    E.open_count = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&W.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // dynamic scheduling as in k_walk: batches of kGrab consecutive items, the next batch requested one ahead
+    constexpr uint32_t kGrab = 8;
+    const uint32_t n_items = (uint32_t)A.n_items;
+    uint32_t s_it = 0, s_end = 0, nb_raw = 0;
+    if (lane == 0) {
+        s_it = atomicAdd(A.sched, kGrab);
+        nb_raw = atomicAdd(A.sched, kGrab);
+    }
+    s_it = __shfl_sync(0xFFFFFFFFu, s_it, 0);
+    s_end = s_it + kGrab < n_items ? s_it + kGrab : n_items;
+    auto advance = [&]() -> bool {
+        ++s_it;
+        if (s_it < s_end) return true;
+        const uint32_t nb = __shfl_sync(0xFFFFFFFFu, nb_raw, 0);
+        if (nb >= n_items) { s_it = n_items; return false; }
+        s_it = nb;
+        s_end = nb + kGrab < n_items ? nb + kGrab : n_items;
+        if (lane == 0) nb_raw = atomicAdd(A.sched, kGrab);
+        return true;
+    };
+    if (s_it >= n_items) return;
+
+    // ---- producer cursor: the item being issued lives in geometry slot p_gs (shared memory); only what issuing needs
+    //      stays in registers.  The descriptor of the item after it is already requested, one 16-byte third per lane.
+    uint32_t p_gs = 0, p_j = 0, p_nch, p_s, p_qlast;
+    const uint8_t *p_tb, *p_qb;
+    bool p_has = true, e_has;
+    uint32_t e_item;
+    uint4 ed = make_uint4(0, 0, 0, 0);
+    auto fetch_desc = [&](uint32_t item) {
+        if (lane < 3) ed = __ldg(reinterpret_cast<const uint4 *>(A.items + item) + lane);
+    };
+    auto open_item = [&](uint32_t item, uint32_t gslot) {  // descriptor thirds (lanes 0..2) -> geometry in slot gslot
+        uint4 d0, d1, d2;
+        d0.x = __shfl_sync(0xFFFFFFFFu, ed.x, 0); d0.y = __shfl_sync(0xFFFFFFFFu, ed.y, 0);
+        d0.z = __shfl_sync(0xFFFFFFFFu, ed.z, 0); d0.w = __shfl_sync(0xFFFFFFFFu, ed.w, 0);
+        d1.x = __shfl_sync(0xFFFFFFFFu, ed.x, 1); d1.y = __shfl_sync(0xFFFFFFFFu, ed.y, 1);
+        d1.z = __shfl_sync(0xFFFFFFFFu, ed.z, 1); d1.w = __shfl_sync(0xFFFFFFFFu, ed.w, 1);
+        d2.x = __shfl_sync(0xFFFFFFFFu, ed.x, 2); d2.y = __shfl_sync(0xFFFFFFFFu, ed.y, 2);
+        d2.z = d2.w = 0;
+        const Geom g = make_geom(A, d0, d1, d2, item);
+        if (lane == 0) W.geom[gslot] = g;
+        p_nch = g.nch; p_s = g.s; p_qlast = g.q_last; p_tb = g.tbase; p_qb = g.qbase;
+        p_j = 0;
+    };
+    fetch_desc(s_it);
+    open_item(s_it, 0);
+    e_has = advance();
+    e_item = s_it;
+    if (e_has) fetch_desc(e_item);
+    uint32_t n_out = 0;  // windows issued and not yet consumed
+    auto produce = [&](uint32_t stage) {
+        if (!p_has) return;
+        const uint32_t cnt = p_nch - p_j < kTmaWin ? p_nch - p_j : kTmaWin;
+        // query vectors p_j .. min(p_j + cnt, q_last): the realign of chunk j needs vector j + 1 unless s == 0
+        uint32_t qend = p_j + cnt;
+        if (p_s == 0) qend -= 1;
+        else if (qend > p_qlast) qend = p_qlast;
+        const uint32_t qcnt = qend - p_j + 1;
+        if (lane == 0) {
+            W.win[stage].gslot = p_gs; W.win[stage].j0 = p_j; W.win[stage].cnt = cnt;
+            mbar_expect_tx(&W.bar[stage], (cnt + qcnt) * 16u);
+            bulk_g2s(W.stage[stage], p_tb + 16ull * p_j, cnt * 16u, &W.bar[stage]);
+            bulk_g2s(W.stage[stage] + kTmaWin * 16, p_qb + 16ull * p_j, qcnt * 16u, &W.bar[stage]);
+        }
+        ++n_out;
+        p_j += cnt;
+        if (p_j >= p_nch) {  // next item
+            p_has = e_has;
+            if (e_has) {
+                p_gs = (p_gs + 1) % kTmaGeoms;
+                open_item(e_item, p_gs);
+                e_has = advance();
+                e_item = s_it;
+                if (e_has) fetch_desc(e_item);
+            }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) produce(s);
+
+    // ---- consumer
+    Geom cur;
+    cur.nch = 0;
+    uint32_t cur_gs = 0xFFFFFFFFu, carry = 0, sc = 0, parity = 0;  // parity: bit s = phase of stage s to wait for
+    while (n_out) {
+        mbar_wait(&W.bar[sc], (parity >> sc) & 1u);
+        parity ^= 1u << sc;
+        const uint32_t gs = W.win[sc].gslot, wj0 = W.win[sc].j0, wcnt = W.win[sc].cnt;
+        if (gs != cur_gs) {
+            cur = W.geom[gs];
+            cur_gs = gs;
+            carry = 0;
+        }
+        const uint8_t *Ts = W.stage[sc], *Qs = W.stage[sc] + kTmaWin * 16;
+        for (uint32_t st = 0; st < wcnt; st += 32) {
+            const uint32_t rel = st + lane, j = wj0 + rel;
+            Vec3 v;
+            v.t = make_uint4(0, 0, 0, 0); v.q0 = v.t; v.q1 = v.t;
+            if (rel < wcnt) {
+                v.t = lds16(Ts + 16u * rel);
+                v.q0 = lds16(Qs + 16u * rel);
+                if (cur.s != 0 && j + 1 <= cur.q_last) v.q1 = lds16(Qs + 16u * rel + 16u);
+            }
+            walk_step<MODE, false>(A, Q, qn, E, lane, cur, wj0 + st, v, carry);
+        }
+        --n_out;
+        __syncwarp();  // every lane is done reading this stage
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        produce(sc);
+        sc = sc + 1 == kTmaStages ? 0 : sc + 1;
+    }
+    if (qn) {
+        walk_batch<MODE, false>(A, Q, qn, lane, E);
+        __syncwarp();
+    }
+    if (RUNS && E.open_item != 0xFFFFFFFFu && lane == 0) A.item_nheads[E.open_item] = E.open_count;
+}
+
+}  // namespace wga

@@ -1,0 +1,28 @@
+// walk_tma_kernels.cu -- translation unit of the TMA-staged column walk (walk_tma.cuh); separate from walk_kernels.cu
+// for the same reason that one is separate from the rest (register allocation near the occupancy budget).
+#define WGA_WALK_NO_SPARSE
+#include "walk_tma.cuh"
+
+namespace wga {
+
+template <int MODE>
+static cudaError_t launch_one(unsigned grid, cudaStream_t stream, const WalkArgs &A) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_walk_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_walk_tma<MODE><<<grid, kWalkThreads, sizeof(TmaSmem), stream>>>(A);
+    return cudaSuccess;
+}
+
+cudaError_t launch_walk_tma(int mode, unsigned grid, cudaStream_t stream, const WalkArgs &A) {
+    switch (mode) {
+        case MODE_STAT: return launch_one<MODE_STAT>(grid, stream, A);
+        case MODE_RUNS_EXT: return launch_one<MODE_RUNS_EXT>(grid, stream, A);
+        default: return launch_one<MODE_RUNS_CALLER>(grid, stream, A);
+    }
+}
+
+}  // namespace wga
