@@ -1,19 +1,34 @@
 // walk_tma.cuh -- TMA-staged variant of the dense column walk (same algorithm and outputs as k_walk, walk.cuh).
 //
-// k_walk keeps its operands in registers: one step of vectors is in flight per warp plus one prefetched step, i.e.
-// ~73 KB per SM -- about what Little's law asks for at 6.5 TB/s, so the kernel idles on `long_scoreboard`
-// (profiles/r01g_walk_full_ncu.md: 50-54 % of DRAM peak).  Here every warp owns a ring of kTmaStages shared-memory
-// windows of kTmaWin chunks (target bytes + query bytes of 2 steps); one lane fills them with 1-D bulk copies
-// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) up to kTmaStages windows ahead -- across item boundaries --
-// and the warp reads its vectors with LDS.128.  Bytes in flight: 24 warps x 3 x 2 KB = 148 KB per SM, and the 24
-// prefetch registers of k_walk are gone.
+// k_walk keeps its operands in registers: one step of vectors is in flight per warp plus one prefetched step, and
+// the kernel idles on `long_scoreboard` (profiles/r01g_walk_full_ncu.md: 50-54 % of DRAM peak).  Here every warp owns
+// a ring of kTmaStages shared-memory windows of kTmaWin chunks (target bytes + query bytes of kTmaWin/32 steps); one
+// lane fills them with 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) up to kTmaStages
+// windows ahead -- across item boundaries -- and the warp reads its vectors with LDS.128.  The 24 prefetch registers
+// of k_walk are gone.  Measured on the bench workload (1 M blocks): the bulk-copy REQUEST rate is what limits this
+// path -- 1 KB requests 2.3 TB/s, 1.5 KB 3.7 TB/s, 2 KB 4.2-4.5 TB/s -- and, at equal request size, the number of
+// resident warps (12 warps 3.5, 16 warps 4.2, 20 warps 4.5 TB/s).  Shared memory (2 x 4 KB of windows + 2.8 KB of
+// slow-chunk queue per warp) caps the SM at 20 warps: 2 CTAs x 10 warps, 2 stages x 128 chunks.
 #pragma once
 #include "walk.cuh"
 
 namespace wga {
 
-constexpr int kTmaStages = 3;
-constexpr uint32_t kTmaWin = 64;                                  // chunks per window (2 steps)
+#ifndef WGA_TMA_STAGES
+#define WGA_TMA_STAGES 2
+#endif
+#ifndef WGA_TMA_WIN
+#define WGA_TMA_WIN 128
+#endif
+#ifndef WGA_TMA_CTAS
+#define WGA_TMA_CTAS 2
+#endif
+#ifndef WGA_TMA_THREADS
+#define WGA_TMA_THREADS 320
+#endif
+constexpr int kTmaThreads = WGA_TMA_THREADS, kTmaWarps = kTmaThreads / 32, kTmaCtasPerSm = WGA_TMA_CTAS;
+constexpr int kTmaStages = WGA_TMA_STAGES;
+constexpr uint32_t kTmaWin = WGA_TMA_WIN;                          // chunks per window (32 per step)
 constexpr uint32_t kTmaStageBytes = kTmaWin * 16 + kTmaWin * 16 + 16;  // T | Q (+ one vector for the realign)
 constexpr int kTmaGeoms = 4;                                      // item geometries in flight per warp
 
@@ -25,8 +40,8 @@ struct __align__(16) TmaWarp {
     unsigned long long bar[kTmaStages];
 };
 struct TmaSmem {
-    uint32_t queue[kWalkWarps][11][64];
-    TmaWarp w[kWalkWarps];
+    uint32_t queue[kTmaWarps][11][64];
+    TmaWarp w[kTmaWarps];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -57,7 +72,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ uint4 lds16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
 template <int MODE>
-__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk_tma(WalkArgs A) {
+__global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArgs A) {
     constexpr bool RUNS = MODE != MODE_STAT;
     extern __shared__ __align__(128) uint8_t s_raw[];
     TmaSmem &S = *reinterpret_cast<TmaSmem *>(s_raw);

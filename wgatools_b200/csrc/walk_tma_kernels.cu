@@ -13,8 +13,14 @@ static cudaError_t launch_one(unsigned grid, cudaStream_t stream, const WalkArgs
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_walk_tma<MODE><<<grid, kWalkThreads, sizeof(TmaSmem), stream>>>(A);
+    k_walk_tma<MODE><<<grid, kTmaThreads, sizeof(TmaSmem), stream>>>(A);
     return cudaSuccess;
+}
+
+// persistent grid of the TMA variant: kTmaCtasPerSm CTAs per SM, never more CTAs than there are warps' worth of items
+unsigned walk_tma_grid(int n_sm, uint64_t n_items) {
+    const uint64_t want = (n_items + kTmaWarps - 1) / kTmaWarps, cap = (uint64_t)n_sm * kTmaCtasPerSm;
+    return (unsigned)(want < cap ? want : cap);
 }
 
 cudaError_t launch_walk_tma(int mode, unsigned grid, cudaStream_t stream, const WalkArgs &A) {

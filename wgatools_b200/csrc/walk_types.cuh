@@ -44,6 +44,7 @@ __device__ __host__ __forceinline__ uint64_t slot_cap(uint64_t n, uint32_t shift
 void launch_walk(int mode, unsigned grid, cudaStream_t stream, const WalkArgs &A);
 // TMA-staged variant (walk_tma.cuh, walk_tma_kernels.cu)
 cudaError_t launch_walk_tma(int mode, unsigned grid, cudaStream_t stream, const WalkArgs &A);
+unsigned walk_tma_grid(int n_sm, uint64_t n_items);
 void launch_rec_slot_need(unsigned grid, unsigned block, cudaStream_t stream, uint64_t n_rec, const uint32_t *n_items,
                           const uint64_t *ncols, uint32_t shift, uint64_t *need);
 void launch_fill_item_desc(unsigned grid, unsigned block, cudaStream_t stream, uint64_t n_rec, const uint32_t *n_items,

@@ -372,8 +372,9 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
         A.text = ctx->d_text; A.items = P.items; A.n_items = n_items; A.rec_cnt = rec_cnt;
         A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf; A.sched = ovf + 1;
         WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        static const bool use_tma = getenv("WGA_WALK_TMA") != nullptr && getenv("WGA_WALK_TMA")[0] == '1';
-        if (use_tma) WGA_CK(launch_walk_tma(MODE, walk_grid(ctx, n_items), ctx->stream, A));
+        // default: the TMA-staged walk (walk_tma.cuh); WGA_WALK_TMA=0 selects the register-staged k_walk (walk.cuh)
+        static const bool use_tma = !(getenv("WGA_WALK_TMA") != nullptr && getenv("WGA_WALK_TMA")[0] == '0');
+        if (use_tma) WGA_CK(launch_walk_tma(MODE, walk_tma_grid(ctx->n_sm, n_items), ctx->stream, A));
         else launch_walk(MODE, walk_grid(ctx, n_items), ctx->stream, A);
         ctx->n_own++;
         WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
