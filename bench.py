@@ -354,7 +354,7 @@ def main():
                                    "mode": "three independent host-buffer calls (file uploaded three times)"},
             "gpu_launches": own1 - own0, "cub_scan_calls": cub1 - cub0,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_walk (dense column walk, all launches of the timed steps)",
+            "roofline": {"bound": "hbm", "kernel": "k_walk_tma (dense column walk, TMA-staged; all launches of the timed steps)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": walk_traffic(args.blocks),
                          "launches": walk["launches"], "avg_launch_ms": walk["ms"] / max(walk["launches"], 1),
