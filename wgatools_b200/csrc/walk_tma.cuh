@@ -197,8 +197,9 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
             walk_step<MODE, false>(A, Q, qn, E, lane, cur, wj0 + st, v, carry);
         }
         --n_out;
-        __syncwarp();  // every lane is done reading this stage
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // every lane has consumed its LDS results (they were compared / queued inside walk_step), so the stage can be
+        // handed back to the async proxy without a proxy fence: the fence is for generic-proxy WRITES, there are none
+        __syncwarp();
         produce(sc);
         sc = sc + 1 == kTmaStages ? 0 : sc + 1;
     }
