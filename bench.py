@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample-mb", type=float, default=float(os.environ.get("WGA_BENCH_CPU_MB", 1500)))
     ap.add_argument("--no-call", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=(2, 3),
+                    help="2 = the headline workload (configs[1]); 3 = long-record shape of configs[2] (side measurement)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer legs")
     ap.add_argument("--slab-mb", type=int, default=int(os.environ.get("WGA_BENCH_SLAB_MB", 256)))
     return ap.parse_args()
@@ -96,9 +98,9 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def make_workload(blocks, seed, pinned_alloc):
+def make_workload(blocks, seed, pinned_alloc, config=2):
     import bench_support as bs
-    params = bs.maf_params(blocks, seed=seed, config=2)
+    params = bs.maf_params(blocks, seed=seed, config=config)
     keep, nbytes, ncols = bs.gen_maf_into(params, pinned_alloc)
     return keep, nbytes, ncols
 
@@ -165,7 +167,8 @@ def main():
     do_call = not args.no_call
     metric = "alignment GB/s (input MAF bytes) for call+stat+maf2paf"
     config = {"workload": f"configs[1]: maf2paf+stat+call(-s -l0) over a synthetic 2-genome MAF, {args.blocks} blocks/GPU "
-                          f"(lognormal median 2 kb, SURVEY 8(d) cfg 2), seed {SEED}+rank",
+                          f"(lognormal median 2 kb, SURVEY 8(d) cfg 2), seed {SEED}+rank" if args.config == 2 else
+                          f"configs[2] shape (side measurement): {args.blocks} long blocks/GPU (lognormal median 50 kb, SVs, SURVEY 8(d) cfg 3)",
               "blocks_per_gpu": args.blocks, "l2": "inputs larger than L2 (no flush needed)",
               "commands": ["maf2paf", "stat", "call -s -l0"] if do_call else ["maf2paf", "stat"]}
 
@@ -232,7 +235,7 @@ def main():
             raise MemoryError("wga_host_alloc failed")
         return p, p
     t_gen = time.perf_counter()
-    host_ptr, nbytes, ncols = make_workload(args.blocks, SEED + rank, pinned)
+    host_ptr, nbytes, ncols = make_workload(args.blocks, SEED + rank, pinned, args.config)
     t_gen = time.perf_counter() - t_gen
     import numpy as np
     h_view = torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(host_ptr)))
@@ -356,7 +359,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_walk_tma (dense column walk, TMA-staged; all launches of the timed steps)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": walk_traffic(args.blocks),
+                         "frac": achieved / peak if peak else None, "traffic": walk_traffic(args.blocks) if args.config == 2 else None,
                          "launches": walk["launches"], "avg_launch_ms": walk["ms"] / max(walk["launches"], 1),
                          "alg_bytes_per_launch": walk["bytes"] / max(walk["launches"], 1)},
             "input_bytes_per_gpu": nbytes, "columns_per_gpu": ncols, "gen_seconds": t_gen, "numa_node": numa}
