@@ -234,6 +234,15 @@ struct RowOut {
     __device__ __forceinline__ void bases(const uint8_t *s, uint64_t k) {
         for (uint64_t i = 0; i < k; ++i) { char c; if (!vcf_base(s[i], &c)) bad_base = true; ch(c); }
     }
+    // k_vcf_rows: sizing never looks at the bases (lengths are arithmetic); writing validates them, and a long REF/ALT
+    // (an SV of up to 100 kb) is left to the whole warp (def_*: at most one such payload per row)
+    const uint8_t *def_src;
+    uint64_t def_off, def_len;
+    __device__ __forceinline__ void bases_sized(uint64_t k) { n += k; }
+    __device__ __forceinline__ void bases_or_defer(const uint8_t *s, uint64_t k) {
+        if (k > 96 && def_len == 0) { def_src = s; def_off = n; def_len = k; n += k; return; }
+        bases(s, k);
+    }
 };
 
 constexpr int kVcfThreads = 128;
@@ -265,6 +274,10 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
         if (row == n_rows) { row_len[row] = 0; return; }
     }
     const bool have_row = row < n_rows;
+    const uint8_t *d_src = nullptr;
+    char *d_dst = nullptr;
+    uint64_t d_len = 0;
+    unsigned long long ekey = 0;
     if (have_row) {
     // run owning this row: last j with rowbase[j] <= row
     uint64_t lo = 0, hi = V.n_runs;
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
     if (PASS == 1) R.o = staged ? s_span[threadIdx.x >> 5] + (span_lo & 3u) + (row_off[row] - span_lo) : out + row_off[row];
     R.n = 0;
     R.bad_base = false;
+    R.def_src = nullptr; R.def_off = 0; R.def_len = 0;
     R.bytes(V.text + V.sl.name_off[tl], V.sl.name_len[tl]);
     R.ch('\t');
     const uint8_t *qn = V.text + V.sl.name_off[ql];
@@ -325,7 +339,7 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
         while (jr < j1 && !cls_has_t(V.run_cls[jr])) { ++jr; if (jr < j1) fc = V.run_pos[jr]; }
         R.u64(t_start + tb0 + 1);
         R.lit("\t.\t");
-        R.bases(tseq + fc, 1);
+        if (PASS == 0) R.bases_sized(1); else R.bases_or_defer(tseq + fc, 1);
         R.lit("\t<INV>\t.\t.\tSVTYPE=INV;END=");
         R.u64(t_start + tb1);
         R.lit("\tGT:QI\t1|1:");
@@ -351,9 +365,9 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
         if (c == CLS_X) {
             R.u64(t_offv + 1);
             R.lit("\t.\t");
-            R.bases(tseq + col, 1);
+            if (PASS == 0) R.bases_sized(1); else R.bases_or_defer(tseq + col, 1);
             R.ch('\t');
-            R.bases(qseq + col, 1);
+            if (PASS == 0) R.bases_sized(1); else R.bases_or_defer(qseq + col, 1);
             R.lit("\t.\t.\t.\tGT:QI\t1|1:");
             R.bytes(qn, qnl);
             R.ch('@');
@@ -363,15 +377,15 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
             R.u64(t_offv);
             R.lit("\t.\t");
             if (c == CLS_I) {
-                R.bases(tseq + an, 1);
+                if (PASS == 0) R.bases_sized(1); else R.bases_or_defer(tseq + an, 1);
                 R.ch('\t');
-                R.bases(qseq + an, 1);
-                R.bases(qseq + pos, el);
+                if (PASS == 0) R.bases_sized(1); else R.bases_or_defer(qseq + an, 1);
+                if (PASS == 0) R.bases_sized(el); else R.bases_or_defer(qseq + pos, el);
             } else {
-                R.bases(tseq + an, 1);
-                R.bases(tseq + pos, el);
+                if (PASS == 0) R.bases_sized(1); else R.bases_or_defer(tseq + an, 1);
+                if (PASS == 0) R.bases_sized(el); else R.bases_or_defer(tseq + pos, el);
                 R.ch('\t');
-                R.bases(qseq + an, 1);
+                if (PASS == 0) R.bases_sized(1); else R.bases_or_defer(qseq + an, 1);
             }
             R.lit("\t.\t.\t");
             if (neg) R.lit("INV_NEST=TRUE;");
@@ -388,12 +402,27 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
             R.ch('@'); R.ch(sfx); R.ch('\n');
         }
     }
-    if (PASS == 0) {
-        row_len[row] = R.n;
-        if (R.bad_base) atomicMin(err_key, (unsigned long long)((V.rec_run_first[rec] /*stable per record*/ << 8) | WGA_E_VCF_BASE));
+    if (PASS == 0) row_len[row] = R.n;
+    else {
+        ekey = (unsigned long long)((V.rec_run_first[rec] /*stable per record*/ << 8) | WGA_E_VCF_BASE);
+        if (R.bad_base) atomicMin(err_key, ekey);
+        d_src = R.def_src; d_len = R.def_len; d_dst = R.o + R.def_off;
     }
     }  // have_row
     if (PASS == 1) {
+        // long REF/ALT payloads: the whole warp copies (upper-cases, validates) one payload at a time
+        uint32_t pend = __ballot_sync(0xFFFFFFFFu, d_len != 0);
+        while (pend) {
+            const int sl = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const uint8_t *src = (const uint8_t *)__shfl_sync(0xFFFFFFFFu, (unsigned long long)d_src, sl);
+            char *dst = (char *)__shfl_sync(0xFFFFFFFFu, (unsigned long long)d_dst, sl);
+            const uint64_t len = __shfl_sync(0xFFFFFFFFu, (unsigned long long)d_len, sl);
+            const unsigned long long key = __shfl_sync(0xFFFFFFFFu, ekey, sl);
+            bool bad = false;
+            for (uint64_t i = lane; i < len; i += 32) { char c; if (!vcf_base(src[i], &c)) bad = true; dst[i] = c; }
+            if (bad) atomicMin(err_key, key);
+        }
         __syncwarp();
         if (staged) {
             const char *sp = s_span[threadIdx.x >> 5];

@@ -66,10 +66,12 @@ struct PafRowArgs {
     uint32_t *row_fixed; // bytes before the CIGAR text
     const uint64_t *row_off;
     char *out;
-    const uint64_t *run_len;   // PASS 1: the CIGAR tokens are written by the row's own thread
+    const uint64_t *run_len;   // PASS 1: the CIGAR tokens are written by the row's own thread ...
     const uint32_t *run_dl;
     const uint8_t *run_cls;
+    uint32_t *any_long;        // ... unless the record has more than kPafLongRuns runs: those are left to k_paf_cigar
 };
+constexpr uint64_t kPafLongRuns = 64;
 
 // forward-strand query coordinates (maf.rs:433-450), wrapping like release Rust
 __device__ __forceinline__ void query_fwd(const SLines &sl, uint64_t ql, uint64_t *qs, uint64_t *qe) {
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(kPafThreads) k_paf_rows(PafRowArgs A) {
                          3 + 1 + 5 + ndigits_u64(n - match) + 1 + 5;
         A.row_fixed[r] = fixed;
         A.row_len[r] = (uint64_t)fixed + cig + 1;
+        if (j1 - j0 > kPafLongRuns) atomicOr(A.any_long, 1u);
     } else {
         char *o = staged ? s_span[threadIdx.x >> 5] + (span_lo & 3u) + (A.row_off[r] - span_lo) : A.out + A.row_off[r];
         o = csv_name_put(o, qn, qnl); *o++ = '\t';
@@ -141,12 +144,14 @@ __global__ void __launch_bounds__(kPafThreads) k_paf_rows(PafRowArgs A) {
         *o++ = 'N'; *o++ = 'M'; *o++ = ':'; *o++ = 'i'; *o++ = ':';
         o = put_u64(o, n - match); *o++ = '\t';
         *o++ = 'c'; *o++ = 'g'; *o++ = ':'; *o++ = 'Z'; *o++ = ':';
-        for (uint64_t j = j0; j < j1; ++j) {  // "<len><op>" per run (cigar.rs:409-410)
-            const int nd = (int)A.run_dl[j] - 1;
-            write_u64(o, A.run_len[j], nd);
-            o[nd] = kClsChar[A.run_cls[j]];
-            o += nd + 1;
-        }
+        if (j1 - j0 > kPafLongRuns) o += cig;  // one thread per run (k_paf_cigar) fills this in afterwards
+        else
+            for (uint64_t j = j0; j < j1; ++j) {  // "<len><op>" per run (cigar.rs:409-410)
+                const int nd = (int)A.run_dl[j] - 1;
+                write_u64(o, A.run_len[j], nd);
+                o[nd] = kClsChar[A.run_cls[j]];
+                o += nd + 1;
+            }
         *o = '\n';
     }
     }
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(kPafThreads) k_paf_rows(PafRowArgs A) {
     }
 }
 
-// one CIGAR token per run
+// one CIGAR token per run, for the records with more than kPafLongRuns runs (a Mbp-long block has 10^4 of them)
 __global__ void k_paf_cigar(uint64_t n_runs, const uint32_t *__restrict__ run_rec,
                             const uint8_t *__restrict__ run_cls, const uint64_t *__restrict__ run_len,
                             const uint32_t *__restrict__ run_dl, const uint64_t *__restrict__ cig_off,
@@ -180,6 +185,7 @@ __global__ void k_paf_cigar(uint64_t n_runs, const uint32_t *__restrict__ run_re
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_runs) return;
     uint32_t rec = run_rec[j];
+    if (rec_run_first[rec + 1] - rec_run_first[rec] <= kPafLongRuns) return;
     char *o = out + row_off[rec] + row_fixed[rec] + (cig_off[j] - cig_off[rec_run_first[rec]]);
     int nd = (int)run_dl[j] - 1;
     write_u64(o, run_len[j], nd);

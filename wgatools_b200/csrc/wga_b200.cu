@@ -644,14 +644,22 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     R.skip = P.rc.skip; R.rec_cnt = rec_cnt; R.rec_run_first = rec_run_first; R.cig_off = cig_off;
     R.row_len = row_len; R.row_fixed = row_fixed; R.row_off = row_off; R.out = nullptr;
     R.run_len = run_len; R.run_dl = run_dl; R.run_cls = run_cls;
+    uint64_t *any_long = ctx->buf<uint64_t>(B_SCALARS, 16) + 8;
+    WGA_CK(cudaMemsetAsync(any_long, 0, 8, ctx->stream));
+    R.any_long = (uint32_t *)any_long;
     LAUNCH(ctx, k_paf_rows<0>, grid_for(n_rec + 1, kPafThreads), kPafThreads, R);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
-    uint64_t total;
-    WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
+    uint64_t tl2[2];
+    WGA_TRY(read_scalars(ctx, {row_off + n_rec, any_long}, tl2));
+    const uint64_t total = tl2[0];
     char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_out) return ctx->err_code;
     R.out = d_out;
     LAUNCH(ctx, k_paf_rows<1>, grid_for(n_rec, kPafThreads), kPafThreads, R);
+    if (tl2[1] & 1u)
+        LAUNCH(ctx, k_paf_cigar, grid_for(n_runs, 256), 256, n_runs, (const uint32_t *)run_rec, (const uint8_t *)run_cls,
+               (const uint64_t *)run_len, (const uint32_t *)run_dl, (const uint64_t *)cig_off, (const uint64_t *)rec_run_first,
+               (const uint64_t *)row_off, (const uint32_t *)row_fixed, d_out);
     // per-record 11 counters stay available for wga_last_record_counts
     unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
     if (!cnt11) return ctx->err_code;
@@ -1018,6 +1026,12 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     char *d_out = (char *)ctx->ensure(B_OUT, sc[0] + 16);
     if (!d_out) return ctx->err_code;
     LAUNCH(ctx, k_vcf_rows<1>, grid_for(n_rows, 128), 128, V, n_rows, rowbase, row_len, row_off, d_out, P.err_key);
+    uint64_t key1;  // REF/ALT bases are validated while they are written
+    WGA_TRY(read_scalars(ctx, {P.err_key}, &key1));
+    if (key1 != kNoErr) {
+        ctx->set_error(WGA_E_VCF_BASE, key1 >> 8, "REF/ALT base outside ACGTNacgtn (noodles-vcf rejects the record)");
+        return WGA_E_VCF_BASE;
+    }
     return finish_output(ctx, d_out, sc[0], mem, flags, out);
 }
 #endif
