@@ -81,23 +81,36 @@ __device__ __forceinline__ uint64_t chunk_walk(const uint64_t *__restrict__ run_
     return k;
 }
 
-// PASS 0: number of chunks per record; PASS 1: chunk start columns
-template <int PASS>
+// Two consecutive chunks always span at least C columns (the first ends at the LAST qualifying gap end inside its
+// window, so the second finds none before the first window's end), hence a record has at most 2*ncols/C + 2 chunks:
+// one pass writes the chunk starts into a region of that capacity and counts them, a tiny copy densifies.
+__device__ __forceinline__ uint64_t chunk_cap(uint64_t ncols, uint64_t C) { return 2 * (ncols / C) + 3; }
+__global__ void k_chunk_caps(uint64_t n_rec, const uint64_t *__restrict__ ncols, const uint8_t *__restrict__ skip, uint64_t C,
+                             uint64_t *__restrict__ cap) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rec) return;
+    cap[r] = (r == n_rec || skip[r] || ncols[r] == 0) ? 0 : chunk_cap(ncols[r], C);
+}
 __global__ void k_chunks(uint64_t n_rec, const uint64_t *__restrict__ rec_run_first, const uint64_t *__restrict__ run_pos,
                          const uint8_t *__restrict__ run_cls, const uint64_t *__restrict__ ncols,
                          const uint8_t *__restrict__ skip, uint64_t C, uint64_t K, uint64_t *__restrict__ n_chunks,
-                         const uint64_t *__restrict__ rec_chunk_first, uint64_t *__restrict__ chunk_cs) {
+                         const uint64_t *__restrict__ cap_base, uint64_t *__restrict__ chunk_tmp) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rec) return;
-    if (r == n_rec) { if (PASS == 0) n_chunks[r] = 0; return; }
-    if (skip[r] || ncols[r] == 0) { if (PASS == 0) n_chunks[r] = 0; return; }
-    uint64_t j0 = rec_run_first[r], j1 = rec_run_first[r + 1];
-    if (PASS == 0) {
-        n_chunks[r] = chunk_walk(run_pos, run_cls, j0, j1, ncols[r], C, K, [](uint64_t, uint64_t, uint64_t) {});
-    } else {
-        uint64_t base = rec_chunk_first[r];
-        chunk_walk(run_pos, run_cls, j0, j1, ncols[r], C, K, [&](uint64_t k, uint64_t s, uint64_t) { chunk_cs[base + k] = s; });
-    }
+    if (r == n_rec) { n_chunks[r] = 0; return; }
+    if (skip[r] || ncols[r] == 0) { n_chunks[r] = 0; return; }
+    const uint64_t j0 = rec_run_first[r], j1 = rec_run_first[r + 1], base = cap_base[r], cap = cap_base[r + 1] - base;
+    n_chunks[r] = chunk_walk(run_pos, run_cls, j0, j1, ncols[r], C, K,
+                             [&](uint64_t k, uint64_t s, uint64_t) { if (k < cap) chunk_tmp[base + k] = s; });
+}
+__global__ void k_chunks_dense(uint64_t n_rec, const uint64_t *__restrict__ cap_base, const uint64_t *__restrict__ chunk_tmp,
+                               const uint64_t *__restrict__ rec_chunk_first, uint64_t *__restrict__ chunk_cs,
+                               uint32_t *__restrict__ chunk_rec, unsigned long long *err_key) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint64_t c0 = rec_chunk_first[r], n = rec_chunk_first[r + 1] - c0, base = cap_base[r];
+    if (n > cap_base[r + 1] - base) { atomicMin(err_key, (unsigned long long)((r << 8) | WGA_E_INTERNAL)); return; }
+    for (uint64_t k = 0; k < n; ++k) { chunk_cs[c0 + k] = chunk_tmp[base + k]; chunk_rec[c0 + k] = (uint32_t)r; }
 }
 
 // index of the run of record r that contains column col (runs [j0,j1) sorted by pos)

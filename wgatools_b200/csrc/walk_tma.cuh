@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
     __syncwarp();
 
     // dynamic scheduling as in k_walk: batches of kGrab consecutive items, the next batch requested one ahead
-    constexpr uint32_t kGrab = 8;
+    const uint32_t kGrab = A.grab;  // 8 for short items; fewer when items are long and few (tail balance)
     const uint32_t n_items = (uint32_t)A.n_items;
     uint32_t s_it = 0, s_end = 0, nb_raw = 0;
     if (lane == 0) {

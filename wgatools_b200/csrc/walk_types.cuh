@@ -36,6 +36,7 @@ struct WalkArgs {
     uint32_t cap_shift;           // slot capacity of an item = (n >> cap_shift) + kSlotPad
     uint32_t *overflow;
     unsigned int *sched;          // dynamic work counter (zero-initialised)
+    uint32_t grab;                // items handed out per request (k_walk_tma; k_walk uses 8)
 };
 
 __device__ __host__ __forceinline__ uint64_t slot_cap(uint64_t n, uint32_t shift) { return (n >> shift) + kSlotPad; }

@@ -372,6 +372,11 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
         A.text = ctx->d_text; A.items = P.items; A.n_items = n_items; A.rec_cnt = rec_cnt;
         A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf; A.sched = ovf + 1;
         WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        // hand out fewer items per request when there are few per warp (long items: the last request is the tail)
+        {
+            const uint64_t per_warp = n_items / ((uint64_t)ctx->n_sm * 20 + 1);
+            A.grab = per_warp >= 256 ? 8u : per_warp >= 64 ? 4u : per_warp >= 16 ? 2u : 1u;
+        }
         // default: the TMA-staged walk (walk_tma.cuh); WGA_WALK_TMA=0 selects the register-staged k_walk (walk.cuh)
         static const bool use_tma = !(getenv("WGA_WALK_TMA") != nullptr && getenv("WGA_WALK_TMA")[0] == '0');
         if (use_tma) WGA_CK(launch_walk_tma(MODE, walk_tma_grid(ctx->n_sm, n_items), ctx->stream, A));
@@ -985,9 +990,17 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     LAUNCH(ctx, k_run_contrib, grid_for(n_runs + 1, 256), 256, n_runs, run_cls, run_len, tcon, qcon);
     WGA_TRY(exclusive_sum(ctx, tcon, St, n_runs + 1));
     WGA_TRY(exclusive_sum(ctx, qcon, Sq, n_runs + 1));
-    // chunk grid
-    LAUNCH(ctx, k_chunks<0>, grid_for(n_rec + 1, 128), 128, n_rec, rec_run_first, run_pos, run_cls, P.rc.ncols, P.rc.skip,
-           opts->chunk_size, opts->svlen_cutoff, nchunks, (const uint64_t *)nullptr, (uint64_t *)nullptr);
+    // chunk grid: one pass into capacity-sized regions, then a dense copy
+    uint64_t *ccap = ctx->buf<uint64_t>(B_PP_A, n_rec + 1), *cap_base = ctx->buf<uint64_t>(B_PP_B, n_rec + 1);
+    if (!ccap || !cap_base) return ctx->err_code;
+    LAUNCH(ctx, k_chunk_caps, grid_for(n_rec + 1, 256), 256, n_rec, (const uint64_t *)P.rc.ncols, (const uint8_t *)P.rc.skip,
+           (uint64_t)opts->chunk_size, ccap);
+    WGA_TRY(exclusive_sum(ctx, ccap, cap_base, n_rec + 1));
+    const uint64_t cap_total = 2 * (P.total_cols / opts->chunk_size) + 3 * n_rec + 8;  // >= sum of the caps
+    uint64_t *chunk_tmp = ctx->buf<uint64_t>(B_PP_C, cap_total);
+    if (!chunk_tmp) return ctx->err_code;
+    LAUNCH(ctx, k_chunks, grid_for(n_rec + 1, 128), 128, n_rec, rec_run_first, run_pos, run_cls, P.rc.ncols, P.rc.skip,
+           opts->chunk_size, opts->svlen_cutoff, nchunks, (const uint64_t *)cap_base, chunk_tmp);
     WGA_TRY(exclusive_sum(ctx, nchunks, rec_chunk_first, n_rec + 1));
     uint64_t n_chunks;
     WGA_TRY(read_scalars(ctx, {rec_chunk_first + n_rec}, &n_chunks));
@@ -996,9 +1009,8 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     uint64_t *inv_cum = ctx->buf<uint64_t>(B_INV_IDX, n_chunks + 1);
     uint64_t *rows = ctx->buf<uint64_t>(B_RUN_CIGOFF, n_runs + 1), *rowbase = ctx->buf<uint64_t>(B_NAME_OFF, n_runs + 1);
     if (!chunk_cs || !chunk_rec || !chunk_inv || !inv_cum || !rows || !rowbase) return ctx->err_code;
-    LAUNCH(ctx, k_chunks<1>, grid_for(n_rec + 1, 128), 128, n_rec, rec_run_first, run_pos, run_cls, P.rc.ncols, P.rc.skip,
-           opts->chunk_size, opts->svlen_cutoff, nchunks, rec_chunk_first, chunk_cs);
-    LAUNCH(ctx, k_chunk_rec, grid_for(n_rec, 256), 256, n_rec, rec_chunk_first, chunk_rec);
+    LAUNCH(ctx, k_chunks_dense, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)cap_base, (const uint64_t *)chunk_tmp,
+           (const uint64_t *)rec_chunk_first, chunk_cs, chunk_rec, P.err_key);
     CallView V;
     V.n_rec = n_rec; V.n_runs = n_runs; V.text = ctx->d_text; V.sl = P.sl; V.tl = P.rc.tl; V.ql = P.rc.ql;
     V.ncols = P.rc.ncols; V.t_off = P.rc.t_off; V.q_off = P.rc.q_off; V.neg = P.rc.neg; V.skip = P.rc.skip;
