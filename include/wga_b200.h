@@ -62,7 +62,13 @@ enum { WGA_MEM_HOST = 0, WGA_MEM_DEVICE = 1 };
 enum {
     WGA_F_FIRST_SLAB = 1u,
     /* with mem == WGA_MEM_DEVICE: still hand the output back in (pinned) host memory */
-    WGA_F_OUT_HOST = 2u
+    WGA_F_OUT_HOST = 2u,
+    /* with mem == WGA_MEM_DEVICE, on wga_maf2paf / wga_maf_stat / wga_maf_call: the caller asserts that (text, len)
+     * is the slab the previous MAF command on this ctx was given and that its bytes have not changed; the on-device
+     * tokenisation of that call (delimiter index, line table, s-line fields) is then reused -- the reference parses
+     * the file once per command -- and only the command-specific record building and walk are run.  Ignored when
+     * no matching index is held. */
+    WGA_F_REUSE_INDEX = 4u
 };
 
 typedef struct wga_ctx wga_ctx;

@@ -252,6 +252,49 @@ def test_resident_maf_pipeline(w, ctx):
         assert w.run_bytes(w.maf2paf, rm, ctx=ctx) == b""
 
 
+def test_reuse_index_across_commands(w, ctx):
+    """WGA_F_REUSE_INDEX: stat / call reuse the tokenisation of the preceding command on the same device slab"""
+    import torch
+    from wgatools_b200._lib import CallOpts, WGA_F_REUSE_INDEX
+    opts = CallOpts(snp=1, inv=1, svlen_cutoff=0, chunk_size=1000000, query_name=None)
+    texts = [bs.gen_maf(bs.maf_params(700, seed=61, p_neg=0.3)), bs.gen_maf(bs.maf_params(500, seed=62)), TEST_MAF]
+    cap = max(len(t) for t in texts) + 64
+    d = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    for text in texts:
+        d.zero_()
+        d[:len(text)].copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
+        torch.cuda.synchronize()
+        ptr = ctypes.c_void_p(d.data_ptr())
+        p, n = ctx.maf2paf_raw(ptr, len(text), 1, 1)                      # tokenises (same pointer, new bytes)
+        assert _dev_bytes(p, n) == orc.maf2paf(text)
+        acc = w.StatAcc(False)
+        ctx.maf_stat_raw(ptr, len(text), 1, 1 | WGA_F_REUSE_INDEX, acc)
+        assert acc.write() == orc.stat_maf(text)
+        p, n = ctx.maf_call_raw(ptr, len(text), 1, 1 | WGA_F_REUSE_INDEX, opts)
+        assert ctx.vcf_header("sample") + _dev_bytes(p, n) == orc.call_maf(text, snp=True, inv=True, svlen=0)
+        # a different query_name / a different length falls back to what each command needs
+        if text is TEST_MAF:
+            p, n = ctx.maf2paf_raw(ptr, len(text), 1, 1 | WGA_F_REUSE_INDEX, "query.chr8")
+            assert _dev_bytes(p, n) == orc.maf2paf(text, "query.chr8")
+        cut = text.rfind(b"\na ", 0, len(text) // 2) + 1
+        p, n = ctx.maf2paf_raw(ptr, cut, 1, 1 | WGA_F_REUSE_INDEX)
+        assert _dev_bytes(p, n) == orc.maf2paf(text[:cut])
+    # errors found while tokenising are reported again by the commands that reuse the index
+    bad = TEST_MAF.replace(b" + ", b" * ", 1)
+    d.zero_()
+    d[:len(bad)].copy_(torch.frombuffer(bytearray(bad), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    ptr = ctypes.c_void_p(d.data_ptr())
+    msgs = []
+    for flags, fn in ((1, lambda f: ctx.maf2paf_raw(ptr, len(bad), 1, f)),
+                      (1 | WGA_F_REUSE_INDEX, lambda f: ctx.maf_stat_raw(ptr, len(bad), 1, f, w.StatAcc(False))),
+                      (1 | WGA_F_REUSE_INDEX, lambda f: ctx.maf_call_raw(ptr, len(bad), 1, f, opts))):
+        with pytest.raises(w.WGAError) as e:
+            fn(flags)
+        msgs.append((e.value.code, str(e.value)))
+    assert msgs[0] == msgs[1] == msgs[2] and msgs[0][0] == 2
+
+
 def test_stat_export_import_roundtrip(w, ctx):
     text = bs.gen_maf(bs.maf_params(600, seed=44, p_neg=0.4))
     L = ctx.L

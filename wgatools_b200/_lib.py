@@ -12,6 +12,7 @@ SO_PATH = os.environ.get("WGA_B200_LIB") or os.path.join(_DIR, "libwga_b200.so")
 WGA_MEM_HOST, WGA_MEM_DEVICE = 0, 1
 WGA_F_FIRST_SLAB = 1
 WGA_F_OUT_HOST = 2
+WGA_F_REUSE_INDEX = 4
 
 
 class Span(ctypes.Structure):

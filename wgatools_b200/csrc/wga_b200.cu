@@ -111,11 +111,37 @@ struct Prep {
     uint64_t total_cols = 0;
 };
 
+// The delimiter index, the line table and the parsed s-line fields of the last MAF slab stay valid in the ctx pool
+// until another text is staged.  A command called with WGA_F_REUSE_INDEX on the SAME device text skips straight to
+// record building (which depends on the command: query_name, 1-s-line semantics).
+struct TokCache {
+    bool valid = false;
+    const void *src = nullptr;      // the caller's pointer
+    const uint8_t *d_text = nullptr;  // where the kernels read it (== src, or the realigned copy)
+    uint64_t len = 0;
+    uint32_t first_slab = 0;
+    LineView lv;
+    SLines sl;
+    uint64_t *rec_first = nullptr, *rec_last = nullptr;
+    uint64_t n_lines = 0, n_rec = 0;
+};
+static TokCache &tok_of(wga_ctx *ctx) {
+    if (!ctx->tok_cache) ctx->tok_cache = new TokCache();
+    return *(TokCache *)ctx->tok_cache;
+}
+
 // stage the slab on the device (host input) or adopt the device pointer
-int stage_text(wga_ctx *ctx, const void *text, uint64_t len, int mem) {
+int stage_text(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags = 0) {
     ctx->last_counts_valid = false;
     ctx->text_len = len;
     ctx->h_text = nullptr;
+    TokCache &tc = tok_of(ctx);
+    if ((flags & WGA_F_REUSE_INDEX) && mem == WGA_MEM_DEVICE && tc.valid && tc.src == text && tc.len == len &&
+        tc.first_slab == (flags & WGA_F_FIRST_SLAB)) {
+        ctx->d_text = tc.d_text;  // same bytes as last time: keep the staged copy and the index
+        return WGA_OK;
+    }
+    tc.valid = false;
     if (mem == WGA_MEM_DEVICE) {
         if (reinterpret_cast<uintptr_t>(text) & 15u) {  // e.g. a slab of a resident text: realign with one D2D copy
             uint8_t *d = (uint8_t *)ctx->ensure(B_TEXT, len + 64);
@@ -123,9 +149,11 @@ int stage_text(wga_ctx *ctx, const void *text, uint64_t len, int mem) {
             if (len) WGA_CK(cudaMemcpyAsync(d, text, len, cudaMemcpyDeviceToDevice, ctx->stream));
             WGA_CK(cudaMemsetAsync(d + len, 0, 64, ctx->stream));
             ctx->d_text = d;
+            tc.src = text;
             return WGA_OK;
         }
         ctx->d_text = (const uint8_t *)text;
+        tc.src = text;
         return WGA_OK;
     }
     if (mem != WGA_MEM_HOST) {
@@ -138,6 +166,7 @@ int stage_text(wga_ctx *ctx, const void *text, uint64_t len, int mem) {
     WGA_CK(cudaMemsetAsync(d + len, 0, 64, ctx->stream));
     ctx->d_text = d;
     ctx->h_text = (const char *)text;
+    tc.src = nullptr;  // host inputs are uploaded on every call: nothing to reuse
     return WGA_OK;
 }
 
@@ -247,16 +276,29 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
     LAUNCH(ctx, k_init_u64, 1, 1, P->err_key, 1, kNoErr);
     if (len == 0) return WGA_OK;
 
+    TokCache &tc = tok_of(ctx);
+    LineView &lv = P->lv;
+    SLines &sl = P->sl;
+    Recs &rc = P->rc;
+    uint64_t n_lines, n_rec;
+    unsigned long long *tok_err = ctx->buf<unsigned long long>(B_TOK_ERR, 1);
+    if (!tok_err) return ctx->err_code;
+    if ((flags & WGA_F_REUSE_INDEX) && tc.valid && tc.d_text == text && tc.len == len) {
+        // ---- the slab was tokenised by the previous command: take its index, restart from its error state
+        lv = tc.lv; sl = tc.sl; rc.first = tc.rec_first; rc.last = tc.rec_last;
+        n_lines = tc.n_lines; n_rec = tc.n_rec;
+        ctx->n_ws = lv.n_ws; ctx->n_nl = lv.n_nl; ctx->n_lines = n_lines; ctx->n_rec = n_rec;
+        WGA_CK(cudaMemcpyAsync(P->err_key, tok_err, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
     // 1. whitespace index
     uint64_t n_ws = 0, n_nl = 0;
     uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
     uint8_t last_byte = 0;
     WGA_TRY((build_delim_index<0, kTokCap>(ctx, text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
     last_byte = *(uint8_t *)(ctx->h_scal + 8);
-    const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
+    n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
     ctx->n_ws = n_ws; ctx->n_nl = n_nl; ctx->n_lines = n_lines;
 
-    LineView &lv = P->lv;
     lv.text = text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
     lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = (flags & WGA_F_FIRST_SLAB) ? 1u : 0u;
 
@@ -269,28 +311,31 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
     WGA_TRY(exclusive_sum(ctx, lhead, lscan, n_lines + 1));
     WGA_CK(cudaMemcpyAsync(ctx->h_scal, lscan + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
     WGA_TRY(sync_check(ctx));
-    const uint64_t n_rec = *(uint32_t *)ctx->h_scal;
+    n_rec = *(uint32_t *)ctx->h_scal;
     ctx->n_rec = n_rec;
 
     // 3. s-line fields
-    SLines &sl = P->sl;
     sl.name_off = ctx->buf<uint64_t>(B_SL_NAME_OFF, n_lines); sl.name_len = ctx->buf<uint32_t>(B_SL_NAME_LEN, n_lines);
     sl.start = ctx->buf<uint64_t>(B_SL_START, n_lines); sl.ali = ctx->buf<uint64_t>(B_SL_ALI, n_lines);
     sl.src = ctx->buf<uint64_t>(B_SL_SRC, n_lines); sl.neg = ctx->buf<uint8_t>(B_SL_NEG, n_lines);
     sl.seq_off = ctx->buf<uint64_t>(B_SL_SEQ_OFF, n_lines); sl.seq_len = ctx->buf<uint64_t>(B_SL_SEQ_LEN, n_lines);
-    Recs &rc = P->rc;
     rc.first = ctx->buf<uint64_t>(B_REC_FIRST, n_rec + 1); rc.last = ctx->buf<uint64_t>(B_REC_LAST, n_rec + 1);
+    if (!sl.name_off || !sl.name_len || !sl.start || !sl.ali || !sl.src || !sl.neg || !sl.seq_off || !sl.seq_len || !rc.first ||
+        !rc.last)
+        return ctx->err_code;
+    LAUNCH(ctx, k_parse_slines, grid_for(n_lines, 256), 256, lv, lflags, lscan, sl, rc.first, rc.last, P->err_key);
+    WGA_CK(cudaMemcpyAsync(tok_err, P->err_key, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    tc.valid = true; tc.d_text = text; tc.len = len; tc.first_slab = flags & WGA_F_FIRST_SLAB;
+    tc.lv = lv; tc.sl = sl; tc.rec_first = rc.first; tc.rec_last = rc.last; tc.n_lines = n_lines; tc.n_rec = n_rec;
+    }
     rc.tl = ctx->buf<uint64_t>(B_REC_TL, n_rec + 1); rc.ql = ctx->buf<uint64_t>(B_REC_QL, n_rec + 1);
     rc.t_off = ctx->buf<uint64_t>(B_REC_TOFF, n_rec + 1); rc.q_off = ctx->buf<uint64_t>(B_REC_QOFF, n_rec + 1);
     rc.ncols = ctx->buf<uint64_t>(B_REC_NCOLS, n_rec + 1); rc.neg = ctx->buf<uint8_t>(B_REC_NEG, n_rec + 1);
     rc.skip = ctx->buf<uint8_t>(B_REC_SKIP, n_rec + 1); rc.n_items = ctx->buf<uint32_t>(B_REC_NITEMS, n_rec + 1);
     P->item_base = ctx->buf<uint64_t>(B_REC_ITEMBASE, n_rec + 1);
     uint64_t *colsum = ctx->buf<uint64_t>(B_GEN_H, n_rec + 1);
-    if (!sl.name_off || !sl.name_len || !sl.start || !sl.ali || !sl.src || !sl.neg || !sl.seq_off || !sl.seq_len ||
-        !rc.first || !rc.last || !rc.tl || !rc.ql || !rc.t_off || !rc.q_off || !rc.ncols || !rc.neg || !rc.skip ||
-        !rc.n_items || !P->item_base || !colsum)
+    if (!rc.tl || !rc.ql || !rc.t_off || !rc.q_off || !rc.ncols || !rc.neg || !rc.skip || !rc.n_items || !P->item_base || !colsum)
         return ctx->err_code;
-    LAUNCH(ctx, k_parse_slines, grid_for(n_lines, 256), 256, lv, lflags, lscan, sl, rc.first, rc.last, P->err_key);
     if (n_rec == 0) {
         uint64_t key;
         WGA_TRY(read_scalars(ctx, {P->err_key}, &key));
@@ -467,6 +512,7 @@ void wga_ctx_destroy(wga_ctx *ctx) {
         if (b.p) cudaFree(b.p);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    delete (TokCache *)ctx->tok_cache;
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -530,6 +576,7 @@ int wga_text_open(wga_ctx *ctx, const void *host_text, uint64_t len, uint64_t sl
     if (slab_bytes == 0) slab_bytes = 256ull << 20;
     if (slab_bytes < 4096) slab_bytes = 4096;
     const char *h = (const char *)host_text;
+    tok_of(ctx).valid = false;  // the resident buffer is about to change under any cached index
     // the previous resident text (same buffer) may still be read by work on the ctx stream
     WGA_CK(cudaStreamSynchronize(ctx->stream));
     uint8_t *d = (uint8_t *)ctx->ensure(B_TEXT_RES, len + 64);
@@ -619,7 +666,7 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     out->data = nullptr;
     out->len = 0;
     walk_begin(ctx);
-    WGA_TRY(stage_text(ctx, text, len, mem));
+    WGA_TRY(stage_text(ctx, text, len, mem, flags));
     Prep P;
     WGA_TRY(prepare_maf(ctx, flags, query_name, 0, &P));
     const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
@@ -886,7 +933,7 @@ int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (!ctx || !acc || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
     walk_begin(ctx);
-    WGA_TRY(stage_text(ctx, text, len, mem));
+    WGA_TRY(stage_text(ctx, text, len, mem, flags));
     Prep P;
     WGA_TRY(prepare_maf(ctx, flags, query_name, 0, &P));
     const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
@@ -966,7 +1013,7 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
         return WGA_E_INVALID_ARG;
     }
     walk_begin(ctx);
-    WGA_TRY(stage_text(ctx, text, len, mem));
+    WGA_TRY(stage_text(ctx, text, len, mem, flags));
     Prep P;
     WGA_TRY(prepare_maf(ctx, flags, opts->query_name, 1, &P));
     const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
