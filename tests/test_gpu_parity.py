@@ -280,7 +280,7 @@ def test_reuse_index_across_commands(w, ctx):
         p, n = ctx.maf2paf_raw(ptr, cut, 1, 1 | WGA_F_REUSE_INDEX)
         assert _dev_bytes(p, n) == orc.maf2paf(text[:cut])
     # errors found while tokenising are reported again by the commands that reuse the index
-    bad = TEST_MAF.replace(b" + ", b" * ", 1)
+    bad = TEST_MAF.replace(b"\t+\t", b"\t*\t", 1)
     d.zero_()
     d[:len(bad)].copy_(torch.frombuffer(bytearray(bad), dtype=torch.uint8))
     torch.cuda.synchronize()
