@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-call", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=(2, 3),
                     help="2 = the headline workload (configs[1]); 3 = long-record shape of configs[2] (side measurement)")
+    ap.add_argument("--no-indep", action="store_true", help="profiling runs only: skip the independent-commands leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer legs")
     ap.add_argument("--slab-mb", type=int, default=int(os.environ.get("WGA_BENCH_SLAB_MB", 256)))
     return ap.parse_args()
@@ -302,7 +303,7 @@ def main():
     sampler = ClockSampler(dev)
     sampler.start()
     # independent commands (every command tokenises the slab again, like three separate invocations) ...
-    ms_indep = timed(1, d_text.data_ptr(), args.steps, False)
+    ms_indep = float("nan") if args.no_indep else timed(1, d_text.data_ptr(), args.steps, False)
     # ... and the job as the product runs it: one tokenisation per step, shared by the three commands
     from wgatools_b200._lib import WGA_F_REUSE_INDEX
     reuse["f"] = WGA_F_REUSE_INDEX

@@ -5,7 +5,7 @@
 TAG=${1:-r01}; BLOCKS=${2:-200000}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --blocks $BLOCKS --steps 1 --warmup 3 --cpu-sample-mb 1 --no-e2e > gpurun_out/launches_${TAG}.log 2>&1
+    python bench.py --blocks $BLOCKS --steps 1 --warmup 3 --cpu-sample-mb 1 --no-e2e --no-indep > gpurun_out/launches_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_walk -s 6 -c 5 -f -o gpurun_out/prof_walk_${TAG} \
-    python bench.py --blocks $BLOCKS --steps 1 --warmup 3 --cpu-sample-mb 1 --no-e2e > gpurun_out/prof_walk_${TAG}.log 2>&1
+    python bench.py --blocks $BLOCKS --steps 1 --warmup 3 --cpu-sample-mb 1 --no-e2e --no-indep > gpurun_out/prof_walk_${TAG}.log 2>&1
 ls -la gpurun_out/ | tail -8
