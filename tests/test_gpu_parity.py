@@ -234,11 +234,12 @@ def test_resident_maf_pipeline(w, ctx):
             opts = CallOpts(snp=1, inv=0, svlen_cutoff=0, chunk_size=1000000, query_name=None)
             acc = w.StatAcc(False)
             out_paf, out_vcf = [], [ctx.vcf_header("sample")]
-            for p, n, fl in rm.slabs():
+            from wgatools_b200._lib import WGA_F_REUSE_INDEX
+            for p, n, fl in rm.slabs():     # as bench.py's e2e leg: tokenise once per slab, reuse for stat and call
                 ptr, ln = ctx.maf2paf_raw(p, n, 1, fl)
                 out_paf.append(ctypes.string_at(ptr, ln) if ln else b"")
-                ctx.maf_stat_raw(p, n, 1, fl, acc)
-                ptr, ln = ctx.maf_call_raw(p, n, 1, fl, opts)
+                ctx.maf_stat_raw(p, n, 1, fl | WGA_F_REUSE_INDEX, acc)
+                ptr, ln = ctx.maf_call_raw(p, n, 1, fl | WGA_F_REUSE_INDEX, opts)
                 out_vcf.append(ctypes.string_at(ptr, ln) if ln else b"")
             assert b"".join(out_paf) == want_paf
             assert acc.write() == want_stat
