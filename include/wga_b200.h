@@ -190,6 +190,14 @@ int wga_paf_call(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t 
 int wga_paf_pseudo(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *fa,
                    const char *target, wga_span *out, wga_span *index);
 
+/* ---- validate: src/tools/validate.rs:44-147 (a free rider on the PAF CIGAR counters) ------------ */
+/* report (always host memory) = the reference's report text: counts, then "{name}:{start}-{end}" of every record whose
+ * query / target end differs from start + the CIGAR's consumed bases; fix != 0: `fixed` = every record re-serialised
+ * with the expected ends (the reference's -f file).  Lists and records come in file order (the reference's rayon fold
+ * has no defined order).  A CIGAR error is the reference's `get_stat().unwrap()` panic -> WGA_E_REF_PANIC. */
+int wga_paf_validate(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, int fix, wga_span *report,
+                     wga_span *fixed);
+
 /* ---- AlignRecord-level batch access (common.rs:142-176 get_stat / get_cigar_string) --------- */
 /* per-record counters of the last wga_maf2paf / wga_maf_stat / wga_paf_stat call, struct Cigar order
  * (cigar.rs:16-29): match, mismatch, ins_event, ins, del_event, del, inv_ins_event, inv_ins,

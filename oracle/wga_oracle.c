@@ -1831,3 +1831,79 @@ int orc_paf_pseudo(const char *paf, size_t paf_len, const char *fa, size_t fa_le
     orc_buf_free(&q);
     return rc;
 }
+
+/* ---------------------------------------------------------------- validate */
+/* src/tools/validate.rs:44-147 parallel_validatepaf: expected ends from the CIGAR counters.  The reduce order of the
+ * rayon fold is unspecified; here (and in the CUDA path) the lists and the fixed records come in FILE order.
+ * `rec.get_stat().unwrap()` (validate.rs:79) turns every CIGAR / tag error into a panic.  fix != 0: all records,
+ * with corrected ends, re-serialised by csv (12 typed columns in decimal, then the tags). */
+int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc_buf *fixed, char *err, size_t errcap) {
+    size_t pos = 0;
+    pafrow row = {0};
+    orc_buf ql = {0}, tl = {0}, conv = {0};
+    uint64_t total = 0, qbad = 0, tbad = 0;
+    int rc = ORC_OK;
+    while (paf_next(text, len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int neg = 0, bad = row.n < 12;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) { if (sv_eq_c(row.f[4], "+")) neg = 0; else if (sv_eq_c(row.f[4], "-")) neg = 1; else bad = 1; continue; }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+        total++;
+        sv cg = {0, 0};
+        int have = 0;
+        for (size_t k = 12; k < row.n && !have; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
+        if (!have)
+            for (size_t k = 12; k < row.n && !have; k++)
+                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
+                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
+                    conv.n = 0;
+                    cs_to_cigar(cs, &conv);
+                    cg.p = conv.p; cg.n = conv.n; have = 1;
+                }
+        orc_counts c;
+        char dis[256];
+        if (!have || orc_parse_paf_cigar(cg.p, cg.n, neg, &c, dis, sizeof dis)) {
+            set_err(err, errcap, "panic: called `Result::unwrap()` on an `Err` value");
+            rc = ORC_E_PANIC;
+            break;
+        }
+        const uint64_t exp_q = u[2] + c.c[0] + c.c[1] + c.c[3] + c.c[7], exp_t = u[7] + c.c[0] + c.c[1] + c.c[5] + c.c[9];
+        uint64_t q_end = u[3], t_end = u[8];
+        if (exp_q != q_end) {
+            qbad++;
+            buf_put(&ql, row.f[0].p, row.f[0].n); buf_putc(&ql, ':'); buf_putu(&ql, u[2]); buf_putc(&ql, '-'); buf_putu(&ql, q_end);
+            buf_putc(&ql, '\n');
+            q_end = exp_q;
+        }
+        if (exp_t != t_end) {
+            tbad++;
+            buf_put(&tl, row.f[5].p, row.f[5].n); buf_putc(&tl, ':'); buf_putu(&tl, u[7]); buf_putc(&tl, '-'); buf_putu(&tl, t_end);
+            buf_putc(&tl, '\n');
+            t_end = exp_t;
+        }
+        if (fix) { /* validate.rs:136-144 csv serialize of PafRecord */
+            csv_field(fixed, row.f[0], 1); csv_u64(fixed, u[1], 0); csv_u64(fixed, u[2], 0); csv_u64(fixed, q_end, 0);
+            buf_putc(fixed, '\t'); buf_putc(fixed, neg ? '-' : '+');
+            csv_field(fixed, row.f[5], 0); csv_u64(fixed, u[6], 0); csv_u64(fixed, u[7], 0); csv_u64(fixed, t_end, 0);
+            csv_u64(fixed, u[9], 0); csv_u64(fixed, u[10], 0); csv_u64(fixed, u[11], 0);
+            for (size_t k = 12; k < row.n; k++) csv_field(fixed, row.f[k], 0);
+            buf_putc(fixed, '\n');
+        }
+    }
+    if (rc == ORC_OK) { /* impl Display for Validations + writeln!(writer, "{}", ..) */
+        buf_puts(report, "Total records: "); buf_putu(report, total);
+        buf_puts(report, "\nQuery invalid records: "); buf_putu(report, qbad);
+        buf_puts(report, "\nTarget invalid records: "); buf_putu(report, tbad);
+        buf_puts(report, "\nQuery invalid list:\n"); buf_put(report, ql.p, ql.n);
+        buf_puts(report, "Target invalid list:\n"); buf_put(report, tl.p, tl.n);
+        buf_putc(report, '\n');
+    } else fixed->n = 0;
+    free(row.f); free(row.scratch);
+    orc_buf_free(&ql); orc_buf_free(&tl); orc_buf_free(&conv);
+    return rc;
+}

@@ -107,6 +107,9 @@ int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_
 int orc_paf_pseudo(const char *paf, size_t paf_len, const char *fa, size_t fa_len, const char *fai, size_t fai_len,
                    const char *target, orc_buf *out, orc_buf *index, char *err, size_t errcap);
 
+/* src/tools/validate.rs:44-147 (`validate [-f fix.paf]`): report text + (fix != 0) the re-serialised records */
+int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc_buf *fixed, char *err, size_t errcap);
+
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */
 void orc_fmt_f32(float v, char *dst /* >= 32 bytes */);      /* ryu 1.0.14 Buffer::format(f32) */

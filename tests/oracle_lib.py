@@ -60,6 +60,8 @@ def lib():
                                                                               ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_paf_pseudo.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 3 + [ctypes.c_char_p, ctypes.POINTER(OrcBuf),
                                                                                 ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_paf_validate.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(OrcBuf), ctypes.POINTER(OrcBuf),
+                                       ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -147,6 +149,17 @@ def paf_pseudo(paf: bytes, fa: bytes = None, fai: bytes = None, target=None) -> 
         files[name] = data[pos:pos + int(n)]
         pos += int(n)
     return files
+
+
+def paf_validate(paf: bytes, fix=False):
+    """(report text, fixed PAF or b"")"""
+    rep, fx = OrcBuf(), OrcBuf()
+    err = ctypes.create_string_buffer(512)
+    rc = lib().orc_paf_validate(paf, len(paf), int(fix), ctypes.byref(rep), ctypes.byref(fx), err, 512)
+    a, b = _take(rep), _take(fx)
+    if rc != 0:
+        raise OracleError(rc, err.value.decode("utf-8", "replace"))
+    return a, b
 
 
 def make_fai(fa: bytes) -> bytes:

@@ -833,3 +833,42 @@ def test_paf_pseudo_edges_and_errors(w, ctx, tmp_path):
     with pytest.raises(w.WGAError) as e:
         w.pseudo_maf_files(w.PAFReader(line(b"4=") + line(b"5=")), F, ctx=ctx)
     assert e.value.code == 102
+
+
+# ---------------------------------------------------------------- validate (8(f) item 3)
+def _validate(w, ctx, paf, fix=True):
+    rep, fx = io.BytesIO(), io.BytesIO()
+    w.parallel_validatepaf(w.PAFReader(paf), rep, fx if fix else None, ctx=ctx)
+    return rep.getvalue(), fx.getvalue()
+
+
+def test_validate_parity(w, ctx):
+    assert _validate(w, ctx, TEST_PAF) == orc.paf_validate(TEST_PAF, True)
+    assert _validate(w, ctx, b"") == orc.paf_validate(b"", True)
+    rng = random.Random(8)
+    for seed, kw in ((1, {}), (2, dict(m_only=1)), (3, dict(ops_median=2000.0, ops_sigma=1.0))):
+        text = bs.gen_paf(bs.paf_params(1500 if seed < 3 else 200, seed=seed, **kw))
+        lines = text.splitlines(keepends=True)
+        for i in rng.sample(range(len(lines)), len(lines) // 5):   # falsify some ends, add awkward tags
+            f = lines[i].rstrip(b"\n").split(b"\t")
+            which = rng.randrange(4)
+            if which in (0, 2):
+                f[3] = b"%d" % (int(f[3]) + rng.randrange(1, 50))
+            if which in (1, 2):
+                f[8] = b"0x%x" % (int(f[8]) + rng.randrange(1, 9))
+            if which == 3:
+                f.insert(12, b'zz:Z:say "hi"')
+                f.append(b"")
+            lines[i] = b"\t".join(f) + b"\n"
+        text = b"#c\n" + b"".join(lines)
+        want = orc.paf_validate(text, True)
+        assert _validate(w, ctx, text) == want
+        assert want[0].count(b"\n") > 10
+        assert _validate(w, ctx, text, fix=False) == (want[0], b"")
+    for bad, code in ((TEST_PAF.replace(b"25M10I", b"25M10S", 1), 8), (TEST_PAF.replace(b"\tcg:Z:25M", b"\tcx:Z:25M", 1), 8),
+                      (TEST_PAF.replace(b"\t300\t0\t200\t+", b"\t300\t0\tx\t+", 1), 9)):
+        with pytest.raises(orc.OracleError) as eo:
+            orc.paf_validate(bad, True)
+        with pytest.raises(w.WGAError) as eg:
+            _validate(w, ctx, bad)
+        assert eo.value.code == code == eg.value.code

@@ -276,3 +276,21 @@ def test_paf_pseudo_hand_derived():
         with pytest.raises(orc.OracleError) as e:
             orc.paf_pseudo(bad, fa, fai)
         assert e.value.code == code, (bad, e.value.code, e.value.msg)
+
+
+def test_validate_golden_and_hand_derived():
+    """validate.rs:73-125 on the reference's own PAF (consistent: nothing to fix, -f output == input) and on records
+    whose ends were falsified by hand"""
+    rep, fx = orc.paf_validate(TEST_PAF, True)
+    assert rep == (b"Total records: 2\nQuery invalid records: 0\nTarget invalid records: 0\nQuery invalid list:\n"
+                   b"Target invalid list:\n\n")
+    assert fx == TEST_PAF
+    # 25M10I15M20D30M20I30M10D70M: query 0 + 170 + 30 = 200, target 0 + 170 + 30 = 200
+    bad = TEST_PAF.replace(b"A\t300\t0\t200\t+\tB\t300\t0\t200", b"A\t300\t0\t190\t+\tB\t300\t0\t0x7", 1)
+    rep, fx = orc.paf_validate(bad, True)
+    assert rep == (b"Total records: 2\nQuery invalid records: 1\nTarget invalid records: 1\nQuery invalid list:\nA:0-190\n"
+                   b"Target invalid list:\nB:0-7\n\n")
+    assert fx == TEST_PAF                      # both ends repaired; the hex target_end comes back in decimal
+    with pytest.raises(orc.OracleError) as e:  # get_stat().unwrap()
+        orc.paf_validate(TEST_PAF.replace(b"25M10I", b"25M10S", 1))
+    assert e.value.code == 8

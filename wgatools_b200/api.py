@@ -397,6 +397,19 @@ def generate_pesudo_maf(reader: PAFReader, out_dir, fa_path=None, target=None, c
             f.write(data)
 
 
+def parallel_validatepaf(reader: PAFReader, writer, fix_writer=None, fix_flag=None, ctx=None):
+    """src/tools/validate.rs:44-71: report -> writer; with a fix_writer the corrected records -> fix_writer"""
+    ctx = ctx or default_context()
+    fix = fix_writer is not None if fix_flag is None else bool(fix_flag)
+    keep, base = _host_ptr(reader.data)
+    rep, fx = Span(), Span()
+    ctx._check(ctx.L.wga_paf_validate(ctx.h, ctypes.c_void_p(base), len(reader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, int(fix),
+                                      ctypes.byref(rep), ctypes.byref(fx)))
+    writer.write(ctypes.string_at(rep.data, rep.len))
+    if fix_writer is not None and fx.len:
+        fix_writer.write(ctypes.string_at(fx.data, fx.len))
+
+
 def run_bytes(fn, *args, **kw) -> bytes:
     """convenience: run one of the functions above into a bytes object (the writer argument is inserted
     where the reference signature has it: 2nd for maf2paf/stat_*, 3rd for call_var_maf, 4th for call_var_paf)"""

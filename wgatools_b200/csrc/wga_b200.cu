@@ -20,6 +20,7 @@
 #include "paf2maf.cuh"
 #include "call_paf.cuh"
 #include "pafpseudo.cuh"
+#include "validate.cuh"
 #endif
 
 using namespace wga;
@@ -1545,6 +1546,86 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
+// ---------------------------------------------------------------- validate (validate.rs:44-147)
+int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, int fix, wga_span *report,
+                     wga_span *fixed) {
+    if (!ctx || !report || !fixed || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    report->data = nullptr; report->len = 0;
+    fixed->data = nullptr; fixed->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    PafPrep PP;
+    WGA_TRY(paf_fasta_prepare(ctx, len, nullptr, nullptr, 1, &PP, false, nullptr));
+    const uint64_t n_rec = PP.n_rec;
+    std::string &rep = ctx->pseudo_index;  // host text owned by the ctx
+    rep.clear();
+    uint64_t nbad[2] = {0, 0};
+    std::string qlist, tlist;
+    uint64_t total = 0;
+    char *d_rows = nullptr;
+    if (n_rec) {
+        const uint8_t *d_text = ctx->d_text;
+        PafRecs R = PP.R;
+        unsigned long long *err_key = PP.err_key;
+        unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_C, n_rec * 11);
+        uint8_t *slow = ctx->buf<uint8_t>(B_RUN_CLS, n_rec);
+        uint64_t *c7 = ctx->buf<uint64_t>(B_GEN_D, 7 * n_rec);
+        uint64_t *l3 = ctx->buf<uint64_t>(B_GEN_E, 6 * (n_rec + 1));
+        unsigned long long *d_nbad = ctx->buf<unsigned long long>(B_TOK_ERR, 4) + 1;
+        if (!cnt11 || !slow || !c7 || !l3 || !d_nbad) return ctx->err_code;
+        ValCols C;
+        C.q_end = c7; C.t_end = c7 + n_rec; C.matches = c7 + 2 * n_rec; C.block_len = c7 + 3 * n_rec; C.mapq = c7 + 4 * n_rec;
+        C.tags_off = c7 + 5 * n_rec; C.line_end = c7 + 6 * n_rec;
+        // the line table of paf_fasta_prepare is still in the pool
+        uint8_t *lflags = ctx->buf<uint8_t>(B_LINE_FLAGS, PP.lv.n_lines + 1);
+        uint32_t *rscan = ctx->buf<uint32_t>(B_LINE_REC, PP.lv.n_lines + 1);
+        LAUNCH(ctx, k_val_cols, grid_for(PP.lv.n_lines, 256), 256, PP.lv, (const uint8_t *)lflags, (const uint32_t *)rscan, C);
+        LAUNCH(ctx, k_paf_cigar_counts_warp, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, cnt11, slow);
+        LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key, (const uint8_t *)slow);
+        WGA_CK(cudaMemsetAsync(d_nbad, 0, 16, ctx->stream));
+        ValView V;
+        V.n_rec = n_rec; V.text = d_text; V.R = R; V.C = C; V.cnt11 = cnt11; V.fix = fix ? 1 : 0;
+        V.q_len = l3; V.t_len = l3 + (n_rec + 1); V.row_len = l3 + 2 * (n_rec + 1);
+        uint64_t *q_off = l3 + 3 * (n_rec + 1), *t_off = l3 + 4 * (n_rec + 1), *row_off = l3 + 5 * (n_rec + 1);
+        V.q_off = q_off; V.t_off = t_off; V.row_off = row_off; V.q_out = V.t_out = V.row_out = nullptr; V.n_bad = d_nbad;
+        LAUNCH(ctx, k_val_rows<0>, grid_for(n_rec + 1, 256), 256, V);
+        WGA_TRY(exclusive_sum(ctx, V.q_len, q_off, n_rec + 1));
+        WGA_TRY(exclusive_sum(ctx, V.t_len, t_off, n_rec + 1));
+        WGA_TRY(exclusive_sum(ctx, V.row_len, row_off, n_rec + 1));
+        uint64_t sc[6];
+        WGA_TRY(read_scalars(ctx, {q_off + n_rec, t_off + n_rec, row_off + n_rec, err_key, d_nbad, d_nbad + 1}, sc));
+        if (sc[3] != kNoErr) {
+            int code = (int)(sc[3] & 0xFF);
+            const uint64_t rec = sc[3] >> 32;
+            std::string msg;
+            if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+            else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+            else { code = WGA_E_REF_PANIC; msg = "the reference panics on this record (get_stat().unwrap() on a CIGAR error, validate.rs:79)"; }
+            ctx->set_error(code, rec, msg);
+            return code;
+        }
+        nbad[0] = sc[4]; nbad[1] = sc[5];
+        total = sc[2];
+        char *d_q = (char *)ctx->ensure(B_NAME_BUF, sc[0] + sc[1] + 16);
+        d_rows = (char *)ctx->ensure(B_OUT, total + 16);
+        if (!d_q || !d_rows) return ctx->err_code;
+        V.q_out = d_q; V.t_out = d_q + sc[0]; V.row_out = d_rows;
+        LAUNCH(ctx, k_val_rows<1>, grid_for(n_rec + 1, 256), 256, V);
+        qlist.resize(sc[0]); tlist.resize(sc[1]);
+        if (sc[0]) WGA_CK(cudaMemcpyAsync(&qlist[0], d_q, sc[0], cudaMemcpyDeviceToHost, ctx->stream));
+        if (sc[1]) WGA_CK(cudaMemcpyAsync(&tlist[0], d_q + sc[0], sc[1], cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_TRY(sync_check(ctx));
+    }
+    // impl Display for Validations (validate.rs:25-41) + writeln!(writer, "{}", validations)
+    rep += "Total records: " + std::to_string(n_rec) + "\nQuery invalid records: " + std::to_string(nbad[0]) +
+           "\nTarget invalid records: " + std::to_string(nbad[1]) + "\nQuery invalid list:\n" + qlist + "Target invalid list:\n" + tlist + "\n";
+    report->data = rep.data();
+    report->len = rep.size();
+    if (fix && total) return finish_output(ctx, d_rows, total, mem, flags, fixed);
+    return WGA_OK;
+}
+
 // ---------------------------------------------------------------- pafpseudo (pseudomaf.rs:18-237, cigar.rs:744-804)
 int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *FA, const char *target,
                    wga_span *out, wga_span *index) {
@@ -1756,6 +1837,7 @@ int wga_paf_call(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fas
 int wga_paf_pseudo(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const char *, wga_span *, wga_span *) {
     return WGA_E_UNSUPPORTED;
 }
+int wga_paf_validate(wga_ctx *, const void *, uint64_t, int, uint32_t, int, wga_span *, wga_span *) { return WGA_E_UNSUPPORTED; }
 #endif
 #ifndef WGA_WITH_CALL
 int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
