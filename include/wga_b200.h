@@ -190,6 +190,17 @@ int wga_paf_call(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t 
 int wga_paf_pseudo(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *fa,
                    const char *target, wga_span *out, wga_span *index);
 
+/* ---- chain: src/converter.rs:57-92 maf2chain, :148-173 paf2chain --------------------------------- */
+/* One chain per record, file order: "chain 255 tName tSize + tStart tEnd qName qSize qStrand qStart qEnd id" with the
+ * head / tail indels trimmed off the coordinates (cigar.rs:155-245; the '-' strand keeps the reference's arithmetic,
+ * chain.rs:133-138), "size qdiff tdiff" lines, the last block's size and a blank line.  id = id_base + index of the
+ * record in this slab (the reference enumerates the records of the file); *n_records (may be NULL) = records in the
+ * slab, i.e. what to add to id_base for the next one. */
+int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name,
+                  uint64_t id_base, wga_span *out, uint64_t *n_records);
+int wga_paf2chain(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
+                  uint64_t *n_records);
+
 /* ---- validate: src/tools/validate.rs:44-147 (a free rider on the PAF CIGAR counters) ------------ */
 /* report (always host memory) = the reference's report text: counts, then "{name}:{start}-{end}" of every record whose
  * query / target end differs from start + the CIGAR's consumed bases; fix != 0: `fixed` = every record re-serialised

@@ -1907,3 +1907,162 @@ int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc
     orc_buf_free(&ql); orc_buf_free(&tl); orc_buf_free(&conv);
     return rc;
 }
+
+/* -------------------------------------------------------------------- chain */
+/* src/converter.rs:57-92 maf2chain / :148-173 paf2chain; src/parser/chain.rs:92-204 (ChainDataLine / ChainHeader
+ * Display, TryFrom<&MAFRecord> / TryFrom<&PafRecord> with the negative-strand quirk: query.end is computed from the
+ * ALREADY UPDATED query.start, chain.rs:133-138,174-179); src/parser/cigar.rs:155-295 (head/tail indel trim,
+ * parse_cigar_to_chain) and :435-490 (parse_maf_seq_to_chain, cigar_unit_chain).  u64 arithmetic wraps like release
+ * Rust.  The reference streams: on an error the records before it are already written; here the buffer keeps them too. */
+typedef struct { uint64_t size, qdiff, tdiff; } chainline;
+static void chain_unit(orc_buf *out, chainline *d, char op, uint64_t count) { /* cigar.rs:458-490 */
+    if (op == 'M') {
+        if (d->size != 0 && d->tdiff + d->qdiff != 0) {
+            buf_putc(out, '\n'); buf_putu(out, d->size); buf_putc(out, '\t'); buf_putu(out, d->qdiff); buf_putc(out, '\t');
+            buf_putu(out, d->tdiff);
+            d->size = 0;
+        }
+        d->size += count;
+        d->tdiff = 0; d->qdiff = 0;
+    } else if (op == 'I') d->tdiff += count;
+    else d->qdiff += count;
+}
+static void chain_header(orc_buf *out, sv tname, uint64_t tsize, uint64_t tstart, uint64_t tend, sv qname, uint64_t qsize,
+                         int neg, uint64_t qstart, uint64_t qend, uint64_t hi, uint64_t hd, uint64_t ti, uint64_t td, uint64_t id) {
+    tstart += hd; tend -= td;
+    if (!neg) { qstart += hi; qend -= ti; }
+    else { qstart = qsize - (qend - hi); qend = qsize - (qstart + ti); } /* chain.rs:133-138: uses the NEW start */
+    buf_puts(out, "chain\t255\t"); buf_put(out, tname.p, tname.n); buf_putc(out, '\t'); buf_putu(out, tsize); buf_puts(out, "\t+\t");
+    buf_putu(out, tstart); buf_putc(out, '\t'); buf_putu(out, tend); buf_putc(out, '\t');
+    buf_put(out, qname.p, qname.n); buf_putc(out, '\t'); buf_putu(out, qsize); buf_putc(out, '\t'); buf_putc(out, neg ? '-' : '+');
+    buf_putc(out, '\t'); buf_putu(out, qstart); buf_putc(out, '\t'); buf_putu(out, qend); buf_putc(out, '\t'); buf_putu(out, id);
+}
+
+int orc_maf2chain(const char *text, size_t len, const char *query_name, orc_buf *out, char *err, size_t errcap) {
+    lreader rd;
+    maf_reader_init(&rd, text, len);
+    mafrec rec = {0};
+    int rc;
+    uint64_t id = 0;
+    while ((rc = maf_next(&rd, &rec, err, errcap)) > 0) {
+        if (query_name) {
+            int e = maf_set_query_byname(&rec, query_name, err, errcap);
+            if (e) { rc = -e; break; }
+        }
+        if (rec.query_idx >= rec.n) {
+            set_err(err, errcap, "panic: index out of bounds: the len is %zu but the index is %zu", rec.n, rec.query_idx);
+            rc = -ORC_E_PANIC;
+            break;
+        }
+        const sline *t = &rec.s[0], *q = &rec.s[rec.query_idx];
+        const size_t n = t->seq.n < q->seq.n ? t->seq.n : q->seq.n;
+        /* cigar.rs:155-199 parse_maf_seq_to_trim over cigar_cat_ext groups */
+        uint64_t hi = 0, hd = 0, ti = 0, td = 0;
+        int head = 1;
+        for (size_t i = 0; i < n;) {
+            char k = cigar_cat_ext(t->seq.p[i], q->seq.p[i]);
+            size_t j = i;
+            while (j < n && cigar_cat_ext(t->seq.p[j], q->seq.p[j]) == k) j++;
+            uint64_t cnt = j - i;
+            if (k == 'I') { if (head) hi += cnt; ti = cnt; }
+            else if (k == 'D') { if (head) hd += cnt; td = cnt; }
+            else { ti = 0; td = 0; head = 0; }
+            i = j;
+        }
+        chain_header(out, t->name, t->size, t->start, t->start + t->align_size, q->name, q->size, q->neg, maf_query_start(&rec),
+                     maf_query_end(&rec), hi, hd, ti, td, id);
+        /* cigar.rs:435-456 parse_maf_seq_to_chain over cigar_cat groups (=/X/both-gap -> M) */
+        chainline d = {0, 0, 0};
+        for (size_t i = 0; i < n;) {
+            char a = t->seq.p[i], b = q->seq.p[i];
+            char k = a == b ? 'M' : a == '-' ? 'I' : b == '-' ? 'D' : 'M';
+            size_t j = i;
+            for (; j < n; j++) {
+                char a2 = t->seq.p[j], b2 = q->seq.p[j];
+                char k2 = a2 == b2 ? 'M' : a2 == '-' ? 'I' : b2 == '-' ? 'D' : 'M';
+                if (k2 != k) break;
+            }
+            chain_unit(out, &d, k, j - i);
+            i = j;
+        }
+        buf_putc(out, '\n'); buf_putu(out, d.size);
+        buf_puts(out, "\n\n");
+        id++;
+    }
+    free(rec.s);
+    return rc < 0 ? -rc : ORC_OK;
+}
+
+int orc_paf2chain(const char *text, size_t len, orc_buf *out, char *err, size_t errcap) {
+    size_t pos = 0;
+    pafrow row = {0};
+    orc_buf conv = {0};
+    int rc = ORC_OK;
+    uint64_t id = 0;
+    while (rc == ORC_OK && paf_next(text, len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int neg = 0, bad = row.n < 12;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) { if (sv_eq_c(row.f[4], "+")) neg = 0; else if (sv_eq_c(row.f[4], "-")) neg = 1; else bad = 1; continue; }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+        sv cg = {0, 0};
+        int have = 0;
+        for (size_t k = 12; k < row.n && !have; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
+        if (!have)
+            for (size_t k = 12; k < row.n && !have; k++)
+                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
+                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
+                    conv.n = 0;
+                    cs_to_cigar(cs, &conv);
+                    cg.p = conv.p; cg.n = conv.n; have = 1;
+                }
+        if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
+        if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
+        /* cigar.rs:202-245 parse_cigar_to_trim: the closure's Result is discarded (a bad token just ends the trim) */
+        uint64_t hi = 0, hd = 0, ti = 0, td = 0;
+        int head = 1;
+        for (size_t i = 0; i < cg.n;) {
+            size_t d0 = i;
+            while (i < cg.n && cg.p[i] >= '0' && cg.p[i] <= '9') i++;
+            size_t o0 = i;
+            while (i < cg.n && !(cg.p[i] >= '0' && cg.p[i] <= '9')) i++;
+            sv digits = {cg.p + d0, o0 - d0};
+            uint64_t cnt;
+            if (i - o0 != 1 || !parse_u64(digits, &cnt)) break;
+            char op = cg.p[o0];
+            if (op == 'M' || op == '=' || op == 'X') { ti = 0; td = 0; head = 0; }
+            else if (op == 'I') { if (head) hi += cnt; ti = cnt; }
+            else if (op == 'D') { if (head) hd += cnt; td = cnt; }
+            else break;
+        }
+        const size_t rec_start = out->n;
+        chain_header(out, row.f[5], u[6], u[7], u[8], row.f[0], u[1], neg, u[2], u[3], hi, hd, ti, td, id);
+        /* cigar.rs:252-295 parse_cigar_to_chain: errors are returned */
+        chainline d = {0, 0, 0};
+        for (size_t i = 0; i < cg.n && rc == ORC_OK;) {
+            size_t d0 = i;
+            while (i < cg.n && cg.p[i] >= '0' && cg.p[i] <= '9') i++;
+            size_t o0 = i;
+            while (i < cg.n && !(cg.p[i] >= '0' && cg.p[i] <= '9')) i++;
+            sv digits = {cg.p + d0, o0 - d0}, op = {cg.p + o0, i - o0};
+            uint64_t cnt;
+            if (op.n != 1) { set_err(err, errcap, "CIGAR OP `%.*s` invalid", (int)op.n, op.p); rc = ORC_E_CIGAR_OP_INVALID; break; }
+            if (!parse_u64(digits, &cnt)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)digits.n, digits.p); rc = ORC_E_PARSE_INT; break; }
+            char c = op.p[0];
+            if (c == 'M' || c == '=' || c == 'X') chain_unit(out, &d, 'M', cnt);
+            else if (c == 'I' || c == 'D') chain_unit(out, &d, c, cnt);
+            else { set_err(err, errcap, "CIGAR OP `%c` invalid", c); rc = ORC_E_CIGAR_OP_INVALID; }
+        }
+        if (rc) { (void)rec_start; break; }
+        buf_putc(out, '\n'); buf_putu(out, d.size);
+        buf_puts(out, "\n\n");
+        id++;
+    }
+    free(row.f); free(row.scratch);
+    orc_buf_free(&conv);
+    return rc;
+}

@@ -110,6 +110,10 @@ int orc_paf_pseudo(const char *paf, size_t paf_len, const char *fa, size_t fa_le
 /* src/tools/validate.rs:44-147 (`validate [-f fix.paf]`): report text + (fix != 0) the re-serialised records */
 int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc_buf *fixed, char *err, size_t errcap);
 
+/* src/converter.rs:57-92 maf2chain, :148-173 paf2chain */
+int orc_maf2chain(const char *text, size_t len, const char *query_name, orc_buf *out, char *err, size_t errcap);
+int orc_paf2chain(const char *text, size_t len, orc_buf *out, char *err, size_t errcap);
+
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */
 void orc_fmt_f32(float v, char *dst /* >= 32 bytes */);      /* ryu 1.0.14 Buffer::format(f32) */

@@ -62,6 +62,9 @@ def lib():
                                                                                 ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_paf_validate.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(OrcBuf), ctypes.POINTER(OrcBuf),
                                        ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_maf2chain.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(OrcBuf), ctypes.c_char_p,
+                                    ctypes.c_size_t]
+        L.orc_paf2chain.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -160,6 +163,14 @@ def paf_validate(paf: bytes, fix=False):
     if rc != 0:
         raise OracleError(rc, err.value.decode("utf-8", "replace"))
     return a, b
+
+
+def maf2chain(text: bytes, query_name=None) -> bytes:
+    return _run(lib().orc_maf2chain, text, len(text), _opt(query_name))
+
+
+def paf2chain(text: bytes) -> bytes:
+    return _run(lib().orc_paf2chain, text, len(text))
 
 
 def make_fai(fa: bytes) -> bytes:

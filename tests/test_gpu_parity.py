@@ -872,3 +872,48 @@ def test_validate_parity(w, ctx):
         with pytest.raises(w.WGAError) as eg:
             _validate(w, ctx, bad)
         assert eo.value.code == code == eg.value.code
+
+
+# ---------------------------------------------------------------- chain (8(f) item 2)
+def test_chain_parity(w, ctx):
+    m2c = lambda t, qn=None: w.run_bytes(w.maf2chain, w.MAFReader(t), qn, ctx=ctx)
+    p2c = lambda t: w.run_bytes(w.paf2chain, w.PAFReader(t), ctx=ctx)
+    assert m2c(TEST_MAF) == orc.maf2chain(TEST_MAF)
+    assert p2c(TEST_PAF) == orc.paf2chain(TEST_PAF)
+    assert m2c(b"") == b"" and p2c(b"") == b""
+    maf = _maf([[b"s t 10 9 + 100 --ACGTAC-GTT", b"s q 5 8 - 50 GGAC-TACAGT-", b"s q2 0 9 + 60 TTACGTAC-GT-"],
+                [b"s t 0 4 + 100 ACGT", b"s q 0 4 + 50 ACGA"], [b"s t 0 3 + 100 ---ACG", b"s q 0 3 + 50 TTT---"]])
+    for qn in (None, "q"):
+        assert m2c(maf, qn) == orc.maf2chain(maf, qn)
+    for seed, kw in ((71, dict(p_neg=0.4)), (72, dict(len_median=30000.0, len_sigma=1.2, p_neg=0.2)), (73, dict(p_gap=0.05, p_bothgap=0.01))):
+        text = bs.gen_maf(bs.maf_params(600 if seed != 72 else 60, seed=seed, **kw))
+        want = orc.maf2chain(text)
+        assert m2c(text) == want
+        assert want == orc.paf2chain(orc.maf2paf(text))          # the same chains through PAF
+        assert p2c(paf(w, ctx, text)) == want
+    old = w.api.SLAB_BYTES
+    try:                                                          # chain ids keep counting across slabs
+        w.api.SLAB_BYTES = 150_000
+        text = bs.gen_maf(bs.maf_params(700, seed=74, p_neg=0.3))
+        assert m2c(text) == orc.maf2chain(text)
+    finally:
+        w.api.SLAB_BYTES = old
+    for seed, kw in ((1, {}), (2, dict(m_only=1)), (3, dict(ops_median=3000.0, ops_sigma=1.0))):
+        text = bs.gen_paf(bs.paf_params(1200 if seed < 3 else 150, seed=seed, **kw))
+        assert p2c(text) == orc.paf2chain(text)
+    line = lambda cg, strand=b"+", tag=True: b"\t".join([b"q", b"1000", b"100", b"200", strand, b"t", b"2000", b"300", b"420", b"1", b"2",
+                                                        b"60"] + ([b"cg:Z:" + cg] if tag else [])) + b"\n"
+    for cg in (b"3I2D5I40=2X10I8=4D6=7I2D3I", b"5I3D", b"7M", b"1D1I1M1I1D"):
+        for strand in (b"+", b"-"):
+            assert p2c(line(cg, strand)) == orc.paf2chain(line(cg, strand))
+    for bad, code in ((line(b"5M2S"), 5), (line(b"5MM"), 5), (line(b"M"), 1), (line(b""), 8), (line(b"5M", tag=False), 6), (b"x\ty\n", 9)):
+        with pytest.raises(orc.OracleError) as eo:
+            orc.paf2chain(bad)
+        with pytest.raises(w.WGAError) as eg:
+            p2c(bad)
+        assert eo.value.code == code == eg.value.code
+        if code in (1, 5, 6):
+            assert str(eg.value) == eo.value.msg
+    with pytest.raises(w.WGAError) as e:
+        m2c(_maf([[b"s t 0 4 + 100 ACGT"]]))
+    assert e.value.code == 8

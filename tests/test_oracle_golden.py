@@ -294,3 +294,30 @@ def test_validate_golden_and_hand_derived():
     with pytest.raises(orc.OracleError) as e:  # get_stat().unwrap()
         orc.paf_validate(TEST_PAF.replace(b"25M10I", b"25M10S", 1))
     assert e.value.code == 8
+
+
+def test_chain_hand_derived():
+    """converter.rs:57-92,148-173 + chain.rs:92-204 + cigar.rs:155-295,435-490 on hand-walked records"""
+    # the reference's own PAF: 25M10I15M20D30M20I30M10D70M and, on '-', 10M10D10M10I20M
+    assert orc.paf2chain(TEST_PAF) == (b"chain\t255\tB\t300\t+\t0\t200\tA\t300\t+\t0\t200\t0\n25\t0\t10\n15\t20\t0\n30\t0\t20\n30\t10\t0\n70\n\n"
+                                       b"chain\t255\tB\t300\t+\t200\t250\tA\t300\t-\t50\t250\t1\n10\t10\t0\n10\t0\t10\n20\n\n")
+    # head / tail indels are trimmed off the coordinates; the tail keeps only the LAST I and the LAST D run; on '-' the
+    # new query end is computed from the new query start (chain.rs:133-138)
+    line = lambda cg, strand: b"\t".join([b"q", b"1000", b"100", b"200", strand, b"t", b"2000", b"300", b"420", b"1", b"2", b"60",
+                                         b"cg:Z:" + cg]) + b"\n"
+    assert orc.paf2chain(line(b"3I2D5I40=2X10I8=4D6=7I2D3I", b"+")) == (
+        b"chain\t255\tt\t2000\t+\t302\t418\tq\t1000\t+\t108\t197\t0\n42\t0\t10\n8\t4\t0\n6\n\n")
+    assert orc.paf2chain(line(b"3I2D5I40=2X10I8=4D6=7I2D3I", b"-")) == (
+        b"chain\t255\tt\t2000\t+\t302\t418\tq\t1000\t-\t808\t189\t0\n42\t0\t10\n8\t4\t0\n6\n\n")
+    assert orc.paf2chain(line(b"5I3D", b"+")) == b"chain\t255\tt\t2000\t+\t303\t417\tq\t1000\t+\t105\t195\t0\n0\n\n"
+    for bad, code in ((line(b"5M2S", b"+"), 5), (line(b"5MM", b"+"), 5), (line(b"M", b"+"), 1), (line(b"", b"+"), 8)):
+        with pytest.raises(orc.OracleError) as e:
+            orc.paf2chain(bad)
+        assert e.value.code == code
+    # MAF: the same chain as converting to PAF first (same coordinates, '='/'X' merge into one ungapped block)
+    maf = _maf([[b"s t 10 9 + 100 --ACGTAC-GTT", b"s q 5 8 - 50 GGAC-TACAGT-"],
+                [b"s t 0 4 + 100 ACGT", b"s q 0 4 + 50 ACGA"]])
+    assert orc.maf2chain(maf) == orc.paf2chain(orc.maf2paf(maf))
+    assert orc.maf2chain(maf) == (b"chain\t255\tt\t100\t+\t10\t18\tq\t50\t-\t7\t43\t0\n2\t1\t0\n3\t0\t1\n2\n\n"
+                                  b"chain\t255\tt\t100\t+\t0\t4\tq\t50\t+\t0\t4\t1\n4\n\n")
+    assert orc.maf2chain(TEST_MAF) == orc.paf2chain(orc.maf2paf(TEST_MAF))

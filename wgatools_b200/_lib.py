@@ -68,6 +68,10 @@ ABI = {
                                      ctypes.c_void_p, ctypes.c_char_p, _P(Span), _P(Span)]),
     "wga_paf_validate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
                                        ctypes.c_int, _P(Span), _P(Span)]),
+    "wga_maf2chain": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p,
+                                    ctypes.c_uint64, _P(Span), _P(ctypes.c_uint64)]),
+    "wga_paf2chain": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64,
+                                    _P(Span), _P(ctypes.c_uint64)]),
     "wga_last_record_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, _P(ctypes.c_uint64)]),
 }
 

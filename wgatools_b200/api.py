@@ -397,6 +397,29 @@ def generate_pesudo_maf(reader: PAFReader, out_dir, fa_path=None, target=None, c
             f.write(data)
 
 
+def maf2chain(mafreader, writer, query_name=None, ctx=None):
+    """src/converter.rs:57-92: one chain per MAF record; chain ids enumerate the records of the file"""
+    ctx = ctx or default_context()
+    base = 0
+    for p, n, mem, flags in _maf_slabs(mafreader, ctx):
+        sp, nrec = Span(), ctypes.c_uint64()
+        ctx._check(ctx.L.wga_maf2chain(ctx.h, p, n, mem, flags, _opt(query_name), base, ctypes.byref(sp), ctypes.byref(nrec)))
+        if sp.len:
+            writer.write(ctypes.string_at(sp.data, sp.len))
+        base += nrec.value
+
+
+def paf2chain(pafreader: PAFReader, writer, ctx=None):
+    """src/converter.rs:148-173"""
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(pafreader.data)
+    sp = Span()
+    ctx._check(ctx.L.wga_paf2chain(ctx.h, ctypes.c_void_p(base), len(pafreader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, 0, ctypes.byref(sp),
+                                   None))
+    if sp.len:
+        writer.write(ctypes.string_at(sp.data, sp.len))
+
+
 def parallel_validatepaf(reader: PAFReader, writer, fix_writer=None, fix_flag=None, ctx=None):
     """src/tools/validate.rs:44-71: report -> writer; with a fix_writer the corrected records -> fix_writer"""
     ctx = ctx or default_context()

@@ -11,6 +11,7 @@
 #include "stat.cuh"
 #include "stat_acc.hpp"
 #include "tokenize.cuh"
+#include "chain.cuh"
 #include "walk_types.cuh"
 #ifdef WGA_WITH_CALL
 #include "call.cuh"
@@ -718,6 +719,54 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     if (!cnt11) return ctx->err_code;
     LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
     ctx->last_counts_valid = true;
+    return finish_output(ctx, d_out, total, mem, flags, out);
+}
+
+// ---------------------------------------------------------------- maf2chain (converter.rs:57-92)
+int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name, uint64_t id_base,
+                  wga_span *out, uint64_t *n_records) {
+    if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    if (n_records) *n_records = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem, flags));
+    Prep P;
+    WGA_TRY(prepare_maf(ctx, flags, query_name, 0, &P));
+    const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
+    if (n_records) *n_records = n_rec;
+    if (n_rec == 0 || n_items == 0) return sync_check(ctx);
+    unsigned long long *rec_cnt = ctx->buf<unsigned long long>(B_REC_CNT, n_rec * 5);
+    if (!rec_cnt) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
+    Runs RU;
+    WGA_TRY(run_walk<MODE_RUNS_EXT>(ctx, P, rec_cnt, &RU));
+    const uint64_t n_runs = RU.n_runs;
+    uint64_t *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
+    uint64_t *rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
+    uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
+    uint64_t *tno = ctx->buf<uint64_t>(B_GEN_C, n_rec), *qno = ctx->buf<uint64_t>(B_GEN_D, n_rec);
+    uint32_t *tnl = ctx->buf<uint32_t>(B_GEN_E, n_rec), *qnl = ctx->buf<uint32_t>(B_GEN_F, n_rec);
+    uint64_t *m6 = ctx->buf<uint64_t>(B_GEN_G, 6 * n_rec);
+    if (!run_len || !rec_run_first || !row_len || !row_off || !tno || !qno || !tnl || !qnl || !m6) return ctx->err_code;
+    LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, RU.run_base, n_items, n_runs, rec_run_first);
+    LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, RU.run_pos, RU.run_rec, P.rc.ncols, run_len, (uint32_t *)nullptr);
+    LAUNCH(ctx, k_chain_meta_maf, grid_for(n_rec, 256), 256, n_rec, P.sl, (const uint64_t *)P.rc.tl, (const uint64_t *)P.rc.ql, tno, qno, tnl,
+           qnl, m6);
+    ChainView V;
+    V.n_rec = n_rec; V.id_base = id_base; V.text = ctx->d_text; V.t_name_off = tno; V.q_name_off = qno; V.t_name_len = tnl;
+    V.q_name_len = qnl; V.t_size = m6; V.q_size = m6 + n_rec; V.t_start = m6 + 2 * n_rec; V.t_end = m6 + 3 * n_rec;
+    V.q_start = m6 + 4 * n_rec; V.q_end = m6 + 5 * n_rec; V.neg = P.rc.neg; V.skip = P.rc.skip; V.run_first = rec_run_first;
+    V.run_len = run_len; V.run_type = RU.run_cls; V.maf = 1; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
+    LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
+    uint64_t total;
+    WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    V.out = d_out;
+    LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
@@ -1546,6 +1595,73 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
+// ---------------------------------------------------------------- paf2chain (converter.rs:148-173)
+int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
+                  uint64_t *n_records) {
+    if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    if (n_records) *n_records = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    PafPrep PP;
+    WGA_TRY(paf_fasta_prepare(ctx, len, nullptr, nullptr, 1, &PP, false, nullptr));
+    const uint64_t n_rec = PP.n_rec;
+    if (n_records) *n_records = n_rec;
+    if (n_rec == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    PafRecs R = PP.R;
+    P2mRecs X = PP.X;
+    unsigned long long *err_key = PP.err_key;
+    uint64_t *n_ops = PP.n_ops, *op_base = PP.op_base;
+    LAUNCH(ctx, k_p2m_ops<0>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+           (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key);
+    WGA_TRY(exclusive_sum(ctx, n_ops, op_base, n_rec + 1));
+    uint64_t sc[2];
+    WGA_TRY(read_scalars(ctx, {op_base + n_rec, err_key}, sc));
+    if (sc[1] != kNoErr) {
+        const int code = (int)(sc[1] & 0xFF);
+        const uint64_t rec = sc[1] >> 32;
+        std::string msg;
+        if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+        else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR)";
+        else {
+            uint64_t oc[2];
+            WGA_TRY(read_scalars(ctx, {R.cig_off + rec, R.cig_len + rec}, oc));
+            std::string cg((size_t)std::min<uint64_t>(oc[1], 1u << 20), '\0');
+            if (!cg.empty()) WGA_CK(cudaMemcpy(&cg[0], d_text + oc[0], cg.size(), cudaMemcpyDeviceToHost));
+            msg = paf_cigar_error_text(cg, code);
+        }
+        ctx->set_error(code, rec, msg);
+        return code;
+    }
+    const uint64_t n_opsT = sc[0];
+    uint64_t *op_len = ctx->buf<uint64_t>(B_RUN_POS, n_opsT + 1);
+    uint8_t *op_type = ctx->buf<uint8_t>(B_RUN_CLS, n_opsT + 1);
+    uint32_t *op_rec = ctx->buf<uint32_t>(B_RUN_REC, n_opsT + 1), *op_pos = ctx->buf<uint32_t>(B_RUN_DL, n_opsT + 1);
+    uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
+    if (!op_len || !op_type || !op_rec || !op_pos || !row_len || !row_off) return ctx->err_code;
+    LAUNCH(ctx, k_p2m_ops<1>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)op_base, op_len, op_type, op_rec,
+           op_pos, err_key);
+    ChainView V;
+    V.n_rec = n_rec; V.id_base = id_base; V.text = d_text; V.t_name_off = R.t_name_off; V.q_name_off = R.q_name_off;
+    V.t_name_len = R.t_name_len; V.q_name_len = R.q_name_len; V.t_size = R.t_size; V.q_size = R.q_size; V.t_start = R.t_start;
+    V.t_end = X.t_end; V.q_start = R.q_start; V.q_end = X.q_end; V.neg = R.neg; V.skip = nullptr; V.run_first = op_base;
+    V.run_len = op_len; V.run_type = op_type; V.maf = 0; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
+    LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
+    uint64_t total;
+    WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    V.out = d_out;
+    LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    return finish_output(ctx, d_out, total, mem, flags, out);
+}
+
 // ---------------------------------------------------------------- validate (validate.rs:44-147)
 int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, int fix, wga_span *report,
                      wga_span *fixed) {
@@ -1838,6 +1954,7 @@ int wga_paf_pseudo(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_f
     return WGA_E_UNSUPPORTED;
 }
 int wga_paf_validate(wga_ctx *, const void *, uint64_t, int, uint32_t, int, wga_span *, wga_span *) { return WGA_E_UNSUPPORTED; }
+int wga_paf2chain(wga_ctx *, const void *, uint64_t, int, uint32_t, uint64_t, wga_span *, uint64_t *) { return WGA_E_UNSUPPORTED; }
 #endif
 #ifndef WGA_WITH_CALL
 int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
