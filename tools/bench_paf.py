@@ -141,6 +141,18 @@ def main():
     orc.stat_paf(smp)
     cpu = len(smp) / (time.perf_counter() - t0) / 1e9
     report("stat -f paf (config 4 shape)", len(paf), ms_dev, ms_e2e, 0, cpu, len(smp), {"records": args.records})
+    # paf2chain on the same PAF (the only command of the reference with a published timing)
+    spc = w.api.Span()
+
+    def pc(ptr, mem):
+        def run():
+            ctx._check(L.wga_paf2chain(ctx.h, ptr, len(paf), mem, 1, 0, ctypes.byref(spc), None))
+        return run
+    ms_dev, ms_e2e = timed(pc(ctypes.c_void_p(d.data_ptr()), 1), args.steps), timed(pc(ctypes.c_void_p(hp), 0), args.steps)
+    t0 = time.perf_counter()
+    orc.paf2chain(smp)
+    cpu = len(smp) / (time.perf_counter() - t0) / 1e9
+    report("paf2chain (config 4 shape)", len(paf), ms_dev, ms_e2e, spc.len, cpu, len(smp), {"records": args.records})
     del d
     if args.only == "stat":
         return
