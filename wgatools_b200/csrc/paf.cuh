@@ -219,6 +219,99 @@ __global__ void __launch_bounds__(128, 8) k_paf_cigar_counts_warp(uint64_t n_rec
     }
 }
 
+// The same warp-per-record scan producing the ordered OP TABLE of every record (paf2chain; the op tables of paf2maf /
+// call -f paf / pafpseudo still use their one-thread kernels).  PASS 0: ops per record + the slow flag (malformed or
+// 9+ digit lengths: redone by the exact kernel, which also raises the reference's error); PASS 1: (length, type) of op
+// k at op_base[r] + k, type 0 = M/=/X, 1 = I, 2 = D.
+template <int PASS>
+__global__ void __launch_bounds__(128, 8) k_paf_ops_warp(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
+                                                         uint64_t *__restrict__ n_ops, uint8_t *__restrict__ slow,
+                                                         const uint64_t *__restrict__ op_base, uint64_t *__restrict__ op_len,
+                                                         uint8_t *__restrict__ op_type) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (r >= n_rec) return;
+    const uint8_t negf = R.neg[r];
+    const uint64_t len = R.cig_len[r];
+    if ((negf & 2) || len == 0) { if (PASS == 0 && lane == 0) { slow[r] = 1; n_ops[r] = 0; } return; }
+    if (PASS == 1 && slow[r]) return;
+    const uint8_t *p = text + R.cig_off[r];
+    const uint64_t a = reinterpret_cast<uintptr_t>(p) & 15u;
+    const uint8_t *base = p - a;
+    const uint64_t nvec = (a + len + 15) >> 4;
+    bool bad = false;
+    uint64_t done = 0;  // ops of the previous steps
+    uint32_t carry_val = 0, carry_nd = 0;
+    for (uint64_t v0 = 0; v0 < nvec; v0 += 32) {
+        const uint64_t vi = v0 + lane;
+        const bool have = vi < nvec;
+        uint4 cur = make_uint4(0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au);
+        if (have) cur = ldg16(base + 16 * vi);
+        uint32_t t_nd, t_val = 0;
+        {
+            const unsigned long long F = ((unsigned long long)digit_flags(cur.w) << 32) | digit_flags(cur.z);
+            const unsigned long long nF = ~F & 0x8080808080808080ull;
+            t_nd = nF ? (uint32_t)__clzll((long long)nF) >> 3 : 8u;
+            if (t_nd == 8u && (digit_flags(cur.y) & 0x80000000u)) t_nd = 9u;
+            if (PASS == 1 && t_nd) {
+                const unsigned long long H = ((unsigned long long)cur.w << 32) | cur.z;
+                const unsigned long long keep = t_nd >= 8u ? ~0ull : ~0ull << (8u * (8u - t_nd));
+                unsigned long long v = ((H & keep) | (0x3030303030303030ull & ~keep)) - 0x3030303030303030ull;
+                v = v * 10 + (v >> 8);
+                v = (((v & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((v >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
+                t_val = (uint32_t)v;
+            }
+        }
+        uint32_t val = __shfl_up_sync(0xFFFFFFFFu, t_val, 1), nd = __shfl_up_sync(0xFFFFFFFFu, t_nd, 1);
+        if (lane == 0) { val = carry_val; nd = carry_nd; }
+        carry_val = __shfl_sync(0xFFFFFFFFu, t_val, 31);
+        carry_nd = __shfl_sync(0xFFFFFFFFu, t_nd, 31);
+        const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;
+        const int klo = idx0 < 0 ? (int)-idx0 : 0;
+        const int khi = !have ? 0 : (uint64_t)(idx0 + 16) > len ? (int)((int64_t)len - idx0) : 16;
+        if (idx0 <= 0) { val = 0; nd = 0; }
+        const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
+        // ops in this piece -> position of the piece's first op inside the record
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t ch = (cw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            mine += (k >= klo && k < khi && (ch - '0') > 9u) ? 1u : 0u;
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (uint32_t)d) incl += y;
+        }
+        const uint32_t step_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint64_t o = (PASS == 1 ? op_base[r] : 0) + done + (incl - mine);
+        done += step_total;
+        if (!have) continue;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t ch = (cw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            const uint32_t dg = ch - '0';
+            const bool in = k >= klo && k < khi;
+            const bool isd = in && dg <= 9u, iso = in && dg > 9u;
+            const bool m = ch == 'M' || ch == '=' || ch == 'X', ii = ch == 'I', dd = ch == 'D';
+            if (PASS == 0) bad = bad || (iso && (nd == 0u || nd > 8u || !(m || ii || dd)));
+            if (PASS == 1 && iso) {
+                op_len[o] = val;
+                op_type[o] = ii ? 1 : dd ? 2 : 0;
+                ++o;
+            }
+            val = isd ? val * 10u + dg : (iso ? 0u : val);
+            nd = isd ? nd + 1u : (iso ? 0u : nd);
+        }
+        if (PASS == 0 && (uint64_t)(idx0 + 16) >= len && nd != 0u) bad = true;
+    }
+    if (PASS == 0) {
+        bad = __any_sync(0xFFFFFFFFu, bad);
+        if (lane == 0) { slow[r] = bad ? 1 : 0; n_ops[r] = bad ? 0 : done; }
+    }
+}
+
 // Exact path, one record per thread: the tokenizer of cigar.rs:43-75 with the reference's errors.  only != nullptr:
 // just the records the warp kernel flagged.
 __global__ void k_paf_cigar_counts(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,

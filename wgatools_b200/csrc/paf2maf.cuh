@@ -140,10 +140,12 @@ __global__ void k_p2m_revcomp_check(uint64_t n_rec, PafRecs R, P2mRecs X, const 
 template <int PASS>
 __global__ void k_p2m_ops(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R, uint64_t *__restrict__ n_ops,
                           const uint64_t *__restrict__ op_base, uint64_t *__restrict__ op_len, uint8_t *__restrict__ op_type,
-                          uint32_t *__restrict__ op_rec, uint32_t *__restrict__ op_pos, unsigned long long *err_key) {
+                          uint32_t *__restrict__ op_rec, uint32_t *__restrict__ op_pos, unsigned long long *err_key,
+                          const uint8_t *__restrict__ only = nullptr) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rec) return;
     if (r == n_rec) { if (PASS == 0) n_ops[r] = 0; return; }
+    if (only && !only[r]) return;  // the warp kernel (paf.cuh k_paf_ops_warp) already did this record
     const uint64_t len = R.cig_len[r];
     const uint8_t *p = text + R.cig_off[r];
     if ((R.neg[r] & 2) || len == 0) {
@@ -172,8 +174,8 @@ __global__ void k_p2m_ops(uint64_t n_rec, const uint8_t *__restrict__ text, PafR
         if (PASS == 1) {
             op_len[o] = val;
             op_type[o] = (op == 'I') ? 1 : (op == 'D') ? 2 : 0;
-            op_rec[o] = (uint32_t)r;
-            op_pos[o] = (uint32_t)(pos > 0x7FFFF0ull ? 0x7FFFF0ull : pos);
+            if (op_rec) op_rec[o] = (uint32_t)r;
+            if (op_pos) op_pos[o] = (uint32_t)(pos > 0x7FFFF0ull ? 0x7FFFF0ull : pos);
             ++o;
         }
         ++cnt;

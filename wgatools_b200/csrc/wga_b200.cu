@@ -1615,8 +1615,13 @@ int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
     P2mRecs X = PP.X;
     unsigned long long *err_key = PP.err_key;
     uint64_t *n_ops = PP.n_ops, *op_base = PP.op_base;
+    uint8_t *slow = ctx->buf<uint8_t>(B_REC_SKIP, n_rec + 1);  // records the warp kernel leaves to the exact one
+    if (!slow) return ctx->err_code;
+    LAUNCH(ctx, k_paf_ops_warp<0>, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, n_ops, slow, (const uint64_t *)nullptr,
+           (uint64_t *)nullptr, (uint8_t *)nullptr);
+    WGA_CK(cudaMemsetAsync(n_ops + n_rec, 0, 8, ctx->stream));
     LAUNCH(ctx, k_p2m_ops<0>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-           (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key);
+           (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key, (const uint8_t *)slow);
     WGA_TRY(exclusive_sum(ctx, n_ops, op_base, n_rec + 1));
     uint64_t sc[2];
     WGA_TRY(read_scalars(ctx, {op_base + n_rec, err_key}, sc));
@@ -1641,11 +1646,12 @@ int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
     const uint64_t n_opsT = sc[0];
     uint64_t *op_len = ctx->buf<uint64_t>(B_RUN_POS, n_opsT + 1);
     uint8_t *op_type = ctx->buf<uint8_t>(B_RUN_CLS, n_opsT + 1);
-    uint32_t *op_rec = ctx->buf<uint32_t>(B_RUN_REC, n_opsT + 1), *op_pos = ctx->buf<uint32_t>(B_RUN_DL, n_opsT + 1);
     uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
-    if (!op_len || !op_type || !op_rec || !op_pos || !row_len || !row_off) return ctx->err_code;
-    LAUNCH(ctx, k_p2m_ops<1>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)op_base, op_len, op_type, op_rec,
-           op_pos, err_key);
+    if (!op_len || !op_type || !row_len || !row_off) return ctx->err_code;
+    LAUNCH(ctx, k_paf_ops_warp<1>, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, n_ops, slow, (const uint64_t *)op_base, op_len,
+           op_type);
+    LAUNCH(ctx, k_p2m_ops<1>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)op_base, op_len, op_type,
+           (uint32_t *)nullptr, (uint32_t *)nullptr, err_key, (const uint8_t *)slow);
     ChainView V;
     V.n_rec = n_rec; V.id_base = id_base; V.text = d_text; V.t_name_off = R.t_name_off; V.q_name_off = R.q_name_off;
     V.t_name_len = R.t_name_len; V.q_name_len = R.q_name_len; V.t_size = R.t_size; V.q_size = R.q_size; V.t_start = R.t_start;
