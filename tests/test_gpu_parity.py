@@ -917,3 +917,71 @@ def test_chain_parity(w, ctx):
     with pytest.raises(w.WGAError) as e:
         m2c(_maf([[b"s t 0 4 + 100 ACGT"]]))
     assert e.value.code == 8
+
+
+# ---------------------------------------------------------------- fuzz: many tiny MAFs with awkward text
+def _fuzz_maf(rng):
+    ws = lambda: rng.choice([b" ", b"\t", b"  ", b" \t", b"\t\t "])
+    nl = lambda: rng.choice([b"\n", b"\n", b"\n", b"\r\n"])
+    out = [rng.choice([b"##maf version=1", b"a score=0", b"s hdr 0 1 + 5 A", b""]) + nl()]
+    for _ in range(rng.randrange(1, 7)):
+        out.append(rng.choice([b"a score=1", b"", b"# c", b"a", b"i x y", b"q t 99", b"e z"]) + nl())
+        n = rng.randrange(0, 70)
+        k = rng.choice([1] + [2] * 14 + [3] * 5)
+        names = [b"t.chr1"] + [rng.choice([b"q", b"q", b"q2", b"query.long_name-1"]) for _ in range(k - 1)]
+        for j in range(k):
+            ln = n if rng.random() < 0.85 else max(0, n + rng.randrange(-3, 4))
+            alpha = b"ACGTACGTACGTNacgt-" if rng.random() < 0.7 else b"AC-"
+            seq = bytes(rng.choice(alpha) for _ in range(ln))
+            if j == 0 and rng.random() < 0.5:
+                seq = seq.replace(b"-", b"A")
+            ali = sum(1 for c in seq if c != 45)
+            start = rng.randrange(0, 1000)
+            size = start + ali + rng.randrange(0, 50)
+            fields = [b"s", names[j], b"%d" % start, b"%d" % ali, rng.choice([b"+", b"+", b"-"]), b"%d" % size, seq]
+            if rng.random() < 0.008:
+                fields[rng.randrange(2, 6)] = rng.choice([b"x1", b"", b"-3", b"*"])
+            if rng.random() < 0.006:
+                fields.append(b"extra")
+            if rng.random() < 0.006:
+                fields = fields[:rng.randrange(2, 7)]
+            line = rng.choice([b"", b"", b""]) + b"".join(f + ws() for f in fields[:-1]) + fields[-1]
+            out.append(line + nl())
+        if rng.random() < 0.8:
+            out.append(nl())
+    text = b"".join(out)
+    return text if rng.random() < 0.9 else text.rstrip(b"\r\n")
+
+
+def test_fuzz_small_mafs(w, ctx):
+    rng = random.Random(20260924)
+    from wgatools_b200._lib import CallOpts
+    n_err = n_ok = 0
+    for it in range(250):
+        text = _fuzz_maf(rng)
+        qn = rng.choice([None, None, None, None, None, "q", "q2"])
+        cases = [
+            ("maf2paf", lambda: orc.maf2paf(text, qn), lambda: w.run_bytes(w.maf2paf, w.MAFReader(text), qn, ctx=ctx)),
+            ("stat", lambda: orc.stat_maf(text, False, qn), lambda: w.run_bytes(w.stat_maf, w.MAFReader(text), False, qn, ctx=ctx)),
+            ("stat-each", lambda: orc.stat_maf(text, True, qn), lambda: w.run_bytes(w.stat_maf, w.MAFReader(text), True, qn, ctx=ctx)),
+            ("chain", lambda: orc.maf2chain(text, qn), lambda: w.run_bytes(w.maf2chain, w.MAFReader(text), qn, ctx=ctx)),
+            ("call", lambda: orc.call_maf(text, snp=True, inv=True, svlen=1, query_name=qn, chunk_size=7),
+             lambda: w.run_bytes(w.call_var_maf, w.MAFReader(text), None, True, True, 1, False, None, qn, None, 7, ctx=ctx)),
+        ]
+        for name, fo, fg in cases:
+            want = err_o = None
+            try:
+                want = fo()
+            except orc.OracleError as e:
+                err_o = e
+            if err_o is None:
+                assert fg() == want, (it, name, text)
+                n_ok += 1
+            else:
+                with pytest.raises(w.WGAError) as eg:
+                    fg()
+                assert eg.value.code == err_o.code, (it, name, text, err_o.msg, str(eg.value))
+                if err_o.code in (1, 2, 3, 4, 7) and name != "call":
+                    assert str(eg.value) == err_o.msg, (it, name, text)
+                n_err += 1
+    assert n_ok > 300 and n_err > 50
