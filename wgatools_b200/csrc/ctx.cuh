@@ -76,7 +76,7 @@ struct wga_ctx {
     int err_code = 0;
     uint64_t err_where = 0;
     std::string err_msg;
-    std::string pseudo_index;  // host text of the last wga_paf_pseudo file index
+    std::string host_text;  // library-owned host text of the last call (pafpseudo file index, validate report)
     void *tok_cache = nullptr;  // TokCache (wga_b200.cu): index of the last tokenised MAF slab
     // accounting
     uint64_t n_own = 0, n_cub = 0;

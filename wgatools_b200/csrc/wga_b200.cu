@@ -1680,7 +1680,7 @@ int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint
     PafPrep PP;
     WGA_TRY(paf_fasta_prepare(ctx, len, nullptr, nullptr, 1, &PP, false, nullptr));
     const uint64_t n_rec = PP.n_rec;
-    std::string &rep = ctx->pseudo_index;  // host text owned by the ctx
+    std::string &rep = ctx->host_text;  // host text owned by the ctx
     rep.clear();
     uint64_t nbad[2] = {0, 0};
     std::string qlist, tlist;
@@ -1755,7 +1755,7 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     cudaSetDevice(ctx->device);
     out->data = nullptr; out->len = 0;
     index->data = nullptr; index->len = 0;
-    ctx->pseudo_index.clear();
+    ctx->host_text.clear();
     walk_begin(ctx);
     WGA_TRY(stage_text(ctx, text, len, mem));
     unsigned long long *tag_key = ctx->buf<unsigned long long>(B_PP_T, 1);
@@ -1924,7 +1924,7 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     std::vector<uint64_t> info(4 * n_targets);
     WGA_CK(cudaMemcpyAsync(info.data(), finfo, info.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGA_TRY(sync_check(ctx));
-    std::string &idx = ctx->pseudo_index;
+    std::string &idx = ctx->host_text;
     for (uint64_t t = 0; t < n_targets; ++t) {
         std::string name((size_t)info[4 * t + 1], '\0');
         if (!name.empty()) WGA_CK(cudaMemcpy(&name[0], d_text + info[4 * t], name.size(), cudaMemcpyDeviceToHost));
