@@ -201,6 +201,12 @@ int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
 int wga_paf2chain(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
                   uint64_t *n_records);
 
+/* ---- pafcov: src/tools/pafcov.rs:13-60 + src/parser/cigar.rs:710-741 ------------------------------- */
+/* BED lines "{target}\t{pos}\t{pos+1}\t{count}\n" for every base of every target (vector length = target_length of
+ * the target's first record; M and = cover, I and S do not move, every other op advances).  Targets come in
+ * first-occurrence order.  One slab = the whole PAF (coverage is a reduction over all records). */
+int wga_paf_cov(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, wga_span *out);
+
 /* ---- validate: src/tools/validate.rs:44-147 (a free rider on the PAF CIGAR counters) ------------ */
 /* report (always host memory) = the reference's report text: counts, then "{name}:{start}-{end}" of every record whose
  * query / target end differs from start + the CIGAR's consumed bases; fix != 0: `fixed` = every record re-serialised

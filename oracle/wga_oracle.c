@@ -2066,3 +2066,76 @@ int orc_paf2chain(const char *text, size_t len, orc_buf *out, char *err, size_t 
     orc_buf_free(&conv);
     return rc;
 }
+
+/* ------------------------------------------------------------------ pafcov */
+/* src/tools/pafcov.rs:13-60 + src/parser/cigar.rs:710-741 update_cov_vec.  Per target a coverage vector of the FIRST
+ * record's target_length; M and = add 1 over [pos, pos+len) clipped to the vector, I and S do not move, every other op
+ * (X, D, N, ...) advances pos (Q4).  Output: one BED line per base.  The reference folds per rayon worker and iterates
+ * a HashMap; here targets come in first-occurrence order. */
+int orc_pafcov(const char *text, size_t len, orc_buf *out, char *err, size_t errcap) {
+    size_t pos = 0;
+    pafrow row = {0};
+    orc_buf conv = {0};
+    struct tgt { sv name; uint64_t L; uint32_t *cov; } *T = NULL;
+    size_t nt = 0, capt = 0;
+    int rc = ORC_OK;
+    while (rc == ORC_OK && paf_next(text, len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int bad = row.n < 12;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) { if (!sv_eq_c(row.f[4], "+") && !sv_eq_c(row.f[4], "-")) bad = 1; continue; }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+        size_t ti = nt;
+        for (size_t k = 0; k < nt; k++) if (sv_eq(T[k].name, row.f[5])) { ti = k; break; }
+        if (ti == nt) {
+            if (nt == capt) { capt = capt ? capt * 2 : 16; T = (struct tgt *)realloc(T, capt * sizeof *T); }
+            T[nt].name = row.f[5]; T[nt].L = u[6]; T[nt].cov = (uint32_t *)calloc(u[6] ? u[6] : 1, sizeof(uint32_t));
+            nt++;
+        }
+        sv cg = {0, 0};
+        int have = 0;
+        for (size_t k = 12; k < row.n && !have; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
+        if (!have)
+            for (size_t k = 12; k < row.n && !have; k++)
+                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
+                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
+                    conv.n = 0;
+                    cs_to_cigar(cs, &conv);
+                    cg.p = conv.p; cg.n = conv.n; have = 1;
+                }
+        if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
+        if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
+        uint64_t p = u[7];
+        for (size_t i = 0; i < cg.n;) {
+            size_t d0 = i;
+            while (i < cg.n && cg.p[i] >= '0' && cg.p[i] <= '9') i++;
+            size_t o0 = i;
+            while (i < cg.n && !(cg.p[i] >= '0' && cg.p[i] <= '9')) i++;
+            sv digits = {cg.p + d0, o0 - d0}, op = {cg.p + o0, i - o0};
+            uint64_t cnt;
+            if (op.n != 1) { set_err(err, errcap, "CIGAR OP `%.*s` invalid", (int)op.n, op.p); rc = ORC_E_CIGAR_OP_INVALID; break; }
+            if (!parse_u64(digits, &cnt)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)digits.n, digits.p); rc = ORC_E_PARSE_INT; break; }
+            char c = op.p[0];
+            if (c == 'M' || c == '=') {
+                uint64_t lo = p < T[ti].L ? p : T[ti].L, hi = (cnt > T[ti].L || p + cnt > T[ti].L) ? T[ti].L : p + cnt;
+                for (uint64_t x = lo; x < hi; x++) T[ti].cov[x]++;
+                p += cnt;
+            } else if (c == 'I' || c == 'S') {
+            } else p += cnt;
+        }
+    }
+    if (rc == ORC_OK)
+        for (size_t k = 0; k < nt; k++)
+            for (uint64_t x = 0; x < T[k].L; x++) {
+                buf_put(out, T[k].name.p, T[k].name.n); buf_putc(out, '\t'); buf_putu(out, x); buf_putc(out, '\t'); buf_putu(out, x + 1);
+                buf_putc(out, '\t'); buf_putu(out, T[k].cov[x]); buf_putc(out, '\n');
+            }
+    for (size_t k = 0; k < nt; k++) free(T[k].cov);
+    free(T); free(row.f); free(row.scratch);
+    orc_buf_free(&conv);
+    return rc;
+}

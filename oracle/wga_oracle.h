@@ -114,6 +114,9 @@ int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc
 int orc_maf2chain(const char *text, size_t len, const char *query_name, orc_buf *out, char *err, size_t errcap);
 int orc_paf2chain(const char *text, size_t len, orc_buf *out, char *err, size_t errcap);
 
+/* src/tools/pafcov.rs:13-60 + cigar.rs:710-741 (`pafcov`): per-base BED coverage of every target */
+int orc_pafcov(const char *text, size_t len, orc_buf *out, char *err, size_t errcap);
+
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */
 void orc_fmt_f32(float v, char *dst /* >= 32 bytes */);      /* ryu 1.0.14 Buffer::format(f32) */

@@ -65,6 +65,7 @@ def lib():
         L.orc_maf2chain.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(OrcBuf), ctypes.c_char_p,
                                     ctypes.c_size_t]
         L.orc_paf2chain.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_pafcov.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -171,6 +172,10 @@ def maf2chain(text: bytes, query_name=None) -> bytes:
 
 def paf2chain(text: bytes) -> bytes:
     return _run(lib().orc_paf2chain, text, len(text))
+
+
+def pafcov(text: bytes) -> bytes:
+    return _run(lib().orc_pafcov, text, len(text))
 
 
 def make_fai(fa: bytes) -> bytes:

@@ -985,3 +985,29 @@ def test_fuzz_small_mafs(w, ctx):
                     assert str(eg.value) == err_o.msg, (it, name, text)
                 n_err += 1
     assert n_ok > 300 and n_err > 50
+
+
+# ---------------------------------------------------------------- pafcov (8(f) item 3)
+def test_pafcov_parity(w, ctx):
+    cov = lambda t: w.run_bytes(w.pafcov, w.PAFReader(t), ctx=ctx)
+    line = lambda cg, t=b"t", tl=20, ts=2, tag=True: b"\t".join([b"q", b"100", b"0", b"10", b"+", t, b"%d" % tl, b"%d" % ts, b"12", b"1", b"2",
+                                                                 b"60"] + ([b"cg:Z:" + cg] if tag else [])) + b"\n"
+    small = line(b"3=2X2I4M3D5=") + line(b"30M", ts=15, tl=999) + line(b"2=1N2H1=", t=b"u", tl=7, ts=0) + line(b"4=", ts=100) + \
+        line(b"1=", t=b"zero", tl=0, ts=0)
+    assert cov(small) == orc.pafcov(small)
+    assert cov(TEST_PAF) == orc.pafcov(TEST_PAF)
+    assert cov(b"") == b"" and cov(b"#only a comment\n") == b""
+    for seed, kw in ((1, dict(chr_size=30_000, n_genomes=2, n_chr=2)), (2, dict(chr_size=200_000, n_genomes=1, n_chr=3, m_only=1))):
+        text = bs.gen_paf(bs.paf_params(400, seed=seed, ops_median=40.0, **kw))
+        want = orc.pafcov(text)
+        assert cov(text) == want
+        assert max(int(l.rsplit(b"\t", 1)[1]) for l in want.splitlines()) >= 2
+    for bad, code in ((line(b"5MM"), 5), (line(b"M"), 1), (line(b""), 8), (line(b"3=", tag=False), 6), (b"a\tb\n", 9),
+                      (line(b"3=") + line(b"2=9999999999999999999999M"), 1)):
+        with pytest.raises(orc.OracleError) as eo:
+            orc.pafcov(bad)
+        with pytest.raises(w.WGAError) as eg:
+            cov(bad)
+        assert eo.value.code == code == eg.value.code
+        if code in (1, 5, 6):
+            assert str(eg.value) == eo.value.msg

@@ -321,3 +321,21 @@ def test_chain_hand_derived():
     assert orc.maf2chain(maf) == (b"chain\t255\tt\t100\t+\t10\t18\tq\t50\t-\t7\t43\t0\n2\t1\t0\n3\t0\t1\n2\n\n"
                                   b"chain\t255\tt\t100\t+\t0\t4\tq\t50\t+\t0\t4\t1\n4\n\n")
     assert orc.maf2chain(TEST_MAF) == orc.paf2chain(orc.maf2paf(TEST_MAF))
+
+
+def test_pafcov_hand_derived():
+    """pafcov.rs:13-60 + cigar.rs:710-741: M/= cover, I/S stay, everything else advances; clipped to the first record's
+    target_length; one BED line per base"""
+    line = lambda cg, t=b"t", tl=20, ts=2: b"\t".join([b"q", b"100", b"0", b"10", b"+", t, b"%d" % tl, b"%d" % ts, b"12", b"1", b"2", b"60",
+                                                     b"cg:Z:" + cg]) + b"\n"
+    got = orc.pafcov(line(b"3=2X2I4M3D5=") + line(b"30M", ts=15, tl=999) + line(b"2=1N2H1=", t=b"u", tl=7, ts=0))
+    cov_t = [0, 0, 1, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1, 2, 2, 2, 2, 1]
+    cov_u = [1, 1, 0, 0, 0, 1, 0]
+    want = b"".join(b"t\t%d\t%d\t%d\n" % (i, i + 1, c) for i, c in enumerate(cov_t)) + \
+        b"".join(b"u\t%d\t%d\t%d\n" % (i, i + 1, c) for i, c in enumerate(cov_u))
+    assert got == want
+    assert orc.pafcov(b"") == b""
+    for bad, code in ((line(b"5MM"), 5), (line(b"M"), 1), (line(b""), 8)):
+        with pytest.raises(orc.OracleError) as e:
+            orc.pafcov(bad)
+        assert e.value.code == code

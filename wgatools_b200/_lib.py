@@ -72,6 +72,7 @@ ABI = {
                                     ctypes.c_uint64, _P(Span), _P(ctypes.c_uint64)]),
     "wga_paf2chain": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64,
                                     _P(Span), _P(ctypes.c_uint64)]),
+    "wga_paf_cov": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, _P(Span)]),
     "wga_last_record_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, _P(ctypes.c_uint64)]),
 }
 

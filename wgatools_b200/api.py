@@ -420,6 +420,16 @@ def paf2chain(pafreader: PAFReader, writer, ctx=None):
         writer.write(ctypes.string_at(sp.data, sp.len))
 
 
+def pafcov(reader: PAFReader, writer, ctx=None):
+    """src/tools/pafcov.rs:13-60: per-base BED coverage of every target"""
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(reader.data)
+    sp = Span()
+    ctx._check(ctx.L.wga_paf_cov(ctx.h, ctypes.c_void_p(base), len(reader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, ctypes.byref(sp)))
+    if sp.len:
+        writer.write(ctypes.string_at(sp.data, sp.len))
+
+
 def parallel_validatepaf(reader: PAFReader, writer, fix_writer=None, fix_flag=None, ctx=None):
     """src/tools/validate.rs:44-71: report -> writer; with a fix_writer the corrected records -> fix_writer"""
     ctx = ctx or default_context()

@@ -22,6 +22,7 @@
 #include "call_paf.cuh"
 #include "pafpseudo.cuh"
 #include "validate.cuh"
+#include "pafcov.cuh"
 #endif
 
 using namespace wga;
@@ -1668,6 +1669,103 @@ int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
+// ---------------------------------------------------------------- pafcov (pafcov.rs:13-60, cigar.rs:710-741)
+int wga_paf_cov(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out) {
+    if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    PafPrep PP;
+    WGA_TRY(paf_fasta_prepare(ctx, len, nullptr, nullptr, 1, &PP, false, nullptr));
+    const uint64_t n_rec = PP.n_rec;
+    if (n_rec == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    PafRecs R = PP.R;
+    unsigned long long *err_key = PP.err_key;
+    // ---- targets in first-occurrence order
+    uint64_t *kt = ctx->buf<uint64_t>(B_PP_A, n_rec), *kp = ctx->buf<uint64_t>(B_PP_B, n_rec), *ft = ctx->buf<uint64_t>(B_PP_C, n_rec);
+    uint64_t *slot_of = ctx->buf<uint64_t>(B_PP_E, n_rec);
+    uint32_t *head = ctx->buf<uint32_t>(B_PP_J, n_rec + 1), *tidx = ctx->buf<uint32_t>(B_PP_K, n_rec + 1);
+    uint64_t cap = 64;
+    while (cap < 2 * n_rec) cap <<= 1;
+    unsigned long long *tkeys = ctx->buf<unsigned long long>(B_PT_KEYS, cap), *tfirst = ctx->buf<unsigned long long>(B_PT_FIRST, cap);
+    if (!kt || !kp || !ft || !slot_of || !head || !tidx || !tkeys || !tfirst) return ctx->err_code;
+    LAUNCH(ctx, k_pp_keys, grid_for(n_rec, 256), 256, n_rec, d_text, R, (const uint8_t *)nullptr, 0u, 0, kt, kp);
+    WGA_CK(cudaMemsetAsync(tkeys, 0, cap * 8, ctx->stream));
+    WGA_CK(cudaMemsetAsync(tfirst, 0xFF, cap * 8, ctx->stream));
+    LAUNCH(ctx, k_pp_first_insert, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)kt, cap - 1, tkeys, tfirst, slot_of);
+    LAUNCH(ctx, k_pp_first_read, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)slot_of, (const unsigned long long *)tfirst, ft);
+    LAUNCH(ctx, k_cov_verify, grid_for(n_rec, 256), 256, n_rec, d_text, R, (const uint64_t *)ft, err_key);
+    LAUNCH(ctx, k_cov_heads, grid_for(n_rec + 1, 256), 256, n_rec, (const uint64_t *)ft, head);
+    WGA_TRY(exclusive_sum(ctx, head, tidx, n_rec + 1));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal, tidx + n_rec, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    const uint64_t n_targets = *(uint32_t *)ctx->h_scal;
+    uint64_t *t_rec = ctx->buf<uint64_t>(B_PP_F, n_targets + 1), *t_len1 = ctx->buf<uint64_t>(B_PP_G, n_targets + 1);
+    uint64_t *t_base = ctx->buf<uint64_t>(B_PP_H, n_targets + 1), *t_ntile = ctx->buf<uint64_t>(B_PP_I, n_targets + 1);
+    uint64_t *t_tile0 = ctx->buf<uint64_t>(B_PP_L, n_targets + 1);
+    if (!t_rec || !t_len1 || !t_base || !t_ntile || !t_tile0) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(t_len1 + n_targets, 0, 8, ctx->stream));
+    LAUNCH(ctx, k_cov_targets, grid_for(n_rec, 256), 256, n_rec, (const uint32_t *)head, (const uint32_t *)tidx, R, t_rec, t_len1);
+    WGA_TRY(exclusive_sum(ctx, t_len1, t_base, n_targets + 1));
+    LAUNCH(ctx, k_cov_tiles, grid_for(n_targets + 1, 256), 256, n_targets, (const uint64_t *)t_len1, t_ntile);
+    WGA_TRY(exclusive_sum(ctx, t_ntile, t_tile0, n_targets + 1));
+    uint64_t sc[3];
+    WGA_TRY(read_scalars(ctx, {t_base + n_targets, t_tile0 + n_targets, err_key}, sc));
+    const uint64_t n_slots = sc[0], n_tiles = sc[1];
+    // ---- difference array -> coverage
+    int *diff = ctx->buf<int>(B_PP_M, n_slots + 1), *cov = ctx->buf<int>(B_PP_N, n_slots + 1);
+    if (!diff || !cov) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(diff, 0, (n_slots + 1) * 4, ctx->stream));
+    LAUNCH(ctx, k_cov_ops, grid_for(n_rec, 128), 128, n_rec, d_text, R, (const uint64_t *)ft, (const uint32_t *)tidx, (const uint64_t *)t_base,
+           (const uint64_t *)t_len1, diff, err_key);
+    {
+        size_t tmp = 0;
+        WGA_CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, diff, cov, (int64_t)n_slots, ctx->stream));
+        void *t = ctx->ensure(B_CUBTMP, tmp);
+        if (!t) return ctx->err_code;
+        WGA_CK(cub::DeviceScan::InclusiveSum(t, tmp, diff, cov, (int64_t)n_slots, ctx->stream));
+        ctx->n_cub++;
+    }
+    // ---- BED text, tile by tile
+    uint64_t *tile_len = ctx->buf<uint64_t>(B_PP_O, n_tiles + 1), *tile_off = ctx->buf<uint64_t>(B_PP_P, n_tiles + 1);
+    if (!tile_len || !tile_off) return ctx->err_code;
+    CovView V;
+    V.n_targets = n_targets; V.n_tiles = n_tiles; V.text = d_text; V.R = R; V.t_rec = t_rec; V.t_base = t_base; V.t_len1 = t_len1;
+    V.t_tile0 = t_tile0; V.cov = cov; V.tile_len = tile_len; V.tile_off = tile_off; V.out = nullptr;
+    LAUNCH(ctx, k_cov_rows<0>, grid_for(n_tiles + 1, 128), 128, V);
+    WGA_TRY(exclusive_sum(ctx, tile_len, tile_off, n_tiles + 1));
+    WGA_TRY(read_scalars(ctx, {tile_off + n_tiles, err_key}, sc));
+    if (sc[1] != kNoErr) {
+        const int code = (int)(sc[1] & 0xFF);
+        const uint64_t rec = sc[1] >> 32;
+        std::string msg;
+        if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+        else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR)";
+        else if (code == WGA_E_INTERNAL) msg = "name hash collision";
+        else {
+            uint64_t oc[2];
+            WGA_TRY(read_scalars(ctx, {R.cig_off + rec, R.cig_len + rec}, oc));
+            std::string cg((size_t)std::min<uint64_t>(oc[1], 1u << 20), '\0');
+            if (!cg.empty()) WGA_CK(cudaMemcpy(&cg[0], d_text + oc[0], cg.size(), cudaMemcpyDeviceToHost));
+            msg = paf_cigar_error_text(cg, code);
+        }
+        ctx->set_error(code, rec, msg);
+        return code;
+    }
+    const uint64_t total = sc[0];
+    if (total == 0) return WGA_OK;
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    V.out = d_out;
+    LAUNCH(ctx, k_cov_rows<1>, grid_for(n_tiles, 128), 128, V);
+    return finish_output(ctx, d_out, total, mem, flags, out);
+}
+
 // ---------------------------------------------------------------- validate (validate.rs:44-147)
 int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, int fix, wga_span *report,
                      wga_span *fixed) {
@@ -1961,6 +2059,7 @@ int wga_paf_pseudo(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_f
 }
 int wga_paf_validate(wga_ctx *, const void *, uint64_t, int, uint32_t, int, wga_span *, wga_span *) { return WGA_E_UNSUPPORTED; }
 int wga_paf2chain(wga_ctx *, const void *, uint64_t, int, uint32_t, uint64_t, wga_span *, uint64_t *) { return WGA_E_UNSUPPORTED; }
+int wga_paf_cov(wga_ctx *, const void *, uint64_t, int, uint32_t, wga_span *) { return WGA_E_UNSUPPORTED; }
 #endif
 #ifndef WGA_WITH_CALL
 int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
