@@ -70,6 +70,8 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
     if (E > S && lv.text[E - 1] == '\r') --E;
     uint64_t wlo = k == 0 ? 0 : lv.nl_ws_idx[k - 1] + 1;
     uint64_t whi = k < lv.n_nl ? lv.nl_ws_idx[k] : lv.n_ws;
+    // a record with fewer than 6 fields never reaches its names: keep them defined (later passes hash / compare them)
+    R.q_name_off[r] = S; R.q_name_len[r] = 0; R.t_name_off[r] = S; R.t_name_len[r] = 0;
     // fields 0..11, then tags
     uint64_t fb = S, w = wlo;
     uint64_t v[12];
