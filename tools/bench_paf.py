@@ -153,6 +153,35 @@ def main():
     orc.paf2chain(smp)
     cpu = len(smp) / (time.perf_counter() - t0) / 1e9
     report("paf2chain (config 4 shape)", len(paf), ms_dev, ms_e2e, spc.len, cpu, len(smp), {"records": args.records})
+    # validate -f on the same PAF
+    spr, spf = w.api.Span(), w.api.Span()
+
+    def vd(ptr, mem):
+        def run():
+            ctx._check(L.wga_paf_validate(ctx.h, ptr, len(paf), mem, 1, 1, ctypes.byref(spr), ctypes.byref(spf)))
+        return run
+    ms_dev, ms_e2e = timed(vd(ctypes.c_void_p(d.data_ptr()), 1), args.steps), timed(vd(ctypes.c_void_p(hp), 0), args.steps)
+    t0 = time.perf_counter()
+    orc.paf_validate(smp, True)
+    cpu = len(smp) / (time.perf_counter() - t0) / 1e9
+    report("validate -f (config 4 shape)", len(paf), ms_dev, ms_e2e, spf.len, cpu, len(smp), {"records": args.records})
+    # pafcov: one BED line per target base, so a PAF over a small target set (10 x 2 Mbp)
+    pafc = bs.gen_paf(bs.paf_params(200_000, seed=20260930, n_genomes=2, n_chr=5, chr_size=2_000_000, ops_median=150.0, ops_max=2000))
+    dc = resident(pafc)
+    hpc = pinned_copy(pafc)
+    spv = w.api.Span()
+
+    def cv(ptr, mem):
+        def run():
+            ctx._check(L.wga_paf_cov(ctx.h, ptr, len(pafc), mem, 1, ctypes.byref(spv)))
+        return run
+    ms_dev, ms_e2e = timed(cv(ctypes.c_void_p(dc.data_ptr()), 1), args.steps), timed(cv(ctypes.c_void_p(hpc), 0), args.steps)
+    smpc = sample_lines(pafc, 20.0)
+    t0 = time.perf_counter()
+    orc.pafcov(smpc)
+    cpu = len(smpc) / (time.perf_counter() - t0) / 1e9
+    report("pafcov (10 targets x 2 Mbp)", len(pafc), ms_dev, ms_e2e, spv.len, cpu, len(smpc), {"records": 200_000})
+    del dc
     del d
     if args.only == "stat":
         return
