@@ -53,9 +53,38 @@ __global__ void k_pair_insert(uint64_t n_rec, RecMeta m, const unsigned long lon
         slot = (slot + 1) & cap_mask;
     }
     rec_slot[r] = slot;
-    atomicMin(&first_rec[slot], (unsigned long long)r);
     unsigned long long *v = vals + slot * kPairVals;
     const unsigned long long *c = cnt11 + r * 11;
+    // Records of one pair are usually consecutive in the file: when all 32 lanes of a warp landed in the same slot the
+    // warp adds up first and issues 13 atomics instead of 416 on one address.
+    int same = 0;
+    const uint32_t act = __activemask();
+    if (act == 0xFFFFFFFFu) __match_all_sync(0xFFFFFFFFu, (unsigned long long)slot, &same);
+    if (same) {
+        const uint32_t lane = threadIdx.x & 31;
+        unsigned long long first = r, ts = m.t_start[r], qs = m.q_start[r];
+        unsigned long long cc[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) cc[i] = c[i];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 11; ++i) cc[i] += __shfl_xor_sync(0xFFFFFFFFu, cc[i], d);
+            const unsigned long long f2 = __shfl_xor_sync(0xFFFFFFFFu, first, d), t2 = __shfl_xor_sync(0xFFFFFFFFu, ts, d),
+                                     q2 = __shfl_xor_sync(0xFFFFFFFFu, qs, d);
+            first = f2 < first ? f2 : first; ts = t2 < ts ? t2 : ts; qs = q2 < qs ? q2 : qs;
+        }
+        if (lane == 0) {
+            atomicMin(&first_rec[slot], first);
+#pragma unroll
+            for (int i = 0; i < 11; ++i)
+                if (cc[i]) atomicAdd(&v[i], cc[i]);
+            atomicMin(&v[11], ts);
+            atomicMin(&v[12], qs);
+        }
+        return;
+    }
+    atomicMin(&first_rec[slot], (unsigned long long)r);
 #pragma unroll
     for (int i = 0; i < 11; ++i)
         if (c[i]) atomicAdd(&v[i], c[i]);
