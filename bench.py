@@ -99,9 +99,9 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def make_workload(blocks, seed, pinned_alloc, config=2):
+def make_workload(blocks, seed, pinned_alloc, config=2, threads=None):
     import bench_support as bs
-    params = bs.maf_params(blocks, seed=seed, config=config)
+    params = bs.maf_params(blocks, seed=seed, config=config, threads=threads)
     keep, nbytes, ncols = bs.gen_maf_into(params, pinned_alloc)
     return keep, nbytes, ncols
 
@@ -237,7 +237,9 @@ def main():
             raise MemoryError("wga_host_alloc failed")
         return p, p
     t_gen = time.perf_counter()
-    host_ptr, nbytes, ncols = make_workload(args.blocks, SEED + rank, pinned, args.config)
+    # generator threads: this rank's share of the CPUs of its NUMA node (ranks of one node generate at the same time)
+    gen_threads = max(4, len(os.sched_getaffinity(0)) // max(1, (world + 1) // 2))
+    host_ptr, nbytes, ncols = make_workload(args.blocks, SEED + rank, pinned, args.config, gen_threads)
     t_gen = time.perf_counter() - t_gen
     import numpy as np
     h_view = torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(host_ptr)))
