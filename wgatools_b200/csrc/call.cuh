@@ -282,18 +282,27 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
             staged = span_hi - span_lo <= (uint64_t)kVcfSpan;
         }
     }
-    if (PASS == 0) {
-        if (row > n_rows) return;
-        if (row == n_rows) { row_len[row] = 0; return; }
-    }
+    if (PASS == 0 && row == n_rows) row_len[row] = 0;  // (no early exit: the warp shares a search below)
     const bool have_row = row < n_rows;
     const uint8_t *d_src = nullptr;
     char *d_dst = nullptr;
     uint64_t d_len = 0;
     unsigned long long ekey = 0;
+    // run owning a row: last j with rowbase[j] <= row.  The 32 rows of a warp are consecutive, so their runs sit in a
+    // short window above the run of the warp's first row: one full binary search per warp, a bounded one per lane.
+    uint64_t j_warp = 0;
+    {
+        const uint64_t row0 = row - lane;
+        if (lane == 0 && row0 < n_rows) {
+            uint64_t lo = 0, hi = V.n_runs;
+            while (hi - lo > 1) { uint64_t m = (lo + hi) >> 1; if (rowbase[m] <= row0) lo = m; else hi = m; }
+            j_warp = lo;
+        }
+        j_warp = __shfl_sync(0xFFFFFFFFu, j_warp, 0);
+    }
     if (have_row) {
-    // run owning this row: last j with rowbase[j] <= row
-    uint64_t lo = 0, hi = V.n_runs;
+    uint64_t lo = j_warp, hi = j_warp + 256 < V.n_runs ? j_warp + 256 : V.n_runs;
+    if (hi < V.n_runs && rowbase[hi] <= row) { lo = hi; hi = V.n_runs; }  // a long stretch of runs without rows
     while (hi - lo > 1) { uint64_t m = (lo + hi) >> 1; if (rowbase[m] <= row) lo = m; else hi = m; }
     const uint64_t j = lo;
     uint64_t k = row - rowbase[j];
