@@ -93,7 +93,8 @@ def test_prev_flags_and_funnel(hd):
 
 def test_decimal(hd):
     rng = random.Random(2)
-    vals = [0, 9, 10, 99, 100, 999, 1000, 99999, 100000, 10**10 - 1, 10**10, 2**64 - 1] + \
+    vals = [0, 9, 10, 99, 100, 999, 1000, 99999, 100000, 10**10 - 1, 10**10, 2**64 - 1, 2**32 - 1, 2**32, 2**32 + 1,
+            10**9 - 1, 10**9, 4294967290, 42949672960, 10**19] + [10**k for k in range(20)] + [10**k - 1 for k in range(1, 20)] + \
            [rng.randrange(0, 2**64) >> rng.randrange(0, 64) for _ in range(3000)]
     buf = ctypes.create_string_buffer(32)
     for v in vals:

@@ -97,6 +97,11 @@ WGA_HD Flags4 classify_prev(uint32_t tb, uint32_t qb, bool valid) {
 
 // decimal digits of v (>= 1)
 WGA_HD int ndigits_u64(uint64_t v) {
+    if (v <= 0xFFFFFFFFull) {  // coordinates and sizes: compares only, no 64-bit division
+        const uint32_t x = (uint32_t)v;
+        return x < 100000u ? (x < 100u ? (x < 10u ? 1 : 2) : (x < 1000u ? 3 : (x < 10000u ? 4 : 5)))
+                           : (x < 10000000u ? (x < 1000000u ? 6 : 7) : (x < 100000000u ? 8 : (x < 1000000000u ? 9 : 10)));
+    }
     int n = 1;
     if (v >= 10000000000ull) { v /= 10000000000ull; n += 10; }
     if (v >= 100000ull) { v /= 100000ull; n += 5; }
@@ -106,9 +111,16 @@ WGA_HD int ndigits_u64(uint64_t v) {
 }
 // writes v in decimal at dst[0..nd) where nd == ndigits_u64(v); returns nd
 WGA_HD int write_u64(char *dst, uint64_t v, int nd) {
-    for (int i = nd - 1; i >= 0; --i) {
+    int i = nd - 1;
+    for (; i >= 0 && v > 0xFFFFFFFFull; --i) {
         dst[i] = (char)('0' + (int)(v % 10));
         v /= 10;
+    }
+    uint32_t x = (uint32_t)v;  // 32-bit division by a constant = one multiply-high
+    for (; i >= 0; --i) {
+        const uint32_t q = x / 10u;
+        dst[i] = (char)('0' + (int)(x - q * 10u));
+        x = q;
     }
     return nd;
 }
