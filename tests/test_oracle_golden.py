@@ -339,3 +339,42 @@ def test_pafcov_hand_derived():
         with pytest.raises(orc.OracleError) as e:
             orc.pafcov(bad)
         assert e.value.code == code
+
+
+_ops = st.lists(st.tuples(st.integers(0, 40), st.sampled_from("M=XID")), min_size=1, max_size=14)
+
+
+def _paf_line(q, qsize, qs, qe, strand, t, tsize, ts, te, cg):
+    return ("\t".join(map(str, [q, qsize, qs, qe, strand, t, tsize, ts, te, 1, 2, 60, "cg:Z:" + cg])) + "\n").encode()
+
+
+@settings(max_examples=300, deadline=None)
+@given(_ops, st.booleans(), st.integers(0, 50), st.integers(0, 50))
+def test_paf_chain_and_counts_vs_pyspec(ops, neg, qs, ts):
+    cg = "".join(f"{n}{o}" for n, o in ops)
+    strand = "-" if neg else "+"
+    c = pyspec.paf_counts(cg, neg)
+    assert orc.paf_cigar_counts(cg.encode(), neg) == c
+    qe = qs + c[0] + c[1] + c[3] + c[7]
+    te = ts + c[0] + c[1] + c[5] + c[9]
+    rec = ("q", 5000, qs, qe, strand, "t", 6000, ts, te, cg)
+    line = _paf_line(*rec)
+    assert orc.paf2chain(line + line).decode() == pyspec.paf_chain(rec, 0) + pyspec.paf_chain(rec, 1)
+    rep, fx = orc.paf_validate(line, True)        # consistent by construction: nothing to fix
+    assert rep.startswith(b"Total records: 1\nQuery invalid records: 0\nTarget invalid records: 0\n") and fx == line
+    rep, _ = orc.paf_validate(_paf_line("q", 5000, qs, qe + 1, strand, "t", 6000, ts, te + 2, cg), False)
+    assert rep == (f"Total records: 1\nQuery invalid records: 1\nTarget invalid records: 1\nQuery invalid list:\nq:{qs}-{qe + 1}\n"
+                   f"Target invalid list:\nt:{ts}-{te + 2}\n\n").encode()
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from(["a", "b"]), st.integers(0, 30),
+                          st.lists(st.tuples(st.integers(0, 12), st.sampled_from("M=XIDSNH")), min_size=1, max_size=8)),
+                min_size=1, max_size=6), st.integers(1, 40))
+def test_pafcov_vs_pyspec(recs, tlen):
+    lines, spec = [], []
+    for t, ts, ops in recs:
+        cg = "".join(f"{n}{o}" for n, o in ops)
+        lines.append(_paf_line("q", 100, 0, 10, "+", t, tlen if t == "a" else tlen + 3, ts, ts + 1, cg))
+        spec.append((t, tlen if t == "a" else tlen + 3, ts, cg))
+    assert orc.pafcov(b"".join(lines)).decode() == pyspec.paf_cov(spec)
