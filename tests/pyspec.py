@@ -162,3 +162,132 @@ def paf_cov(recs):  # pafcov.rs:13-60, cigar.rs:710-741; recs = (target, tlen, t
             elif op not in "IS":
                 pos += n
     return "".join(f"{t}\t{i}\t{i + 1}\t{c}\n" for t in order for i, c in enumerate(cov[t]))
+
+
+_COMP = str.maketrans("ACGTacgt", "TGCAtgca")
+
+
+def pseudo_maf(recs, fasta=None):
+    """pseudomaf.rs:78-237 + cigar.rs:744-804 for ONE target; recs = (q, qsize, qs, qe, strand, t, tsize, ts, te, cg) in file
+    order, fasta = {name: sequence} or None.  Queries in first-occurrence order; raises on the reference's panics."""
+    groups, order = {}, []
+    for r in recs:
+        g = groups.setdefault(r[0], [])
+        if r[0] not in order:
+            order.append(r[0])
+        g.append(r)
+    out = ["a score=0\n"]
+    first = True
+    tsize = 0
+    for q in order:
+        g = sorted(groups[q], key=lambda r: r[7])   # distinct target_start assumed (ties are unspecified)
+        firstq, lte = True, 0
+        for (qn, qsize, qs, qe, strand, t, tsz, ts, te, cg) in g:
+            tsize = tsz
+            if first:
+                seq = fasta[t][0:tsz] if fasta is not None else "N" * tsz
+                out.append(f"s\t{t}\t0\t{tsz}\t+\t{tsz}\t{seq}\n")
+                first = False
+            if firstq:
+                out.append(f"s\t{qn}\t0\t{qsize}\t+\t{qsize}\t")
+            overlap = 0
+            if ts > lte:
+                out.append("-" * (ts - lte))
+            else:
+                if lte > te:
+                    continue
+                overlap = lte - ts
+            lte = te
+            s = fasta[qn][qs:qe] if fasta is not None else ""
+            if strand == "-":
+                s = s[::-1].translate(_COMP)
+            s = list(s)
+            off = 0
+            for n, op in cigar_tokens(cg):
+                if op in "M=X":
+                    if fasta is not None:
+                        off += n
+                    else:
+                        s += ("1" if op != "X" else "0") * n
+                elif op in "IS":
+                    if fasta is not None:
+                        assert off + n <= len(s), "drain panics"
+                        del s[off:off + n]
+                elif op == "D":
+                    if fasta is not None:
+                        assert off <= len(s), "insert_str panics"
+                        s[off:off] = "-" * n
+                        off += n
+                    else:
+                        s += "-" * n
+            assert overlap <= len(s), "drain panics"
+            out.append("".join(s[overlap:]))
+            firstq = False
+        assert lte <= tsize, "subtract overflows"
+        out.append("-" * (tsize - lte) + "\n")
+    out.append("\n")
+    return "".join(out)
+
+
+def call_paf_rows(rec, fasta_t, fasta_q, snp, svlen):
+    """caller.rs:610-822 for one record -> list of VCF body rows; raises AssertionError on the reference's panics and
+    ValueError on its real errors (<INV> row).  Sequences are fetched with an inclusive end, no reverse complement."""
+    q, qsize, qs, qe, strand, t, tsize, ts, te, cg = rec
+    tseq, qseq = fasta_t[t][ts:te + 1], fasta_q[q][qs:qe + 1]
+    up = lambda s: s.upper()
+    ok = lambda s: all(c in "ACGTN" for c in s.upper())
+    sfx = "N" if strand == "-" else "P"
+    rows = []
+    if strand == "-":
+        assert len(tseq) >= 1
+        if not ok(tseq[0]):
+            raise ValueError("bad base")
+        rows.append(f"{t}\t{ts + 1}\t.\t{up(tseq[0])}\t<INV>\t.\t.\tSVTYPE=INV;END={te}\tGT:QI\t1|1:{q}@{qs}@{qe}@{sfx}\n")
+    nest = "INV_NEST=TRUE;" if strand == "-" else ""
+    tp, qp, after_m = ts, qs, False
+    toks = []
+    i = 0
+    while i < len(cg):   # stop silently at the first malformed token (the closure's Result is discarded)
+        m = _TOK.match(cg, i)
+        d, op = m.group(1), m.group(2)
+        if len(op) != 1 or d == "" or int(d) >= 2 ** 64:
+            break
+        toks.append((int(d), op)); i = m.end()
+    for n, op in toks:
+        if op in "M=":
+            tp += n; qp += n; after_m = True
+        elif op == "X":
+            if snp:
+                for _ in range(n):
+                    a, b = tp - ts, qp - qs
+                    assert a + 1 <= len(tseq) and b + 1 <= len(qseq)
+                    if not (ok(tseq[a]) and ok(qseq[b])):
+                        return rows
+                    rows.append(f"{t}\t{tp + 1}\t.\t{up(tseq[a])}\t{up(qseq[b])}\t.\t.\t.\tGT:QI\t1|1:{q}@{qp}@{sfx}\n")
+                    tp += 1; qp += 1
+            else:
+                tp += n; qp += n
+            after_m = True
+        elif op in "ID":
+            if n > svlen and after_m:
+                assert tp > ts and qp > qs
+                a, b = tp - ts - 1, qp - qs - 1
+                if op == "I":
+                    assert a + 1 <= len(tseq) and b + n + 1 <= len(qseq)
+                    ref, alt = tseq[a], qseq[b:b + n + 1]
+                    info, qi = f"{nest}SVTYPE=INS;SVLEN={n};END={tp}", f"{q}@{qp}@{qp + n}@{sfx}"
+                else:
+                    assert a + n + 1 <= len(tseq) and b + 1 <= len(qseq)
+                    ref, alt = tseq[a:a + n + 1], qseq[b]
+                    info, qi = f"{nest}SVTYPE=DEL;SVLEN={n};END={tp + n}", f"{q}@{qp}@{qp}@{sfx}"
+                if not (ok(ref) and ok(alt)):
+                    return rows
+                rows.append(f"{t}\t{tp}\t.\t{up(ref)}\t{up(alt)}\t.\t.\t{info}\tGT:QI\t1|1:{qi}\n")
+            if op == "I":
+                qp += n
+            else:
+                tp += n
+            after_m = False
+        else:
+            return rows
+    return rows

@@ -378,3 +378,80 @@ def test_pafcov_vs_pyspec(recs, tlen):
         lines.append(_paf_line("q", 100, 0, 10, "+", t, tlen if t == "a" else tlen + 3, ts, ts + 1, cg))
         spec.append((t, tlen if t == "a" else tlen + 3, ts, cg))
     assert orc.pafcov(b"".join(lines)).decode() == pyspec.paf_cov(spec)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.data())
+def test_paf_pseudo_vs_pyspec(data):
+    """random consistent records (CIGAR spans == coordinate spans) over a tiny FASTA, one target, two queries"""
+    rnd = data.draw(st.randoms(use_true_random=False))
+    bases = "ACGTacgtN"
+    tlen = rnd.randrange(20, 60)
+    fasta = {"t": "".join(rnd.choice(bases) for _ in range(tlen)), "qa": "".join(rnd.choice(bases) for _ in range(80)),
+             "qb": "".join(rnd.choice(bases) for _ in range(70))}
+    recs, used = [], set()
+    for _ in range(rnd.randrange(1, 6)):
+        q = rnd.choice(["qa", "qb"])
+        ts = rnd.randrange(0, tlen - 5)
+        if (q, ts) in used:
+            continue
+        used.add((q, ts))
+        ops, tcons, qcons = [], 0, 0
+        for _ in range(rnd.randrange(1, 6)):
+            op = rnd.choice("M=XIDS" if rnd.random() < 0.9 else "NH")
+            n = rnd.randrange(1, 6)
+            if op in "M=XD" and ts + tcons + n > tlen:
+                break
+            ops.append(f"{n}{op}")
+            tcons += n if op in "M=XD" else 0
+            qcons += n if op in "M=XIS" else 0
+        if not ops or tcons == 0:
+            continue
+        qs = rnd.randrange(0, len(fasta[q]) - qcons) if len(fasta[q]) > qcons else 0
+        recs.append((q, len(fasta[q]), qs, qs + max(qcons, 1), rnd.choice("+-"), "t", tlen, ts, ts + tcons, "".join(ops)))
+    if not recs:
+        return
+    paf = b"".join(_paf_line(*r) for r in recs)
+    fa = "".join(f">{k}\n{v}\n" for k, v in fasta.items()).encode()
+    fai = orc.make_fai(fa)
+    for use_fa in (True, False):
+        try:
+            want = pyspec.pseudo_maf(recs, fasta if use_fa else None)
+        except AssertionError:
+            with pytest.raises(orc.OracleError) as e:
+                orc.paf_pseudo(paf, fa if use_fa else None, fai if use_fa else None)
+            assert e.value.code == 8
+            continue
+        got = orc.paf_pseudo(paf, fa if use_fa else None, fai if use_fa else None)
+        assert list(got) == [b"t"] and got[b"t"].decode() == want
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.data())
+def test_call_paf_vs_pyspec(data):
+    rnd = data.draw(st.randoms(use_true_random=False))
+    bases = "ACGTacgtN" if rnd.random() < 0.8 else "ACGTRY"
+    ft = {"t": "".join(rnd.choice(bases) for _ in range(60))}
+    fq = {"q": "".join(rnd.choice(bases) for _ in range(60))}
+    recs = []
+    for _ in range(rnd.randrange(1, 4)):
+        ops = "".join(f"{rnd.randrange(0, 7)}{rnd.choice('M=XXIDDI' if rnd.random() < 0.95 else 'SN')}" for _ in range(rnd.randrange(1, 7)))
+        ts, qs = rnd.randrange(0, 30), rnd.randrange(0, 30)
+        recs.append(("q", 60, qs, qs + rnd.randrange(0, 30), rnd.choice("+-"), "t", 60, ts, ts + rnd.randrange(0, 30), ops))
+    paf = b"".join(_paf_line(*r) for r in recs)
+    tfa, qfa = f">t\n{ft['t']}\n".encode(), f">q\n{fq['q']}\n".encode()
+    snp, svlen = rnd.random() < 0.7, rnd.choice([0, 0, 1, 3])
+    hdr = orc.call_maf(b"##maf version=1\n")
+    try:
+        want = hdr.decode() + "".join("".join(pyspec.call_paf_rows(r, ft, fq, snp, svlen)) for r in recs)
+        err = None
+    except AssertionError:
+        err = 8
+    except ValueError:
+        err = 10
+    if err is None:
+        assert orc.call_paf(paf, tfa, orc.make_fai(tfa), qfa, orc.make_fai(qfa), snp=snp, svlen=svlen).decode() == want
+    else:
+        with pytest.raises(orc.OracleError) as e:
+            orc.call_paf(paf, tfa, orc.make_fai(tfa), qfa, orc.make_fai(qfa), snp=snp, svlen=svlen)
+        assert e.value.code == err
