@@ -91,3 +91,55 @@ def test_stat_allreduce_gloo_world2():
         assert p.exitcode == 0
     want = orc.stat_maf(text)
     assert outs[0] == want and outs[1] == want
+
+
+def _shard_worker(rank, world, port, text, paf, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib as orc
+    from wgatools_b200 import dist as wd
+    lo, hi = wd.shard_range(text, rank, world, "maf")
+    mine = text[lo:hi] if rank == 0 else b"#not the file header\n" + text[lo:hi]   # only rank 0 holds the real first line
+    out = orc.maf2paf(mine)                     # the per-rank command (the CPU oracle stands in for the GPU here)
+    plo, phi = wd.shard_range(paf, rank, world, "paf")
+    outs = [None] * world
+    dist.all_gather_object(outs, (lo, hi, out, plo, phi))
+    if rank == 0:
+        q.put(outs)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_record_sharding_gloo_world2():
+    """byte ranges snapped to record boundaries; outputs concatenated in rank order == one process"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as g
+    g.build()
+    import bench_support as bs
+    import oracle_lib as orc
+    from wgatools_b200 import dist as wd
+    text = bs.gen_maf(bs.maf_params(300, seed=5, p_neg=0.2))
+    paf = bs.gen_paf(bs.paf_params(200, seed=6))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_shard_worker, args=(r, 2, port, text, paf, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    outs = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert outs[0][0] == 0 and outs[0][1] == outs[1][0] and outs[1][1] == len(text)
+    assert 0 < outs[0][1] < len(text) and text[outs[0][1]:outs[0][1] + 1] != b"s"
+    assert outs[0][2] + outs[1][2] == orc.maf2paf(text)
+    assert outs[0][3] == 0 and outs[0][4] == outs[1][3] and outs[1][4] == len(paf) and paf[outs[0][4] - 1:outs[0][4]] == b"\n"
+    # more ranks than records / odd worlds still tile the file
+    for world in (1, 3, 7, 50):
+        r = [wd.shard_range(text, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == len(text) and all(r[k][1] == r[k + 1][0] for k in range(world - 1))

@@ -99,3 +99,30 @@ def allreduce_stat(acc: StatAcc, dist, device=None) -> StatAcc:
     out = StatAcc(False)
     out.import_(build_blob(0, gkeys, gvals, np.zeros(P, np.float32), g_pair, g_num))
     return out
+
+
+def shard_range(data, rank: int, world: int, kind: str = "maf"):
+    """Byte range [lo, hi) of `data` that rank `rank` of `world` processes: contiguous ranges snapped to
+    record boundaries, concatenating the ranks' outputs in rank order reproduces the single-process output.
+    MAF: a range starts at a line that does not begin with 's', so s-line groups are never split (maf.rs:395-413); only
+    rank 0's range holds the file's first line, which the reader swallows (pass WGA_F_FIRST_SLAB there only).
+    PAF: a range starts right after a newline."""
+    n = len(data)
+
+    def snap(pos):
+        if pos <= 0:
+            return 0
+        if pos >= n:
+            return n
+        nl = data.find(b"\n", pos - 1)           # first line start at or after pos
+        if nl < 0:
+            return n
+        p = nl + 1
+        if kind == "maf":
+            while p < n and data[p:p + 1] == b"s":  # skip the rest of a split s-line group
+                nl = data.find(b"\n", p)
+                if nl < 0:
+                    return n
+                p = nl + 1
+        return min(p, n)
+    return snap(n * rank // world), snap(n * (rank + 1) // world)
