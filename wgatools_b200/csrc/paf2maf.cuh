@@ -285,6 +285,29 @@ __global__ void k_p2m_blocks(P2mView V) {
     }
 }
 
+// warp-wide copy of n bytes: destination brought to 4-byte alignment, then one 32-bit store per lane and iteration fed
+// by two aligned loads and a funnel shift (source and destination are misaligned against each other), byte tails
+__device__ __forceinline__ void warp_copy(char *dst, const uint8_t *src, uint64_t n, uint32_t lane) {
+    if (n < 96) {
+        for (uint64_t i = lane; i < n; i += 32) dst[i] = (char)src[i];
+        return;
+    }
+    const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+    if (lane < head) dst[lane] = (char)src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t sm = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - sm);
+    uint64_t nw = n >> 2;
+    if (sm && nw) --nw;  // the funnel reads word w + 1: keep every load inside [src - sm, src + n)
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+    for (uint64_t w = lane; w < nw; w += 32) {
+        const uint32_t lo = __ldg(sw + w);
+        dw[w] = sm ? __funnelshift_r(lo, __ldg(sw + w + 1), sm * 8u) : lo;
+    }
+    const uint64_t done = nw << 2;
+    for (uint64_t i = done + lane; i < n; i += 32) dst[i] = (char)src[i];
+}
+
 // one warp per CIGAR op (+ one virtual op per record for the bases left over after the last op): writes the op's
 // slice of the target row and of the query row
 __global__ void k_p2m_rows(P2mView V) {
@@ -325,15 +348,14 @@ __global__ void k_p2m_rows(P2mView V) {
         for (uint64_t i = lane; i < len; i += 32) trow[o + i] = '-';
     } else if (tb < LT) {
         uint64_t n = LT - tb < len ? LT - tb : len;
-        const uint64_t pos = tb + (o - tb);  // = o: base b sits at b + (gaps inserted before it)
-        for (uint64_t i = lane; i < n; i += 32) trow[pos + i] = (char)T[tb + i];
+        warp_copy(trow + o, T + tb, n, lane);  // base b sits at b + (gaps inserted before it) = o
     }
     // query row
     if (type == 2) {
         for (uint64_t i = lane; i < len; i += 32) qrow[o + i] = '-';
     } else if (qb < LQ) {
         uint64_t n = LQ - qb < len ? LQ - qb : len;
-        if (!neg) for (uint64_t i = lane; i < n; i += 32) qrow[o + i] = (char)Q[qb + i];
+        if (!neg) warp_copy(qrow + o, Q + qb, n, lane);
         else for (uint64_t i = lane; i < n; i += 32) qrow[o + i] = (char)comp_base(Q[LQ - 1 - (qb + i)]);
     }
 }

@@ -441,7 +441,7 @@ __global__ void k_pp_rows(PpView V) {
     }
     const uint8_t *Q = V.seq + V.S.q_src[i];
     const uint64_t LQ = V.S.LQ[i];
-    if (!(V.R.neg[V.ord[i]] & 1)) for (uint64_t j = j0 + lane; j < n; j += 32) piece[o + j - ov] = (char)Q[src + j];
+    if (!(V.R.neg[V.ord[i]] & 1)) { if (n > j0) warp_copy(piece + o + j0 - ov, Q + src + j0, n - j0, lane); }
     else for (uint64_t j = j0 + lane; j < n; j += 32) piece[o + j - ov] = (char)comp_base(Q[LQ - 1 - (src + j)]);
 }
 
