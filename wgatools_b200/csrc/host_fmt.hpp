@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <string_view>
 
 namespace wga {
 
@@ -57,9 +58,9 @@ inline bool nat_ws(char c) { return c == ' ' || (c >= 9 && c <= 13); }
 
 // natord::compare: whitespace skipped, digit runs compared numerically (right-aligned) unless one
 // starts with '0' (left-aligned, "fractional"), everything else by char
-inline int natord_cmp(const std::string &a, const std::string &b) {
+inline int natord_cmp(std::string_view a, std::string_view b) {
     size_t i = 0, j = 0;
-    auto dig = [](const std::string &s, size_t p) -> int {
+    auto dig = [](std::string_view s, size_t p) -> int {
         return p < s.size() && s[p] >= '0' && s[p] <= '9' ? s[p] - '0' : -1;
     };
     for (;;) {
@@ -91,10 +92,10 @@ inline int natord_cmp(const std::string &a, const std::string &b) {
     }
 }
 
-inline void csv_field(std::string &out, const std::string &f) {
+inline void csv_field(std::string &out, std::string_view f) {
     bool need = false;
     for (char c : f) need |= c == '\t' || c == '"' || c == '\r' || c == '\n';
-    if (!need) { out += f; return; }
+    if (!need) { out.append(f.data(), f.size()); return; }
     out.push_back('"');
     for (char c : f) { if (c == '"') out.push_back('"'); out.push_back(c); }
     out.push_back('"');

@@ -119,8 +119,9 @@ __global__ void k_slot_flags(uint64_t cap, const unsigned long long *__restrict_
 }
 
 // compact used slots -> pair arrays; also name lengths (t then q) for the name gather
+// pair_sizes = {ref_size, query_size, pair hash} per pair
 __global__ void k_pair_gather(uint64_t cap, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ idx,
-                              const unsigned long long *__restrict__ first_rec,
+                              const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ first_rec,
                               const unsigned long long *__restrict__ vals, RecMeta m,
                               uint64_t *__restrict__ pair_first, uint64_t *__restrict__ pair_vals,
                               uint64_t *__restrict__ pair_sizes, uint32_t *__restrict__ name_len) {
@@ -130,8 +131,9 @@ __global__ void k_pair_gather(uint64_t cap, const uint32_t *__restrict__ flag, c
     uint64_t f = first_rec[s];
     pair_first[p] = f;
     for (int i = 0; i < kPairVals; ++i) pair_vals[(uint64_t)p * kPairVals + i] = vals[s * kPairVals + i];
-    pair_sizes[2 * (uint64_t)p] = m.t_size[f];
-    pair_sizes[2 * (uint64_t)p + 1] = m.q_size[f];
+    pair_sizes[3 * (uint64_t)p] = m.t_size[f];
+    pair_sizes[3 * (uint64_t)p + 1] = m.q_size[f];
+    pair_sizes[3 * (uint64_t)p + 2] = keys[s];
     name_len[2 * (uint64_t)p] = m.t_name_len[f];
     name_len[2 * (uint64_t)p + 1] = m.q_name_len[f];
 }

@@ -2,67 +2,98 @@
 // back from the GPU, in file order, and prints the TSV of src/tools/stat.rs:107-126.
 // merged mode : src/tools/stat.rs:167-223 merge_final_from_pair
 // each mode   : src/tools/stat.rs:129-164 split_final
+//
+// Layout: rows are PODs, names live in one arena, the key -> row map is a flat open-addressing table keyed by the
+// SAME 64-bit pair hash the device table uses (stat.cuh pair_key), so merging a 10^5-pair table coming back from the
+// GPU is one probe + one memcmp per pair (no std::string, no node allocations).
 #pragma once
 #include <algorithm>
+#include <charconv>
 #include <cstdint>
+#include <cstring>
 #include <string>
-#include <unordered_map>
+#include <string_view>
 #include <vector>
 
 #include "../../include/wga_b200.h"
+#include "hd_core.h"
 #include "host_fmt.hpp"
+
+namespace wga {
+// host spelling of stat.cuh pair_key (FNV-1a over the names, splitmix finaliser over the sizes)
+inline uint64_t host_pair_key(const char *rn, uint32_t lr, uint64_t rs, const char *qn, uint32_t lq, uint64_t qs) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (uint32_t i = 0; i < lr; ++i) h = (h ^ (unsigned char)rn[i]) * 0x100000001B3ull;
+    h = mix64(h ^ rs);
+    h ^= 0x9E3779B97F4A7C15ull;
+    for (uint32_t i = 0; i < lq; ++i) h = (h ^ (unsigned char)qn[i]) * 0x100000001B3ull;
+    h = mix64(h ^ (qs * 0xD1342543DE82EF95ull));
+    return h ? h : 1;
+}
+}  // namespace wga
 
 struct wga_stat_acc {
     struct Row {
-        std::string ref_name, query_name;
+        uint64_t name_off = 0;  // names[name_off .. +lr) = ref_name, then lq bytes of query_name
+        uint32_t lr = 0, lq = 0;
         uint64_t ref_size = 0, query_size = 0;
+        uint64_t key = 0;      // pair hash (merged mode)
         uint64_t v[13] = {0};  // 11 counters (struct Cigar order), ref_start_min, query_start_min
-        float inv_size = 0.f;  // each mode only
+        // each mode: the record's inv_size.  merged mode: the f32 sum of every '-' record that precedes this
+        // accumulator's own list (set by the cross-rank ring carry of wga_stat_allreduce; 0 otherwise)
+        float inv_size = 0.f;
     };
     int each = 0;
-    std::vector<Row> rows;                            // first-seen order (merged) / record order (each)
-    std::unordered_map<std::string, uint32_t> index;  // merged mode: key -> row
-    std::vector<uint32_t> inv_pair;                   // '-'-strand records in file order: row index
-    std::vector<uint64_t> inv_num;                    //   and (aligned + query_aligned)
+    std::vector<char> names;
+    std::vector<Row> rows;            // first-seen order (merged) / record order (each)
+    std::vector<uint32_t> table;      // merged mode: open addressing, row index + 1, 0 = empty
+    std::vector<uint32_t> inv_pair;   // '-'-strand records in file order: row index
+    std::vector<uint64_t> inv_num;    //   and (aligned + query_aligned)
     std::string text, blob;
 
-    static std::string key_of(const std::string &rn, uint64_t rs, const std::string &qn, uint64_t qs) {
-        std::string k;
-        k.reserve(rn.size() + qn.size() + 20);
-        k += rn; k.push_back('\0'); k += qn; k.push_back('\0');
-        k.append((const char *)&rs, 8);
-        k.append((const char *)&qs, 8);
-        return k;
+    std::string_view ref_name(const Row &r) const { return std::string_view(names.data() + r.name_off, r.lr); }
+    std::string_view query_name(const Row &r) const { return std::string_view(names.data() + r.name_off + r.lr, r.lq); }
+
+    void grow_table(size_t want_rows) {
+        size_t cap = table.size() ? table.size() : 1024;
+        while (cap < 2 * want_rows + 2) cap <<= 1;
+        if (cap == table.size()) return;
+        table.assign(cap, 0u);
+        const size_t mask = cap - 1;
+        for (uint32_t i = 0; i < rows.size(); ++i) {
+            size_t s = rows[i].key & mask;
+            while (table[s]) s = (s + 1) & mask;
+            table[s] = i + 1;
+        }
     }
-    // the key -> row map is only needed once a SECOND table is merged in (another slab, an imported blob); the first
-    // table is bulk-loaded without it
-    void ensure_index() {
-        if (index.size() == rows.size()) return;
-        index.clear();
-        index.reserve(rows.size() * 2);
-        for (uint32_t i = 0; i < rows.size(); ++i)
-            index.emplace(key_of(rows[i].ref_name, rows[i].ref_size, rows[i].query_name, rows[i].query_size), i);
-    }
-    uint32_t add_new(const char *rn, size_t lr, uint64_t rs, const char *qn, size_t lq, uint64_t qs) {
-        rows.emplace_back();
-        Row &r = rows.back();
-        r.ref_name.assign(rn, lr); r.query_name.assign(qn, lq); r.ref_size = rs; r.query_size = qs;
+    uint32_t push_row(const char *rn, uint32_t lr, uint64_t rs, const char *qn, uint32_t lq, uint64_t qs, uint64_t key) {
+        Row r;
+        r.name_off = names.size();
+        r.lr = lr; r.lq = lq; r.ref_size = rs; r.query_size = qs; r.key = key;
+        names.insert(names.end(), rn, rn + lr);
+        names.insert(names.end(), qn, qn + lq);
         r.v[11] = rs;  // stat.rs:186,189: minima start at the sizes
         r.v[12] = qs;
+        rows.push_back(r);
         return (uint32_t)rows.size() - 1;
     }
-    uint32_t find_or_add(const std::string &rn, uint64_t rs, const std::string &qn, uint64_t qs) {
-        ensure_index();
-        std::string k = key_of(rn, rs, qn, qs);
-        auto it = index.find(k);
-        if (it != index.end()) return it->second;
-        Row r;
-        r.ref_name = rn; r.query_name = qn; r.ref_size = rs; r.query_size = qs;
-        r.v[11] = rs;  // stat.rs:186,189: minima start at the sizes
-        r.v[12] = qs;
-        rows.push_back(std::move(r));
-        uint32_t id = (uint32_t)rows.size() - 1;
-        index.emplace(std::move(k), id);
+    // merged mode; key == 0: compute it here
+    uint32_t find_or_add(const char *rn, uint32_t lr, uint64_t rs, const char *qn, uint32_t lq, uint64_t qs, uint64_t key = 0) {
+        if (!key) key = wga::host_pair_key(rn, lr, rs, qn, lq, qs);
+        if (table.size() < 2 * (rows.size() + 1) + 2) grow_table(rows.size() + 1);
+        const size_t mask = table.size() - 1;
+        size_t s = key & mask;
+        for (;;) {
+            const uint32_t e = table[s];
+            if (!e) break;
+            const Row &r = rows[e - 1];
+            if (r.key == key && r.lr == lr && r.lq == lq && r.ref_size == rs && r.query_size == qs &&
+                !memcmp(names.data() + r.name_off, rn, lr) && !memcmp(names.data() + r.name_off + lr, qn, lq))
+                return e - 1;
+            s = (s + 1) & mask;
+        }
+        const uint32_t id = push_row(rn, lr, rs, qn, lq, qs, key);
+        table[s] = id + 1;
         return id;
     }
     void add_pair_vals(uint32_t id, const uint64_t *v) {
@@ -72,26 +103,64 @@ struct wga_stat_acc {
         if (v[12] < r.v[12]) r.v[12] = v[12];
     }
 
+    // write_style_result (stat.rs:107-126): stable natord sort on ref_name, TSV with header
     void write() {
         text.clear();
-        std::vector<float> inv(rows.size(), 0.f);
+        const size_t n = rows.size();
+        std::vector<float> inv(n, 0.f);
+        for (size_t i = 0; i < n; ++i) inv[i] = rows[i].inv_size;
         if (!each) {
             // stat.inv_size += rec_stat.inv_size in record order (f32, order-dependent); a '+' record adds 0.0
             for (size_t i = 0; i < inv_pair.size(); ++i)
                 inv[inv_pair[i]] += (float)inv_num[i] / (float)2;  // common.rs:134-137 with inv_event == 1
-        } else {
-            for (size_t i = 0; i < rows.size(); ++i) inv[i] = rows[i].inv_size;
         }
-        std::vector<uint32_t> order(rows.size());
-        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            return wga::natord_cmp(rows[a].ref_name, rows[b].ref_name) < 0;
+        // Rows with the same ref_name compare equal, so the stable sort only has to order the DISTINCT names:
+        // group rows by ref_name (first-seen order), sort the groups, emit rows group by group.
+        std::vector<uint32_t> grp_of(n), grp_first;
+        {
+            size_t cap = 64;
+            while (cap < 2 * n + 2) cap <<= 1;
+            std::vector<uint32_t> gt(cap, 0u);
+            for (uint32_t i = 0; i < n; ++i) {
+                const std::string_view nm = ref_name(rows[i]);
+                uint64_t h = 0xCBF29CE484222325ull;
+                for (unsigned char c : nm) h = (h ^ c) * 0x100000001B3ull;
+                size_t s = wga::mix64(h) & (cap - 1);
+                for (;;) {
+                    const uint32_t e = gt[s];
+                    if (!e) { grp_first.push_back(i); gt[s] = (uint32_t)grp_first.size(); grp_of[i] = gt[s] - 1; break; }
+                    if (ref_name(rows[grp_first[e - 1]]) == nm) { grp_of[i] = e - 1; break; }
+                    s = (s + 1) & (cap - 1);
+                }
+            }
+        }
+        const size_t ng = grp_first.size();
+        std::vector<uint32_t> gorder(ng), grank(ng), gcount(ng + 1, 0u), order(n);
+        for (uint32_t g = 0; g < ng; ++g) gorder[g] = g;
+        std::stable_sort(gorder.begin(), gorder.end(), [&](uint32_t a, uint32_t b) {
+            return wga::natord_cmp(ref_name(rows[grp_first[a]]), ref_name(rows[grp_first[b]])) < 0;
         });
-        if (!rows.empty())
+        // groups that natord calls equal (e.g. names differing in whitespace only) must keep row order ACROSS groups:
+        // give them one shared rank
+        {
+            uint32_t rank = 0;
+            for (size_t k = 0; k < ng; ++k) {
+                if (k && wga::natord_cmp(ref_name(rows[grp_first[gorder[k - 1]]]), ref_name(rows[grp_first[gorder[k]]])) != 0) ++rank;
+                grank[gorder[k]] = rank;
+            }
+        }
+        for (uint32_t i = 0; i < n; ++i) gcount[grank[grp_of[i]] + 1]++;
+        for (size_t g = 0; g < ng; ++g) gcount[g + 1] += gcount[g];
+        for (uint32_t i = 0; i < n; ++i) order[gcount[grank[grp_of[i]]]++] = i;
+
+        if (n) {
+            text.reserve(n * 192 + 512);
             text += "ref_name\tref_size\tref_start\tquery_name\tquery_size\tquery_start\taligned_size\t"
                     "unaligned_size\tidentity\tsimilarity\tmatched\tmismatched\tins_event\tdel_event\t"
                     "ins_size\tdel_size\tinv_event\tinv_size\tinv_ins_event\tinv_ins_size\t"
                     "inv_del_event\tinv_del_size\n";
+        }
+        char nb[24];
         for (uint32_t id : order) {
             const Row &r = rows[id];
             const uint64_t *c = r.v;
@@ -100,11 +169,15 @@ struct wga_stat_acc {
             uint64_t unaligned = each ? 0 : r.ref_size - aligned;  // wraps like release Rust (stat.rs:216)
             float identity = (float)matched / (float)aligned;
             float similarity = (float)(matched + mism) / (float)aligned;
-            wga::csv_field(text, r.ref_name);
-            auto u = [&](uint64_t x) { text.push_back('\t'); text += std::to_string(x); };
+            wga::csv_field(text, ref_name(r));
+            auto u = [&](uint64_t x) {
+                text.push_back('\t');
+                auto res = std::to_chars(nb, nb + sizeof nb, x);
+                text.append(nb, res.ptr - nb);
+            };
             auto f = [&](float x) { text.push_back('\t'); text += wga::fmt_f32(x); };
             u(r.ref_size); u(c[11]);
-            text.push_back('\t'); wga::csv_field(text, r.query_name);
+            text.push_back('\t'); wga::csv_field(text, query_name(r));
             u(r.query_size); u(c[12]); u(aligned); u(unaligned);
             f(identity); f(similarity);
             u(matched); u(mism); u(c[2]); u(c[4]); u(c[3]); u(c[5]); u(c[10]);
@@ -122,9 +195,8 @@ struct wga_stat_acc {
         uint64_t e = (uint64_t)each, n = rows.size();
         put(&e, 8); put(&n, 8);
         for (const Row &r : rows) {
-            uint32_t lr = (uint32_t)r.ref_name.size(), lq = (uint32_t)r.query_name.size();
-            put(&lr, 4); put(&lq, 4);
-            put(r.ref_name.data(), lr); put(r.query_name.data(), lq);
+            put(&r.lr, 4); put(&r.lq, 4);
+            put(names.data() + r.name_off, (size_t)r.lr + r.lq);
             put(&r.ref_size, 8); put(&r.query_size, 8); put(r.v, 13 * 8);
             uint32_t pad = 0;
             put(&r.inv_size, 4); put(&pad, 4);
@@ -134,8 +206,11 @@ struct wga_stat_acc {
         put(inv_pair.data(), ni * 4);
         put(inv_num.data(), ni * 8);
     }
-    int import_blob(const char *p, uint64_t len) {
-        const char *end = p + len;
+    // Transactional: the blob is validated in full before anything is merged.  A merged-mode row's inv_size (a carried
+    // f32 sum) is adopted only for rows this accumulator did not hold yet; f32 sums cannot be merged exactly otherwise.
+    int import_blob(const char *p0, uint64_t len) {
+        struct In { const char *rn; uint32_t lr, lq; uint64_t rs, qs, v[13]; float invs; };
+        const char *p = p0, *end = p0 + len;
         auto get = [&](void *d, size_t n) -> bool {
             if ((size_t)(end - p) < n) return false;
             memcpy(d, p, n);
@@ -144,38 +219,47 @@ struct wga_stat_acc {
         };
         uint64_t e, n;
         if (!get(&e, 8) || !get(&n, 8) || (int)e != each) return WGA_E_INVALID_ARG;
-        std::vector<uint32_t> map(n);
+        if (n > (uint64_t)(end - p) / 136) return WGA_E_INVALID_ARG;  // a row is at least 8 + 16 + 104 + 8 bytes
+        std::vector<In> in((size_t)n);
         for (uint64_t i = 0; i < n; ++i) {
-            uint32_t lr, lq;
-            if (!get(&lr, 4) || !get(&lq, 4) || (size_t)(end - p) < (size_t)lr + lq) return WGA_E_INVALID_ARG;
-            std::string rn(p, lr), qn(p + lr, lq);
-            p += lr + lq;
-            uint64_t rs, qs, v[13];
-            float invs;
+            In &r = in[i];
+            if (!get(&r.lr, 4) || !get(&r.lq, 4) || (uint64_t)(end - p) < (uint64_t)r.lr + r.lq) return WGA_E_INVALID_ARG;
+            r.rn = p;
+            p += (size_t)r.lr + r.lq;
             uint32_t pad;
-            if (!get(&rs, 8) || !get(&qs, 8) || !get(v, 13 * 8) || !get(&invs, 4) || !get(&pad, 4))
-                return WGA_E_INVALID_ARG;
-            if (each) {
-                Row r;
-                r.ref_name = rn; r.query_name = qn; r.ref_size = rs; r.query_size = qs;
-                memcpy(r.v, v, sizeof v);
-                r.inv_size = invs;
-                rows.push_back(std::move(r));
-                map[i] = (uint32_t)rows.size() - 1;
-            } else {
-                map[i] = find_or_add(rn, rs, qn, qs);
-                add_pair_vals(map[i], v);
-            }
+            if (!get(&r.rs, 8) || !get(&r.qs, 8) || !get(r.v, 13 * 8) || !get(&r.invs, 4) || !get(&pad, 4)) return WGA_E_INVALID_ARG;
         }
         uint64_t ni;
-        if (!get(&ni, 8) || (uint64_t)(end - p) < ni * 12) return WGA_E_INVALID_ARG;
+        if (!get(&ni, 8) || ni > (uint64_t)(end - p) / 12) return WGA_E_INVALID_ARG;
         const char *pp = p, *pn = p + ni * 4;
+        for (uint64_t i = 0; i < ni; ++i) {
+            uint32_t a;
+            memcpy(&a, pp + i * 4, 4);
+            if (a >= n) return WGA_E_INVALID_ARG;
+        }
+        // ---- commit
+        std::vector<uint32_t> map((size_t)n);
+        for (uint64_t i = 0; i < n; ++i) {
+            const In &r = in[i];
+            if (each) {
+                map[i] = push_row(r.rn, r.lr, r.rs, r.rn + r.lr, r.lq, r.qs, 0);
+                Row &row = rows[map[i]];
+                memcpy(row.v, r.v, sizeof r.v);
+                row.inv_size = r.invs;
+            } else {
+                const size_t before = rows.size();
+                map[i] = find_or_add(r.rn, r.lr, r.rs, r.rn + r.lr, r.lq, r.qs);
+                add_pair_vals(map[i], r.v);
+                if (rows.size() != before) rows[map[i]].inv_size = r.invs;
+            }
+        }
+        inv_pair.reserve(inv_pair.size() + ni);
+        inv_num.reserve(inv_num.size() + ni);
         for (uint64_t i = 0; i < ni; ++i) {
             uint32_t a;
             uint64_t b;
             memcpy(&a, pp + i * 4, 4);
             memcpy(&b, pn + i * 8, 8);
-            if (a >= n) return WGA_E_INVALID_ARG;
             inv_pair.push_back(map[a]);
             inv_num.push_back(b);
         }

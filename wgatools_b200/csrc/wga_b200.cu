@@ -854,14 +854,14 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         }
         uint64_t *p_first = ctx->buf<uint64_t>(B_PAIR_FIRST, n_pairs + 1);
         uint64_t *p_vals = ctx->buf<uint64_t>(B_PAIR_VALS, (n_pairs + 1) * kPairVals);
-        uint64_t *p_sizes = ctx->buf<uint64_t>(B_GEN_B, (n_pairs + 1) * 2);
+        uint64_t *p_sizes = ctx->buf<uint64_t>(B_GEN_B, (n_pairs + 1) * 3);
         uint32_t *nlen = ctx->buf<uint32_t>(B_NAME_LEN, 2 * n_pairs + 1);
         uint64_t *noff = ctx->buf<uint64_t>(B_NAME_OFF, 2 * n_pairs + 1);
         uint32_t *inv_pair = ctx->buf<uint32_t>(B_INV_PAIR, n_inv + 1);
         uint64_t *inv_num = ctx->buf<uint64_t>(B_INV_NUM, n_inv + 1);
         if (!p_first || !p_vals || !p_sizes || !nlen || !noff || !inv_pair || !inv_num) return ctx->err_code;
         WGA_CK(cudaMemsetAsync(nlen + 2 * n_pairs, 0, 4, ctx->stream));
-        LAUNCH(ctx, k_pair_gather, grid_for(cap, 256), 256, cap, flag, idx, first, vals, M, p_first, p_vals, p_sizes, nlen);
+        LAUNCH(ctx, k_pair_gather, grid_for(cap, 256), 256, cap, flag, idx, keys, first, vals, M, p_first, p_vals, p_sizes, nlen);
         WGA_TRY(exclusive_sum(ctx, nlen, noff, 2 * n_pairs + 1));
         uint64_t name_total;
         WGA_TRY(read_scalars(ctx, {noff + 2 * n_pairs}, &name_total));
@@ -878,7 +878,7 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
             LAUNCH(ctx, k_iota, grid_for(n_pairs, 256), 256, ord_i, n_pairs);
             WGA_TRY(sort_pairs_u64(ctx, p_first, ord_k, ord_i, ord_v, n_pairs));
         }
-        const size_t b_vals = n_pairs * kPairVals * 8, b_sizes = n_pairs * 16, b_nlen = n_pairs * 8, b_ord = n_pairs * 8;
+        const size_t b_vals = n_pairs * kPairVals * 8, b_sizes = n_pairs * 24, b_nlen = n_pairs * 8, b_ord = n_pairs * 8;
         const size_t b_invp = (n_inv * 4 + 7) & ~(size_t)7, b_invn = n_inv * 8;
         const size_t o_vals = 0, o_sizes = o_vals + b_vals, o_nlen = o_sizes + b_sizes, o_ord = o_nlen + b_nlen, o_invp = o_ord + b_ord,
                      o_invn = o_invp + b_invp, o_names = o_invn + b_invn;
@@ -906,14 +906,12 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         std::vector<uint32_t> map(n_pairs);
         std::vector<uint64_t> name_pos(2 * n_pairs + 1, 0);
         for (uint64_t i = 0; i < 2 * n_pairs; ++i) name_pos[i + 1] = name_pos[i] + h_nlen[i];
-        const bool bulk = acc->rows.empty();  // first table: every pair is new, no key map needed
-        if (bulk) acc->rows.reserve(n_pairs);
-        for (uint64_t oi = 0; oi < n_pairs; ++oi) {
+        acc->rows.reserve(acc->rows.size() + n_pairs);
+        acc->grow_table(acc->rows.size() + n_pairs);
+        for (uint64_t oi = 0; oi < n_pairs; ++oi) {  // first-occurrence order; the device's pair hash is the host table's key
             const uint32_t p = (uint32_t)order[oi];
             const char *rn = h_names + name_pos[2 * p], *qn = h_names + name_pos[2 * p + 1];
-            if (bulk) map[p] = acc->add_new(rn, h_nlen[2 * p], h_sizes[2 * p], qn, h_nlen[2 * p + 1], h_sizes[2 * p + 1]);
-            else map[p] = acc->find_or_add(std::string(rn, h_nlen[2 * p]), h_sizes[2 * p], std::string(qn, h_nlen[2 * p + 1]),
-                                           h_sizes[2 * p + 1]);
+            map[p] = acc->find_or_add(rn, h_nlen[2 * p], h_sizes[3 * p], qn, h_nlen[2 * p + 1], h_sizes[3 * p + 1], h_sizes[3 * p + 2]);
             acc->add_pair_vals(map[p], &h_vals[(uint64_t)p * kPairVals]);
         }
         const size_t i0 = acc->inv_pair.size();
@@ -954,14 +952,14 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
     if (name_total) WGA_CK(cudaMemcpyAsync(h_names.data(), nbuf, name_total, cudaMemcpyDeviceToHost, ctx->stream));
     WGA_TRY(sync_check(ctx));
     uint64_t pos = 0;
+    acc->rows.reserve(acc->rows.size() + n_rec);
     for (uint64_t r = 0; r < n_rec; ++r) {
-        std::string rn(h_names.data() + pos, h_nlen[2 * r]);
+        const char *rn = h_names.data() + pos;
         pos += h_nlen[2 * r];
-        std::string qn(h_names.data() + pos, h_nlen[2 * r + 1]);
+        const char *qn = h_names.data() + pos;
         pos += h_nlen[2 * r + 1];
         if (skip[r]) continue;
-        wga_stat_acc::Row row;
-        row.ref_name = rn; row.query_name = qn; row.ref_size = tsz[r]; row.query_size = qsz[r];
+        wga_stat_acc::Row &row = acc->rows[acc->push_row(rn, h_nlen[2 * r], tsz[r], qn, h_nlen[2 * r + 1], qsz[r], 0)];
         const uint64_t *c = &c11[r * 11];
         for (int i = 0; i < 11; ++i) row.v[i] = c[i];
         row.v[11] = tst[r];
@@ -970,7 +968,6 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
             uint64_t aligned = c[0] + c[1] + c[5] + c[9], qal = c[0] + c[1] + c[3] + c[7];
             row.inv_size = (float)(aligned + qal) / (float)(c[10] + 1);
         }
-        acc->rows.push_back(std::move(row));
     }
     return WGA_OK;
 }
