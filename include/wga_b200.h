@@ -52,7 +52,8 @@ enum wga_status {
     WGA_E_INVALID_ARG = 101,
     WGA_E_UNSUPPORTED = 102,
     WGA_E_NOMEM = 103,
-    WGA_E_INTERNAL = 104
+    WGA_E_INTERNAL = 104,
+    WGA_E_NCCL = 105
 };
 
 enum { WGA_MEM_HOST = 0, WGA_MEM_DEVICE = 1 };
@@ -88,6 +89,8 @@ void wga_ctx_destroy(wga_ctx *ctx);
 const char *wga_last_error(const wga_ctx *ctx, uint64_t *where);
 /* number of kernels this ctx launched since creation (hand-written kernels / CUB utility scans) */
 void wga_ctx_launch_counts(const wga_ctx *ctx, uint64_t *own_kernels, uint64_t *cub_calls);
+/* NCCL collectives / point-to-point groups this ctx enqueued since creation */
+uint64_t wga_ctx_nccl_calls(const wga_ctx *ctx);
 /* elapsed device milliseconds of the dense column-walk kernel(s) of the last command and the
  * algorithmic bytes they covered (sum over launches) -- measured with CUDA events on the ctx stream */
 void wga_ctx_last_walk(const wga_ctx *ctx, float *ms, uint64_t *alg_bytes, uint32_t *launches);
@@ -142,6 +145,38 @@ int wga_stat_acc_write(wga_stat_acc *acc, wga_span *out);
 int wga_stat_acc_export(wga_stat_acc *acc, wga_span *blob);
 int wga_stat_acc_import(wga_stat_acc *acc, const void *blob, uint64_t len);
 uint64_t wga_stat_acc_npairs(const wga_stat_acc *acc);
+
+/* ---- cross-rank reduction of stat partials: SURVEY.md 8(e), src/tools/stat.rs:167-223 --------------------------------
+ * One rank per GPU; ranks hold contiguous byte ranges of the input in rank order and feed their own accumulator with
+ * wga_maf_stat / wga_paf_stat.  wga_stat_allreduce then turns every rank's (merged-mode) accumulator into the
+ * accumulator of the whole file: the ranks agree on the pair list (first-seen order over ranks 0..N-1 = file order),
+ * ONE all-reduce(sum, u64) of the [n_pairs x 11] counter table, one all-reduce(min, u64) of the [n_pairs x 2] starts,
+ * and the order-dependent f32 inv_size column carried rank to rank (n_pairs x 4 B per hop) so that the result is
+ * bit-identical to a single process reading the whole file.  wga_stat_acc_write on any rank prints the global TSV. */
+typedef struct wga_comm wga_comm;
+/* 128 bytes (ncclUniqueId): produced on one rank, distributed by the host's own means (MPI, torch.distributed, ...) */
+int wga_nccl_unique_id(void *id128);
+/* ncclCommInitRank on ctx's device; collectives run on the ctx stream */
+int wga_comm_init_nccl(wga_ctx *ctx, const void *id128, int rank, int world, wga_comm **out);
+/* adopt a communicator the host already owns (an ncclComm_t; not destroyed by wga_comm_destroy) */
+int wga_comm_from_nccl(wga_ctx *ctx, void *nccl_comm, wga_comm **out);
+/* hosts with another kind of communicator (and the CPU tests, over gloo) provide the three primitives on HOST buffers;
+ * each returns 0 on success.  op: 0 = sum, 1 = min.  sendrecv is one ring hop: send to dst and receive from src, either
+ * of which may be -1 (none). */
+typedef struct {
+    void *user;
+    int rank, world;
+    int (*allgather)(void *user, const void *send, void *recv, uint64_t bytes_per_rank);
+    int (*allreduce_u64)(void *user, uint64_t *buf, uint64_t n, int op);
+    int (*sendrecv)(void *user, const void *send, uint64_t send_bytes, int dst, void *recv, uint64_t recv_bytes, int src);
+} wga_transport;
+int wga_comm_from_transport(const wga_transport *t, wga_comm **out);
+void wga_comm_destroy(wga_comm *c);
+int wga_comm_rank(const wga_comm *c);
+int wga_comm_world(const wga_comm *c);
+const char *wga_comm_last_error(const wga_comm *c);
+/* collective: every rank calls it with its own accumulator (merged mode); on return all accumulators are identical */
+int wga_stat_allreduce(wga_comm *c, wga_stat_acc *acc);
 
 /* ---- call: src/tools/caller.rs:42-157, 159-265, 388-608 ------------------------------------- */
 typedef struct {

@@ -93,6 +93,78 @@ def test_stat_allreduce_gloo_world2():
     assert outs[0] == want and outs[1] == want
 
 
+def _blob_worker(rank, world, port, blobs, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import wgatools_b200 as w
+    from wgatools_b200 import dist as wd
+    comm = wd.make_comm(dist)
+    out = []
+    for case in blobs:
+        acc = w.StatAcc(False)
+        acc.import_(case[rank])
+        comm.allreduce_stat(acc)
+        out.append(acc.write())
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stat_allreduce_dictionary_paths_world3():
+    """pair-dictionary edge cases of wga_stat_allreduce: identical key sets in different order (the digest shortcut),
+    a rank with no records, pairs only a later rank holds, starts >= 2^63 under the unsigned min.  Expected = one
+    accumulator fed with the ranks' partials in rank order (the single-process merge of the same host code; the
+    world-2 test above pins the reduction against the oracle)."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    import wgatools_b200 as w
+    from wgatools_b200 import dist as wd
+    rng = np.random.default_rng(11)
+
+    def part(names, n_inv, big=False):
+        keys = [(f"ref.{a}".encode(), 1000 + a, f"qry.{b}".encode(), 2000 + b) for a, b in names]
+        vals = rng.integers(0, 1 << 40, size=(len(keys), 13), dtype=np.uint64)
+        vals[:, 11] = rng.integers(0, 900, size=len(keys))
+        vals[:, 12] = rng.integers(0, 1900, size=len(keys))
+        if big and len(keys):
+            vals[0, 11] = np.uint64((1 << 63) + 5)
+        inv_pair = rng.integers(0, max(len(keys), 1), size=n_inv if keys else 0, dtype=np.uint32)
+        inv_num = rng.integers(1, 1 << 33, size=len(inv_pair), dtype=np.uint64) | np.uint64(1)   # odd: halves are inexact in f32
+        return wd.build_blob(0, keys, vals, np.zeros(len(keys), np.float32), inv_pair, inv_num)
+
+    base = [(a, b) for a in range(12) for b in range(9)]
+    perm1 = [base[i] for i in rng.permutation(len(base))]
+    perm2 = [base[i] for i in rng.permutation(len(base))]
+    cases = [
+        [part(base, 400), part(perm1, 300), part(perm2, 500)],                      # same set, three orders
+        [part(base[:40], 100), part([], 0), part(base[20:], 200)],                  # empty rank, late pairs
+        [part([], 0), part(perm1[:30], 50, big=True), part(perm1[10:50], 60)],      # rank 0 empty
+        [part([], 0), part([], 0), part([], 0)],                                    # nothing anywhere
+    ]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_blob_worker, args=(r, 3, port, cases, q)) for r in range(3)]
+    for p in ps:
+        p.start()
+    outs = dict(q.get(timeout=180) for _ in range(3))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for ci, case in enumerate(cases):
+        one = w.StatAcc(False)
+        for blob in case:
+            one.import_(blob)
+        want = one.write()
+        for r in range(3):
+            assert outs[r][ci] == want, (ci, r)
+        assert ci == 3 or want.count(b"\n") > 10
+
+
 def _shard_worker(rank, world, port, text, paf, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -24,6 +24,18 @@ class CallOpts(ctypes.Structure):
                 ("chunk_size", ctypes.c_uint64), ("query_name", ctypes.c_char_p)]
 
 
+# wga_transport (include/wga_b200.h): host-buffer collective primitives provided by the caller
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int)
+SENDRECV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p,
+                               ctypes.c_uint64, ctypes.c_int)
+
+
+class Transport(ctypes.Structure):
+    _fields_ = [("user", ctypes.c_void_p), ("rank", ctypes.c_int), ("world", ctypes.c_int), ("allgather", ALLGATHER_FN),
+                ("allreduce_u64", ALLREDUCE_FN), ("sendrecv", SENDRECV_FN)]
+
+
 # every symbol include/wga_b200.h declares: name -> (restype, argtypes)
 _P = ctypes.POINTER
 ABI = {
@@ -31,6 +43,16 @@ ABI = {
     "wga_ctx_destroy": (None, [ctypes.c_void_p]),
     "wga_last_error": (ctypes.c_char_p, [ctypes.c_void_p, _P(ctypes.c_uint64)]),
     "wga_ctx_launch_counts": (None, [ctypes.c_void_p, _P(ctypes.c_uint64), _P(ctypes.c_uint64)]),
+    "wga_ctx_nccl_calls": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "wga_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "wga_comm_init_nccl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_void_p)]),
+    "wga_comm_from_nccl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _P(ctypes.c_void_p)]),
+    "wga_comm_from_transport": (ctypes.c_int, [_P(Transport), _P(ctypes.c_void_p)]),
+    "wga_comm_destroy": (None, [ctypes.c_void_p]),
+    "wga_comm_rank": (ctypes.c_int, [ctypes.c_void_p]),
+    "wga_comm_world": (ctypes.c_int, [ctypes.c_void_p]),
+    "wga_comm_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "wga_stat_allreduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "wga_ctx_last_walk": (None, [ctypes.c_void_p, _P(ctypes.c_float), _P(ctypes.c_uint64), _P(ctypes.c_uint32)]),
     "wga_host_alloc": (ctypes.c_void_p, [ctypes.c_uint64]),
     "wga_host_free": (None, [ctypes.c_void_p]),

@@ -162,6 +162,112 @@ class StatAcc:
             pass
 
 
+class Comm:
+    """Communicator for the one exchange step of the path, the stat all-reduce (include/wga_b200.h wga_comm_*).
+
+    Comm.nccl(ctx, dist)  -- production: an ncclComm_t created INSIDE the C-ABI library on ctx's device; torch.distributed
+                             only carries the 128-byte ncclUniqueId from rank 0 to the others (plumbing);
+    Comm.host(dist)       -- the same C++ reduction over caller-provided host-buffer primitives (wga_transport), here
+                             torch.distributed on CPU tensors (gloo): used by the CPU tests, world_size 2."""
+
+    def __init__(self, L, h, keep=None):
+        self.L, self.h, self._keep = L, h, keep
+
+    @classmethod
+    def nccl(cls, ctx, dist):
+        import torch
+        L = ctx.L
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            rc = L.wga_nccl_unique_id(ident)
+            if rc:
+                raise WGAError(rc, "wga_nccl_unique_id failed (libnccl.so.2 not found?)")
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        h = ctypes.c_void_p()
+        ctx._check(L.wga_comm_init_nccl(ctx.h, box[0], rank, world, ctypes.byref(h)))
+        return cls(L, h)
+
+    @classmethod
+    def host(cls, dist):
+        import numpy as np
+        import torch
+        L = _lib.load()
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def view(ptr, n, dtype=np.uint8):
+            return np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(ptr)).view(dtype)
+
+        def allgather(_u, send, recv, n):
+            try:
+                mine = torch.from_numpy(view(send, n).copy())
+                outs = [torch.empty(n, dtype=torch.uint8) for _ in range(world)]
+                dist.all_gather(outs, mine)
+                dst = view(recv, n * world)
+                for r, t in enumerate(outs):
+                    dst[r * n:(r + 1) * n] = t.numpy()
+                return 0
+            except Exception:
+                return 104
+
+        def allreduce(_u, buf, n, op):
+            try:
+                a = view(buf, n * 8, np.uint64)
+                if op == 0:   # wrapping u64 sum == wrapping i64 sum
+                    t = torch.from_numpy(a.view(np.int64).copy())
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                    a[:] = t.numpy().view(np.uint64)
+                else:         # unsigned min through the order-preserving map x ^ 2^63 -> i64
+                    t = torch.from_numpy((a ^ np.uint64(1 << 63)).view(np.int64).copy())
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    a[:] = t.numpy().view(np.uint64) ^ np.uint64(1 << 63)
+                return 0
+            except Exception:
+                return 104
+
+        def sendrecv(_u, send, sb, dst, recv, rb, src):
+            try:
+                req = None
+                if dst >= 0 and sb:
+                    req = dist.isend(torch.from_numpy(view(send, sb).copy()), dst)
+                if src >= 0 and rb:
+                    t = torch.empty(rb, dtype=torch.uint8)
+                    dist.recv(t, src)
+                    view(recv, rb)[:] = t.numpy()
+                if req is not None:
+                    req.wait()
+                return 0
+            except Exception:
+                return 104
+
+        fns = (_lib.ALLGATHER_FN(allgather), _lib.ALLREDUCE_FN(allreduce), _lib.SENDRECV_FN(sendrecv))
+        tr = _lib.Transport(None, rank, world, *fns)
+        h = ctypes.c_void_p()
+        rc = L.wga_comm_from_transport(ctypes.byref(tr), ctypes.byref(h))
+        if rc:
+            raise WGAError(rc, "wga_comm_from_transport failed")
+        return cls(L, h, keep=fns)
+
+    def allreduce_stat(self, acc):
+        """collective; acc (merged mode) becomes the accumulator of the whole file on every rank"""
+        rc = self.L.wga_stat_allreduce(self.h, acc.h)
+        if rc:
+            raise WGAError(rc, (self.L.wga_comm_last_error(self.h) or b"").decode("utf-8", "replace"))
+        return acc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wga_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _opt(s):
     return None if s is None else (s if isinstance(s, bytes) else str(s).encode())
 

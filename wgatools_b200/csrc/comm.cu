@@ -359,8 +359,6 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
         uint32_t lr, lq;
         uint64_t rs, qs;
         memcpy(&lr, p, 4); memcpy(&lq, p + 4, 4); memcpy(&rs, p + 8, 8); memcpy(&qs, p + 16, 8);
-        const uint64_t *hl = nullptr;
-        (void)hl;
         const uint32_t id = out.find_or_add(p + 24, lr, rs, p + 24 + lr, lq, qs);
         if (id != g) { *err = "pair identity collision across ranks; refusing to merge distinct pairs"; return WGA_E_INTERNAL; }
         cur[owner[g]] = p + 24 + lr + lq;

@@ -79,7 +79,7 @@ struct wga_ctx {
     std::string host_text;  // library-owned host text of the last call (pafpseudo file index, validate report)
     void *tok_cache = nullptr;  // TokCache (wga_b200.cu): index of the last tokenised MAF slab
     // accounting
-    uint64_t n_own = 0, n_cub = 0;
+    uint64_t n_own = 0, n_cub = 0, n_nccl = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float walk_ms = 0.f;
     uint64_t walk_bytes = 0;

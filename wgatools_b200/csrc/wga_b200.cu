@@ -534,6 +534,8 @@ void wga_ctx_launch_counts(const wga_ctx *ctx, uint64_t *own, uint64_t *cub_call
     if (cub_calls) *cub_calls = ctx ? ctx->n_cub : 0;
 }
 
+uint64_t wga_ctx_nccl_calls(const wga_ctx *ctx) { return ctx ? ctx->n_nccl : 0; }
+
 void wga_ctx_last_walk(const wga_ctx *ctx, float *ms, uint64_t *alg_bytes, uint32_t *launches) {
     if (ms) *ms = ctx->walk_ms;
     if (alg_bytes) *alg_bytes = ctx->walk_bytes;

@@ -1,21 +1,18 @@
-"""Cross-rank reduction of `stat` partials: one rank per GPU, records sharded by contiguous
-byte ranges in rank order; the only exchange of the whole hot path.
+"""Record sharding and the one exchange step of the hot path: one rank per GPU, the input cut into
+contiguous byte ranges in rank order, outputs concatenated in rank order; `stat` is the only command whose partial
+results meet.
 
-  1. ranks all-gather their Pair keys (ref_name, ref_size, query_name, query_size) -- a few kB;
-  2. every rank derives the same global pair list (first-seen order over ranks 0..N-1 = file order);
-  3. ONE all-reduce(sum) of the dense [n_pairs x 11] u64 counter table and one all-reduce(min) of the
-     [n_pairs x 2] start coordinates (NCCL when the tensors live on the GPU, gloo in the CPU tests);
-  4. the order-dependent f32 inv_size needs the '-'-strand records in file order: the (pair, numerator)
-     lists are all-gathered and concatenated in rank order (SURVEY hard part 5 / Q6).
-torch.distributed is plumbing here; all compute stays behind the C ABI.
+The reduction itself is C++ behind the C ABI (include/wga_b200.h `wga_stat_allreduce`, wgatools_b200/csrc/comm.cu):
+pair dictionary by all-gather of key hashes, ONE ncclAllReduce(sum) of the [n_pairs x 11] u64 counters, one
+ncclAllReduce(min) of the [n_pairs x 2] starts, and the order-dependent f32 inv_size carried rank to rank
+(src/tools/stat.rs:167-223).  torch.distributed is plumbing here: it launches the ranks and carries the
+ncclUniqueId; on CPU (gloo, the tests) it also provides the three host-buffer primitives of `wga_transport`.
 """
 import struct
 
 import numpy as np
 
-from .api import StatAcc
-
-_I64_MAX = np.iinfo(np.int64).max
+from .api import Comm, StatAcc
 
 
 def parse_blob(blob: bytes):
@@ -60,52 +57,35 @@ def build_blob(each, keys, vals, invs, inv_pair, inv_num) -> bytes:
     return b"".join(out)
 
 
-def allreduce_stat(acc: StatAcc, dist, device=None) -> StatAcc:
-    """merged-mode stat accumulators of all ranks -> the global accumulator (identical on every rank)"""
-    import torch
-    world = dist.get_world_size()
-    each, keys, vals, invs, inv_pair, inv_num = parse_blob(acc.export())
-    if each:
-        raise ValueError("--each rows are concatenated in rank order, not reduced")
-    gathered = [None] * world
-    dist.all_gather_object(gathered, keys)
-    gkeys, index = [], {}
-    for ks in gathered:  # rank order == file order
-        for k in ks:
-            if k not in index:
-                index[k] = len(gkeys)
-                gkeys.append(k)
-    P = len(gkeys)
-    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
-    sums = torch.zeros((max(P, 1), 11), dtype=torch.int64)
-    mins = torch.full((max(P, 1), 2), _I64_MAX, dtype=torch.int64)
-    local = np.array([index[k] for k in keys], dtype=np.int64)
-    if len(keys):
-        sums[local] = torch.from_numpy(vals[:, :11].astype(np.int64))
-        mins[local] = torch.from_numpy(vals[:, 11:13].astype(np.int64))
-    sums, mins = sums.to(dev), mins.to(dev)
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM)  # the single counter all-reduce
-    dist.all_reduce(mins, op=dist.ReduceOp.MIN)
-    sums, mins = sums.cpu().numpy(), mins.cpu().numpy()
-    inv_lists = [None] * world
-    dist.all_gather_object(inv_lists, (local[inv_pair].astype(np.uint32) if len(inv_pair) else np.zeros(0, np.uint32),
-                                       inv_num))
-    g_pair = np.concatenate([p for p, _ in inv_lists]) if world else np.zeros(0, np.uint32)
-    g_num = np.concatenate([n for _, n in inv_lists]) if world else np.zeros(0, np.uint64)
-    gvals = np.zeros((P, 13), dtype=np.uint64)
-    if P:
-        gvals[:, :11] = sums[:P].astype(np.uint64)
-        gvals[:, 11:13] = mins[:P].astype(np.uint64)
-    out = StatAcc(False)
-    out.import_(build_blob(0, gkeys, gvals, np.zeros(P, np.float32), g_pair, g_num))
-    return out
+def make_comm(dist, ctx=None) -> Comm:
+    """NCCL communicator inside the C-ABI library when a Context (GPU) is given and the process group is nccl;
+    otherwise the host-buffer transport over torch.distributed (gloo)."""
+    if ctx is not None and dist.get_backend() == "nccl":
+        return Comm.nccl(ctx, dist)
+    return Comm.host(dist)
+
+
+def allreduce_stat(acc: StatAcc, dist=None, comm: Comm = None, ctx=None) -> StatAcc:
+    """merged-mode stat accumulators of all ranks -> the accumulator of the whole file, in place, identical on every
+    rank (wga_stat_allreduce).  Pass a `comm` made once with make_comm() when calling this repeatedly."""
+    own = comm is None
+    if own:
+        comm = make_comm(dist, ctx)
+    try:
+        return comm.allreduce_stat(acc)
+    finally:
+        if own:
+            comm.close()
 
 
 def shard_range(data, rank: int, world: int, kind: str = "maf"):
     """Byte range [lo, hi) of `data` that rank `rank` of `world` processes: contiguous ranges snapped to
-    record boundaries, concatenating the ranks' outputs in rank order reproduces the single-process output.
-    MAF: a range starts at a line that does not begin with 's', so s-line groups are never split (maf.rs:395-413); only
-    rank 0's range holds the file's first line, which the reader swallows (pass WGA_F_FIRST_SLAB there only).
+    record boundaries; concatenating the ranks' outputs in rank order reproduces the single-process output (chain ids:
+    see chain_id_base).
+    MAF: a range starts at a line that does not begin with 's', so s-line groups are never split (maf.rs:395-413).  The
+    file's first line -- which the reader swallows (maf.rs:25-36) -- belongs to the range that starts at byte 0 and is not
+    empty: pass WGA_F_FIRST_SLAB exactly when first_slab(lo, hi) says so (with more ranks than records several ranges
+    start at byte 0; all but the last of them are empty).
     PAF: a range starts right after a newline."""
     n = len(data)
 
@@ -126,3 +106,20 @@ def shard_range(data, rank: int, world: int, kind: str = "maf"):
                 p = nl + 1
         return min(p, n)
     return snap(n * rank // world), snap(n * (rank + 1) // world)
+
+
+def first_slab(lo: int, hi: int) -> bool:
+    """does the byte range [lo, hi) hold the file's first line?"""
+    return lo == 0 and hi > 0
+
+
+def chain_id_base(n_records: int, dist) -> int:
+    """maf2chain / paf2chain number the chains of the WHOLE file (converter.rs:82-88 `enumerate`): rank r passes
+    id_base = number of records of ranks 0..r-1, i.e. an exclusive scan of the per-rank record counts."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor([int(n_records)], dtype=torch.int64, device=dev)
+    every = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(every, mine)
+    return int(sum(int(t.item()) for t in every[:rank]))
