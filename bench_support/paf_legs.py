@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Second-wave measurements (scaled): `stat -f paf`, `paf2maf`, `call -f paf`, `pafpseudo`.
 
-Not the headline bench (that is bench.py, config 2).  One JSON line per command:
+Not the headline workload (that is bench.py's config 2); bench.py runs these legs as `--config 4` / `--config 5` and, in
+its default single-GPU run, reports them under the `side_configs` key.  One JSON object per command:
   value     = input bytes / device time with the PAF (and FASTA) resident in HBM   (CUDA events on the ctx stream)
   e2e       = same through the host-buffer C-ABI call (H2D + D2H inside)
   cpu       = the CPU port (oracle) on a bounded sample of the same input, one thread (these reference paths
               are sequential: src/tools/caller.rs:283-292, src/converter.rs:196, src/tools/stat.rs:92-99 is rayon)
-Usage (GPU box): python tools/bench_paf.py [--records 2000000] [--genomes 4] [--chrs 5] [--chr-mbp 1.0] [--fa-records 50000]
+Usage (GPU box): python bench_support/paf_legs.py [--records 2000000] [--genomes 4] [--chrs 5] [--chr-mbp 1.0] [--fa-records 50000]
 (pafpseudo writes one target-sized row per (target, query) pair, so the FASTA-backed part is kept to a few hundred pairs)
 """
 import argparse
@@ -17,8 +18,9 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 import numpy as np  # noqa: E402
 
@@ -58,7 +60,7 @@ def dedupe_ties(paf):
     return b"".join(out)
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--records", type=int, default=2_000_000, help="config-4 PAF records for stat -f paf")
     ap.add_argument("--genomes", type=int, default=4)
@@ -68,17 +70,21 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--cpu-mb", type=float, default=60.0)
     ap.add_argument("--only", default="", help="stat | fasta : run one half only (profiling)")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
 
+
+def run(args, ctx=None, emit=None):
+    """runs the legs `args.only` selects on the current CUDA device; every JSON object goes to emit() (default: print)"""
     import torch
-    import __graft_entry__ as g
-    g.build()
     import bench_support as bs
     import oracle_lib as orc
     import wgatools_b200 as w
-    torch.cuda.set_device(0)
-    ctx = w.Context(0, torch.cuda.current_stream().cuda_stream)
+    if ctx is None:
+        ctx = w.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
     L = ctx.L
+    if emit is None:
+        def emit(line):
+            print(json.dumps(line), flush=True)
 
     def timed(fn, steps):
         fn()
@@ -113,7 +119,7 @@ def main():
                                  "sample": f"first {cpu_n / 1e6:.0f} MB of the same PAF, C restatement of the reference algorithm"}}
         if extra:
             line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     # ---------------- config 4 (scaled): stat -f paf
     if args.only == "fasta":
@@ -223,6 +229,14 @@ def main():
         if name in ("paf2maf", "pseudo") and walk_ms > 0:
             extra["expand_kernels"] = {"ms": walk_ms, "output_GBps": walk_bytes / walk_ms / 1e6}
         report(label, len(paf5), ms_dev, ms_e2e, outn[name], cpu, len(smp5), extra)
+
+
+def main():
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    torch.cuda.set_device(0)
+    run(parse_args())
 
 
 if __name__ == "__main__":

@@ -46,7 +46,9 @@ enum wga_status {
                                        stat/maf2paf: slines[1], maf.rs:426-453) */
     WGA_E_CSV = 9,                  /* CsvDeserialize       errors.rs:20-21 */
     WGA_E_VCF_BASE = 10,            /* noodles REF/ALT base outside ACGTNacgtn (caller.rs:379-382) */
-    WGA_E_NOM = 11,
+    WGA_E_NOM = 11,                 /* NomErr               errors.rs:45-46,88-97 */
+    WGA_E_CHAIN_FIELD_MISSING = 12, /* ParseChain(FiledMissing) errors.rs:47-48,109-112 */
+    WGA_E_PARSE_FLOAT = 13,         /* ParseFloatError      errors.rs:54-56 */
     /* library errors */
     WGA_E_CUDA = 100,
     WGA_E_INVALID_ARG = 101,
@@ -67,9 +69,16 @@ enum {
     /* with mem == WGA_MEM_DEVICE, on wga_maf2paf / wga_maf_stat / wga_maf_call: the caller asserts that (text, len)
      * is the slab the previous MAF command on this ctx was given and that its bytes have not changed; the on-device
      * tokenisation of that call (delimiter index, line table, s-line fields) is then reused -- the reference parses
-     * the file once per command -- and only the command-specific record building and walk are run.  Ignored when
-     * no matching index is held. */
-    WGA_F_REUSE_INDEX = 4u
+     * the file once per command -- and only the command-specific record building and walk are run (not even those
+     * when the previous command left them behind, see WGA_F_SHARE_WALK).  Ignored when no matching index is held, and
+     * by the PAF entry points. */
+    WGA_F_REUSE_INDEX = 4u,
+    /* on wga_maf2paf, when further MAF commands on the SAME slab follow (with WGA_F_REUSE_INDEX): run the dense column
+     * walk once in the finer classification `call` needs (both-gap columns kept apart, cigar.rs:314-328) and keep what
+     * it produced -- the 11 counters of every record and the run list.  A following wga_maf_stat then needs no walk
+     * at all (RecStat::from(Cigar), common.rs:116-140, is a function of those counters) and a following wga_maf_call
+     * starts at its chunk grid.  The reference computes the same walk once per command. */
+    WGA_F_SHARE_WALK = 8u
 };
 
 typedef struct wga_ctx wga_ctx;
@@ -235,6 +244,20 @@ int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
                   uint64_t id_base, wga_span *out, uint64_t *n_records);
 int wga_paf2chain(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
                   uint64_t *n_records);
+
+/* ---- chain2paf / chain2maf: src/converter.rs:391-416, :268-388 with the reader of src/parser/chain.rs:27-75,206-383 ----
+ * `text` = whole chain records (it must start with a `chain` header line).  The reader's nom grammar is reproduced
+ * line-locally on the device (wgatools_b200/csrc/chain_in.cuh): a data line is a line without any of the letters
+ * c,h,a,i,n that ends in a newline; lines between a record's data lines and the next header are skipped; a last data
+ * line without its newline is dropped, as the reference drops it.
+ * chain2paf: one PAF row per chain, 12 columns + "cg:Z:<size>M[<target_diff>I][<query_diff>D]..." (chain.rs:430-451,
+ * cigar.rs:554-626; data lines are read as "size query_diff target_diff", chain.rs:333-350).
+ * chain2maf: "a score=255" blocks; target [t_start, t_end-1] and query [q_start, q_end-1] from the FASTAs, '-' queries
+ * reverse-complemented, gaps inserted by the data lines (converter.rs:360-388); header text from wga_chain2maf_header. */
+int wga_chain2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out);
+int wga_chain2maf_header(wga_ctx *ctx, const char *t_fa_path, const char *q_fa_path, wga_span *out);
+int wga_chain2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *target,
+                  const wga_fasta *query, wga_span *out);
 
 /* ---- pafcov: src/tools/pafcov.rs:13-60 + src/parser/cigar.rs:710-741 ------------------------------- */
 /* BED lines "{target}\t{pos}\t{pos+1}\t{count}\n" for every base of every target (vector length = target_length of

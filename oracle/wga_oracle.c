@@ -1118,6 +1118,16 @@ int orc_call_maf(const char *text, size_t len, int snp, int inv, uint64_t svlen_
             rc = -ORC_E_PANIC;
             break;
         }
+        { /* create_chunk_record slices EVERY s-line of the block with [start..end] (caller.rs:233-234): any row shorter
+             than the target row panics once the chunk grid reaches its end */
+            int ragged = 0;
+            for (size_t i = 0; i < rec.n; i++) ragged |= rec.s[i].seq.n < total;
+            if (ragged) {
+                set_err(err, errcap, "panic: byte index out of range of an s-line seq");
+                rc = -ORC_E_PANIC;
+                break;
+            }
+        }
         size_t cs = 0;
         int e = ORC_OK;
         if (chunk_size == 0 && total > 0) { /* the reference would loop forever (caller.rs:119) */
@@ -2138,4 +2148,233 @@ int orc_pafcov(const char *text, size_t len, orc_buf *out, char *err, size_t err
     free(T); free(row.f); free(row.scratch);
     orc_buf_free(&conv);
     return rc;
+}
+
+/* ======================================================================================
+ * chain reader, chain2paf, chain2maf
+ *   src/parser/chain.rs:27-37,60-75 (ChainReader::records: the whole file is read into one String and
+ *   chain_parser is applied to what is left of it), :206-383 (parse_header, line_not_chain,
+ *   parse_line_to_cdl, parse_chain_data_line, chain_parser), :430-452 (ChainRecord::convert2paf),
+ *   src/parser/cigar.rs:554-626 (parse_chain_to_cigar), src/converter.rs:268-357 (chain2maf),
+ *   :360-388 (parse_chain_to_insert), :391-416 (chain2paf).
+ * nom 7.1.3 combinators restated from their documented behaviour (parity unpinned beyond the round trips):
+ *   tag("chain")            the rest must START with "chain" (no skipping before the first record)
+ *   not_line_ending         header text up to "\n" / "\r\n" (a lone '\r' is an error)
+ *   line_ending             "\n" or "\r\n" must follow the header (a header that ends the file is an error)
+ *   fold_many1(terminated(is_not("chain\n"), line_ending))
+ *                           a data line = >= 1 characters none of which is one of c,h,a,i,n,'\n', followed by a line
+ *                           ending; the fold stops at the first line that is not one (a blank line, a line that
+ *                           holds one of those letters, a last line WITHOUT its newline -- which is therefore
+ *                           silently dropped) and needs at least one
+ *   take_while(|x| x != 'c') everything up to the next 'c' is skipped (blank lines, comments without a 'c')
+ * A data line is split_whitespace(): size, then query_diff (default 0), then target_diff (default 0) -- in that
+ * order (chain.rs:333-350; the UCSC format has dt before dq, the reference reads AND writes them as it does).
+ * ====================================================================================== */
+typedef struct {
+    sv tname, qname;
+    uint64_t tsize, tstart, tend, qsize, qstart, qend, id;
+    int tneg, qneg;
+    chainline *lines;
+    size_t n, cap;
+} chainrec;
+
+/* Rust's str::parse::<f64>() accepts: [+-] (digits [. digits?] | . digits) [(e|E) [+-] digits] | [+-] inf | infinity | nan
+ * (case-insensitive words); only validity matters here (the score is never printed) */
+static int rust_f64_ok(sv s) {
+    size_t i = 0;
+    if (s.n == 0) return 0;
+    if (s.p[0] == '+' || s.p[0] == '-') i = 1;
+    if (i == s.n) return 0;
+    {
+        char w[9]; size_t m = s.n - i;
+        if (m <= 8) {
+            for (size_t k = 0; k < m; k++) { char c = s.p[i + k]; w[k] = (c >= 'A' && c <= 'Z') ? (char)(c + 32) : c; }
+            w[m] = 0;
+            if (!strcmp(w, "inf") || !strcmp(w, "infinity") || !strcmp(w, "nan")) return 1;
+        }
+    }
+    size_t nd = 0;
+    while (i < s.n && s.p[i] >= '0' && s.p[i] <= '9') { i++; nd++; }
+    if (i < s.n && s.p[i] == '.') { i++; while (i < s.n && s.p[i] >= '0' && s.p[i] <= '9') { i++; nd++; } }
+    if (nd == 0) return 0;
+    if (i < s.n && (s.p[i] == 'e' || s.p[i] == 'E')) {
+        i++;
+        if (i < s.n && (s.p[i] == '+' || s.p[i] == '-')) i++;
+        size_t ne = 0;
+        while (i < s.n && s.p[i] >= '0' && s.p[i] <= '9') { i++; ne++; }
+        if (ne == 0) return 0;
+    }
+    return i == s.n;
+}
+
+static int ws_next(sv line, size_t *pos, sv *tok) { /* str::split_whitespace */
+    size_t i = *pos;
+    while (i < line.n && is_ws(line.p[i])) i++;
+    if (i >= line.n) { *pos = i; return 0; }
+    size_t b = i;
+    while (i < line.n && !is_ws(line.p[i])) i++;
+    tok->p = line.p + b; tok->n = i - b;
+    *pos = i;
+    return 1;
+}
+
+static int nom_err(char *err, size_t errcap, const char *code, const char *at, size_t left) {
+    /* errors.rs:88-97: e.input[..10] -- itself a panic when fewer than 10 bytes are left */
+    if (left < 10) { set_err(err, errcap, "panic: byte index 10 is out of bounds (nom error %s on a short rest)", code); return ORC_E_PANIC; }
+    set_err(err, errcap, "Format error %s at: %.10s Parse Error by rust::nom, please check", code, at);
+    return ORC_E_NOM;
+}
+
+/* one chain_parser() call on text[*pos..]; 1 = record, 0 = input exhausted, < 0 = -error */
+static int chain_next(const char *t, size_t len, size_t *pos, chainrec *rec, char *err, size_t errcap) {
+    size_t i = *pos;
+    if (i >= len) return 0;
+    if (len - i < 5 || memcmp(t + i, "chain", 5) != 0) return -nom_err(err, errcap, "Tag", t + i, len - i);
+    i += 5;
+    size_t h0 = i;
+    while (i < len && t[i] != '\n' && t[i] != '\r') i++;
+    if (i < len && t[i] == '\r' && !(i + 1 < len && t[i + 1] == '\n')) return -nom_err(err, errcap, "Tag", t + i, len - i);
+    sv hl = {t + h0, i - h0};
+    /* parse_header (chain.rs:206-315) */
+    static const char *fname[12] = {"score", "target_name", "target_size", "target_strand", "target_start", "target_end",
+                                    "query_name", "query_size", "query_strand", "query_start", "query_end", "chain_id"};
+    sv f[12];
+    size_t hp = 0;
+    uint64_t u[12] = {0};
+    for (int k = 0; k < 12; k++) {
+        if (!ws_next(hl, &hp, &f[k])) {
+            set_err(err, errcap, "Parse Chain Error By: Chain Line Field `%s` Missing", fname[k]);
+            return -ORC_E_CHAIN_FIELD_MISSING;
+        }
+        if (k == 0) {
+            if (!rust_f64_ok(f[k])) { set_err(err, errcap, "Parse `%.*s` Into Float Error", (int)f[k].n, f[k].p); return -ORC_E_PARSE_FLOAT; }
+        } else if (k == 3 || k == 8) {
+            if (!(sv_eq_c(f[k], "+") || sv_eq_c(f[k], "-"))) { set_err(err, errcap, "Parse Strand `%.*s` Error", (int)f[k].n, f[k].p); return -ORC_E_PARSE_STRAND; }
+        } else if (k != 1 && k != 6) {
+            if (!parse_u64(f[k], &u[k])) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)f[k].n, f[k].p); return -ORC_E_PARSE_INT; }
+        }
+    }
+    rec->tname = f[1]; rec->tsize = u[2]; rec->tneg = sv_eq_c(f[3], "-"); rec->tstart = u[4]; rec->tend = u[5];
+    rec->qname = f[6]; rec->qsize = u[7]; rec->qneg = sv_eq_c(f[8], "-"); rec->qstart = u[9]; rec->qend = u[10]; rec->id = u[11];
+    /* line_ending */
+    if (i >= len) return -nom_err(err, errcap, "CrLf", t + i, 0);
+    i += t[i] == '\r' ? 2 : 1;
+    /* fold_many1(line_not_chain): the closure's `?` parks the first parse error in the accumulator, later lines
+     * are still consumed (chain.rs:352-369) */
+    rec->n = 0;
+    int line_rc = 0;
+    size_t nl_lines = 0;
+    for (;;) {
+        size_t j = i;
+        while (j < len && t[j] != 'c' && t[j] != 'h' && t[j] != 'a' && t[j] != 'i' && t[j] != 'n' && t[j] != '\n') j++;
+        if (j == i) break;                       /* is_not needs one character */
+        if (j >= len || t[j] != '\n') break;     /* terminated(.., line_ending): "\r\n" ends in '\n' too ('\r' is matched by is_not) */
+        sv dl = {t + i, j - i};
+        i = j + 1;
+        nl_lines++;
+        if (line_rc) continue;
+        size_t dp = 0;
+        sv tok;
+        chainline c = {0, 0, 0};
+        if (!ws_next(dl, &dp, &tok)) { set_err(err, errcap, "Parse Chain Error By: Chain Line Field `size` Missing"); line_rc = ORC_E_CHAIN_FIELD_MISSING; continue; }
+        if (!parse_u64(tok, &c.size)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)tok.n, tok.p); line_rc = ORC_E_PARSE_INT; continue; }
+        if (ws_next(dl, &dp, &tok) && !parse_u64(tok, &c.qdiff)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)tok.n, tok.p); line_rc = ORC_E_PARSE_INT; continue; }
+        if (dp < dl.n && ws_next(dl, &dp, &tok) && !parse_u64(tok, &c.tdiff)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)tok.n, tok.p); line_rc = ORC_E_PARSE_INT; continue; }
+        if (rec->n == rec->cap) { rec->cap = rec->cap ? rec->cap * 2 : 64; rec->lines = (chainline *)realloc(rec->lines, rec->cap * sizeof(chainline)); }
+        rec->lines[rec->n++] = c;
+    }
+    if (nl_lines == 0) return -nom_err(err, errcap, "Many1", t + i, len - i);
+    if (line_rc) return -line_rc;
+    while (i < len && t[i] != 'c') i++;  /* take_while(|x| x != 'c') */
+    *pos = i;
+    return 1;
+}
+
+/* chain.rs:430-451 convert2paf + cigar.rs:554-626 parse_chain_to_cigar + the csv writer of converter.rs:396-414:
+ * 12 columns + the one cg:Z: tag; block_length = match + mismatch + del + inv_del with del = query_diff */
+int orc_chain2paf(const char *text, size_t len, orc_buf *out, char *err, size_t errcap) {
+    size_t pos = 0;
+    chainrec rec = {0};
+    int rc;
+    while ((rc = chain_next(text, len, &pos, &rec, err, errcap)) > 0) {
+        uint64_t match = 0, del = 0;
+        for (size_t k = 0; k < rec.n; k++) { match += rec.lines[k].size; del += rec.lines[k].qdiff; }
+        csv_field(out, rec.qname, 1);
+        csv_u64(out, rec.qsize, 0); csv_u64(out, rec.qstart, 0); csv_u64(out, rec.qend, 0);
+        buf_putc(out, '\t'); buf_putc(out, rec.qneg ? '-' : '+');
+        csv_field(out, rec.tname, 0);
+        csv_u64(out, rec.tsize, 0); csv_u64(out, rec.tstart, 0); csv_u64(out, rec.tend, 0);
+        csv_u64(out, match, 0); csv_u64(out, match + del, 0); csv_u64(out, 255, 0);
+        buf_puts(out, "\tcg:Z:");
+        for (size_t k = 0; k < rec.n; k++) {
+            buf_putu(out, rec.lines[k].size); buf_putc(out, 'M');
+            if (rec.lines[k].tdiff) { buf_putu(out, rec.lines[k].tdiff); buf_putc(out, 'I'); }
+            if (rec.lines[k].qdiff) { buf_putu(out, rec.lines[k].qdiff); buf_putc(out, 'D'); }
+        }
+        buf_putc(out, '\n');
+    }
+    free(rec.lines);
+    return rc < 0 ? -rc : ORC_OK;
+}
+
+/* converter.rs:268-388 chain2maf: score 255, target fetched [t_start, t_end-1], query [q_start, q_end-1] with the header's
+ * own query coordinates, reverse-complemented for '-'; s-line start of a '-' query = q_size - q_end; the target strand is
+ * printed as the header has it; parse_chain_to_insert walks one shared offset: += size, target_diff x '-' into the TARGET
+ * row, query_diff x '-' into the QUERY row (insert_str panics past the end of the row) */
+int orc_chain2maf(const char *text, size_t len, const char *t_fa, size_t t_fa_len, const char *t_fai, size_t t_fai_len,
+                  const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, const char *t_path,
+                  const char *q_path, orc_buf *out, char *err, size_t errcap) {
+    faidx tf, qf;
+    if (fai_parse(t_fai, t_fai_len, t_fa, t_fa_len, &tf) || fai_parse(q_fai, q_fai_len, q_fa, q_fa_len, &qf)) {
+        set_err(err, errcap, "HTS library error by bad .fai");
+        return ORC_E_CSV;
+    }
+    buf_puts(out, "#maf version=1.6 convert_from=chain t_seq_path=");
+    buf_puts(out, t_path);
+    buf_puts(out, " q_seq_path=");
+    buf_puts(out, q_path);
+    buf_putc(out, '\n');
+    size_t pos = 0;
+    chainrec rec = {0};
+    orc_buf ts = {0}, qs = {0};
+    int rc, e = ORC_OK;
+    while ((rc = chain_next(text, len, &pos, &rec, err, errcap)) > 0) {
+        ts.n = 0; qs.n = 0;
+        /* `target_end() - 1` / `query_end() - 1` are u64 subtractions: 0 - 1 panics in debug, wraps in release; the wrapped
+         * value then clamps to the sequence end in faidx -- the release build's behaviour is kept */
+        if (fai_fetch(&tf, rec.tname, rec.tstart, rec.tend - 1, &ts) || fai_fetch(&qf, rec.qname, rec.qstart, rec.qend - 1, &qs)) {
+            set_err(err, errcap, "HTS library error by sequence not found");
+            e = ORC_E_NOM; break;
+        }
+        if (rec.qneg) {
+            char c = revcomp_inplace(qs.p, qs.n);
+            if (c) { set_err(err, errcap, "Invalid Base: `%c`", c); e = ORC_E_VCF_BASE; break; }
+        }
+        uint64_t off = 0;
+        for (size_t k = 0; k < rec.n && !e; k++) {
+            off += rec.lines[k].size;
+            if (rec.lines[k].tdiff) {
+                if (buf_insert_gaps(&ts, off, rec.lines[k].tdiff)) { set_err(err, errcap, "panic: insert_str index out of range"); e = ORC_E_PANIC; break; }
+                off += rec.lines[k].tdiff;
+            }
+            if (rec.lines[k].qdiff) {
+                if (buf_insert_gaps(&qs, off, rec.lines[k].qdiff)) { set_err(err, errcap, "panic: insert_str index out of range"); e = ORC_E_PANIC; break; }
+                off += rec.lines[k].qdiff;
+            }
+        }
+        if (e) break;
+        uint64_t q_start_maf = rec.qneg ? rec.qsize - rec.qend : rec.qstart;
+        buf_puts(out, "a score=255\n");
+        buf_puts(out, "s\t"); buf_put(out, rec.tname.p, rec.tname.n); buf_putc(out, '\t'); buf_putu(out, rec.tstart); buf_putc(out, '\t');
+        buf_putu(out, rec.tend - rec.tstart); buf_putc(out, '\t'); buf_putc(out, rec.tneg ? '-' : '+'); buf_putc(out, '\t');
+        buf_putu(out, rec.tsize); buf_putc(out, '\t'); buf_put(out, ts.p, ts.n); buf_putc(out, '\n');
+        buf_puts(out, "s\t"); buf_put(out, rec.qname.p, rec.qname.n); buf_putc(out, '\t'); buf_putu(out, q_start_maf); buf_putc(out, '\t');
+        buf_putu(out, rec.qend - rec.qstart); buf_putc(out, '\t'); buf_putc(out, rec.qneg ? '-' : '+'); buf_putc(out, '\t');
+        buf_putu(out, rec.qsize); buf_putc(out, '\t'); buf_put(out, qs.p, qs.n); buf_putc(out, '\n');
+        buf_putc(out, '\n');
+    }
+    free(rec.lines); free(tf.e); free(qf.e);
+    orc_buf_free(&ts); orc_buf_free(&qs);
+    if (e) return e;
+    return rc < 0 ? -rc : ORC_OK;
 }

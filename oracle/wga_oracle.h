@@ -39,7 +39,9 @@ enum {
     ORC_E_PANIC = 8,              /* the reference would panic (index out of bounds, slice) */
     ORC_E_CSV = 9,                /* "CSV deserialize error by: ..."     errors.rs:20-21 */
     ORC_E_VCF_BASE = 10,          /* noodles REF/ALT base parse failure (parity unpinned) */
-    ORC_E_NOM = 11                /* nom tag("cg:Z:") failure */
+    ORC_E_NOM = 11,               /* nom tag("cg:Z:") / tag("chain") / line_ending failure */
+    ORC_E_CHAIN_FIELD_MISSING = 12, /* "Parse Chain Error By: Chain Line Field `{0}` Missing"  errors.rs:47-48,109-112 */
+    ORC_E_PARSE_FLOAT = 13        /* "Parse `{0}` Into Float Error"      errors.rs:54-56 */
 };
 
 typedef struct {
@@ -116,6 +118,11 @@ int orc_paf2chain(const char *text, size_t len, orc_buf *out, char *err, size_t 
 
 /* src/tools/pafcov.rs:13-60 + cigar.rs:710-741 (`pafcov`): per-base BED coverage of every target */
 int orc_pafcov(const char *text, size_t len, orc_buf *out, char *err, size_t errcap);
+/* chain.rs:206-383 reader + converter.rs:391-416 chain2paf / :268-388 chain2maf */
+int orc_chain2paf(const char *text, size_t len, orc_buf *out, char *err, size_t errcap);
+int orc_chain2maf(const char *text, size_t len, const char *t_fa, size_t t_fa_len, const char *t_fai, size_t t_fai_len,
+                  const char *q_fa, size_t q_fa_len, const char *q_fai, size_t q_fai_len, const char *t_path,
+                  const char *q_path, orc_buf *out, char *err, size_t errcap);
 
 /* helpers exposed for unit tests */
 int  orc_natord_compare(const char *a, const char *b);       /* natord 1.0.9 compare */

@@ -66,6 +66,9 @@ def lib():
                                     ctypes.c_size_t]
         L.orc_paf2chain.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_pafcov.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_chain2paf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_chain2maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 5 + [ctypes.c_char_p, ctypes.c_char_p,
+                                                                               ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_paf_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(OrcCounts), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_parse_maf_seq_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
@@ -172,6 +175,15 @@ def maf2chain(text: bytes, query_name=None) -> bytes:
 
 def paf2chain(text: bytes) -> bytes:
     return _run(lib().orc_paf2chain, text, len(text))
+
+
+def chain2paf(text: bytes) -> bytes:
+    return _run(lib().orc_chain2paf, text, len(text))
+
+
+def chain2maf(text: bytes, t_fa: bytes, t_fai: bytes, q_fa: bytes, q_fai: bytes, t_path="t.fa", q_path="q.fa") -> bytes:
+    return _run(lib().orc_chain2maf, text, len(text), t_fa, len(t_fa), t_fai, len(t_fai), q_fa, len(q_fa), q_fai, len(q_fai),
+                _opt(t_path), _opt(q_path))
 
 
 def pafcov(text: bytes) -> bytes:

@@ -291,3 +291,120 @@ def call_paf_rows(rec, fasta_t, fasta_q, snp, svlen):
         else:
             return rows
     return rows
+
+
+# ---------------------------------------------------------------- chain reader / chain2paf / chain2maf (second spelling)
+def chain_records(text: str):
+    """src/parser/chain.rs:352-383 chain_parser, applied to what is left of the text.  Independent of the C oracle: this
+    one works on the whole string with str methods, the oracle walks bytes.  Raises ValueError(kind)."""
+    out, rest = [], text
+    while rest:
+        if not rest.startswith("chain"):
+            raise ValueError("nom" if len(rest) >= 10 else "panic")
+        rest = rest[5:]
+        nl = rest.find("\n")
+        header = rest if nl < 0 else rest[:nl]
+        if header.endswith("\r"):
+            header = header[:-1]
+        if "\r" in header:
+            raise ValueError("nom")
+        f = header.split()
+        names = ["score", "target_name", "target_size", "target_strand", "target_start", "target_end", "query_name", "query_size",
+                 "query_strand", "query_start", "query_end", "chain_id"]
+        vals = {}
+        for i, nm in enumerate(names):
+            if i >= len(f):
+                raise ValueError("missing:" + nm)
+            if nm == "score":
+                try:
+                    float(f[i])
+                    if "_" in f[i] or f[i].strip() != f[i] or f[i].lower().lstrip("+-") in ("infinity", "inf", "nan") and False:
+                        raise ValueError
+                except ValueError:
+                    raise ValueError("float:" + f[i])
+            elif nm.endswith("strand"):
+                if f[i] not in "+-" or len(f[i]) != 1:
+                    raise ValueError("strand:" + f[i])
+            elif not nm.endswith("name"):
+                if not _is_u64(f[i]):
+                    raise ValueError("int:" + f[i])
+            vals[nm] = f[i]
+        if nl < 0:
+            raise ValueError("panic")          # line_ending on an empty rest -> e.input[..10] panics
+        rest = rest[nl + 1:]
+        lines, err = [], None
+        n_lines = 0
+        while True:
+            nl = rest.find("\n")
+            if nl <= 0:
+                break
+            cand = rest[:nl]
+            if any(c in "chain" for c in cand):
+                break
+            rest = rest[nl + 1:]
+            n_lines += 1
+            if err:
+                continue
+            t = cand.split()
+            if not t:
+                err = "missing:size"
+                continue
+            bad = [x for x in t[:3] if not _is_u64(x)]
+            if bad:
+                err = "int:" + bad[0]
+                continue
+            lines.append((int(t[0]), int(t[1]) if len(t) > 1 else 0, int(t[2]) if len(t) > 2 else 0))
+        if n_lines == 0:
+            raise ValueError("nom" if len(rest) >= 10 else "panic")
+        if err:
+            raise ValueError(err)
+        c = rest.find("c")
+        rest = "" if c < 0 else rest[c:]
+        out.append((vals, lines))
+    return out
+
+
+def _is_u64(s):
+    t = s[1:] if s.startswith("+") else s
+    return t.isascii() and t.isdigit() and int(t) < (1 << 64)
+
+
+def chain2paf(text: str) -> str:
+    rows = []
+    for h, lines in chain_records(text):
+        match = sum(l[0] for l in lines)
+        dele = sum(l[1] for l in lines)
+        cg = "".join(f"{s}M" + (f"{td}I" if td else "") + (f"{qd}D" if qd else "") for s, qd, td in lines)
+        rows.append("\t".join([h["query_name"], str(int(h["query_size"])), str(int(h["query_start"])), str(int(h["query_end"])),
+                               h["query_strand"], h["target_name"], str(int(h["target_size"])), str(int(h["target_start"])),
+                               str(int(h["target_end"])), str(match), str(match + dele), "255", "cg:Z:" + cg]) + "\n")
+    return "".join(rows)
+
+
+def chain2maf(text: str, fa: dict, t_path="t.fa", q_path="q.fa") -> str:
+    """fa: name -> sequence (both FASTAs); well-formed inputs only (every name present, sizes consistent)"""
+    comp = str.maketrans("ACGTacgt", "TGCAtgca")
+    out = [f"#maf version=1.6 convert_from=chain t_seq_path={t_path} q_seq_path={q_path}\n"]
+    for h, lines in chain_records(text):
+        ts, te, qs, qe = int(h["target_start"]), int(h["target_end"]), int(h["query_start"]), int(h["query_end"])
+        t = fa[h["target_name"]][ts:te]
+        q = fa[h["query_name"]][qs:qe]
+        neg = h["query_strand"] == "-"
+        if neg:
+            q = q[::-1].translate(comp)
+        off = 0
+        for size, qd, td in lines:
+            off += size
+            if td:
+                assert off <= len(t)
+                t = t[:off] + "-" * td + t[off:]
+                off += td
+            if qd:
+                assert off <= len(q)
+                q = q[:off] + "-" * qd + q[off:]
+                off += qd
+        qsz = int(h["query_size"])
+        out.append("a score=255\n")
+        out.append(f"s\t{h['target_name']}\t{ts}\t{te - ts}\t{h['target_strand']}\t{int(h['target_size'])}\t{t}\n")
+        out.append(f"s\t{h['query_name']}\t{qsz - qe if neg else qs}\t{qe - qs}\t{h['query_strand']}\t{qsz}\t{q}\n\n")
+    return "".join(out)

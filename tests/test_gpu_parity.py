@@ -296,6 +296,75 @@ def test_reuse_index_across_commands(w, ctx):
     assert msgs[0] == msgs[1] == msgs[2] and msgs[0][0] == 2
 
 
+def test_share_walk_one_pass(w, ctx):
+    """WGA_F_SHARE_WALK: maf2paf runs the dense walk once in the caller classification and keeps counters + run list;
+    stat then needs no walk and call starts at its chunk grid.  Outputs stay byte-identical to the oracle, with and
+    without both-gap columns (where the EXT and the caller run lists differ), in either order of stat / call."""
+    import torch
+    from wgatools_b200._lib import CallOpts, WGA_F_REUSE_INDEX, WGA_F_SHARE_WALK
+    texts = [
+        (bs.gen_maf(bs.maf_params(600, seed=71, p_neg=0.3, p_bothgap=2e-3, p_mis=5e-3, p_gap=2e-3)), None),
+        (bs.gen_maf(bs.maf_params(40, seed=72, len_median=60000.0, len_sigma=0.5, len_max=200000, p_bothgap=1e-3, p_neg=0.5)), None),
+        (bs.gen_maf(bs.maf_params(500, seed=73, p_neg=0.1)), None),            # no both-gap columns: lists coincide
+        (TEST_MAF, None),
+        (TEST_MAF, "query.chr8"),
+        # hand-made: = W = / X W X / I W I / leading and trailing W, adjacent blocks
+        (b"##maf version=1\na score=0\ns t.c 10 8 + 100 AC-GT--ACG-\ns q.c 5 8 - 90 AC-CT--A-GA\n\n"
+         b"a\ns t.c 30 4 + 100 --AC-GT-\ns q.c 40 5 + 90 --ACTG--\n\na\ns t.c 50 3 + 100 A-C-G\ns q.c 60 3 + 90 A-T-G\n", None),
+    ]
+    cap = max(len(t) for t, _ in texts) + 64
+    d = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    for text, qn in texts:
+        opts = CallOpts(snp=1, inv=1, svlen_cutoff=0, chunk_size=20000, query_name=qn.encode() if qn else None)
+        d.zero_()
+        d[:len(text)].copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
+        torch.cuda.synchronize()
+        ptr = ctypes.c_void_p(d.data_ptr())
+        want_vcf = orc.call_maf(text, snp=True, inv=True, svlen=0, query_name=qn, chunk_size=20000)
+        for order in ("stat,call", "call,stat"):
+            p, n = ctx.maf2paf_raw(ptr, len(text), 1, 1 | WGA_F_SHARE_WALK, qn)
+            assert _dev_bytes(p, n) == orc.maf2paf(text, qn)
+            assert ctx.last_walk()[2] == 1
+            cnt = ctx.last_record_counts()
+            for cmd in order.split(","):
+                if cmd == "stat":
+                    for each in (False, True):
+                        acc = w.StatAcc(each)
+                        ctx.maf_stat_raw(ptr, len(text), 1, 1 | WGA_F_REUSE_INDEX, acc, qn)
+                        assert acc.write() == orc.stat_maf(text, each, qn)
+                        assert ctx.last_walk()[2] == 0, "stat after a shared walk must not walk again"
+                        assert (ctx.last_record_counts() == cnt).all()
+                else:
+                    p, n = ctx.maf_call_raw(ptr, len(text), 1, 1 | WGA_F_REUSE_INDEX, opts)
+                    assert ctx.vcf_header("sample") + _dev_bytes(p, n) == want_vcf
+                    assert ctx.last_walk()[2] == 0, "call after a shared walk must not walk again"
+        # another query name than the one the walk was shared for: every command falls back to its own pass
+        if qn is None and text is TEST_MAF:
+            ctx.maf2paf_raw(ptr, len(text), 1, 1 | WGA_F_SHARE_WALK)
+            acc = w.StatAcc(False)
+            ctx.maf_stat_raw(ptr, len(text), 1, 1 | WGA_F_REUSE_INDEX, acc, "query.chr8")
+            assert acc.write() == orc.stat_maf(text, False, "query.chr8") and ctx.last_walk()[2] == 1
+    # a block `call` sees differently (third row shorter than the target row -> the reference panics in
+    # create_chunk_record): maf2paf / stat are fine, call must not pick up the shared records
+    rag = (b"##maf version=1\na\ns t.c 0 8 + 100 ACGTACGT\ns q.c 0 8 + 90 ACGTACGA\ns r.c 0 4 + 80 ACGT\n\n"
+           b"a\ns t.c 20 4 + 100 ACGT\ns q.c 30 4 + 90 AGGT\n")
+    d.zero_()
+    d[:len(rag)].copy_(torch.frombuffer(bytearray(rag), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    ptr = ctypes.c_void_p(d.data_ptr())
+    opts = CallOpts(snp=1, inv=0, svlen_cutoff=0, chunk_size=1000000, query_name=None)
+    p, n = ctx.maf2paf_raw(ptr, len(rag), 1, 1 | WGA_F_SHARE_WALK)
+    assert _dev_bytes(p, n) == orc.maf2paf(rag)
+    acc = w.StatAcc(False)
+    ctx.maf_stat_raw(ptr, len(rag), 1, 1 | WGA_F_REUSE_INDEX, acc)
+    assert acc.write() == orc.stat_maf(rag) and ctx.last_walk()[2] == 0
+    with pytest.raises(orc.OracleError) as oe:
+        orc.call_maf(rag, snp=True, svlen=0)
+    with pytest.raises(w.WGAError) as e:
+        ctx.maf_call_raw(ptr, len(rag), 1, 1 | WGA_F_REUSE_INDEX, opts)
+    assert e.value.code == 8 and oe.value.code == 8
+
+
 def test_stat_export_import_roundtrip(w, ctx):
     text = bs.gen_maf(bs.maf_params(600, seed=44, p_neg=0.4))
     L = ctx.L
@@ -917,6 +986,82 @@ def test_chain_parity(w, ctx):
     with pytest.raises(w.WGAError) as e:
         m2c(_maf([[b"s t 0 4 + 100 ACGT"]]))
     assert e.value.code == 8
+
+
+def test_chain_reader_parity(w, ctx):
+    """chain2paf / chain2maf (converter.rs:268-416) with the on-device chain reader (chain_in.cuh) against the oracle:
+    well-formed files of every shape, the nom grammar's quirks, and every error class with its code"""
+    c2p = lambda t: w.run_bytes(w.chain2paf, w.ChainReader(t), ctx=ctx)
+    ch = orc.paf2chain(TEST_PAF)
+    assert c2p(ch) == orc.chain2paf(ch)
+    assert c2p(b"") == b""
+    two = (b"chain 255 t 100 + 0 10 q 90 - 5 15 0\n4\t1\t2\n3\n\n# a note without the letter\n\n"
+           b"chain 255 t 100 + 20 30 q 90 + 1 2 1\n7 2\n5")
+    H = b"chain 1 t 9 + 0 1 q 9 + 0 1 0\n"
+    good = [two, b"chain255 t 9 + 0 1 q 9 + 0 1 7 extra fields\r\n1 0 0 9\r\n", H + b"1\n2 3\nh\n9 9 9\n" + H + b"5\n",
+            H + b"0\n", H + b"18446744073709551615 1 1\n1\n", b'chain 1e3 "t" 9 + 0 1 q"x 9 - 0 1 0\n4 0 3\n2\n\n\n\n' + H + b"1\n",
+            H + b"1\n" * 3000 + b"\n" + H + b"2 1\n" * 70000 + b"9\n"]
+    for t in good:
+        assert c2p(t) == orc.chain2paf(t), t[:80]
+    bads = [b"xchain 1 t 9 + 0 1 q 9 + 0 1 0\n1\n", b"xchain\n", H + b"\n", H + b"\n" + b"#" * 12, H[:-1],
+            b"chain a t 9 + 0 1 q 9 + 0 1 0\n1\n", b"chain 1 t x + 0 1 q 9 + 0 1 0\n1\n", b"chain 1 t 9 * 0 1 q 9 + 0 1 0\n1\n",
+            b"chain 1 t 9 + 0 1 q 9 + 0 1\n1\n", H + b"1\n2 x\n", H + b"1\n \n", H + b"1\n\n# a comment\n" + H + b"1\n",
+            H + b"1\n12 c\n", H + b"1\n" + H + b"x\n" + H + b"1\n", H + b"1\n\nzzz\n" + b"chain 1 t 9 + 0 1\n1\n" + b"chain x\n",
+            b"\n" + H + b"1\n", H + b"1\n" + b"chain 1 t 9 + 0 1 q 9 + 0 1 0\n" + b"#" * 20 + b"\n", H + b"99999999999999999999\n"]
+    for t in bads:
+        with pytest.raises(orc.OracleError) as eo:
+            orc.chain2paf(t)
+        with pytest.raises(w.WGAError) as eg:
+            c2p(t)
+        assert eg.value.code == eo.value.code, (t, eo.value, eg.value)
+        if eo.value.code in (1, 2, 12, 13):
+            assert str(eg.value) == eo.value.msg, t
+    # synthetic: the chains of generated PAFs / MAFs (long chains, both strands), then back
+    for seed, kw in ((1, {}), (2, dict(m_only=1)), (3, dict(ops_median=3000.0, ops_sigma=1.0))):
+        text = orc.paf2chain(bs.gen_paf(bs.paf_params(1500 if seed < 3 else 200, seed=seed, **kw)))
+        got = c2p(text)
+        assert got == orc.chain2paf(text)
+        assert w.run_bytes(w.paf2chain, w.PAFReader(got), ctx=ctx) == orc.paf2chain(got)   # and back (not the identity on '-': chain.rs:133-138)
+    text = orc.maf2chain(bs.gen_maf(bs.maf_params(800, seed=75, p_neg=0.3)))
+    assert c2p(text) == orc.chain2paf(text)
+    assert c2p(text.replace(b"\t", b" ")) == orc.chain2paf(text.replace(b"\t", b" "))
+    # ---- chain2maf
+    from bench_support.paf_legs import make_fasta
+    fa, fai = make_fasta(3, 2, 300000, seed=9)
+    F = w.Fasta(ctx, fa, fai)
+    c2m = lambda t: w.run_bytes(w.chain2maf, w.ChainReader(t), "t.fa", "q.fa", ctx=ctx, target=F, query=F)
+    want = lambda t: orc.chain2maf(t, fa, fai, fa, fai)
+    paf5 = bs.gen_paf(bs.paf_params(400, seed=93, n_genomes=3, n_chr=2, chr_size=300000, ops_median=20.0, ops_max=200, p_neg=0.0))
+    chain5 = orc.paf2chain(paf5)
+    assert c2m(chain5) == want(chain5)
+    assert orc.maf2chain(want(chain5)) == chain5                                  # README.md:225 round trip
+    # '-' records: paf2chain's header quirk (chain.rs:133-138) leaves query coordinates that do not match the blocks, and
+    # chain2maf then panics in insert_str on the first such record -- the same record here
+    chain6 = orc.paf2chain(bs.gen_paf(bs.paf_params(400, seed=94, n_genomes=3, n_chr=2, chr_size=300000, ops_median=20.0, ops_max=200,
+                                                    p_neg=0.5)))
+    with pytest.raises(orc.OracleError) as eo:
+        want(chain6)
+    with pytest.raises(w.WGAError) as eg:
+        c2m(chain6)
+    assert eo.value.code == eg.value.code == 8
+    small = (b"chain 9 g0#chr1 30000 + 2 12 g1#chr2 30000 - 3 12 5\n3 1 2\n4\n\nchain 9 g2#chr1 30000 - 0 5 g0#chr2 30000 + 10 15 6\n5\n"
+             b"chain 9 g0#chr1 300000 + 299990 300000 g0#chr1 300000 + 0 10 7\n4 0 0\n6\n")
+    assert c2m(small) == want(small)
+    assert c2m(b"") == want(b"")
+    fa_bad = fa + b">k\nACGTRACGT\n"
+    fai_bad = orc.make_fai(fa_bad)
+    FB = w.Fasta(ctx, fa_bad, fai_bad)
+    for t in (b"chain 9 g0#chr1 30000 + 2 4 g1#chr1 30000 + 3 5 0\n9 0 1\n",            # insert past the end of the target row
+              b"chain 9 zz 20 + 2 4 g0#chr1 30000 + 3 5 0\n2\n",                          # sequence not in the .fai
+              b"chain 9 g0#chr1 30000 + 2 4 k 9 - 0 5 0\n2\n",                            # reverse complement of a non-ACGTN base
+              small + b"chain 9 g0#chr1 30000 + 2 4 k 9 - 0 5 0\n2\n" + b"chain x\n1\n",    # later stage error BEFORE a later reader error
+              small + b"chain x\n1\n" + b"chain 9 g0#chr1 30000 + 2 4 k 9 - 0 5 0\n2\n",    # reader error before a later stage error
+              b"chain 9 g0#chr1 30000 + 2 4 k 9 - 0 5 0\nx\n"):                           # same record: the reader comes first
+        with pytest.raises(orc.OracleError) as eo:
+            orc.chain2maf(t, fa_bad, fai_bad, fa_bad, fai_bad)
+        with pytest.raises(w.WGAError) as eg:
+            w.run_bytes(w.chain2maf, w.ChainReader(t), "t.fa", "q.fa", ctx=ctx, target=FB, query=FB)
+        assert eg.value.code == eo.value.code, (t, eo.value, eg.value)
 
 
 # ---------------------------------------------------------------- fuzz: many tiny MAFs with awkward text

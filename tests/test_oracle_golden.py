@@ -7,6 +7,8 @@ Sources (all under /root/reference, copied as data fixtures into tests/golden/):
 The reference has no unit tests of its own; these are all the vectors that exist.
 """
 import os
+
+import numpy as np
 import random
 
 import pytest
@@ -365,6 +367,86 @@ def test_paf_chain_and_counts_vs_pyspec(ops, neg, qs, ts):
     rep, _ = orc.paf_validate(_paf_line("q", 5000, qs, qe + 1, strand, "t", 6000, ts, te + 2, cg), False)
     assert rep == (f"Total records: 1\nQuery invalid records: 1\nTarget invalid records: 1\nQuery invalid list:\nq:{qs}-{qe + 1}\n"
                    f"Target invalid list:\nt:{ts}-{te + 2}\n\n").encode()
+
+
+def test_chain_reader_chain2paf_chain2maf():
+    """src/parser/chain.rs:206-383 + converter.rs:268-416 + cigar.rs:554-626.  Pins: the README's round trip
+    (README.md:225 `paf2chain | chain2maf | maf2chain | chain2paf`) on the reference's own PAF, the nom grammar's quirks
+    one by one, and the independent Python spelling in tests/pyspec.py."""
+    ch = orc.paf2chain(TEST_PAF)
+    # chain2paf of the reference's PAF through paf2chain: '='/'X'/'M' merged, I = target_diff, D = query_diff
+    assert orc.chain2paf(ch) == (b"A\t300\t0\t200\t+\tB\t300\t0\t200\t170\t200\t255\tcg:Z:25M10I15M20D30M20I30M10D70M\n"
+                                 b"A\t300\t50\t250\t-\tB\t300\t200\t250\t40\t50\t255\tcg:Z:10M10D10M10I20M\n")
+    assert orc.chain2paf(ch).decode() == pyspec.chain2paf(ch.decode())
+    # a chain round trip is the identity on chains: paf2chain(chain2paf(x)) == x (ids restart at 0 either way)
+    assert orc.paf2chain(orc.chain2paf(ch)) == ch
+    # quirks of the grammar (each line of the docstring in oracle/wga_oracle.c)
+    two = (b"chain 255 t 100 + 0 10 q 90 - 5 15 0\n4\t1\t2\n3\n\n# a note without the letter\n\n"
+           b"chain 255 t 100 + 20 30 q 90 + 1 2 1\n7 2\n5")
+    assert orc.chain2paf(two) == (b"q\t90\t5\t15\t-\tt\t100\t0\t10\t7\t8\t255\tcg:Z:4M2I1D3M\n"          # size qdiff tdiff: I before D
+                                  b"q\t90\t1\t2\t+\tt\t100\t20\t30\t7\t9\t255\tcg:Z:7M2D\n")          # last line without '\n': dropped
+    assert orc.chain2paf(two).decode() == pyspec.chain2paf(two.decode())
+    assert orc.chain2paf(b"") == b""
+    assert orc.chain2paf(b"chain255 t 9 + 0 1 q 9 + 0 1 7 extra fields\r\n1 0 0 9\r\n") == b"q\t9\t0\t1\t+\tt\t9\t0\t1\t1\t1\t255\tcg:Z:1M\n"
+    H = b"chain 1 t 9 + 0 1 q 9 + 0 1 0\n"
+    for bad, code in ((b"xchain 1 t 9 + 0 1 q 9 + 0 1 0\n1\n", 11), (b"xchain\n", 8),      # tag("chain"); short rest -> input[..10] panics
+                      (H + b"\n", 8), (H + b"\n" + b"#" * 12, 11),                            # fold_many1 needs one data line
+                      (H[:-1], 8),                                                             # header that ends the file
+                      (b"chain a t 9 + 0 1 q 9 + 0 1 0\n1\n", 13), (b"chain 1 t x + 0 1 q 9 + 0 1 0\n1\n", 1),
+                      (b"chain 1 t 9 * 0 1 q 9 + 0 1 0\n1\n", 2), (b"chain 1 t 9 + 0 1 q 9 + 0 1\n1\n", 12),
+                      (H + b"1\n2 x\n", 1), (H + b"1\n \n", 12),                            # data line errors
+                      (H + b"1\n\n# a comment\n" + H + b"1\n", 11),                         # 'c' in the skipped part: tag fails there
+                      (H + b"1\n12 c\n", 8)):
+        with pytest.raises(orc.OracleError) as e:
+            orc.chain2paf(bad)
+        assert e.value.code == code, (bad, e.value)
+        with pytest.raises(ValueError):
+            pyspec.chain2paf(bad.decode())
+    assert orc.chain2paf(H + b"1\n2 3\nh\n9 9 9\n" + H + b"5\n") == (b"q\t9\t0\t1\t+\tt\t9\t0\t1\t3\t6\t255\tcg:Z:1M2M3D\n"
+                                                                  b"q\t9\t0\t1\t+\tt\t9\t0\t1\t5\t5\t255\tcg:Z:5M\n")   # lines after 'h' are skipped
+    # chain2maf: rows through the FASTA, '-' strand reverse-complemented, gaps by the data lines
+    fa = b">t\nACGTACGTAC\nGTACGTACGT\n>q\nTTGCATGCAT\nGCATGCAAGG\n"
+    fai = orc.make_fai(fa)
+    seqs = {"t": "ACGTACGTACGTACGTACGT", "q": "TTGCATGCATGCATGCAAGG"}
+    c2 = b"chain 9 t 20 + 2 12 q 20 - 3 12 5\n3 1 2\n4\n\nchain 9 t 20 - 0 5 q 20 + 10 15 6\n5\n"
+    got = orc.chain2maf(c2, fa, fai, fa, fai)
+    assert got.decode() == pyspec.chain2maf(c2.decode(), seqs)
+    assert got == (b"#maf version=1.6 convert_from=chain t_seq_path=t.fa q_seq_path=q.fa\n"
+                   b"a score=255\ns\tt\t2\t10\t+\t20\tGTA--CGTACGT\ns\tq\t8\t9\t-\t20\tGCATG-CATG\n\n"
+                   b"a score=255\ns\tt\t0\t5\t-\t20\tACGTA\ns\tq\t10\t5\t+\t20\tGCATG\n\n")
+    for bad, code in ((b"chain 9 t 20 + 2 4 q 20 + 3 5 0\n9 0 1\n", 8),            # insert_str past the end of the target row
+                      (b"chain 9 zz 20 + 2 4 q 20 + 3 5 0\n2\n", 11),              # sequence not in the .fai
+                      (b"chain 9 t 20 + 2 4 k 20 - 0 5 0\n2\n", 10)):              # revcomp of a non-ACGTN base
+        with pytest.raises(orc.OracleError) as e:
+            orc.chain2maf(bad, fa + b">k\nACGTR\n", orc.make_fai(fa + b">k\nACGTR\n"), fa + b">k\nACGTR\n", orc.make_fai(fa + b">k\nACGTR\n"))
+        assert e.value.code == code, (bad, e.value)
+    # README.md:225 round trip on the reference's PAF with a FASTA that fits its coordinates: chain -> maf -> chain -> paf
+    rng = np.random.default_rng(5)
+    fa2 = b"".join(b">" + n + b"\n" + bytes(rng.choice(list(b"ACGT"), 300).astype(np.uint8)) + b"\n" for n in (b"A", b"B"))
+    fai2 = orc.make_fai(fa2)
+    maf = orc.chain2maf(ch, fa2, fai2, fa2, fai2)
+    assert orc.maf2chain(maf) == ch                      # gapped rows carry exactly the chain's blocks
+    assert orc.chain2paf(orc.maf2chain(maf)) == orc.chain2paf(ch)
+
+
+@settings(max_examples=150, deadline=None, derandomize=True)
+@given(st.lists(st.tuples(st.booleans(), st.lists(st.tuples(st.integers(0, 30), st.integers(0, 9), st.integers(0, 9)), min_size=1, max_size=6),
+                          st.sampled_from(["\n", "\n\n", "\n# zzz\n", "\r\n\n"])), min_size=1, max_size=5), st.booleans())
+def test_chain2paf_vs_pyspec(recs, final_newline):
+    text = ""
+    for i, (neg, lines, sep) in enumerate(recs):
+        text += f"chain 4{i}.5 t{i} 1000 + 10 {10 + i} q 900 {'-' if neg else '+'} 5 50 {i}\n"
+        text += "\n".join("\t".join(str(x) for x in (l if j + 1 < len(lines) else l[:1 + (l[1] + l[2] > 0) * 2])) for j, l in enumerate(lines))
+        text += sep
+    if not final_newline:
+        text = text.rstrip("\n")
+    try:
+        want = pyspec.chain2paf(text)
+    except ValueError:
+        with pytest.raises(orc.OracleError):
+            orc.chain2paf(text.encode())
+        return
+    assert orc.chain2paf(text.encode()).decode() == want
 
 
 @settings(max_examples=200, deadline=None, derandomize=True)

@@ -13,6 +13,7 @@ WGA_MEM_HOST, WGA_MEM_DEVICE = 0, 1
 WGA_F_FIRST_SLAB = 1
 WGA_F_OUT_HOST = 2
 WGA_F_REUSE_INDEX = 4
+WGA_F_SHARE_WALK = 8
 
 
 class Span(ctypes.Structure):
@@ -94,6 +95,10 @@ ABI = {
                                     ctypes.c_uint64, _P(Span), _P(ctypes.c_uint64)]),
     "wga_paf2chain": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64,
                                     _P(Span), _P(ctypes.c_uint64)]),
+    "wga_chain2paf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, _P(Span)]),
+    "wga_chain2maf_header": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, _P(Span)]),
+    "wga_chain2maf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
+                                    ctypes.c_void_p, ctypes.c_void_p, _P(Span)]),
     "wga_paf_cov": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, _P(Span)]),
     "wga_last_record_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, _P(ctypes.c_uint64)]),
 }

@@ -526,6 +526,38 @@ def paf2chain(pafreader: PAFReader, writer, ctx=None):
         writer.write(ctypes.string_at(sp.data, sp.len))
 
 
+class ChainReader:
+    """src/parser/chain.rs:17-44: the whole file is read into memory and parsed record by record"""
+
+    def __init__(self, reader):
+        self.data = _read_all(reader)
+
+
+def chain2paf(chainreader: ChainReader, writer, ctx=None):
+    """src/converter.rs:391-416: one PAF row (12 columns + cg:Z:) per chain, file order"""
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(chainreader.data)
+    sp = Span()
+    ctx._check(ctx.L.wga_chain2paf(ctx.h, ctypes.c_void_p(base), len(chainreader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, ctypes.byref(sp)))
+    if sp.len:
+        writer.write(ctypes.string_at(sp.data, sp.len))
+
+
+def chain2maf(chainreader: ChainReader, writer, t_fa_path, q_fa_path, ctx=None, target=None, query=None):
+    """src/converter.rs:268-357.  target/query: preloaded Fasta objects (else loaded from the two paths)."""
+    ctx = ctx or default_context()
+    target = target or Fasta.from_path(ctx, t_fa_path)
+    query = query or Fasta.from_path(ctx, q_fa_path)
+    sp = Span()
+    ctx._check(ctx.L.wga_chain2maf_header(ctx.h, _opt(t_fa_path), _opt(q_fa_path), ctypes.byref(sp)))
+    writer.write(ctypes.string_at(sp.data, sp.len))
+    keep, base = _host_ptr(chainreader.data)
+    ctx._check(ctx.L.wga_chain2maf(ctx.h, ctypes.c_void_p(base), len(chainreader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, target.h,
+                                   query.h, ctypes.byref(sp)))
+    if sp.len:
+        writer.write(ctypes.string_at(sp.data, sp.len))
+
+
 def pafcov(reader: PAFReader, writer, ctx=None):
     """src/tools/pafcov.rs:13-60: per-base BED coverage of every target"""
     ctx = ctx or default_context()

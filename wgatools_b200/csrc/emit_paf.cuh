@@ -36,6 +36,41 @@ __global__ void k_run_len(uint64_t n_runs, const uint64_t *__restrict__ run_pos,
     if (run_dl) run_dl[j] = (uint32_t)ndigits_u64(len) + 1u;
 }
 
+// ---- EXT run list out of the caller-classified one (WGA_F_SHARE_WALK, only when the slab has both-gap columns):
+// cigar_cat_ext (cigar.rs:298-308) calls a both-gap column '=', cigar_cat_ext_caller (cigar.rs:314-328) calls it 'W';
+// I / D / X columns are the same in both.  So the EXT list is the caller list with W relabelled '=' and every run
+// dropped whose relabelled class equals that of the run before it in the same record.
+__global__ void k_ext_flags(uint64_t n_runs, const uint32_t *__restrict__ run_rec, const uint8_t *__restrict__ run_cls,
+                            uint32_t *__restrict__ flag) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n_runs) return;
+    if (j == n_runs) { flag[j] = 0; return; }
+    uint32_t keep = 1;
+    if (j > 0 && run_rec[j - 1] == run_rec[j]) {
+        const uint8_t a = run_cls[j - 1] == CLS_W ? (uint8_t)CLS_EQ : run_cls[j - 1];
+        const uint8_t b = run_cls[j] == CLS_W ? (uint8_t)CLS_EQ : run_cls[j];
+        keep = a != b;
+    }
+    flag[j] = keep;
+}
+__global__ void k_ext_scatter(uint64_t n_runs, const uint32_t *__restrict__ flag, const uint64_t *__restrict__ idx,
+                              const uint64_t *__restrict__ run_pos, const uint32_t *__restrict__ run_rec,
+                              const uint8_t *__restrict__ run_cls, uint64_t *__restrict__ xpos, uint32_t *__restrict__ xrec,
+                              uint8_t *__restrict__ xcls) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_runs || !flag[j]) return;
+    const uint64_t o = idx[j];
+    xpos[o] = run_pos[j];
+    xrec[o] = run_rec[j];
+    xcls[o] = run_cls[j] == CLS_W ? (uint8_t)CLS_EQ : run_cls[j];
+}
+// the first run of a record always survives: its new index is the scan value at its old index
+__global__ void k_ext_rec_first(uint64_t n_rec, const uint64_t *__restrict__ rec_run_first, const uint64_t *__restrict__ idx,
+                                uint64_t *__restrict__ xfirst) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= n_rec) xfirst[r] = idx[rec_run_first[r]];
+}
+
 __device__ __forceinline__ uint32_t csv_name_len(const uint8_t *p, uint32_t n) {
     uint32_t q = 0;
     for (uint32_t i = 0; i < n; ++i) q += p[i] == '"';

@@ -222,6 +222,7 @@ struct P2mView {
     const uint64_t *blk_off;
     uint32_t *fix_t, *fix_q;                // bytes before each row's sequence
     char *out;
+    const uint8_t *t_neg = nullptr;         // chain2maf prints the chain header's own target strand; null = '+'
 };
 
 // insert_str past the end of the row = the reference's panic (cigar.rs:507,513)
@@ -274,7 +275,8 @@ __global__ void k_p2m_blocks(P2mView V) {
         o = put_u64(o, V.X.mapq[r]); *o++ = '\n';
         *o++ = 's'; *o++ = '\t';
         for (uint32_t i = 0; i < tnl; ++i) *o++ = (char)V.text[V.R.t_name_off[r] + i];
-        *o++ = '\t'; o = put_u64(o, t_st); *o++ = '\t'; o = put_u64(o, t_al); *o++ = '\t'; *o++ = '+'; *o++ = '\t';
+        *o++ = '\t'; o = put_u64(o, t_st); *o++ = '\t'; o = put_u64(o, t_al); *o++ = '\t';
+        *o++ = (V.t_neg && V.t_neg[r]) ? '-' : '+'; *o++ = '\t';
         o = put_u64(o, V.R.t_size[r]); *o++ = '\t';
         o += trow; *o++ = '\n';
         *o++ = 's'; *o++ = '\t';

@@ -374,7 +374,7 @@ struct Recs {
 // (maf.rs:263-285 set_query_idx_byname, :424-540 AlignRecord; caller.rs:62-108)
 __global__ void k_build_records(uint64_t n_rec, const uint8_t *__restrict__ text, SLines sl, Recs rc,
                                 const uint8_t *__restrict__ qname, uint32_t qname_len, int has_qname,
-                                int mode, unsigned long long *err_key) {
+                                int mode, unsigned long long *err_key, unsigned long long *ragged) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
     uint64_t first = rc.first[r], last = rc.last[r], nl = last - first + 1;
@@ -404,9 +404,20 @@ __global__ void k_build_records(uint64_t n_rec, const uint8_t *__restrict__ text
     uint64_t tl = first, ql = first + (skip ? 0 : qi);
     uint64_t nt = sl.seq_len[tl], nq = sl.seq_len[ql];
     uint64_t n = nt < nq ? nt : nq;  // zip() stops at the shorter sequence (cigar.rs:359-361)
-    if (mode == 1 && !skip && nq < nt) {  // query_seq()[start..end] slicing panics (caller.rs:173-175)
-        report(err_key, last, WGA_E_REF_PANIC);
-        skip = true;
+    if (mode == 1 && !skip) {
+        // query_seq()[start..end] slicing panics (caller.rs:173-175), and create_chunk_record slices EVERY s-line of the
+        // block with the chunk bounds (caller.rs:233-234): any row shorter than the target row panics
+        bool bad = nq < nt;
+        for (uint64_t i = 0; i < nl && !bad; ++i) bad = sl.seq_len[first + i] < nt;
+        if (bad) {
+            report(err_key, last, WGA_E_REF_PANIC);
+            skip = true;
+        }
+    }
+    if (mode == 0 && !skip) {  // would `call` see another record here?  (rows shorter than the target, single s-line blocks)
+        bool bad = nl == 1;
+        for (uint64_t i = 0; i < nl && !bad; ++i) bad = sl.seq_len[first + i] < nt;
+        if (bad) *ragged = 1ull;
     }
     if (mode == 1) n = nt;
     rc.tl[r] = tl;

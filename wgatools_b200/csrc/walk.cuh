@@ -80,7 +80,7 @@ struct WarpEmit {  // run-head emission state of the warp: the item whose slot r
 // saves 256 B of shared memory per warp for the TMA-staged variant)
 template <int MODE, bool RECQ = true>
 __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64], uint32_t cnt, uint32_t lane, WarpEmit &E) {
-    constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
+    constexpr bool CALLER = MODE == MODE_RUNS_CALLER || MODE == MODE_RUNS_ALL;
     constexpr bool RUNS = MODE != MODE_STAT;
     constexpr bool COUNTS = MODE != MODE_RUNS_CALLER;
     uint32_t H[4] = {0, 0, 0, 0}, hc = 0, item = 0xFFFFFFFFu, colrel = 0;
@@ -96,7 +96,7 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
         const int f0 = meta & 31, t0 = (meta >> 5) & 31, t1 = (meta >> 10) & 31;
         const int f1 = ((meta >> 15) & 1u) ? f0 : 0;  // bytes before the record start are not columns
         colrel = meta >> 16;
-        uint32_t cX = 0, cI = 0, cD = 0, eI = 0, eD = 0;
+        uint32_t cX = 0, cI = 0, cD = 0, eI = 0, eD = 0, hw = 0;
         Flags4 pf = classify_prev<CALLER>(pv & 0xFFu, (pv >> 8) & 0xFFu, (pv >> 16) & 1u);
         uint32_t p_eq = pf.eq, p_x = pf.x, p_i = pf.i, p_d = pf.d, p_w = pf.w;
 #pragma unroll
@@ -117,9 +117,11 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
                 if (CALLER) same |= F[k].w & prev_flags(p_w, F[k].w);
                 H[k] = cm & ~same;
                 hc += __popc(H[k]);
+                if (MODE == MODE_RUNS_ALL) hw |= H[k] & F[k].w;
             }
             p_eq = F[k].eq; p_x = F[k].x; p_i = F[k].i; p_d = F[k].d; p_w = F[k].w;
         }
+        if (MODE == MODE_RUNS_ALL && hw) atomicAdd(A.n_w, 1u);  // only "are there any" matters
         if (COUNTS && (cX | cI | cD)) {
             const uint32_t rec = RECQ ? Q[11][lane] : __ldg(&A.items[item].rec);
             unsigned long long *c = A.rec_cnt + (uint64_t)rec * 5;
@@ -229,11 +231,18 @@ __device__ __forceinline__ void realign(const uint4 &q0, const uint4 &q1, uint32
     o2 = __funnelshift_r(w2, w3, sh); o3 = __funnelshift_r(w3, w4, sh);
 }
 
+// The column before a step's first chunk, kept lazily: its "is not plain '='" bit costs nothing (it falls out of the
+// ballot below); its bytes are only needed when lane 0 of the next step turns out slow, so every lane just remembers its
+// own last words and the slow branch fetches lane 31's.
+struct PrevCol {
+    uint32_t bit, tw3, qw3;
+};
+
 // one step (32 chunks) of the current item: 128-bit compare, push the slow chunks, run a batch when 32 are queued
 template <int MODE, bool RECQ = true>
 __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane,
-                                          const Geom &g, uint32_t j0, const Vec3 &v, uint32_t &carry) {
-    constexpr bool CALLER = MODE == MODE_RUNS_CALLER;
+                                          const Geom &g, uint32_t j0, const Vec3 &v, PrevCol &P) {
+    constexpr bool CALLER = MODE == MODE_RUNS_CALLER || MODE == MODE_RUNS_ALL;
     const uint32_t j = j0 + lane;
     const bool act = j < g.nch;
     const uint4 tv = v.t;
@@ -245,24 +254,30 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
         case 2: realign<2>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
         default: realign<3>(v.q0, v.q1, sh, qw0, qw1, qw2, qw3); break;
     }
-    // last column of this chunk -> neighbour lane (previous column of the next chunk)
-    const uint32_t lastb = act ? ((tv.w >> 24) | ((qw3 >> 24) << 8)) : 0u;
-    uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, lastb, 1);
-    if (lane == 0) pb = carry;
-    carry = __shfl_sync(0xFFFFFFFFu, lastb, 31);
-    uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | (tv.w ^ qw3);
-    bool prev_ne = (pb & 0xFFu) != (pb >> 8);
+    const uint32_t x3 = tv.w ^ qw3;
+    uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | x3;
+    bool ne_last = x3 > 0x00FFFFFFu;  // the chunk's last column differs
     if (CALLER) {
-        x |= has_zero_byte(tv.x ^ kGap4) | has_zero_byte(tv.y ^ kGap4) | has_zero_byte(tv.z ^ kGap4) |
-             has_zero_byte(tv.w ^ kGap4);
-        prev_ne |= (pb & 0xFFu) == '-';
+        // a both-gap column is '=' for the byte compare but a run of its own for the caller (cigar.rs:314-328).  '-' is
+        // 0x2D; every letter has bit 6 set, so "some target byte has bit 6 clear" is a cheap superset of "holds a gap";
+        // the slow path classifies exactly.
+        const uint32_t g6 = tv.x & tv.y & tv.z & tv.w;
+        x |= ~g6 & 0x40404040u;
+        ne_last |= (tv.w & 0x40000000u) == 0u;
     }
+    ne_last &= act;
+    const uint32_t nb = __ballot_sync(0xFFFFFFFFu, ne_last);
+    const bool prev_ne = (((nb << 1) | P.bit) >> lane) & 1u;
     // interior chunks: fully inside the item -> 16j >= a and 16j+16 <= n+a
     const uint32_t jf = (g.a + 15u) >> 4, jl = (g.n + g.a) >> 4;
     const bool edge = j == 0 || j < jf || j >= jl;
     const bool slow = act && (edge || x != 0u || prev_ne);
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
     if (mask) {
+        // bytes of the column before each chunk: the neighbour lane's last column, lane 31 of the previous step for lane 0
+        uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, (tv.w >> 24) | ((qw3 >> 24) << 8), 1);
+        const uint32_t cb = __shfl_sync(0xFFFFFFFFu, (P.tw3 >> 24) | ((P.qw3 >> 24) << 8), 31);
+        if (lane == 0) pb = cb;
         if (slow) {
             const uint32_t slot = qn + __popc(mask & ((1u << lane) - 1u));
             Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
@@ -299,6 +314,9 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
             __syncwarp();
         }
     }
+    P.bit = nb >> 31;
+    P.tw3 = tv.w;
+    P.qw3 = qw3;
 }
 
 template <int MODE>
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) k_walk(WalkArgs 
                 const uint4 *ep = reinterpret_cast<const uint4 *>(A.items + item3);
                 e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2);
             }
-            uint32_t carry = 0;  // (t,q) bytes of the column before this step's first chunk: t | q<<8
+            PrevCol carry = {0u, 0u, 0u};  // the column before this step's first chunk
             for (uint32_t j0 = 0; j0 < cur.nch; j0 += 32) {
                 Vec3 nv;
                 if (j0 + 32 < cur.nch) nv = load_vec(cur, j0 + 32 + lane);

@@ -7,6 +7,7 @@ void launch_walk(int mode, unsigned grid, cudaStream_t stream, const WalkArgs &A
     switch (mode) {
         case MODE_STAT: k_walk<MODE_STAT><<<grid, kWalkThreads, 0, stream>>>(A); break;
         case MODE_RUNS_EXT: k_walk<MODE_RUNS_EXT><<<grid, kWalkThreads, 0, stream>>>(A); break;
+        case MODE_RUNS_ALL: k_walk<MODE_RUNS_ALL><<<grid, kWalkThreads, 0, stream>>>(A); break;
         default: k_walk<MODE_RUNS_CALLER><<<grid, kWalkThreads, 0, stream>>>(A); break;
     }
 }

@@ -26,11 +26,19 @@ namespace wga {
 #ifndef WGA_TMA_THREADS
 #define WGA_TMA_THREADS 320
 #endif
+#ifndef WGA_TMA_PREFETCH
+#define WGA_TMA_PREFETCH 0
+#endif
 constexpr int kTmaThreads = WGA_TMA_THREADS, kTmaWarps = kTmaThreads / 32, kTmaCtasPerSm = WGA_TMA_CTAS;
 constexpr int kTmaStages = WGA_TMA_STAGES;
 constexpr uint32_t kTmaWin = WGA_TMA_WIN;                          // chunks per window (32 per step)
 constexpr uint32_t kTmaStageBytes = kTmaWin * 16 + kTmaWin * 16 + 16;  // T | Q (+ one vector for the realign)
 constexpr int kTmaGeoms = 4;                                      // item geometries in flight per warp
+// Experiment knob (off): request the windows that come kTmaPrefetch ring turns later into L2 already now
+// (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2).  Measured on the bench workload (profiles/r02_walk_experiments.md): 2 and 4
+// windows ahead make the kernel SLOWER (1.65 / 1.64 ms against 1.52 ms), i.e. the walk is not waiting for DRAM latency
+// that more bytes in flight could hide.
+constexpr uint32_t kTmaPrefetch = WGA_TMA_PREFETCH;               // windows ahead (0 = off)
 
 struct TmaWin { uint32_t gslot, j0, cnt, pad; };
 struct __align__(16) TmaWarp {
@@ -68,6 +76,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint4 lds16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
@@ -135,11 +146,24 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
         p_nch = g.nch; p_s = g.s; p_qlast = g.q_last; p_tb = g.tbase; p_qb = g.qbase;
         p_j = 0;
     };
+    // the first kTmaPrefetch windows of the item AFTER the one being issued: its descriptor thirds sit in lanes 0..2
+    auto prefetch_next_item = [&]() {
+        if (kTmaPrefetch == 0) return;
+        const uint32_t n = __shfl_sync(0xFFFFFFFFu, ed.z, 1);
+        if (lane == 0) {
+            const uint64_t t_off = ((uint64_t)ed.y << 32) | ed.x, q_off = ((uint64_t)ed.w << 32) | ed.z;
+            const uint32_t cap = kTmaPrefetch * kTmaWin * 16u + 16u;
+            const uint32_t want = n + 31u < cap ? n + 31u : cap;
+            const uint32_t bytes = want & ~15u;
+            l2_prefetch(reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(A.text + t_off) & ~(uintptr_t)15), bytes);
+            l2_prefetch(reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(A.text + q_off) & ~(uintptr_t)15), bytes);
+        }
+    };
     fetch_desc(s_it);
     open_item(s_it, 0);
     e_has = advance();
     e_item = s_it;
-    if (e_has) fetch_desc(e_item);
+    if (e_has) { fetch_desc(e_item); prefetch_next_item(); }
     uint32_t n_out = 0;  // windows issued and not yet consumed
     auto produce = [&](uint32_t stage) {
         if (!p_has) return;
@@ -154,6 +178,14 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
             mbar_expect_tx(&W.bar[stage], (cnt + qcnt) * 16u);
             bulk_g2s(W.stage[stage], p_tb + 16ull * p_j, cnt * 16u, &W.bar[stage]);
             bulk_g2s(W.stage[stage] + kTmaWin * 16, p_qb + 16ull * p_j, qcnt * 16u, &W.bar[stage]);
+            if (kTmaPrefetch) {  // the window kTmaPrefetch turns ahead, while it still lies inside this item
+                const uint32_t pj = p_j + kTmaPrefetch * kTmaWin;
+                if (pj < p_nch) {
+                    const uint32_t c2 = (p_nch - pj < kTmaWin ? p_nch - pj : kTmaWin) * 16u;
+                    l2_prefetch(p_tb + 16ull * pj, c2);
+                    l2_prefetch(p_qb + 16ull * pj, c2);
+                }
+            }
         }
         ++n_out;
         p_j += cnt;
@@ -164,7 +196,7 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
                 open_item(e_item, p_gs);
                 e_has = advance();
                 e_item = s_it;
-                if (e_has) fetch_desc(e_item);
+                if (e_has) { fetch_desc(e_item); prefetch_next_item(); }
             }
         }
     };
@@ -174,7 +206,8 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
     // ---- consumer
     Geom cur;
     cur.nch = 0;
-    uint32_t cur_gs = 0xFFFFFFFFu, carry = 0, sc = 0, parity = 0;  // parity: bit s = phase of stage s to wait for
+    uint32_t cur_gs = 0xFFFFFFFFu, sc = 0, parity = 0;  // parity: bit s = phase of stage s to wait for
+    PrevCol carry = {0u, 0u, 0u};
     while (n_out) {
         mbar_wait(&W.bar[sc], (parity >> sc) & 1u);
         parity ^= 1u << sc;
@@ -182,18 +215,17 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
         if (gs != cur_gs) {
             cur = W.geom[gs];
             cur_gs = gs;
-            carry = 0;
+            carry.bit = 0; carry.tw3 = 0; carry.qw3 = 0;
         }
         const uint8_t *Ts = W.stage[sc], *Qs = W.stage[sc] + kTmaWin * 16;
         for (uint32_t st = 0; st < wcnt; st += 32) {
-            const uint32_t rel = st + lane, j = wj0 + rel;
+            // lanes past the window's end read its last chunk again (they are inactive in walk_step: j >= nch); the
+            // vector after the last query vector lies inside the stage buffer and only feeds columns past the item's end
+            const uint32_t rel = min(st + lane, wcnt - 1u);
             Vec3 v;
-            v.t = make_uint4(0, 0, 0, 0); v.q0 = v.t; v.q1 = v.t;
-            if (rel < wcnt) {
-                v.t = lds16(Ts + 16u * rel);
-                v.q0 = lds16(Qs + 16u * rel);
-                if (cur.s != 0 && j + 1 <= cur.q_last) v.q1 = lds16(Qs + 16u * rel + 16u);
-            }
+            v.t = lds16(Ts + 16u * rel);
+            v.q0 = lds16(Qs + 16u * rel);
+            v.q1 = lds16(Qs + 16u * rel + 16u);
             walk_step<MODE, false>(A, Q, qn, E, lane, cur, wj0 + st, v, carry);
         }
         --n_out;

@@ -27,6 +27,7 @@ cudaError_t launch_walk_tma(int mode, unsigned grid, cudaStream_t stream, const 
     switch (mode) {
         case MODE_STAT: return launch_one<MODE_STAT>(grid, stream, A);
         case MODE_RUNS_EXT: return launch_one<MODE_RUNS_EXT>(grid, stream, A);
+        case MODE_RUNS_ALL: return launch_one<MODE_RUNS_ALL>(grid, stream, A);
         default: return launch_one<MODE_RUNS_CALLER>(grid, stream, A);
     }
 }

@@ -8,7 +8,8 @@
 
 namespace wga {
 
-enum { MODE_STAT = 0, MODE_RUNS_EXT = 1, MODE_RUNS_CALLER = 2 };
+// MODE_RUNS_ALL: caller classification (W runs kept apart) + the counters: one walk that serves maf2paf, stat AND call
+enum { MODE_STAT = 0, MODE_RUNS_EXT = 1, MODE_RUNS_CALLER = 2, MODE_RUNS_ALL = 3 };
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
 #ifndef WGA_WALK_CTAS
@@ -35,6 +36,7 @@ struct WalkArgs {
     uint32_t *slots;              // run-head slots
     uint32_t cap_shift;           // slot capacity of an item = (n >> cap_shift) + kSlotPad
     uint32_t *overflow;
+    uint32_t *n_w;                // MODE_RUNS_ALL: number of W (both-gap) run heads emitted
     unsigned int *sched;          // dynamic work counter (zero-initialised)
     uint32_t grab;                // items handed out per request (k_walk_tma; k_walk uses 8)
 };

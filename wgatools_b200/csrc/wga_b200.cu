@@ -23,6 +23,7 @@
 #include "pafpseudo.cuh"
 #include "validate.cuh"
 #include "pafcov.cuh"
+#include "chain_in.cuh"
 #endif
 
 using namespace wga;
@@ -112,12 +113,40 @@ struct Prep {
     ItemDesc *items = nullptr;
     unsigned long long *err_key = nullptr;
     uint64_t total_cols = 0;
+    uint64_t ragged = 0;  // mode 0: some block would be seen differently by `call` (k_build_records)
 };
 
 // The delimiter index, the line table and the parsed s-line fields of the last MAF slab stay valid in the ctx pool
 // until another text is staged.  A command called with WGA_F_REUSE_INDEX on the SAME device text skips straight to
 // record building (which depends on the command: query_name, 1-s-line semantics).
+struct Runs {
+    uint64_t n_runs = 0, n_w = 0;  // n_w != 0: MODE_RUNS_ALL saw both-gap ('W') runs
+    uint64_t *run_base = nullptr, *run_pos = nullptr;
+    uint32_t *run_rec = nullptr;
+    uint8_t *run_cls = nullptr;
+};
+
+// What the last MAF command's record building and dense walk left in the ctx pool (WGA_F_SHARE_WALK): valid only together
+// with the TokCache it hangs off.  Buffers involved: B_REC_*, B_ITEM_REC (records / items), B_CNT11 (counters),
+// B_RUN_POS / B_RUN_REC / B_RUN_CLS / B_RUN_LEN / B_REC_RUNFIRST (run list); every command that rewrites one of them
+// drops the corresponding flag first.
+struct WalkCache {
+    bool recs = false;          // P, n_rec, n_items describe the slab's records (built in maf2paf/stat mode, no error)
+    bool call_same = false;     // ... and `call` would build exactly the same records (no ragged / single-row block)
+    bool has_q = false;
+    std::string qname;
+    Prep P;
+    uint64_t n_rec = 0, n_items = 0;
+    bool counts = false;        // B_CNT11 = the 11 counters of every record
+    bool runs = false;          // caller-classified run list + run_len + rec_run_first
+    Runs RU;
+    uint64_t *rec_run_first = nullptr, *run_len = nullptr;
+    void drop() { recs = call_same = counts = runs = false; }
+    bool same_q(const char *q) const { return q ? (has_q && qname == q) : !has_q; }
+};
+
 struct TokCache {
+    WalkCache wc;
     bool valid = false;
     const void *src = nullptr;      // the caller's pointer
     const uint8_t *d_text = nullptr;  // where the kernels read it (== src, or the realigned copy)
@@ -145,6 +174,7 @@ int stage_text(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t f
         return WGA_OK;
     }
     tc.valid = false;
+    tc.wc.drop();
     if (mem == WGA_MEM_DEVICE) {
         if (reinterpret_cast<uintptr_t>(text) & 15u) {  // e.g. a slab of a resident text: realign with one D2D copy
             uint8_t *d = (uint8_t *)ctx->ensure(B_TEXT, len + 64);
@@ -274,12 +304,14 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
     const uint64_t len = ctx->text_len;
     const uint8_t *text = ctx->d_text;
     ctx->n_rec = ctx->n_items = ctx->n_runs = 0;
-    P->err_key = ctx->buf<unsigned long long>(B_ERR, 1);
+    P->err_key = ctx->buf<unsigned long long>(B_ERR, 2);  // [1]: "call would build other records" (k_build_records)
     if (!P->err_key) return ctx->err_code;
     LAUNCH(ctx, k_init_u64, 1, 1, P->err_key, 1, kNoErr);
-    if (len == 0) return WGA_OK;
-
+    WGA_CK(cudaMemsetAsync(P->err_key + 1, 0, 8, ctx->stream));
     TokCache &tc = tok_of(ctx);
+    tc.wc.drop();  // the record / item / run buffers are about to be rewritten
+    P->ragged = 0;
+    if (len == 0) return WGA_OK;
     LineView &lv = P->lv;
     SLines &sl = P->sl;
     Recs &rc = P->rc;
@@ -354,16 +386,18 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
         if (!d_q) return ctx->err_code;
         WGA_CK(cudaMemcpyAsync(d_q, qname, qlen, cudaMemcpyHostToDevice, ctx->stream));
     }
-    LAUNCH(ctx, k_build_records, grid_for(n_rec, 256), 256, n_rec, text, sl, rc, d_q, qlen, qname ? 1 : 0, mode, P->err_key);
+    LAUNCH(ctx, k_build_records, grid_for(n_rec, 256), 256, n_rec, text, sl, rc, d_q, qlen, qname ? 1 : 0, mode, P->err_key,
+           P->err_key + 1);
     WGA_CK(cudaMemsetAsync(rc.n_items + n_rec, 0, 4, ctx->stream));
     WGA_CK(cudaMemsetAsync(rc.ncols + n_rec, 0, 8, ctx->stream));
     WGA_TRY(exclusive_sum(ctx, rc.n_items, P->item_base, n_rec + 1));
     WGA_TRY(exclusive_sum(ctx, rc.ncols, colsum, n_rec + 1));
-    uint64_t sc[3];
-    WGA_TRY(read_scalars(ctx, {P->item_base + n_rec, P->err_key, colsum + n_rec}, sc));
+    uint64_t sc[4];
+    WGA_TRY(read_scalars(ctx, {P->item_base + n_rec, P->err_key, colsum + n_rec, P->err_key + 1}, sc));
     if (sc[1] != kNoErr) return resolve_error(ctx, *P, sc[1], qname);
     ctx->n_items = sc[0];
     P->total_cols = sc[2];
+    P->ragged = sc[3];
     return WGA_OK;
 }
 
@@ -378,13 +412,6 @@ void walk_begin(wga_ctx *ctx) {
     ctx->walk_bytes = 0;
     ctx->walk_launches = 0;
 }
-
-struct Runs {
-    uint64_t n_runs = 0;
-    uint64_t *run_base = nullptr, *run_pos = nullptr;
-    uint32_t *run_rec = nullptr;
-    uint8_t *run_cls = nullptr;
-};
 
 // the dense pass: one k_walk launch (timed with CUDA events on the ctx stream); for the RUNS modes the item slot
 // regions are compacted into dense run arrays afterwards.  rec_cnt must be zeroed by the caller.
@@ -415,10 +442,10 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
                               P.rc.ncols, (const uint64_t *)slot_base, shift, P.items);
         ctx->n_own++;
         WGA_CK(cudaMemsetAsync(nheads, 0, (n_items + 1) * 4, ctx->stream));
-        WGA_CK(cudaMemsetAsync(ovf, 0, 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(ovf, 0, 16, ctx->stream));
         WalkArgs A;
         A.text = ctx->d_text; A.items = P.items; A.n_items = n_items; A.rec_cnt = rec_cnt;
-        A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf; A.sched = ovf + 1;
+        A.item_nheads = nheads; A.slots = slots; A.cap_shift = shift; A.overflow = ovf; A.sched = ovf + 1; A.n_w = ovf + 2;
         WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
         // hand out fewer items per request when there are few per warp (long items: the last request is the tail)
         {
@@ -437,8 +464,9 @@ int run_walk(wga_ctx *ctx, Prep &P, unsigned long long *rec_cnt, Runs *R) {
         R->run_base = ctx->buf<uint64_t>(B_GEN_H, n_items + 1);
         if (!R->run_base) return ctx->err_code;
         WGA_TRY(exclusive_sum(ctx, nheads, R->run_base, n_items + 1));
-        uint64_t sc[2];
-        WGA_TRY(read_scalars(ctx, {R->run_base + n_items, ovf}, sc));
+        uint64_t sc[3];
+        WGA_TRY(read_scalars(ctx, {R->run_base + n_items, ovf, ovf + 2}, sc));
+        R->n_w = (uint32_t)sc[2];
         float ms = 0.f;
         WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->walk_ms += ms;
@@ -680,21 +708,52 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     unsigned long long *rec_cnt = ctx->buf<unsigned long long>(B_REC_CNT, n_rec * 5);
     if (!rec_cnt) return ctx->err_code;
     WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
+    const bool share = (flags & WGA_F_SHARE_WALK) != 0;
     Runs RU;
-    WGA_TRY(run_walk<MODE_RUNS_EXT>(ctx, P, rec_cnt, &RU));
-    const uint64_t n_runs = RU.n_runs;
+    if (share) WGA_TRY(run_walk<MODE_RUNS_ALL>(ctx, P, rec_cnt, &RU));
+    else WGA_TRY(run_walk<MODE_RUNS_EXT>(ctx, P, rec_cnt, &RU));
+    uint64_t n_runs = RU.n_runs;
     uint64_t *run_base = RU.run_base, *run_pos = RU.run_pos;
     uint32_t *run_rec = RU.run_rec;
     uint8_t *run_cls = RU.run_cls;
     uint64_t *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
     uint32_t *run_dl = ctx->buf<uint32_t>(B_RUN_DL, n_runs + 1);
-    uint64_t *cig_off = ctx->buf<uint64_t>(B_RUN_CIGOFF, n_runs + 1);
     uint64_t *rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
     uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
     uint32_t *row_fixed = ctx->buf<uint32_t>(B_ROW_FIXED, n_rec + 1);
-    if (!run_len || !run_dl || !cig_off || !rec_run_first || !row_len || !row_off || !row_fixed) return ctx->err_code;
+    if (!run_len || !run_dl || !rec_run_first || !row_len || !row_off || !row_fixed) return ctx->err_code;
     LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, run_base, n_items, n_runs, rec_run_first);
     LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, run_pos, run_rec, P.rc.ncols, run_len, run_dl);
+    WalkCache &wc = tok_of(ctx).wc;
+    if (share) {  // what stat / call on the same slab can pick up (the counters join below)
+        wc.P = P; wc.n_rec = n_rec; wc.n_items = n_items; wc.has_q = query_name != nullptr; wc.qname = query_name ? query_name : "";
+        wc.recs = true; wc.call_same = P.ragged == 0;
+        wc.RU = RU; wc.rec_run_first = rec_run_first; wc.run_len = run_len; wc.runs = true;
+    }
+    if (share && RU.n_w) {
+        // both-gap columns: the PAF rows need the coarser EXT list (k_ext_flags); the caller list above stays for `call`
+        const uint64_t n_all = n_runs;
+        uint32_t *xflag = ctx->buf<uint32_t>(B_XRUN_FLAG, n_all + 1);
+        uint64_t *xidx = ctx->buf<uint64_t>(B_XRUN_IDX, n_all + 1);
+        if (!xflag || !xidx) return ctx->err_code;
+        LAUNCH(ctx, k_ext_flags, grid_for(n_all + 1, 256), 256, n_all, (const uint32_t *)run_rec, (const uint8_t *)run_cls, xflag);
+        WGA_TRY(exclusive_sum(ctx, xflag, xidx, n_all + 1));
+        uint64_t n_x;
+        WGA_TRY(read_scalars(ctx, {xidx + n_all}, &n_x));
+        uint64_t *xpos = ctx->buf<uint64_t>(B_XRUN_POS, n_x + 1);
+        uint32_t *xrec = ctx->buf<uint32_t>(B_XRUN_REC, n_x + 1);
+        uint8_t *xcls = ctx->buf<uint8_t>(B_XRUN_CLS, n_x + 1);
+        uint64_t *xfirst = ctx->buf<uint64_t>(B_GEN_C, n_rec + 1), *xlen = ctx->buf<uint64_t>(B_GEN_D, n_x + 1);
+        uint32_t *xdl = ctx->buf<uint32_t>(B_GEN_E, n_x + 1);
+        if (!xpos || !xrec || !xcls || !xfirst || !xlen || !xdl) return ctx->err_code;
+        LAUNCH(ctx, k_ext_scatter, grid_for(n_all, 256), 256, n_all, (const uint32_t *)xflag, (const uint64_t *)xidx,
+               (const uint64_t *)run_pos, (const uint32_t *)run_rec, (const uint8_t *)run_cls, xpos, xrec, xcls);
+        LAUNCH(ctx, k_ext_rec_first, grid_for(n_rec + 1, 256), 256, n_rec, (const uint64_t *)rec_run_first, (const uint64_t *)xidx, xfirst);
+        LAUNCH(ctx, k_run_len, grid_for(n_x + 1, 256), 256, n_x, xpos, xrec, P.rc.ncols, xlen, xdl);
+        n_runs = n_x; run_pos = xpos; run_rec = xrec; run_cls = xcls; run_len = xlen; run_dl = xdl; rec_run_first = xfirst;
+    }
+    uint64_t *cig_off = ctx->buf<uint64_t>(B_RUN_CIGOFF, n_runs + 1);
+    if (!cig_off) return ctx->err_code;
     WGA_TRY(exclusive_sum(ctx, run_dl, cig_off, n_runs + 1));
     PafRowArgs R;
     R.n_rec = n_rec; R.text = ctx->d_text; R.sl = P.sl; R.tl = P.rc.tl; R.ql = P.rc.ql; R.ncols = P.rc.ncols;
@@ -717,11 +776,12 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
         LAUNCH(ctx, k_paf_cigar, grid_for(n_runs, 256), 256, n_runs, (const uint32_t *)run_rec, (const uint8_t *)run_cls,
                (const uint64_t *)run_len, (const uint32_t *)run_dl, (const uint64_t *)cig_off, (const uint64_t *)rec_run_first,
                (const uint64_t *)row_off, (const uint32_t *)row_fixed, d_out);
-    // per-record 11 counters stay available for wga_last_record_counts
-    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
+    // per-record 11 counters stay available for wga_last_record_counts (and for a following wga_maf_stat)
+    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_CNT11, n_rec * 11);
     if (!cnt11) return ctx->err_code;
     LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
     ctx->last_counts_valid = true;
+    if (share) wc.counts = true;
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
@@ -984,16 +1044,31 @@ int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     cudaSetDevice(ctx->device);
     walk_begin(ctx);
     WGA_TRY(stage_text(ctx, text, len, mem, flags));
+    TokCache &tc = tok_of(ctx);
+    WalkCache &wc = tc.wc;
     Prep P;
-    WGA_TRY(prepare_maf(ctx, flags, query_name, 0, &P));
+    unsigned long long *cnt11 = nullptr;
+    // RecStat::from(Cigar) (common.rs:116-140) is a function of the 11 counters: when the previous command on this slab
+    // left them behind (wga_maf2paf with WGA_F_SHARE_WALK), stat needs neither record building nor a walk
+    const bool reuse = (flags & WGA_F_REUSE_INDEX) && tc.valid && tc.d_text == ctx->d_text && tc.len == len && wc.recs && wc.counts &&
+                       wc.same_q(query_name);
+    if (reuse) {
+        P = wc.P;
+        ctx->n_rec = wc.n_rec; ctx->n_items = wc.n_items;
+        cnt11 = (unsigned long long *)ctx->bufs[B_CNT11].p;
+    } else {
+        WGA_TRY(prepare_maf(ctx, flags, query_name, 0, &P));
+    }
     const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
     if (n_rec == 0) return sync_check(ctx);
-    unsigned long long *rec_cnt = ctx->buf<unsigned long long>(B_REC_CNT, n_rec * 5);
-    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
-    if (!rec_cnt || !cnt11) return ctx->err_code;
-    WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
-    if (n_items) WGA_TRY(run_walk<MODE_STAT>(ctx, P, rec_cnt, nullptr));
-    LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
+    if (!reuse) {
+        unsigned long long *rec_cnt = ctx->buf<unsigned long long>(B_REC_CNT, n_rec * 5);
+        cnt11 = ctx->buf<unsigned long long>(B_CNT11, n_rec * 11);
+        if (!rec_cnt || !cnt11) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(rec_cnt, 0, n_rec * 5 * 8, ctx->stream));
+        if (n_items) WGA_TRY(run_walk<MODE_STAT>(ctx, P, rec_cnt, nullptr));
+        LAUNCH(ctx, k_maf_counts11, grid_for(n_rec, 256), 256, n_rec, rec_cnt, P.rc.ncols, P.rc.neg, P.rc.skip, cnt11);
+    }
     RecMeta M;
     M.text = ctx->d_text;
     uint64_t *tno = ctx->buf<uint64_t>(B_GEN_C, n_rec), *qno = ctx->buf<uint64_t>(B_GEN_D, n_rec);
@@ -1005,7 +1080,10 @@ int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     M.t_name_off = tno; M.q_name_off = qno; M.t_name_len = tnl; M.q_name_len = qnl;
     M.t_size = m4; M.q_size = m4 + n_rec; M.t_start = m4 + 2 * n_rec; M.q_start = m4 + 3 * n_rec;
     M.neg = P.rc.neg; M.skip = P.rc.skip;
-    int rc = stat_reduce(ctx, n_rec, M, cnt11, P.err_key, acc);
+    unsigned long long *err_key = ctx->buf<unsigned long long>(B_ERR, 2);
+    if (!err_key) return ctx->err_code;
+    if (reuse) LAUNCH(ctx, k_init_u64, 1, 1, err_key, 1, kNoErr);
+    int rc = stat_reduce(ctx, n_rec, M, cnt11, err_key, acc);
     if (rc) return rc;
     if (ctx->walk_launches) {
         float ms = 0.f;
@@ -1025,7 +1103,7 @@ int wga_last_record_counts(wga_ctx *ctx, uint64_t *dst, uint64_t cap_records, ui
     *n_records = ctx->n_rec;
     uint64_t n = std::min(cap_records, ctx->n_rec);
     if (n && dst) {
-        WGA_CK(cudaMemcpyAsync(dst, ctx->bufs[B_GEN_A].p, n * 88, cudaMemcpyDeviceToHost, ctx->stream));
+        WGA_CK(cudaMemcpyAsync(dst, ctx->bufs[B_CNT11].p, n * 88, cudaMemcpyDeviceToHost, ctx->stream));
         WGA_TRY(sync_check(ctx));
     }
     return WGA_OK;
@@ -1064,26 +1142,48 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     }
     walk_begin(ctx);
     WGA_TRY(stage_text(ctx, text, len, mem, flags));
+    TokCache &tc = tok_of(ctx);
+    WalkCache &wc = tc.wc;
     Prep P;
-    WGA_TRY(prepare_maf(ctx, flags, opts->query_name, 1, &P));
+    Runs RU;
+    uint64_t *run_len = nullptr, *rec_run_first = nullptr;
+    // the caller-classified run list of this slab may still be there (wga_maf2paf with WGA_F_SHARE_WALK): `call` then
+    // starts at its chunk grid.  Only when it would have built exactly the same records (no single-row / ragged block).
+    const bool reuse = (flags & WGA_F_REUSE_INDEX) && tc.valid && tc.d_text == ctx->d_text && tc.len == len && wc.recs && wc.runs &&
+                       wc.call_same && wc.same_q(opts->query_name);
+    if (reuse) {
+        P = wc.P;
+        RU = wc.RU;
+        run_len = wc.run_len;
+        rec_run_first = wc.rec_run_first;
+        ctx->n_rec = wc.n_rec; ctx->n_items = wc.n_items; ctx->n_runs = RU.n_runs;
+        P.err_key = ctx->buf<unsigned long long>(B_ERR, 2);
+        if (!P.err_key) return ctx->err_code;
+        LAUNCH(ctx, k_init_u64, 1, 1, P.err_key, 1, kNoErr);
+    } else {
+        WGA_TRY(prepare_maf(ctx, flags, opts->query_name, 1, &P));
+    }
     const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
     if (n_rec == 0 || n_items == 0) return sync_check(ctx);
 
     // dense pass: caller-classified run list
-    Runs RU;
-    WGA_TRY(run_walk<MODE_RUNS_CALLER>(ctx, P, nullptr, &RU));
+    if (!reuse) WGA_TRY(run_walk<MODE_RUNS_CALLER>(ctx, P, nullptr, &RU));
     const uint64_t n_runs = RU.n_runs;
     uint64_t *run_base = RU.run_base, *run_pos = RU.run_pos;
     uint32_t *run_rec = RU.run_rec;
     uint8_t *run_cls = RU.run_cls;
-    uint64_t *run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
-    uint64_t *rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
+    if (!reuse) {
+        run_len = ctx->buf<uint64_t>(B_RUN_LEN, n_runs + 1);
+        rec_run_first = ctx->buf<uint64_t>(B_REC_RUNFIRST, n_rec + 1);
+    }
     uint64_t *tcon = ctx->buf<uint64_t>(B_GEN_A, n_runs + 1), *qcon = ctx->buf<uint64_t>(B_GEN_B, n_runs + 1);
     uint64_t *St = ctx->buf<uint64_t>(B_GEN_C, n_runs + 1), *Sq = ctx->buf<uint64_t>(B_GEN_D, n_runs + 1);
     uint64_t *nchunks = ctx->buf<uint64_t>(B_GEN_E, n_rec + 1), *rec_chunk_first = ctx->buf<uint64_t>(B_GEN_F, n_rec + 1);
     if (!run_len || !rec_run_first || !tcon || !qcon || !St || !Sq || !nchunks || !rec_chunk_first) return ctx->err_code;
-    LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, run_base, n_items, n_runs, rec_run_first);
-    LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, run_pos, run_rec, P.rc.ncols, run_len, (uint32_t *)nullptr);
+    if (!reuse) {
+        LAUNCH(ctx, k_rec_run_first, grid_for(n_rec + 1, 256), 256, n_rec, P.item_base, run_base, n_items, n_runs, rec_run_first);
+        LAUNCH(ctx, k_run_len, grid_for(n_runs + 1, 256), 256, n_runs, run_pos, run_rec, P.rc.ncols, run_len, (uint32_t *)nullptr);
+    }
     LAUNCH(ctx, k_run_contrib, grid_for(n_runs + 1, 256), 256, n_runs, run_cls, run_len, tcon, qcon);
     WGA_TRY(exclusive_sum(ctx, tcon, St, n_runs + 1));
     WGA_TRY(exclusive_sum(ctx, qcon, Sq, n_runs + 1));
@@ -1204,7 +1304,7 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     R.q_name_len = ctx->buf<uint32_t>(B_PAF_F, n_rec); R.t_name_len = ctx->buf<uint32_t>(B_PAF_G, n_rec);
     uint64_t *m4 = ctx->buf<uint64_t>(B_PAF_H, 4 * n_rec);
     R.neg = ctx->buf<uint8_t>(B_PAF_I, n_rec);
-    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_A, n_rec * 11);
+    unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_CNT11, n_rec * 11);
     if (!R.q_name_off || !R.t_name_off || !R.cig_off || !R.cig_len || !R.q_name_len || !R.t_name_len || !m4 || !R.neg || !cnt11)
         return ctx->err_code;
     R.q_size = m4; R.t_size = m4 + n_rec; R.q_start = m4 + 2 * n_rec; R.t_start = m4 + 3 * n_rec;
@@ -1447,7 +1547,7 @@ int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     P2mView V;
     V.n_rec = n_rec; V.n_ops = n_opsT; V.text = d_text; V.R = R; V.X = X; V.op_base = op_base; V.op_len = op_len; V.op_type = op_type;
     V.op_rec = op_rec; V.op_pos = op_pos; V.S_all = S_all; V.S_i = S_i; V.S_d = S_d; V.tseq = TF->d_seq; V.qseq = QF->d_seq;
-    V.blk_len = blk_len; V.blk_off = blk_off; V.fix_t = fix_t; V.fix_q = fix_q; V.out = nullptr;
+    V.blk_len = blk_len; V.blk_off = blk_off; V.fix_t = fix_t; V.fix_q = fix_q; V.out = nullptr; V.t_neg = nullptr;
     if (key == kNoErr) {
         LAUNCH(ctx, k_p2m_ops<1>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)op_base, op_len, op_type,
                op_rec, op_pos, err_key);
@@ -1665,6 +1765,271 @@ int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
     if (!d_out) return ctx->err_code;
     V.out = d_out;
     LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    return finish_output(ctx, d_out, total, mem, flags, out);
+}
+
+// ---------------------------------------------------------------- chain reader front end (chain.rs:27-75,206-383)
+}  // extern "C"
+namespace {
+struct ChainPrep {
+    LineView lv;
+    uint64_t n_lines = 0, n_rec = 0;
+    uint32_t *hdr_scan = nullptr;
+    uint64_t *hdr_line = nullptr;
+    ChainRecs C;
+    uint64_t *v = nullptr;
+    uint32_t *dl_cig = nullptr, *dl_ops = nullptr;
+    unsigned long long *err_key = nullptr;  // [0] reader errors, [1] errors of the stages after it (chain2maf)
+};
+
+// host restatement of the reader's error wording (chain.rs:206-350, errors.rs) for the line a device error points at
+std::string chain_error_text(const std::string &line, int code, bool header) {
+    static const char *fname[12] = {"score", "target_name", "target_size", "target_strand", "target_start", "target_end",
+                                    "query_name", "query_size", "query_strand", "query_start", "query_end", "chain_id"};
+    std::vector<std::string> f;
+    size_t i = header ? std::min<size_t>(5, line.size()) : 0;
+    while (i < line.size()) {
+        while (i < line.size() && nat_ws(line[i])) ++i;
+        if (i >= line.size()) break;
+        size_t b = i;
+        while (i < line.size() && !nat_ws(line[i])) ++i;
+        f.push_back(line.substr(b, i - b));
+    }
+    auto bad_int = [](const std::string &t) {
+        uint64_t v;
+        return !parse_u64_bytes((const unsigned char *)t.data(), t.size(), &v);
+    };
+    if (header) {
+        for (int k = 0; k < 12; ++k) {
+            if ((size_t)k >= f.size()) return std::string("Parse Chain Error By: Chain Line Field `") + fname[k] + "` Missing";
+            if (k == 0) { if (code == WGA_E_PARSE_FLOAT) return "Parse `" + f[0] + "` Into Float Error"; }
+            else if (k == 3 || k == 8) { if (f[k] != "+" && f[k] != "-") return "Parse Strand `" + f[k] + "` Error"; }
+            else if (k != 1 && k != 6 && bad_int(f[k])) return "Parse `" + f[k] + "` Into Integer Error";
+        }
+    } else {
+        if (f.empty()) return "Parse Chain Error By: Chain Line Field `size` Missing";
+        for (size_t k = 0; k < f.size() && k < 3; ++k)
+            if (bad_int(f[k])) return "Parse `" + f[k] + "` Into Integer Error";
+    }
+    return "chain parse error code " + std::to_string(code);
+}
+
+int chain_resolve_error(wga_ctx *ctx, const ChainPrep &CP, uint64_t key) {
+    const int code = (int)(key & 0xFF);
+    const uint64_t rec = key >> 32, stage = (key >> 8) & 0xFFFFFF;
+    std::string msg;
+    if (code == WGA_E_NOM) msg = "Format error at record " + std::to_string(rec) + " Parse Error by rust::nom, please check (a chain record must start with `chain` and hold at least one data line)";
+    else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this input (nom error with fewer than 10 bytes left, errors.rs:92)";
+    else if (code == WGA_E_UNSUPPORTED) msg = "unsupported chain construct: `chain` in the middle of a line";
+    else if (rec < CP.n_rec && (stage == 1 || stage >= 3)) {
+        uint64_t h;
+        WGA_TRY(read_scalars(ctx, {CP.hdr_line + rec}, &h));
+        std::string line;
+        if (fetch_line(ctx, CP.lv, stage == 1 ? h : h + (stage - 3), &line) == WGA_OK) msg = chain_error_text(line, code, stage == 1);
+    }
+    if (msg.empty()) msg = "chain parse error code " + std::to_string(code);
+    ctx->set_error(code, rec, msg);
+    return code;
+}
+
+// text -> line classes -> records (headers) + per-line data values; leaves the reader's error key unread in err_key[0]
+int chain_prepare(wga_ctx *ctx, uint64_t len, ChainPrep *CP) {
+    ctx->n_rec = 0;
+    const uint8_t *d_text = ctx->d_text;
+    unsigned long long *err_key = ctx->buf<unsigned long long>(B_ERR, 2);
+    if (!err_key) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, err_key, 2, kNoErr);
+    CP->err_key = err_key;
+    if (len == 0) return WGA_OK;
+    uint64_t n_ws = 0, n_nl = 0;
+    uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
+    WGA_TRY((build_delim_index<0, kTokCap>(ctx, d_text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
+    const uint8_t last_byte = *(uint8_t *)(ctx->h_scal + 8);
+    const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
+    LineView lv;
+    lv.text = d_text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
+    lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = 0;
+    uint8_t *cls = ctx->buf<uint8_t>(B_LINE_FLAGS, n_lines + 1);
+    uint32_t *is_hdr = ctx->buf<uint32_t>(B_LINE_HEAD, n_lines + 1), *hdr_scan = ctx->buf<uint32_t>(B_LINE_REC, n_lines + 1);
+    uint32_t *nonvalid = ctx->buf<uint32_t>(B_PT_FLAG, n_lines + 1), *nv_scan = ctx->buf<uint32_t>(B_PT_IDX, n_lines + 1);
+    uint64_t *first_c = ctx->buf<uint64_t>(B_PP_J, n_lines + 1);
+    if (!cls || !is_hdr || !hdr_scan || !nonvalid || !nv_scan || !first_c) return ctx->err_code;
+    LAUNCH(ctx, k_chain_classify, grid_for(n_lines + 1, 256), 256, lv, cls, is_hdr, nonvalid, first_c);
+    WGA_TRY(exclusive_sum(ctx, is_hdr, hdr_scan, n_lines + 1));
+    WGA_TRY(exclusive_sum(ctx, nonvalid, nv_scan, n_lines + 1));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal, hdr_scan + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal + 1, nv_scan + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    const uint64_t n_rec = *(uint32_t *)ctx->h_scal, n_nv = *(uint32_t *)(ctx->h_scal + 1);
+    ctx->n_rec = n_rec;
+    uint64_t *hdr_line = ctx->buf<uint64_t>(B_REC_FIRST, n_rec + 1), *nv_line = ctx->buf<uint64_t>(B_REC_LAST, n_nv + 1);
+    ChainRecs C;
+    PafRecs &R = C.R;
+    R.q_name_off = ctx->buf<uint64_t>(B_PAF_B, n_rec + 1); R.t_name_off = ctx->buf<uint64_t>(B_PAF_C, n_rec + 1);
+    R.cig_off = ctx->buf<uint64_t>(B_PAF_D, n_rec + 1); R.cig_len = ctx->buf<uint64_t>(B_PAF_E, n_rec + 1);
+    R.q_name_len = ctx->buf<uint32_t>(B_PAF_F, n_rec + 1); R.t_name_len = ctx->buf<uint32_t>(B_PAF_G, n_rec + 1);
+    uint64_t *m4 = ctx->buf<uint64_t>(B_PAF_H, 4 * (n_rec + 1));
+    R.neg = ctx->buf<uint8_t>(B_PAF_I, n_rec + 1);
+    uint64_t *e2 = ctx->buf<uint64_t>(B_PP_K, 2 * (n_rec + 1));
+    C.first_data = ctx->buf<uint64_t>(B_PP_L, n_rec + 1); C.n_data = ctx->buf<uint64_t>(B_PP_M, n_rec + 1);
+    C.t_neg = ctx->buf<uint8_t>(B_PP_N, n_rec + 1);
+    uint64_t *v = ctx->buf<uint64_t>(B_PP_A, 3 * (n_lines + 1));
+    uint32_t *dl_cig = ctx->buf<uint32_t>(B_PP_B, n_lines + 1), *dl_ops = ctx->buf<uint32_t>(B_PP_C, n_lines + 1);
+    if (!hdr_line || !nv_line || !R.q_name_off || !R.t_name_off || !R.cig_off || !R.cig_len || !R.q_name_len || !R.t_name_len || !m4 ||
+        !R.neg || !e2 || !C.first_data || !C.n_data || !C.t_neg || !v || !dl_cig || !dl_ops)
+        return ctx->err_code;
+    R.q_size = m4; R.t_size = m4 + (n_rec + 1); R.q_start = m4 + 2 * (n_rec + 1); R.t_start = m4 + 3 * (n_rec + 1);
+    C.t_end = e2; C.q_end = e2 + (n_rec + 1);
+    LAUNCH(ctx, k_chain_lists, grid_for(n_lines, 256), 256, n_lines, (const uint8_t *)cls, (const uint32_t *)hdr_scan, (const uint32_t *)nv_scan,
+           hdr_line, nv_line);
+    if (n_rec)
+        LAUNCH(ctx, k_chain_headers, grid_for(n_rec, 128), 128, lv, n_rec, (const uint64_t *)hdr_line, (const uint32_t *)nv_scan,
+               (const uint64_t *)nv_line, n_nv, C, err_key);
+    LAUNCH(ctx, k_chain_data, grid_for(n_lines + 1, 256), 256, lv, (const uint8_t *)cls, (const uint32_t *)hdr_scan, (const uint32_t *)nv_scan,
+           (const uint64_t *)hdr_line, (const uint64_t *)first_c, v, dl_cig, dl_ops, err_key);
+    CP->lv = lv; CP->n_lines = n_lines; CP->n_rec = n_rec; CP->hdr_scan = hdr_scan; CP->hdr_line = hdr_line; CP->C = C; CP->v = v;
+    CP->dl_cig = dl_cig; CP->dl_ops = dl_ops;
+    return WGA_OK;
+}
+}  // namespace
+extern "C" {
+
+// ---------------------------------------------------------------- chain2paf (converter.rs:391-416, chain.rs:430-451)
+int wga_chain2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out) {
+    if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    ChainPrep CP;
+    WGA_TRY(chain_prepare(ctx, len, &CP));
+    if (len == 0) return WGA_OK;
+    const uint64_t n_rec = CP.n_rec, n_lines = CP.n_lines;
+    uint64_t *a = ctx->buf<uint64_t>(B_PP_H, n_lines + 1), *b = ctx->buf<uint64_t>(B_PP_I, n_lines + 1);
+    uint64_t *S_size = ctx->buf<uint64_t>(B_PP_D, n_lines + 1), *S_qd = ctx->buf<uint64_t>(B_PP_E, n_lines + 1);
+    uint64_t *S_cig = ctx->buf<uint64_t>(B_PP_F, n_lines + 1);
+    uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
+    uint32_t *row_fixed = ctx->buf<uint32_t>(B_ROW_FIXED, n_rec + 1);
+    if (!a || !b || !S_size || !S_qd || !S_cig || !row_len || !row_off || !row_fixed) return ctx->err_code;
+    LAUNCH(ctx, k_chain_split3, grid_for(n_lines + 1, 256), 256, n_lines, (const uint64_t *)CP.v, a, b);
+    WGA_TRY(exclusive_sum(ctx, a, S_size, n_lines + 1));
+    WGA_TRY(exclusive_sum(ctx, b, S_qd, n_lines + 1));
+    WGA_TRY(exclusive_sum(ctx, CP.dl_cig, S_cig, n_lines + 1));
+    uint64_t key;
+    WGA_TRY(read_scalars(ctx, {CP.err_key}, &key));
+    if (key != kNoErr) return chain_resolve_error(ctx, CP, key);
+    if (n_rec == 0) return WGA_OK;
+    C2pView V;
+    V.n_rec = n_rec; V.text = ctx->d_text; V.C = CP.C; V.S_size = S_size; V.S_qd = S_qd; V.S_cig = S_cig; V.v = CP.v;
+    V.row_len = row_len; V.row_fixed = row_fixed; V.row_off = row_off; V.out = nullptr;
+    LAUNCH(ctx, k_c2p_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
+    uint64_t total;
+    WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    V.out = d_out;
+    LAUNCH(ctx, k_c2p_rows<1>, grid_for(n_rec, 128), 128, V);
+    LAUNCH(ctx, k_c2p_cigar, grid_for(n_lines, 256), 256, n_lines, (const uint32_t *)CP.dl_cig, (const uint32_t *)CP.hdr_scan, V);
+    return finish_output(ctx, d_out, total, mem, flags, out);
+}
+
+// ---------------------------------------------------------------- chain2maf (converter.rs:268-388)
+int wga_chain2maf_header(wga_ctx *ctx, const char *t_fa_path, const char *q_fa_path, wga_span *out) {
+    if (!ctx || !out || !t_fa_path || !q_fa_path) return WGA_E_INVALID_ARG;
+    static thread_local std::string hdr;
+    hdr = std::string("#maf version=1.6 convert_from=chain t_seq_path=") + t_fa_path + " q_seq_path=" + q_fa_path + "\n";
+    out->data = hdr.data();
+    out->len = hdr.size();
+    return WGA_OK;
+}
+
+int wga_chain2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
+                  wga_span *out) {
+    if (!ctx || !out || !TF || !QF || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    ChainPrep CP;
+    WGA_TRY(chain_prepare(ctx, len, &CP));
+    if (len == 0) return WGA_OK;
+    const uint64_t n_rec = CP.n_rec, n_lines = CP.n_lines;
+    const uint8_t *d_text = ctx->d_text;
+    unsigned long long *fe_key = CP.err_key, *be_key = CP.err_key + 1;
+    uint64_t *S_ops = ctx->buf<uint64_t>(B_PP_G, n_lines + 1);
+    if (!S_ops) return ctx->err_code;
+    WGA_TRY(exclusive_sum(ctx, CP.dl_ops, S_ops, n_lines + 1));
+    uint64_t sc[3];
+    WGA_TRY(read_scalars(ctx, {S_ops + n_lines, fe_key}, sc));
+    if (n_rec == 0) return sc[1] != kNoErr ? chain_resolve_error(ctx, CP, sc[1]) : WGA_OK;
+    // every data line of a record the reader accepted has >= 1 op, so the ops of record r are S_ops[first_data .. +n_data)
+    const uint64_t n_opsT = sc[0];
+    const uint64_t fe = sc[1];
+    PafRecs R = CP.C.R;
+    uint64_t *x7 = ctx->buf<uint64_t>(B_PAF_J, 7 * (n_rec + 1));
+    uint64_t *n_ops = ctx->buf<uint64_t>(B_GEN_A, n_rec + 1), *op_base = ctx->buf<uint64_t>(B_GEN_B, n_rec + 1);
+    uint64_t *op_len = ctx->buf<uint64_t>(B_RUN_POS, n_opsT + 1), *c_all = ctx->buf<uint64_t>(B_GEN_C, n_opsT + 1);
+    uint64_t *c_i = ctx->buf<uint64_t>(B_GEN_D, n_opsT + 1), *c_d = ctx->buf<uint64_t>(B_GEN_E, n_opsT + 1);
+    uint64_t *S_all = ctx->buf<uint64_t>(B_GEN_F, n_opsT + 1), *S_i = ctx->buf<uint64_t>(B_GEN_G, n_opsT + 1);
+    uint64_t *S_d = ctx->buf<uint64_t>(B_GEN_H, n_opsT + 1);
+    uint8_t *op_type = ctx->buf<uint8_t>(B_RUN_CLS, n_opsT + 1);
+    uint32_t *op_rec = ctx->buf<uint32_t>(B_RUN_REC, n_opsT + 1), *op_pos = ctx->buf<uint32_t>(B_RUN_DL, n_opsT + 1);
+    uint64_t *blk_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rec + 1), *blk_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rec + 1);
+    uint32_t *fix_t = ctx->buf<uint32_t>(B_ROW_FIXED, n_rec + 1), *fix_q = ctx->buf<uint32_t>(B_NAME_LEN, n_rec + 1);
+    if (!x7 || !n_ops || !op_base || !op_len || !c_all || !c_i || !c_d || !S_all || !S_i || !S_d || !op_type || !op_rec || !op_pos ||
+        !blk_len || !blk_off || !fix_t || !fix_q)
+        return ctx->err_code;
+    P2mRecs X;
+    X.q_end = x7; X.t_end = x7 + (n_rec + 1); X.mapq = x7 + 2 * (n_rec + 1); X.t_src = x7 + 3 * (n_rec + 1);
+    X.q_src = x7 + 4 * (n_rec + 1); X.LT = x7 + 5 * (n_rec + 1); X.LQ = x7 + 6 * (n_rec + 1); X.n_ops = n_ops;
+    FaView T{TF->d_seq, TF->d_names, TF->d_meta, TF->n_seq}, Q{QF->d_seq, QF->d_names, QF->d_meta, QF->n_seq};
+    uint64_t be = kNoErr, total = 0;
+    P2mView V;
+    if (fe == kNoErr || (fe >> 32) > 0) {  // a reader error in record 0 precedes everything else
+        LAUNCH(ctx, k_c2m_spans, grid_for(n_rec + 1, 256), 256, n_rec, d_text, CP.C, X, T, Q, (const uint64_t *)S_ops, op_base, be_key);
+        LAUNCH(ctx, k_p2m_revcomp_check, (unsigned)n_rec, 128, n_rec, R, X, QF->d_seq, be_key);
+        LAUNCH(ctx, k_c2m_ops, grid_for(n_lines, 256), 256, n_lines, (const uint32_t *)CP.dl_ops, (const uint32_t *)CP.hdr_scan,
+               (const uint64_t *)S_ops, (const uint64_t *)CP.v, op_len, op_type, op_rec, op_pos);
+        V.n_rec = n_rec; V.n_ops = n_opsT; V.text = d_text; V.R = R; V.X = X; V.op_base = op_base; V.op_len = op_len; V.op_type = op_type;
+        V.op_rec = op_rec; V.op_pos = op_pos; V.S_all = S_all; V.S_i = S_i; V.S_d = S_d; V.tseq = TF->d_seq; V.qseq = QF->d_seq;
+        V.blk_len = blk_len; V.blk_off = blk_off; V.fix_t = fix_t; V.fix_q = fix_q; V.out = nullptr; V.t_neg = CP.C.t_neg;
+        LAUNCH(ctx, k_p2m_contrib, grid_for(n_opsT + 1, 256), 256, n_opsT, op_len, op_type, c_all, c_i, c_d);
+        WGA_TRY(exclusive_sum(ctx, c_all, S_all, n_opsT + 1));
+        WGA_TRY(exclusive_sum(ctx, c_i, S_i, n_opsT + 1));
+        WGA_TRY(exclusive_sum(ctx, c_d, S_d, n_opsT + 1));
+        if (n_opsT) LAUNCH(ctx, k_p2m_check, grid_for(n_opsT, 256), 256, V, be_key);
+        LAUNCH(ctx, k_p2m_blocks<0>, grid_for(n_rec + 1, 256), 256, V);
+        WGA_TRY(exclusive_sum(ctx, blk_len, blk_off, n_rec + 1));
+        WGA_TRY(read_scalars(ctx, {blk_off + n_rec, be_key}, sc));
+        total = sc[0];
+        be = sc[1];
+    }
+    // the reference reads record r, then fetches / reverse-complements / expands it, then reads record r+1: the reader's
+    // error in record a comes before a later stage's error in record b iff a <= b
+    if (fe != kNoErr && (be == kNoErr || (fe >> 32) <= (be >> 32))) return chain_resolve_error(ctx, CP, fe);
+    if (be != kNoErr) {
+        const int code = (int)(be & 0xFF);
+        const uint64_t rec = be >> 32, pos = (be >> 8) & 0xFFFFFF;
+        std::string msg;
+        if (code == WGA_E_NOM) msg = "HTS library error by sequence of record " + std::to_string(rec) + " not found in the FASTA index";
+        else if (code == WGA_E_VCF_BASE) {
+            uint64_t ql[2];
+            WGA_TRY(read_scalars(ctx, {X.q_src + rec, X.LQ + rec}, ql));
+            char c = '?';
+            if (pos >= 2 && ql[1] > pos - 2) WGA_CK(cudaMemcpy(&c, QF->d_seq + ql[0] + ql[1] - 1 - (pos - 2), 1, cudaMemcpyDeviceToHost));
+            msg = std::string("Invalid Base: `") + c + "`";
+        } else msg = "the reference panics on this record (an insert past the end of the fetched sequence)";
+        ctx->set_error(code, rec, msg);
+        return code;
+    }
+    char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_out) return ctx->err_code;
+    V.out = d_out;
+    LAUNCH(ctx, k_p2m_blocks<1>, grid_for(n_rec + 1, 256), 256, V);
+    LAUNCH(ctx, k_p2m_rows, grid_for((n_opsT + n_rec) * 32, 256), 256, V);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
