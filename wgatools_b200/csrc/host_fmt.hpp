@@ -13,45 +13,61 @@
 
 namespace wga {
 
-inline std::string fmt_f32(float v) {
-    if (std::isnan(v)) return "NaN";
-    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
-    std::string out;
-    if (std::signbit(v)) { out.push_back('-'); v = -v; }
-    if (v == 0.0f) return out + "0.0";
-    // shortest round-trip digits in scientific form: d[.ddd]e[+-]XX
-    char buf[48];
-    auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
-    std::string sci(buf, res.ptr);
-    size_t epos = sci.find('e');
-    std::string digits;
-    for (size_t i = 0; i < epos; ++i)
-        if (sci[i] >= '0' && sci[i] <= '9') digits.push_back(sci[i]);
-    int e10 = std::stoi(sci.substr(epos + 1));
-    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
-    int length = (int)digits.size(), k = e10 - (length - 1), kk = length + k;
-    if (0 <= k && kk <= 13) {  // 1234e7 -> 12340000000.0
-        out += digits;
-        out.append((size_t)(kk - length), '0');
-        out += ".0";
-    } else if (0 < kk && kk <= 13) {  // 1234e-2 -> 12.34
-        out += digits.substr(0, (size_t)kk);
-        out.push_back('.');
-        out += digits.substr((size_t)kk);
-    } else if (-6 < kk && kk <= 0) {  // 1234e-6 -> 0.001234
-        out += "0.";
-        out.append((size_t)(-kk), '0');
-        out += digits;
-    } else if (length == 1) {  // 1e30
-        out += digits;
-        out += "e" + std::to_string(kk - 1);
-    } else {  // 1234e30 -> 1.234e33
-        out.push_back(digits[0]);
-        out.push_back('.');
-        out += digits.substr(1);
-        out += "e" + std::to_string(kk - 1);
+// ryu's Buffer::format(f32) text (what csv prints): shortest round-trip digits, laid out as ryu's pretty printer does
+// (d2s/f2s "format32": plain decimals for exponents in [-5, 13), scientific otherwise).  Writes at most 24 bytes, returns
+// the length.
+inline size_t fmt_f32_to(char *out, float v) {
+    char *o = out;
+    if (std::isnan(v)) { memcpy(o, "NaN", 3); return 3; }
+    if (std::isinf(v)) {
+        if (v < 0) { memcpy(o, "-inf", 4); return 4; }
+        memcpy(o, "inf", 3);
+        return 3;
     }
-    return out;
+    if (std::signbit(v)) { *o++ = '-'; v = -v; }
+    if (v == 0.0f) { memcpy(o, "0.0", 3); return (size_t)(o - out) + 3; }
+    // shortest round-trip digits in scientific form: d[.ddd]e[+-]XX
+    char buf[32];
+    auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    char digits[16];
+    int length = 0;
+    const char *p = buf;
+    for (; p < res.ptr && *p != 'e'; ++p)
+        if (*p >= '0' && *p <= '9') digits[length++] = *p;
+    int e10 = 0;
+    {
+        ++p;  // 'e'
+        bool neg = *p == '-';
+        if (*p == '-' || *p == '+') ++p;
+        for (; p < res.ptr; ++p) e10 = e10 * 10 + (*p - '0');
+        if (neg) e10 = -e10;
+    }
+    while (length > 1 && digits[length - 1] == '0') --length;
+    const int k = e10 - (length - 1), kk = length + k;
+    if (0 <= k && kk <= 13) {  // 1234e7 -> 12340000000.0
+        memcpy(o, digits, (size_t)length); o += length;
+        for (int i = length; i < kk; ++i) *o++ = '0';
+        *o++ = '.'; *o++ = '0';
+    } else if (0 < kk && kk <= 13) {  // 1234e-2 -> 12.34
+        memcpy(o, digits, (size_t)kk); o += kk;
+        *o++ = '.';
+        memcpy(o, digits + kk, (size_t)(length - kk)); o += length - kk;
+    } else if (-6 < kk && kk <= 0) {  // 1234e-6 -> 0.001234
+        *o++ = '0'; *o++ = '.';
+        for (int i = 0; i < -kk; ++i) *o++ = '0';
+        memcpy(o, digits, (size_t)length); o += length;
+    } else {  // 1e30, 1.234e33
+        *o++ = digits[0];
+        if (length > 1) { *o++ = '.'; memcpy(o, digits + 1, (size_t)(length - 1)); o += length - 1; }
+        *o++ = 'e';
+        auto r2 = std::to_chars(o, o + 8, kk - 1);
+        o = r2.ptr;
+    }
+    return (size_t)(o - out);
+}
+inline std::string fmt_f32(float v) {
+    char b[32];
+    return std::string(b, fmt_f32_to(b, v));
 }
 
 inline bool nat_ws(char c) { return c == ' ' || (c >= 9 && c <= 13); }

@@ -9,10 +9,15 @@
 #pragma once
 #include <algorithm>
 #include <charconv>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <vector>
 
 #include "../../include/wga_b200.h"
@@ -105,6 +110,14 @@ struct wga_stat_acc {
 
     // write_style_result (stat.rs:107-126): stable natord sort on ref_name, TSV with header
     void write() {
+        static const bool dbg = getenv("WGA_DEBUG_TIMING") != nullptr;
+        auto T0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char *w) {
+            if (!dbg) return;
+            auto t = std::chrono::steady_clock::now();
+            fprintf(stderr, "[acc.write] %-10s %8.3f ms\n", w, std::chrono::duration<double, std::milli>(t - T0).count());
+            T0 = t;
+        };
         text.clear();
         const size_t n = rows.size();
         std::vector<float> inv(n, 0.f);
@@ -134,6 +147,7 @@ struct wga_stat_acc {
                 }
             }
         }
+        lap("group");
         const size_t ng = grp_first.size();
         std::vector<uint32_t> gorder(ng), grank(ng), gcount(ng + 1, 0u), order(n);
         for (uint32_t g = 0; g < ng; ++g) gorder[g] = g;
@@ -153,38 +167,74 @@ struct wga_stat_acc {
         for (size_t g = 0; g < ng; ++g) gcount[g + 1] += gcount[g];
         for (uint32_t i = 0; i < n; ++i) order[gcount[grank[grp_of[i]]]++] = i;
 
-        if (n) {
-            text.reserve(n * 192 + 512);
-            text += "ref_name\tref_size\tref_start\tquery_name\tquery_size\tquery_start\taligned_size\t"
-                    "unaligned_size\tidentity\tsimilarity\tmatched\tmismatched\tins_event\tdel_event\t"
-                    "ins_size\tdel_size\tinv_event\tinv_size\tinv_ins_event\tinv_ins_size\t"
-                    "inv_del_event\tinv_del_size\n";
-        }
-        char nb[24];
-        for (uint32_t id : order) {
-            const Row &r = rows[id];
-            const uint64_t *c = r.v;
-            uint64_t matched = c[0], mism = c[1];
-            uint64_t aligned = c[0] + c[1] + c[5] + c[9];       // common.rs:124-125
-            uint64_t unaligned = each ? 0 : r.ref_size - aligned;  // wraps like release Rust (stat.rs:216)
-            float identity = (float)matched / (float)aligned;
-            float similarity = (float)(matched + mism) / (float)aligned;
-            wga::csv_field(text, ref_name(r));
-            auto u = [&](uint64_t x) {
-                text.push_back('\t');
-                auto res = std::to_chars(nb, nb + sizeof nb, x);
-                text.append(nb, res.ptr - nb);
+        lap("order");
+        if (n == 0) return;
+        static const char kHeader[] =
+            "ref_name\tref_size\tref_start\tquery_name\tquery_size\tquery_start\taligned_size\t"
+            "unaligned_size\tidentity\tsimilarity\tmatched\tmismatched\tins_event\tdel_event\t"
+            "ins_size\tdel_size\tinv_event\tinv_size\tinv_ins_event\tinv_ins_size\t"
+            "inv_del_event\tinv_del_size\n";
+        // Rows are independent: ranges of the sorted order are formatted by a few host threads, each into its own buffer
+        // sized for the worst case (19 integers <= 20 digits, 3 floats <= 24 bytes, 22 separators, the two names -- csv
+        // quoting at most doubles them and adds two quotes), then laid end to end.
+        struct Part { std::unique_ptr<char[]> p; size_t n = 0; };
+        auto format_range = [&](size_t lo, size_t hi, Part &dst) {
+            size_t cap = 16;
+            for (size_t k = lo; k < hi; ++k) { const Row &r = rows[order[k]]; cap += 19 * 20 + 3 * 24 + 22 + 2 * ((size_t)r.lr + r.lq) + 4; }
+            dst.p.reset(new char[cap]);  // uninitialised: only the bytes written are ever touched
+            char *o = dst.p.get();
+            auto name = [&](std::string_view f) {
+                bool need = false;
+                for (char c : f) need |= c == '\t' || c == '"' || c == '\r' || c == '\n';
+                if (!need) { memcpy(o, f.data(), f.size()); o += f.size(); return; }
+                *o++ = '"';
+                for (char c : f) { if (c == '"') *o++ = '"'; *o++ = c; }
+                *o++ = '"';
             };
-            auto f = [&](float x) { text.push_back('\t'); text += wga::fmt_f32(x); };
-            u(r.ref_size); u(c[11]);
-            text.push_back('\t'); wga::csv_field(text, query_name(r));
-            u(r.query_size); u(c[12]); u(aligned); u(unaligned);
-            f(identity); f(similarity);
-            u(matched); u(mism); u(c[2]); u(c[4]); u(c[3]); u(c[5]); u(c[10]);
-            f(inv[id]);
-            u(c[6]); u(c[7]); u(c[8]); u(c[9]);
-            text.push_back('\n');
+            auto u = [&](uint64_t x) { *o++ = '\t'; o = std::to_chars(o, o + 20, x).ptr; };
+            auto f = [&](float x) { *o++ = '\t'; o += wga::fmt_f32_to(o, x); };
+            for (size_t k = lo; k < hi; ++k) {
+                const uint32_t id = order[k];
+                const Row &r = rows[id];
+                const uint64_t *c = r.v;
+                const uint64_t matched = c[0], mism = c[1];
+                const uint64_t aligned = c[0] + c[1] + c[5] + c[9];          // common.rs:124-125
+                const uint64_t unaligned = each ? 0 : r.ref_size - aligned;  // wraps like release Rust (stat.rs:216)
+                const float identity = (float)matched / (float)aligned;
+                const float similarity = (float)(matched + mism) / (float)aligned;
+                name(ref_name(r));
+                u(r.ref_size); u(c[11]);
+                *o++ = '\t'; name(query_name(r));
+                u(r.query_size); u(c[12]); u(aligned); u(unaligned);
+                f(identity); f(similarity);
+                u(matched); u(mism); u(c[2]); u(c[4]); u(c[3]); u(c[5]); u(c[10]);
+                f(inv[id]);
+                u(c[6]); u(c[7]); u(c[8]); u(c[9]);
+                *o++ = '\n';
+            }
+            dst.n = (size_t)(o - dst.p.get());
+        };
+        unsigned nt = 1;
+        if (n >= 8192) {
+            nt = std::thread::hardware_concurrency();
+            nt = nt == 0 ? 4 : (nt > 16 ? 16 : nt);
         }
+        std::vector<Part> part(nt);
+        if (nt == 1) {
+            format_range(0, n, part[0]);
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(format_range, n * t / nt, n * (t + 1) / nt, std::ref(part[t]));
+            for (auto &x : th) x.join();
+        }
+        lap("format");
+        size_t total = sizeof kHeader - 1;
+        for (const auto &x : part) total += x.n;
+        text.resize(total);
+        memcpy(&text[0], kHeader, sizeof kHeader - 1);
+        size_t pos = sizeof kHeader - 1;
+        for (const auto &x : part) { memcpy(&text[pos], x.p.get(), x.n); pos += x.n; }
+        lap("concat");
     }
 
     // flat blob: u64 each, u64 n_rows, rows{u32 lr,u32 lq,bytes,u64 rs,u64 qs,u64 v[13],f32 inv,u32 pad},

@@ -68,7 +68,7 @@ __global__ void k_fill_item_desc(uint64_t n_rec, const uint32_t *__restrict__ n_
 #endif  // WGA_WALK_NO_SPARSE
 
 __device__ __forceinline__ uint32_t has_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & kHi; }
-__device__ __forceinline__ int clamp16(int64_t v) { return v < 0 ? 0 : (v > 16 ? 16 : (int)v); }
+__device__ __forceinline__ int clamp16(int32_t v) { return v < 0 ? 0 : (v > 16 ? 16 : v); }
 
 struct WarpEmit {  // run-head emission state of the warp: the item whose slot region is still being filled
     uint32_t open_item;   // 0xFFFFFFFF = none
@@ -239,9 +239,12 @@ struct PrevCol {
 };
 
 // one step (32 chunks) of the current item: 128-bit compare, push the slow chunks, run a batch when 32 are queued
+// tprev / qprev (TMA-staged variant): shared-memory address of the target / query byte of the column before this lane's
+// chunk, valid for every lane but the first chunk of a window (first_in_win); null = take them from the neighbour lane
 template <int MODE, bool RECQ = true>
 __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], uint32_t &qn, WarpEmit &E, uint32_t lane,
-                                          const Geom &g, uint32_t j0, const Vec3 &v, PrevCol &P) {
+                                          const Geom &g, uint32_t j0, const Vec3 &v, PrevCol &P, const uint8_t *tprev = nullptr,
+                                          const uint8_t *qprev = nullptr, bool first_in_win = true) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER || MODE == MODE_RUNS_ALL;
     const uint32_t j = j0 + lane;
     const bool act = j < g.nch;
@@ -275,20 +278,27 @@ __device__ __forceinline__ void walk_step(const WalkArgs &A, uint32_t (*Q)[64], 
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
     if (mask) {
         // bytes of the column before each chunk: the neighbour lane's last column, lane 31 of the previous step for lane 0
-        uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, (tv.w >> 24) | ((qw3 >> 24) << 8), 1);
-        const uint32_t cb = __shfl_sync(0xFFFFFFFFu, (P.tw3 >> 24) | ((P.qw3 >> 24) << 8), 31);
-        if (lane == 0) pb = cb;
+        uint32_t pb;
+        if (tprev) {
+            pb = 0;
+            if (first_in_win && (mask & 1u)) pb = __shfl_sync(0xFFFFFFFFu, (P.tw3 >> 24) | ((P.qw3 >> 24) << 8), 31);  // warp-uniform
+            if (slow && !(first_in_win && lane == 0)) pb = (uint32_t)tprev[0] | ((uint32_t)qprev[0] << 8);
+        } else {
+            pb = __shfl_up_sync(0xFFFFFFFFu, (tv.w >> 24) | ((qw3 >> 24) << 8), 1);
+            const uint32_t cb = __shfl_sync(0xFFFFFFFFu, (P.tw3 >> 24) | ((P.qw3 >> 24) << 8), 31);
+            if (lane == 0) pb = cb;
+        }
         if (slow) {
             const uint32_t slot = qn + __popc(mask & ((1u << lane) - 1u));
             Q[0][slot] = tv.x; Q[1][slot] = tv.y; Q[2][slot] = tv.z; Q[3][slot] = tv.w;
             Q[4][slot] = qw0; Q[5][slot] = qw1; Q[6][slot] = qw2; Q[7][slot] = qw3;
             Q[8][slot] = j == 0 ? g.first_prev : ((1u << 16) | pb);
             uint32_t f0 = 0, t0 = 16, t1 = 16;
-            if (edge) {
-                const int64_t lo = (int64_t)g.a - 16ll * j, hi = (int64_t)g.n + (int64_t)g.a - 16ll * j;
+            if (edge) {  // a <= 15, n <= kSeg, j < nch <= kSeg / 16 + 2: everything fits 32-bit signed arithmetic
+                const int32_t lo = (int32_t)g.a - 16 * (int32_t)j, hi = (int32_t)(g.n + g.a) - 16 * (int32_t)j;
                 f0 = clamp16(lo);
                 t0 = clamp16(hi);
-                t1 = clamp16(hi + (int64_t)g.tail);  // columns of the next item are context only
+                t1 = clamp16(hi + (int32_t)g.tail);  // columns of the next item are context only
             }
             Q[9][slot] = f0 | (t0 << 5) | (t1 << 10) | ((g.seg == 0 ? 1u : 0u) << 15) | ((16u * j + 16u - g.a) << 16);
             Q[10][slot] = g.item;

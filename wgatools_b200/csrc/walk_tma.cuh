@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
             v.t = lds16(Ts + 16u * rel);
             v.q0 = lds16(Qs + 16u * rel);
             v.q1 = lds16(Qs + 16u * rel + 16u);
-            walk_step<MODE, false>(A, Q, qn, E, lane, cur, wj0 + st, v, carry);
+            walk_step<MODE, false>(A, Q, qn, E, lane, cur, wj0 + st, v, carry, Ts + 16u * rel - 1u, Qs + 16u * rel + cur.s - 1u, st == 0);
         }
         --n_out;
         // every lane has consumed its LDS results (they were compared / queued inside walk_step), so the stage can be

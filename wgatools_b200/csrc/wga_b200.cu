@@ -1838,7 +1838,7 @@ int chain_prepare(wga_ctx *ctx, uint64_t len, ChainPrep *CP) {
     const uint8_t *d_text = ctx->d_text;
     unsigned long long *err_key = ctx->buf<unsigned long long>(B_ERR, 2);
     if (!err_key) return ctx->err_code;
-    LAUNCH(ctx, k_init_u64, 1, 1, err_key, 2, kNoErr);
+    LAUNCH(ctx, k_init_u64, 1, 2, err_key, 2, kNoErr);
     CP->err_key = err_key;
     if (len == 0) return WGA_OK;
     uint64_t n_ws = 0, n_nl = 0;
