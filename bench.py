@@ -340,6 +340,16 @@ def sharded_paf_leg(args, ctx, comm, rank, world, dist, timed_fn, all_cpus):
     return res
 
 
+VERBOSE = bool(os.environ.get("WGA_BENCH_VERBOSE"))
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    if VERBOSE:
+        sys.stderr.write(f"[bench {time.perf_counter() - _T0:7.2f}s rank {os.environ.get('RANK', 0)}] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -352,6 +362,10 @@ def main():
         reference_arm(args, rank, metric)
         return
 
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import __graft_entry__ as g
     if rank == 0:
@@ -401,6 +415,8 @@ def main():
         if rank == 0:
             from bench_support import paf_legs
             pa = paf_legs.parse_args(["--steps", str(args.steps), "--only", "stat" if args.config == 4 else "fasta"])
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
             paf_legs.run(pa, ctx)
         if world > 1:
             dist.barrier()
@@ -468,7 +484,9 @@ def main():
         finish_stat(acc)
         return acc
 
+    note(f"workload ready: {nbytes} bytes, gen {t_gen:.1f}s")
     step(1, d_text.data_ptr())
+    note("first step done")
     for _ in range(max(args.warmup - 1, 0)):
         step(1, d_text.data_ptr())
     sampler = ClockSampler(dev)
@@ -488,6 +506,7 @@ def main():
     own1, cub1 = ctx.launch_counts()
     nc1 = L.wga_ctx_nccl_calls(ctx.h)
     tsv_job = last["tsv"]
+    note(f"device-resident legs done: {ms_dev / args.steps:.2f} ms/step")
     # e2e: host buffers, copies inside the timed region.
     # (1) the public pipeline: ONE asynchronous slab-wise upload per step (ResidentMaf = wga_text_open), the three
     #     commands run on every slab as it arrives, outputs copied back to pinned host memory inside each call;
@@ -518,6 +537,7 @@ def main():
         ms_e2e_sep = timed_fn(lambda: step(0, host_ptr), sep_steps)
         mode["share"] = True
     tsv_e2e = last["tsv"]
+    note("host-buffer legs done")
     # the exchange alone (N > 1): per-rank tables rebuilt outside the timed region
     ms_ar = 0.0
     if world > 1:
@@ -560,6 +580,7 @@ def main():
                          "alg_bytes_per_launch": walk["bytes"] / max(walk["launches"], 1)},
             "input_bytes_per_gpu": nbytes, "columns_per_gpu": ncols, "gen_seconds": t_gen, "numa_node": numa}
     failed = []
+    note("exchange-only leg done")
     if world > 1:
         line["allreduce_ms"] = ms_ar / args.steps
     # ---- parity of the multi-GPU exchange: the merged table against ONE process reading the whole file
@@ -602,6 +623,7 @@ def main():
                                  "against": "the oracle's PAF / TSV / VCF of the cpu_baseline sample, byte for byte"}
         if not line["parity"]:
             failed.append("GPU outputs differ from the oracle on the cpu_baseline sample")
+    note("parity checks done")
     # free the MAF before the PAF legs
     del d_text
     del h_view
@@ -610,6 +632,7 @@ def main():
     if not args.no_sharded and args.config == 2:
         sh = sharded_paf_leg(args, ctx, comm, rank, world, dist, timed_fn, all_cpus)
         line["sharded"] = sh
+        note("sharded leg done")
         if rank == 0 and not sh.get("parity", True):
             failed.append("sharded stat -f paf differs from the single-GPU / oracle table")
     if rank == 0 and world == 1 and not args.no_side and args.config == 2:
@@ -623,7 +646,10 @@ def main():
         except Exception as e:  # a side leg must not take the headline line down
             line["side_configs"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         comm.close()

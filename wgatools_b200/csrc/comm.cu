@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <exception>
 #include <new>
 
@@ -208,35 +209,38 @@ struct CallbackTransport : Transport {
 inline uint64_t key2_of(const wga_stat_acc &a, const wga_stat_acc::Row &r) {
     uint64_t h = 0x9AE16A3B2F90404Full;
     const unsigned char *p = (const unsigned char *)a.names.data() + r.name_off;
-    for (uint32_t i = 0; i < r.lr; ++i) h = wga::mix64(h + p[i] + 0x100);
+    for (uint32_t i = 0; i < r.lr; ++i) h = (h + p[i] + 0x100) * 0x9FB21C651E98DF25ull;
     h = wga::mix64(h ^ (r.ref_size + 0x632BE59BD9B4E019ull));
-    for (uint32_t i = 0; i < r.lq; ++i) h = wga::mix64(h + p[r.lr + i] + 0x200);
+    for (uint32_t i = 0; i < r.lq; ++i) h = (h + p[r.lr + i] + 0x200) * 0x9FB21C651E98DF25ull;
     return wga::mix64(h ^ (r.query_size * 0x9E3779B97F4A7C15ull));
 }
 
-struct GlobalIndex {  // (key, key2) -> global pair index
-    std::vector<uint64_t> k1, k2;
-    std::vector<uint32_t> val;  // index + 1
+struct GlobalIndex {  // (key, key2) -> global pair index; one 24-byte entry per slot = one cache line per probe
+    struct Ent { uint64_t k1, k2; uint32_t val, pad; };  // val = index + 1, 0 = empty
+    std::vector<Ent> e;
     size_t mask = 0;
     void init(size_t n) {
         size_t cap = 1024;
         while (cap < 2 * n + 2) cap <<= 1;
-        k1.assign(cap, 0); k2.assign(cap, 0); val.assign(cap, 0); mask = cap - 1;
+        e.assign(cap, Ent{0, 0, 0, 0});
+        mask = cap - 1;
     }
     // returns the index; *fresh = inserted now with index `next`
     uint32_t find_or_insert(uint64_t a, uint64_t b, uint32_t next, bool *fresh) {
         size_t s = a & mask;
         for (;;) {
-            if (!val[s]) { k1[s] = a; k2[s] = b; val[s] = next + 1; *fresh = true; return next; }
-            if (k1[s] == a && k2[s] == b) { *fresh = false; return val[s] - 1; }
+            Ent &x = e[s];
+            if (!x.val) { x.k1 = a; x.k2 = b; x.val = next + 1; *fresh = true; return next; }
+            if (x.k1 == a && x.k2 == b) { *fresh = false; return x.val - 1; }
             s = (s + 1) & mask;
         }
     }
     int64_t find(uint64_t a, uint64_t b) const {
         size_t s = a & mask;
         for (;;) {
-            if (!val[s]) return -1;
-            if (k1[s] == a && k2[s] == b) return (int64_t)val[s] - 1;
+            const Ent &x = e[s];
+            if (!x.val) return -1;
+            if (x.k1 == a && x.k2 == b) return (int64_t)x.val - 1;
             s = (s + 1) & mask;
         }
     }
@@ -244,6 +248,14 @@ struct GlobalIndex {  // (key, key2) -> global pair index
 
 int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     const int R = T.rank, W = T.world;
+    static const bool dbg = getenv("WGA_DEBUG_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *w) {
+        if (!dbg || R != 0) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[allreduce] %-14s %8.3f ms\n", w, std::chrono::duration<double, std::milli>(t - T0).count());
+        T0 = t;
+    };
     if (acc->each) { *err = "--each rows are concatenated in rank order, not reduced"; return WGA_E_INVALID_ARG; }
     for (const auto &r : acc->rows)
         if (r.inv_size != 0.f) { *err = "this accumulator already holds a reduced inv_size column"; return WGA_E_INVALID_ARG; }
@@ -260,6 +272,7 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     if (!hdr_s || !hdr_r) return WGA_E_NOMEM;
     hdr_s[0] = n; hdr_s[1] = dsum; hdr_s[2] = dxor; hdr_s[3] = 0;
     WGA_TRY(T.allgather(hdr_s, hdr_r, 32));
+    lap("digests");
     std::vector<uint64_t> hdr(hdr_r, hdr_r + 4 * (size_t)W);
     uint64_t n_max = 0, n_tot = 0;
     for (int r = 0; r < W; ++r) { n_max = std::max(n_max, hdr[4 * r]); n_tot += hdr[4 * r]; }
@@ -270,9 +283,10 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     for (uint64_t i = 0; i < n; ++i) { hl_s[2 * i] = acc->rows[i].key; hl_s[2 * i + 1] = my2[i]; }
     memset(hl_s + 2 * n, 0, (n_max - n) * 16);
     WGA_TRY(T.allgather(hl_s, hl_r, n_max * 16));
+    lap("hash lists");
     // ---- 1c. global order: first seen over ranks in order
     GlobalIndex G;
-    G.init(std::min<uint64_t>(n_tot, hdr[0] + (n_tot - hdr[0])));
+    G.init(n_tot);
     uint32_t P = 0;
     std::vector<uint32_t> owner;       // global index -> rank that introduces it
     std::vector<uint32_t> mine_global;  // global indices this rank introduces, ascending
@@ -297,11 +311,14 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
         if (g < 0) { *err = "internal: a local pair is missing from the global dictionary"; return WGA_E_INTERNAL; }
         lmap[i] = (uint32_t)g;
     }
-    // ---- 1d. names of the pairs each rank introduces: {u32 lr, u32 lq, u64 rs, u64 qs, bytes} in ascending global order
+    lap("local map");
+    lap("global order");
+    // ---- 1d. names of the pairs each rank introduces: {u32 lr, u32 lq, u64 rs, u64 qs, u64 pair hash, bytes} in ascending
+    //      global order
     std::vector<uint32_t> g2l(P, ~0u);
     for (uint64_t i = 0; i < n; ++i) g2l[lmap[i]] = (uint32_t)i;
     uint64_t my_blob = 0;
-    for (uint32_t g : mine_global) { const auto &r = acc->rows[g2l[g]]; my_blob += 24 + r.lr + r.lq; }
+    for (uint32_t g : mine_global) { const auto &r = acc->rows[g2l[g]]; my_blob += 32 + r.lr + r.lq; }
     hdr_s = (uint64_t *)T.scratch(0, 8);
     hdr_r = (uint64_t *)T.scratch(1, 8 * (size_t)W);
     if (!hdr_s || !hdr_r) return WGA_E_NOMEM;
@@ -318,12 +335,14 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
         for (uint32_t g : mine_global) {
             const auto &r = acc->rows[g2l[g]];
             memcpy(p, &r.lr, 4); memcpy(p + 4, &r.lq, 4); memcpy(p + 8, &r.ref_size, 8); memcpy(p + 16, &r.query_size, 8);
-            memcpy(p + 24, acc->names.data() + r.name_off, (size_t)r.lr + r.lq);
-            p += 24 + r.lr + r.lq;
+            memcpy(p + 24, &r.key, 8);
+            memcpy(p + 32, acc->names.data() + r.name_off, (size_t)r.lr + r.lq);
+            p += 32 + r.lr + r.lq;
         }
         memset(p, 0, blob_max - my_blob);
     }
     WGA_TRY(T.allgather(bl_s, bl_r, blob_max));
+    lap("names");
     // ---- 2. counters: one all-reduce(sum), one all-reduce(min)
     uint64_t *sums = (uint64_t *)T.scratch(4, (size_t)P * 11 * 8), *mins = (uint64_t *)T.scratch(5, (size_t)P * 2 * 8);
     if (!sums || !mins) return WGA_E_NOMEM;
@@ -337,6 +356,7 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     }
     WGA_TRY(T.allreduce_u64(sums, (uint64_t)P * 11, 0));
     WGA_TRY(T.allreduce_u64(mins, (uint64_t)P * 2, 1));
+    lap("counters");
     // ---- 3. inv_size: the f32 partial travels the ranks in file order
     float *carry = (float *)T.scratch(0, (size_t)P * 4), *carry_all = (float *)T.scratch(1, (size_t)P * 4 * (size_t)W);
     if (!carry || !carry_all) return WGA_E_NOMEM;
@@ -347,30 +367,37 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     if (R + 1 < W) WGA_TRY(T.sendrecv(carry, (uint64_t)P * 4, R + 1, nullptr, 0, -1));
     WGA_TRY(T.allgather(carry, carry_all, (uint64_t)P * 4));
     const float *fin = carry_all + (size_t)(W - 1) * P;
+    lap("inv carry");
     // ---- rebuild the accumulator in global order
     wga_stat_acc out;
     out.each = 0;
     out.rows.reserve(P);
-    out.grow_table(P);
+    {
+        size_t name_bytes = 0;
+        for (int r = 0; r < W; ++r) name_bytes += blob_len[r];
+        out.names.reserve(name_bytes);
+    }
     std::vector<const char *> cur(W);
     for (int r = 0; r < W; ++r) cur[r] = bl_r + (size_t)r * blob_max;
     for (uint32_t g = 0; g < P; ++g) {
         const char *p = cur[owner[g]];
         uint32_t lr, lq;
-        uint64_t rs, qs;
-        memcpy(&lr, p, 4); memcpy(&lq, p + 4, 4); memcpy(&rs, p + 8, 8); memcpy(&qs, p + 16, 8);
-        const uint32_t id = out.find_or_add(p + 24, lr, rs, p + 24 + lr, lq, qs);
-        if (id != g) { *err = "pair identity collision across ranks; refusing to merge distinct pairs"; return WGA_E_INTERNAL; }
-        cur[owner[g]] = p + 24 + lr + lq;
+        uint64_t rs, qs, key;
+        memcpy(&lr, p, 4); memcpy(&lq, p + 4, 4); memcpy(&rs, p + 8, 8); memcpy(&qs, p + 16, 8); memcpy(&key, p + 24, 8);
+        // identity across ranks is the 128-bit (pair hash, key2) the dictionary was built on; the rebuilt accumulator's
+        // own lookup table is made on demand from the rows' keys (find_or_add -> grow_table)
+        const uint32_t id = out.push_row(p + 32, lr, rs, p + 32 + lr, lq, qs, key);
+        cur[owner[g]] = p + 32 + lr + lq;
         wga_stat_acc::Row &row = out.rows[id];
         memcpy(row.v, sums + (size_t)g * 11, 88);
         row.v[11] = mins[2 * (size_t)g];
         row.v[12] = mins[2 * (size_t)g + 1];
         row.inv_size = fin[g];
     }
+    lap("rebuild");
     acc->names.swap(out.names);
     acc->rows.swap(out.rows);
-    acc->table.swap(out.table);
+    acc->table.clear();  // rebuilt on demand
     acc->inv_pair.clear();
     acc->inv_num.clear();
     return WGA_OK;

@@ -310,6 +310,134 @@ __device__ __forceinline__ void warp_copy(char *dst, const uint8_t *src, uint64_
     for (uint64_t i = done + lane; i < n; i += 32) dst[i] = (char)src[i];
 }
 
+// ---- 16-byte variant for long copies: dst brought to 16-byte alignment by a byte head, then every lane stores one uint4
+// per iteration, assembled from two aligned 16-byte loads (the source is misaligned against the destination by sm bytes)
+__device__ __forceinline__ uint4 shift16(const uint4 &a, const uint4 &b, uint32_t ws, uint32_t sh) {
+    // bytes [sm, sm + 16) of the 32-byte pair (a, b), sm = 4 * ws + sh / 8; ws is warp-uniform
+    uint32_t w0, w1, w2, w3, w4;
+    switch (ws) {
+        case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+        case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+        case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+        default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+    }
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+__device__ __forceinline__ void warp_copy16(char *dst, const uint8_t *src, uint64_t n, uint32_t lane) {
+    if (n < 512) { warp_copy(dst, src, n, lane); return; }
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (lane < head) dst[lane] = (char)src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t sm = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4 *sv = reinterpret_cast<const uint4 *>(src - sm);
+    uint64_t nv = n >> 4;
+    if (sm && nv) --nv;  // the realign reads vector v + 1: keep every load inside [src - sm, src + n)
+    uint4 *dv = reinterpret_cast<uint4 *>(dst);
+    const uint32_t ws = sm >> 2, sh = (sm & 3u) * 8u;
+    for (uint64_t v = lane; v < nv; v += 32) {
+        const uint4 a = __ldg(sv + v);
+        dv[v] = sm ? shift16(a, __ldg(sv + v + 1), ws, sh) : a;
+    }
+    const uint64_t done = nv << 4;
+    for (uint64_t i = done + lane; i < n; i += 32) dst[i] = (char)src[i];
+}
+// complement of 4 bases at once (ACGTNacgtn only -- validated by k_p2m_revcomp_check): A<->T differ by 0x15, C<->G by 0x04;
+// bit 1 set and bit 3 clear = C/G, bit 1 clear = A/T, bit 3 set = N (unchanged)
+__device__ __forceinline__ uint32_t comp4(uint32_t w) {
+    const uint32_t b1 = (w >> 1) & 0x01010101u, b3 = (w >> 3) & 0x01010101u;
+    const uint32_t cg = b1 & ~b3, at = ~b1 & 0x01010101u;
+    return w ^ ((cg << 2) | at | (at << 2) | (at << 4));
+}
+// dst[i] = complement(src_end[-1 - i]) for i in [0, n): the reverse complement of the n bytes that END at src_end
+__device__ __forceinline__ void warp_revcomp16(char *dst, const uint8_t *src_end, uint64_t n, uint32_t lane) {
+    if (n < 512) {
+        for (uint64_t i = lane; i < n; i += 32) dst[i] = (char)comp_base(src_end[-1 - (int64_t)i]);
+        return;
+    }
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (lane < head) dst[lane] = (char)comp_base(src_end[-1 - (int64_t)lane]);
+    dst += head; src_end -= head; n -= head;
+    // destination vector v <- source block [src_end - 16 (v + 1), src_end - 16 v), reversed
+    const uint32_t sm = (uint32_t)(reinterpret_cast<uintptr_t>(src_end) & 15u);  // same misalignment for every block
+    const uint4 *top = reinterpret_cast<const uint4 *>(src_end - sm);          // aligned vector that holds src_end[0]
+    uint64_t nv = n >> 4;
+    uint4 *dv = reinterpret_cast<uint4 *>(dst);
+    const uint32_t ws = sm >> 2, sh = (sm & 3u) * 8u;
+    for (uint64_t v = lane; v < nv; v += 32) {
+        // block start = src_end - 16 (v + 1) = (top - (v + 1)) + sm bytes
+        const uint4 a = __ldg(top - (v + 1));
+        const uint4 blk = sm ? shift16(a, __ldg(top - v), ws, sh) : a;
+        dv[v] = make_uint4(comp4(__byte_perm(blk.w, 0, 0x0123)), comp4(__byte_perm(blk.z, 0, 0x0123)),
+                           comp4(__byte_perm(blk.y, 0, 0x0123)), comp4(__byte_perm(blk.x, 0, 0x0123)));
+    }
+    const uint64_t done = nv << 4;
+    for (uint64_t i = done + lane; i < n; i += 32) dst[i] = (char)comp_base(src_end[-1 - (int64_t)i]);
+}
+
+// ---- row expansion by RUNS (the default): a row is a plain copy of fetched bases between the gap runs inserted into IT
+// (I ops for the target row, D ops for the query row), shifted by the gaps inserted so far.  One warp per gap op = its
+// '-' fill + the copy run that follows it up to the next gap op of the same row (or to the end of the fetched bases when
+// it is the row's last), plus one warp per record and row for the run before the first gap op.  Runs are ~10 ops long on
+// whole-genome CIGARs, so the copies are kilobytes, stored as 16-byte vectors.
+__global__ void k_p2m_gap_flags(uint64_t n_ops, const uint8_t *__restrict__ op_type, uint32_t *__restrict__ fI, uint32_t *__restrict__ fD) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_ops) return;
+    const uint8_t t = k < n_ops ? op_type[k] : (uint8_t)0;
+    fI[k] = t == 1;
+    fD[k] = t == 2;
+}
+__global__ void k_p2m_gap_lists(uint64_t n_ops, const uint8_t *__restrict__ op_type, const uint64_t *__restrict__ idxI,
+                                const uint64_t *__restrict__ idxD, uint64_t *__restrict__ Ilist, uint64_t *__restrict__ Dlist) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_ops) return;
+    const uint8_t t = op_type[k];
+    if (t == 1) Ilist[idxI[k]] = k;
+    else if (t == 2) Dlist[idxD[k]] = k;
+}
+__global__ void k_p2m_runs(P2mView V, uint64_t n_I, uint64_t n_D, const uint64_t *__restrict__ idxI, const uint64_t *__restrict__ Ilist,
+                           const uint64_t *__restrict__ idxD, const uint64_t *__restrict__ Dlist) {
+    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_t = n_I + V.n_rec;
+    if (w >= n_t + n_D + V.n_rec) return;
+    const bool qrow = w >= n_t;
+    if (qrow) w -= n_t;
+    const uint64_t n_gap = qrow ? n_D : n_I;
+    const uint64_t *gl = qrow ? Dlist : Ilist, *gidx = qrow ? idxD : idxI;
+    uint32_t r;
+    uint64_t a, next, b0, b1, gap_o = 0, gap_len = 0;
+    if (w < n_gap) {  // a gap op and the run after it
+        const uint64_t k = gl[w];
+        r = V.op_rec[k];
+        b0 = V.op_base[r]; b1 = V.op_base[r + 1];
+        gap_o = V.S_all[k] - V.S_all[b0];
+        gap_len = V.op_len[k];
+        a = k + 1;
+        next = (w + 1 < n_gap && gl[w + 1] < b1) ? gl[w + 1] : b1;
+    } else {          // the run before the record's first gap op
+        r = (uint32_t)(w - n_gap);
+        b0 = V.op_base[r]; b1 = V.op_base[r + 1];
+        a = b0;
+        const uint64_t j = gidx[b0];
+        next = (j < n_gap && gl[j] < b1) ? gl[j] : b1;
+    }
+    const uint64_t tot_i = V.S_i[b1] - V.S_i[b0];
+    const uint64_t L = qrow ? V.X.LQ[r] : V.X.LT[r];
+    char *trow = V.out + V.blk_off[r] + V.fix_t[r];
+    char *row = qrow ? trow + (V.X.LT[r] + tot_i) + 1 + V.fix_q[r] : trow;
+    for (uint64_t i = lane; i < gap_len; i += 32) row[gap_o + i] = '-';
+    // the run [a, next): its first output column and the first base it copies
+    const uint64_t o = V.S_all[a] - V.S_all[b0];
+    const uint64_t gaps = qrow ? V.S_d[a] - V.S_d[b0] : V.S_i[a] - V.S_i[b0];
+    const uint64_t base = o - gaps;
+    if (base >= L) return;
+    uint64_t n = L - base;                                  // the row's last run also carries the bases no op covers
+    if (next < b1) { const uint64_t rl = V.S_all[next] - V.S_all[a]; n = rl < n ? rl : n; }
+    if (!qrow) warp_copy16(row + o, V.tseq + V.X.t_src[r] + base, n, lane);
+    else if (V.R.neg[r] != 1) warp_copy16(row + o, V.qseq + V.X.q_src[r] + base, n, lane);
+    else warp_revcomp16(row + o, V.qseq + V.X.q_src[r] + (L - base), n, lane);  // base b of the row = complement of Q[L - 1 - b]
+}
+
 // one warp per CIGAR op (+ one virtual op per record for the bases left over after the last op): writes the op's
 // slice of the target row and of the query row
 __global__ void k_p2m_rows(P2mView V) {

@@ -149,7 +149,25 @@ __global__ void k_pair_names(uint64_t n_pairs, const uint64_t *__restrict__ pair
     for (uint32_t k = 0; k < n; ++k) dst[k] = (char)src[k];
 }
 
-// ordered list of '-'-strand records: (compact pair index, aligned + query_aligned) in record order
+// pairs in first-occurrence order: the host merges them front to back, so everything it reads is laid out in that order
+// here (perm = compact pair index of sorted position oi)
+__global__ void k_pair_permute(uint64_t n_pairs, const uint64_t *__restrict__ perm, const uint64_t *__restrict__ pair_first,
+                               const uint64_t *__restrict__ pair_vals, const uint64_t *__restrict__ pair_sizes,
+                               const uint32_t *__restrict__ name_len, uint64_t *__restrict__ first2, uint64_t *__restrict__ vals2,
+                               uint64_t *__restrict__ sizes2, uint32_t *__restrict__ name_len2, uint32_t *__restrict__ invperm) {
+    uint64_t oi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (oi > n_pairs) return;
+    if (oi == n_pairs) { name_len2[2 * oi] = 0; return; }
+    const uint64_t p = perm[oi];
+    first2[oi] = pair_first[p];
+    for (int i = 0; i < kPairVals; ++i) vals2[oi * kPairVals + i] = pair_vals[p * kPairVals + i];
+    for (int i = 0; i < 3; ++i) sizes2[3 * oi + i] = pair_sizes[3 * p + i];
+    name_len2[2 * oi] = name_len[2 * p];
+    name_len2[2 * oi + 1] = name_len[2 * p + 1];
+    invperm[p] = (uint32_t)oi;
+}
+
+// ordered list of '-'-strand records: (pair index in first-occurrence order, aligned + query_aligned) in record order
 __global__ void k_inv_flags(uint64_t n_rec, const uint8_t *__restrict__ neg, const uint8_t *__restrict__ skip,
                             uint32_t *__restrict__ flag) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,15 +175,15 @@ __global__ void k_inv_flags(uint64_t n_rec, const uint8_t *__restrict__ neg, con
 }
 __global__ void k_inv_gather(uint64_t n_rec, const uint32_t *__restrict__ flag, const uint64_t *__restrict__ idx,
                              const uint64_t *__restrict__ rec_slot, const uint32_t *__restrict__ slot_idx,
-                             const unsigned long long *__restrict__ cnt11, uint32_t *__restrict__ inv_pair,
-                             uint64_t *__restrict__ inv_num) {
+                             const uint32_t *__restrict__ invperm, const unsigned long long *__restrict__ cnt11,
+                             uint32_t *__restrict__ inv_pair, uint64_t *__restrict__ inv_num) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec || !flag[r]) return;
     const unsigned long long *c = cnt11 + r * 11;
     // RecStat::from (common.rs:116-140): aligned = m + x + del + inv_del; query_align = m + x + ins + inv_ins
     uint64_t aligned = c[0] + c[1] + c[5] + c[9], qal = c[0] + c[1] + c[3] + c[7];
     uint64_t o = idx[r];
-    inv_pair[o] = slot_idx[rec_slot[r]];
+    inv_pair[o] = invperm[slot_idx[rec_slot[r]]];
     inv_num[o] = aligned + qal;
 }
 

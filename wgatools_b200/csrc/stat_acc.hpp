@@ -61,6 +61,7 @@ struct wga_stat_acc {
 
     void grow_table(size_t want_rows) {
         size_t cap = table.size() ? table.size() : 1024;
+        if (want_rows < rows.size()) want_rows = rows.size();
         while (cap < 2 * want_rows + 2) cap <<= 1;
         if (cap == table.size()) return;
         table.assign(cap, 0u);

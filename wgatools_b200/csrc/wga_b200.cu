@@ -924,33 +924,39 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         if (!p_first || !p_vals || !p_sizes || !nlen || !noff || !inv_pair || !inv_num) return ctx->err_code;
         WGA_CK(cudaMemsetAsync(nlen + 2 * n_pairs, 0, 4, ctx->stream));
         LAUNCH(ctx, k_pair_gather, grid_for(cap, 256), 256, cap, flag, idx, keys, first, vals, M, p_first, p_vals, p_sizes, nlen);
-        WGA_TRY(exclusive_sum(ctx, nlen, noff, 2 * n_pairs + 1));
-        uint64_t name_total;
-        WGA_TRY(read_scalars(ctx, {noff + 2 * n_pairs}, &name_total));
-        char *nbuf = (char *)ctx->ensure(B_NAME_BUF, name_total + 1);
-        if (!nbuf) return ctx->err_code;
-        LAUNCH(ctx, k_pair_names, grid_for(2 * n_pairs, 256), 256, n_pairs, p_first, M, noff, nbuf);
-        LAUNCH(ctx, k_inv_gather, grid_for(n_rec, 256), 256, n_rec, iflag, iidx, rec_slot, idx, cnt11, inv_pair, inv_num);
-        // pairs in first-occurrence order (the reference's HashMap order is unspecified; natord sort is stable):
-        // sort (first record, pair id) on the device, read everything back through pinned scratch
+        // pairs in first-occurrence order (the reference's HashMap order is unspecified; natord sort is stable): sort
+        // (first record, pair id) on the device and lay every array out in that order, so that the host merge reads
+        // front to back
         uint64_t *ord_k = ctx->buf<uint64_t>(B_PP_A, n_pairs + 1), *ord_v = ctx->buf<uint64_t>(B_PP_B, n_pairs + 1);
         uint64_t *ord_i = ctx->buf<uint64_t>(B_PP_C, n_pairs + 1);
-        if (!ord_k || !ord_v || !ord_i) return ctx->err_code;
+        uint64_t *vals2 = ctx->buf<uint64_t>(B_PP_D, (n_pairs + 1) * kPairVals), *sizes2 = ctx->buf<uint64_t>(B_PP_E, (n_pairs + 1) * 3);
+        uint32_t *nlen2 = ctx->buf<uint32_t>(B_PP_F, 2 * n_pairs + 2), *invperm = ctx->buf<uint32_t>(B_PP_H, n_pairs + 1);
+        if (!ord_k || !ord_v || !ord_i || !vals2 || !sizes2 || !nlen2 || !invperm) return ctx->err_code;
         if (n_pairs) {
             LAUNCH(ctx, k_iota, grid_for(n_pairs, 256), 256, ord_i, n_pairs);
             WGA_TRY(sort_pairs_u64(ctx, p_first, ord_k, ord_i, ord_v, n_pairs));
         }
-        const size_t b_vals = n_pairs * kPairVals * 8, b_sizes = n_pairs * 24, b_nlen = n_pairs * 8, b_ord = n_pairs * 8;
+        LAUNCH(ctx, k_pair_permute, grid_for(n_pairs + 1, 256), 256, n_pairs, (const uint64_t *)ord_v, (const uint64_t *)p_first,
+               (const uint64_t *)p_vals, (const uint64_t *)p_sizes, (const uint32_t *)nlen, ord_i /* first2 */, vals2, sizes2, nlen2, invperm);
+        uint64_t *first2 = ord_i;
+        WGA_TRY(exclusive_sum(ctx, nlen2, noff, 2 * n_pairs + 1));
+        uint64_t name_total;
+        WGA_TRY(read_scalars(ctx, {noff + 2 * n_pairs}, &name_total));
+        char *nbuf = (char *)ctx->ensure(B_NAME_BUF, name_total + 1);
+        if (!nbuf) return ctx->err_code;
+        LAUNCH(ctx, k_pair_names, grid_for(2 * n_pairs, 256), 256, n_pairs, first2, M, noff, nbuf);
+        LAUNCH(ctx, k_inv_gather, grid_for(n_rec, 256), 256, n_rec, iflag, iidx, rec_slot, idx, (const uint32_t *)invperm, cnt11, inv_pair,
+               inv_num);
+        const size_t b_vals = n_pairs * kPairVals * 8, b_sizes = n_pairs * 24, b_nlen = n_pairs * 8;
         const size_t b_invp = (n_inv * 4 + 7) & ~(size_t)7, b_invn = n_inv * 8;
-        const size_t o_vals = 0, o_sizes = o_vals + b_vals, o_nlen = o_sizes + b_sizes, o_ord = o_nlen + b_nlen, o_invp = o_ord + b_ord,
-                     o_invn = o_invp + b_invp, o_names = o_invn + b_invn;
+        const size_t o_vals = 0, o_sizes = o_vals + b_vals, o_nlen = o_sizes + b_sizes, o_invp = o_nlen + b_nlen, o_invn = o_invp + b_invp,
+                     o_names = o_invn + b_invn;
         char *hs = (char *)ctx->ensure_host_scratch(o_names + name_total + 8);
         if (!hs) return ctx->err_code;
         if (n_pairs) {
-            WGA_CK(cudaMemcpyAsync(hs + o_vals, p_vals, b_vals, cudaMemcpyDeviceToHost, ctx->stream));
-            WGA_CK(cudaMemcpyAsync(hs + o_sizes, p_sizes, b_sizes, cudaMemcpyDeviceToHost, ctx->stream));
-            WGA_CK(cudaMemcpyAsync(hs + o_nlen, nlen, b_nlen, cudaMemcpyDeviceToHost, ctx->stream));
-            WGA_CK(cudaMemcpyAsync(hs + o_ord, ord_v, b_ord, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_vals, vals2, b_vals, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_sizes, sizes2, b_sizes, cudaMemcpyDeviceToHost, ctx->stream));
+            WGA_CK(cudaMemcpyAsync(hs + o_nlen, nlen2, b_nlen, cudaMemcpyDeviceToHost, ctx->stream));
             if (name_total) WGA_CK(cudaMemcpyAsync(hs + o_names, nbuf, name_total, cudaMemcpyDeviceToHost, ctx->stream));
         }
         if (n_inv) {
@@ -961,20 +967,19 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         lap("gather + sort + D2H");
         const uint64_t *h_vals = (const uint64_t *)(hs + o_vals), *h_sizes = (const uint64_t *)(hs + o_sizes);
         const uint32_t *h_nlen = (const uint32_t *)(hs + o_nlen);
-        const uint64_t *order = (const uint64_t *)(hs + o_ord);
         const uint32_t *h_inv_pair = (const uint32_t *)(hs + o_invp);
         const uint64_t *h_inv_num = (const uint64_t *)(hs + o_invn);
         const char *h_names = hs + o_names;
         std::vector<uint32_t> map(n_pairs);
-        std::vector<uint64_t> name_pos(2 * n_pairs + 1, 0);
-        for (uint64_t i = 0; i < 2 * n_pairs; ++i) name_pos[i + 1] = name_pos[i] + h_nlen[i];
         acc->rows.reserve(acc->rows.size() + n_pairs);
+        acc->names.reserve(acc->names.size() + name_total);
         acc->grow_table(acc->rows.size() + n_pairs);
-        for (uint64_t oi = 0; oi < n_pairs; ++oi) {  // first-occurrence order; the device's pair hash is the host table's key
-            const uint32_t p = (uint32_t)order[oi];
-            const char *rn = h_names + name_pos[2 * p], *qn = h_names + name_pos[2 * p + 1];
-            map[p] = acc->find_or_add(rn, h_nlen[2 * p], h_sizes[3 * p], qn, h_nlen[2 * p + 1], h_sizes[3 * p + 1], h_sizes[3 * p + 2]);
-            acc->add_pair_vals(map[p], &h_vals[(uint64_t)p * kPairVals]);
+        const char *nm = h_names;
+        for (uint64_t p = 0; p < n_pairs; ++p) {  // first-occurrence order; the device's pair hash is the host table's key
+            const uint32_t lr = h_nlen[2 * p], lq = h_nlen[2 * p + 1];
+            map[p] = acc->find_or_add(nm, lr, h_sizes[3 * p], nm + lr, lq, h_sizes[3 * p + 1], h_sizes[3 * p + 2]);
+            acc->add_pair_vals(map[p], &h_vals[p * kPairVals]);
+            nm += lr + lq;
         }
         const size_t i0 = acc->inv_pair.size();
         acc->inv_pair.resize(i0 + n_inv);
@@ -1507,6 +1512,33 @@ static int paf_fasta_prepare(wga_ctx *ctx, uint64_t len, const wga_fasta *TF, co
     return WGA_OK;
 }
 
+}  // extern "C"
+// row expansion of paf2maf / chain2maf: by runs between gap ops (k_p2m_runs); WGA_P2M_OPS=1 selects the per-op kernel
+static int p2m_expand_rows(wga_ctx *ctx, const P2mView &V, uint64_t n_opsT) {
+    static const bool per_op = getenv("WGA_P2M_OPS") != nullptr && getenv("WGA_P2M_OPS")[0] == '1';
+    const uint64_t n_rec = V.n_rec;
+    if (per_op) {
+        LAUNCH(ctx, k_p2m_rows, grid_for((n_opsT + n_rec) * 32, 256), 256, V);
+        return WGA_OK;
+    }
+    uint32_t *fI = ctx->buf<uint32_t>(B_XRUN_FLAG, n_opsT + 1), *fD = ctx->buf<uint32_t>(B_PP_O, n_opsT + 1);
+    uint64_t *idxI = ctx->buf<uint64_t>(B_XRUN_IDX, n_opsT + 1), *idxD = ctx->buf<uint64_t>(B_PP_P, n_opsT + 1);
+    if (!fI || !fD || !idxI || !idxD) return ctx->err_code;
+    LAUNCH(ctx, k_p2m_gap_flags, grid_for(n_opsT + 1, 256), 256, n_opsT, V.op_type, fI, fD);
+    WGA_TRY(exclusive_sum(ctx, fI, idxI, n_opsT + 1));
+    WGA_TRY(exclusive_sum(ctx, fD, idxD, n_opsT + 1));
+    uint64_t cnt[2];
+    WGA_TRY(read_scalars(ctx, {idxI + n_opsT, idxD + n_opsT}, cnt));
+    uint64_t *Ilist = ctx->buf<uint64_t>(B_XRUN_POS, cnt[0] + 1), *Dlist = ctx->buf<uint64_t>(B_PP_Q, cnt[1] + 1);
+    if (!Ilist || !Dlist) return ctx->err_code;
+    if (n_opsT)
+        LAUNCH(ctx, k_p2m_gap_lists, grid_for(n_opsT, 256), 256, n_opsT, V.op_type, (const uint64_t *)idxI, (const uint64_t *)idxD, Ilist, Dlist);
+    LAUNCH(ctx, k_p2m_runs, grid_for((cnt[0] + cnt[1] + 2 * n_rec) * 32, 256), 256, V, cnt[0], cnt[1], (const uint64_t *)idxI,
+           (const uint64_t *)Ilist, (const uint64_t *)idxD, (const uint64_t *)Dlist);
+    return WGA_OK;
+}
+
+extern "C" {
 int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
                 wga_span *out) {
     (void)flags;
@@ -1592,7 +1624,7 @@ int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     V.out = d_out;
     LAUNCH(ctx, k_p2m_blocks<1>, grid_for(n_rec + 1, 256), 256, V);
     WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    LAUNCH(ctx, k_p2m_rows, grid_for((n_opsT + n_rec) * 32, 256), 256, V);
+    WGA_TRY(p2m_expand_rows(ctx, V, n_opsT));
     WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     int rc = finish_output(ctx, d_out, total, mem, flags, out);
     if (rc) return rc;
@@ -2029,7 +2061,7 @@ int wga_chain2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
     if (!d_out) return ctx->err_code;
     V.out = d_out;
     LAUNCH(ctx, k_p2m_blocks<1>, grid_for(n_rec + 1, 256), 256, V);
-    LAUNCH(ctx, k_p2m_rows, grid_for((n_opsT + n_rec) * 32, 256), 256, V);
+    WGA_TRY(p2m_expand_rows(ctx, V, n_opsT));
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 
