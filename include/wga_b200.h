@@ -265,6 +265,16 @@ int wga_chain2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
  * first-occurrence order.  One slab = the whole PAF (coverage is a reduction over all records). */
 int wga_paf_cov(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, wga_span *out);
 
+/* ---- filter -f paf: src/tools/filter.rs:41-63 filter_paf, :92-106 filter_alignrec, :108-160 filter_paf_align_pair
+ *  ---------------------------------------------------------------------------------------------------- */
+/* min_align_size == NULL: a record is dropped when target_end - target_start < min_block_size or query_length <
+ * min_query_size.  min_align_size != NULL (`-a`, all-to-all PAF): records are grouped by (query_name, target_name), the
+ * group's summed target_end - target_start must reach *min_align_size, and the two other cut-offs are ignored
+ * (src/utils.rs:559-563).  out = the kept records re-serialised by the csv writer, in file order (the reference's
+ * par_bridge order is unspecified).  One slab = the whole PAF (the pair sums are a reduction over all records). */
+int wga_paf_filter(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, uint64_t min_block_size,
+                   uint64_t min_query_size, const uint64_t *min_align_size, wga_span *out);
+
 /* ---- validate: src/tools/validate.rs:44-147 (a free rider on the PAF CIGAR counters) ------------ */
 /* report (always host memory) = the reference's report text: counts, then "{name}:{start}-{end}" of every record whose
  * query / target end differs from start + the CIGAR's consumed bases; fix != 0: `fixed` = every record re-serialised

@@ -812,7 +812,7 @@ static int csv_parse_u64(sv s, uint64_t *out) {
 }
 
 /* paf.rs:159-218 cs_to_cigar; regex (:[0-9]+|\*[a-z][a-z]|[=\+\-][A-Za-z]+), leftmost matches */
-static void cs_to_cigar(sv cs, orc_buf *cigar) {
+static int cs_to_cigar(sv cs, orc_buf *cigar) { /* 1 = a `:N` length does not fit usize: parse().unwrap() panics (paf.rs:171) */
     char last_op = 'M';
     uint64_t last_len = 0;
     size_t i = 0;
@@ -821,8 +821,12 @@ static void cs_to_cigar(sv cs, orc_buf *cigar) {
         if (c == ':' && i + 1 < cs.n && cs.p[i + 1] >= '0' && cs.p[i + 1] <= '9') {
             size_t j = i + 1;
             uint64_t v = 0;
-            while (j < cs.n && cs.p[j] >= '0' && cs.p[j] <= '9') v = v * 10 + (uint64_t)(cs.p[j++] - '0');
-            if (last_op == 'M') last_len += v;
+            while (j < cs.n && cs.p[j] >= '0' && cs.p[j] <= '9') {
+                const uint64_t d = (uint64_t)(cs.p[j++] - '0');
+                if (v > (UINT64_MAX - d) / 10) return 1;
+                v = v * 10 + d;
+            }
+            if (last_op == 'M') last_len += v; /* release build: wrapping add */
             else {
                 if (last_len > 0) { buf_putu(cigar, last_len); buf_putc(cigar, last_op); }
                 last_op = 'M';
@@ -856,6 +860,36 @@ static void cs_to_cigar(sv cs, orc_buf *cigar) {
         }
     }
     if (last_len > 0) { buf_putu(cigar, last_len); buf_putc(cigar, last_op); }
+    return 0;
+}
+
+/* paf.rs:122-140 get_cigar_string: the first cg:Z: tag, else the first cs:Z: tag converted (text after "cg:Z:").
+ * 1 = found, 0 = CigarTagNotFound, -1 = the conversion panics */
+static int paf_get_cigar(const pafrow *row, orc_buf *conv, sv *cg) {
+    for (size_t k = 12; k < row->n; k++)
+        if (row->f[k].n >= 5 && memcmp(row->f[k].p, "cg:Z:", 5) == 0) {
+            cg->p = row->f[k].p + 5; cg->n = row->f[k].n - 5;
+            return 1;
+        }
+    for (size_t k = 12; k < row->n; k++)
+        if (row->f[k].n >= 5 && memcmp(row->f[k].p, "cs:Z:", 5) == 0) {
+            sv cs = {row->f[k].p + 5, row->f[k].n - 5};
+            conv->n = 0;
+            buf_reserve(conv, 1);
+            if (cs_to_cigar(cs, conv)) return -1;
+            cg->p = conv->p; cg->n = conv->n;
+            return 1;
+        }
+    return 0;
+}
+#define CS_PANIC_MSG "panic: called `Result::unwrap()` on an `Err` value: ParseIntError { kind: PosOverflow }"
+
+/* test hook: the bare conversion (text after "cs:Z:" -> text after "cg:Z:") */
+int orc_cs_to_cigar(const char *cs, size_t n, orc_buf *out, char *err, size_t errcap) {
+    sv v = {cs, n};
+    buf_reserve(out, 1);
+    if (cs_to_cigar(v, out)) { set_err(err, errcap, CS_PANIC_MSG); return ORC_E_PANIC; }
+    return ORC_OK;
 }
 
 /* stat.rs:87-105 stat_paf */
@@ -891,19 +925,8 @@ int orc_stat_paf(const char *text, size_t len, int each, orc_buf *out, char *err
         }
         /* paf.rs:122-140 get_cigar_string */
         sv cg = {0, 0};
-        int have = 0;
-        for (size_t k = 12; k < row.n && !have; k++)
-            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) {
-                cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1;
-            }
-        if (!have)
-            for (size_t k = 12; k < row.n && !have; k++)
-                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
-                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
-                    conv.n = 0;
-                    cs_to_cigar(cs, &conv);
-                    cg.p = conv.p; cg.n = conv.n; have = 1;
-                }
+        const int have = paf_get_cigar(&row, &conv, &cg);
+        if (have < 0) { set_err(err, errcap, CS_PANIC_MSG); rc = ORC_E_PANIC; break; }
         if (!have) {
             set_err(err, errcap, "CIGAR start tag not found");
             rc = ORC_E_CIGAR_TAG_NOT_FOUND;
@@ -1468,7 +1491,7 @@ int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_l
     buf_putc(out, '\n');
     size_t pos = 0;
     pafrow row = {0};
-    orc_buf ts = {0}, qs = {0};
+    orc_buf ts = {0}, qs = {0}, conv = {0};
     int rc = ORC_OK;
     while (rc == ORC_OK && paf_next(paf, paf_len, &pos, &row)) {
         uint64_t u[12] = {0};
@@ -1492,9 +1515,9 @@ int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_l
             if (c) { set_err(err, errcap, "Invalid Base: `%c`", c); rc = ORC_E_VCF_BASE; break; }
         }
         /* cigar.rs:492-551 parse_cigar_to_insert */
-        sv cg = {0, 0}; int have = 0;
-        for (size_t k = 12; k < row.n && !have; k++)
-            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
+        sv cg = {0, 0};
+        const int have = paf_get_cigar(&row, &conv, &cg);
+        if (have < 0) { set_err(err, errcap, CS_PANIC_MSG); rc = ORC_E_PANIC; break; }
         if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
         if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
         uint64_t off = 0;
@@ -1527,7 +1550,7 @@ int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_l
         buf_putc(out, '\n');
     }
     free(row.f); free(row.scratch); free(tf.e); free(qf.e);
-    orc_buf_free(&ts); orc_buf_free(&qs);
+    orc_buf_free(&ts); orc_buf_free(&qs); orc_buf_free(&conv);
     return rc;
 }
 
@@ -1580,17 +1603,8 @@ int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_
         }
         /* paf.rs:122-140 get_cigar_string */
         sv cg = {0, 0};
-        int have = 0;
-        for (size_t k = 12; k < row.n && !have; k++)
-            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
-        if (!have)
-            for (size_t k = 12; k < row.n && !have; k++)
-                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
-                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
-                    conv.n = 0;
-                    cs_to_cigar(cs, &conv);
-                    cg.p = conv.p; cg.n = conv.n; have = 1;
-                }
+        const int have = paf_get_cigar(&row, &conv, &cg);
+        if (have < 0) { set_err(err, errcap, CS_PANIC_MSG); rc = ORC_E_PANIC; break; }
         if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
         if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
         uint64_t t_pos = t_st, q_pos = q_st;
@@ -1673,15 +1687,22 @@ int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_
  * out = the files' bytes concatenated in target order; index = one line "{target}\t{bytes}\n" per file
  * ({out_dir}/{target}.maf).  On error nothing is returned (the reference may leave other targets' files behind). */
 typedef struct {
-    sv qname, tname, cg;
+    sv qname, tname, cg, cs;
     uint64_t q_size, q_st, q_en, t_size, t_st, t_en;
-    int neg, have_cg;
+    int neg, have_cg, have_cs;
 } pprec;
 
 static int pp_project(const pprec *r, orc_buf *q, int base, char *err, size_t errcap) {
     /* cigar.rs:744-804 */
-    if (!r->have_cg) { set_err(err, errcap, "CIGAR start tag not found"); return ORC_E_CIGAR_TAG_NOT_FOUND; }
+    static __thread orc_buf conv; /* the converted cs:Z: of this record (paf.rs:129-135), reused between calls */
     sv cg = r->cg;
+    if (!r->have_cg) {
+        if (!r->have_cs) { set_err(err, errcap, "CIGAR start tag not found"); return ORC_E_CIGAR_TAG_NOT_FOUND; }
+        conv.n = 0;
+        buf_reserve(&conv, 1);
+        if (cs_to_cigar(r->cs, &conv)) { set_err(err, errcap, CS_PANIC_MSG); return ORC_E_PANIC; }
+        cg.p = conv.p; cg.n = conv.n;
+    }
     if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); return ORC_E_PANIC; }
     uint64_t off = 0;
     size_t i = 0;
@@ -1745,10 +1766,11 @@ int orc_paf_pseudo(const char *paf, size_t paf_len, const char *fa, size_t fa_le
         pprec *r = &recs[n++];
         r->qname = row.f[0]; r->tname = row.f[5];
         r->q_size = u[1]; r->q_st = u[2]; r->q_en = u[3]; r->t_size = u[6]; r->t_st = u[7]; r->t_en = u[8];
-        r->neg = neg; r->have_cg = 0; r->cg.p = NULL; r->cg.n = 0;
+        r->neg = neg; r->have_cg = 0; r->cg.p = NULL; r->cg.n = 0; r->have_cs = 0; r->cs.p = NULL; r->cs.n = 0;
         for (size_t k = 12; k < row.n && !r->have_cg; k++)
             if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { r->cg.p = row.f[k].p + 5; r->cg.n = row.f[k].n - 5; r->have_cg = 1; }
-        /* cs:Z: conversion is not restated for this command (the CUDA path reports it as unsupported) */
+        for (size_t k = 12; k < row.n && !r->have_cg && !r->have_cs; k++)
+            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) { r->cs.p = row.f[k].p + 5; r->cs.n = row.f[k].n - 5; r->have_cs = 1; }
     }
     uint8_t *done = (uint8_t *)calloc(n ? n : 1, 1);
     size_t *grp = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
@@ -1864,17 +1886,8 @@ int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc
         if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
         total++;
         sv cg = {0, 0};
-        int have = 0;
-        for (size_t k = 12; k < row.n && !have; k++)
-            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
-        if (!have)
-            for (size_t k = 12; k < row.n && !have; k++)
-                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
-                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
-                    conv.n = 0;
-                    cs_to_cigar(cs, &conv);
-                    cg.p = conv.p; cg.n = conv.n; have = 1;
-                }
+        const int have = paf_get_cigar(&row, &conv, &cg);
+        if (have < 0) { set_err(err, errcap, CS_PANIC_MSG); rc = ORC_E_PANIC; break; }
         orc_counts c;
         char dis[256];
         if (!have || orc_parse_paf_cigar(cg.p, cg.n, neg, &c, dis, sizeof dis)) {
@@ -1915,6 +1928,69 @@ int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc
     } else fixed->n = 0;
     free(row.f); free(row.scratch);
     orc_buf_free(&ql); orc_buf_free(&tl); orc_buf_free(&conv);
+    return rc;
+}
+
+
+/* -------------------------------------------------------------------- filter -f paf */
+/* src/tools/filter.rs:41-63 filter_paf + :92-106 filter_alignrec; :108-160 filter_paf_align_pair (have_align != 0: the
+ * per-(query_name, target_name) sum of target_end - target_start must reach min_align; -b / -q are ignored then,
+ * src/utils.rs:559-563).  Records come out in file order (the reference's par_bridge order is unspecified); the kept
+ * records go through the csv writer.  u64 arithmetic wraps like release Rust.  filter_paf streams (rows before a bad
+ * record are already written); nothing is returned on error here. */
+int orc_paf_filter(const char *text, size_t len, uint64_t min_block, uint64_t min_query, int have_align, uint64_t min_align,
+                   orc_buf *out, char *err, size_t errcap) {
+    typedef struct { sv q, t; uint64_t sum; } fpair;
+    fpair *pairs = NULL;
+    size_t np = 0, capp = 0;
+    int rc = ORC_OK;
+    for (int pass = 0; pass < 2 && rc == ORC_OK; pass++) {
+        size_t pos = 0;
+        pafrow row = {0};
+        while (paf_next(text, len, &pos, &row)) {
+            uint64_t u[12] = {0};
+            int neg = 0, bad = row.n < 12;
+            for (int k = 0; k < 12 && !bad; k++) {
+                if (k == 0 || k == 5) continue;
+                if (k == 4) { if (sv_eq_c(row.f[4], "+")) neg = 0; else if (sv_eq_c(row.f[4], "-")) neg = 1; else bad = 1; continue; }
+                if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+            }
+            if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+            const uint64_t block = u[8] - u[7];
+            int keep;
+            if (have_align) {
+                size_t i = 0;
+                while (i < np && !(sv_eq(pairs[i].q, row.f[0]) && sv_eq(pairs[i].t, row.f[5]))) i++;
+                if (pass == 0) {
+                    if (i == np) {
+                        if (np == capp) { capp = capp ? capp * 2 : 64; pairs = (fpair *)realloc(pairs, capp * sizeof(fpair)); }
+                        char *cq = (char *)malloc(row.f[0].n + 1), *ct = (char *)malloc(row.f[5].n + 1); /* quoted names live in row scratch */
+                        memcpy(cq, row.f[0].p, row.f[0].n); memcpy(ct, row.f[5].p, row.f[5].n);
+                        pairs[np].q.p = cq; pairs[np].q.n = row.f[0].n; pairs[np].t.p = ct; pairs[np].t.n = row.f[5].n;
+                        pairs[np].sum = 0; np++;
+                    }
+                    pairs[i].sum += block;
+                    continue;
+                }
+                keep = pairs[i].sum >= min_align;
+            } else {
+                if (pass == 0) break; /* one pass is enough */
+                keep = !((block < min_block) | (u[1] < min_query));
+            }
+            if (keep) {
+                csv_field(out, row.f[0], 1); csv_u64(out, u[1], 0); csv_u64(out, u[2], 0); csv_u64(out, u[3], 0);
+                buf_putc(out, '\t'); buf_putc(out, neg ? '-' : '+');
+                csv_field(out, row.f[5], 0); csv_u64(out, u[6], 0); csv_u64(out, u[7], 0); csv_u64(out, u[8], 0);
+                csv_u64(out, u[9], 0); csv_u64(out, u[10], 0); csv_u64(out, u[11], 0);
+                for (size_t k = 12; k < row.n; k++) csv_field(out, row.f[k], 0);
+                buf_putc(out, '\n');
+            }
+        }
+        free(row.f); free(row.scratch);
+    }
+    if (rc != ORC_OK) out->n = 0;
+    for (size_t i = 0; i < np; i++) { free((void *)pairs[i].q.p); free((void *)pairs[i].t.p); }
+    free(pairs);
     return rc;
 }
 
@@ -2019,17 +2095,8 @@ int orc_paf2chain(const char *text, size_t len, orc_buf *out, char *err, size_t 
         }
         if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
         sv cg = {0, 0};
-        int have = 0;
-        for (size_t k = 12; k < row.n && !have; k++)
-            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
-        if (!have)
-            for (size_t k = 12; k < row.n && !have; k++)
-                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
-                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
-                    conv.n = 0;
-                    cs_to_cigar(cs, &conv);
-                    cg.p = conv.p; cg.n = conv.n; have = 1;
-                }
+        const int have = paf_get_cigar(&row, &conv, &cg);
+        if (have < 0) { set_err(err, errcap, CS_PANIC_MSG); rc = ORC_E_PANIC; break; }
         if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
         if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
         /* cigar.rs:202-245 parse_cigar_to_trim: the closure's Result is discarded (a bad token just ends the trim) */
@@ -2106,17 +2173,8 @@ int orc_pafcov(const char *text, size_t len, orc_buf *out, char *err, size_t err
             nt++;
         }
         sv cg = {0, 0};
-        int have = 0;
-        for (size_t k = 12; k < row.n && !have; k++)
-            if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cg:Z:", 5) == 0) { cg.p = row.f[k].p + 5; cg.n = row.f[k].n - 5; have = 1; }
-        if (!have)
-            for (size_t k = 12; k < row.n && !have; k++)
-                if (row.f[k].n >= 5 && memcmp(row.f[k].p, "cs:Z:", 5) == 0) {
-                    sv cs = {row.f[k].p + 5, row.f[k].n - 5};
-                    conv.n = 0;
-                    cs_to_cigar(cs, &conv);
-                    cg.p = conv.p; cg.n = conv.n; have = 1;
-                }
+        const int have = paf_get_cigar(&row, &conv, &cg);
+        if (have < 0) { set_err(err, errcap, CS_PANIC_MSG); rc = ORC_E_PANIC; break; }
         if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
         if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
         uint64_t p = u[7];

@@ -75,6 +75,13 @@ int orc_maf2paf(const char *text, size_t len, const char *query_name, orc_buf *o
  * nondeterministic within equal ref_name -- SURVEY Q8). */
 int orc_stat_maf(const char *text, size_t len, int each, const char *query_name,
                  orc_buf *out, char *err, size_t errcap);
+/* filter.rs:41-63,92-160: filter -f paf [-b -q | -a] */
+int orc_paf_filter(const char *text, size_t len, uint64_t min_block, uint64_t min_query, int have_align, uint64_t min_align,
+                   orc_buf *out, char *err, size_t errcap);
+
+/* paf.rs:159-218 cs_to_cigar alone (test hook) */
+int orc_cs_to_cigar(const char *cs, size_t n, orc_buf *out, char *err, size_t errcap);
+
 int orc_stat_paf(const char *text, size_t len, int each, orc_buf *out,
                  char *err, size_t errcap);
 

@@ -47,6 +47,9 @@ def lib():
                                    ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_stat_paf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                    ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_paf_filter.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64,
+                                     ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_cs_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_call_maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64,
                                    ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
@@ -123,6 +126,14 @@ def stat_maf_mt(text: bytes, threads, each=False, query_name=None) -> bytes:
 
 def stat_paf(text: bytes, each=False) -> bytes:
     return _run(lib().orc_stat_paf, text, len(text), int(each))
+
+
+def paf_filter(text: bytes, min_block=0, min_query=0, min_align=None) -> bytes:
+    return _run(lib().orc_paf_filter, text, len(text), min_block, min_query, int(min_align is not None), min_align or 0)
+
+
+def cs_to_cigar(cs: bytes) -> bytes:
+    return _run(lib().orc_cs_to_cigar, cs, len(cs))
 
 
 def call_maf(text: bytes, snp=False, inv=False, svlen=50, sample="sample", query_name=None,

@@ -96,6 +96,40 @@ def cigar_tokens(cg):  # cigar.rs:43-75: digits* then non-digits*; None when a t
     return out
 
 
+_CS = re.compile(r"(:[0-9]+|\*[a-z][a-z]|[=\+\-][A-Za-z]+)")  # the reference's own regex, paf.rs:165
+
+
+def cs_to_cigar(cs):  # paf.rs:159-218; None = a `:N` beyond usize (parse().unwrap() panics)
+    out, last_op, last_len = [], "M", 0
+    for part in _CS.findall(cs):
+        k = part[0]
+        if k == ":":
+            n = int(part[1:])
+            if n >= 2 ** 64:
+                return None
+            if last_op == "M":
+                last_len = (last_len + n) % 2 ** 64
+            else:
+                if last_len:
+                    out.append(f"{last_len}{last_op}")
+                last_op, last_len = "M", n
+        elif k in "-+":
+            if last_len:
+                out.append(f"{last_len}{last_op}")
+            out.append(f"{len(part) - 1}{'D' if k == '-' else 'I'}")
+            last_op, last_len = "M", 0
+        elif k == "*":
+            if last_op == "X":
+                last_len += 1
+            else:
+                if last_len:
+                    out.append(f"{last_len}{last_op}")
+                last_op, last_len = "X", 1
+    if last_len:
+        out.append(f"{last_len}{last_op}")
+    return "".join(out)
+
+
 def paf_counts(cg, neg):  # cigar.rs:629-707
     c = [0] * 11
     if neg:

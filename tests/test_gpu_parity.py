@@ -4,6 +4,7 @@ import ctypes
 import io
 import os
 import random
+import re
 
 import numpy as np
 import pytest
@@ -1156,3 +1157,125 @@ def test_pafcov_parity(w, ctx):
         assert eo.value.code == code == eg.value.code
         if code in (1, 5, 6):
             assert str(eg.value) == eo.value.msg
+
+
+# ---------------------------------------------------------------- cs:Z: standing in for cg:Z: (row a7, paf.rs:122-140,159-218)
+def _cg_to_cs(rng, cg, noise=True):
+    """a cs:Z: spelling whose conversion gives the ops of `cg` back (M/= -> `:N` pieces, X -> `*xy` runs, I/D -> +seq / -seq),
+    sprinkled with the things cs_to_cigar skips or ignores"""
+    import re as _re
+    out = []
+    for n, op in _re.findall(rb"(\d+)([M=XID])", cg):
+        n = int(n)
+        if op in b"M=":
+            a = rng.randrange(0, n + 1) if n > 1 and rng.random() < 0.5 else n
+            out.append(b":%d" % a)
+            if a != n:
+                out.append(b":%0*d" % (rng.randrange(1, 4), n - a))
+        elif op == b"X":
+            out.append(b"".join(b"*" + bytes(rng.choice(b"acgt") for _ in range(2)) for _ in range(n)))
+        else:
+            out.append((b"+" if op == b"I" else b"-") + bytes(rng.choice(b"acgtACGTn") for _ in range(n)))
+        if noise and rng.random() < 0.15:
+            out.append(rng.choice([b"=ACGT", b"~", b"*AT", b":", b" ", b"=a", b"*a"]))
+    return b"".join(out)
+
+
+def _cs_paf(rng, paf, frac=0.7):
+    lines = []
+    for l in paf.splitlines(keepends=True):
+        f = l.rstrip(b"\n").split(b"\t")
+        if len(f) > 12 and rng.random() < frac:
+            for k in range(12, len(f)):
+                if f[k].startswith(b"cg:Z:") and not re.search(rb"(^|\D)0+[MIDX=]", f[k][5:]):
+                    f[k] = b"cs:Z:" + _cg_to_cs(rng, f[k][5:])
+                    if rng.random() < 0.3:
+                        f.append(b"cs:Z::999")       # only the FIRST cs:Z: tag counts
+                    break
+        lines.append(b"\t".join(f) + b"\n")
+    return b"".join(lines)
+
+
+def test_cs_tag_all_paf_commands(w, ctx):
+    rng = random.Random(4242)
+    # stat / paf2chain / pafcov / validate over the synthetic config-4 shape, most records re-spelled with cs:Z:
+    for seed, kw in ((1, {}), (3, dict(ops_median=1500.0, ops_sigma=1.0))):
+        text = _cs_paf(rng, bs.gen_paf(bs.paf_params(800 if seed == 1 else 120, seed=seed, **kw)))
+        assert text.count(b"cs:Z:") > 50
+        check_paf(w, ctx, text)
+        assert w.run_bytes(w.paf2chain, w.PAFReader(text), ctx=ctx) == orc.paf2chain(text)
+        assert _validate(w, ctx, text) == orc.paf_validate(text, True)
+    small = _cs_paf(rng, bs.gen_paf(bs.paf_params(200, seed=9, ops_median=30.0, chr_size=30_000, n_genomes=2, n_chr=2)))
+    assert w.run_bytes(w.pafcov, w.PAFReader(small), ctx=ctx) == orc.pafcov(small)
+    # the FASTA commands
+    for it in range(3):
+        case = make_paf2maf_case(rng, n_rec=60, soft=it % 2 == 0)
+        paf = _cs_paf(rng, case[0])
+        assert paf.count(b"cs:Z:") > 10
+        assert p2m(w, ctx, paf, *case[1:]) == orc.paf2maf(paf, *case[1:])
+        assert cpaf(w, ctx, paf, *case[1:], snp=True, svlen=0, sample="s") == orc.call_paf(paf, *case[1:], snp=True, svlen=0, sample="s")
+        pp = _dedupe_starts(paf)
+        fa = case[1] + case[3]
+        fai = orc.make_fai(fa)
+        want = orc.paf_pseudo(pp, fa, fai)
+        got = w.pseudo_maf_files(w.PAFReader(pp), w.Fasta(ctx, fa, fai), ctx=ctx)
+        assert list(got) == list(want) and all(got[k] == want[k] for k in want)
+    # quirks and the two panics
+    base = b"q\t100\t0\t12\t+\tt\t100\t0\t13\t1\t2\t60\t"
+    ok = [base + b"cs:Z::6-a*ac+tt:3\n", base + b"tp:A:P\tcs:Z:=ACGT:3*AT*at~~:*ga-N+nn:0:0\n",
+          base + b"cs:Z::3\tcg:Z:7=\n",                          # cg:Z: wins wherever it stands
+          base + b"cs:Z::18446744073709551615\n", base + b"cs:Z::6\n" + base.replace(b"+", b"-") + b"cs:Z:*ac*ac:2-acgt\n"]
+    for t in ok:
+        check_paf(w, ctx, t)
+    for t, code in [(base + b"cs:Z:junk\tcs:Z::6\n", 8), (base + b"cs:Z:\n", 8), (base + b"cs:Z::18446744073709551616\n", 8),
+                    (base + b"cs:Z::5\n" + base + b"cs:Z::99999999999999999999999\n" + base + b"\n", 8)]:
+        with pytest.raises(orc.OracleError) as eo:
+            orc.stat_paf(t)
+        with pytest.raises(w.WGAError) as eg:
+            statp(w, ctx, t)
+        assert eo.value.code == code == eg.value.code, (t, eo.value.code, eg.value.code)
+
+
+# ---------------------------------------------------------------- filter -f paf (8(f) item 3, filter.rs:41-63,92-160)
+def test_paf_filter_parity(w, ctx):
+    flt = lambda t, b=0, q=0: w.run_bytes(w.filter_paf, w.PAFReader(t), b, q, ctx=ctx)
+    fla = lambda t, a: w.run_bytes(w.filter_paf_align_pair, w.PAFReader(t), a, ctx=ctx)
+    assert flt(TEST_PAF) == orc.paf_filter(TEST_PAF) == TEST_PAF
+    assert fla(TEST_PAF, 0) == TEST_PAF and fla(b"", 5) == b"" and flt(b"#only a comment\n") == b""
+    rng = random.Random(31)
+    for seed, kw in ((1, {}), (4, dict(ops_median=3.0, ops_sigma=0.8, n_genomes=3, n_chr=2)), (5, dict(n_genomes=2, n_chr=1))):
+        text = bs.gen_paf(bs.paf_params(3000, seed=seed, **kw))
+        lines = text.splitlines(keepends=True)
+        for i in rng.sample(range(len(lines)), len(lines) // 10):       # awkward tags, csv hex ints, a wrapping span
+            f = lines[i].rstrip(b"\n").split(b"\t")
+            which = rng.randrange(4)
+            if which == 0:
+                f.insert(12, b'zz:Z:say "hi"')
+            elif which == 1:
+                f[8] = b"0x%x" % int(f[8])
+            elif which == 2:
+                f[7], f[8] = f[8], f[7]
+            else:
+                f = f[:12]
+            lines[i] = b"\t".join(f) + b"\n"
+        text = b"#c\n" + b"".join(lines)
+        spans = sorted(int(l.split(b"\t")[8], 0) - int(l.split(b"\t")[7], 0) for l in lines)
+        for b, q in ((0, 0), (spans[len(spans) // 2], 0), (0, 250000001), (spans[len(spans) // 4], 1000)):
+            want = orc.paf_filter(text, b, q)
+            assert flt(text, b, q) == want
+        sums = {}
+        for l in lines:
+            f = l.split(b"\t")
+            sums[(f[0], f[5])] = (sums.get((f[0], f[5]), 0) + int(f[8], 0) - int(f[7], 0)) % 2 ** 64
+        cuts = sorted(sums.values())
+        for a in (0, cuts[len(cuts) // 2], cuts[-1], cuts[-1] + 1, 2 ** 64 - 1):
+            want = orc.paf_filter(text, min_align=a)
+            assert fla(text, a) == want, (seed, a)
+        assert 0 < orc.paf_filter(text, min_align=cuts[len(cuts) // 2]).count(b"\n") < len(lines)
+    for bad, code in ((b"q\t1\t2\n", 9), (TEST_PAF + b"a\tb\tc\td\t+\tt\t1\t2\t3\t4\t5\t6\n", 9)):
+        for a in (None, 3):
+            with pytest.raises(orc.OracleError) as eo:
+                orc.paf_filter(bad, min_align=a)
+            with pytest.raises(w.WGAError) as eg:
+                fla(bad, a) if a is not None else flt(bad)
+            assert eo.value.code == code == eg.value.code

@@ -537,3 +537,60 @@ def test_call_paf_vs_pyspec(data):
         with pytest.raises(orc.OracleError) as e:
             orc.call_paf(paf, tfa, orc.make_fai(tfa), qfa, orc.make_fai(qfa), snp=snp, svlen=svlen)
         assert e.value.code == err
+
+
+# ---------------------------------------------------------------- cs:Z: -> CIGAR (row a7, paf.rs:159-218)
+def test_cs_to_cigar_reference_doc_example():
+    """the worked example of the reference's own doc comment (paf.rs:156-158) -- a reference-held vector"""
+    assert orc.cs_to_cigar(b":6-ata:10+gtc:4*at*tg:3") == b"6M3D10M3I4M2X3M"
+    assert pyspec.cs_to_cigar(":6-ata:10+gtc:4*at*tg:3") == "6M3D10M3I4M2X3M"
+    # quirks: `=ACGT` is matched but ignored, garbage is skipped, upper-case `*AT` is no token, `:` needs digits
+    assert orc.cs_to_cigar(b"=ACGT:3*AT*at~~:*ga-N+nn:0:0") == b"3M2X1D2I"
+    assert orc.cs_to_cigar(b"") == b"" and orc.cs_to_cigar(b"=ACGT") == b""
+    with pytest.raises(orc.OracleError) as e:
+        orc.cs_to_cigar(b":18446744073709551616")
+    assert e.value.code == 8
+    assert orc.cs_to_cigar(b":18446744073709551615") == b"18446744073709551615M"
+    line = b"q\t100\t0\t12\t+\tt\t100\t0\t13\t1\t2\t60\ttp:A:P\tcs:Z:junk\tcs:Z::6-a*ac+tt:3\n"
+    with pytest.raises(orc.OracleError) as e:   # the FIRST cs tag is taken: "junk" -> "" -> the empty-CIGAR panic
+        orc.stat_paf(line)
+    assert e.value.code == 8
+    line2 = line.replace(b"cs:Z:junk\t", b"")
+    assert orc.stat_paf(line2) == orc.stat_paf(line2.replace(b"cs:Z::6-a*ac+tt:3", b"cg:Z:6M1D1X2I3M"))
+    assert orc.stat_paf(line2.replace(b"tp:A:P", b"cg:Z:9=")) == orc.stat_paf(line2.replace(b"cs:Z::6-a*ac+tt:3", b"cg:Z:9="))
+
+
+@settings(max_examples=500, deadline=None, derandomize=True)
+@given(st.text(alphabet=":*=+-0123459acgtnACGTZ~ é", max_size=60))
+def test_cs_to_cigar_vs_pyspec(cs):
+    want = pyspec.cs_to_cigar(cs)
+    if want is None:
+        with pytest.raises(orc.OracleError):
+            orc.cs_to_cigar(cs.encode())
+    else:
+        assert orc.cs_to_cigar(cs.encode()).decode() == want
+
+
+# ---------------------------------------------------------------- filter -f paf (8(f) item 3, filter.rs:41-63,92-160)
+def test_paf_filter_hand_derived():
+    paf = open(os.path.join(G, "ref_testdotplot.paf"), "rb").read()
+    rows = paf.splitlines(keepends=True)
+    assert orc.paf_filter(paf) == paf                                   # nothing to drop, csv round trip is the identity here
+    # records of test/testdotplot.paf: target spans and query lengths by hand
+    spans = [int(r.split(b"\t")[8]) - int(r.split(b"\t")[7]) for r in rows]
+    qlens = [int(r.split(b"\t")[1]) for r in rows]
+    for b, q in ((0, 0), (max(spans), 0), (max(spans) + 1, 0), (0, max(qlens) + 1), (min(spans) + 1, min(qlens))):
+        want = b"".join(r for r, s_, l in zip(rows, spans, qlens) if not (s_ < b or l < q))
+        assert orc.paf_filter(paf, b, q) == want
+    # -a: pair sums over the whole file, -b/-q ignored
+    def line(q, t, ts, te, extra=b""):
+        return b"\t".join([q, b"100", b"0", b"10", b"+", t, b"200", b"%d" % ts, b"%d" % te, b"5", b"10", b"60"]) + extra + b"\n"
+    f = line(b"a", b"x", 0, 10) + line(b"b", b"x", 0, 30) + b"#c\n" + line(b"a", b"x", 50, 65, b"\tcg:Z:15=\tzz:Z:say \"hi\"") + \
+        line(b"a", b"y", 0, 24) + line(b"b", b"x", 5, 4)                # the last one wraps: 2^64 - 1 added to (b, x)
+    got = orc.paf_filter(f, min_align=25)
+    assert got == line(b"a", b"x", 0, 10) + line(b"b", b"x", 0, 30) + line(b"a", b"x", 50, 65, b"\tcg:Z:15=\t\"zz:Z:say \"\"hi\"\"\"") + line(b"b", b"x", 5, 4)
+    assert orc.paf_filter(f, min_align=26) == line(b"b", b"x", 0, 30) + line(b"b", b"x", 5, 4)
+    assert orc.paf_filter(f, 1000, 1000, min_align=0) == orc.paf_filter(f)
+    with pytest.raises(orc.OracleError) as e:
+        orc.paf_filter(f + b"q\t1\n", min_align=0)
+    assert e.value.code == 9

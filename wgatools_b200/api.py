@@ -568,6 +568,28 @@ def pafcov(reader: PAFReader, writer, ctx=None):
         writer.write(ctypes.string_at(sp.data, sp.len))
 
 
+def _paf_filter(reader, writer, min_block_size, min_query_size, min_align_size, ctx):
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(reader.data)
+    sp = Span()
+    cut = None if min_align_size is None else ctypes.byref(ctypes.c_uint64(min_align_size))
+    ctx._check(ctx.L.wga_paf_filter(ctx.h, ctypes.c_void_p(base), len(reader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, min_block_size,
+                                    min_query_size, cut, ctypes.byref(sp)))
+    if sp.len:
+        writer.write(ctypes.string_at(sp.data, sp.len))
+
+
+def filter_paf(reader: PAFReader, writer, min_block_size, min_query_size, ctx=None):
+    """src/tools/filter.rs:41-63: drop records with target_end - target_start < min_block_size or query_length < min_query_size"""
+    _paf_filter(reader, writer, min_block_size, min_query_size, None, ctx)
+
+
+def filter_paf_align_pair(reader: PAFReader, writer, filt_align_size, ctx=None):
+    """src/tools/filter.rs:108-160 (`filter -f paf -a`): keep the records of (query, target) pairs whose summed
+    target_end - target_start reaches filt_align_size"""
+    _paf_filter(reader, writer, 0, 0, filt_align_size, ctx)
+
+
 def parallel_validatepaf(reader: PAFReader, writer, fix_writer=None, fix_flag=None, ctx=None):
     """src/tools/validate.rs:44-71: report -> writer; with a fix_writer the corrected records -> fix_writer"""
     ctx = ctx or default_context()

@@ -8,7 +8,10 @@
 // The delimiter index ('\t', '\n') reuses the single-pass slot scan of tokenize.cuh with a PAF byte class.
 // CIGAR text is walked one record per thread with 16-byte loads (records are short -- a few hundred ops --
 // and the per-op work, a decimal parse, dominates; see DESIGN.md for the bound).
-// Not supported (reported, never silently wrong): quoted csv fields, a lone '\r' as record terminator, cs:Z:.
+// A record without cg:Z: but with a cs:Z: tag gets its CIGAR from k_cs_convert (paf.rs:159-218 cs_to_cigar), written to a
+// device arena; cig_off then points there (as a wrapped 64-bit distance from the slab text, so every consumer's
+// `text + cig_off` keeps working).
+// Not supported (reported, never silently wrong): quoted csv fields, a lone '\r' as record terminator.
 #pragma once
 #include "ctx.cuh"
 #include "stat.cuh"
@@ -61,8 +64,10 @@ __device__ __forceinline__ void paf_report(unsigned long long *err_key, uint64_t
 
 // one PAF line -> 12 typed columns + cg:Z: span (paf.rs:48-65,122-140)
 // tag_key: where a missing cg:Z: tag is reported (== err_key for commands that look every record's CIGAR up in file order)
+// cs_total: summed length of the cs:Z: tags that stand in for a missing cg:Z: (arena bound for k_cs_convert)
 __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, const uint32_t *__restrict__ rec_scan,
-                            PafRecs R, unsigned long long *err_key, unsigned long long *tag_key) {
+                            PafRecs R, unsigned long long *err_key, unsigned long long *tag_key,
+                            unsigned long long *cs_total) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= lv.n_lines || !flags[k]) return;
     const uint64_t r = rec_scan[k];
@@ -77,7 +82,7 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
     uint64_t v[12];
     uint8_t neg = 0;
     int code = 0;
-    uint64_t cg_off = 0, cg_len = 0;
+    uint64_t cg_off = 0, cg_len = 0, cs_off = 0, cs_len = 0;
     bool have_cg = false, have_cs = false, quoted = false;
     uint64_t nf = 0;
     for (;; ++nf) {
@@ -96,7 +101,7 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
             } else if (!csv_u64(f, fl, &v[nf])) { if (!code) code = WGA_E_CSV; }
         } else if (!have_cg && fl >= 5 && f[0] == 'c' && f[2] == ':' && f[3] == 'Z' && f[4] == ':') {
             if (f[1] == 'g') { have_cg = true; cg_off = fb + 5; cg_len = fl - 5; }
-            else if (f[1] == 's') have_cs = true;
+            else if (f[1] == 's' && !have_cs) { have_cs = true; cs_off = fb + 5; cs_len = fl - 5; }  // the FIRST cs:Z: tag
         }
         if (w >= whi) { ++nf; break; }
         fb = fe + 1;
@@ -113,14 +118,85 @@ __global__ void k_paf_parse(LineView lv, const uint8_t *__restrict__ flags, cons
     R.q_size[r] = v[1]; R.q_start[r] = v[2];
     R.t_size[r] = v[6]; R.t_start[r] = v[7];
     R.neg[r] = neg;
-    if (!have_cg) {  // cs:Z: conversion (paf.rs:159-218) is not accelerated; no tag at all is the reference's error
-        paf_report(tag_key, r, 0x800000, have_cs ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
-        cg_len = 0;
-        cg_off = 0;
+    if (!have_cg) {  // no tag at all is the reference's error; a cs:Z: tag is converted by k_cs_convert (paf.rs:129-135)
+        if (have_cs) {
+            cg_off = cs_off; cg_len = cs_len;
+            atomicAdd(cs_total, (unsigned long long)cs_len + 1ull);
+        } else {
+            paf_report(tag_key, r, 0x800000, WGA_E_CIGAR_TAG_NOT_FOUND);
+            cg_len = 0;
+            cg_off = 0;
+        }
         R.neg[r] = neg | 2 | (have_cs ? 4 : 0);  // bit 1 marks "no cg:Z:" (bit 0 stays the strand), bit 2 "but a cs:Z:"
     }
     R.cig_off[r] = cg_off;
     R.cig_len[r] = cg_len;
+}
+
+// cs:Z: -> CIGAR (paf.rs:159-218 cs_to_cigar): the regex (:[0-9]+|\*[a-z][a-z]|[=\+\-][A-Za-z]+) finds leftmost
+// non-overlapping tokens (anything else is skipped); `:N` extends or opens an M run, `*xy` an X run, `-seq` / `+seq`
+// close the open run and emit their own op, `=seq` is matched but ignored (the match arm `_ => {}`).  The output is
+// never longer than the input (every token yields at most its own byte count), so record r owns cs_len + 1 arena
+// bytes handed out by an atomic cursor; the bytes behind the CIGAR are tab-filled, as in PAF text.  A `:N` beyond u64 makes the reference's parse().unwrap() panic.
+// One thread per cs record: cs:Z: without cg:Z: is the rare spelling (minimap2 --cs without -c).
+__device__ __forceinline__ uint32_t cs_put_u64(uint8_t *o, unsigned long long v) {
+    uint8_t tmp[20];
+    uint32_t n = 0;
+    do { tmp[n++] = (uint8_t)('0' + v % 10); v /= 10; } while (v);
+    for (uint32_t i = 0; i < n; ++i) o[i] = tmp[n - 1 - i];
+    return n;
+}
+__global__ void k_cs_convert(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R, uint8_t *__restrict__ arena,
+                             unsigned long long *__restrict__ cursor, unsigned long long *tag_key) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint8_t negf = R.neg[r];
+    if ((negf & 6) != 6) return;
+    const uint64_t n = R.cig_len[r];
+    const uint8_t *cs = text + R.cig_off[r];
+    uint8_t *o = arena + atomicAdd(cursor, (unsigned long long)n + 1ull);
+    uint64_t w = 0, i = 0;
+    uint8_t last_op = 'M';
+    unsigned long long last_len = 0;
+    auto is_alpha = [](uint8_t c) { return (uint8_t)((c | 0x20) - 'a') < 26u; };
+    auto flush = [&]() { if (last_len) { w += cs_put_u64(o + w, last_len); o[w++] = last_op; } };
+    while (i < n) {
+        const uint8_t c = cs[i];
+        if (c == ':' && i + 1 < n && (uint8_t)(cs[i + 1] - '0') < 10u) {
+            unsigned long long v = 0;
+            uint64_t j = i + 1;
+            for (; j < n && (uint8_t)(cs[j] - '0') < 10u; ++j) {
+                const unsigned long long d = cs[j] - '0';
+                if (v > (0xFFFFFFFFFFFFFFFFull - d) / 10) { paf_report(tag_key, r, 0x800000, WGA_E_REF_PANIC); return; }
+                v = v * 10 + d;
+            }
+            if (last_op == 'M') last_len += v;
+            else { flush(); last_op = 'M'; last_len = v; }
+            i = j;
+        } else if (c == '*' && i + 2 < n && (uint8_t)(cs[i + 1] - 'a') < 26u && (uint8_t)(cs[i + 2] - 'a') < 26u) {
+            if (last_op == 'X') last_len += 1;
+            else { flush(); last_op = 'X'; last_len = 1; }
+            i += 3;
+        } else if ((c == '=' || c == '+' || c == '-') && i + 1 < n && is_alpha(cs[i + 1])) {
+            uint64_t j = i + 1;
+            while (j < n && is_alpha(cs[j])) ++j;
+            if (c != '=') {
+                flush();
+                w += cs_put_u64(o + w, j - (i + 1));
+                o[w++] = c == '-' ? 'D' : 'I';
+                last_len = 0;
+                last_op = 'M';
+            }
+            i = j;
+        } else {
+            ++i;
+        }
+    }
+    flush();
+    for (uint64_t k = w; k <= n; ++k) o[k] = '\t';  // what follows a CIGAR in PAF text: never a digit, never stale bytes
+    R.cig_off[r] = (uint64_t)(o - text);  // wraps when the arena lies below the slab: text + cig_off is the arena address
+    R.cig_len[r] = w;
+    R.neg[r] = negf & 1;                  // from here on the record is indistinguishable from one that carried cg:Z:
 }
 
 // CIGAR text -> the 11 counters of struct Cigar (cigar.rs:16-29), fast path: one WARP per record, lane i of a step

@@ -232,8 +232,8 @@ __global__ void k_pp_ops(uint64_t n, const uint8_t *__restrict__ text, const uin
     if ((negf & 2) || len == 0) {
         if (PASS == 0) {
             n_ops[i] = 0;
-            // CigarTagNotFound / cs:Z: were recorded per FILE-order record by k_paf_parse; re-report in sorted order
-            if (negf & 2) paf_report(err_key, i, 0x800000, (negf & 4) ? WGA_E_UNSUPPORTED : WGA_E_CIGAR_TAG_NOT_FOUND);
+            // CigarTagNotFound / a panicking cs:Z: conversion were recorded per FILE-order record by k_paf_parse; re-report in sorted order
+            if (negf & 2) paf_report(err_key, i, 0x800000, (negf & 4) ? WGA_E_REF_PANIC : WGA_E_CIGAR_TAG_NOT_FOUND);  // bit 2 left set: the cs:Z: conversion panics
             else paf_report(err_key, i, 0x800001, WGA_E_REF_PANIC);
         }
         return;

@@ -23,6 +23,7 @@
 #include "pafpseudo.cuh"
 #include "validate.cuh"
 #include "pafcov.cuh"
+#include "filter.cuh"
 #include "chain_in.cuh"
 #endif
 
@@ -1270,6 +1271,20 @@ std::string paf_cigar_error_text(const std::string &cg, int code) {
     return "CIGAR error code " + std::to_string(code);
 }
 }  // namespace
+// cs:Z: tags standing in for a missing cg:Z: (paf.rs:129-135): k_paf_parse summed their lengths into *cs_total;
+// when there are any, k_cs_convert writes the converted CIGARs to an arena and repoints cig_off / cig_len.
+static int paf_cs_to_cigar(wga_ctx *ctx, const uint8_t *d_text, const PafRecs &R, uint64_t n_rec, unsigned long long *cs_total,
+                           unsigned long long *tag_key) {
+    uint64_t total;
+    WGA_TRY(read_scalars(ctx, {(const uint64_t *)cs_total}, &total));
+    if (total == 0) return WGA_OK;
+    uint8_t *arena = ctx->buf<uint8_t>(B_CS_ARENA, total + 16);
+    if (!arena) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, cs_total, 1, 0ull);
+    LAUNCH(ctx, k_cs_convert, grid_for(n_rec, 128), 128, n_rec, d_text, R, arena, cs_total, tag_key);
+    return WGA_OK;
+}
+
 extern "C" {
 
 // ---------------------------------------------------------------- stat -f paf
@@ -1313,7 +1328,11 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (!R.q_name_off || !R.t_name_off || !R.cig_off || !R.cig_len || !R.q_name_len || !R.t_name_len || !m4 || !R.neg || !cnt11)
         return ctx->err_code;
     R.q_size = m4; R.t_size = m4 + n_rec; R.q_start = m4 + 2 * n_rec; R.t_start = m4 + 3 * n_rec;
-    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key, err_key);
+    unsigned long long *cs_total = ctx->buf<unsigned long long>(B_CS_TOTAL, 1);
+    if (!cs_total) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, cs_total, 1, 0ull);
+    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key, err_key, cs_total);
+    WGA_TRY(paf_cs_to_cigar(ctx, d_text, R, n_rec, cs_total, err_key));
     WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     uint8_t *slow = ctx->buf<uint8_t>(B_RUN_CLS, n_rec);
     if (!slow) return ctx->err_code;
@@ -1333,8 +1352,8 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
         std::string msg;
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
-        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on an empty cg:Z: tag";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field) in record " + std::to_string(rec);
+        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR, or a cs:Z: length beyond u64)";
         else {
             uint64_t oc[2];
             WGA_TRY(read_scalars(ctx, {R.cig_off + rec, R.cig_len + rec}, oc));
@@ -1506,7 +1525,11 @@ static int paf_fasta_prepare(wga_ctx *ctx, uint64_t len, const wga_fasta *TF, co
     FaView T{nullptr, nullptr, nullptr, 0}, Q{nullptr, nullptr, nullptr, 0};
     if (TF) T = FaView{TF->d_seq, TF->d_names, TF->d_meta, TF->n_seq};
     if (QF) Q = FaView{QF->d_seq, QF->d_names, QF->d_meta, QF->n_seq};
-    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key, tag_key ? tag_key : err_key);
+    unsigned long long *cs_total = ctx->buf<unsigned long long>(B_CS_TOTAL, 1);
+    if (!cs_total) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, cs_total, 1, 0ull);
+    LAUNCH(ctx, k_paf_parse, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, err_key, tag_key ? tag_key : err_key, cs_total);
+    WGA_TRY(paf_cs_to_cigar(ctx, d_text, R, n_rec, cs_total, tag_key ? tag_key : err_key));
     LAUNCH(ctx, k_p2m_spans, grid_for(n_lines, 256), 256, lv, lflags, rscan, R, X, T, Q, end_adj, with_spans ? 1 : 0, err_key);
     PP->lv = lv; PP->R = R; PP->X = X; PP->n_rec = n_rec; PP->err_key = err_key; PP->n_ops = n_ops; PP->op_base = op_base;
     return WGA_OK;
@@ -1600,7 +1623,7 @@ int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_NOM) msg = "HTS library error by sequence of record " + std::to_string(rec) + " not found in the FASTA index";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field) in record " + std::to_string(rec);
         else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR, or an insert past the end of the fetched sequence)";
         else if (code == WGA_E_VCF_BASE) {
             uint64_t ql[2];
@@ -1707,7 +1730,7 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_NOM) msg = "HTS library error by sequence of record " + std::to_string(rec) + " not found in the FASTA index";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field) in record " + std::to_string(rec);
         else if (code == WGA_E_VCF_BASE) {
             uint64_t ts;
             WGA_TRY(read_scalars(ctx, {X.t_src + rec}, &ts));
@@ -1763,8 +1786,8 @@ int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
         std::string msg;
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
-        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR)";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field) in record " + std::to_string(rec);
+        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR, or a cs:Z: length beyond u64)";
         else {
             uint64_t oc[2];
             WGA_TRY(read_scalars(ctx, {R.cig_off + rec, R.cig_len + rec}, oc));
@@ -2140,8 +2163,8 @@ int wga_paf_cov(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
         std::string msg;
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
-        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR)";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field) in record " + std::to_string(rec);
+        else if (code == WGA_E_REF_PANIC) msg = "the reference panics on this record (empty CIGAR, or a cs:Z: length beyond u64)";
         else if (code == WGA_E_INTERNAL) msg = "name hash collision";
         else {
             uint64_t oc[2];
@@ -2216,7 +2239,7 @@ int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint
             const uint64_t rec = sc[3] >> 32;
             std::string msg;
             if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
-            else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field or cs:Z: tag without cg:Z:) in record " + std::to_string(rec);
+            else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field) in record " + std::to_string(rec);
             else { code = WGA_E_REF_PANIC; msg = "the reference panics on this record (get_stat().unwrap() on a CIGAR error, validate.rs:79)"; }
             ctx->set_error(code, rec, msg);
             return code;
@@ -2240,6 +2263,84 @@ int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint
     report->len = rep.size();
     if (fix && total) return finish_output(ctx, d_rows, total, mem, flags, fixed);
     return WGA_OK;
+}
+
+// ---------------------------------------------------------------- filter -f paf (filter.rs:41-63,92-160)
+int wga_paf_filter(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t min_block_size,
+                   uint64_t min_query_size, const uint64_t *min_align_size, wga_span *out) {
+    if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr; out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem));
+    unsigned long long *tag_key = ctx->buf<unsigned long long>(B_PP_T, 1);  // filter never looks at the CIGAR: not an error here
+    if (!tag_key) return ctx->err_code;
+    PafPrep PP;
+    WGA_TRY(paf_fasta_prepare(ctx, len, nullptr, nullptr, 1, &PP, false, tag_key));
+    const uint64_t n_rec = PP.n_rec;
+    if (n_rec == 0) return WGA_OK;
+    const uint8_t *d_text = ctx->d_text;
+    PafRecs R = PP.R;
+    unsigned long long *err_key = PP.err_key;
+    uint64_t *c7 = ctx->buf<uint64_t>(B_GEN_D, 7 * n_rec);
+    uint64_t *l2 = ctx->buf<uint64_t>(B_GEN_E, 2 * (n_rec + 1));
+    uint8_t *keep = ctx->buf<uint8_t>(B_RUN_CLS, n_rec);
+    if (!c7 || !l2 || !keep) return ctx->err_code;
+    ValCols C;
+    C.q_end = c7; C.t_end = c7 + n_rec; C.matches = c7 + 2 * n_rec; C.block_len = c7 + 3 * n_rec; C.mapq = c7 + 4 * n_rec;
+    C.tags_off = c7 + 5 * n_rec; C.line_end = c7 + 6 * n_rec;
+    uint8_t *lflags = ctx->buf<uint8_t>(B_LINE_FLAGS, PP.lv.n_lines + 1);  // the line table of paf_fasta_prepare
+    uint32_t *rscan = ctx->buf<uint32_t>(B_LINE_REC, PP.lv.n_lines + 1);
+    LAUNCH(ctx, k_val_cols, grid_for(PP.lv.n_lines, 256), 256, PP.lv, (const uint8_t *)lflags, (const uint32_t *)rscan, C);
+    if (min_align_size) {
+        unsigned long long *cnt11 = ctx->buf<unsigned long long>(B_GEN_C, n_rec * 11);
+        uint64_t *zeros = ctx->buf<uint64_t>(B_GEN_F, n_rec);
+        uint64_t cap = 1024;
+        while (cap < 2 * n_rec) cap <<= 1;
+        unsigned long long *keys = ctx->buf<unsigned long long>(B_PT_KEYS, cap);
+        unsigned long long *first = ctx->buf<unsigned long long>(B_PT_FIRST, cap);
+        unsigned long long *vals = ctx->buf<unsigned long long>(B_PT_VALS, cap * kPairVals);
+        uint64_t *rec_slot = ctx->buf<uint64_t>(B_REC_SLOT, n_rec);
+        if (!cnt11 || !zeros || !keys || !first || !vals || !rec_slot) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(zeros, 0, n_rec * 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(keys, 0, cap * 8, ctx->stream));
+        WGA_CK(cudaMemsetAsync(first, 0xFF, cap * 8, ctx->stream));
+        LAUNCH(ctx, k_pt_init, grid_for(cap * kPairVals, 256), 256, vals, cap);
+        LAUNCH(ctx, k_flt_contrib, grid_for(n_rec, 256), 256, n_rec, R, (const uint64_t *)C.t_end, cnt11);
+        // the key of filter.rs:125 is (query_name, target_name): the sizes of stat's Pair key are left out (all zero)
+        RecMeta M;
+        M.text = d_text; M.t_name_off = R.t_name_off; M.q_name_off = R.q_name_off; M.t_name_len = R.t_name_len; M.q_name_len = R.q_name_len;
+        M.t_size = zeros; M.q_size = zeros; M.t_start = zeros; M.q_start = zeros; M.neg = R.neg; M.skip = nullptr;
+        LAUNCH(ctx, k_pair_insert, grid_for(n_rec, 256), 256, n_rec, M, (const unsigned long long *)cnt11, cap - 1, keys, first, vals, rec_slot);
+        LAUNCH(ctx, k_pair_verify, grid_for(n_rec, 256), 256, n_rec, M, (const unsigned long long *)first, (const uint64_t *)rec_slot, err_key);
+        LAUNCH(ctx, k_flt_keep_pair, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)rec_slot, (const unsigned long long *)vals,
+               *min_align_size, keep);
+    } else {
+        LAUNCH(ctx, k_flt_keep, grid_for(n_rec, 256), 256, n_rec, R, (const uint64_t *)C.t_end, min_block_size, min_query_size, keep);
+    }
+    FltView V;
+    V.n_rec = n_rec; V.text = d_text; V.R = R; V.C = C; V.keep = keep; V.row_len = l2; V.row_off = l2 + (n_rec + 1); V.out = nullptr;
+    LAUNCH(ctx, k_flt_rows<0>, grid_for(n_rec + 1, 256), 256, V);
+    WGA_TRY(exclusive_sum(ctx, V.row_len, l2 + (n_rec + 1), n_rec + 1));
+    uint64_t sc[2];
+    WGA_TRY(read_scalars(ctx, {l2 + (n_rec + 1) + n_rec, err_key}, sc));
+    if (sc[1] != kNoErr) {
+        const int code = (int)(sc[1] & 0xFF);
+        const uint64_t rec = sc[1] >> 32;
+        std::string msg;
+        if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field) in record " + std::to_string(rec);
+        else msg = "internal: pair key collision";
+        ctx->set_error(code, rec, msg);
+        return code;
+    }
+    const uint64_t total = sc[0];
+    if (total == 0) return WGA_OK;
+    char *d_rows = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_rows) return ctx->err_code;
+    V.out = d_rows;
+    LAUNCH(ctx, k_flt_rows<1>, grid_for(n_rec + 1, 256), 256, V);
+    return finish_output(ctx, d_rows, total, mem, flags, out);
 }
 
 // ---------------------------------------------------------------- pafpseudo (pseudomaf.rs:18-237, cigar.rs:744-804)
@@ -2272,7 +2373,7 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_NOM) msg = "HTS library error by sequence not found in the FASTA index";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported input: quoted csv field, cs:Z: without cg:Z:, or records of one (target, query) group with equal target_start";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported input: quoted csv field, or records of one (target, query) group with equal target_start";
         else if (code == WGA_E_VCF_BASE) msg = "Invalid Base in a '-' strand query";
         else if (code == WGA_E_CIGAR_OP_INVALID) msg = "CIGAR OP invalid";
         else if (code == WGA_E_PARSE_INT) msg = "Parse Into Integer Error";
@@ -2456,6 +2557,7 @@ int wga_paf_pseudo(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_f
 int wga_paf_validate(wga_ctx *, const void *, uint64_t, int, uint32_t, int, wga_span *, wga_span *) { return WGA_E_UNSUPPORTED; }
 int wga_paf2chain(wga_ctx *, const void *, uint64_t, int, uint32_t, uint64_t, wga_span *, uint64_t *) { return WGA_E_UNSUPPORTED; }
 int wga_paf_cov(wga_ctx *, const void *, uint64_t, int, uint32_t, wga_span *) { return WGA_E_UNSUPPORTED; }
+int wga_paf_filter(wga_ctx *, const void *, uint64_t, int, uint32_t, uint64_t, uint64_t, const uint64_t *, wga_span *) { return WGA_E_UNSUPPORTED; }
 #endif
 #ifndef WGA_WITH_CALL
 int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
