@@ -275,6 +275,18 @@ int wga_paf_cov(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t f
 int wga_paf_filter(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, uint64_t min_block_size,
                    uint64_t min_query_size, const uint64_t *min_align_size, wga_span *out);
 
+/* ---- dotplot -m base-level, the plot data: src/parser/cigar.rs:807-985 (emit_baseplotdatas, parse_cigar_to_base_plotdata,
+ * parse_maf_to_base_plotdata) + the csv rendering of src/tools/dotplot.rs:283-289 -------------------- */
+/* out = one csv row "ref_start,ref_end,query_start,query_end,cigar,ref_chro,query_chro\n" per plot segment (struct
+ * BasePlotdata, dotplot.rs:181-190), records in file order (the reference's par_bridge order is unspecified).  The csv
+ * writer's header row (WGA_PLOTDATA_CSV_HEADER) precedes the first row of a non-empty result and is left to the caller,
+ * who may be concatenating slabs.  skip_cutoff = `-l` (an I / D longer than it becomes a segment of its own).  PAF: ops
+ * other than M = X I D are ignored, as the reference's match arm does. */
+#define WGA_PLOTDATA_CSV_HEADER "ref_start,ref_end,query_start,query_end,cigar,ref_chro,query_chro\n"
+int wga_maf_plotdata(wga_ctx *ctx, const void *maf, uint64_t len, int mem, uint32_t flags, const char *query_name,
+                     uint64_t skip_cutoff, wga_span *out);
+int wga_paf_plotdata(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, uint64_t skip_cutoff, wga_span *out);
+
 /* ---- validate: src/tools/validate.rs:44-147 (a free rider on the PAF CIGAR counters) ------------ */
 /* report (always host memory) = the reference's report text: counts, then "{name}:{start}-{end}" of every record whose
  * query / target end differs from start + the CIGAR's consumed bases; fix != 0: `fixed` = every record re-serialised

@@ -1994,6 +1994,135 @@ int orc_paf_filter(const char *text, size_t len, uint64_t min_block, uint64_t mi
     return rc;
 }
 
+
+/* -------------------------------------------------------------------- dotplot -m base-level: the plot data */
+/* src/parser/cigar.rs:807-914 reserve_query_start_end + emit_baseplotdatas, :917-952 parse_cigar_to_base_plotdata,
+ * :955-985 parse_maf_to_base_plotdata; rendered as dotplot.rs:283-289 does for --out-format csv (csv::Writer with the
+ * struct's header row, written when there is at least one segment; struct BasePlotdata dotplot.rs:181-190).  Records in
+ * file order (the reference's par_bridge order is unspecified).  Pinned on test/test.html (the same data as JSON). */
+typedef struct { uint64_t rs, re, qs, qe; char c; } plotseg;
+typedef struct { plotseg *v; size_t n, cap; uint64_t ref, qry; int last_m; } plotstate;
+static void plot_push(plotstate *st, uint64_t rs, uint64_t re, uint64_t qs, uint64_t qe, char c, int neg) {
+    if (st->n == st->cap) { st->cap = st->cap ? st->cap * 2 : 16; st->v = (plotseg *)realloc(st->v, st->cap * sizeof(plotseg)); }
+    plotseg g = {rs, re, qs, qe, c};
+    if (neg) { g.qs = qe; g.qe = qs; } /* reserve_query_start_end */
+    st->v[st->n++] = g;
+}
+static void plot_emit(plotstate *st, char op, uint64_t length, uint64_t cutoff, int neg) { /* cigar.rs:814-914 */
+    if (op == 'M' || op == '=' || op == 'X') {
+        const uint64_t re = st->ref + length, qe = st->qry + length;
+        if (!st->last_m) plot_push(st, st->ref, re, st->qry, qe, 'M', neg);
+        else {
+            plotseg *m = &st->v[st->n - 1];
+            m->re = re;
+            if (neg) m->qs = qe; else m->qe = qe;
+        }
+        st->ref += length; st->qry += length;
+        st->last_m = 1;
+    } else if (op == 'I') {
+        const uint64_t qe = st->qry + length;
+        if (length > cutoff) { plot_push(st, st->ref, st->ref, st->qry, qe, 'I', neg); st->last_m = 0; }
+        else if (st->last_m) { plotseg *m = &st->v[st->n - 1]; if (neg) m->qs = qe; else m->qe = qe; }
+        st->qry += length;
+    } else if (op == 'D') {
+        const uint64_t re = st->ref + length;
+        if (length > cutoff) { plot_push(st, st->ref, re, st->qry, st->qry, 'D', neg); st->last_m = 0; }
+        else if (st->last_m) st->v[st->n - 1].re = re;
+        st->ref += length;
+    }
+}
+static void csvc_field(orc_buf *out, sv f) { /* csv::Writer default: ',' delimiter, QuoteStyle::Necessary */
+    int need = 0;
+    for (size_t i = 0; i < f.n; i++) if (f.p[i] == '"' || f.p[i] == ',' || f.p[i] == '\r' || f.p[i] == '\n') need = 1;
+    if (!need) { buf_put(out, f.p, f.n); return; }
+    buf_putc(out, '"');
+    for (size_t i = 0; i < f.n; i++) { if (f.p[i] == '"') buf_putc(out, '"'); buf_putc(out, f.p[i]); }
+    buf_putc(out, '"');
+}
+static void plot_write(orc_buf *out, const plotstate *st, sv ref_chro, sv query_chro) {
+    for (size_t i = 0; i < st->n; i++) {
+        const plotseg *g = &st->v[i];
+        if (out->n == 0) buf_puts(out, "ref_start,ref_end,query_start,query_end,cigar,ref_chro,query_chro\n");
+        buf_putu(out, g->rs); buf_putc(out, ','); buf_putu(out, g->re); buf_putc(out, ','); buf_putu(out, g->qs); buf_putc(out, ',');
+        buf_putu(out, g->qe); buf_putc(out, ','); buf_putc(out, g->c); buf_putc(out, ',');
+        csvc_field(out, ref_chro); buf_putc(out, ','); csvc_field(out, query_chro); buf_putc(out, '\n');
+    }
+}
+
+int orc_maf_plotdata(const char *text, size_t len, const char *query_name, uint64_t cutoff, orc_buf *out, char *err, size_t errcap) {
+    lreader rd;
+    maf_reader_init(&rd, text, len);
+    mafrec rec = {0};
+    plotstate st = {0};
+    int rc;
+    while ((rc = maf_next(&rd, &rec, err, errcap)) > 0) {
+        if (query_name) {
+            int e = maf_set_query_byname(&rec, query_name, err, errcap);
+            if (e) { rc = -e; break; }
+        }
+        if (rec.query_idx >= rec.n) {
+            set_err(err, errcap, "panic: index out of bounds: the len is %zu but the index is %zu", rec.n, rec.query_idx);
+            rc = -ORC_E_PANIC;
+            break;
+        }
+        const sline *t = &rec.s[0], *q = &rec.s[rec.query_idx];
+        const size_t n = t->seq.n < q->seq.n ? t->seq.n : q->seq.n;
+        st.n = 0; st.ref = t->start; st.qry = maf_query_start(&rec); st.last_m = 0;
+        for (size_t i = 0; i < n;) {
+            char k = cigar_cat_ext(t->seq.p[i], q->seq.p[i]);
+            size_t j = i;
+            while (j < n && cigar_cat_ext(t->seq.p[j], q->seq.p[j]) == k) j++;
+            plot_emit(&st, k, j - i, cutoff, q->neg);
+            i = j;
+        }
+        plot_write(out, &st, t->name, q->name);
+    }
+    free(rec.s); free(st.v);
+    if (rc < 0) out->n = 0;
+    return rc < 0 ? -rc : ORC_OK;
+}
+
+int orc_paf_plotdata(const char *text, size_t len, uint64_t cutoff, orc_buf *out, char *err, size_t errcap) {
+    size_t pos = 0;
+    pafrow row = {0};
+    orc_buf conv = {0};
+    plotstate st = {0};
+    int rc = ORC_OK;
+    while (paf_next(text, len, &pos, &row)) {
+        uint64_t u[12] = {0};
+        int neg = 0, bad = row.n < 12;
+        for (int k = 0; k < 12 && !bad; k++) {
+            if (k == 0 || k == 5) continue;
+            if (k == 4) { if (sv_eq_c(row.f[4], "+")) neg = 0; else if (sv_eq_c(row.f[4], "-")) neg = 1; else bad = 1; continue; }
+            if (!csv_parse_u64(row.f[k], &u[k])) bad = 1;
+        }
+        if (bad) { set_err(err, errcap, "CSV deserialize error by: field parse"); rc = ORC_E_CSV; break; }
+        sv cg = {0, 0};
+        const int have = paf_get_cigar(&row, &conv, &cg);
+        if (have < 0) { set_err(err, errcap, CS_PANIC_MSG); rc = ORC_E_PANIC; break; }
+        if (!have) { set_err(err, errcap, "CIGAR start tag not found"); rc = ORC_E_CIGAR_TAG_NOT_FOUND; break; }
+        if (cg.n == 0) { set_err(err, errcap, "panic: byte index 10 is out of bounds of ``"); rc = ORC_E_PANIC; break; }
+        st.n = 0; st.ref = u[7]; st.qry = u[2]; st.last_m = 0;
+        for (size_t i = 0; i < cg.n && rc == ORC_OK;) { /* cigar.rs:43-75 tokens: digits* then non-digits* */
+            size_t d0 = i;
+            while (i < cg.n && cg.p[i] >= '0' && cg.p[i] <= '9') i++;
+            size_t o0 = i;
+            while (i < cg.n && !(cg.p[i] >= '0' && cg.p[i] <= '9')) i++;
+            sv digits = {cg.p + d0, o0 - d0}, op = {cg.p + o0, i - o0};
+            uint64_t l;
+            if (op.n != 1) { set_err(err, errcap, "CIGAR OP `%.*s` invalid", (int)op.n, op.p); rc = ORC_E_CIGAR_OP_INVALID; break; }
+            if (!parse_u64(digits, &l)) { set_err(err, errcap, "Parse `%.*s` Into Integer Error", (int)digits.n, digits.p); rc = ORC_E_PARSE_INT; break; }
+            plot_emit(&st, op.p[0], l, cutoff, neg); /* ops other than M = X I D: the `_ => {}` arm */
+        }
+        if (rc != ORC_OK) break;
+        plot_write(out, &st, row.f[5], row.f[0]);
+    }
+    if (rc != ORC_OK) out->n = 0;
+    free(row.f); free(row.scratch); free(st.v);
+    orc_buf_free(&conv);
+    return rc;
+}
+
 /* -------------------------------------------------------------------- chain */
 /* src/converter.rs:57-92 maf2chain / :148-173 paf2chain; src/parser/chain.rs:92-204 (ChainDataLine / ChainHeader
  * Display, TryFrom<&MAFRecord> / TryFrom<&PafRecord> with the negative-strand quirk: query.end is computed from the

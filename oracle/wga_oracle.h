@@ -79,6 +79,10 @@ int orc_stat_maf(const char *text, size_t len, int each, const char *query_name,
 int orc_paf_filter(const char *text, size_t len, uint64_t min_block, uint64_t min_query, int have_align, uint64_t min_align,
                    orc_buf *out, char *err, size_t errcap);
 
+/* cigar.rs:807-985 + dotplot.rs:283-289: the base-level plot data as csv (header row when there is at least one segment) */
+int orc_maf_plotdata(const char *text, size_t len, const char *query_name, uint64_t cutoff, orc_buf *out, char *err, size_t errcap);
+int orc_paf_plotdata(const char *text, size_t len, uint64_t cutoff, orc_buf *out, char *err, size_t errcap);
+
 /* paf.rs:159-218 cs_to_cigar alone (test hook) */
 int orc_cs_to_cigar(const char *cs, size_t n, orc_buf *out, char *err, size_t errcap);
 

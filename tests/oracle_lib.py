@@ -49,6 +49,10 @@ def lib():
                                    ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_paf_filter.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64,
                                      ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_maf_plotdata.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(OrcBuf),
+                                       ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_paf_plotdata.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.POINTER(OrcBuf), ctypes.c_char_p,
+                                       ctypes.c_size_t]
         L.orc_cs_to_cigar.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_call_maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64,
@@ -130,6 +134,14 @@ def stat_paf(text: bytes, each=False) -> bytes:
 
 def paf_filter(text: bytes, min_block=0, min_query=0, min_align=None) -> bytes:
     return _run(lib().orc_paf_filter, text, len(text), min_block, min_query, int(min_align is not None), min_align or 0)
+
+
+def maf_plotdata(text: bytes, cutoff=0, query_name=None) -> bytes:
+    return _run(lib().orc_maf_plotdata, text, len(text), _opt(query_name), cutoff)
+
+
+def paf_plotdata(text: bytes, cutoff=0) -> bytes:
+    return _run(lib().orc_paf_plotdata, text, len(text), cutoff)
 
 
 def cs_to_cigar(cs: bytes) -> bytes:

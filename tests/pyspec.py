@@ -442,3 +442,51 @@ def chain2maf(text: str, fa: dict, t_path="t.fa", q_path="q.fa") -> str:
         out.append(f"s\t{h['target_name']}\t{ts}\t{te - ts}\t{h['target_strand']}\t{int(h['target_size'])}\t{t}\n")
         out.append(f"s\t{h['query_name']}\t{qsz - qe if neg else qs}\t{qe - qs}\t{h['query_strand']}\t{qsz}\t{q}\n\n")
     return "".join(out)
+
+
+def plot_segments(ops, ref0, qry0, neg, cutoff):
+    """cigar.rs:807-952 spelled by stretches instead of the reference's state machine: I / D ops longer than `cutoff` are
+    segments of their own and cut the op list into stretches; a stretch yields one M segment from the offsets at its first
+    M/=/X op to the offsets at its end; other ops are ignored.  ops = [(len, op)]; returns [(rs, re, qs, qe, c)]."""
+    segs, stretch = [], []
+    ref, qry = ref0, qry0
+
+    def close():
+        nonlocal ref, qry
+        r, q = ref, qry
+        start = None
+        for n, op in stretch:
+            if op in "M=X":
+                if start is None:
+                    start = (r, q)
+                r += n; q += n
+            elif op == "I":
+                q += n
+            elif op == "D":
+                r += n
+        if start is not None:
+            segs.append((start[0], r, start[1], q, "M"))
+        ref, qry = r, q
+        stretch.clear()
+
+    for n, op in ops:
+        if op in "ID" and n > cutoff:
+            close()
+            if op == "I":
+                segs.append((ref, ref, qry, qry + n, "I")); qry += n
+            else:
+                segs.append((ref, ref + n, qry, qry, "D")); ref += n
+        else:
+            stretch.append((n, op))
+    close()
+    if neg:
+        segs = [(rs, re, qe, qs, c) for rs, re, qs, qe, c in segs]
+    return segs
+
+
+def plot_csv(recs, cutoff):  # recs = [(ref_chro, query_chro, ref_start, query_start, neg, ops)]
+    rows = []
+    for tname, qname, ref0, qry0, neg, ops in recs:
+        for rs, re_, qs, qe, c in plot_segments(ops, ref0, qry0, neg, cutoff):
+            rows.append(f"{rs},{re_},{qs},{qe},{c},{tname},{qname}\n")
+    return ("ref_start,ref_end,query_start,query_end,cigar,ref_chro,query_chro\n" + "".join(rows)) if rows else ""

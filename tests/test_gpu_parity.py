@@ -1279,3 +1279,47 @@ def test_paf_filter_parity(w, ctx):
             with pytest.raises(w.WGAError) as eg:
                 fla(bad, a) if a is not None else flt(bad)
             assert eo.value.code == code == eg.value.code
+
+
+# ---------------------------------------------------------------- dotplot base-level plot data (8(f) item 4, cigar.rs:807-985)
+def test_plotdata_parity(w, ctx):
+    pm = lambda t, c=0, qn=None: w.run_bytes(w.generate_maf_basedata, w.MAFReader(t), c, qn, ctx=ctx)
+    pp = lambda t, c=0: w.run_bytes(w.generate_paf_basedata, w.PAFReader(t), c, ctx=ctx)
+    for c in (0, 5, 10, 19, 20, 10 ** 9):
+        assert pp(TEST_PAF, c) == orc.paf_plotdata(TEST_PAF, c)
+        assert pm(TEST_MAF, c) == orc.maf_plotdata(TEST_MAF, c)
+    assert pp(b"") == b"" and pm(b"##maf version=1\n") == b"" and pp(b"#x\n") == b""
+    for seed in (3, 4):
+        maf = bs.gen_maf(bs.maf_params(400, seed=seed, p_bothgap=1e-3))
+        for c in (0, 1, 3, 50):
+            assert pm(maf, c) == orc.maf_plotdata(maf, c), (seed, c)
+    long_maf = bs.gen_maf(bs.maf_params(6, seed=11, len_median=200000.0, len_sigma=0.3))
+    assert pm(long_maf, 2) == orc.maf_plotdata(long_maf, 2)
+    rng = random.Random(12)
+    for seed, kw in ((1, {}), (3, dict(ops_median=1500.0, ops_sigma=1.0)), (4, dict(ops_median=3.0, ops_sigma=0.8, n_genomes=3, n_chr=2))):
+        text = bs.gen_paf(bs.paf_params(1500 if seed != 3 else 150, seed=seed, **kw))
+        lines = text.splitlines(keepends=True)
+        for i in rng.sample(range(len(lines)), len(lines) // 8):       # ops the match arm ignores, names the csv writer quotes
+            f = lines[i].rstrip(b"\n").split(b"\t")
+            k = [j for j in range(12, len(f)) if f[j].startswith(b"cg:Z:")][0]
+            which = rng.randrange(4)
+            if which == 0:
+                f[k] = f[k] + b"7N3S" + rng.choice([b"12=", b"4I", b""])
+            elif which == 1:
+                f[k] = b"cg:Z:5H" + f[k][5:]
+            elif which == 2:
+                f[0] = b'a,b'
+            else:
+                f[5] = b'say"hi'
+            lines[i] = b"\t".join(f) + b"\n"
+        text = b"".join(lines)
+        for c in (0, 2, 100):
+            assert pp(text, c) == orc.paf_plotdata(text, c), (seed, c)
+    base = b"q\t100\t7\t12\t-\tt\t100\t3\t13\t1\t2\t60\t"
+    for t, code in [(base + b"cg:Z:5MM\n", 5), (base + b"cg:Z:M\n", 1), (base + b"cg:Z:\n", 8), (base + b"NM:i:1\n", 6), (b"a\tb\n", 9),
+                    (base + b"cg:Z:3=\n" + base + b"cg:Z:2=99999999999999999999999M\n", 1)]:
+        with pytest.raises(orc.OracleError) as eo:
+            orc.paf_plotdata(t)
+        with pytest.raises(w.WGAError) as eg:
+            pp(t)
+        assert eo.value.code == code == eg.value.code, (t, eo.value.code, eg.value.code)

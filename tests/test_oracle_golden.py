@@ -594,3 +594,62 @@ def test_paf_filter_hand_derived():
     with pytest.raises(orc.OracleError) as e:
         orc.paf_filter(f + b"q\t1\n", min_align=0)
     assert e.value.code == 9
+
+
+# ---------------------------------------------------------------- dotplot base-level plot data (8(f) item 4, cigar.rs:807-985)
+def _csv_to_values(csv_text):
+    rows = csv_text.decode().splitlines()
+    assert rows[0] == "ref_start,ref_end,query_start,query_end,cigar,ref_chro,query_chro"
+    out = []
+    for r in rows[1:]:
+        rs, re_, qs, qe, c, tn, qn = r.split(",")
+        out.append({"cigar": c, "query_chro": qn, "query_end": int(qe), "query_start": int(qs), "ref_chro": tn, "ref_end": int(re_),
+                    "ref_start": int(rs)})
+    return out
+
+
+def test_plotdata_reference_html_golden():
+    """test/test.html is the reference's own `dotplot -f paf` output: its vega `data.values` are the BasePlotdata of record 1
+    of test/testdotplot.paf (9 segments M I M D M I M D M) -- a true reference output for the coordinate walk"""
+    import json
+    html = open(os.path.join(G, "ref_test.html")).read()
+    i = html.index('"values":') + len('"values":')
+    values, _ = json.JSONDecoder().raw_decode(html[i:])
+    assert [v["cigar"] for v in values] == list("MIMDMIMDM")
+    paf = open(os.path.join(G, "ref_testdotplot.paf"), "rb").read()
+    got = _csv_to_values(orc.paf_plotdata(paf, 0))
+    assert got[:9] == values
+    # record 2 is on the '-' strand: query_start / query_end change places (cigar.rs:807-811), offsets still count up
+    assert got[9:] == [
+        {"cigar": "M", "query_chro": "A", "query_end": 200, "query_start": 210, "ref_chro": "B", "ref_end": 210, "ref_start": 200},
+        {"cigar": "D", "query_chro": "A", "query_end": 210, "query_start": 210, "ref_chro": "B", "ref_end": 220, "ref_start": 210},
+        {"cigar": "M", "query_chro": "A", "query_end": 210, "query_start": 220, "ref_chro": "B", "ref_end": 230, "ref_start": 220},
+        {"cigar": "I", "query_chro": "A", "query_end": 220, "query_start": 230, "ref_chro": "B", "ref_end": 230, "ref_start": 230},
+        {"cigar": "M", "query_chro": "A", "query_end": 230, "query_start": 250, "ref_chro": "B", "ref_end": 250, "ref_start": 230}]
+    # -l 10: nothing is longer than the cut-off except the 20D / 20I of record 1; short indels stretch the open M segment
+    got = _csv_to_values(orc.paf_plotdata(paf, 10))
+    assert [(v["cigar"], v["ref_start"], v["ref_end"], v["query_start"], v["query_end"]) for v in got] == [
+        ("M", 0, 40, 0, 50), ("D", 40, 60, 50, 50), ("M", 60, 90, 50, 80), ("I", 90, 90, 80, 100), ("M", 90, 200, 100, 200),
+        ("M", 200, 250, 250, 200)]
+    # the MAF route over the same alignment gives the same segments (test.maf block 1 is another alignment: just shape-check it)
+    maf = open(os.path.join(G, "ref_test.maf"), "rb").read()
+    rows = orc.maf_plotdata(maf, 0).decode().splitlines()
+    assert rows[0].startswith("ref_start,") and len(rows) > 2
+    assert orc.maf_plotdata(b"##maf version=1\n", 0) == b"" and orc.paf_plotdata(b"", 0) == b""
+
+
+_pops = st.lists(st.tuples(st.integers(0, 30), st.sampled_from("M=XIDNSH")), min_size=1, max_size=16)
+
+
+@settings(max_examples=400, deadline=None, derandomize=True)
+@given(st.lists(st.tuples(_pops, st.booleans(), st.integers(0, 40), st.integers(0, 40)), min_size=1, max_size=4), st.integers(0, 12))
+def test_plotdata_vs_pyspec(recs, cutoff):
+    lines, spec = [], []
+    for k, (ops, neg, ts, qs) in enumerate(recs):
+        cg = "".join(f"{n}{o}" for n, o in ops)
+        tn, qn = f"t{k},x" if k == 1 else f"t{k}", f'q"{k}' if k == 2 else f"q{k}"
+        lines.append(_paf_line(qn, 5000, qs, qs + 1, "-" if neg else "+", tn, 6000, ts, ts + 1, cg))
+        tq = '"' + tn + '"' if "," in tn else tn
+        qq = '"' + qn.replace('"', '""') + '"' if '"' in qn else qn
+        spec.append((tq, qq, ts, qs, neg, ops))
+    assert orc.paf_plotdata(b"".join(lines), cutoff).decode() == pyspec.plot_csv(spec, cutoff)

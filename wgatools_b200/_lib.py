@@ -101,6 +101,10 @@ ABI = {
                                     ctypes.c_void_p, ctypes.c_void_p, _P(Span)]),
     "wga_paf_filter": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64,
                                       ctypes.c_uint64, ctypes.c_void_p, _P(Span)]),
+    "wga_maf_plotdata": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p,
+                                        ctypes.c_uint64, _P(Span)]),
+    "wga_paf_plotdata": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64,
+                                        _P(Span)]),
     "wga_paf_cov": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, _P(Span)]),
     "wga_last_record_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, _P(ctypes.c_uint64)]),
 }

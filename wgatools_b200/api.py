@@ -568,6 +568,33 @@ def pafcov(reader: PAFReader, writer, ctx=None):
         writer.write(ctypes.string_at(sp.data, sp.len))
 
 
+PLOTDATA_CSV_HEADER = b"ref_start,ref_end,query_start,query_end,cigar,ref_chro,query_chro\n"
+
+
+def generate_maf_basedata(reader: MAFReader, writer, cutoff=0, query_name=None, ctx=None):
+    """src/tools/dotplot.rs:358-379 + render_output(.., Csv): the base-level plot segments of every record as csv"""
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(reader.data)
+    sp = Span()
+    ctx._check(ctx.L.wga_maf_plotdata(ctx.h, ctypes.c_void_p(base), len(reader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, _opt(query_name),
+                                      cutoff, ctypes.byref(sp)))
+    if sp.len:
+        writer.write(PLOTDATA_CSV_HEADER)
+        writer.write(ctypes.string_at(sp.data, sp.len))
+
+
+def generate_paf_basedata(reader: PAFReader, writer, cutoff=0, ctx=None):
+    """src/tools/dotplot.rs:338-356 + render_output(.., Csv)"""
+    ctx = ctx or default_context()
+    keep, base = _host_ptr(reader.data)
+    sp = Span()
+    ctx._check(ctx.L.wga_paf_plotdata(ctx.h, ctypes.c_void_p(base), len(reader.data), WGA_MEM_HOST, WGA_F_FIRST_SLAB, cutoff,
+                                      ctypes.byref(sp)))
+    if sp.len:
+        writer.write(PLOTDATA_CSV_HEADER)
+        writer.write(ctypes.string_at(sp.data, sp.len))
+
+
 def _paf_filter(reader, writer, min_block_size, min_query_size, min_align_size, ctx):
     ctx = ctx or default_context()
     keep, base = _host_ptr(reader.data)

@@ -141,7 +141,7 @@ template <int PASS>
 __global__ void k_p2m_ops(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R, uint64_t *__restrict__ n_ops,
                           const uint64_t *__restrict__ op_base, uint64_t *__restrict__ op_len, uint8_t *__restrict__ op_type,
                           uint32_t *__restrict__ op_rec, uint32_t *__restrict__ op_pos, unsigned long long *err_key,
-                          const uint8_t *__restrict__ only = nullptr) {
+                          const uint8_t *__restrict__ only = nullptr, bool other_ok = false) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rec) return;
     if (r == n_rec) { if (PASS == 0) n_ops[r] = 0; return; }
@@ -165,7 +165,8 @@ __global__ void k_p2m_ops(uint64_t n_rec, const uint8_t *__restrict__ text, PafR
         int code = 0;
         if (op_run != 1) code = WGA_E_CIGAR_OP_INVALID;
         else if (nd == 0 || ovf) code = WGA_E_PARSE_INT;
-        else if (!(op == 'M' || op == '=' || op == 'X' || op == 'I' || op == 'D')) code = WGA_E_CIGAR_OP_INVALID;
+        const bool known = op == 'M' || op == '=' || op == 'X' || op == 'I' || op == 'D';
+        if (!code && !known && !other_ok) code = WGA_E_CIGAR_OP_INVALID;  // other_ok: type 3, ignored by the consumer (plot.cuh)
         if (code) {
             failed = true;
             if (PASS == 0) paf_report(err_key, r, 0x800002 + (pos > 0x7FFFF0ull ? 0x7FFFF0ull : pos), code);
@@ -173,7 +174,7 @@ __global__ void k_p2m_ops(uint64_t n_rec, const uint8_t *__restrict__ text, PafR
         }
         if (PASS == 1) {
             op_len[o] = val;
-            op_type[o] = (op == 'I') ? 1 : (op == 'D') ? 2 : 0;
+            op_type[o] = (op == 'I') ? 1 : (op == 'D') ? 2 : known ? 0 : 3;
             if (op_rec) op_rec[o] = (uint32_t)r;
             if (op_pos) op_pos[o] = (uint32_t)(pos > 0x7FFFF0ull ? 0x7FFFF0ull : pos);
             ++o;

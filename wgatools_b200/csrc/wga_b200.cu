@@ -13,10 +13,7 @@
 #include "tokenize.cuh"
 #include "chain.cuh"
 #include "walk_types.cuh"
-#ifdef WGA_WITH_CALL
 #include "call.cuh"
-#endif
-#ifdef WGA_WITH_PAF
 #include "paf.cuh"
 #include "paf2maf.cuh"
 #include "call_paf.cuh"
@@ -24,8 +21,8 @@
 #include "validate.cuh"
 #include "pafcov.cuh"
 #include "filter.cuh"
+#include "plot.cuh"
 #include "chain_in.cuh"
-#endif
 
 using namespace wga;
 
@@ -787,8 +784,10 @@ int wga_maf2paf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
 }
 
 // ---------------------------------------------------------------- maf2chain (converter.rs:57-92)
-int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name, uint64_t id_base,
-                  wga_span *out, uint64_t *n_records) {
+// kind 0: chain records (k_chain_rows); kind 1: base-level plot segments (k_plot_rows, plot.cuh) -- both are one sparse
+// pass per record over the EXT-classified run list of the dense walk
+static int maf_run_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name, uint64_t id_base,
+                        wga_span *out, uint64_t *n_records, int kind, uint64_t cutoff) {
     if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
     out->data = nullptr;
@@ -823,15 +822,27 @@ int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
     V.q_name_len = qnl; V.t_size = m6; V.q_size = m6 + n_rec; V.t_start = m6 + 2 * n_rec; V.t_end = m6 + 3 * n_rec;
     V.q_start = m6 + 4 * n_rec; V.q_end = m6 + 5 * n_rec; V.neg = P.rc.neg; V.skip = P.rc.skip; V.run_first = rec_run_first;
     V.run_len = run_len; V.run_type = RU.run_cls; V.maf = 1; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
-    LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    if (kind == 0) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    else LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
     WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
+    if (total == 0) return WGA_OK;
     char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_out) return ctx->err_code;
     V.out = d_out;
-    LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    if (kind == 0) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    else LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
     return finish_output(ctx, d_out, total, mem, flags, out);
+}
+int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name, uint64_t id_base,
+                  wga_span *out, uint64_t *n_records) {
+    return maf_run_rows(ctx, text, len, mem, flags, query_name, id_base, out, n_records, 0, 0);
+}
+// ---------------------------------------------------------------- dotplot -m base-level, MAF (cigar.rs:955-985)
+int wga_maf_plotdata(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name,
+                     uint64_t skip_cutoff, wga_span *out) {
+    return maf_run_rows(ctx, text, len, mem, flags, query_name, 0, out, nullptr, 1, skip_cutoff);
 }
 
 // ---------------------------------------------------------------- stat
@@ -1115,7 +1126,6 @@ int wga_last_record_counts(wga_ctx *ctx, uint64_t *dst, uint64_t cap_records, ui
     return WGA_OK;
 }
 
-#ifdef WGA_WITH_CALL
 // ---------------------------------------------------------------- call
 int wga_vcf_header(wga_ctx *ctx, const char *sample, wga_span *out) {
     if (!ctx || !out) return WGA_E_INVALID_ARG;
@@ -1249,9 +1259,7 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     }
     return finish_output(ctx, d_out, sc[0], mem, flags, out);
 }
-#endif
 
-#ifdef WGA_WITH_PAF
 }  // extern "C"
 namespace {
 // host restatement of the tokenizer's error wording (cigar.rs:43-75, errors.rs) for one CIGAR string
@@ -1374,9 +1382,7 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     ctx->last_counts_valid = true;
     return WGA_OK;
 }
-#endif
 
-#ifdef WGA_WITH_PAF
 // ---------------------------------------------------------------- paf2maf
 int wga_fasta_load(wga_ctx *ctx, const void *fa, uint64_t fa_len, const void *fai, uint64_t fai_len, wga_fasta **out) {
     if (!ctx || !out || !fa || !fai) return WGA_E_INVALID_ARG;
@@ -1751,8 +1757,9 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
 }
 
 // ---------------------------------------------------------------- paf2chain (converter.rs:148-173)
-int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
-                  uint64_t *n_records) {
+// kind 0: chain records; kind 1: base-level plot segments (ops other than M = X I D are legal there and ignored)
+static int paf_op_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
+                       uint64_t *n_records, int kind, uint64_t cutoff) {
     if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
     out->data = nullptr;
@@ -1776,7 +1783,7 @@ int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
            (uint64_t *)nullptr, (uint8_t *)nullptr);
     WGA_CK(cudaMemsetAsync(n_ops + n_rec, 0, 8, ctx->stream));
     LAUNCH(ctx, k_p2m_ops<0>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-           (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key, (const uint8_t *)slow);
+           (uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, err_key, (const uint8_t *)slow, kind == 1);
     WGA_TRY(exclusive_sum(ctx, n_ops, op_base, n_rec + 1));
     uint64_t sc[2];
     WGA_TRY(read_scalars(ctx, {op_base + n_rec, err_key}, sc));
@@ -1806,21 +1813,32 @@ int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
     LAUNCH(ctx, k_paf_ops_warp<1>, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, n_ops, slow, (const uint64_t *)op_base, op_len,
            op_type);
     LAUNCH(ctx, k_p2m_ops<1>, grid_for(n_rec + 1, 128), 128, n_rec, d_text, R, n_ops, (const uint64_t *)op_base, op_len, op_type,
-           (uint32_t *)nullptr, (uint32_t *)nullptr, err_key, (const uint8_t *)slow);
+           (uint32_t *)nullptr, (uint32_t *)nullptr, err_key, (const uint8_t *)slow, kind == 1);
     ChainView V;
     V.n_rec = n_rec; V.id_base = id_base; V.text = d_text; V.t_name_off = R.t_name_off; V.q_name_off = R.q_name_off;
     V.t_name_len = R.t_name_len; V.q_name_len = R.q_name_len; V.t_size = R.t_size; V.q_size = R.q_size; V.t_start = R.t_start;
     V.t_end = X.t_end; V.q_start = R.q_start; V.q_end = X.q_end; V.neg = R.neg; V.skip = nullptr; V.run_first = op_base;
     V.run_len = op_len; V.run_type = op_type; V.maf = 0; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
-    LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    if (kind == 0) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    else LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
     WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
+    if (total == 0) return WGA_OK;
     char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_out) return ctx->err_code;
     V.out = d_out;
-    LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    if (kind == 0) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    else LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
     return finish_output(ctx, d_out, total, mem, flags, out);
+}
+int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
+                  uint64_t *n_records) {
+    return paf_op_rows(ctx, text, len, mem, flags, id_base, out, n_records, 0, 0);
+}
+// ---------------------------------------------------------------- dotplot -m base-level, PAF (cigar.rs:917-952)
+int wga_paf_plotdata(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t skip_cutoff, wga_span *out) {
+    return paf_op_rows(ctx, text, len, mem, flags, 0, out, nullptr, 1, skip_cutoff);
 }
 
 // ---------------------------------------------------------------- chain reader front end (chain.rs:27-75,206-383)
@@ -2537,37 +2555,6 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     ctx->walk_ms = ms; ctx->walk_launches = 1; ctx->walk_bytes = total;  // expansion: output-bound
     return WGA_OK;
 }
-#endif
 
-#ifndef WGA_WITH_PAF
-int wga_paf_stat(wga_ctx *ctx, const void *, uint64_t, int, uint32_t, wga_stat_acc *) {
-    if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "paf stat not built");
-    return WGA_E_UNSUPPORTED;
-}
-int wga_fasta_load(wga_ctx *, const void *, uint64_t, const void *, uint64_t, wga_fasta **) { return WGA_E_UNSUPPORTED; }
-void wga_fasta_free(wga_fasta *) {}
-int wga_paf2maf_header(wga_ctx *, const char *, const char *, wga_span *) { return WGA_E_UNSUPPORTED; }
-int wga_paf2maf(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const wga_fasta *, wga_span *) { return WGA_E_UNSUPPORTED; }
-int wga_paf_call(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const wga_fasta *, int, uint64_t, wga_span *) {
-    return WGA_E_UNSUPPORTED;
-}
-int wga_paf_pseudo(wga_ctx *, const void *, uint64_t, int, uint32_t, const wga_fasta *, const char *, wga_span *, wga_span *) {
-    return WGA_E_UNSUPPORTED;
-}
-int wga_paf_validate(wga_ctx *, const void *, uint64_t, int, uint32_t, int, wga_span *, wga_span *) { return WGA_E_UNSUPPORTED; }
-int wga_paf2chain(wga_ctx *, const void *, uint64_t, int, uint32_t, uint64_t, wga_span *, uint64_t *) { return WGA_E_UNSUPPORTED; }
-int wga_paf_cov(wga_ctx *, const void *, uint64_t, int, uint32_t, wga_span *) { return WGA_E_UNSUPPORTED; }
-int wga_paf_filter(wga_ctx *, const void *, uint64_t, int, uint32_t, uint64_t, uint64_t, const uint64_t *, wga_span *) { return WGA_E_UNSUPPORTED; }
-#endif
-#ifndef WGA_WITH_CALL
-int wga_vcf_header(wga_ctx *ctx, const char *, wga_span *) {
-    if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "call not built");
-    return WGA_E_UNSUPPORTED;
-}
-int wga_maf_call(wga_ctx *ctx, const void *, uint64_t, int, uint32_t, const wga_call_opts *, wga_span *) {
-    if (ctx) ctx->set_error(WGA_E_UNSUPPORTED, 0, "call not built");
-    return WGA_E_UNSUPPORTED;
-}
-#endif
 
 }  // extern "C"
