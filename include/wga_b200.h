@@ -229,8 +229,9 @@ int wga_paf_call(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t 
  * "{target}\t{bytes}\n" per file, i.e. what the reference writes to {out_dir}/{target}.maf.  fa = the FASTA holding
  * targets and queries, or NULL ('N' target row, 1/0/- query rows); target = --target filter or NULL.
  * Targets, and queries inside a target, come in first-occurrence order (the reference iterates HashMaps).  Records of
- * one (target, query) group with equal target_start are refused with WGA_E_UNSUPPORTED: their order depends on the
- * tie behaviour of std's binary_search (pseudomaf.rs:91-94).  On error nothing is returned. */
+ * one (target, query) group with equal target_start are placed as the reference's sorted insert places them
+ * (pseudomaf.rs:91-94: slice::binary_search_by + Vec::insert, core::slice of rustc 1.52-1.81).  On error nothing is
+ * returned. */
 int wga_paf_pseudo(wga_ctx *ctx, const void *paf, uint64_t len, int mem, uint32_t flags, const wga_fasta *fa,
                    const char *target, wga_span *out, wga_span *index);
 

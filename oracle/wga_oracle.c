@@ -1683,7 +1683,8 @@ int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_
  * Iteration order of the two HashMaps (targets; queries inside a target) is nondeterministic in the reference; here
  * it is FIRST-OCCURRENCE order (the same convention as the stat rows).  Records with equal target_start
  * inside one (target, query) group are placed by slice::binary_search_by's tie behaviour (pseudomaf.rs:91-94); this
- * restates the classic three-way loop of std (1.52-1.8x) -- parity unpinned, and the CUDA path refuses such inputs.
+ * restates the three-way loop of core::slice 1.52-1.81; the reference's flake.lock pins nixpkgs-unstable of 2024-01-22,
+ * i.e. rustc 1.75 -- parity unpinned beyond that (no golden vector).
  * out = the files' bytes concatenated in target order; index = one line "{target}\t{bytes}\n" per file
  * ({out_dir}/{target}.maf).  On error nothing is returned (the reference may leave other targets' files behind). */
 typedef struct {

@@ -556,6 +556,9 @@ def test_paf_stat_quirks_and_errors(w, ctx):
         _pafline("100M") + b"\n" + _pafline("5=", extra=("tp:A:P", "cg:Z:9=")) + b"\n",  # first cg:Z: tag wins
         "\t".join(["q", "0x10", "1", "2", "+", "t", "0x20", "3", "4", "1", "1", "0", "cg:Z:1="]).encode(),  # csv hex ints
         _pafline("18446744073709551615=1X"),
+        # csv Terminator::CRLF: a lone '\r' ends a record too; a comment runs to the next '\n' whatever '\r' it holds
+        _pafline("10M") + b"\r" + _pafline("7=", "-", "q2") + b"\r\r\n\r" + _pafline("3=1X", "-") + b"\r",
+        b"#c\rstill comment\r" + _pafline("9=") + b"\n" + _pafline("4=") + b"\r#x\r" + _pafline("8=") + b"\n\r" + _pafline("5=", "-"),
     ]
     for t in ok:
         check_paf(w, ctx, t)
@@ -848,7 +851,8 @@ def test_paf_pseudo_parity(w, ctx):
     for it in range(5):
         paf, t_fa, _, q_fa, _ = make_paf2maf_case(rng, n_rec=120, width_t=rng.choice([50, 60, 80]), width_q=rng.choice([60, 61, 100]),
                                                   soft=it % 2 == 0)
-        paf = _dedupe_starts(paf)
+        if it % 2:
+            paf = _dedupe_starts(paf)
         fa = t_fa + q_fa
         fai = orc.make_fai(fa)
         F = w.Fasta(ctx, fa, fai)
@@ -899,10 +903,37 @@ def test_paf_pseudo_edges_and_errors(w, ctx, tmp_path):
         with pytest.raises(w.WGAError) as eg:
             w.pseudo_maf_files(w.PAFReader(p), F, ctx=ctx)
         assert eo.value.code == code == eg.value.code, (p, eo.value.code, eg.value.code, eo.value.msg)
-    # equal target_start inside one (target, query) group: order is unspecified in the reference -> refused
-    with pytest.raises(w.WGAError) as e:
-        w.pseudo_maf_files(w.PAFReader(line(b"4=") + line(b"5=")), F, ctx=ctx)
-    assert e.value.code == 102
+    # equal target_start inside one (target, query) group: placed as binary_search_by + insert do (pseudomaf.rs:91-94)
+    two = line(b"4=") + line(b"5=")
+    assert w.pseudo_maf_files(w.PAFReader(two), F, ctx=ctx) == orc.paf_pseudo(two, fa, fai)
+
+
+def test_paf_pseudo_equal_target_starts(w, ctx):
+    """tie classes of every size between smaller and greater records of the group, in every insertion order: the order
+    of the reference's sorted insert (the three-way binary search of core::slice, rustc 1.75 by the reference's flake.lock)"""
+    fa = b">T\n" + b"ACGT" * 64 + b"\n>Q\n" + b"TTGCA" * 60 + b"\n>R\n" + b"GATTACA" * 40 + b"\n"
+    fai = orc.make_fai(fa)
+    F = w.Fasta(ctx, fa, fai)
+    rng = random.Random(17)
+    def line(q, ts, n, qs, strand=b"+"):
+        return b"\t".join([q, b"280", b"%d" % qs, b"%d" % (qs + n), strand, b"T", b"256", b"%d" % ts, b"%d" % (ts + n), b"1", b"1", b"60",
+                           b"cg:Z:%d=" % n]) + b"\n"
+    for it in range(40):
+        recs = []
+        for q in (b"Q", b"R"):
+            starts = [rng.choice([0, 10, 10, 10, 40, 40, 90, 120, 120]) for _ in range(rng.randrange(1, 14))]
+            recs += [line(q, ts, rng.randrange(1, 30), rng.randrange(0, 100), rng.choice([b"+", b"-"])) for ts in starts]
+        rng.shuffle(recs)
+        paf = b"".join(recs)
+        for use_fa in (True, False):
+            want = orc.paf_pseudo(paf, fa, fai) if use_fa else orc.paf_pseudo(paf)
+            got = w.pseudo_maf_files(w.PAFReader(paf), F if use_fa else None, ctx=ctx)
+            assert list(got) == list(want) and all(got[k] == want[k] for k in want), (it, paf)
+    # a big group: 3000 records, 60 distinct starts
+    big = b"".join(line(b"Q", 4 * rng.randrange(60), rng.randrange(1, 12), rng.randrange(0, 200)) for _ in range(3000))
+    want = orc.paf_pseudo(big)
+    got = w.pseudo_maf_files(w.PAFReader(big), None, ctx=ctx)
+    assert list(got) == list(want) and all(got[k] == want[k] for k in want)
 
 
 # ---------------------------------------------------------------- validate (8(f) item 3)

@@ -11,7 +11,7 @@
 // A record without cg:Z: but with a cs:Z: tag gets its CIGAR from k_cs_convert (paf.rs:159-218 cs_to_cigar), written to a
 // device arena; cig_off then points there (as a wrapped 64-bit distance from the slab text, so every consumer's
 // `text + cig_off` keeps working).
-// Not supported (reported, never silently wrong): quoted csv fields, a lone '\r' as record terminator.
+// Not supported (reported, never silently wrong): quoted csv fields.
 #pragma once
 #include "ctx.cuh"
 #include "stat.cuh"
@@ -26,14 +26,19 @@ struct PafRecs {
     uint8_t *neg;
 };
 
-// flags: bit0 = record line (non-empty, not a '#' comment)
+// flags: bit0 = record line (non-empty, not a '#' comment).  Lines end at '\r' or '\n' (tokenize.cuh CLS 1); a comment runs
+// to the next '\n' (csv-core InComment), so a line is also a comment when a line before it -- reached only through
+// '\r' line ends -- starts with '#'.
 __global__ void k_paf_line_flags(LineView lv, uint8_t *__restrict__ flags, uint32_t *__restrict__ isrec) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k > lv.n_lines) return;
     if (k == lv.n_lines) { isrec[k] = 0; return; }
-    uint64_t s = lv.start(k), e = lv.end(k);
-    if (e > s && lv.text[e - 1] == '\r') --e;  // CRLF
+    const uint64_t s = lv.start(k), e = lv.end(k);
     bool rec = e > s && lv.text[s] != '#';     // csv: empty lines skipped, comment(Some(b'#'))
+    for (uint64_t j = k; rec && j > 0 && lv.text[lv.end(j - 1)] == '\r'; --j) {
+        const uint64_t ps = lv.start(j - 1);
+        if (lv.end(j - 1) > ps && lv.text[ps] == '#') rec = false;
+    }
     flags[k] = rec ? 1 : 0;
     isrec[k] = rec ? 1u : 0u;
 }

@@ -12,8 +12,10 @@
 // The reference's two HashMaps iterate in arbitrary order; here targets, and queries inside a target, come in
 // first-occurrence order (the convention of the stat rows).  The reference edits Strings (drain / insert_str, O(L) per
 // indel); here the whole output is laid out by prefix sums, filled with '-' once, and every CIGAR op writes its own
-// slice.  Records of one group with EQUAL target_start are ordered by std's binary_search tie behaviour in the
-// reference (pseudomaf.rs:91-94), which is not specified: such inputs are refused (WGA_E_UNSUPPORTED).
+// slice.  Records of one group with EQUAL target_start sit where `binary_search_by(..).unwrap_or_else(|e| e)` +
+// `insert(idx, rec)` (pseudomaf.rs:91-94) puts them: k_pp_ties replays that search for every record of a tie class
+// (the answer is a function of how many smaller / equal / greater records of the group came earlier in the file).
+// The search is the three-way loop of the std the reference's flake.lock pins (nixpkgs 2024-01: rustc 1.75).
 #pragma once
 #include "ctx.cuh"
 #include "paf.cuh"
@@ -113,10 +115,10 @@ struct PpRecs {  // per SORTED record (targets by first occurrence, then query g
 };
 enum : uint32_t { PP_GHEAD = 1, PP_THEAD = 2, PP_GLAST = 4, PP_TLAST = 8, PP_KEPT = 16 };
 
-// group / target boundaries in sorted order; equal target_start inside a group is refused
+// group / target boundaries in sorted order; tie[i] = position i continues a run of equal target_start inside its group
 __global__ void k_pp_flags(uint64_t n, const uint64_t *__restrict__ ord, const uint64_t *__restrict__ ft, const uint64_t *__restrict__ fp,
                            const uint64_t *__restrict__ t_start, uint32_t *__restrict__ flags, uint32_t *__restrict__ ghead,
-                           unsigned long long *err_key) {
+                           unsigned long long *n_ties) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     if (i == n) { ghead[i] = 0; return; }
@@ -125,7 +127,49 @@ __global__ void k_pp_flags(uint64_t n, const uint64_t *__restrict__ ord, const u
     const bool gl = i + 1 == n || fp[ord[i + 1]] != fp[r], tl = i + 1 == n || ft[ord[i + 1]] != ft[r];
     flags[i] = (gh ? PP_GHEAD : 0) | (th ? PP_THEAD : 0) | (gl ? PP_GLAST : 0) | (tl ? PP_TLAST : 0);
     ghead[i] = gh ? 1u : 0u;
-    if (!gh && t_start[ord[i - 1]] == t_start[r]) paf_report(err_key, i, 0, WGA_E_UNSUPPORTED);
+    if (!gh && t_start[ord[i - 1]] == t_start[r]) atomicAdd(n_ties, 1ull);
+}
+
+// slice::binary_search_by (core 1.52 .. 1.81) over [L smaller | E equal | G greater]: the index it returns
+__device__ __forceinline__ uint64_t std_binary_search_pos(uint64_t L, uint64_t E, uint64_t G) {
+    uint64_t size = L + E + G, left = 0, right = size;
+    while (left < right) {
+        const uint64_t mid = left + size / 2;
+        if (mid < L) left = mid + 1;
+        else if (mid >= L + E) right = mid;
+        else return mid;
+        size = right - left;
+    }
+    return left;
+}
+// pseudomaf.rs:88-95: the records of a (target, query) group are inserted one by one, in file order, at the index the
+// binary search over target_start returns.  Records with distinct target_start end up sorted whatever the search does;
+// a class of equal starts (file order in `ord`, the sorts are stable) is replayed here: the k-th record of the class
+// sees L smaller and G greater records that came before it in the file, plus its k predecessors of the class, and is
+// inserted in front of the class member the search hits.  One thread per tie class (classes are tiny; the counting
+// loops run over the group).  ord_out = ord with every tie class permuted.
+__global__ void k_pp_ties(uint64_t n, const uint64_t *__restrict__ ord, const uint64_t *__restrict__ fp, const uint64_t *__restrict__ t_start,
+                          const uint32_t *__restrict__ gid, const uint64_t *__restrict__ gstart, uint64_t *__restrict__ ord_out) {
+    uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint64_t r = ord[a], ts = t_start[r];
+    const uint64_t g = gid[a + 1] - 1, ga = gstart[g], gb = gstart[g + 1];  // gid = exclusive scan of the head flags
+    const bool cont = a > ga && t_start[ord[a - 1]] == ts;
+    const bool more = a + 1 < gb && t_start[ord[a + 1]] == ts;
+    if (!cont && !more) { ord_out[a] = r; return; }
+    if (cont) return;  // the class head does the work
+    uint64_t b = a + 1;
+    while (b < gb && t_start[ord[b]] == ts) ++b;
+    ord_out[a] = r;
+    for (uint64_t k = 1; k < b - a; ++k) {
+        const uint64_t f = ord[a + k];
+        uint64_t L = 0, G = 0;
+        for (uint64_t i = ga; i < a; ++i) L += ord[i] < f;
+        for (uint64_t i = b; i < gb; ++i) G += ord[i] < f;
+        const uint64_t p = std_binary_search_pos(L, k, G) - L;  // k >= 1 equal elements: the search always hits one
+        for (uint64_t j = k; j > p; --j) ord_out[a + j] = ord_out[a + j - 1];
+        ord_out[a + p] = f;
+    }
 }
 __global__ void k_pp_group_starts(uint64_t n, const uint32_t *__restrict__ ghead, const uint32_t *__restrict__ gid, uint64_t *__restrict__ gstart,
                                   uint64_t n_groups) {

@@ -16,10 +16,16 @@ constexpr int kWsTile = 32768;    // bytes per CTA in the whitespace-index kerne
 constexpr int kWsThreads = 256;
 
 // ---------------------------------------------------------------- 1. whitespace index
-// CLS 0: ASCII whitespace (MAF, split_whitespace); CLS 1: PAF delimiters '\t' and '\n' (csv reader, paf.rs:22-31)
+// CLS 0: ASCII whitespace (MAF, split_whitespace), lines end at '\n'; CLS 1: PAF delimiters (csv reader, paf.rs:22-31):
+// '\t' between fields, and the csv crate's default Terminator::CRLF ends a record at '\r', '\n' or "\r\n" -- both bytes
+// are line ends here ("\r\n" = a line end plus an empty line, and empty lines are skipped)
+template <int CLS>
+__device__ __forceinline__ uint32_t line_end_bytes(uint32_t w) {
+    return CLS == 0 ? nl_bytes(w) : (zero_bytes(w ^ 0x0A0A0A0Au) | zero_bytes(w ^ 0x0D0D0D0Du));
+}
 template <int CLS>
 __device__ __forceinline__ uint32_t delim_bytes(uint32_t w) {
-    return CLS == 0 ? ws_bytes(w) : (zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au));
+    return CLS == 0 ? ws_bytes(w) : (zero_bytes(w ^ 0x09090909u) | line_end_bytes<1>(w));
 }
 template <int CLS>
 __device__ __forceinline__ void ws_flags16(const uint8_t *text, uint64_t off, uint64_t len, uint32_t ws[4],
@@ -31,7 +37,7 @@ __device__ __forceinline__ void ws_flags16(const uint8_t *text, uint64_t off, ui
     for (int k = 0; k < 4; ++k) {
         uint32_t valid = rem >= 4 * (k + 1) ? kHi : range_flags(0, (int)(rem - 4 * k));
         ws[k] = delim_bytes<CLS>(w[k]) & valid;
-        nl[k] = nl_bytes(w[k]) & valid;
+        nl[k] = line_end_bytes<CLS>(w[k]) & valid;
     }
 }
 
@@ -137,7 +143,7 @@ constexpr int kTokWarps = 8;
 __device__ __forceinline__ uint32_t lt21_bytes(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w) & kHi; }
 template <int CLS>
 __device__ __forceinline__ bool is_delim(uint32_t ch) {
-    return CLS == 0 ? (ch == 0x20u || (ch - 9u) < 5u) : (ch == 9u || ch == 10u);
+    return CLS == 0 ? (ch == 0x20u || (ch - 9u) < 5u) : (ch == 9u || ch == 10u || ch == 13u);
 }
 
 template <int CLS, int CAP>
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_ws_scan(const uint8_t *__res
                         const uint32_t ch = (w[i] >> (8 * byte)) & 0xFFu;
                         const uint32_t rel = rel0 + 4u * i + byte;
                         if (is_delim<CLS>(ch) && base + rel < len) {
-                            const uint32_t isnl = ch == 0x0Au;
+                            const uint32_t isnl = ch == 0x0Au || (CLS == 1 && ch == 0x0Du);
                             const uint32_t idx = atomicAdd(&s_cnt[wid][0], 1u);
                             if (isnl) atomicAdd(&s_cnt[wid][1], 1u);
                             if (idx < (uint32_t)CAP) slot[idx] = (uint16_t)(rel | (isnl << 15));

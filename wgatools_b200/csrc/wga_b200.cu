@@ -1312,7 +1312,7 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
     WGA_TRY((build_delim_index<1, kTokCapPaf>(ctx, d_text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
     const uint8_t last_byte = *(uint8_t *)(ctx->h_scal + 8);
-    const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
+    const uint64_t n_lines = n_nl + (last_byte != '\n' && last_byte != '\r' ? 1 : 0);  // PAF lines end at either
     LineView lv;
     lv.text = d_text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
     lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = 0;
@@ -1499,7 +1499,7 @@ static int paf_fasta_prepare(wga_ctx *ctx, uint64_t len, const wga_fasta *TF, co
     uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
     WGA_TRY((build_delim_index<1, kTokCapPaf>(ctx, d_text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
     const uint8_t last_byte = *(uint8_t *)(ctx->h_scal + 8);
-    const uint64_t n_lines = n_nl + (last_byte != '\n' ? 1 : 0);
+    const uint64_t n_lines = n_nl + (last_byte != '\n' && last_byte != '\r' ? 1 : 0);  // PAF lines end at either
     LineView lv;
     lv.text = d_text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
     lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = 0;
@@ -2391,7 +2391,7 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_NOM) msg = "HTS library error by sequence not found in the FASTA index";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported input: quoted csv field, or records of one (target, query) group with equal target_start";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported input: quoted csv field";
         else if (code == WGA_E_VCF_BASE) msg = "Invalid Base in a '-' strand query";
         else if (code == WGA_E_CIGAR_OP_INVALID) msg = "CIGAR OP invalid";
         else if (code == WGA_E_PARSE_INT) msg = "Parse Into Integer Error";
@@ -2459,15 +2459,25 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     S.gap = p8; S.overlap = p8 + (n + 1); S.tail = p8 + 2 * (n + 1); S.q_src = p8 + 3 * (n + 1); S.LQ = p8 + 4 * (n + 1);
     S.P = p8 + 5 * (n + 1); S.seg_len = p8 + 6 * (n + 1); S.seg_off = p8 + 7 * (n + 1);
     uint64_t *t_src = p8 + 8 * (n + 1), *t_cnt = p8 + 9 * (n + 1);
+    unsigned long long *d_nties = ctx->buf<unsigned long long>(B_CS_TOTAL, 1);
+    if (!d_nties) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, d_nties, 1, 0ull);
     LAUNCH(ctx, k_pp_flags, grid_for(n + 1, 256), 256, n, ord, (const uint64_t *)ft, (const uint64_t *)fp, (const uint64_t *)R.t_start, S.flags,
-           ghead, err_key);
+           ghead, d_nties);
     WGA_TRY(exclusive_sum(ctx, ghead, gid, n + 1));
     WGA_CK(cudaMemcpyAsync(ctx->h_scal, gid + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_CK(cudaMemcpyAsync(ctx->h_scal + 1, d_nties, 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGA_TRY(sync_check(ctx));
-    const uint64_t n_groups = *(uint32_t *)ctx->h_scal;
+    const uint64_t n_groups = *(uint32_t *)ctx->h_scal, n_ties = ctx->h_scal[1];
     uint64_t *gstart = ctx->buf<uint64_t>(B_PP_N, n_groups + 1);
     if (!gstart) return ctx->err_code;
     LAUNCH(ctx, k_pp_group_starts, grid_for(n + 1, 256), 256, n, (const uint32_t *)ghead, (const uint32_t *)gid, gstart, n_groups);
+    if (n_ties) {  // equal target_start inside a (target, query) group: the order of pseudomaf.rs:91-94
+        LAUNCH(ctx, k_pp_ties, grid_for(n, 128), 128, n, ord, (const uint64_t *)fp, (const uint64_t *)R.t_start, (const uint32_t *)gid,
+               (const uint64_t *)gstart, va);
+        ord = va;
+        S.rec = va;
+    }
     LAUNCH(ctx, k_pp_groups, grid_for(n_groups, 128), 128, n_groups, (const uint64_t *)gstart, ord, R, X, S, err_key);
     // target heads
     uint32_t *tflag = ghead, *tid = gid;  // reuse
