@@ -89,4 +89,23 @@ __global__ void k_flt_rows(FltView V) {
     }
 }
 
+// warp-per-record twin of k_flt_rows (validate.cuh warp_paf_row)
+template <int PASS>
+__global__ void __launch_bounds__(128) k_flt_rows_warp(FltView V) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (r > V.n_rec) return;
+    if (r == V.n_rec || !V.keep[r]) { if (PASS == 0 && lane == 0) V.row_len[r] = 0; return; }
+    PafRowIn I;
+    I.qn = V.text + V.R.q_name_off[r]; I.tn = V.text + V.R.t_name_off[r]; I.qnl = V.R.q_name_len[r]; I.tnl = V.R.t_name_len[r];
+    I.neg = V.R.neg[r] & 1;
+    I.v[1] = V.R.q_size[r]; I.v[2] = V.R.q_start[r]; I.v[3] = V.C.q_end[r]; I.v[6] = V.R.t_size[r]; I.v[7] = V.R.t_start[r];
+    I.v[8] = V.C.t_end[r]; I.v[9] = V.C.matches[r]; I.v[10] = V.C.block_len[r]; I.v[11] = V.C.mapq[r];
+    I.has_tags = V.C.tags_off[r] <= V.C.line_end[r];
+    I.tags_n = I.has_tags ? V.C.line_end[r] - V.C.tags_off[r] : 0;
+    I.tags = V.text + V.C.tags_off[r];
+    const uint64_t n = warp_paf_row<PASS>(I, PASS == 1 ? V.out + V.row_off[r] : nullptr, lane);
+    if (PASS == 0 && lane == 0) V.row_len[r] = n;
+}
+
 }  // namespace wga

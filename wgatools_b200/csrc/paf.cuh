@@ -302,6 +302,216 @@ __global__ void __launch_bounds__(128, 8) k_paf_cigar_counts_warp(uint64_t n_rec
     }
 }
 
+// ---- flattened CIGAR counters (the default): the 16-byte pieces of ALL records form one stream, lane i of a warp step
+// owns piece g0 + i whatever record it belongs to, so short records do not leave lanes idle and neighbouring lanes read
+// neighbouring memory.  k_cig_pieces counts the pieces of every record (>= 1: a record without a usable CIGAR keeps a
+// dummy piece and goes to the exact kernel), an exclusive scan gives pbase[], k_cig_chunk_rec notes the record every
+// chunk of kCigChunk pieces starts in, and k_paf_cigar_flat walks its chunk: the record of a lane falls out of one
+// __reduce_or_sync over the next 32 record boundaries; inside a piece the lane loops over its op characters (tokens),
+// not over its bytes: the digits in front of an op are parsed with two multiplies (<= 4 digits) and the digits a token
+// has in the previous piece arrive by shuffle as before.  Sums go to acc6[r] = {M/=, X, I, D lengths, I, D events} with
+// one atomic per non-zero value and run of lanes; k_cig_finish spreads them into the 11 counters by strand.
+constexpr uint32_t kCigChunk = 512;  // pieces per warp (8 KB of CIGAR text)
+
+__global__ void k_cig_pieces(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R, uint64_t *__restrict__ nvec,
+                             uint8_t *__restrict__ slow) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rec) return;
+    if (r == n_rec) { nvec[r] = 0; return; }
+    const uint64_t len = R.cig_len[r];
+    if ((R.neg[r] & 2) || len == 0) { nvec[r] = 1; slow[r] = 1; return; }
+    const uint64_t a = reinterpret_cast<uintptr_t>(text + R.cig_off[r]) & 15u;
+    nvec[r] = (a + len + 15) >> 4;
+    slow[r] = 0;
+}
+__global__ void k_cig_chunk_rec(uint64_t n_rec, const uint64_t *__restrict__ pbase, uint32_t *__restrict__ chunk_rec) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint64_t lo = pbase[r], hi = pbase[r + 1];
+    for (uint64_t c = (lo + kCigChunk - 1) / kCigChunk; c * kCigChunk < hi; ++c) chunk_rec[c] = (uint32_t)r;
+}
+
+// digit run at the END of a piece: (value, digits); 9 digits = "longer than the 8-byte window" (flagged by the consumer)
+__device__ __forceinline__ uint32_t cig_trailing(const uint4 &cur, uint32_t &t_val) {
+    const unsigned long long F = ((unsigned long long)digit_flags(cur.w) << 32) | digit_flags(cur.z);
+    const unsigned long long nF = ~F & 0x8080808080808080ull;
+    uint32_t t_nd = nF ? (uint32_t)__clzll((long long)nF) >> 3 : 8u;
+    if (t_nd == 8u && (digit_flags(cur.y) & 0x80000000u)) t_nd = 9u;
+    t_val = 0;
+    if (t_nd) {
+        const unsigned long long H = ((unsigned long long)cur.w << 32) | cur.z;
+        const unsigned long long keep = t_nd >= 8u ? ~0ull : ~0ull << (8u * (8u - t_nd));
+        unsigned long long v = ((H & keep) | (0x3030303030303030ull & ~keep)) - 0x3030303030303030ull;
+        v = v * 10 + (v >> 8);
+        v = (((v & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((v >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
+        t_val = (uint32_t)v;
+    }
+    return t_nd;
+}
+__device__ __forceinline__ uint32_t movemask4(uint32_t hi_flags) {  // bit 7 of byte k -> bit k
+    return (((hi_flags >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t sel4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t k) {
+    return k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : k == 3 ? w3 : 0x3A3A3A3Au;
+}
+
+__global__ void __launch_bounds__(128) k_paf_cigar_flat(uint64_t n_rec, const uint8_t *__restrict__ text, PafRecs R,
+                                                        const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ chunk_rec,
+                                                        unsigned long long *__restrict__ acc6, uint8_t *__restrict__ slow) {
+    const uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t P = pbase[n_rec];
+    uint64_t g0 = c * kCigChunk;
+    if (g0 >= P) return;
+    const uint64_t g_end = g0 + kCigChunk < P ? g0 + kCigChunk : P;
+    uint64_t r0 = chunk_rec[c];
+    uint32_t carry_val = 0, carry_nd = 0;  // trailing number of the piece before the step
+    if (g0 > pbase[r0]) {  // the chunk starts inside record r0: every lane reads the piece before it (one address)
+        const uint8_t *p = text + R.cig_off[r0];
+        const uint8_t *base = p - (reinterpret_cast<uintptr_t>(p) & 15u);
+        const uint4 prev = ldg16(base + 16 * (g0 - pbase[r0] - 1));
+        carry_nd = cig_trailing(prev, carry_val);
+    }
+    for (; g0 < g_end; g0 += 32) {
+        // ---- which record does piece g0 + lane belong to: boundaries pbase[r0 + 1 ..] that fall into (g0, g0 + 32]
+        const uint64_t bi = r0 + 1 + lane;
+        const uint64_t rel = (bi <= n_rec ? pbase[bi] : ~0ull) - g0;
+        const uint32_t M = __reduce_or_sync(0xFFFFFFFFu, (rel >= 1 && rel <= 32) ? 1u << (uint32_t)(rel - 1) : 0u);
+        const uint64_t r = r0 + __popc(M & ((1u << lane) - 1u));
+        r0 += __popc(M);
+        const uint64_t g = g0 + lane;
+        const bool have = g < g_end;
+        uint4 cur = make_uint4(0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au, 0x3A3A3A3Au);
+        uint64_t vi = 0, len = 0, a = 0;
+        bool dummy = true;
+        if (have) {
+            len = R.cig_len[r];
+            dummy = (R.neg[r] & 2) || len == 0;
+            if (!dummy) {
+                const uint8_t *p = text + R.cig_off[r];
+                a = reinterpret_cast<uintptr_t>(p) & 15u;
+                vi = g - pbase[r];
+                cur = ldg16(p - a + 16 * vi);
+            }
+        }
+        // ---- phase 1: digit run at the end of the piece, handed to the right neighbour
+        uint32_t t_val;
+        const uint32_t t_nd = cig_trailing(cur, t_val);
+        uint32_t val = __shfl_up_sync(0xFFFFFFFFu, t_val, 1), nd = __shfl_up_sync(0xFFFFFFFFu, t_nd, 1);
+        if (lane == 0) { val = carry_val; nd = carry_nd; }
+        carry_val = __shfl_sync(0xFFFFFFFFu, t_val, 31);
+        carry_nd = __shfl_sync(0xFFFFFFFFu, t_nd, 31);
+        uint32_t am = 0, ax = 0, ai = 0, ad = 0, e_i = 0, e_d = 0;
+        bool bad = false;
+        if (have && !dummy) {
+            // ---- phase 2: one iteration per op character of the piece
+            const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;  // CIGAR index of byte 0 of this piece
+            const uint32_t klo = idx0 < 0 ? (uint32_t)-idx0 : 0u;
+            const uint32_t khi = (uint64_t)(idx0 + 16) > len ? (uint32_t)((int64_t)len - idx0) : 16u;
+            if (vi == 0) { val = 0; nd = 0; }  // nothing belongs to the CIGAR on the left of its first piece
+            const uint32_t w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
+            const uint32_t dg16 = movemask4(digit_flags(w0)) | (movemask4(digit_flags(w1)) << 4) | (movemask4(digit_flags(w2)) << 8) |
+                                  (movemask4(digit_flags(w3)) << 12);
+            const uint32_t rm = ((1u << khi) - 1u) & ~((1u << klo) - 1u);
+            uint32_t ops = ~dg16 & rm;
+            uint32_t start = klo;
+            while (ops) {
+                const uint32_t p = __ffs(ops) - 1;
+                ops &= ops - 1;
+                const uint32_t ndl = p - start;  // digits of this token inside the piece
+                uint32_t v = 0;
+                if (ndl) {
+                    const uint32_t k = start >> 2, sh = (start & 3u) * 8u;
+                    const uint32_t lo = sel4(w0, w1, w2, w3, k), mid = sel4(w0, w1, w2, w3, k + 1);
+                    const uint32_t W = __funnelshift_r(lo, mid, sh);
+                    if (ndl <= 4) {
+                        const uint32_t X = (W << (8u * (4u - ndl))) & 0x0F0F0F0Fu;
+                        const uint32_t t = X * 10u + (X >> 8);
+                        v = (t & 0xFFu) * 100u + ((t >> 16) & 0xFFu);
+                    } else if (ndl <= 8) {
+                        const uint32_t W2 = __funnelshift_r(mid, sel4(w0, w1, w2, w3, k + 2), sh);
+                        unsigned long long X = (((unsigned long long)W2 << 32) | W) << (8u * (8u - ndl));
+                        X &= 0x0F0F0F0F0F0F0F0Full;
+                        X = X * 10 + (X >> 8);
+                        X = (((X & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((X >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
+                        v = (uint32_t)X;
+                    }
+                }
+                const uint32_t tot = nd + ndl;
+                if (nd) {  // the token began in the previous piece: val * 10^ndl + v
+                    uint32_t p10 = 1;
+                    if (ndl & 1u) p10 *= 10u;
+                    if (ndl & 2u) p10 *= 100u;
+                    if (ndl & 4u) p10 *= 10000u;
+                    if (ndl & 8u) p10 *= 100000000u;
+                    v += val * p10;
+                }
+                const uint32_t ch = (sel4(w0, w1, w2, w3, p >> 2) >> (8u * (p & 3u))) & 0xFFu;
+                // '=' 'D' 'I' 'M' 'X' = 0x3D + {0, 7, 12, 16, 27}
+                const uint32_t o = ch - 0x3Du;
+                const bool valid = o < 28u && ((0x08011081u >> o) & 1u);
+                bad = bad || !valid || tot == 0u || tot > 8u;
+                const bool m = ch == 'M' || ch == '=', x = ch == 'X', ii = ch == 'I', dd = ch == 'D';
+                am += m ? v : 0u; ax += x ? v : 0u; ai += ii ? v : 0u; ad += dd ? v : 0u;
+                e_i += ii ? 1u : 0u; e_d += dd ? 1u : 0u;
+                nd = 0; val = 0;
+                start = p + 1;
+            }
+            // digits after the last op of the piece belong to the next piece's first token; the CIGAR must not end in them
+            if ((uint64_t)(idx0 + 16) >= len && start < khi) bad = true;
+        }
+        // ---- per-record sums: lanes of one record are contiguous; one warp-uniform pass per run of the step (full-mask
+        //      REDUX; u32 run totals can overflow -- 32 pieces x 2 eight-digit tokens -- so 16-bit halves are added)
+        uint32_t heads = (M << 1) | 1u;  // bit i: lane i starts a run
+        const uint32_t rare_v = ax | ai | ad | (bad ? 1u : 0u);
+        while (heads) {
+            const uint32_t h = __ffs(heads) - 1;
+            heads &= heads - 1;
+            const uint32_t e = heads ? (uint32_t)__ffs(heads) - 1u : 32u;
+            const bool in = lane >= h && lane < e;
+            const uint32_t s_lo = __reduce_add_sync(0xFFFFFFFFu, in ? am & 0xFFFFu : 0u), s_hi = __reduce_add_sync(0xFFFFFFFFu, in ? am >> 16 : 0u);
+            const uint32_t rare = __reduce_or_sync(0xFFFFFFFFu, in ? rare_v : 0u);
+            const bool owner = lane == h && have;
+            unsigned long long *o6 = acc6 + r * 6;
+            if (owner) {
+                const unsigned long long sm = ((unsigned long long)s_hi << 16) + s_lo;
+                if (sm) atomicAdd(o6 + 0, sm);
+            }
+            if (rare) {
+                const uint32_t x_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ax & 0xFFFFu : 0u), x_hi = __reduce_add_sync(0xFFFFFFFFu, in ? ax >> 16 : 0u);
+                const uint32_t i_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ai & 0xFFFFu : 0u), i_hi = __reduce_add_sync(0xFFFFFFFFu, in ? ai >> 16 : 0u);
+                const uint32_t d_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ad & 0xFFFFu : 0u), d_hi = __reduce_add_sync(0xFFFFFFFFu, in ? ad >> 16 : 0u);
+                const uint32_t s_ei = __reduce_add_sync(0xFFFFFFFFu, in ? e_i : 0u), s_ed = __reduce_add_sync(0xFFFFFFFFu, in ? e_d : 0u);
+                const uint32_t s_bad = __reduce_or_sync(0xFFFFFFFFu, in && bad ? 1u : 0u);
+                if (owner) {
+                    const unsigned long long sx = ((unsigned long long)x_hi << 16) + x_lo, si = ((unsigned long long)i_hi << 16) + i_lo,
+                                             sd = ((unsigned long long)d_hi << 16) + d_lo;
+                    if (sx) atomicAdd(o6 + 1, sx);
+                    if (si) atomicAdd(o6 + 2, si);
+                    if (sd) atomicAdd(o6 + 3, sd);
+                    if (s_ei) atomicAdd(o6 + 4, (unsigned long long)s_ei);
+                    if (s_ed) atomicAdd(o6 + 5, (unsigned long long)s_ed);
+                    if (s_bad) slow[r] = 1;
+                }
+            }
+        }
+    }
+}
+
+// acc6 -> the 11 counters of struct Cigar by strand (records flagged slow are redone by k_paf_cigar_counts)
+__global__ void k_cig_finish(uint64_t n_rec, PafRecs R, const unsigned long long *__restrict__ acc6, const uint8_t *__restrict__ slow,
+                             unsigned long long *__restrict__ cnt11) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec || slow[r]) return;
+    const unsigned long long *a = acc6 + r * 6;
+    const bool neg = (R.neg[r] & 1) != 0;
+    unsigned long long *o = cnt11 + r * 11;
+    o[0] = a[0]; o[1] = a[1];
+    o[2] = neg ? 0 : a[4]; o[3] = neg ? 0 : a[2]; o[4] = neg ? 0 : a[5]; o[5] = neg ? 0 : a[3];
+    o[6] = neg ? a[4] : 0; o[7] = neg ? a[2] : 0; o[8] = neg ? a[5] : 0; o[9] = neg ? a[3] : 0;
+    o[10] = neg ? 1 : 0;
+}
+
 // The same warp-per-record scan producing the ordered OP TABLE of every record (paf2chain; the op tables of paf2maf /
 // call -f paf / pafpseudo still use their one-thread kernels).  PASS 0: ops per record + the slow flag (malformed or
 // 9+ digit lengths: redone by the exact kernel, which also raises the reference's error); PASS 1: (length, type) of op

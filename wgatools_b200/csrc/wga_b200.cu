@@ -1279,6 +1279,33 @@ std::string paf_cigar_error_text(const std::string &cg, int code) {
     return "CIGAR error code " + std::to_string(code);
 }
 }  // namespace
+// CIGAR text -> 11 counters per record: the flattened piece stream (paf.cuh k_paf_cigar_flat) and, for the records it
+// flags (anything that is not `digits{1,8} one-of(M=XID)`, i.e. every error input), the exact one-thread kernel.
+// WGA_PAF_CIGAR_WARP=1 selects the older warp-per-record kernel.
+static int paf_cigar_counts(wga_ctx *ctx, uint64_t n_rec, uint64_t text_len, const uint8_t *d_text, const PafRecs &R,
+                            unsigned long long *cnt11, uint8_t *slow, unsigned long long *err_key) {
+    static const bool per_rec = getenv("WGA_PAF_CIGAR_WARP") != nullptr && getenv("WGA_PAF_CIGAR_WARP")[0] == '1';
+    if (per_rec) {
+        LAUNCH(ctx, k_paf_cigar_counts_warp, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, cnt11, slow);
+    } else {
+        // pieces <= (CIGAR bytes + 30 per record) / 16: the grid is sized for that bound, chunks past the real total exit
+        const uint64_t max_pieces = text_len / 16 + 3 * n_rec + 1, n_chunks = (max_pieces + kCigChunk - 1) / kCigChunk;
+        uint64_t *nvec = ctx->buf<uint64_t>(B_CIG_NVEC, n_rec + 1), *pbase = ctx->buf<uint64_t>(B_CIG_PBASE, n_rec + 1);
+        uint32_t *chunk_rec = ctx->buf<uint32_t>(B_CIG_CHUNK, n_chunks + 1);
+        unsigned long long *acc6 = ctx->buf<unsigned long long>(B_CIG_ACC, n_rec * 6);
+        if (!nvec || !pbase || !chunk_rec || !acc6) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(acc6, 0, n_rec * 48, ctx->stream));
+        LAUNCH(ctx, k_cig_pieces, grid_for(n_rec + 1, 256), 256, n_rec, d_text, R, nvec, slow);
+        WGA_TRY(exclusive_sum(ctx, nvec, pbase, n_rec + 1));
+        LAUNCH(ctx, k_cig_chunk_rec, grid_for(n_rec, 256), 256, n_rec, (const uint64_t *)pbase, chunk_rec);
+        LAUNCH(ctx, k_paf_cigar_flat, grid_for(n_chunks * 32, 128), 128, n_rec, d_text, R, (const uint64_t *)pbase,
+               (const uint32_t *)chunk_rec, acc6, slow);
+        LAUNCH(ctx, k_cig_finish, grid_for(n_rec, 256), 256, n_rec, R, (const unsigned long long *)acc6, (const uint8_t *)slow, cnt11);
+    }
+    LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key, (const uint8_t *)slow);
+    return WGA_OK;
+}
+
 // cs:Z: tags standing in for a missing cg:Z: (paf.rs:129-135): k_paf_parse summed their lengths into *cs_total;
 // when there are any, k_cs_convert writes the converted CIGARs to an arena and repoints cig_off / cig_len.
 static int paf_cs_to_cigar(wga_ctx *ctx, const uint8_t *d_text, const PafRecs &R, uint64_t n_rec, unsigned long long *cs_total,
@@ -1344,8 +1371,7 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     WGA_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     uint8_t *slow = ctx->buf<uint8_t>(B_RUN_CLS, n_rec);
     if (!slow) return ctx->err_code;
-    LAUNCH(ctx, k_paf_cigar_counts_warp, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, cnt11, slow);
-    LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key, (const uint8_t *)slow);
+    WGA_TRY(paf_cigar_counts(ctx, n_rec, len, d_text, R, cnt11, slow, err_key));
     WGA_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     uint64_t key;
     WGA_TRY(read_scalars(ctx, {err_key}, &key));
@@ -2238,15 +2264,14 @@ int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint
         uint8_t *lflags = ctx->buf<uint8_t>(B_LINE_FLAGS, PP.lv.n_lines + 1);
         uint32_t *rscan = ctx->buf<uint32_t>(B_LINE_REC, PP.lv.n_lines + 1);
         LAUNCH(ctx, k_val_cols, grid_for(PP.lv.n_lines, 256), 256, PP.lv, (const uint8_t *)lflags, (const uint32_t *)rscan, C);
-        LAUNCH(ctx, k_paf_cigar_counts_warp, grid_for(n_rec * 32, 128), 128, n_rec, d_text, R, cnt11, slow);
-        LAUNCH(ctx, k_paf_cigar_counts, grid_for(n_rec, 128), 128, n_rec, d_text, R, cnt11, err_key, (const uint8_t *)slow);
+        WGA_TRY(paf_cigar_counts(ctx, n_rec, len, d_text, R, cnt11, slow, err_key));
         WGA_CK(cudaMemsetAsync(d_nbad, 0, 16, ctx->stream));
         ValView V;
         V.n_rec = n_rec; V.text = d_text; V.R = R; V.C = C; V.cnt11 = cnt11; V.fix = fix ? 1 : 0;
         V.q_len = l3; V.t_len = l3 + (n_rec + 1); V.row_len = l3 + 2 * (n_rec + 1);
         uint64_t *q_off = l3 + 3 * (n_rec + 1), *t_off = l3 + 4 * (n_rec + 1), *row_off = l3 + 5 * (n_rec + 1);
         V.q_off = q_off; V.t_off = t_off; V.row_off = row_off; V.q_out = V.t_out = V.row_out = nullptr; V.n_bad = d_nbad;
-        LAUNCH(ctx, k_val_rows<0>, grid_for(n_rec + 1, 256), 256, V);
+        LAUNCH(ctx, k_val_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V);
         WGA_TRY(exclusive_sum(ctx, V.q_len, q_off, n_rec + 1));
         WGA_TRY(exclusive_sum(ctx, V.t_len, t_off, n_rec + 1));
         WGA_TRY(exclusive_sum(ctx, V.row_len, row_off, n_rec + 1));
@@ -2268,7 +2293,7 @@ int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint
         d_rows = (char *)ctx->ensure(B_OUT, total + 16);
         if (!d_q || !d_rows) return ctx->err_code;
         V.q_out = d_q; V.t_out = d_q + sc[0]; V.row_out = d_rows;
-        LAUNCH(ctx, k_val_rows<1>, grid_for(n_rec + 1, 256), 256, V);
+        LAUNCH(ctx, k_val_rows_warp<1>, grid_for((n_rec + 1) * 32, 128), 128, V);
         qlist.resize(sc[0]); tlist.resize(sc[1]);
         if (sc[0]) WGA_CK(cudaMemcpyAsync(&qlist[0], d_q, sc[0], cudaMemcpyDeviceToHost, ctx->stream));
         if (sc[1]) WGA_CK(cudaMemcpyAsync(&tlist[0], d_q + sc[0], sc[1], cudaMemcpyDeviceToHost, ctx->stream));
@@ -2338,7 +2363,7 @@ int wga_paf_filter(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     }
     FltView V;
     V.n_rec = n_rec; V.text = d_text; V.R = R; V.C = C; V.keep = keep; V.row_len = l2; V.row_off = l2 + (n_rec + 1); V.out = nullptr;
-    LAUNCH(ctx, k_flt_rows<0>, grid_for(n_rec + 1, 256), 256, V);
+    LAUNCH(ctx, k_flt_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V);
     WGA_TRY(exclusive_sum(ctx, V.row_len, l2 + (n_rec + 1), n_rec + 1));
     uint64_t sc[2];
     WGA_TRY(read_scalars(ctx, {l2 + (n_rec + 1) + n_rec, err_key}, sc));
@@ -2357,7 +2382,7 @@ int wga_paf_filter(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     char *d_rows = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_rows) return ctx->err_code;
     V.out = d_rows;
-    LAUNCH(ctx, k_flt_rows<1>, grid_for(n_rec + 1, 256), 256, V);
+    LAUNCH(ctx, k_flt_rows_warp<1>, grid_for((n_rec + 1) * 32, 128), 128, V);
     return finish_output(ctx, d_rows, total, mem, flags, out);
 }
 
