@@ -54,7 +54,20 @@ struct wga_stat_acc {
     std::vector<uint32_t> table;      // merged mode: open addressing, row index + 1, 0 = empty
     std::vector<uint32_t> inv_pair;   // '-'-strand records in file order: row index
     std::vector<uint64_t> inv_num;    //   and (aligned + query_aligned)
-    std::string text, blob;
+    // the TSV: a raw buffer (std::string::resize would zero-fill 10^7 bytes that are overwritten right away)
+    struct RawText {
+        std::unique_ptr<char[]> p;
+        size_t n = 0, cap = 0;
+        void clear() { n = 0; }
+        void resize_and_overwrite_compat(size_t m) {
+            if (m > cap) { p.reset(new char[m]); cap = m; }
+            n = m;
+        }
+        char *data() { return p.get(); }
+        const char *data() const { return p.get(); }
+        size_t size() const { return n; }
+    } text;
+    std::string blob;
 
     std::string_view ref_name(const Row &r) const { return std::string_view(names.data() + r.name_off, r.lr); }
     std::string_view query_name(const Row &r) const { return std::string_view(names.data() + r.name_off + r.lr, r.lq); }
@@ -101,6 +114,25 @@ struct wga_stat_acc {
         const uint32_t id = push_row(rn, lr, rs, qn, lq, qs, key);
         table[s] = id + 1;
         return id;
+    }
+    // an EMPTY accumulator takes over a table of distinct pairs (names back to back: ref then query, per pair)
+    void adopt_table(uint64_t n, const char *nm, uint64_t name_total, const uint32_t *nlen, const uint64_t *sizes /* rs, qs, key */,
+                     const uint64_t *vals, int stride) {
+        names.assign(nm, nm + name_total);
+        rows.resize(n);
+        uint64_t off = 0;
+        for (uint64_t p = 0; p < n; ++p) {
+            Row &r = rows[p];
+            r.name_off = off; r.lr = nlen[2 * p]; r.lq = nlen[2 * p + 1];
+            off += (uint64_t)r.lr + r.lq;
+            r.ref_size = sizes[3 * p]; r.query_size = sizes[3 * p + 1]; r.key = sizes[3 * p + 2];
+            const uint64_t *v = vals + p * stride;
+            for (int i = 0; i < 11; ++i) r.v[i] = v[i];
+            r.v[11] = v[11] < r.ref_size ? v[11] : r.ref_size;      // stat.rs:186,189: minima start at the sizes
+            r.v[12] = v[12] < r.query_size ? v[12] : r.query_size;
+        }
+        table.clear();
+        grow_table(n);
     }
     void add_pair_vals(uint32_t id, const uint64_t *v) {
         Row &r = rows[id];
@@ -230,11 +262,16 @@ struct wga_stat_acc {
         }
         lap("format");
         size_t total = sizeof kHeader - 1;
-        for (const auto &x : part) total += x.n;
-        text.resize(total);
-        memcpy(&text[0], kHeader, sizeof kHeader - 1);
-        size_t pos = sizeof kHeader - 1;
-        for (const auto &x : part) { memcpy(&text[pos], x.p.get(), x.n); pos += x.n; }
+        std::vector<size_t> at(nt);
+        for (unsigned t = 0; t < nt; ++t) { at[t] = total; total += part[t].n; }
+        text.resize_and_overwrite_compat(total);
+        memcpy(text.data(), kHeader, sizeof kHeader - 1);
+        if (nt == 1) memcpy(text.data() + at[0], part[0].p.get(), part[0].n);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t] { memcpy(text.data() + at[t], part[t].p.get(), part[t].n); });
+            for (auto &x : th) x.join();
+        }
         lap("concat");
     }
 

@@ -982,6 +982,15 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
         const uint32_t *h_inv_pair = (const uint32_t *)(hs + o_invp);
         const uint64_t *h_inv_num = (const uint64_t *)(hs + o_invn);
         const char *h_names = hs + o_names;
+        if (acc->rows.empty() && acc->inv_pair.empty()) {
+            // first table of this accumulator (the whole job when the file is one slab): the device already made the pairs
+            // distinct and laid them out in first-occurrence order -- adopt them wholesale, no probing, no per-row copies
+            acc->adopt_table(n_pairs, h_names, name_total, h_nlen, h_sizes, h_vals, kPairVals);
+            acc->inv_pair.assign(h_inv_pair, h_inv_pair + n_inv);
+            acc->inv_num.assign(h_inv_num, h_inv_num + n_inv);
+            lap("host merge");
+            return WGA_OK;
+        }
         std::vector<uint32_t> map(n_pairs);
         acc->rows.reserve(acc->rows.size() + n_pairs);
         acc->names.reserve(acc->names.size() + name_total);
@@ -994,12 +1003,9 @@ int stat_reduce(wga_ctx *ctx, uint64_t n_rec, const RecMeta &M, const unsigned l
             nm += lr + lq;
         }
         const size_t i0 = acc->inv_pair.size();
-        acc->inv_pair.resize(i0 + n_inv);
-        acc->inv_num.resize(i0 + n_inv);
-        for (uint64_t i = 0; i < n_inv; ++i) {
-            acc->inv_pair[i0 + i] = map[h_inv_pair[i]];
-            acc->inv_num[i0 + i] = h_inv_num[i];
-        }
+        acc->inv_pair.reserve(i0 + n_inv);
+        for (uint64_t i = 0; i < n_inv; ++i) acc->inv_pair.push_back(map[h_inv_pair[i]]);
+        acc->inv_num.insert(acc->inv_num.end(), h_inv_num, h_inv_num + n_inv);
         lap("host merge");
         return WGA_OK;
     }
