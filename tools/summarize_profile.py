@@ -9,6 +9,7 @@ import sys
 
 tag = sys.argv[1]
 note = sys.argv[2] if len(sys.argv) > 2 else ""
+blocks = sys.argv[3] if len(sys.argv) > 3 else "1000000"
 os.makedirs("profiles", exist_ok=True)
 lines = [l for l in open(f"gpurun_out/launches_{tag}.csv") if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
@@ -20,8 +21,9 @@ for r in rows:
 tot = sum(d[1] for d in agg.values())
 with open(f"profiles/{tag}_launches.md", "w") as f:
     f.write(f"# ncu launch list `{tag}` — {note}\n\n")
-    f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --blocks 200000 --steps 1 "
-            "--warmup 3` (cold-cache, serialised: compare SHARES, not absolutes).  "
+    f.write(f"Command (tools/profile.sh): `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --blocks {blocks} "
+            "--steps 1 --warmup 3 --no-e2e --no-indep --no-side --no-sharded` (cold-cache, serialised: compare SHARES, not absolutes; the "
+            "`at::...FillFunctor` launches are torch zero-filling the bench's device buffer, outside every step).  "
             f"{len(rows)} launches, {tot / 1e6:.2f} ms in total.\n\n| kernel | launches | total ms | us/launch | share |\n|---|---:|---:|---:|---:|\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k[:90]}` | {n} | {t / 1e6:.3f} | {t / n / 1e3:.1f} | {100 * t / tot:.1f}% |\n")
@@ -38,8 +40,8 @@ if os.path.exists(rep):
             "lts__t_sector_hit_rate.pct"]
     with open(f"profiles/{tag}_walk_ncu.md", "w") as f:
         f.write(f"# ncu --set full, dense column-walk kernel, `{tag}` — {note}\n\n")
-        f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:k_walk -s 6 -c 5 python bench.py --blocks 200000 "
-                "--steps 1 --warmup 3`.  Input 1.34 GB MAF (2 x 0.66 G columns).  Never a bench value: kernels are replayed.\n\n")
+        f.write(f"Command (tools/profile.sh): `ncu --set full --clock-control none --import-source on -k regex:k_walk_tma -s 4 -c 1 python bench.py "
+                f"--blocks {blocks} --steps 1 --warmup 3 ...`.  Never a bench value: kernels are replayed.\n\n")
         for d in data:
             f.write(f"## {d[idx['Kernel Name']]}\n\n| metric | value | unit |\n|---|---:|---|\n")
             for w in want:

@@ -445,7 +445,8 @@ __global__ void k_pp_target_rows(PpView V, const uint64_t *__restrict__ thead_po
         dst[b] = src ? (char)src[b] : 'N';
 }
 
-// one warp per CIGAR op (+ one virtual op per sorted record: the query bases left over after the last op)
+// one warp per CIGAR op (+ one virtual op per sorted record: the query bases left over after the last op); with a FASTA
+// the warp of the first op of every gap-free stretch copies the whole stretch (16-byte stores)
 __global__ void k_pp_rows(PpView V) {
     const uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -460,6 +461,20 @@ __global__ void k_pp_rows(PpView V) {
         len = V.op_len[wid];
         type = V.op_type[wid];
         if (type == PO_I || type == PO_D) return;  // nothing to write: deleted bases / '-' is the fill value
+        if (V.base) {
+            // with a FASTA the M / = / X ops between two gap ops copy ONE contiguous stretch of the query to ONE contiguous
+            // stretch of the row: the first op of the stretch copies all of it, the others have nothing left to do
+            if (wid > b0) { const uint8_t pt = V.op_type[wid - 1]; if (pt != PO_I && pt != PO_D) return; }
+            const uint64_t b1 = V.op_base[i + 1];
+            uint64_t g = wid + 1;
+            for (;; g += 32) {  // first gap op (or the record's end) after this op
+                const uint64_t k = g + lane;
+                const bool stop = k >= b1 || V.op_type[k] == PO_I || V.op_type[k] == PO_D;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, stop);
+                if (m) { g += (uint32_t)__ffs(m) - 1u; break; }
+            }
+            len = V.S_out[g] - V.S_out[wid];
+        }
     } else {
         i = wid - V.n_ops;
         if (!V.base || !(V.S.flags[i] & PP_KEPT)) return;
@@ -485,8 +500,9 @@ __global__ void k_pp_rows(PpView V) {
     }
     const uint8_t *Q = V.seq + V.S.q_src[i];
     const uint64_t LQ = V.S.LQ[i];
-    if (!(V.R.neg[V.ord[i]] & 1)) { if (n > j0) warp_copy(piece + o + j0 - ov, Q + src + j0, n - j0, lane); }
-    else for (uint64_t j = j0 + lane; j < n; j += 32) piece[o + j - ov] = (char)comp_base(Q[LQ - 1 - (src + j)]);
+    if (n <= j0) return;
+    if (!(V.R.neg[V.ord[i]] & 1)) warp_copy16(piece + o + j0 - ov, Q + src + j0, n - j0, lane);
+    else warp_revcomp16(piece + o + j0 - ov, Q + LQ - (src + j0), n - j0, lane);  // bases validated by k_pp_revcomp_check
 }
 
 // per target file: name and byte range, for the host-side index

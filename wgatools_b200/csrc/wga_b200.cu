@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <new>
 #include "ctx.cuh"
 #include "emit_paf.cuh"
 #include "stat.cuh"
@@ -25,6 +26,19 @@
 #include "chain_in.cuh"
 
 using namespace wga;
+
+// No C++ exception crosses the C ABI (include/wga_b200.h: entry points never abort or throw): host-side STL work runs
+// under this guard.
+template <class F>
+static int no_throw(F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return WGA_E_NOMEM;
+    } catch (...) {
+        return WGA_E_INTERNAL;
+    }
+}
 
 namespace {
 
@@ -847,29 +861,35 @@ int wga_maf_plotdata(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint
 
 // ---------------------------------------------------------------- stat
 wga_stat_acc *wga_stat_acc_create(int each) {
-    wga_stat_acc *a = new wga_stat_acc();
-    a->each = each ? 1 : 0;
+    wga_stat_acc *a = new (std::nothrow) wga_stat_acc();
+    if (a) a->each = each ? 1 : 0;
     return a;
 }
 void wga_stat_acc_destroy(wga_stat_acc *acc) { delete acc; }
 uint64_t wga_stat_acc_npairs(const wga_stat_acc *acc) { return acc ? acc->rows.size() : 0; }
 int wga_stat_acc_write(wga_stat_acc *acc, wga_span *out) {
     if (!acc || !out) return WGA_E_INVALID_ARG;
-    acc->write();
-    out->data = acc->text.data();
-    out->len = acc->text.size();
-    return WGA_OK;
+    out->data = nullptr; out->len = 0;
+    return no_throw([&] {
+        acc->write();
+        out->data = acc->text.data();
+        out->len = acc->text.size();
+        return (int)WGA_OK;
+    });
 }
 int wga_stat_acc_export(wga_stat_acc *acc, wga_span *blob) {
     if (!acc || !blob) return WGA_E_INVALID_ARG;
-    acc->export_blob();
-    blob->data = acc->blob.data();
-    blob->len = acc->blob.size();
-    return WGA_OK;
+    blob->data = nullptr; blob->len = 0;
+    return no_throw([&] {
+        acc->export_blob();
+        blob->data = acc->blob.data();
+        blob->len = acc->blob.size();
+        return (int)WGA_OK;
+    });
 }
 int wga_stat_acc_import(wga_stat_acc *acc, const void *blob, uint64_t len) {
     if (!acc || !blob) return WGA_E_INVALID_ARG;
-    return acc->import_blob((const char *)blob, len);
+    return no_throw([&] { return acc->import_blob((const char *)blob, len); });
 }
 
 }  // extern "C"
@@ -1106,7 +1126,7 @@ int wga_maf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     unsigned long long *err_key = ctx->buf<unsigned long long>(B_ERR, 2);
     if (!err_key) return ctx->err_code;
     if (reuse) LAUNCH(ctx, k_init_u64, 1, 1, err_key, 1, kNoErr);
-    int rc = stat_reduce(ctx, n_rec, M, cnt11, err_key, acc);
+    int rc = no_throw([&] { return stat_reduce(ctx, n_rec, M, cnt11, err_key, acc); });
     if (rc) return rc;
     if (ctx->walk_launches) {
         float ms = 0.f;
@@ -1409,7 +1429,7 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     M.t_name_off = R.t_name_off; M.q_name_off = R.q_name_off; M.t_name_len = R.t_name_len; M.q_name_len = R.q_name_len;
     M.t_size = R.t_size; M.q_size = R.q_size; M.t_start = R.t_start; M.q_start = R.q_start;
     M.neg = R.neg; M.skip = nullptr;
-    int rc = stat_reduce(ctx, n_rec, M, cnt11, err_key, acc);
+    int rc = no_throw([&] { return stat_reduce(ctx, n_rec, M, cnt11, err_key, acc); });
     if (rc) return rc;
     ctx->last_counts_valid = true;
     return WGA_OK;
