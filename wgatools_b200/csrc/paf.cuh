@@ -404,95 +404,100 @@ __global__ void __launch_bounds__(128) k_paf_cigar_flat(uint64_t n_rec, const ui
         uint32_t am = 0, ax = 0, ai = 0, ad = 0, e_i = 0, e_d = 0;
         bool bad = false;
         if (have && !dummy) {
-            // ---- phase 2: one iteration per op character of the piece
+            // ---- phase 2: the 16 bytes, branch-free and fully unrolled (CIGAR text runs ~2.5 bytes per token: a loop over
+            //      the tokens diverges and costs ~100 instructions each, this costs ~20 per byte).  Bytes outside the CIGAR
+            //      are replaced by 'M' (adds the running value 0 to the total); structure is checked on bit masks afterwards.
             const int64_t idx0 = (int64_t)(16 * vi) - (int64_t)a;  // CIGAR index of byte 0 of this piece
             const uint32_t klo = idx0 < 0 ? (uint32_t)-idx0 : 0u;
             const uint32_t khi = (uint64_t)(idx0 + 16) > len ? (uint32_t)((int64_t)len - idx0) : 16u;
             if (vi == 0) { val = 0; nd = 0; }  // nothing belongs to the CIGAR on the left of its first piece
-            const uint32_t w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
-            const uint32_t dg16 = movemask4(digit_flags(w0)) | (movemask4(digit_flags(w1)) << 4) | (movemask4(digit_flags(w2)) << 8) |
-                                  (movemask4(digit_flags(w3)) << 12);
+            uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
             const uint32_t rm = ((1u << khi) - 1u) & ~((1u << klo) - 1u);
-            uint32_t ops = ~dg16 & rm;
-            uint32_t start = klo;
-            while (ops) {
-                const uint32_t p = __ffs(ops) - 1;
-                ops &= ops - 1;
-                const uint32_t ndl = p - start;  // digits of this token inside the piece
-                uint32_t v = 0;
-                if (ndl) {
-                    const uint32_t k = start >> 2, sh = (start & 3u) * 8u;
-                    const uint32_t lo = sel4(w0, w1, w2, w3, k), mid = sel4(w0, w1, w2, w3, k + 1);
-                    const uint32_t W = __funnelshift_r(lo, mid, sh);
-                    if (ndl <= 4) {
-                        const uint32_t X = (W << (8u * (4u - ndl))) & 0x0F0F0F0Fu;
-                        const uint32_t t = X * 10u + (X >> 8);
-                        v = (t & 0xFFu) * 100u + ((t >> 16) & 0xFFu);
-                    } else if (ndl <= 8) {
-                        const uint32_t W2 = __funnelshift_r(mid, sel4(w0, w1, w2, w3, k + 2), sh);
-                        unsigned long long X = (((unsigned long long)W2 << 32) | W) << (8u * (8u - ndl));
-                        X &= 0x0F0F0F0F0F0F0F0Full;
-                        X = X * 10 + (X >> 8);
-                        X = (((X & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((X >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
-                        v = (uint32_t)X;
-                    }
+            if (rm != 0xFFFFu) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t in4 = (rm >> (4 * q)) & 0xFu;  // bit b: byte b of word q is inside the CIGAR
+                    const uint32_t bm = ((in4 & 1u) * 0xFFu) | ((in4 & 2u) * 0x7F80u) | ((in4 & 4u) * 0x3FC000u) | ((in4 & 8u) * 0x1FE00000u);
+                    w[q] = (w[q] & bm) | (0x4D4D4D4Du & ~bm);
                 }
-                const uint32_t tot = nd + ndl;
-                if (nd) {  // the token began in the previous piece: val * 10^ndl + v
-                    uint32_t p10 = 1;
-                    if (ndl & 1u) p10 *= 10u;
-                    if (ndl & 2u) p10 *= 100u;
-                    if (ndl & 4u) p10 *= 10000u;
-                    if (ndl & 8u) p10 *= 100000000u;
-                    v += val * p10;
-                }
-                const uint32_t ch = (sel4(w0, w1, w2, w3, p >> 2) >> (8u * (p & 3u))) & 0xFFu;
-                // '=' 'D' 'I' 'M' 'X' = 0x3D + {0, 7, 12, 16, 27}
-                const uint32_t o = ch - 0x3Du;
-                const bool valid = o < 28u && ((0x08011081u >> o) & 1u);
-                bad = bad || !valid || tot == 0u || tot > 8u;
-                const bool m = ch == 'M' || ch == '=', x = ch == 'X', ii = ch == 'I', dd = ch == 'D';
-                am += m ? v : 0u; ax += x ? v : 0u; ai += ii ? v : 0u; ad += dd ? v : 0u;
-                e_i += ii ? 1u : 0u; e_d += dd ? 1u : 0u;
-                nd = 0; val = 0;
-                start = p + 1;
             }
-            // digits after the last op of the piece belong to the next piece's first token; the CIGAR must not end in them
-            if ((uint64_t)(idx0 + 16) >= len && start < khi) bad = true;
+            uint32_t tot = 0, ev = 0, nok = 0, v = val;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t ch = __byte_perm(w[k >> 2], 0u, 0x4440u | (uint32_t)(k & 3));
+                // predicated adds spelled in PTX (nvcc turns the C++ `if (c) x += v` into SEL + IADD, twice the instructions):
+                //   any non-digit closes the running number into `tot`, X / I / D also into their own sums, I / D count events
+                asm("{\n\t.reg .pred pd, px, pi, pe;\n\t.reg .u32 dg, ok;\n\t"
+                    "sub.u32 dg, %7, 48;\n\t"
+                    "setp.lt.u32 pd, dg, 10;\n\t"
+                    "setp.eq.u32 px, %7, 88;\n\t"
+                    "setp.eq.u32 pi, %7, 73;\n\t"
+                    "setp.eq.u32 pe, %7, 68;\n\t"
+                    "@!pd add.u32 %0, %0, %5;\n\t"
+                    "@px add.u32 %1, %1, %5;\n\t"
+                    "@pi add.u32 %2, %2, %5;\n\t"
+                    "@pe add.u32 %3, %3, %5;\n\t"
+                    "@pi add.u32 %4, %4, 1;\n\t"
+                    "@pe add.u32 %4, %4, 65536;\n\t"
+                    "sub.u32 ok, %7, 61;\n\t"           // '=' 'D' 'I' 'M' 'X' = 0x3D + {0, 7, 12, 16, 27}; shr clamps: other bytes give 0
+                    "shr.u32 ok, 0x08011081, ok;\n\t"
+                    "and.b32 ok, ok, 1;\n\t"
+                    "add.u32 %6, %6, ok;\n\t"
+                    "mad.lo.u32 %5, %5, 10, dg;\n\t"
+                    "@!pd mov.u32 %5, 0;\n\t}"
+                    : "+r"(tot), "+r"(ax), "+r"(ai), "+r"(ad), "+r"(ev), "+r"(v), "+r"(nok)
+                    : "r"(ch));
+            }
+            am = tot - ax - ai - ad;
+            e_i = ev & 0xFFFFu; e_d = ev >> 16;
+            const uint32_t dmask = movemask4(digit_flags(w[0])) | (movemask4(digit_flags(w[1])) << 4) | (movemask4(digit_flags(w[2])) << 8) |
+                                   (movemask4(digit_flags(w[3])) << 12);
+            const uint32_t nd16 = ~dmask & 0xFFFFu;
+            // every non-digit byte must be one of M = X I D (the bytes outside the CIGAR were replaced by 'M'); no op right
+            // after a non-digit (no digits of its own: the byte before the CIGAR's first byte counts as one, the left
+            // neighbour's last byte is a non-digit iff it hands over 0 digits)
+            const uint32_t prev_nd = (nd16 << 1) | ((vi == 0 || nd == 0u) ? 1u : 0u);
+            bad = nok != (uint32_t)__popc(nd16) || (nd16 & prev_nd & rm);
+            // more than 8 digits: nine in a row inside the piece, or the run that continues the left neighbour's
+            uint32_t r8 = dmask & (dmask >> 1);
+            r8 &= r8 >> 2;
+            r8 &= r8 >> 4;
+            const uint32_t lead = (uint32_t)__ffs(~dmask) - 1u;  // digits at the start of the piece (dmask has 16 bits: < 32)
+            bad = bad || (r8 & (dmask >> 8)) || (nd + lead > 8u && nd != 0u);
+            // the CIGAR must not end in a digit
+            if ((uint64_t)(idx0 + 16) >= len && ((dmask >> (khi - 1u)) & 1u)) bad = true;
         }
-        // ---- per-record sums: lanes of one record are contiguous; one warp-uniform pass per run of the step (full-mask
-        //      REDUX; u32 run totals can overflow -- 32 pieces x 2 eight-digit tokens -- so 16-bit halves are added)
+        // ---- per-record sums: lanes of one record are contiguous; one warp-uniform pass per run of the step, seven
+        //      full-mask REDUX each.  A lane's sums are < 2^28 (two eight-digit tokens per piece at most): the low 24 bits of
+        //      the four sums are added as they are (32 x 2^24 fits), the high 4 bits and the two event counts ride in
+        //      10-bit fields (32 x 15 and 32 x 8 fit).
         uint32_t heads = (M << 1) | 1u;  // bit i: lane i starts a run
-        const uint32_t rare_v = ax | ai | ad | (bad ? 1u : 0u);
+        const uint32_t hiA = (ax >> 24) | ((ai >> 24) << 10) | ((ad >> 24) << 20);
+        const uint32_t hiB = (am >> 24) | (e_i << 10) | (e_d << 20);
         while (heads) {
             const uint32_t h = __ffs(heads) - 1;
             heads &= heads - 1;
             const uint32_t e = heads ? (uint32_t)__ffs(heads) - 1u : 32u;
             const bool in = lane >= h && lane < e;
-            const uint32_t s_lo = __reduce_add_sync(0xFFFFFFFFu, in ? am & 0xFFFFu : 0u), s_hi = __reduce_add_sync(0xFFFFFFFFu, in ? am >> 16 : 0u);
-            const uint32_t rare = __reduce_or_sync(0xFFFFFFFFu, in ? rare_v : 0u);
-            const bool owner = lane == h && have;
-            unsigned long long *o6 = acc6 + r * 6;
-            if (owner) {
-                const unsigned long long sm = ((unsigned long long)s_hi << 16) + s_lo;
+            const uint32_t m_lo = __reduce_add_sync(0xFFFFFFFFu, in ? am & 0xFFFFFFu : 0u);
+            const uint32_t x_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ax & 0xFFFFFFu : 0u);
+            const uint32_t i_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ai & 0xFFFFFFu : 0u);
+            const uint32_t d_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ad & 0xFFFFFFu : 0u);
+            const uint32_t sA = __reduce_add_sync(0xFFFFFFFFu, in ? hiA : 0u), sB = __reduce_add_sync(0xFFFFFFFFu, in ? hiB : 0u);
+            const uint32_t s_bad = __reduce_or_sync(0xFFFFFFFFu, in && bad ? 1u : 0u);
+            if (lane == h && have) {
+                unsigned long long *o6 = acc6 + r * 6;
+                const unsigned long long sm = ((unsigned long long)(sB & 0x3FFu) << 24) + m_lo, sx = ((unsigned long long)(sA & 0x3FFu) << 24) + x_lo,
+                                         si = ((unsigned long long)((sA >> 10) & 0x3FFu) << 24) + i_lo,
+                                         sd = ((unsigned long long)((sA >> 20) & 0x3FFu) << 24) + d_lo;
+                const uint32_t s_ei = (sB >> 10) & 0x3FFu, s_ed = (sB >> 20) & 0x3FFu;
                 if (sm) atomicAdd(o6 + 0, sm);
-            }
-            if (rare) {
-                const uint32_t x_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ax & 0xFFFFu : 0u), x_hi = __reduce_add_sync(0xFFFFFFFFu, in ? ax >> 16 : 0u);
-                const uint32_t i_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ai & 0xFFFFu : 0u), i_hi = __reduce_add_sync(0xFFFFFFFFu, in ? ai >> 16 : 0u);
-                const uint32_t d_lo = __reduce_add_sync(0xFFFFFFFFu, in ? ad & 0xFFFFu : 0u), d_hi = __reduce_add_sync(0xFFFFFFFFu, in ? ad >> 16 : 0u);
-                const uint32_t s_ei = __reduce_add_sync(0xFFFFFFFFu, in ? e_i : 0u), s_ed = __reduce_add_sync(0xFFFFFFFFu, in ? e_d : 0u);
-                const uint32_t s_bad = __reduce_or_sync(0xFFFFFFFFu, in && bad ? 1u : 0u);
-                if (owner) {
-                    const unsigned long long sx = ((unsigned long long)x_hi << 16) + x_lo, si = ((unsigned long long)i_hi << 16) + i_lo,
-                                             sd = ((unsigned long long)d_hi << 16) + d_lo;
-                    if (sx) atomicAdd(o6 + 1, sx);
-                    if (si) atomicAdd(o6 + 2, si);
-                    if (sd) atomicAdd(o6 + 3, sd);
-                    if (s_ei) atomicAdd(o6 + 4, (unsigned long long)s_ei);
-                    if (s_ed) atomicAdd(o6 + 5, (unsigned long long)s_ed);
-                    if (s_bad) slow[r] = 1;
-                }
+                if (sx) atomicAdd(o6 + 1, sx);
+                if (si) atomicAdd(o6 + 2, si);
+                if (sd) atomicAdd(o6 + 3, sd);
+                if (s_ei) atomicAdd(o6 + 4, (unsigned long long)s_ei);
+                if (s_ed) atomicAdd(o6 + 5, (unsigned long long)s_ed);
+                if (s_bad) slow[r] = 1;
             }
         }
     }
