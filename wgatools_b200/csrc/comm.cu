@@ -368,32 +368,37 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     WGA_TRY(T.allgather(carry, carry_all, (uint64_t)P * 4));
     const float *fin = carry_all + (size_t)(W - 1) * P;
     lap("inv carry");
-    // ---- rebuild the accumulator in global order
+    // ---- rebuild the accumulator in global order: rows and names are laid out in bulk (no per-row vector growth)
     wga_stat_acc out;
     out.each = 0;
-    out.rows.reserve(P);
+    out.rows.resize(P);
     {
         size_t name_bytes = 0;
-        for (int r = 0; r < W; ++r) name_bytes += blob_len[r];
-        out.names.reserve(name_bytes);
+        for (int r = 0; r < W; ++r) name_bytes += blob_len[r];  // upper bound: the blobs also hold 32 header bytes per pair
+        out.names.resize(name_bytes);
     }
     std::vector<const char *> cur(W);
     for (int r = 0; r < W; ++r) cur[r] = bl_r + (size_t)r * blob_max;
+    size_t noff = 0;
+    char *nm = out.names.data();
     for (uint32_t g = 0; g < P; ++g) {
         const char *p = cur[owner[g]];
-        uint32_t lr, lq;
-        uint64_t rs, qs, key;
-        memcpy(&lr, p, 4); memcpy(&lq, p + 4, 4); memcpy(&rs, p + 8, 8); memcpy(&qs, p + 16, 8); memcpy(&key, p + 24, 8);
+        wga_stat_acc::Row &row = out.rows[g];
+        memcpy(&row.lr, p, 4); memcpy(&row.lq, p + 4, 4); memcpy(&row.ref_size, p + 8, 8); memcpy(&row.query_size, p + 16, 8);
         // identity across ranks is the 128-bit (pair hash, key2) the dictionary was built on; the rebuilt accumulator's
         // own lookup table is made on demand from the rows' keys (find_or_add -> grow_table)
-        const uint32_t id = out.push_row(p + 32, lr, rs, p + 32 + lr, lq, qs, key);
-        cur[owner[g]] = p + 32 + lr + lq;
-        wga_stat_acc::Row &row = out.rows[id];
+        memcpy(&row.key, p + 24, 8);
+        const size_t nl = (size_t)row.lr + row.lq;
+        row.name_off = noff;
+        memcpy(nm + noff, p + 32, nl);
+        noff += nl;
+        cur[owner[g]] = p + 32 + nl;
         memcpy(row.v, sums + (size_t)g * 11, 88);
         row.v[11] = mins[2 * (size_t)g];
         row.v[12] = mins[2 * (size_t)g + 1];
         row.inv_size = fin[g];
     }
+    out.names.resize(noff);
     lap("rebuild");
     acc->names.swap(out.names);
     acc->rows.swap(out.rows);
