@@ -48,18 +48,6 @@ def make_fasta(n_genomes, n_chr, chr_size, seed=5):
     return b"".join(parts), b"".join(fai)
 
 
-def dedupe_ties(paf):
-    """pafpseudo refuses equal target_start inside one (target, query) group (unspecified order in the reference)"""
-    seen, out = set(), []
-    for l in paf.splitlines(keepends=True):
-        f = l.split(b"\t", 8)
-        k = (f[0], f[5], f[7])
-        if k not in seen:
-            seen.add(k)
-            out.append(l)
-    return b"".join(out)
-
-
 def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--records", type=int, default=2_000_000, help="config-4 PAF records for stat -f paf")
@@ -171,6 +159,30 @@ def run(args, ctx=None, emit=None):
     orc.paf_validate(smp, True)
     cpu = len(smp) / (time.perf_counter() - t0) / 1e9
     report("validate -f (config 4 shape)", len(paf), ms_dev, ms_e2e, spf.len, cpu, len(smp), {"records": args.records})
+    # filter -a (pair-sum filter, cut-off = the median pair sum would need a pre-pass: 1 Mbp keeps roughly half) and the
+    # base-level plot data on the same PAF
+    spx = w.api.Span()
+    cut = ctypes.c_uint64(1_000_000)
+
+    def fl(ptr, mem):
+        def run():
+            ctx._check(L.wga_paf_filter(ctx.h, ptr, len(paf), mem, 1, 0, 0, ctypes.byref(cut), ctypes.byref(spx)))
+        return run
+    ms_dev, ms_e2e = timed(fl(ctypes.c_void_p(d.data_ptr()), 1), args.steps), timed(fl(ctypes.c_void_p(hp), 0), args.steps)
+    t0 = time.perf_counter()
+    orc.paf_filter(smp, min_align=1_000_000)
+    cpu = len(smp) / (time.perf_counter() - t0) / 1e9
+    report("filter -f paf -a 1000000 (config 4 shape)", len(paf), ms_dev, ms_e2e, spx.len, cpu, len(smp), {"records": args.records})
+
+    def pdat(ptr, mem):
+        def run():
+            ctx._check(L.wga_paf_plotdata(ctx.h, ptr, len(paf), mem, 1, 50, ctypes.byref(spx)))
+        return run
+    ms_dev, ms_e2e = timed(pdat(ctypes.c_void_p(d.data_ptr()), 1), args.steps), timed(pdat(ctypes.c_void_p(hp), 0), args.steps)
+    t0 = time.perf_counter()
+    orc.paf_plotdata(smp, 50)
+    cpu = len(smp) / (time.perf_counter() - t0) / 1e9
+    report("dotplot base-level data -l 50 (config 4 shape)", len(paf), ms_dev, ms_e2e, spx.len, cpu, len(smp), {"records": args.records})
     # pafcov: one BED line per target base, so a PAF over a small target set (10 x 2 Mbp)
     pafc = bs.gen_paf(bs.paf_params(200_000, seed=20260930, n_genomes=2, n_chr=5, chr_size=2_000_000, ops_median=150.0, ops_max=2000))
     dc = resident(pafc)
@@ -198,7 +210,6 @@ def run(args, ctx=None, emit=None):
     F = w.Fasta(ctx, fa, fai)
     paf5 = bs.gen_paf(bs.paf_params(args.fa_records, seed=20260929, n_genomes=args.genomes, n_chr=args.chrs, chr_size=chr_size,
                                     ops_median=150.0, ops_max=2000))
-    paf5 = dedupe_ties(paf5)
     d5 = resident(paf5)
     hp5 = pinned_copy(paf5)
     sp, sp2 = w.api.Span(), w.api.Span()

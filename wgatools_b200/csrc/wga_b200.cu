@@ -836,7 +836,12 @@ static int maf_run_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, u
     V.q_name_len = qnl; V.t_size = m6; V.q_size = m6 + n_rec; V.t_start = m6 + 2 * n_rec; V.t_end = m6 + 3 * n_rec;
     V.q_start = m6 + 4 * n_rec; V.q_end = m6 + 5 * n_rec; V.neg = P.rc.neg; V.skip = P.rc.skip; V.run_first = rec_run_first;
     V.run_len = run_len; V.run_type = RU.run_cls; V.maf = 1; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
-    if (kind == 0) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    static const bool chain_seq = getenv("WGA_CHAIN_SEQ") != nullptr && getenv("WGA_CHAIN_SEQ")[0] == '1';  // one thread per record
+    uint32_t *hdr_len = ctx->buf<uint32_t>(B_CHAIN_HDR, n_rec + 1);
+    uint8_t *irregular = ctx->buf<uint8_t>(B_CHAIN_IRR, n_rec + 1);
+    if (!hdr_len || !irregular) return ctx->err_code;
+    if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V, hdr_len, irregular);
     else LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
@@ -845,7 +850,8 @@ static int maf_run_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, u
     char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_out) return ctx->err_code;
     V.out = d_out;
-    if (kind == 0) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<1>, grid_for(n_rec * 32, 128), 128, V, hdr_len, irregular);
     else LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
@@ -1871,7 +1877,12 @@ static int paf_op_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, ui
     V.t_name_len = R.t_name_len; V.q_name_len = R.q_name_len; V.t_size = R.t_size; V.q_size = R.q_size; V.t_start = R.t_start;
     V.t_end = X.t_end; V.q_start = R.q_start; V.q_end = X.q_end; V.neg = R.neg; V.skip = nullptr; V.run_first = op_base;
     V.run_len = op_len; V.run_type = op_type; V.maf = 0; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
-    if (kind == 0) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    static const bool chain_seq = getenv("WGA_CHAIN_SEQ") != nullptr && getenv("WGA_CHAIN_SEQ")[0] == '1';  // one thread per record
+    uint32_t *hdr_len = ctx->buf<uint32_t>(B_CHAIN_HDR, n_rec + 1);
+    uint8_t *irregular = ctx->buf<uint8_t>(B_CHAIN_IRR, n_rec + 1);
+    if (!hdr_len || !irregular) return ctx->err_code;
+    if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
+    else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V, hdr_len, irregular);
     else LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
@@ -1880,7 +1891,8 @@ static int paf_op_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, ui
     char *d_out = (char *)ctx->ensure(B_OUT, total + 16);
     if (!d_out) return ctx->err_code;
     V.out = d_out;
-    if (kind == 0) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
+    else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<1>, grid_for(n_rec * 32, 128), 128, V, hdr_len, irregular);
     else LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
