@@ -653,3 +653,15 @@ def test_plotdata_vs_pyspec(recs, cutoff):
         qq = '"' + qn.replace('"', '""') + '"' if '"' in qn else qn
         spec.append((tq, qq, ts, qs, neg, ops))
     assert orc.paf_plotdata(b"".join(lines), cutoff).decode() == pyspec.plot_csv(spec, cutoff)
+
+
+def test_validate_report_labels_match_readme():
+    """README.md:366-372 shows the report of `wgatools validate wrong.paf`: the five labels and their order are the
+    reference's own text (the numbers there belong to a file the reference does not ship)"""
+    bad = b"q\t100\t0\t9\t+\tt\t100\t0\t12\t5\t10\t60\tcg:Z:10=\n"      # query end 9 != 0 + 10, target end 12 != 0 + 10
+    rep, _ = orc.paf_validate(bad, False)
+    lines = rep.decode().split("\n")
+    assert lines[0] == "Total records: 1" and lines[1] == "Query invalid records: 1" and lines[2] == "Target invalid records: 1"
+    assert lines[3] == "Query invalid list:" and lines[4] == "q:0-9" and lines[5] == "Target invalid list:" and lines[6] == "t:0-12"
+    for label in ("Total records: ", "Query invalid records: ", "Target invalid records: ", "Query invalid list:", "Target invalid list:"):
+        assert label.encode() in rep

@@ -51,7 +51,7 @@ enum BufId {
     B_TEXT_RES, B_TOK_ERR, B_CNT11, B_XRUN_POS, B_XRUN_REC, B_XRUN_CLS, B_XRUN_FLAG, B_XRUN_IDX,
     B_PP_A, B_PP_B, B_PP_C, B_PP_D, B_PP_E, B_PP_F, B_PP_G, B_PP_H, B_PP_I, B_PP_J, B_PP_K, B_PP_L, B_PP_M, B_PP_N, B_PP_O, B_PP_P,
     B_PP_Q, B_PP_R, B_PP_S, B_PP_T,
-    B_PAF_A, B_PAF_B, B_PAF_C, B_PAF_D, B_PAF_E, B_PAF_F, B_PAF_G, B_PAF_H, B_PAF_I, B_PAF_J, B_CS_ARENA, B_CS_TOTAL, B_CIG_NVEC, B_CIG_PBASE, B_CIG_CHUNK, B_CIG_ACC, B_CHAIN_HDR, B_CHAIN_IRR,
+    B_PAF_A, B_PAF_B, B_PAF_C, B_PAF_D, B_PAF_E, B_PAF_F, B_PAF_G, B_PAF_H, B_PAF_I, B_PAF_J, B_CS_ARENA, B_CS_TOTAL, B_CIG_NVEC, B_CIG_PBASE, B_CIG_CHUNK, B_CIG_ACC, B_CHAIN_HDR, B_CHAIN_IRR, B_UNQ_TEXT,
     B_COUNT_
 };
 

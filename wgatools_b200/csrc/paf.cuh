@@ -11,7 +11,7 @@
 // A record without cg:Z: but with a cs:Z: tag gets its CIGAR from k_cs_convert (paf.rs:159-218 cs_to_cigar), written to a
 // device arena; cig_off then points there (as a wrapped 64-bit distance from the slab text, so every consumer's
 // `text + cig_off` keeps working).
-// Not supported (reported, never silently wrong): quoted csv fields.
+// Quoted csv fields: see k_unquote_lines below (simple quoting is normalised away, the rest is reported, never silently wrong).
 #pragma once
 #include "ctx.cuh"
 #include "stat.cuh"
@@ -65,6 +65,55 @@ __device__ __forceinline__ bool csv_u64(const uint8_t *p, uint64_t n, uint64_t *
 __device__ __forceinline__ void paf_report(unsigned long long *err_key, uint64_t rec, uint64_t pos, int code) {
     if (pos > 0xFFFFFFull) pos = 0xFFFFFFull;
     atomicMin(err_key, (unsigned long long)((rec << 32) | (pos << 8) | (uint64_t)code));
+}
+
+// ---- quoted csv fields (csv reader default: quoting on).  The fast path refuses a field that starts with '"'
+// (k_paf_parse reports WGA_E_UNSUPPORTED); the entry points then normalise the text and run again: a field "abc" whose
+// content holds no quote, tab or line break -- quoting that was not needed -- is replaced by its content, which is what
+// the reader would hand to the deserializer.  Content that holds a '"' (escaped ""), a tab or a line break, text behind
+// the closing quote, or a first field whose content starts with '#', stay refused.
+// PASS 0: byte length of every normalised line (terminator included); PASS 1: the bytes.
+template <int PASS>
+__global__ void k_unquote_lines(LineView lv, const uint8_t *__restrict__ flags, uint64_t *__restrict__ new_len,
+                                const uint64_t *__restrict__ new_off, uint8_t *__restrict__ out, unsigned long long *err_key) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > lv.n_lines) return;
+    if (k == lv.n_lines) { if (PASS == 0) new_len[k] = 0; return; }
+    const uint64_t S = lv.start(k), E = lv.end(k);
+    const uint64_t term = k < lv.n_nl ? 1 : 0;  // the line's own terminator byte ('\n' or '\r') is kept
+    uint8_t *o = PASS == 1 ? out + new_off[k] : nullptr;
+    if (!flags[k]) {  // empty line or comment: verbatim
+        if (PASS == 0) new_len[k] = (E - S) + term;
+        else for (uint64_t i = S; i < E + term; ++i) *o++ = lv.text[i];
+        return;
+    }
+    const uint64_t wlo = k == 0 ? 0 : lv.nl_ws_idx[k - 1] + 1, whi = k < lv.n_nl ? lv.nl_ws_idx[k] : lv.n_ws;
+    uint64_t fb = S, w = wlo, n = 0;
+    bool complex = false;
+    for (uint64_t nf = 0;; ++nf) {
+        uint64_t fe = w < whi ? (lv.ws_ent[w] & kPosMask) : E;
+        if (fe > E) fe = E;
+        uint64_t cb = fb, ce = fe;  // content
+        if (fe > fb && lv.text[fb] == '"') {
+            bool simple = fe - fb >= 2 && lv.text[fe - 1] == '"';
+            for (uint64_t i = fb + 1; simple && i + 1 < fe; ++i) simple = lv.text[i] != '"';
+            if (simple && nf == 0 && fe - fb > 2 && lv.text[fb + 1] == '#') simple = false;  // would turn into a comment line
+            if (!simple) complex = true;
+            cb = fb + 1; ce = fe - 1;
+        }
+        if (PASS == 0) n += ce - cb;
+        else for (uint64_t i = cb; i < ce; ++i) *o++ = lv.text[i];
+        if (w >= whi) break;
+        if (PASS == 0) n += 1;
+        else *o++ = '\t';
+        fb = fe + 1;
+        ++w;
+    }
+    if (PASS == 0) {
+        if (n == 0) complex = true;  // a record of one empty quoted field is not an empty line
+        if (complex) paf_report(err_key, k, 0, WGA_E_UNSUPPORTED);
+        new_len[k] = n + term;
+    } else if (term) *o = lv.text[E];
 }
 
 // one PAF line -> 12 typed columns + cg:Z: span (paf.rs:48-65,122-140)

@@ -1311,6 +1311,57 @@ std::string paf_cigar_error_text(const std::string &cg, int code) {
     return "CIGAR error code " + std::to_string(code);
 }
 }  // namespace
+// Quoted csv fields: the front end refuses a field that starts with '"' (k_paf_parse).  The PAF entry points then
+// normalise the staged text (k_unquote_lines: quoting that was not needed is stripped; anything else stays refused) and
+// run once more on the normalised copy.  Inputs without quotes never get here.
+static int paf_unquote(wga_ctx *ctx, const uint8_t **d_out, uint64_t *len_out) {
+    const uint8_t *d_text = ctx->d_text;
+    const uint64_t len = ctx->text_len;
+    unsigned long long *err_key = ctx->buf<unsigned long long>(B_ERR, 1);
+    if (!err_key) return ctx->err_code;
+    LAUNCH(ctx, k_init_u64, 1, 1, err_key, 1, kNoErr);
+    uint64_t n_ws = 0, n_nl = 0;
+    uint64_t *ws_ent = nullptr, *nl_idx = nullptr;
+    WGA_TRY((build_delim_index<1, kTokCapPaf>(ctx, d_text, len, &n_ws, &n_nl, &ws_ent, &nl_idx)));
+    const uint8_t last_byte = *(uint8_t *)(ctx->h_scal + 8);
+    const uint64_t n_lines = n_nl + (last_byte != '\n' && last_byte != '\r' ? 1 : 0);
+    LineView lv;
+    lv.text = d_text; lv.len = len; lv.ws_ent = ws_ent; lv.nl_ws_idx = nl_idx;
+    lv.n_ws = n_ws; lv.n_nl = n_nl; lv.n_lines = n_lines; lv.first_slab = 0;
+    uint8_t *lflags = ctx->buf<uint8_t>(B_LINE_FLAGS, n_lines + 1);
+    uint32_t *isrec = ctx->buf<uint32_t>(B_LINE_HEAD, n_lines + 1);
+    uint64_t *nlen = ctx->buf<uint64_t>(B_GEN_A, n_lines + 1), *noff = ctx->buf<uint64_t>(B_GEN_B, n_lines + 1);
+    if (!lflags || !isrec || !nlen || !noff) return ctx->err_code;
+    LAUNCH(ctx, k_paf_line_flags, grid_for(n_lines + 1, 256), 256, lv, lflags, isrec);
+    LAUNCH(ctx, k_unquote_lines<0>, grid_for(n_lines + 1, 256), 256, lv, (const uint8_t *)lflags, nlen, (const uint64_t *)nullptr, (uint8_t *)nullptr,
+           err_key);
+    WGA_TRY(exclusive_sum(ctx, nlen, noff, n_lines + 1));
+    uint64_t sc[2];
+    WGA_TRY(read_scalars(ctx, {noff + n_lines, err_key}, sc));
+    if (sc[1] != kNoErr) {
+        ctx->set_error(WGA_E_UNSUPPORTED, sc[1] >> 32,
+                       "unsupported PAF construct: a quoted csv field that holds a quote, a tab or a line break, or text behind its closing "
+                       "quote (line " + std::to_string(sc[1] >> 32) + ")");
+        return WGA_E_UNSUPPORTED;
+    }
+    uint8_t *d_new = ctx->buf<uint8_t>(B_UNQ_TEXT, sc[0] + 64);
+    if (!d_new) return ctx->err_code;
+    LAUNCH(ctx, k_unquote_lines<1>, grid_for(n_lines + 1, 256), 256, lv, (const uint8_t *)lflags, nlen, (const uint64_t *)noff, d_new, err_key);
+    WGA_CK(cudaMemsetAsync(d_new + sc[0], 0, 64, ctx->stream));
+    *d_out = d_new;
+    *len_out = sc[0];
+    return WGA_OK;
+}
+// rc of a PAF command -> rc, after one retry on the normalised text when the refusal was a quoted field
+template <class F>
+static int paf_retry_unquoted(wga_ctx *ctx, int rc, int mem, uint32_t flags, F &&again) {
+    if (rc != WGA_E_UNSUPPORTED || !ctx || ctx->err_msg.find("(quoted csv field)") == std::string::npos) return rc;
+    const uint8_t *d2 = nullptr;
+    uint64_t n2 = 0;
+    WGA_TRY(paf_unquote(ctx, &d2, &n2));
+    return again((const void *)d2, n2, (int)WGA_MEM_DEVICE, flags | (mem == WGA_MEM_HOST ? (uint32_t)WGA_F_OUT_HOST : 0u));
+}
+
 // CIGAR text -> 11 counters per record: the flattened piece stream (paf.cuh k_paf_cigar_flat) and, for the records it
 // flags (anything that is not `digits{1,8} one-of(M=XID)`, i.e. every error input), the exact one-thread kernel.
 // WGA_PAF_CIGAR_WARP=1 selects the older warp-per-record kernel.
@@ -1355,7 +1406,7 @@ static int paf_cs_to_cigar(wga_ctx *ctx, const uint8_t *d_text, const PafRecs &R
 extern "C" {
 
 // ---------------------------------------------------------------- stat -f paf
-int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_stat_acc *acc) {
+static int wga_paf_stat_impl(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_stat_acc *acc) {
     (void)flags;
     if (!ctx || !acc || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
@@ -1439,6 +1490,12 @@ int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (rc) return rc;
     ctx->last_counts_valid = true;
     return WGA_OK;
+}
+int wga_paf_stat(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_stat_acc *acc) {
+    const int rc = wga_paf_stat_impl(ctx, text, len, mem, flags, acc);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return wga_paf_stat_impl(ctx, t2, n2, m2, f2, acc);
+    });
 }
 
 // ---------------------------------------------------------------- paf2maf
@@ -1626,7 +1683,7 @@ static int p2m_expand_rows(wga_ctx *ctx, const P2mView &V, uint64_t n_opsT) {
 }
 
 extern "C" {
-int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
+static int wga_paf2maf_impl(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
                 wga_span *out) {
     (void)flags;
     if (!ctx || !out || !TF || !QF || (!text && len)) return WGA_E_INVALID_ARG;
@@ -1720,9 +1777,15 @@ int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     ctx->walk_ms = ms; ctx->walk_launches = 1; ctx->walk_bytes = total;  // expansion kernel: output-bound
     return WGA_OK;
 }
+int wga_paf2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF, wga_span *out) {
+    const int rc = wga_paf2maf_impl(ctx, text, len, mem, flags, TF, QF, out);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return wga_paf2maf_impl(ctx, t2, n2, m2, f2, TF, QF, out);
+    });
+}
 
 // ---------------------------------------------------------------- call -f paf (caller.rs:268-302,610-822)
-int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
+static int wga_paf_call_impl(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF,
                  int snp, uint64_t svlen_cutoff, wga_span *out) {
     if (!ctx || !out || !TF || !QF || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
@@ -1813,6 +1876,12 @@ int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
            err_key);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
+int wga_paf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *TF, const wga_fasta *QF, int snp, uint64_t svlen_cutoff, wga_span *out) {
+    const int rc = wga_paf_call_impl(ctx, text, len, mem, flags, TF, QF, snp, svlen_cutoff, out);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return wga_paf_call_impl(ctx, t2, n2, m2, f2, TF, QF, snp, svlen_cutoff, out);
+    });
+}
 
 // ---------------------------------------------------------------- paf2chain (converter.rs:148-173)
 // kind 0: chain records; kind 1: base-level plot segments (ops other than M = X I D are legal there and ignored)
@@ -1898,11 +1967,17 @@ static int paf_op_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, ui
 }
 int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
                   uint64_t *n_records) {
-    return paf_op_rows(ctx, text, len, mem, flags, id_base, out, n_records, 0, 0);
+    const int rc = paf_op_rows(ctx, text, len, mem, flags, id_base, out, n_records, 0, 0);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return paf_op_rows(ctx, t2, n2, m2, f2, id_base, out, n_records, 0, 0);
+    });
 }
 // ---------------------------------------------------------------- dotplot -m base-level, PAF (cigar.rs:917-952)
 int wga_paf_plotdata(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t skip_cutoff, wga_span *out) {
-    return paf_op_rows(ctx, text, len, mem, flags, 0, out, nullptr, 1, skip_cutoff);
+    const int rc = paf_op_rows(ctx, text, len, mem, flags, 0, out, nullptr, 1, skip_cutoff);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return paf_op_rows(ctx, t2, n2, m2, f2, 0, out, nullptr, 1, skip_cutoff);
+    });
 }
 
 // ---------------------------------------------------------------- chain reader front end (chain.rs:27-75,206-383)
@@ -2171,7 +2246,7 @@ int wga_chain2maf(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_
 }
 
 // ---------------------------------------------------------------- pafcov (pafcov.rs:13-60, cigar.rs:710-741)
-int wga_paf_cov(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out) {
+static int wga_paf_cov_impl(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out) {
     if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
     out->data = nullptr;
@@ -2266,9 +2341,15 @@ int wga_paf_cov(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t 
     LAUNCH(ctx, k_cov_rows<1>, grid_for(n_tiles, 128), 128, V);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
+int wga_paf_cov(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out) {
+    const int rc = wga_paf_cov_impl(ctx, text, len, mem, flags, out);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return wga_paf_cov_impl(ctx, t2, n2, m2, f2, out);
+    });
+}
 
 // ---------------------------------------------------------------- validate (validate.rs:44-147)
-int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, int fix, wga_span *report,
+static int wga_paf_validate_impl(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, int fix, wga_span *report,
                      wga_span *fixed) {
     if (!ctx || !report || !fixed || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
@@ -2345,9 +2426,15 @@ int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint
     if (fix && total) return finish_output(ctx, d_rows, total, mem, flags, fixed);
     return WGA_OK;
 }
+int wga_paf_validate(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, int fix, wga_span *report, wga_span *fixed) {
+    const int rc = wga_paf_validate_impl(ctx, text, len, mem, flags, fix, report, fixed);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return wga_paf_validate_impl(ctx, t2, n2, m2, f2, fix, report, fixed);
+    });
+}
 
 // ---------------------------------------------------------------- filter -f paf (filter.rs:41-63,92-160)
-int wga_paf_filter(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t min_block_size,
+static int wga_paf_filter_impl(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t min_block_size,
                    uint64_t min_query_size, const uint64_t *min_align_size, wga_span *out) {
     if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
@@ -2423,9 +2510,15 @@ int wga_paf_filter(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     LAUNCH(ctx, k_flt_rows_warp<1>, grid_for((n_rec + 1) * 32, 128), 128, V);
     return finish_output(ctx, d_rows, total, mem, flags, out);
 }
+int wga_paf_filter(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t min_block_size, uint64_t min_query_size, const uint64_t *min_align_size, wga_span *out) {
+    const int rc = wga_paf_filter_impl(ctx, text, len, mem, flags, min_block_size, min_query_size, min_align_size, out);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return wga_paf_filter_impl(ctx, t2, n2, m2, f2, min_block_size, min_query_size, min_align_size, out);
+    });
+}
 
 // ---------------------------------------------------------------- pafpseudo (pseudomaf.rs:18-237, cigar.rs:744-804)
-int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *FA, const char *target,
+static int wga_paf_pseudo_impl(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *FA, const char *target,
                    wga_span *out, wga_span *index) {
     if (!ctx || !out || !index || (!text && len)) return WGA_E_INVALID_ARG;
     cudaSetDevice(ctx->device);
@@ -2454,7 +2547,7 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
         if (code == WGA_E_CSV) msg = "CSV deserialize error by: record " + std::to_string(rec) + " does not match the 12 typed PAF columns";
         else if (code == WGA_E_NOM) msg = "HTS library error by sequence not found in the FASTA index";
         else if (code == WGA_E_CIGAR_TAG_NOT_FOUND) msg = "CIGAR start tag not found";
-        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported input: quoted csv field";
+        else if (code == WGA_E_UNSUPPORTED) msg = "unsupported PAF construct (quoted csv field)";
         else if (code == WGA_E_VCF_BASE) msg = "Invalid Base in a '-' strand query";
         else if (code == WGA_E_CIGAR_OP_INVALID) msg = "CIGAR OP invalid";
         else if (code == WGA_E_PARSE_INT) msg = "Parse Into Integer Error";
@@ -2627,6 +2720,12 @@ int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32
     WGA_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->walk_ms = ms; ctx->walk_launches = 1; ctx->walk_bytes = total;  // expansion: output-bound
     return WGA_OK;
+}
+int wga_paf_pseudo(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_fasta *FA, const char *target, wga_span *out, wga_span *index) {
+    const int rc = wga_paf_pseudo_impl(ctx, text, len, mem, flags, FA, target, out, index);
+    return paf_retry_unquoted(ctx, rc, mem, flags, [&](const void *t2, uint64_t n2, int m2, uint32_t f2) {
+        return wga_paf_pseudo_impl(ctx, t2, n2, m2, f2, FA, target, out, index);
+    });
 }
 
 
