@@ -52,7 +52,9 @@ enum wga_status {
     /* library errors */
     WGA_E_CUDA = 100,
     WGA_E_INVALID_ARG = 101,
-    WGA_E_UNSUPPORTED = 102,
+    WGA_E_UNSUPPORTED = 102,        /* input the reference accepts and this library reports instead of parsing: a csv-quoted PAF
+                                     * field whose content holds a quote, a tab or a line break (plain quoted fields are fine);
+                                     * `chain` in the middle of a line; call: --query-regex / <maf>.index */
     WGA_E_NOMEM = 103,
     WGA_E_INTERNAL = 104,
     WGA_E_NCCL = 105

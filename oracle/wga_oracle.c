@@ -732,6 +732,10 @@ static void pafrow_push(pafrow *r, const char *p, size_t n) {
     r->n++;
 }
 
+static void pafrow_free_scratch(pafrow *r) {
+    while (r->scratch) { char *nx = *(char **)r->scratch; free(r->scratch); r->scratch = nx; }
+}
+
 /* returns 1 if a record was read, 0 at end */
 static int paf_next(const char *t, size_t len, size_t *pos, pafrow *row) {
     for (;;) {
@@ -744,23 +748,28 @@ static int paf_next(const char *t, size_t len, size_t *pos, pafrow *row) {
             continue;
         }
         row->n = 0;
-        row->sn = 0;
         for (;;) {
             if (i < len && t[i] == '"') { /* quoted field -> unescape into scratch */
-                size_t need = len - i;
-                if (row->sn + need > row->scap) {
-                    /* scratch may move: fields already pushed from scratch would dangle, so
-                     * reserve generously once (whole remaining text) */
-                    row->scap = row->sn + need + 16;
-                    char *ns = (char *)malloc(row->scap);
-                    memcpy(ns, row->scratch, row->sn);
-                    for (size_t k = 0; k < row->n; k++)
-                        if (row->f[k].p >= row->scratch && row->f[k].p < row->scratch + row->sn)
-                            row->f[k].p = ns + (row->f[k].p - row->scratch);
-                    free(row->scratch);
-                    row->scratch = ns;
+                /* the decoded field is never longer than the raw field; chunks are never moved or reused, so the
+                 * fields (names kept by stat / pafpseudo / filter across records) stay valid until pafrow_free_scratch */
+                size_t need = 0;
+                {
+                    size_t j = i + 1;
+                    while (j < len) {
+                        if (t[j] == '"') { if (j + 1 < len && t[j + 1] == '"') { j += 2; need++; continue; } j++; break; }
+                        j++; need++;
+                    }
+                    while (j < len && t[j] != '\t' && t[j] != '\n' && t[j] != '\r') { j++; need++; }
                 }
-                char *dst = row->scratch + row->sn;
+                if (!row->scratch || row->sn + need > row->scap) {
+                    const size_t cap = need > 65536 ? need : 65536;
+                    char *ns = (char *)malloc(sizeof(char *) + cap);
+                    *(char **)ns = row->scratch; /* chunk list */
+                    row->scratch = ns;
+                    row->sn = 0;
+                    row->scap = cap;
+                }
+                char *dst = row->scratch + sizeof(char *) + row->sn;
                 size_t dn = 0;
                 i++;
                 while (i < len) {
@@ -942,7 +951,7 @@ int orc_stat_paf(const char *text, size_t len, int each, orc_buf *out, char *err
     /* names reference row scratch only for quoted fields; copy-free path is the norm.  To be
      * safe for quoted names we would need owned copies; quoted names are not generated by tests. */
     if (rc == ORC_OK) stat_write(&v, each, out);
-    free(row.f); free(row.scratch); free(v.r); free(v.ht);
+    free(row.f); pafrow_free_scratch(&row); free(v.r); free(v.ht);
     orc_buf_free(&conv);
     return rc;
 }
@@ -1549,7 +1558,7 @@ int orc_paf2maf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_l
         buf_putc(out, '\t'); buf_put(out, qs.p, qs.n); buf_putc(out, '\n');
         buf_putc(out, '\n');
     }
-    free(row.f); free(row.scratch); free(tf.e); free(qf.e);
+    free(row.f); pafrow_free_scratch(&row); free(tf.e); free(qf.e);
     orc_buf_free(&ts); orc_buf_free(&qs); orc_buf_free(&conv);
     return rc;
 }
@@ -1672,7 +1681,7 @@ int orc_call_paf(const char *paf, size_t paf_len, const char *t_fa, size_t t_fa_
         vcf_header(out, sample ? sample : "sample");
         buf_put(out, body.p, body.n);
     }
-    free(row.f); free(row.scratch); free(tf.e); free(qf.e);
+    free(row.f); pafrow_free_scratch(&row); free(tf.e); free(qf.e);
     orc_buf_free(&ts); orc_buf_free(&qs); orc_buf_free(&body); orc_buf_free(&conv); orc_buf_free(&rowb);
     return rc;
 }
@@ -1860,7 +1869,7 @@ int orc_paf_pseudo(const char *paf, size_t paf_len, const char *fa, size_t fa_le
         buf_put(index, tname.p, tname.n); buf_putc(index, '\t'); buf_putu(index, out->n - file_start); buf_putc(index, '\n');
     }
     if (rc) { out->n = 0; index->n = 0; }
-    free(done); free(grp); free(recs); free(row.f); free(row.scratch); free(fx.e);
+    free(done); free(grp); free(recs); free(row.f); pafrow_free_scratch(&row); free(fx.e);
     orc_buf_free(&q);
     return rc;
 }
@@ -1927,7 +1936,7 @@ int orc_paf_validate(const char *text, size_t len, int fix, orc_buf *report, orc
         buf_puts(report, "Target invalid list:\n"); buf_put(report, tl.p, tl.n);
         buf_putc(report, '\n');
     } else fixed->n = 0;
-    free(row.f); free(row.scratch);
+    free(row.f); pafrow_free_scratch(&row);
     orc_buf_free(&ql); orc_buf_free(&tl); orc_buf_free(&conv);
     return rc;
 }
@@ -1987,7 +1996,7 @@ int orc_paf_filter(const char *text, size_t len, uint64_t min_block, uint64_t mi
                 buf_putc(out, '\n');
             }
         }
-        free(row.f); free(row.scratch);
+        free(row.f); pafrow_free_scratch(&row);
     }
     if (rc != ORC_OK) out->n = 0;
     for (size_t i = 0; i < np; i++) { free((void *)pairs[i].q.p); free((void *)pairs[i].t.p); }
@@ -2119,7 +2128,7 @@ int orc_paf_plotdata(const char *text, size_t len, uint64_t cutoff, orc_buf *out
         plot_write(out, &st, row.f[5], row.f[0]);
     }
     if (rc != ORC_OK) out->n = 0;
-    free(row.f); free(row.scratch); free(st.v);
+    free(row.f); pafrow_free_scratch(&row); free(st.v);
     orc_buf_free(&conv);
     return rc;
 }
@@ -2269,7 +2278,7 @@ int orc_paf2chain(const char *text, size_t len, orc_buf *out, char *err, size_t 
         buf_puts(out, "\n\n");
         id++;
     }
-    free(row.f); free(row.scratch);
+    free(row.f); pafrow_free_scratch(&row);
     orc_buf_free(&conv);
     return rc;
 }
@@ -2333,7 +2342,7 @@ int orc_pafcov(const char *text, size_t len, orc_buf *out, char *err, size_t err
                 buf_putc(out, '\t'); buf_putu(out, T[k].cov[x]); buf_putc(out, '\n');
             }
     for (size_t k = 0; k < nt; k++) free(T[k].cov);
-    free(T); free(row.f); free(row.scratch);
+    free(T); free(row.f); pafrow_free_scratch(&row);
     orc_buf_free(&conv);
     return rc;
 }

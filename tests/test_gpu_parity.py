@@ -1354,3 +1354,57 @@ def test_plotdata_parity(w, ctx):
         with pytest.raises(w.WGAError) as eg:
             pp(t)
         assert eo.value.code == code == eg.value.code, (t, eo.value.code, eg.value.code)
+
+
+# ---------------------------------------------------------------- quoted csv fields in PAF input (paf.rs:22-31, csv quoting on)
+def _quote_fields(rng, paf, frac=0.5):
+    """quote some fields the way a csv writer with QuoteStyle::Always would: "content" (content has no special byte)"""
+    out = []
+    for l in paf.splitlines(keepends=True):
+        if l.startswith(b"#") or not l.strip():
+            out.append(l)
+            continue
+        f = l.rstrip(b"\n").split(b"\t")
+        f = [b'"' + x + b'"' if rng.random() < frac else x for x in f]
+        out.append(b"\t".join(f) + b"\n")
+    return b"".join(out)
+
+
+def test_paf_quoted_fields(w, ctx):
+    rng = random.Random(77)
+    plain = b"#c\n" + bs.gen_paf(bs.paf_params(600, seed=11, ops_median=40.0, chr_size=30_000, n_genomes=2, n_chr=2))
+    q = _quote_fields(rng, plain)
+    assert q.count(b'"') > 2000
+    # the reader hands the deserializer the unquoted content: every command gives what it gives on the plain file
+    assert orc.stat_paf(q) == orc.stat_paf(plain)
+    assert statp(w, ctx, q) == orc.stat_paf(q)
+    assert statp(w, ctx, q, True) == orc.stat_paf(q, True)
+    assert w.run_bytes(w.paf2chain, w.PAFReader(q), ctx=ctx) == orc.paf2chain(q)
+    assert _validate(w, ctx, q) == orc.paf_validate(q, True)
+    assert w.run_bytes(w.filter_paf_align_pair, w.PAFReader(q), 1000, ctx=ctx) == orc.paf_filter(q, min_align=1000)
+    assert w.run_bytes(w.pafcov, w.PAFReader(q), ctx=ctx) == orc.pafcov(q)
+    assert w.run_bytes(w.generate_paf_basedata, w.PAFReader(q), 3, ctx=ctx) == orc.paf_plotdata(q, 3)
+    case = make_paf2maf_case(rng, n_rec=40)
+    qp = _quote_fields(rng, case[0])
+    assert p2m(w, ctx, qp, *case[1:]) == orc.paf2maf(qp, *case[1:])
+    assert cpaf(w, ctx, qp, *case[1:], snp=True, svlen=0, sample="s") == orc.call_paf(qp, *case[1:], snp=True, svlen=0, sample="s")
+    fa = case[1] + case[3]
+    fai = orc.make_fai(fa)
+    want = orc.paf_pseudo(qp, fa, fai)
+    got = w.pseudo_maf_files(w.PAFReader(qp), w.Fasta(ctx, fa, fai), ctx=ctx)
+    assert list(got) == list(want) and all(got[k] == want[k] for k in want)
+    # an error behind the quotes is still the reference's error
+    bad = q + b'"q"\t"x"\t2\n'
+    with pytest.raises(orc.OracleError) as eo:
+        orc.stat_paf(bad)
+    with pytest.raises(w.WGAError) as eg:
+        statp(w, ctx, bad)
+    assert eo.value.code == eg.value.code == 9
+    # what stays refused: a quote, a tab or a line break inside the quotes, text behind the closing quote
+    line = plain.splitlines(keepends=True)[1]
+    f = line.rstrip(b"\n").split(b"\t")
+    for weird in (b'"a""b"', b'"a\tb"', b'"ab"c', b'"#ab"'):
+        g = [weird] + f[1:]
+        with pytest.raises(w.WGAError) as e:
+            statp(w, ctx, plain + b"\t".join(g) + b"\n")
+        assert e.value.code == 102, weird
