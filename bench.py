@@ -255,9 +255,10 @@ def snap_newline(view, pos):
 
 
 def sharded_paf_leg(args, ctx, comm, rank, world, dist, timed_fn, all_cpus):
-    """strong scaling on the config-4 shape: ONE all-to-all PAF (16 genomes x 20 chromosomes, `=`/X/I/D CIGARs), cut into
-    `world` byte ranges at line starts (dist.shard_range semantics); every timed step = wga_paf_stat on the rank's range +
-    wga_stat_allreduce + the TSV on rank 0."""
+    """the config-4 shape across ranks: ONE all-to-all PAF (16 genomes x 20 chromosomes, `=`/X/I/D CIGARs) made of `world`
+    consecutive parts of --paf-records records each; rank r holds part r (its byte range of the file, cut at a line start:
+    dist.shard_range semantics).  Every timed step = wga_paf_stat on the rank's range + wga_stat_allreduce + the TSV on
+    rank 0.  Weak scaling (2.02 GB per GPU); rank 0 then runs ONE single-GPU pass over the whole file and compares."""
     import numpy as np
     import torch
     import bench_support as bs
@@ -272,14 +273,20 @@ def sharded_paf_leg(args, ctx, comm, rank, world, dist, timed_fn, all_cpus):
         keep["p"] = p
         return p, p
     threads = max(4, len(os.sched_getaffinity(0)) // max(1, (world + 1) // 2))
-    _, nbytes = bs.gen_paf_into(bs.paf_params(args.paf_records, seed=PAF_SEED, threads=threads), pinned)
+    _, n_mine = bs.gen_paf_into(bs.paf_params(args.paf_records, seed=PAF_SEED + rank, threads=threads), pinned)
     host = keep["p"]
-    view = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(host))
-    lo, hi = snap_newline(view, nbytes * rank // world), snap_newline(view, nbytes * (rank + 1) // world)
-    n_mine = hi - lo
+    view = np.ctypeslib.as_array((ctypes.c_uint8 * n_mine).from_address(host))
+    assert n_mine and view[n_mine - 1] == 10, "a part must end at a line end"
     d = torch.zeros(n_mine + 64, dtype=torch.uint8, device="cuda")
-    d[:n_mine].copy_(torch.from_numpy(view[lo:hi]))
+    d[:n_mine].copy_(torch.from_numpy(view))
     torch.cuda.synchronize()
+    sizes = torch.tensor([n_mine], dtype=torch.int64, device="cuda")
+    if world > 1:
+        allsz = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(allsz, sizes)
+        nbytes = int(sum(int(t.item()) for t in allsz))
+    else:
+        nbytes = n_mine
     out = {"tsv": b""}
 
     def step(mem, ptr):
@@ -295,8 +302,8 @@ def sharded_paf_leg(args, ctx, comm, rank, world, dist, timed_fn, all_cpus):
     nc0 = L.wga_ctx_nccl_calls(ctx.h)
     ms_dev = timed_fn(lambda: step(1, d.data_ptr()), args.steps)
     nc1 = L.wga_ctx_nccl_calls(ctx.h)
-    step(0, host + lo)
-    ms_e2e = timed_fn(lambda: step(0, host + lo), args.steps)
+    step(0, host)
+    ms_e2e = timed_fn(lambda: step(0, host), args.steps)
     # the exchange alone: the per-range tables are rebuilt outside the timed region
     ms_ar = 0.0
     if world > 1:
@@ -307,19 +314,33 @@ def sharded_paf_leg(args, ctx, comm, rank, world, dist, timed_fn, all_cpus):
             accs.append(a)
         it = iter(accs)
         ms_ar = timed_fn(lambda: comm.allreduce_stat(next(it)), args.steps)
-    res = {"workload": f"config 4 shape: stat -f paf over ONE all-to-all PAF of {args.paf_records} records ({nbytes / 1e9:.2f} GB), "
-                       f"cut into {world} byte range(s) at line starts; every step = wga_paf_stat + wga_stat_allreduce + TSV on rank 0",
-           "scaling": "strong", "value": nbytes / (ms_dev / args.steps * 1e-3) / 1e9, "unit": "GB/s",
+    res = {"workload": f"config 4 shape: stat -f paf over ONE all-to-all PAF of {world} x {args.paf_records} records ({nbytes / 1e9:.2f} GB), "
+                       f"rank r holds the r-th of {world} consecutive byte range(s); every step = wga_paf_stat + wga_stat_allreduce + TSV "
+                       "on rank 0",
+           "scaling": "weak", "value": nbytes / (ms_dev / args.steps * 1e-3) / 1e9, "unit": "GB/s",
            "ms_per_step": ms_dev / args.steps,
            "e2e": {"value": nbytes / (ms_e2e / args.steps * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e2e / args.steps,
                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 0},
            "allreduce_ms": ms_ar / args.steps, "nccl_calls_per_step": (nc1 - nc0) / max(args.steps, 1),
            "input_bytes": nbytes, "range_bytes_rank0": n_mine}
+    del d
+    L.wga_host_free(ctypes.c_void_p(host))
+    torch.cuda.empty_cache()
     if rank == 0:
         os.sched_setaffinity(0, all_cpus)
-        # parity 1: the single-GPU pass over the WHOLE file
+        # parity 1: ONE single-GPU pass over the WHOLE file (all parts regenerated into one host buffer, in rank order)
+        whole = L.wga_host_alloc(nbytes + 64)
+        if not whole:
+            raise MemoryError("wga_host_alloc failed")
+        off = 0
+        for r in range(world):
+            def into(n, base=whole + off):
+                return base, base
+            _, pn = bs.gen_paf_into(bs.paf_params(args.paf_records, seed=PAF_SEED + r), into)
+            off += pn
+        assert off == nbytes
         one = w.StatAcc(False)
-        ctx.paf_stat_raw(ctypes.c_void_p(host), nbytes, 0, 0, one)
+        ctx.paf_stat_raw(ctypes.c_void_p(whole), nbytes, 0, 0, one)
         tsv1 = one.write()
         ok = out["tsv"] == tsv1
         res["parity_vs_single_gpu"] = bool(ok)
@@ -328,15 +349,14 @@ def sharded_paf_leg(args, ctx, comm, rank, world, dist, timed_fn, all_cpus):
         if nbytes <= float(os.environ.get("WGA_BENCH_ORACLE_MB", 2600)) * 1e6:
             import oracle_lib as orc
             t0 = time.perf_counter()
-            want = orc.stat_paf(ctypes.string_at(host, nbytes))
+            want = orc.stat_paf(ctypes.string_at(whole, nbytes))
             res["parity_vs_oracle"] = bool(out["tsv"] == want)
             res["oracle_seconds"] = time.perf_counter() - t0
             res["cpu_baseline"] = {"value": nbytes / res["oracle_seconds"] / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
                                    "sample": "the whole PAF, one thread (stat_paf, src/tools/stat.rs:87-105)"}
             ok = ok and res["parity_vs_oracle"]
         res["parity"] = bool(ok)
-    del d
-    L.wga_host_free(ctypes.c_void_p(host))
+        L.wga_host_free(ctypes.c_void_p(whole))
     return res
 
 
