@@ -215,32 +215,34 @@ inline uint64_t key2_of(const wga_stat_acc &a, const wga_stat_acc::Row &r) {
     return wga::mix64(h ^ (r.query_size * 0x9E3779B97F4A7C15ull));
 }
 
-struct GlobalIndex {  // (key, key2) -> global pair index; one 24-byte entry per slot = one cache line per probe
-    struct Ent { uint64_t k1, k2; uint32_t val, pad; };  // val = index + 1, 0 = empty
-    std::vector<Ent> e;
+struct GlobalIndex {  // (key, key2) -> global pair index: a 4-byte slot table over a flat key array (both stay cache resident)
+    std::vector<uint32_t> slot;  // index + 1, 0 = empty
+    std::vector<uint64_t> keys;  // two per global pair, in global order
     size_t mask = 0;
     void init(size_t n) {
         size_t cap = 1024;
         while (cap < 2 * n + 2) cap <<= 1;
-        e.assign(cap, Ent{0, 0, 0, 0});
+        slot.assign(cap, 0u);
+        keys.clear();
+        keys.reserve(2 * n);
         mask = cap - 1;
     }
     // returns the index; *fresh = inserted now with index `next`
     uint32_t find_or_insert(uint64_t a, uint64_t b, uint32_t next, bool *fresh) {
         size_t s = a & mask;
         for (;;) {
-            Ent &x = e[s];
-            if (!x.val) { x.k1 = a; x.k2 = b; x.val = next + 1; *fresh = true; return next; }
-            if (x.k1 == a && x.k2 == b) { *fresh = false; return x.val - 1; }
+            const uint32_t e = slot[s];
+            if (!e) { slot[s] = next + 1; keys.push_back(a); keys.push_back(b); *fresh = true; return next; }
+            if (keys[2 * (size_t)(e - 1)] == a && keys[2 * (size_t)(e - 1) + 1] == b) { *fresh = false; return e - 1; }
             s = (s + 1) & mask;
         }
     }
     int64_t find(uint64_t a, uint64_t b) const {
         size_t s = a & mask;
         for (;;) {
-            const Ent &x = e[s];
-            if (!x.val) return -1;
-            if (x.k1 == a && x.k2 == b) return (int64_t)x.val - 1;
+            const uint32_t e = slot[s];
+            if (!e) return -1;
+            if (keys[2 * (size_t)(e - 1)] == a && keys[2 * (size_t)(e - 1) + 1] == b) return (int64_t)e - 1;
             s = (s + 1) & mask;
         }
     }
@@ -263,10 +265,25 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     // ---- 1a. counts, set digests
     std::vector<uint64_t> my2(n);
     uint64_t dsum = 0, dxor = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        my2[i] = key2_of(*acc, acc->rows[i]);
-        dsum += wga::mix64(acc->rows[i].key ^ my2[i]);
-        dxor ^= wga::mix64(acc->rows[i].key + my2[i]);
+    {
+        const unsigned nt = n >= 16384 ? 4u : 1u;  // hashing 10^5 name pairs is a millisecond per thread
+        uint64_t ps[4] = {0, 0, 0, 0}, px[4] = {0, 0, 0, 0};
+        auto part = [&](unsigned t) {
+            uint64_t a = 0, b = 0;
+            for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
+                my2[i] = key2_of(*acc, acc->rows[i]);
+                a += wga::mix64(acc->rows[i].key ^ my2[i]);
+                b ^= wga::mix64(acc->rows[i].key + my2[i]);
+            }
+            ps[t] = a; px[t] = b;
+        };
+        if (nt == 1) part(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(part, t);
+            for (auto &x : th) x.join();
+        }
+        for (unsigned t = 0; t < nt; ++t) { dsum += ps[t]; dxor ^= px[t]; }
     }
     uint64_t *hdr_s = (uint64_t *)T.scratch(0, 32), *hdr_r = (uint64_t *)T.scratch(1, 32 * (size_t)W);
     if (!hdr_s || !hdr_r) return WGA_E_NOMEM;
@@ -284,32 +301,41 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     memset(hl_s + 2 * n, 0, (n_max - n) * 16);
     WGA_TRY(T.allgather(hl_s, hl_r, n_max * 16));
     lap("hash lists");
-    // ---- 1c. global order: first seen over ranks in order
+    // ---- 1c. global order: first seen over ranks in order.  `uniform`: every rank holds rank 0's key set (an all-to-all
+    //      file cut into ranges: every range meets every pair) -- the global list is rank 0's list, rank 0 maps to itself,
+    //      and nobody needs anybody's names
+    bool uniform = true;
+    for (int r = 1; r < W; ++r) uniform = uniform && hdr[4 * r] == hdr[0] && hdr[4 * r + 1] == hdr[1] && hdr[4 * r + 2] == hdr[2];
     GlobalIndex G;
-    G.init(n_tot);
     uint32_t P = 0;
     std::vector<uint32_t> owner;       // global index -> rank that introduces it
     std::vector<uint32_t> mine_global;  // global indices this rank introduces, ascending
-    owner.reserve(hdr[0] + 16);
-    for (int r = 0; r < W; ++r) {
-        const uint64_t nr = hdr[4 * r];
-        if (r > 0 && nr == hdr[0] && hdr[4 * r + 1] == hdr[1] && hdr[4 * r + 2] == hdr[2]) continue;  // same key set as rank 0
-        const uint64_t *hl = hl_r + (size_t)r * n_max * 2;
-        for (uint64_t i = 0; i < nr; ++i) {
-            bool fresh;
-            G.find_or_insert(hl[2 * i], hl[2 * i + 1], P, &fresh);
-            if (fresh) {
-                owner.push_back((uint32_t)r);
-                if (r == R) mine_global.push_back(P);
-                ++P;
+    std::vector<uint32_t> lmap(n);     // local row -> global index
+    if (uniform && R == 0) {
+        P = (uint32_t)n;
+        for (uint64_t i = 0; i < n; ++i) lmap[i] = (uint32_t)i;
+    } else {
+        G.init(uniform ? hdr[0] : n_tot);
+        owner.reserve(hdr[0] + 16);
+        for (int r = 0; r < W; ++r) {
+            const uint64_t nr = hdr[4 * r];
+            if (r > 0 && nr == hdr[0] && hdr[4 * r + 1] == hdr[1] && hdr[4 * r + 2] == hdr[2]) continue;  // same key set as rank 0
+            const uint64_t *hl = hl_r + (size_t)r * n_max * 2;
+            for (uint64_t i = 0; i < nr; ++i) {
+                bool fresh;
+                G.find_or_insert(hl[2 * i], hl[2 * i + 1], P, &fresh);
+                if (fresh) {
+                    owner.push_back((uint32_t)r);
+                    if (r == R) mine_global.push_back(P);
+                    ++P;
+                }
             }
         }
-    }
-    std::vector<uint32_t> lmap(n);  // local row -> global index
-    for (uint64_t i = 0; i < n; ++i) {
-        const int64_t g = G.find(acc->rows[i].key, my2[i]);
-        if (g < 0) { *err = "internal: a local pair is missing from the global dictionary"; return WGA_E_INTERNAL; }
-        lmap[i] = (uint32_t)g;
+        for (uint64_t i = 0; i < n; ++i) {
+            const int64_t g = G.find(acc->rows[i].key, my2[i]);
+            if (g < 0) { *err = "internal: a local pair is missing from the global dictionary"; return WGA_E_INTERNAL; }
+            lmap[i] = (uint32_t)g;
+        }
     }
     lap("local map");
     lap("global order");
@@ -317,20 +343,23 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     //      global order
     std::vector<uint32_t> g2l(P, ~0u);
     for (uint64_t i = 0; i < n; ++i) g2l[lmap[i]] = (uint32_t)i;
-    uint64_t my_blob = 0;
-    for (uint32_t g : mine_global) { const auto &r = acc->rows[g2l[g]]; my_blob += 32 + r.lr + r.lq; }
-    hdr_s = (uint64_t *)T.scratch(0, 8);
-    hdr_r = (uint64_t *)T.scratch(1, 8 * (size_t)W);
-    if (!hdr_s || !hdr_r) return WGA_E_NOMEM;
-    hdr_s[0] = my_blob;
-    WGA_TRY(T.allgather(hdr_s, hdr_r, 8));
-    std::vector<uint64_t> blob_len(hdr_r, hdr_r + W);
+    std::vector<uint64_t> blob_len(W, 0);
     uint64_t blob_max = 0;
-    for (int r = 0; r < W; ++r) blob_max = std::max(blob_max, blob_len[r]);
-    blob_max = (blob_max + 7) & ~7ull;
-    char *bl_s = (char *)T.scratch(2, blob_max ? blob_max : 8), *bl_r = (char *)T.scratch(3, (blob_max ? blob_max : 8) * (size_t)W);
-    if (!bl_s || !bl_r) return WGA_E_NOMEM;
-    {
+    char *bl_r = nullptr;
+    if (!uniform) {
+        uint64_t my_blob = 0;
+        for (uint32_t g : mine_global) { const auto &r = acc->rows[g2l[g]]; my_blob += 32 + r.lr + r.lq; }
+        hdr_s = (uint64_t *)T.scratch(0, 8);
+        hdr_r = (uint64_t *)T.scratch(1, 8 * (size_t)W);
+        if (!hdr_s || !hdr_r) return WGA_E_NOMEM;
+        hdr_s[0] = my_blob;
+        WGA_TRY(T.allgather(hdr_s, hdr_r, 8));
+        blob_len.assign(hdr_r, hdr_r + W);
+        for (int r = 0; r < W; ++r) blob_max = std::max(blob_max, blob_len[r]);
+        blob_max = (blob_max + 7) & ~7ull;
+        char *bl_s = (char *)T.scratch(2, blob_max ? blob_max : 8);
+        bl_r = (char *)T.scratch(3, (blob_max ? blob_max : 8) * (size_t)W);
+        if (!bl_s || !bl_r) return WGA_E_NOMEM;
         char *p = bl_s;
         for (uint32_t g : mine_global) {
             const auto &r = acc->rows[g2l[g]];
@@ -340,8 +369,8 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
             p += 32 + r.lr + r.lq;
         }
         memset(p, 0, blob_max - my_blob);
+        WGA_TRY(T.allgather(bl_s, bl_r, blob_max));
     }
-    WGA_TRY(T.allgather(bl_s, bl_r, blob_max));
     lap("names");
     // ---- 2. counters: one all-reduce(sum), one all-reduce(min)
     uint64_t *sums = (uint64_t *)T.scratch(4, (size_t)P * 11 * 8), *mins = (uint64_t *)T.scratch(5, (size_t)P * 2 * 8);
@@ -378,21 +407,30 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
         out.names.resize(name_bytes);
     }
     std::vector<const char *> cur(W);
-    for (int r = 0; r < W; ++r) cur[r] = bl_r + (size_t)r * blob_max;
+    for (int r = 0; r < W; ++r) cur[r] = uniform ? nullptr : bl_r + (size_t)r * blob_max;
     size_t noff = 0;
+    if (uniform) out.names.resize(acc->names.size());
     char *nm = out.names.data();
     for (uint32_t g = 0; g < P; ++g) {
-        const char *p = cur[owner[g]];
         wga_stat_acc::Row &row = out.rows[g];
-        memcpy(&row.lr, p, 4); memcpy(&row.lq, p + 4, 4); memcpy(&row.ref_size, p + 8, 8); memcpy(&row.query_size, p + 16, 8);
-        // identity across ranks is the 128-bit (pair hash, key2) the dictionary was built on; the rebuilt accumulator's
-        // own lookup table is made on demand from the rows' keys (find_or_add -> grow_table)
-        memcpy(&row.key, p + 24, 8);
+        const char *src;
+        if (uniform) {  // every rank holds every pair: its own copy of the names and sizes
+            const wga_stat_acc::Row &l = acc->rows[g2l[g]];
+            row.lr = l.lr; row.lq = l.lq; row.ref_size = l.ref_size; row.query_size = l.query_size; row.key = l.key;
+            src = acc->names.data() + l.name_off;
+        } else {
+            const char *p = cur[owner[g]];
+            memcpy(&row.lr, p, 4); memcpy(&row.lq, p + 4, 4); memcpy(&row.ref_size, p + 8, 8); memcpy(&row.query_size, p + 16, 8);
+            // identity across ranks is the 128-bit (pair hash, key2) the dictionary was built on; the rebuilt accumulator's
+            // own lookup table is made on demand from the rows' keys (find_or_add -> grow_table)
+            memcpy(&row.key, p + 24, 8);
+            src = p + 32;
+            cur[owner[g]] = p + 32 + (size_t)row.lr + row.lq;
+        }
         const size_t nl = (size_t)row.lr + row.lq;
         row.name_off = noff;
-        memcpy(nm + noff, p + 32, nl);
+        memcpy(nm + noff, src, nl);
         noff += nl;
-        cur[owner[g]] = p + 32 + nl;
         memcpy(row.v, sums + (size_t)g * 11, 88);
         row.v[11] = mins[2 * (size_t)g];
         row.v[12] = mins[2 * (size_t)g + 1];
