@@ -138,6 +138,14 @@ class StatAcc:
             raise WGAError(rc, "wga_stat_acc_write failed")
         return ctypes.string_at(sp.data, sp.len) if sp.len else b""
 
+    def write_span(self):
+        """(address, length) of the TSV inside the accumulator (valid until the next call on it): what a host writes out"""
+        sp = Span()
+        rc = self.L.wga_stat_acc_write(self.h, ctypes.byref(sp))
+        if rc:
+            raise WGAError(rc, "wga_stat_acc_write failed")
+        return sp.data, sp.len
+
     def export(self) -> bytes:
         sp = Span()
         rc = self.L.wga_stat_acc_export(self.h, ctypes.byref(sp))

@@ -391,8 +391,22 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     if (!carry || !carry_all) return WGA_E_NOMEM;
     if (R == 0) memset(carry, 0, (size_t)P * 4);
     else WGA_TRY(T.sendrecv(nullptr, 0, -1, carry, (uint64_t)P * 4, R - 1));
-    for (size_t i = 0; i < acc->inv_pair.size(); ++i)
-        carry[lmap[acc->inv_pair[i]]] += (float)acc->inv_num[i] / (float)2;  // common.rs:134-137 with inv_event == 1
+    {
+        // f32 addition in file order per PAIR: threads take the pairs of one residue class each and walk the whole list
+        const size_t ni = acc->inv_pair.size();
+        auto add_class = [&](uint32_t t, uint32_t Tn) {
+            for (size_t i = 0; i < ni; ++i) {
+                const uint32_t g = lmap[acc->inv_pair[i]];
+                if (Tn == 1 || (g & (Tn - 1)) == t) carry[g] += (float)acc->inv_num[i] / (float)2;  // common.rs:134-137 with inv_event == 1
+            }
+        };
+        if (ni < 200000) add_class(0, 1);
+        else {
+            std::vector<std::thread> th;
+            for (uint32_t t = 0; t < 4; ++t) th.emplace_back(add_class, t, 4u);
+            for (auto &x : th) x.join();
+        }
+    }
     if (R + 1 < W) WGA_TRY(T.sendrecv(carry, (uint64_t)P * 4, R + 1, nullptr, 0, -1));
     WGA_TRY(T.allgather(carry, carry_all, (uint64_t)P * 4));
     const float *fin = carry_all + (size_t)(W - 1) * P;

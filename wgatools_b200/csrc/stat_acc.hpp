@@ -157,8 +157,21 @@ struct wga_stat_acc {
         for (size_t i = 0; i < n; ++i) inv[i] = rows[i].inv_size;
         if (!each) {
             // stat.inv_size += rec_stat.inv_size in record order (f32, order-dependent); a '+' record adds 0.0
-            for (size_t i = 0; i < inv_pair.size(); ++i)
-                inv[inv_pair[i]] += (float)inv_num[i] / (float)2;  // common.rs:134-137 with inv_event == 1
+            // (the order matters per PAIR only: with many '-' records a few threads each take the pairs of one residue class
+            // and walk the whole list in file order)
+            const size_t ni = inv_pair.size();
+            auto add_class = [&](uint32_t t, uint32_t T) {
+                for (size_t i = 0; i < ni; ++i) {
+                    const uint32_t p = inv_pair[i];
+                    if (T == 1 || (p & (T - 1)) == t) inv[p] += (float)inv_num[i] / (float)2;  // common.rs:134-137 with inv_event == 1
+                }
+            };
+            if (ni < 200000) add_class(0, 1);
+            else {
+                std::vector<std::thread> th;
+                for (uint32_t t = 0; t < 4; ++t) th.emplace_back(add_class, t, 4u);
+                for (auto &x : th) x.join();
+            }
         }
         // Rows with the same ref_name compare equal, so the stable sort only has to order the DISTINCT names:
         // group rows by ref_name (first-seen order), sort the groups, emit rows group by group.
@@ -250,7 +263,7 @@ struct wga_stat_acc {
         unsigned nt = 1;
         if (n >= 8192) {
             nt = std::thread::hardware_concurrency();
-            nt = nt == 0 ? 4 : (nt > 16 ? 16 : nt);
+            nt = nt == 0 ? 4 : (nt > 32 ? 32 : nt);
         }
         std::vector<Part> part(nt);
         if (nt == 1) {
