@@ -78,8 +78,24 @@ struct WarpEmit {  // run-head emission state of the warp: the item whose slot r
 // classify one queued chunk per lane (lanes >= cnt idle); counts -> atomics, heads -> item slots in order
 // RECQ: the record index travels in queue field 11 (false: it is read from the item descriptor instead, which
 // saves 256 B of shared memory per warp for the TMA-staged variant)
-template <int MODE, bool RECQ = true>
-__device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64], uint32_t cnt, uint32_t lane, WarpEmit &E) {
+// queue layouts: walk_batch reads one entry per lane through load()
+template <bool RECQ>
+struct QueueSoA {  // k_walk: one 64-slot row per field
+    uint32_t (*Q)[64];
+    static constexpr bool kHasRec = RECQ;
+    __device__ __forceinline__ void load(uint32_t lane, uint32_t (&tw)[4], uint32_t (&qw)[4], uint32_t &pv, uint32_t &meta,
+                                         uint32_t &item, uint32_t &rec) const {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tw[k] = Q[k][lane]; qw[k] = Q[4 + k][lane]; }
+        pv = Q[8][lane];
+        meta = Q[9][lane];
+        item = Q[10][lane];
+        rec = RECQ ? Q[11][lane] : 0u;
+    }
+};
+
+template <int MODE, class QA>
+__device__ __forceinline__ void walk_batch_q(const WalkArgs &A, const QA &qa, uint32_t cnt, uint32_t lane, WarpEmit &E) {
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER || MODE == MODE_RUNS_ALL;
     constexpr bool RUNS = MODE != MODE_STAT;
     constexpr bool COUNTS = MODE != MODE_RUNS_CALLER;
@@ -88,11 +104,10 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
     const bool act = lane < cnt;
     if (act) {
         uint32_t tw[4], qw[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { tw[k] = Q[k][lane]; qw[k] = Q[4 + k][lane]; }
-        const uint32_t pv = Q[8][lane];    // bit16: valid, bits 0-7 target byte, 8-15 query byte
-        const uint32_t meta = Q[9][lane];  // f0 | t0<<5 | t1<<10 | seg0<<15 | colrel<<16 (column of byte 0 + 16, in item)
-        item = Q[10][lane];
+        uint32_t pv;    // bit16: valid, bits 0-7 target byte, 8-15 query byte
+        uint32_t meta;  // f0 | t0<<5 | t1<<10 | seg0<<15 | colrel<<16 (column of byte 0 + 16, in item)
+        uint32_t rec_q;
+        qa.load(lane, tw, qw, pv, meta, item, rec_q);
         const int f0 = meta & 31, t0 = (meta >> 5) & 31, t1 = (meta >> 10) & 31;
         const int f1 = ((meta >> 15) & 1u) ? f0 : 0;  // bytes before the record start are not columns
         colrel = meta >> 16;
@@ -123,7 +138,7 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
         }
         if (MODE == MODE_RUNS_ALL && hw) atomicAdd(A.n_w, 1u);  // only "are there any" matters
         if (COUNTS && (cX | cI | cD)) {
-            const uint32_t rec = RECQ ? Q[11][lane] : __ldg(&A.items[item].rec);
+            const uint32_t rec = QA::kHasRec ? rec_q : __ldg(&A.items[item].rec);
             unsigned long long *c = A.rec_cnt + (uint64_t)rec * 5;
             if (cX) atomicAdd(c + 0, (unsigned long long)cX);
             if (eI) atomicAdd(c + 1, (unsigned long long)eI);
@@ -182,6 +197,11 @@ __device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64],
         E.open_item = __shfl_sync(0xFFFFFFFFu, item, last);
         E.open_count = __shfl_sync(0xFFFFFFFFu, incl, last);
     }
+}
+
+template <int MODE, bool RECQ = true>
+__device__ __forceinline__ void walk_batch(const WalkArgs &A, uint32_t (*Q)[64], uint32_t cnt, uint32_t lane, WarpEmit &E) {
+    walk_batch_q<MODE>(A, QueueSoA<RECQ>{Q}, cnt, lane, E);
 }
 
 // geometry of one work item in the 16-byte frame of its target stream

@@ -33,24 +33,47 @@ constexpr int kTmaThreads = WGA_TMA_THREADS, kTmaWarps = kTmaThreads / 32, kTmaC
 constexpr int kTmaStages = WGA_TMA_STAGES;
 constexpr uint32_t kTmaWin = WGA_TMA_WIN;                          // chunks per window (32 per step)
 constexpr uint32_t kTmaStageBytes = kTmaWin * 16 + kTmaWin * 16 + 16;  // T | Q (+ one vector for the realign)
-constexpr int kTmaGeoms = 4;                                      // item geometries in flight per warp
+constexpr int kTmaGeoms = 3;                                      // item geometries in flight per warp: the (at most) two
+                                                                  // items of the windows in flight + the one opened ahead
 // Experiment knob (off): request the windows that come kTmaPrefetch ring turns later into L2 already now
 // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2).  Measured on the bench workload (profiles/r02_walk_experiments.md): 2 and 4
 // windows ahead make the kernel SLOWER (1.65 / 1.64 ms against 1.52 ms), i.e. the walk is not waiting for DRAM latency
 // that more bytes in flight could hide.
 constexpr uint32_t kTmaPrefetch = WGA_TMA_PREFETCH;               // windows ahead (0 = off)
 
-struct TmaWin { uint32_t gslot, j0, cnt, pad; };
+struct __align__(16) TmaWin { uint32_t gslot, j0, cnt, pad; };
 struct __align__(16) TmaWarp {
     uint8_t stage[kTmaStages][kTmaStageBytes];
     Geom geom[kTmaGeoms];
     TmaWin win[kTmaStages];
     unsigned long long bar[kTmaStages];
 };
+// slow-chunk queue of a warp: a ring of 64 entries, three 16-byte vectors per entry (3 STS.128 per push, 3 LDS.128 per
+// batch lane; the row-per-field layout of k_walk costs 11 of each)
+struct __align__(16) TmaQueue {
+    uint4 t[64];  // target words of the chunk
+    uint4 q[64];  // query words, realigned to the target's columns
+    uint4 m[64];  // prev column | meta | item | rec (walk_batch_q)
+};
+struct QueueVec {
+    const TmaQueue *q;
+    uint32_t head;
+    static constexpr bool kHasRec = true;
+    __device__ __forceinline__ void load(uint32_t lane, uint32_t (&tw)[4], uint32_t (&qw)[4], uint32_t &pv, uint32_t &meta,
+                                         uint32_t &item, uint32_t &rec) const {
+        const uint32_t i = (head + lane) & 63u;
+        const uint4 a = q->t[i], b = q->q[i], c = q->m[i];
+        tw[0] = a.x; tw[1] = a.y; tw[2] = a.z; tw[3] = a.w;
+        qw[0] = b.x; qw[1] = b.y; qw[2] = b.z; qw[3] = b.w;
+        pv = c.x; meta = c.y; item = c.z; rec = c.w;
+    }
+};
 struct TmaSmem {
-    uint32_t queue[kTmaWarps][11][64];
+    TmaQueue queue[kTmaWarps];
     TmaWarp w[kTmaWarps];
 };
+// two CTAs per SM: 2 x (sizeof(TmaSmem) + 1 KB reserved per CTA) must fit the SM's 228 KB
+static_assert(kTmaCtasPerSm * (sizeof(TmaSmem) + 1024) <= 233472, "k_walk_tma: shared memory budget of the SM");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
@@ -82,15 +105,80 @@ __device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes) {
 }
 __device__ __forceinline__ uint4 lds16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
+// Steps st, st+32, ... of one window (same algorithm as walk_step, walk.cuh) until the window ends or 32 slow chunks are
+// queued.  WS = word part of the query's byte shift (warp-uniform per item): the caller dispatches on it once per call,
+// not once per step.  Lane i of a step owns chunk st+i of the window; lanes past the window's end read stale shared
+// memory and are inactive.  jlm1 = (first chunk that is not fully inside the item) - 1: edge <=> j == 0 || j >= jl
+// <=> (j - 1) >= jlm1 in unsigned arithmetic.
+template <int MODE, int WS>
+__device__ __forceinline__ uint32_t tma_steps(TmaQueue &QV, uint32_t qhead, uint32_t &qn, uint32_t lane, const Geom &g,
+                                              uint32_t jlm1, uint32_t wj0, uint32_t wcnt, uint32_t st, const uint8_t *Ts,
+                                              PrevCol &P) {
+    constexpr bool CALLER = MODE == MODE_RUNS_CALLER || MODE == MODE_RUNS_ALL;
+    const uint32_t sh = (g.s & 3u) * 8u;
+    const uint8_t *pT = Ts + 16u * (st + lane);  // this lane's target vector; its query vectors sit kTmaWin * 16 behind
+    do {
+        const uint4 tv = lds16(pT), q0 = lds16(pT + kTmaWin * 16), q1 = lds16(pT + kTmaWin * 16 + 16);
+        uint32_t qw0, qw1, qw2, qw3;
+        realign<WS>(q0, q1, sh, qw0, qw1, qw2, qw3);
+        const uint32_t rel = st + lane;
+        const bool act = rel < wcnt;
+        const uint32_t x3 = tv.w ^ qw3;
+        uint32_t x = (tv.x ^ qw0) | (tv.y ^ qw1) | (tv.z ^ qw2) | x3;
+        bool ne_last = x3 > 0x00FFFFFFu;  // the chunk's last column differs
+        if (CALLER) {                     // bit 6 clear in a target byte: superset of "holds a gap" (see walk_step)
+            const uint32_t g6 = tv.x & tv.y & tv.z & tv.w;
+            x |= ~g6 & 0x40404040u;
+            ne_last |= (tv.w & 0x40000000u) == 0u;
+        }
+        ne_last &= act;
+        const uint32_t nb = __ballot_sync(0xFFFFFFFFu, ne_last);
+        const bool prev_ne = (((nb << 1) | P.bit) >> lane) & 1u;
+        const uint32_t j = wj0 + rel;
+        const bool edge = j - 1u >= jlm1;
+        const bool slow = act && (edge || x != 0u || prev_ne);
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, slow);
+        if (mask) {
+            // bytes of the column before the chunk: one byte back in the window; for the window's first chunk the last
+            // column of the previous window (lane 31 of its last step keeps it)
+            uint32_t pb = 0;
+            if (st == 0 && (mask & 1u)) pb = __shfl_sync(0xFFFFFFFFu, (P.tw3 >> 24) | ((P.qw3 >> 24) << 8), 31);  // warp-uniform
+            if (slow) {
+                if (rel != 0) pb = (uint32_t)pT[-1] | ((uint32_t)pT[kTmaWin * 16 + g.s - 1u] << 8);
+                uint32_t f0 = 0, t0 = 16, t1 = 16;
+                if (edge) {  // a <= 15, n <= kSeg: everything fits 32-bit signed arithmetic
+                    const int32_t lo = (int32_t)g.a - 16 * (int32_t)j, hi = (int32_t)(g.n + g.a) - 16 * (int32_t)j;
+                    f0 = clamp16(lo);
+                    t0 = clamp16(hi);
+                    t1 = clamp16(hi + (int32_t)g.tail);  // columns of the next item are context only
+                }
+                const uint32_t slot = (qhead + qn + __popc(mask & ((1u << lane) - 1u))) & 63u;
+                QV.t[slot] = tv;
+                QV.q[slot] = make_uint4(qw0, qw1, qw2, qw3);
+                QV.m[slot] = make_uint4(j == 0 ? g.first_prev : ((1u << 16) | pb),
+                                        f0 | (t0 << 5) | (t1 << 10) | ((g.seg == 0 ? 1u : 0u) << 15) | ((16u * j + 16u - g.a) << 16),
+                                        g.item, g.rec);
+            }
+            qn += __popc(mask);
+        }
+        P.bit = nb >> 31;
+        P.tw3 = tv.w;
+        P.qw3 = qw3;
+        st += 32;
+        pT += 512;
+    } while (st < wcnt && qn < 32);
+    return st;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArgs A) {
     constexpr bool RUNS = MODE != MODE_STAT;
     extern __shared__ __align__(128) uint8_t s_raw[];
     TmaSmem &S = *reinterpret_cast<TmaSmem *>(s_raw);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t (*Q)[64] = S.queue[wid];
+    TmaQueue &QV = S.queue[wid];
     TmaWarp &W = S.w[wid];
-    uint32_t qn = 0;
+    uint32_t qn = 0, qhead = 0;  // queued entries, ring position of the oldest
     WarpEmit E;
     E.open_item = 0xFFFFFFFFu;
     E.open_count = 0;
@@ -206,37 +294,47 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
     // ---- consumer
     Geom cur;
     cur.nch = 0;
-    uint32_t cur_gs = 0xFFFFFFFFu, sc = 0, parity = 0;  // parity: bit s = phase of stage s to wait for
+    uint32_t cur_gs = 0xFFFFFFFFu, sc = 0, parity = 0, jlm1 = 0;  // parity: bit s = phase of stage s to wait for
     PrevCol carry = {0u, 0u, 0u};
     while (n_out) {
         mbar_wait(&W.bar[sc], (parity >> sc) & 1u);
         parity ^= 1u << sc;
-        const uint32_t gs = W.win[sc].gslot, wj0 = W.win[sc].j0, wcnt = W.win[sc].cnt;
+        const uint4 wm = *reinterpret_cast<const uint4 *>(&W.win[sc]);
+        const uint32_t gs = wm.x, wj0 = wm.y, wcnt = wm.z;
         if (gs != cur_gs) {
             cur = W.geom[gs];
             cur_gs = gs;
+            jlm1 = ((cur.n + cur.a) >> 4) - 1u;
             carry.bit = 0; carry.tw3 = 0; carry.qw3 = 0;
         }
-        const uint8_t *Ts = W.stage[sc], *Qs = W.stage[sc] + kTmaWin * 16;
-        for (uint32_t st = 0; st < wcnt; st += 32) {
-            // lanes past the window's end read its last chunk again (they are inactive in walk_step: j >= nch); the
-            // vector after the last query vector lies inside the stage buffer and only feeds columns past the item's end
-            const uint32_t rel = min(st + lane, wcnt - 1u);
-            Vec3 v;
-            v.t = lds16(Ts + 16u * rel);
-            v.q0 = lds16(Qs + 16u * rel);
-            v.q1 = lds16(Qs + 16u * rel + 16u);
-            walk_step<MODE, false>(A, Q, qn, E, lane, cur, wj0 + st, v, carry, Ts + 16u * rel - 1u, Qs + 16u * rel + cur.s - 1u, st == 0);
+        const uint8_t *Ts = W.stage[sc];
+        const uint32_t ws = cur.s >> 2;  // warp-uniform
+        uint32_t st = 0;
+        while (st < wcnt) {
+            switch (ws) {
+                case 0: st = tma_steps<MODE, 0>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
+                case 1: st = tma_steps<MODE, 1>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
+                case 2: st = tma_steps<MODE, 2>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
+                default: st = tma_steps<MODE, 3>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
+            }
+            if (qn >= 32) {  // the one classification site of the kernel
+                __syncwarp();
+                walk_batch_q<MODE>(A, QueueVec{&QV, qhead}, 32, lane, E);
+                __syncwarp();
+                qhead = (qhead + 32u) & 63u;
+                qn -= 32;
+            }
         }
         --n_out;
-        // every lane has consumed its LDS results (they were compared / queued inside walk_step), so the stage can be
+        // every lane has consumed its LDS results (they were compared / queued inside tma_steps), so the stage can be
         // handed back to the async proxy without a proxy fence: the fence is for generic-proxy WRITES, there are none
         __syncwarp();
         produce(sc);
         sc = sc + 1 == kTmaStages ? 0 : sc + 1;
     }
     if (qn) {
-        walk_batch<MODE, false>(A, Q, qn, lane, E);
+        __syncwarp();
+        walk_batch_q<MODE>(A, QueueVec{&QV, qhead}, qn, lane, E);
         __syncwarp();
     }
     if (RUNS && E.open_item != 0xFFFFFFFFu && lane == 0) A.item_nheads[E.open_item] = E.open_count;
