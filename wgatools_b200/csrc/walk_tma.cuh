@@ -29,6 +29,9 @@ namespace wga {
 #ifndef WGA_TMA_PREFETCH
 #define WGA_TMA_PREFETCH 0
 #endif
+#ifndef WGA_TMA_LANE32
+#define WGA_TMA_LANE32 0  // 1 = 32 columns per lane and step (tma_steps2): measured SLOWER (1.35 against 1.30 ms, see tma_steps2)
+#endif
 constexpr int kTmaThreads = WGA_TMA_THREADS, kTmaWarps = kTmaThreads / 32, kTmaCtasPerSm = WGA_TMA_CTAS;
 constexpr int kTmaStages = WGA_TMA_STAGES;
 constexpr uint32_t kTmaWin = WGA_TMA_WIN;                          // chunks per window (32 per step)
@@ -166,6 +169,100 @@ __device__ __forceinline__ uint32_t tma_steps(TmaQueue &QV, uint32_t qhead, uint
         P.qw3 = qw3;
         st += 32;
         pT += 512;
+    } while (st < wcnt && qn < 32);
+    return st;
+}
+
+// 32 columns per lane: lane i of a double step owns chunks st+2i (A) and st+2i+1 (B) of the window, i.e. 32 contiguous
+// target bytes and the 48 query bytes around them.  Everything that tma_steps pays once per 32 chunks (loop, ballots,
+// the push bookkeeping) is paid once per 64 here.  The queue takes at most 32 new entries at a time (ring of 64, up to
+// 31 waiting): a double step with more slow chunks than fit is pushed in two halves -- lanes 0..15, then, after the
+// caller had a chance to classify a batch, lanes 16..31 (`half`, warp-uniform; the step is recomputed, the carry is not
+// advanced in between).
+// Experiment knob (WGA_TMA_LANE32=1, off): parity-green, but on the bench workload the walk takes 1.35 ms against 1.30 ms
+// with tma_steps -- the two-entry push costs what the shared bookkeeping saves (188 SASS instructions per 64 chunks either
+// way), the 32-byte lane stride makes every LDS.128 a 2-way bank conflict and the last step of an item idles more lanes.
+template <int MODE, int WS>
+__device__ __forceinline__ uint32_t tma_steps2(TmaQueue &QV, uint32_t qhead, uint32_t &qn, uint32_t lane, const Geom &g,
+                                               uint32_t jlm1, uint32_t wj0, uint32_t wcnt, uint32_t st, uint32_t &half,
+                                               const uint8_t *Ts, PrevCol &P) {
+    constexpr bool CALLER = MODE == MODE_RUNS_CALLER || MODE == MODE_RUNS_ALL;
+    const uint32_t sh = (g.s & 3u) * 8u;
+    const uint8_t *pT = Ts + 16u * st + 32u * lane;  // this lane's two target vectors; the query vectors kTmaWin * 16 behind
+    const uint32_t lt = (1u << lane) - 1u;
+    do {
+        const uint4 ta = lds16(pT), tb = lds16(pT + 16);
+        const uint4 q0 = lds16(pT + kTmaWin * 16), q1 = lds16(pT + kTmaWin * 16 + 16), q2 = lds16(pT + kTmaWin * 16 + 32);
+        uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+        realign<WS>(q0, q1, sh, a0, a1, a2, a3);
+        realign<WS>(q1, q2, sh, b0, b1, b2, b3);
+        const uint32_t rel = st + 2u * lane;  // chunk A; B = rel + 1
+        const bool act_a = rel < wcnt, act_b = rel + 1u < wcnt;
+        const uint32_t xa3 = ta.w ^ a3, xb3 = tb.w ^ b3;
+        uint32_t xa = (ta.x ^ a0) | (ta.y ^ a1) | (ta.z ^ a2) | xa3;
+        uint32_t xb = (tb.x ^ b0) | (tb.y ^ b1) | (tb.z ^ b2) | xb3;
+        bool ne_a = xa3 > 0x00FFFFFFu, ne_b = xb3 > 0x00FFFFFFu;  // the chunk's last column differs
+        if (CALLER) {  // bit 6 clear in a target byte: superset of "holds a gap" (see walk_step)
+            xa |= ~(ta.x & ta.y & ta.z & ta.w) & 0x40404040u;
+            xb |= ~(tb.x & tb.y & tb.z & tb.w) & 0x40404040u;
+            ne_a |= (ta.w & 0x40000000u) == 0u;
+            ne_b |= (tb.w & 0x40000000u) == 0u;
+        }
+        ne_a &= act_a;
+        ne_b &= act_b;
+        const uint32_t nb = __ballot_sync(0xFFFFFFFFu, ne_b);
+        const bool prev_a = (((nb << 1) | P.bit) >> lane) & 1u;  // B's previous column is A's last: ne_a
+        const uint32_t j = wj0 + rel;                           // chunk A's index in the item; B is j + 1 (never 0)
+        const bool edge_a = j - 1u >= jlm1, edge_b = j >= jlm1;
+        const bool slow_a = act_a && (edge_a || xa != 0u || prev_a);
+        const bool slow_b = act_b && (edge_b || xb != 0u || ne_a);
+        uint32_t ma = __ballot_sync(0xFFFFFFFFu, slow_a), mb = __ballot_sync(0xFFFFFFFFu, slow_b);
+        bool again = false;  // warp-uniform: the upper half of this step is still to be pushed
+        if (ma | mb) {
+            uint32_t allow = half ? 0xFFFF0000u : 0xFFFFFFFFu;
+            if (!half && qn + __popc(ma) + __popc(mb) > 64u) { allow = 0x0000FFFFu; again = true; }
+            ma &= allow;
+            mb &= allow;
+            const bool push_a = slow_a && ((allow >> lane) & 1u), push_b = slow_b && ((allow >> lane) & 1u);
+            // the column before chunk A (see tma_steps); the one before chunk B is A's last column, still in registers
+            uint32_t pa = 0x4141u;
+            if (__any_sync(0xFFFFFFFFu, push_a && prev_a)) {
+                if (st == 0 && (ma & 1u)) pa = __shfl_sync(0xFFFFFFFFu, (P.tw3 >> 24) | ((P.qw3 >> 24) << 8), 31);  // warp-uniform
+                if (push_a && rel != 0) pa = (uint32_t)pT[-1] | ((uint32_t)pT[kTmaWin * 16 + g.s - 1u] << 8);
+            }
+            const uint32_t pb = (ta.w >> 24) | ((a3 >> 24) << 8);
+            uint32_t meta_a = (16u << 5) | (16u << 10), meta_b = meta_a;
+            if (__any_sync(0xFFFFFFFFu, (push_a && edge_a) || (push_b && edge_b))) {
+                // a <= 15, n <= kSeg: everything fits 32-bit signed arithmetic; tail: context columns only
+                const int32_t lo = (int32_t)g.a - 16 * (int32_t)j, hi = (int32_t)(g.n + g.a) - 16 * (int32_t)j;
+                if (edge_a) meta_a = clamp16(lo) | (clamp16(hi) << 5) | (clamp16(hi + (int32_t)g.tail) << 10);
+                if (edge_b) meta_b = clamp16(lo - 16) | (clamp16(hi - 16) << 5) | (clamp16(hi - 16 + (int32_t)g.tail) << 10);
+            }
+            const uint32_t seg0 = (g.seg == 0 ? 1u : 0u) << 15, col = (16u * j + 16u - g.a) << 16;
+            uint32_t slot = qhead + qn + __popc(ma & lt) + __popc(mb & lt);
+            if (push_a) {
+                const uint32_t sl = slot & 63u;
+                QV.t[sl] = ta;
+                QV.q[sl] = make_uint4(a0, a1, a2, a3);
+                QV.m[sl] = make_uint4(j == 0 ? g.first_prev : ((1u << 16) | pa), meta_a | seg0 | col, g.item, g.rec);
+                ++slot;
+            }
+            if (push_b) {
+                const uint32_t sl = slot & 63u;
+                QV.t[sl] = tb;
+                QV.q[sl] = make_uint4(b0, b1, b2, b3);
+                QV.m[sl] = make_uint4((1u << 16) | pb, meta_b | seg0 | (col + (16u << 16)), g.item, g.rec);
+            }
+            qn += __popc(ma) + __popc(mb);
+        }
+        half = again ? 1u : 0u;
+        if (!again) {
+            P.bit = nb >> 31;
+            P.tw3 = tb.w;
+            P.qw3 = b3;
+            st += 64;
+            pT += 1024;
+        }
     } while (st < wcnt && qn < 32);
     return st;
 }
@@ -310,14 +407,20 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
         const uint8_t *Ts = W.stage[sc];
         const uint32_t ws = cur.s >> 2;  // warp-uniform
         uint32_t st = 0;
+#if WGA_TMA_LANE32
+        uint32_t half = 0;
+#define WGA_TMA_STEPS(WSV) st = tma_steps2<MODE, WSV>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, half, Ts, carry)
+#else
+#define WGA_TMA_STEPS(WSV) st = tma_steps<MODE, WSV>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry)
+#endif
         while (st < wcnt) {
             switch (ws) {
-                case 0: st = tma_steps<MODE, 0>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
-                case 1: st = tma_steps<MODE, 1>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
-                case 2: st = tma_steps<MODE, 2>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
-                default: st = tma_steps<MODE, 3>(QV, qhead, qn, lane, cur, jlm1, wj0, wcnt, st, Ts, carry); break;
+                case 0: WGA_TMA_STEPS(0); break;
+                case 1: WGA_TMA_STEPS(1); break;
+                case 2: WGA_TMA_STEPS(2); break;
+                default: WGA_TMA_STEPS(3); break;
             }
-            if (qn >= 32) {  // the one classification site of the kernel
+            while (qn >= 32) {  // the one classification site of the kernel
                 __syncwarp();
                 walk_batch_q<MODE>(A, QueueVec{&QV, qhead}, 32, lane, E);
                 __syncwarp();
@@ -325,6 +428,7 @@ __global__ void __launch_bounds__(kTmaThreads, kTmaCtasPerSm) k_walk_tma(WalkArg
                 qn -= 32;
             }
         }
+#undef WGA_TMA_STEPS
         --n_out;
         // every lane has consumed its LDS results (they were compared / queued inside tma_steps), so the stage can be
         // handed back to the async proxy without a proxy fence: the fence is for generic-proxy WRITES, there are none
