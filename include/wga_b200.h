@@ -54,7 +54,7 @@ enum wga_status {
     WGA_E_INVALID_ARG = 101,
     WGA_E_UNSUPPORTED = 102,        /* input the reference accepts and this library reports instead of parsing: a csv-quoted PAF
                                      * field whose content holds a quote, a tab or a line break (plain quoted fields are fine);
-                                     * `chain` in the middle of a line; call: --query-regex / <maf>.index */
+                                     * `chain` in the middle of a line */
     WGA_E_NOMEM = 103,
     WGA_E_INTERNAL = 104,
     WGA_E_NCCL = 105
@@ -195,10 +195,25 @@ typedef struct {
     int32_t inv;           /* -i/--inv   (cli.rs:149-150) */
     uint64_t svlen_cutoff; /* -l/--svlen, default 50 (cli.rs:152-153) */
     uint64_t chunk_size;   /* -c/--chunk-size, default 1000000 (cli.rs:171-173); 0 is rejected */
-    const char *query_name; /* --query-name or NULL (query regex is not supported: WGA_E_UNSUPPORTED) */
+    const char *query_name; /* --query-name or NULL */
+    /* --query-regex (cli.rs:166-170; caller.rs:91-104, maf.rs:267-271 `position(|x| regex.is_match_at(&x.name, 0))`): the
+     * regex engine stays with the host.  The host asks for the slab's distinct s-line names (wga_maf_sline_names), keeps
+     * those its Regex matches and passes them here, '\n'-separated (NULL = no regex; "" = nothing matched, every block is
+     * skipped).  Per block the query is then the first s-line whose name is in the list.  Ignored when query_name is set
+     * ("Use regex only if query_name not provided", caller.rs:76). */
+    const char *query_match;
 } wga_call_opts;
-/* VCF header text for `sample` (caller.rs:304-337; no <maf>.index => no ##contig lines) */
+/* VCF header text for `sample` (caller.rs:304-337) without ##contig lines (no <maf>.index) */
 int wga_vcf_header(wga_ctx *ctx, const char *sample, wga_span *out);
+/* the same with the ##contig lines of a <maf>.index (caller.rs:339-357 add_header_contig): `names` / `sizes` = the
+ * index's entries with isref == true, in any order; they are natord-sorted here and written as
+ * "##contig=<ID=name,length=size>" behind the FORMAT lines (noodles-vcf 0.43 header order).  A name that is not a valid
+ * VCF contig ID fails like the reference's `name.parse()?` (WGA_E_INVALID_ARG).  Host-side text: ctx may be NULL. */
+int wga_vcf_header_contigs(wga_ctx *ctx, const char *sample, const char *const *names, const uint64_t *sizes, uint64_t n,
+                           wga_span *out);
+/* distinct s-line names of one slab, first-occurrence order, each followed by '\n' (host memory, valid until the next
+ * call on this thread): what the host evaluates --query-regex on.  Blocks are the ones `call` builds (maf.rs:371-421). */
+int wga_maf_sline_names(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out);
 /* VCF body rows of one slab, file order */
 int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags,
                  const wga_call_opts *opts, wga_span *out);

@@ -1126,11 +1126,77 @@ done:
     return rc;
 }
 
-/* caller.rs:42-157 call_var_maf */
+/* caller.rs:339-357 add_header_contig: the index's isref entries, sorted by natord::compare on the name (Vec::sort_by is
+ * stable), each parsed into a noodles contig name (`name.parse()?`: VCF 4.3 section 1.4.7 grammar -- third-party, parity
+ * unpinned) and written by noodles-vcf 0.43 as "##contig=<ID=name,length=size>" behind the FORMAT lines. */
+static int contig_name_ok(const char *s) {
+    if (!*s || *s == '*' || *s == '=') return 0;
+    for (const unsigned char *p = (const unsigned char *)s; *p; p++)
+        if (*p < '!' || *p > '~' || strchr("\\,\"`'()[]{}<>", *p)) return 0;
+    return 1;
+}
+static int vcf_header_contigs(orc_buf *out, const char *sample, const char *const *names, const uint64_t *sizes, size_t n,
+                              char *err, size_t errcap) {
+    size_t *idx = (size_t *)malloc((n + 1) * sizeof(size_t));
+    for (size_t i = 0; i < n; i++) idx[i] = i;
+    for (size_t i = 1; i < n; i++) { /* stable insertion sort */
+        size_t v = idx[i], j = i;
+        while (j > 0 && orc_natord_compare(names[v], names[idx[j - 1]]) < 0) { idx[j] = idx[j - 1]; j--; }
+        idx[j] = v;
+    }
+    orc_buf h = {0};
+    vcf_header(&h, sample);
+    /* everything in front of "#CHROM" first, then the contig lines */
+    size_t cut = 0;
+    for (size_t i = 0; i + 6 <= h.n; i++)
+        if (memcmp(h.p + i, "#CHROM", 6) == 0 && (i == 0 || h.p[i - 1] == '\n')) { cut = i; break; }
+    buf_put(out, h.p, cut);
+    int rc = ORC_OK;
+    for (size_t k = 0; k < n && rc == ORC_OK; k++) {
+        const size_t i = idx[k];
+        if (!contig_name_ok(names[i])) {
+            set_err(err, errcap, "invalid contig name `%s`", names[i]);
+            rc = ORC_E_OTHER;
+            break;
+        }
+        char num[32];
+        snprintf(num, sizeof num, "%llu", (unsigned long long)sizes[i]);
+        buf_puts(out, "##contig=<ID=");
+        buf_puts(out, names[i]);
+        buf_puts(out, ",length=");
+        buf_puts(out, num);
+        buf_puts(out, ">\n");
+    }
+    if (rc == ORC_OK) buf_put(out, h.p + cut, h.n - cut);
+    orc_buf_free(&h);
+    free(idx);
+    return rc;
+}
+
+/* caller.rs:42-157 call_var_maf.  query_pred stands for `query_regex.is_match_at(&x.name, 0)` (maf.rs:267-271): the
+ * regex engine itself is the regex crate, outside this restatement; has_index != 0 = a <maf>.index was given. */
+int orc_call_maf_ex(const char *text, size_t len, int snp, int inv, uint64_t svlen_cutoff,
+                    const char *sample, const char *query_name, orc_name_pred query_pred, void *pred_ud,
+                    uint64_t chunk_size, int has_index, const char *const *contig_names, const uint64_t *contig_sizes,
+                    size_t n_contigs, orc_buf *out, char *err, size_t errcap);
+
 int orc_call_maf(const char *text, size_t len, int snp, int inv, uint64_t svlen_cutoff,
                  const char *sample, const char *query_name, uint64_t chunk_size, orc_buf *out,
                  char *err, size_t errcap) {
-    vcf_header(out, sample ? sample : "sample");
+    return orc_call_maf_ex(text, len, snp, inv, svlen_cutoff, sample, query_name, NULL, NULL, chunk_size, 0, NULL, NULL, 0, out,
+                           err, errcap);
+}
+
+int orc_call_maf_ex(const char *text, size_t len, int snp, int inv, uint64_t svlen_cutoff,
+                    const char *sample, const char *query_name, orc_name_pred query_pred, void *pred_ud,
+                    uint64_t chunk_size, int has_index, const char *const *contig_names, const uint64_t *contig_sizes,
+                    size_t n_contigs, orc_buf *out, char *err, size_t errcap) {
+    if (has_index) {
+        int hrc = vcf_header_contigs(out, sample ? sample : "sample", contig_names, contig_sizes, n_contigs, err, errcap);
+        if (hrc) return -hrc;
+    } else {
+        vcf_header(out, sample ? sample : "sample");
+    }
     lreader rd;
     maf_reader_init(&rd, text, len);
     mafrec rec = {0};
@@ -1140,6 +1206,12 @@ int orc_call_maf(const char *text, size_t len, int snp, int inv, uint64_t svlen_
         if (query_name) {
             char e2[8];
             if (maf_set_query_byname(&rec, query_name, e2, sizeof e2)) continue; /* caller.rs:79-89 */
+        } else if (query_pred) { /* caller.rs:91-104: first s-line (the target included) whose name matches, else skip */
+            size_t hit = rec.n;
+            for (size_t i = 0; i < rec.n && hit == rec.n; i++)
+                if (query_pred(rec.s[i].name.p, rec.s[i].name.n, pred_ud)) hit = i;
+            if (hit == rec.n) continue;
+            rec.query_idx = hit;
         } else {
             rec.query_idx = 1;
         }

@@ -41,7 +41,8 @@ enum {
     ORC_E_VCF_BASE = 10,          /* noodles REF/ALT base parse failure (parity unpinned) */
     ORC_E_NOM = 11,               /* nom tag("cg:Z:") / tag("chain") / line_ending failure */
     ORC_E_CHAIN_FIELD_MISSING = 12, /* "Parse Chain Error By: Chain Line Field `{0}` Missing"  errors.rs:47-48,109-112 */
-    ORC_E_PARSE_FLOAT = 13        /* "Parse `{0}` Into Float Error"      errors.rs:54-56 */
+    ORC_E_PARSE_FLOAT = 13,       /* "Parse `{0}` Into Float Error"      errors.rs:54-56 */
+    ORC_E_OTHER = 14              /* anyhow::Error passed through (e.g. noodles rejecting a contig name) */
 };
 
 typedef struct {
@@ -93,6 +94,15 @@ int orc_stat_paf(const char *text, size_t len, int each, orc_buf *out,
 int orc_call_maf(const char *text, size_t len, int snp, int inv, uint64_t svlen_cutoff,
                  const char *sample, const char *query_name, uint64_t chunk_size,
                  orc_buf *out, char *err, size_t errcap);
+
+/* the same with --query-regex and a <maf>.index: query_pred(name, n, ud) != 0 stands for
+ * `query_regex.is_match_at(&x.name, 0)` (maf.rs:267-271; the regex crate is outside this restatement), has_index != 0
+ * adds the ##contig lines of caller.rs:339-357 for the given isref entries. */
+typedef int (*orc_name_pred)(const char *name, size_t n, void *ud);
+int orc_call_maf_ex(const char *text, size_t len, int snp, int inv, uint64_t svlen_cutoff,
+                    const char *sample, const char *query_name, orc_name_pred query_pred, void *pred_ud,
+                    uint64_t chunk_size, int has_index, const char *const *contig_names, const uint64_t *contig_sizes,
+                    size_t n_contigs, orc_buf *out, char *err, size_t errcap);
 
 /* the reference's rayon structure with `-t threads` (serial reader under par_bridge's lock + worker pool);
  * output identical to the sequential functions (file order).  Used as the CPU baseline of bench.py. */

@@ -15,6 +15,9 @@ class OrcBuf(ctypes.Structure):
     _fields_ = [("p", ctypes.c_void_p), ("n", ctypes.c_size_t), ("cap", ctypes.c_size_t)]
 
 
+NAME_PRED = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+
+
 class OrcCounts(ctypes.Structure):
     _fields_ = [("c", ctypes.c_uint64 * 11)]
 
@@ -57,6 +60,10 @@ def lib():
         L.orc_call_maf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64,
                                    ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_call_maf_ex.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p,
+                                      ctypes.c_char_p, NAME_PRED, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_uint64), ctypes.c_size_t,
+                                      ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_maf2paf_mt.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int,
                                      ctypes.POINTER(OrcBuf), ctypes.c_char_p, ctypes.c_size_t]
         L.orc_stat_maf_mt.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
@@ -152,6 +159,19 @@ def call_maf(text: bytes, snp=False, inv=False, svlen=50, sample="sample", query
              chunk_size=1000000) -> bytes:
     return _run(lib().orc_call_maf, text, len(text), int(snp), int(inv), svlen, _opt(sample),
                 _opt(query_name), chunk_size)
+
+
+def call_maf_ex(text: bytes, snp=False, inv=False, svlen=50, sample="sample", query_name=None, query_regex=None,
+                chunk_size=1000000, mafindex=None) -> bytes:
+    """call with --query-regex (Python's re.search stands in for Regex::is_match_at(name, 0)) and a parsed <maf>.index"""
+    import re
+    rx = re.compile(query_regex) if query_regex is not None else None
+    pred = NAME_PRED(lambda p, n, ud: 1 if rx.search(ctypes.string_at(p, n)) else 0) if rx is not None else NAME_PRED()
+    contigs = [(k, v["size"]) for k, v in mafindex.items() if v.get("isref")] if mafindex is not None else []
+    names = (ctypes.c_char_p * max(len(contigs), 1))(*[c[0].encode() for c in contigs])
+    sizes = (ctypes.c_uint64 * max(len(contigs), 1))(*[c[1] for c in contigs])
+    return _run(lib().orc_call_maf_ex, text, len(text), int(snp), int(inv), svlen, _opt(sample), _opt(query_name), pred, None,
+                chunk_size, 1 if mafindex is not None else 0, names, sizes, len(contigs))
 
 
 def paf2maf(paf: bytes, t_fa: bytes, t_fai: bytes, q_fa: bytes, q_fai: bytes, t_path="t.fa", q_path="q.fa") -> bytes:

@@ -55,3 +55,27 @@ def test_safe_cut(built):
     want = max(i for i in range(1, len(txt)) if txt[i - 1:i] == b"\n" and txt[i:i + 1] != b"s")
     assert L.wga_maf_safe_cut(txt, len(txt)) == want
     assert L.wga_maf_safe_cut(b"s a\ns b\n", 8) == 0
+
+
+def test_vcf_header_contigs_host_only(built):
+    """wga_vcf_header_contigs is host-side text (ctx may be NULL): natord order, isref entries as given, name grammar --
+    against the oracle's restatement of caller.rs:339-357"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    L = built.load()
+    idx = {"t.chr10": 30, "t.chr2": 20, "t.chr1": 100, "scaffold_7": 9, "Chr01": 4, "chrX": 7, "chr 9": 1}
+    idx.pop("chr 9")
+    names = (ctypes.c_char_p * len(idx))(*[k.encode() for k in idx])
+    sizes = (ctypes.c_uint64 * len(idx))(*idx.values())
+    sp = built.Span()
+    assert L.wga_vcf_header_contigs(None, b"smp", names, sizes, len(idx), ctypes.byref(sp)) == 0
+    got = ctypes.string_at(sp.data, sp.len)
+    txt = b"##maf version=1\na\ns t 0 1 + 9 A\ns q 0 1 + 9 A\n"
+    want = orc.call_maf_ex(txt, sample="smp", mafindex={k: {"size": v, "isref": True} for k, v in idx.items()})
+    assert got == want
+    assert L.wga_vcf_header_contigs(None, None, None, None, 0, ctypes.byref(sp)) == 0
+    assert ctypes.string_at(sp.data, sp.len) == orc.call_maf(txt)
+    for bad in (b"a,b", b"*x", b"=x", b"a b", b"", b"x<y"):
+        nm = (ctypes.c_char_p * 1)(bad)
+        assert L.wga_vcf_header_contigs(None, b"s", nm, sizes, 1, ctypes.byref(sp)) == 101

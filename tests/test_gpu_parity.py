@@ -445,6 +445,51 @@ def test_call_quirks(w, ctx):
     assert e.value.code == 101
 
 
+def test_call_query_regex_and_contigs(w, ctx):
+    """--query-regex (caller.rs:91-104, maf.rs:267-271) through wga_maf_sline_names + wga_call_opts.query_match, and the
+    ##contig lines of a <maf>.index (caller.rs:339-357) through wga_vcf_header_contigs: the host mirror against the
+    oracle's predicate restatement, on hand-made multi-row blocks and on a generated 3-row MAF with many names."""
+    import random
+    hand = _maf([[b"s t.chr1 0 4 + 100 ACGT", b"s hg002#1 0 4 + 100 ACGA", b"s hg002#2 0 4 + 100 AC-T"],
+                 [b"s t.chr1 10 4 + 100 ACGT", b"s other 0 4 + 100 AGGT"],
+                 [b"s t.chr2 0 4 + 100 ACGT", b"s zz 0 4 - 100 ACGT", b"s hg002#2 9 4 + 100 TCGT"],
+                 [b"s t.chr2 0 4 + 100 ACGT"]])
+    rng = random.Random(5)
+    blocks = []
+    for b in range(400):
+        t = bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(20, 200)))
+        rows = [b"s ref.chr%d %d %d + 100000 " % (b % 7, b * 10, len(t)) + t]
+        for k in range(rng.randrange(1, 4)):
+            q = bytearray(t)
+            for i in range(len(q)):
+                if rng.random() < 0.05:
+                    q[i] = rng.choice(b"ACGT-")
+            n = sum(1 for c in q if c != 45)
+            rows.append(b"s sp%d#%d.ctg%d %d %d %s 100000 " % (rng.randrange(4), rng.randrange(2), rng.randrange(30), b, n,
+                                                              rng.choice([b"+", b"-"])) + bytes(q))
+        blocks.append(rows)
+    big = _maf(blocks)
+    idx = {"ref.chr10": {"size": 30, "isref": True}, "ref.chr2": {"size": 20, "isref": True}, "sp1#0.ctg1": {"size": 5, "isref": False},
+           "ref.chr1": {"size": 100000, "isref": True}}
+    for text, pats in ((hand, [rb"^hg002#.*", rb"#2", rb"chr", rb"nomatch", rb"^(zz|other)$", rb"."]),
+                       (big, [rb"^sp2#", rb"#1\.ctg1\d$", rb"^sp[03]#0", rb"ctg7$", rb"^ref", rb"xyz"])):
+        for pat in pats:
+            for mi in (None, idx):
+                got = w.run_bytes(w.call_var_maf, w.MAFReader(text), mi, True, True, 0, query_regex=pat, ctx=ctx)
+                assert got == orc.call_maf_ex(text, snp=True, inv=True, svlen=0, query_regex=pat, mafindex=mi), pat
+        # --query-name wins over the regex (caller.rs:76)
+        got = w.run_bytes(w.call_var_maf, w.MAFReader(text), None, True, False, 0, query_name="zz", query_regex=rb"hg002", ctx=ctx)
+        assert got == orc.call_maf(text, snp=True, svlen=0, query_name="zz")
+    # the names the host evaluates the regex on: distinct, first-occurrence order
+    from wgatools_b200._lib import WGA_F_FIRST_SLAB, WGA_MEM_HOST
+    hbuf = ctypes.c_char_p(hand)
+    names = ctx.maf_sline_names(ctypes.cast(hbuf, ctypes.c_void_p), len(hand), WGA_MEM_HOST, WGA_F_FIRST_SLAB)
+    assert names == [b"t.chr1", b"hg002#1", b"hg002#2", b"other", b"t.chr2", b"zz"]
+    with pytest.raises(w.WGAError) as e:
+        ctx.vcf_header_contigs("s", [("bad,name", 3)])
+    assert e.value.code == 101
+
+
 def test_call_random_chunks(w, ctx):
     rng = random.Random(17)
     for it in range(60):

@@ -171,6 +171,36 @@ def test_query_name_selection():
     assert len(orc.call_maf(txt, query_name="zz").splitlines()) == 8  # call skips instead
 
 
+def test_query_regex_and_contig_lines():
+    """caller.rs:91-104 (--query-regex: first s-line whose name matches -- the target line included -- else the block is
+    skipped; ignored when --query-name is given) and caller.rs:339-357 (##contig lines of the <maf>.index: isref entries,
+    natord order, behind the FORMAT lines).  Hand-derived from the source; the regex crate itself is played by Python's re."""
+    txt = _maf([[b"s t.chr1 0 4 + 100 ACGT", b"s hg002#1 0 4 + 100 ACGA", b"s hg002#2 0 4 + 100 AC-T"],
+                [b"s t.chr1 10 4 + 100 ACGT", b"s other 0 4 + 100 AGGT"],
+                [b"s t.chr2 0 4 + 100 ACGT", b"s zz 0 4 + 100 ACGT", b"s hg002#2 9 4 + 100 TCGT"]])
+    body = lambda v: [l for l in v.splitlines() if not l.startswith(b"#")]
+    # regex picks hg002#1 in block 1, nothing in block 2 (skipped), hg002#2 in block 3
+    got = body(orc.call_maf_ex(txt, snp=True, svlen=0, query_regex=rb"^hg002#.*"))
+    assert [l.split(b"\t")[:2] for l in got] == [[b"t.chr1", b"4"], [b"t.chr2", b"1"]]
+    assert got[0].endswith(b"1|1:hg002#1@3@P") and got[1].endswith(b"1|1:hg002#2@9@P")
+    # an unanchored search (is_match_at(name, 0)): "#2" finds hg002#2 (a deletion at POS 2); "chr" matches the TARGET line itself
+    assert body(orc.call_maf_ex(txt, snp=True, svlen=0, query_regex=rb"#2"))[0].startswith(b"t.chr1\t2\t.\tCG\tC\t")
+    assert body(orc.call_maf_ex(txt, snp=True, svlen=0, query_regex=rb"chr")) == []  # target vs itself: no variant
+    # --query-name wins over the regex
+    assert orc.call_maf_ex(txt, snp=True, svlen=0, query_name="other", query_regex=rb"hg002") == \
+        orc.call_maf(txt, snp=True, svlen=0, query_name="other")
+    # contig lines: natord (chr2 < chr10), only isref entries, behind the FORMAT lines and in front of #CHROM
+    idx = {"t.chr10": {"size": 30, "isref": True}, "t.chr2": {"size": 20, "isref": True}, "q.chr1": {"size": 5, "isref": False},
+           "t.chr1": {"size": 100, "isref": True}}
+    hdr = [l for l in orc.call_maf_ex(txt, mafindex=idx).splitlines() if l.startswith(b"#")]
+    assert hdr[-4:] == [b"##contig=<ID=t.chr1,length=100>", b"##contig=<ID=t.chr2,length=20>", b"##contig=<ID=t.chr10,length=30>",
+                        b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tsample"]
+    assert hdr[-5].startswith(b"##FORMAT=<ID=GT")
+    assert orc.call_maf_ex(txt, mafindex={}) == orc.call_maf(txt)  # an empty index adds nothing
+    with pytest.raises(orc.OracleError):
+        orc.call_maf_ex(txt, mafindex={"bad,name": {"size": 1, "isref": True}})
+
+
 seqs = st.text(alphabet="ACGTacgtN-", min_size=1, max_size=80)
 
 

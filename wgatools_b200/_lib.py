@@ -22,7 +22,7 @@ class Span(ctypes.Structure):
 
 class CallOpts(ctypes.Structure):
     _fields_ = [("snp", ctypes.c_int32), ("inv", ctypes.c_int32), ("svlen_cutoff", ctypes.c_uint64),
-                ("chunk_size", ctypes.c_uint64), ("query_name", ctypes.c_char_p)]
+                ("chunk_size", ctypes.c_uint64), ("query_name", ctypes.c_char_p), ("query_match", ctypes.c_char_p)]
 
 
 # wga_transport (include/wga_b200.h): host-buffer collective primitives provided by the caller
@@ -77,6 +77,9 @@ ABI = {
     "wga_stat_acc_import": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]),
     "wga_stat_acc_npairs": (ctypes.c_uint64, [ctypes.c_void_p]),
     "wga_vcf_header": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _P(Span)]),
+    "wga_vcf_header_contigs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _P(ctypes.c_char_p), _P(ctypes.c_uint64),
+                                              ctypes.c_uint64, _P(Span)]),
+    "wga_maf_sline_names": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, _P(Span)]),
     "wga_maf_call": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32,
                                    _P(CallOpts), _P(Span)]),
     "wga_fasta_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,

@@ -84,6 +84,21 @@ class Context:
         self._check(self.L.wga_maf_call(self.h, ptr, n, mem, flags, ctypes.byref(opts), ctypes.byref(sp)))
         return sp.data, sp.len
 
+    def vcf_header_contigs(self, sample, contigs):
+        """header with the ##contig lines of a <maf>.index: contigs = [(name, size)] of its isref entries (caller.rs:339-357)"""
+        n = len(contigs)
+        names = (ctypes.c_char_p * max(n, 1))(*[c[0].encode() if isinstance(c[0], str) else c[0] for c in contigs])
+        sizes = (ctypes.c_uint64 * max(n, 1))(*[int(c[1]) for c in contigs])
+        sp = Span()
+        self._check(self.L.wga_vcf_header_contigs(self.h, _opt(sample), names, sizes, n, ctypes.byref(sp)))
+        return ctypes.string_at(sp.data, sp.len)
+
+    def maf_sline_names(self, ptr, n, mem, flags):
+        """distinct s-line names of one slab (first-occurrence order): what a host evaluates --query-regex on"""
+        sp = Span()
+        self._check(self.L.wga_maf_sline_names(self.h, ptr, n, mem, flags, ctypes.byref(sp)))
+        return ctypes.string_at(sp.data, sp.len).split(b"\n")[:-1] if sp.len else []
+
     def vcf_header(self, sample="sample"):
         sp = Span()
         self._check(self.L.wga_vcf_header(self.h, _opt(sample), ctypes.byref(sp)))
@@ -441,14 +456,33 @@ def stat_paf(reader: PAFReader, writer, each=False, ctx=None):
 
 def call_var_maf(mafreader: MAFReader, mafindex, writer, if_snp=False, if_inv=False, svlen_cutoff=50,
                  _between=False, sample=None, query_name=None, query_regex=None, chunk_size=None, ctx=None):
-    """src/tools/caller.rs:42-157.  mafindex (contig lines) and query_regex are not supported."""
+    """src/tools/caller.rs:42-157.
+    mafindex: the parsed <maf>.index (tools/index.rs:78-86: {name: {"size": .., "isref": ..}}) or None -- its isref
+    entries become the header's ##contig lines (caller.rs:339-357).
+    query_regex: a pattern string or compiled pattern.  The regex engine stays on the host, as it would in the Rust
+    wrapper: the slab's distinct s-line names come back from the library, the host keeps the names the
+    regex matches (`Regex::is_match_at(name, 0)` = an unanchored search, maf.rs:267-271; Python's `re.search` stands in
+    for the Rust crate here) and the library picks, per block, the first s-line whose name is in that list."""
     ctx = ctx or default_context()
-    if mafindex is not None or query_regex is not None:
-        raise WGAError(102, "mafindex / query_regex are outside the accelerated path")
-    writer.write(ctx.vcf_header(sample or "sample"))
-    opts = CallOpts(snp=int(bool(if_snp)), inv=int(bool(if_inv)), svlen_cutoff=int(svlen_cutoff),
-                    chunk_size=int(1000000 if chunk_size is None else chunk_size), query_name=_opt(query_name))
+    if mafindex is not None:
+        contigs = [(name, item["size"]) for name, item in mafindex.items() if item.get("isref")]
+        writer.write(ctx.vcf_header_contigs(sample or "sample", contigs))
+    else:
+        writer.write(ctx.vcf_header(sample or "sample"))
+    rx = None
+    if query_name is None and query_regex is not None:
+        import re
+        rx = re.compile(query_regex.encode() if isinstance(query_regex, str) else query_regex) if not hasattr(query_regex, "search") \
+            else query_regex
     for p, n, mem, flags in _maf_slabs(mafreader, ctx):
+        match = None
+        if rx is not None:
+            names = ctx.maf_sline_names(p, n, mem, flags)
+            hit = [nm for nm in names if rx.search(nm if isinstance(rx.pattern, bytes) else nm.decode("utf-8", "replace"))]
+            match = b"".join(nm + b"\n" for nm in hit)
+        opts = CallOpts(snp=int(bool(if_snp)), inv=int(bool(if_inv)), svlen_cutoff=int(svlen_cutoff),
+                        chunk_size=int(1000000 if chunk_size is None else chunk_size), query_name=_opt(query_name),
+                        query_match=match)
         ptr, ln = ctx.maf_call_raw(p, n, mem, flags, opts)
         if ln:
             writer.write(ctypes.string_at(ptr, ln))

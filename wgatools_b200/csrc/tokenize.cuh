@@ -378,8 +378,37 @@ struct Recs {
 // mode 0: maf2paf/stat (missing query => error like the reference); mode 1: call (skip the block)
 // target = slines[0]; query = slines[1] or the first s-line named `qname`
 // (maf.rs:263-285 set_query_idx_byname, :424-540 AlignRecord; caller.rs:62-108)
+// --query-regex (maf.rs:267-271, caller.rs:91-104): the host evaluates its Regex on the slab's distinct s-line names
+// (wga_maf_sline_names) and hands the matching names back; "first s-line whose name matches" is then "first s-line whose
+// name is in the set".  The set travels as FNV-1a hashes in ascending order + the names themselves (exact compare).
+struct NameSet {
+    const uint64_t *hash;  // [n] ascending
+    const uint32_t *off;   // [n+1] into bytes, same order
+    const uint8_t *bytes;
+    uint32_t n;
+};
+__host__ __device__ __forceinline__ uint64_t fnv1a64(const uint8_t *p, uint32_t n) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (uint32_t i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001B3ull; }
+    return h;
+}
+__device__ __forceinline__ bool name_in_set(const NameSet &S, const uint8_t *nm, uint32_t len) {
+    const uint64_t h = fnv1a64(nm, len);
+    uint32_t lo = 0, hi = S.n;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (S.hash[m] < h) lo = m + 1; else hi = m; }
+    for (; lo < S.n && S.hash[lo] == h; ++lo) {
+        if (S.off[lo + 1] - S.off[lo] != len) continue;
+        const uint8_t *c = S.bytes + S.off[lo];
+        bool eq = true;
+        for (uint32_t j = 0; j < len && eq; ++j) eq = nm[j] == c[j];
+        if (eq) return true;
+    }
+    return false;
+}
+
+// has_qname: 0 = slines[1], 1 = the first s-line named `qname`, 2 = the first s-line whose name is in `qset`
 __global__ void k_build_records(uint64_t n_rec, const uint8_t *__restrict__ text, SLines sl, Recs rc,
-                                const uint8_t *__restrict__ qname, uint32_t qname_len, int has_qname,
+                                const uint8_t *__restrict__ qname, uint32_t qname_len, int has_qname, NameSet qset,
                                 int mode, unsigned long long *err_key, unsigned long long *ragged) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
@@ -391,6 +420,10 @@ __global__ void k_build_records(uint64_t n_rec, const uint8_t *__restrict__ text
         bool found = false;
         for (uint64_t i = 0; i < nl && !found; ++i) {
             uint64_t k = first + i;
+            if (has_qname == 2) {
+                if (name_in_set(qset, text + sl.name_off[k], sl.name_len[k])) { found = true; qi = i; }
+                continue;
+            }
             if (sl.name_len[k] != qname_len) continue;
             const uint8_t *nm = text + sl.name_off[k];
             bool eq = true;
@@ -434,6 +467,23 @@ __global__ void k_build_records(uint64_t n_rec, const uint8_t *__restrict__ text
     rc.neg[r] = sl.neg[ql];
     rc.skip[r] = skip ? 1 : 0;
     rc.n_items[r] = skip ? 0u : (uint32_t)((n + kSeg - 1) / kSeg);
+}
+
+// wga_maf_sline_names: byte count (name + '\n') of every s-line that belongs to a record, then the names themselves
+__global__ void k_sline_name_len(uint64_t n_rec, Recs rc, SLines sl, uint64_t n_lines, uint64_t *__restrict__ nlen) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    for (uint64_t k = rc.first[r]; k <= rc.last[r] && k < n_lines; ++k) nlen[k] = (uint64_t)sl.name_len[k] + 1;
+}
+__global__ void k_sline_name_copy(uint64_t n_lines, const uint8_t *__restrict__ text, SLines sl, const uint64_t *__restrict__ nlen,
+                                  const uint64_t *__restrict__ noff, char *__restrict__ out) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_lines || nlen[k] == 0) return;
+    char *o = out + noff[k];
+    const uint8_t *nm = text + sl.name_off[k];
+    const uint32_t n = sl.name_len[k];
+    for (uint32_t j = 0; j < n; ++j) o[j] = (char)nm[j];
+    o[n] = '\n';
 }
 
 __global__ void k_fill_items(uint64_t n_rec, const uint32_t *__restrict__ n_items,

@@ -6,7 +6,12 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cstring>
 #include <new>
+#include <string>
+#include <string_view>
+#include <unordered_set>
+#include <vector>
 #include "ctx.cuh"
 #include "emit_paf.cuh"
 #include "stat.cuh"
@@ -312,7 +317,8 @@ int build_delim_index(wga_ctx *ctx, const uint8_t *text, uint64_t len, uint64_t 
 }
 
 // tokenise the slab: whitespace index -> lines -> s-lines -> records -> work items
-int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep *P) {
+// qmatch: '\n'-separated names a --query-regex matched (see NameSet, tokenize.cuh); only looked at when qname is null
+int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep *P, const char *qmatch = nullptr) {
     const uint64_t len = ctx->text_len;
     const uint8_t *text = ctx->d_text;
     ctx->n_rec = ctx->n_items = ctx->n_runs = 0;
@@ -393,13 +399,49 @@ int prepare_maf(wga_ctx *ctx, uint32_t flags, const char *qname, int mode, Prep 
     // 4. records + work items
     uint8_t *d_q = nullptr;
     uint32_t qlen = qname ? (uint32_t)strlen(qname) : 0;
+    NameSet qset = {nullptr, nullptr, nullptr, 0};
+    std::vector<uint8_t> h_set;  // stays alive until the stream has consumed it (the read-back below synchronises)
     if (qname) {
         d_q = ctx->buf<uint8_t>(B_QNAME, qlen + 1);
         if (!d_q) return ctx->err_code;
         WGA_CK(cudaMemcpyAsync(d_q, qname, qlen, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (qmatch) {
+        size_t off_at = 0, bytes_at = 0, n = 0;
+        const int brc = no_throw([&] {
+        // [hash x n | off x (n+1) | bytes], names in ascending hash order
+        std::vector<std::pair<uint64_t, std::pair<const char *, uint32_t>>> nm;
+        for (const char *b = qmatch; *b;) {
+            const char *e = strchr(b, '\n');
+            const size_t l = e ? (size_t)(e - b) : strlen(b);
+            if (l) nm.push_back({fnv1a64((const uint8_t *)b, (uint32_t)l), {b, (uint32_t)l}});
+            b += l + (e ? 1 : 0);
+        }
+        std::sort(nm.begin(), nm.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+        n = nm.size();
+        size_t bytes = 0;
+        for (auto &x : nm) bytes += x.second.second;
+        off_at = 8 * n; bytes_at = off_at + 4 * (n + 1);
+        h_set.resize(bytes_at + bytes + 8);
+        uint64_t *hh = (uint64_t *)h_set.data();
+        uint32_t *ho = (uint32_t *)(h_set.data() + off_at);
+        uint32_t o = 0;
+        for (size_t i = 0; i < n; ++i) {
+            hh[i] = nm[i].first;
+            ho[i] = o;
+            memcpy(h_set.data() + bytes_at + o, nm[i].second.first, nm[i].second.second);
+            o += nm[i].second.second;
+        }
+        ho[n] = o;
+        return WGA_OK;
+        });
+        if (brc) return brc;
+        d_q = (uint8_t *)ctx->ensure(B_QNAME, h_set.size());
+        if (!d_q) return ctx->err_code;
+        WGA_CK(cudaMemcpyAsync(d_q, h_set.data(), h_set.size(), cudaMemcpyHostToDevice, ctx->stream));
+        qset.hash = (const uint64_t *)d_q; qset.off = (const uint32_t *)(d_q + off_at); qset.bytes = d_q + bytes_at; qset.n = (uint32_t)n;
     }
-    LAUNCH(ctx, k_build_records, grid_for(n_rec, 256), 256, n_rec, text, sl, rc, d_q, qlen, qname ? 1 : 0, mode, P->err_key,
-           P->err_key + 1);
+    LAUNCH(ctx, k_build_records, grid_for(n_rec, 256), 256, n_rec, text, sl, rc, d_q, qlen, qname ? 1 : (qmatch ? 2 : 0), qset, mode,
+           P->err_key, P->err_key + 1);
     WGA_CK(cudaMemsetAsync(rc.n_items + n_rec, 0, 4, ctx->stream));
     WGA_CK(cudaMemsetAsync(rc.ncols + n_rec, 0, 8, ctx->stream));
     WGA_TRY(exclusive_sum(ctx, rc.n_items, P->item_base, n_rec + 1));
@@ -1178,6 +1220,99 @@ int wga_vcf_header(wga_ctx *ctx, const char *sample, wga_span *out) {
     return WGA_OK;
 }
 
+// noodles-vcf 0.43 contig name (Map<Contig> key, FromStr): the VCF 4.3 grammar of section 1.4.7 -- printable ASCII without
+// \ , " ` ' ( ) [ ] { } < >, not starting with '*' or '='.  (third-party behaviour restated: parity unpinned)
+static bool vcf_contig_name_ok(const char *s) {
+    if (!*s || *s == '*' || *s == '=') return false;
+    for (const unsigned char *p = (const unsigned char *)s; *p; ++p)
+        if (*p < '!' || *p > '~' || strchr("\\,\"`'()[]{}<>", *p)) return false;
+    return true;
+}
+
+int wga_vcf_header_contigs(wga_ctx *ctx, const char *sample, const char *const *names, const uint64_t *sizes, uint64_t n,
+                           wga_span *out) {
+    (void)ctx;  // host-side text only
+    if (!out || (n && (!names || !sizes))) return WGA_E_INVALID_ARG;
+    // caller.rs:339-357 add_header_contig: the index's isref entries, natord-sorted by name (stable), one
+    // "##contig=<ID=name,length=size>" each; noodles writes them behind the FORMAT lines
+    return no_throw([&]() -> int {
+    std::vector<uint64_t> idx(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!names[i] || !vcf_contig_name_ok(names[i])) {
+            if (ctx) ctx->set_error(WGA_E_INVALID_ARG, i, "contig name is not a valid VCF contig ID");
+            return WGA_E_INVALID_ARG;
+        }
+        idx[i] = i;
+    }
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return natord_cmp(names[a], names[b]) < 0; });
+    static thread_local std::string hdr;
+    hdr = "##fileformat=VCFv4.4\n"
+          "##INFO=<ID=SVLEN,Number=A,Type=Integer,Description=\"Length of structural variant\">\n"
+          "##INFO=<ID=SVTYPE,Number=1,Type=String,Description=\"Type of structural variant\">\n"
+          "##INFO=<ID=END,Number=1,Type=Integer,Description=\"End position of the longest variant described in this record\">\n"
+          "##INFO=<ID=INV_NEST,Number=1,Type=String,Description=\"Varations nested within inversion\">\n"
+          "##FORMAT=<ID=QI,Number=1,Type=String,Description=\"Query informations\">\n"
+          "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n";
+    for (uint64_t i : idx) {
+        hdr += "##contig=<ID=";
+        hdr += names[i];
+        hdr += ",length=";
+        hdr += std::to_string(sizes[i]);
+        hdr += ">\n";
+    }
+    hdr += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t";
+    hdr += sample ? sample : "sample";
+    hdr += "\n";
+    out->data = hdr.data();
+    out->len = hdr.size();
+    return WGA_OK;
+    });
+}
+
+int wga_maf_sline_names(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, wga_span *out) {
+    if (!ctx || !out || (!text && len)) return WGA_E_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    out->data = nullptr;
+    out->len = 0;
+    walk_begin(ctx);
+    WGA_TRY(stage_text(ctx, text, len, mem, flags));
+    Prep P;
+    WGA_TRY(prepare_maf(ctx, flags, nullptr, 1, &P));  // the records `call` builds (parse errors are call's errors)
+    const uint64_t n_rec = ctx->n_rec, n_lines = ctx->n_lines;
+    if (n_rec == 0) return sync_check(ctx);
+    uint64_t *nlen = ctx->buf<uint64_t>(B_GEN_A, n_lines + 1), *noff = ctx->buf<uint64_t>(B_GEN_B, n_lines + 1);
+    if (!nlen || !noff) return ctx->err_code;
+    WGA_CK(cudaMemsetAsync(nlen, 0, (n_lines + 1) * 8, ctx->stream));
+    LAUNCH(ctx, k_sline_name_len, grid_for(n_rec, 256), 256, n_rec, P.rc, P.sl, n_lines, nlen);
+    WGA_TRY(exclusive_sum(ctx, nlen, noff, n_lines + 1));
+    uint64_t total;
+    WGA_TRY(read_scalars(ctx, {noff + n_lines}, &total));
+    if (total == 0) return sync_check(ctx);
+    char *d_all = (char *)ctx->ensure(B_OUT, total + 16);
+    if (!d_all) return ctx->err_code;
+    LAUNCH(ctx, k_sline_name_copy, grid_for(n_lines, 256), 256, n_lines, ctx->d_text, P.sl, (const uint64_t *)nlen,
+           (const uint64_t *)noff, d_all);
+    // distinct names in first-occurrence order: a few hundred among millions of s-lines, deduplicated on the host
+    return no_throw([&]() -> int {
+    std::vector<char> all(total);
+    WGA_CK(cudaMemcpyAsync(all.data(), d_all, total, cudaMemcpyDeviceToHost, ctx->stream));
+    WGA_TRY(sync_check(ctx));
+    static thread_local std::string names;
+    names.clear();
+    std::unordered_set<std::string_view> seen;
+    for (uint64_t b = 0; b < total;) {
+        const char *e = (const char *)memchr(all.data() + b, '\n', total - b);
+        const uint64_t l = (uint64_t)(e - (all.data() + b));
+        std::string_view nm(all.data() + b, l);
+        if (seen.insert(nm).second) { names.append(nm); names.push_back('\n'); }
+        b += l + 1;
+    }
+    out->data = names.data();
+    out->len = names.size();
+    return WGA_OK;
+    });
+}
+
 int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const wga_call_opts *opts,
                  wga_span *out) {
     if (!ctx || !out || !opts || (!text && len)) return WGA_E_INVALID_ARG;
@@ -1198,7 +1333,7 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     // the caller-classified run list of this slab may still be there (wga_maf2paf with WGA_F_SHARE_WALK): `call` then
     // starts at its chunk grid.  Only when it would have built exactly the same records (no single-row / ragged block).
     const bool reuse = (flags & WGA_F_REUSE_INDEX) && tc.valid && tc.d_text == ctx->d_text && tc.len == len && wc.recs && wc.runs &&
-                       wc.call_same && wc.same_q(opts->query_name);
+                       wc.call_same && wc.same_q(opts->query_name) && !(opts->query_match && !opts->query_name);
     if (reuse) {
         P = wc.P;
         RU = wc.RU;
@@ -1209,7 +1344,7 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
         if (!P.err_key) return ctx->err_code;
         LAUNCH(ctx, k_init_u64, 1, 1, P.err_key, 1, kNoErr);
     } else {
-        WGA_TRY(prepare_maf(ctx, flags, opts->query_name, 1, &P));
+        WGA_TRY(prepare_maf(ctx, flags, opts->query_name, 1, &P, opts->query_match));
     }
     const uint64_t n_rec = ctx->n_rec, n_items = ctx->n_items;
     if (n_rec == 0 || n_items == 0) return sync_check(ctx);
