@@ -264,8 +264,16 @@ constexpr int kVcfSpan = 6144;  // bytes of output one warp (32 consecutive rows
 // one VCF body row per thread.  PASS 0: row_len[row] = bytes.  PASS 1: the 32 rows of a warp are consecutive in
 // the output, so they are formatted into one shared-memory span and copied out with aligned word stores
 // (a span longer than kVcfSpan -- long SV rows -- is written directly).
+// row -> run map: run j is written at its first row (runs without rows write nothing), a running maximum fills the rest
+__global__ void k_row_run_seed(uint64_t n_runs, const uint64_t *__restrict__ rows, const uint64_t *__restrict__ rowbase,
+                               uint32_t *__restrict__ row_run) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_runs && rows[j] != 0) row_run[rowbase[j]] = (uint32_t)j;
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n_rows, const uint64_t *__restrict__ rowbase,
+                                                          const uint32_t *__restrict__ row_run,
                                                           uint64_t *__restrict__ row_len, const uint64_t *__restrict__ row_off,
                                                           char *__restrict__ out, unsigned long long *err_key) {
     __shared__ __align__(16) char s_span[PASS == 1 ? kVcfThreads / 32 : 1][PASS == 1 ? kVcfSpan + 16 : 16];
@@ -288,10 +296,10 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
     char *d_dst = nullptr;
     uint64_t d_len = 0;
     unsigned long long ekey = 0;
-    // run owning a row: last j with rowbase[j] <= row.  The 32 rows of a warp are consecutive, so their runs sit in a
-    // short window above the run of the warp's first row: one full binary search per warp, a bounded one per lane.
+    // run owning a row: last j with rowbase[j] <= row -- read from the row -> run map (k_row_run_seed + running maximum);
+    // without the map (more than 2^32 runs) one full binary search per warp and a bounded one per lane
     uint64_t j_warp = 0;
-    {
+    if (!row_run) {
         const uint64_t row0 = row - lane;
         if (lane == 0 && row0 < n_rows) {
             uint64_t lo = 0, hi = V.n_runs;
@@ -301,9 +309,14 @@ __global__ void __launch_bounds__(kVcfThreads) k_vcf_rows(CallView V, uint64_t n
         j_warp = __shfl_sync(0xFFFFFFFFu, j_warp, 0);
     }
     if (have_row) {
-    uint64_t lo = j_warp, hi = j_warp + 256 < V.n_runs ? j_warp + 256 : V.n_runs;
-    if (hi < V.n_runs && rowbase[hi] <= row) { lo = hi; hi = V.n_runs; }  // a long stretch of runs without rows
-    while (hi - lo > 1) { uint64_t m = (lo + hi) >> 1; if (rowbase[m] <= row) lo = m; else hi = m; }
+    uint64_t lo;
+    if (row_run) lo = row_run[row];
+    else {
+        lo = j_warp;
+        uint64_t hi = j_warp + 256 < V.n_runs ? j_warp + 256 : V.n_runs;
+        if (hi < V.n_runs && rowbase[hi] <= row) { lo = hi; hi = V.n_runs; }  // a long stretch of runs without rows
+        while (hi - lo > 1) { uint64_t m = (lo + hi) >> 1; if (rowbase[m] <= row) lo = m; else hi = m; }
+    }
     const uint64_t j = lo;
     uint64_t k = row - rowbase[j];
     const uint32_t rec = V.run_rec[j];

@@ -51,7 +51,7 @@ enum BufId {
     B_TEXT_RES, B_TOK_ERR, B_CNT11, B_XRUN_POS, B_XRUN_REC, B_XRUN_CLS, B_XRUN_FLAG, B_XRUN_IDX,
     B_PP_A, B_PP_B, B_PP_C, B_PP_D, B_PP_E, B_PP_F, B_PP_G, B_PP_H, B_PP_I, B_PP_J, B_PP_K, B_PP_L, B_PP_M, B_PP_N, B_PP_O, B_PP_P,
     B_PP_Q, B_PP_R, B_PP_S, B_PP_T,
-    B_PAF_A, B_PAF_B, B_PAF_C, B_PAF_D, B_PAF_E, B_PAF_F, B_PAF_G, B_PAF_H, B_PAF_I, B_PAF_J, B_CS_ARENA, B_CS_TOTAL, B_CIG_NVEC, B_CIG_PBASE, B_CIG_CHUNK, B_CIG_ACC, B_CHAIN_HDR, B_CHAIN_IRR, B_UNQ_TEXT,
+    B_PAF_A, B_PAF_B, B_PAF_C, B_PAF_D, B_PAF_E, B_PAF_F, B_PAF_G, B_PAF_H, B_PAF_I, B_PAF_J, B_CS_ARENA, B_CS_TOTAL, B_CIG_NVEC, B_CIG_PBASE, B_CIG_CHUNK, B_CIG_ACC, B_CHAIN_HDR, B_CHAIN_IRR, B_UNQ_TEXT, B_ROW_RUN,
     B_COUNT_
 };
 
@@ -173,6 +173,21 @@ static int exclusive_sum(wga_ctx *ctx, const InT *in, OutT *out, uint64_t n) {
     void *t = ctx->ensure(B_CUBTMP, tmp);
     if (!t) return ctx->err_code;
     WGA_CK(cub::DeviceScan::ExclusiveSum(t, tmp, in, out, (int64_t)n, ctx->stream));
+    ctx->n_cub++;
+    return WGA_OK;
+}
+
+// running maximum (utility: turns "index j scattered at the first row of run j" into the row -> run map of call.cuh)
+struct MaxU32 {
+    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+static int inclusive_max_u32(wga_ctx *ctx, uint32_t *io, uint64_t n) {
+    if (n == 0) return WGA_OK;
+    size_t tmp = 0;
+    WGA_CK(cub::DeviceScan::InclusiveScan(nullptr, tmp, io, io, MaxU32(), (int64_t)n, ctx->stream));
+    void *t = ctx->ensure(B_CUBTMP, tmp);
+    if (!t) return ctx->err_code;
+    WGA_CK(cub::DeviceScan::InclusiveScan(t, tmp, io, io, MaxU32(), (int64_t)n, ctx->stream));
     ctx->n_cub++;
     return WGA_OK;
 }

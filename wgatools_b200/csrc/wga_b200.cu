@@ -1406,8 +1406,17 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     if (n_rows == 0) return sync_check(ctx);
     uint64_t *row_len = ctx->buf<uint64_t>(B_ROW_LEN, n_rows + 1), *row_off = ctx->buf<uint64_t>(B_ROW_OFF, n_rows + 1);
     if (!row_len || !row_off) return ctx->err_code;
-    LAUNCH(ctx, k_vcf_rows<0>, grid_for(n_rows + 1, 128), 128, V, n_rows, rowbase, row_len, (const uint64_t *)nullptr,
-           (char *)nullptr, P.err_key);
+    // row -> run map (both row passes start from it instead of searching rowbase)
+    uint32_t *row_run = nullptr;
+    if (n_runs < 0xFFFFFFFFull) {
+        row_run = ctx->buf<uint32_t>(B_ROW_RUN, n_rows + 1);
+        if (!row_run) return ctx->err_code;
+        WGA_CK(cudaMemsetAsync(row_run, 0, (n_rows + 1) * 4, ctx->stream));
+        LAUNCH(ctx, k_row_run_seed, grid_for(n_runs, 256), 256, n_runs, (const uint64_t *)rows, (const uint64_t *)rowbase, row_run);
+        WGA_TRY(inclusive_max_u32(ctx, row_run, n_rows));
+    }
+    LAUNCH(ctx, k_vcf_rows<0>, grid_for(n_rows + 1, 128), 128, V, n_rows, rowbase, (const uint32_t *)row_run, row_len,
+           (const uint64_t *)nullptr, (char *)nullptr, P.err_key);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rows + 1));
     uint64_t sc[2];
     WGA_TRY(read_scalars(ctx, {row_off + n_rows, P.err_key}, sc));
@@ -1417,7 +1426,8 @@ int wga_maf_call(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t
     }
     char *d_out = (char *)ctx->ensure(B_OUT, sc[0] + 16);
     if (!d_out) return ctx->err_code;
-    LAUNCH(ctx, k_vcf_rows<1>, grid_for(n_rows, 128), 128, V, n_rows, rowbase, row_len, row_off, d_out, P.err_key);
+    LAUNCH(ctx, k_vcf_rows<1>, grid_for(n_rows, 128), 128, V, n_rows, rowbase, (const uint32_t *)row_run, row_len, row_off, d_out,
+           P.err_key);
     uint64_t key1;  // REF/ALT bases are validated while they are written
     WGA_TRY(read_scalars(ctx, {P.err_key}, &key1));
     if (key1 != kNoErr) {
