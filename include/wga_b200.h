@@ -161,9 +161,12 @@ uint64_t wga_stat_acc_npairs(const wga_stat_acc *acc);
  * One rank per GPU; ranks hold contiguous byte ranges of the input in rank order and feed their own accumulator with
  * wga_maf_stat / wga_paf_stat.  wga_stat_allreduce then turns every rank's (merged-mode) accumulator into the
  * accumulator of the whole file: the ranks agree on the pair list (first-seen order over ranks 0..N-1 = file order),
- * ONE all-reduce(sum, u64) of the [n_pairs x 11] counter table, one all-reduce(min, u64) of the [n_pairs x 2] starts,
- * and the order-dependent f32 inv_size column carried rank to rank (n_pairs x 4 B per hop) so that the result is
- * bit-identical to a single process reading the whole file.  wga_stat_acc_write on any rank prints the global TSV. */
+ * ONE all-reduce(sum, u64) of the [n_pairs x 12] table (11 counters + the integer sum of the '-' records' inv_size
+ * numerators), one all-reduce(min, u64) of the [n_pairs x 2] starts.  inv_size is an f32 sum in file order; for a pair
+ * whose numerators total less than 2^24 every partial sum is exact, the order cannot matter and the integer column
+ * settles it; only pairs beyond that bound have their f32 partial carried rank to rank (4 B per such pair and hop;
+ * no hop at all when there is none), so that the result is bit-identical to a single process reading the whole file.
+ * wga_stat_acc_write on any rank prints the global TSV. */
 typedef struct wga_comm wga_comm;
 /* 128 bytes (ncclUniqueId): produced on one rank, distributed by the host's own means (MPI, torch.distributed, ...) */
 int wga_nccl_unique_id(void *id128);

@@ -125,7 +125,7 @@ def test_stat_allreduce_dictionary_paths_world3():
     from wgatools_b200 import dist as wd
     rng = np.random.default_rng(11)
 
-    def part(names, n_inv, big=False):
+    def part(names, n_inv, big=False, num_hi=1 << 33, hot=None):
         keys = [(f"ref.{a}".encode(), 1000 + a, f"qry.{b}".encode(), 2000 + b) for a, b in names]
         vals = rng.integers(0, 1 << 40, size=(len(keys), 13), dtype=np.uint64)
         vals[:, 11] = rng.integers(0, 900, size=len(keys))
@@ -133,7 +133,10 @@ def test_stat_allreduce_dictionary_paths_world3():
         if big and len(keys):
             vals[0, 11] = np.uint64((1 << 63) + 5)
         inv_pair = rng.integers(0, max(len(keys), 1), size=n_inv if keys else 0, dtype=np.uint32)
-        inv_num = rng.integers(1, 1 << 33, size=len(inv_pair), dtype=np.uint64) | np.uint64(1)   # odd: halves are inexact in f32
+        inv_num = rng.integers(1, num_hi, size=len(inv_pair), dtype=np.uint64) | np.uint64(1)   # odd: halves are inexact in f32
+        if hot is not None and len(inv_pair):   # one pair far beyond 2^24 among exact ones: only it takes the rank-order ring
+            sel = inv_pair == inv_pair[hot % len(inv_pair)]
+            inv_num[sel] = rng.integers(1 << 23, 1 << 26, size=int(sel.sum()), dtype=np.uint64) | np.uint64(1)
         return wd.build_blob(0, keys, vals, np.zeros(len(keys), np.float32), inv_pair, inv_num)
 
     base = [(a, b) for a in range(12) for b in range(9)]
@@ -144,6 +147,9 @@ def test_stat_allreduce_dictionary_paths_world3():
         [part(base[:40], 100), part([], 0), part(base[20:], 200)],                  # empty rank, late pairs
         [part([], 0), part(perm1[:30], 50, big=True), part(perm1[10:50], 60)],      # rank 0 empty
         [part([], 0), part([], 0), part([], 0)],                                    # nothing anywhere
+        # every pair's numerators stay below 2^24 in total: the order-free integer column settles inv_size, no ring
+        [part(base, 400, num_hi=9000), part(perm1, 300, num_hi=9000), part(perm2, 500, num_hi=9000)],
+        [part(base, 400, num_hi=9000, hot=3), part(perm1[:50], 300, num_hi=9000), part(perm2, 500, num_hi=9000, hot=7)],  # mixed
     ]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

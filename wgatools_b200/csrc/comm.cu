@@ -372,44 +372,79 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
         WGA_TRY(T.allgather(bl_s, bl_r, blob_max));
     }
     lap("names");
-    // ---- 2. counters: one all-reduce(sum), one all-reduce(min)
-    uint64_t *sums = (uint64_t *)T.scratch(4, (size_t)P * 11 * 8), *mins = (uint64_t *)T.scratch(5, (size_t)P * 2 * 8);
+    // ---- 2. counters: one all-reduce(sum), one all-reduce(min).  Column 11 of the sum table carries, per pair, the integer
+    //      sum of the '-' records' inv_size numerators (see 3.)
+    constexpr size_t SC = 12;
+    uint64_t *sums = (uint64_t *)T.scratch(4, (size_t)P * SC * 8), *mins = (uint64_t *)T.scratch(5, (size_t)P * 2 * 8);
     if (!sums || !mins) return WGA_E_NOMEM;
-    memset(sums, 0, (size_t)P * 88);
+    memset(sums, 0, (size_t)P * SC * 8);
     memset(mins, 0xFF, (size_t)P * 16);
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t *v = acc->rows[i].v;
-        memcpy(sums + (size_t)lmap[i] * 11, v, 88);
+        memcpy(sums + (size_t)lmap[i] * SC, v, 88);
         mins[2 * (size_t)lmap[i]] = v[11];
         mins[2 * (size_t)lmap[i] + 1] = v[12];
     }
-    WGA_TRY(T.allreduce_u64(sums, (uint64_t)P * 11, 0));
-    WGA_TRY(T.allreduce_u64(mins, (uint64_t)P * 2, 1));
-    lap("counters");
-    // ---- 3. inv_size: the f32 partial travels the ranks in file order
-    float *carry = (float *)T.scratch(0, (size_t)P * 4), *carry_all = (float *)T.scratch(1, (size_t)P * 4 * (size_t)W);
-    if (!carry || !carry_all) return WGA_E_NOMEM;
-    if (R == 0) memset(carry, 0, (size_t)P * 4);
-    else WGA_TRY(T.sendrecv(nullptr, 0, -1, carry, (uint64_t)P * 4, R - 1));
     {
-        // f32 addition in file order per PAIR: threads take the pairs of one residue class each and walk the whole list
+        // integer sums are order-free: the record list is cut into one range per thread, each with its own compact table
         const size_t ni = acc->inv_pair.size();
-        auto add_class = [&](uint32_t t, uint32_t Tn) {
-            for (size_t i = 0; i < ni; ++i) {
-                const uint32_t g = lmap[acc->inv_pair[i]];
-                if (Tn == 1 || (g & (Tn - 1)) == t) carry[g] += (float)acc->inv_num[i] / (float)2;  // common.rs:134-137 with inv_event == 1
-            }
+        const unsigned nt = ni >= 200000 ? 4u : 1u;
+        std::vector<std::vector<uint64_t>> ks(nt, std::vector<uint64_t>(P, 0));
+        auto part = [&](unsigned t) {
+            uint64_t *k = ks[t].data();
+            for (size_t i = ni * t / nt; i < ni * (t + 1) / nt; ++i) k[lmap[acc->inv_pair[i]]] += acc->inv_num[i];
         };
-        if (ni < 200000) add_class(0, 1);
+        if (nt == 1) part(0);
         else {
             std::vector<std::thread> th;
-            for (uint32_t t = 0; t < 4; ++t) th.emplace_back(add_class, t, 4u);
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(part, t);
             for (auto &x : th) x.join();
         }
+        for (uint32_t g = 0; g < P; ++g) {
+            uint64_t v = 0;
+            for (unsigned t = 0; t < nt; ++t) v += ks[t][g];
+            sums[(size_t)g * SC + 11] = v;
+        }
     }
-    if (R + 1 < W) WGA_TRY(T.sendrecv(carry, (uint64_t)P * 4, R + 1, nullptr, 0, -1));
-    WGA_TRY(T.allgather(carry, carry_all, (uint64_t)P * 4));
-    const float *fin = carry_all + (size_t)(W - 1) * P;
+    WGA_TRY(T.allreduce_u64(sums, (uint64_t)P * SC, 0));
+    WGA_TRY(T.allreduce_u64(mins, (uint64_t)P * 2, 1));
+    lap("counters");
+    // ---- 3. inv_size = the f32 sum, in file order, of (numerator as f32) / 2 over a pair's '-' records (common.rs:134-137).
+    //      While a pair's numerators add up to less than 2^24 every term and every partial sum is exactly representable
+    //      (k / 2 with k < 2^24), so the sum does not depend on the order: it IS (f32)total / 2, and the all-reduced integer
+    //      column settles it.  Only the pairs beyond that bound need the order: their f32 partials (a compact array, one
+    //      float per such pair) travel the ranks in file order, rank r continuing the sums with its own records -- a serial
+    //      chain of W hops, skipped altogether when no pair needs it (every rank sees the same totals and takes the same
+    //      branch).
+    constexpr uint64_t kExact = 1ull << 24;
+    float *fin = (float *)T.scratch(0, (size_t)P * 4);
+    if (!fin) return WGA_E_NOMEM;
+    std::vector<uint32_t> big_of;  // global pair -> index among the pairs that need the ring (~0u: settled)
+    uint32_t n_big = 0;
+    for (uint32_t g = 0; g < P; ++g) {
+        const uint64_t k = sums[(size_t)g * SC + 11];
+        fin[g] = (float)k / (float)2;
+        if (k >= kExact) {
+            if (big_of.empty()) big_of.assign(P, ~0u);
+            big_of[g] = n_big++;
+        }
+    }
+    if (n_big) {
+        float *c = (float *)T.scratch(1, (size_t)n_big * 4), *c_all = (float *)T.scratch(2, (size_t)n_big * 4 * (size_t)W);
+        if (!c || !c_all) return WGA_E_NOMEM;
+        if (R == 0) memset(c, 0, (size_t)n_big * 4);
+        else WGA_TRY(T.sendrecv(nullptr, 0, -1, c, (uint64_t)n_big * 4, R - 1));
+        const size_t ni = acc->inv_pair.size();
+        for (size_t i = 0; i < ni; ++i) {  // file order
+            const uint32_t b = big_of[lmap[acc->inv_pair[i]]];
+            if (b != ~0u) c[b] += (float)acc->inv_num[i] / (float)2;  // common.rs:134-137 with inv_event == 1
+        }
+        if (R + 1 < W) WGA_TRY(T.sendrecv(c, (uint64_t)n_big * 4, R + 1, nullptr, 0, -1));
+        WGA_TRY(T.allgather(c, c_all, (uint64_t)n_big * 4));
+        const float *last = c_all + (size_t)(W - 1) * n_big;
+        for (uint32_t g = 0; g < P; ++g)
+            if (big_of[g] != ~0u) fin[g] = last[big_of[g]];
+    }
     lap("inv carry");
     // ---- rebuild the accumulator in global order: rows and names are laid out in bulk (no per-row vector growth)
     wga_stat_acc out;
@@ -445,7 +480,7 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
         row.name_off = noff;
         memcpy(nm + noff, src, nl);
         noff += nl;
-        memcpy(row.v, sums + (size_t)g * 11, 88);
+        memcpy(row.v, sums + (size_t)g * SC, 88);
         row.v[11] = mins[2 * (size_t)g];
         row.v[12] = mins[2 * (size_t)g + 1];
         row.inv_size = fin[g];

@@ -180,11 +180,27 @@ struct wga_stat_acc {
             size_t cap = 64;
             while (cap < 2 * n + 2) cap <<= 1;
             std::vector<uint32_t> gt(cap, 0u);
+            // the name hashes are independent (a few threads); only the probing below is sequential
+            std::vector<uint64_t> hs(n);
+            {
+                const unsigned nt = n >= 16384 ? 4u : 1u;
+                auto part = [&](unsigned t) {
+                    for (size_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
+                        uint64_t h = 0xCBF29CE484222325ull;
+                        for (unsigned char c : ref_name(rows[i])) h = (h ^ c) * 0x100000001B3ull;
+                        hs[i] = wga::mix64(h);
+                    }
+                };
+                if (nt == 1) part(0);
+                else {
+                    std::vector<std::thread> th;
+                    for (unsigned t = 0; t < nt; ++t) th.emplace_back(part, t);
+                    for (auto &x : th) x.join();
+                }
+            }
             for (uint32_t i = 0; i < n; ++i) {
                 const std::string_view nm = ref_name(rows[i]);
-                uint64_t h = 0xCBF29CE484222325ull;
-                for (unsigned char c : nm) h = (h ^ c) * 0x100000001B3ull;
-                size_t s = wga::mix64(h) & (cap - 1);
+                size_t s = hs[i] & (cap - 1);
                 for (;;) {
                     const uint32_t e = gt[s];
                     if (!e) { grp_first.push_back(i); gt[s] = (uint32_t)grp_first.size(); grp_of[i] = gt[s] - 1; break; }

@@ -879,12 +879,14 @@ static int maf_run_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, u
     V.q_start = m6 + 4 * n_rec; V.q_end = m6 + 5 * n_rec; V.neg = P.rc.neg; V.skip = P.rc.skip; V.run_first = rec_run_first;
     V.run_len = run_len; V.run_type = RU.run_cls; V.maf = 1; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
     static const bool chain_seq = getenv("WGA_CHAIN_SEQ") != nullptr && getenv("WGA_CHAIN_SEQ")[0] == '1';  // one thread per record
+    static const bool plot_seq = getenv("WGA_PLOT_SEQ") != nullptr && getenv("WGA_PLOT_SEQ")[0] == '1';     // one thread per record
     uint32_t *hdr_len = ctx->buf<uint32_t>(B_CHAIN_HDR, n_rec + 1);
     uint8_t *irregular = ctx->buf<uint8_t>(B_CHAIN_IRR, n_rec + 1);
     if (!hdr_len || !irregular) return ctx->err_code;
     if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
     else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V, hdr_len, irregular);
-    else LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
+    else if (plot_seq) LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
+    else LAUNCH(ctx, k_plot_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V, cutoff);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
     WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
@@ -894,7 +896,8 @@ static int maf_run_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, u
     V.out = d_out;
     if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
     else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<1>, grid_for(n_rec * 32, 128), 128, V, hdr_len, irregular);
-    else LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
+    else if (plot_seq) LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
+    else LAUNCH(ctx, k_plot_rows_warp<1>, grid_for(n_rec * 32, 128), 128, V, cutoff);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 int wga_maf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, const char *query_name, uint64_t id_base,
@@ -2092,12 +2095,14 @@ static int paf_op_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, ui
     V.t_end = X.t_end; V.q_start = R.q_start; V.q_end = X.q_end; V.neg = R.neg; V.skip = nullptr; V.run_first = op_base;
     V.run_len = op_len; V.run_type = op_type; V.maf = 0; V.row_len = row_len; V.row_off = row_off; V.out = nullptr;
     static const bool chain_seq = getenv("WGA_CHAIN_SEQ") != nullptr && getenv("WGA_CHAIN_SEQ")[0] == '1';  // one thread per record
+    static const bool plot_seq = getenv("WGA_PLOT_SEQ") != nullptr && getenv("WGA_PLOT_SEQ")[0] == '1';     // one thread per record
     uint32_t *hdr_len = ctx->buf<uint32_t>(B_CHAIN_HDR, n_rec + 1);
     uint8_t *irregular = ctx->buf<uint8_t>(B_CHAIN_IRR, n_rec + 1);
     if (!hdr_len || !irregular) return ctx->err_code;
     if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<0>, grid_for(n_rec + 1, 128), 128, V);
     else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V, hdr_len, irregular);
-    else LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
+    else if (plot_seq) LAUNCH(ctx, k_plot_rows<0>, grid_for(n_rec + 1, 128), 128, V, cutoff);
+    else LAUNCH(ctx, k_plot_rows_warp<0>, grid_for((n_rec + 1) * 32, 128), 128, V, cutoff);
     WGA_TRY(exclusive_sum(ctx, row_len, row_off, n_rec + 1));
     uint64_t total;
     WGA_TRY(read_scalars(ctx, {row_off + n_rec}, &total));
@@ -2107,7 +2112,8 @@ static int paf_op_rows(wga_ctx *ctx, const void *text, uint64_t len, int mem, ui
     V.out = d_out;
     if (kind == 0 && chain_seq) LAUNCH(ctx, k_chain_rows<1>, grid_for(n_rec, 128), 128, V);
     else if (kind == 0) LAUNCH(ctx, k_chain_rows_warp<1>, grid_for(n_rec * 32, 128), 128, V, hdr_len, irregular);
-    else LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
+    else if (plot_seq) LAUNCH(ctx, k_plot_rows<1>, grid_for(n_rec, 128), 128, V, cutoff);
+    else LAUNCH(ctx, k_plot_rows_warp<1>, grid_for(n_rec * 32, 128), 128, V, cutoff);
     return finish_output(ctx, d_out, total, mem, flags, out);
 }
 int wga_paf2chain(wga_ctx *ctx, const void *text, uint64_t len, int mem, uint32_t flags, uint64_t id_base, wga_span *out,
