@@ -1049,6 +1049,21 @@ def test_chain_parity(w, ctx):
         assert p2c(text) == orc.paf2chain(text)
     line = lambda cg, strand=b"+", tag=True: b"\t".join([b"q", b"1000", b"100", b"200", strand, b"t", b"2000", b"300", b"420", b"1", b"2",
                                                         b"60"] + ([b"cg:Z:" + cg] if tag else [])) + b"\n"
+    # op lengths on both sides of 2^16 inside one record (the row writer switches between its packed segmented scan and the
+    # general three-scan path step by step, carrying the run / gap-group state across), gap groups across 32-op boundaries
+    rng = random.Random(77)
+    for _ in range(60):
+        n_ops = rng.choice([3, 31, 32, 33, 64, 65, 150, 400])
+        big_p = rng.choice([0.0, 0.02, 0.3, 1.0])
+        ops, prev = [], None
+        for k in range(n_ops):
+            op = rng.choice(b"=XID" if rng.random() < 0.6 else b"ID=")
+            ln = rng.randrange(65536, 400000) if rng.random() < big_p else rng.choice([1, 2, 7, 65535, rng.randrange(1, 3000)])
+            ops.append(b"%d%c" % (ln, op))
+        cg = b"".join(ops)
+        for strand in (b"+", b"-"):
+            l = b"\t".join([b"q", b"4000000000", b"100", b"200", strand, b"t", b"4000000000", b"300", b"420", b"1", b"2", b"60", b"cg:Z:" + cg]) + b"\n"
+            assert p2c(l * 3) == orc.paf2chain(l * 3), cg
     for cg in (b"3I2D5I40=2X10I8=4D6=7I2D3I", b"5I3D", b"7M", b"1D1I1M1I1D"):
         for strand in (b"+", b"-"):
             assert p2c(line(cg, strand)) == orc.paf2chain(line(cg, strand))
