@@ -4,7 +4,7 @@ aliases and defaults (src/cli.rs:20-343), running on the GPU path.  Global flags
 
   maf2paf|m2p [INPUT] [-q/--query-name NAME]                         src/cli.rs:42-49
   stat|st     [INPUT] [-f/--format maf|paf] [-e/--each] [-q NAME]    src/cli.rs:187-200
-  call|c      [INPUT] [-n/--sample S] [-s/--snp] [-i/--inv] [-l/--svlen N] [--query-name NAME] [-c/--chunk-size N]
+  call|c      [INPUT] [-n/--sample S] [-s/--snp] [-i/--inv] [-l/--svlen N] [--query-name NAME] [--query-regex RE] [-c/--chunk-size N]
                                                                     src/cli.rs:132-174
 Errors are printed like the reference (`main.rs:14-22`) and exit with status 1.
 """
@@ -66,6 +66,7 @@ def main(argv=None):
     p.add_argument("-l", "--svlen", type=int, default=50)
     p.add_argument("-f", "--format", default="maf", choices=["maf"])
     p.add_argument("--query-name")
+    p.add_argument("--query-regex")
     p.add_argument("-c", "--chunk-size", type=int, default=1000000)
     a = ap.parse_args(argv)
     try:
@@ -79,8 +80,13 @@ def main(argv=None):
             else:
                 api.stat_paf(api.PAFReader(data), out, a.each)
         else:
-            api.call_var_maf(api.MAFReader(data), None, out, a.snp, a.inv, a.svlen, False, a.sample, a.query_name, None,
-                             a.chunk_size)
+            mafindex = None  # "<input>.index" next to a file input, like utils.rs:414-431 (stdin: no index)
+            if a.input and a.input != "-" and os.path.exists(a.input + ".index"):
+                import json
+                with open(a.input + ".index") as fh:
+                    mafindex = json.load(fh)
+            api.call_var_maf(api.MAFReader(data), mafindex, out, a.snp, a.inv, a.svlen, False, a.sample, a.query_name,
+                             a.query_regex, a.chunk_size)
         if out is not sys.stdout.buffer:
             out.close()
         else:
