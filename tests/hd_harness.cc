@@ -23,4 +23,8 @@ uint32_t hd_prev_flags(uint32_t p, uint32_t c) { return prev_flags(p, c); }
 uint32_t hd_funnel(uint32_t lo, uint32_t hi, uint32_t sh) { return funnel_r_bytes(lo, hi, sh); }
 void hd_fmt_f32(float v, char *dst) { std::string s = fmt_f32(v); memcpy(dst, s.c_str(), s.size() + 1); }
 int hd_natord(const char *a, const char *b) { return natord_cmp(a, b); }
+uint32_t hd_nibble_flags(uint32_t n) { return nibble_flags(n); }
+uint32_t hd_class_codes(uint32_t t, uint32_t q, uint32_t valid, int caller) {
+    return class_codes(caller ? classify4<true>(t, q, valid) : classify4<false>(t, q, valid));
+}
 }

@@ -84,6 +84,32 @@ def test_classify4_matches_reference_classifiers(hd):
             assert all(out[c] & 0x7FFFFFFF == 0 for c in range(5))
 
 
+def test_nibble_flags_and_class_codes(hd):
+    """the batch's byte-range masks (one multiply per word) and the per-column class codes the head emission reads"""
+    hd.hd_nibble_flags.restype = hd.hd_class_codes.restype = ctypes.c_uint32
+    hd.hd_nibble_flags.argtypes = [ctypes.c_uint32]
+    hd.hd_class_codes.argtypes = [ctypes.c_uint32] * 3 + [ctypes.c_int]
+    for n in range(64):  # only the low nibble counts
+        assert hd.hd_nibble_flags(n) == sum(0x80 << (8 * i) for i in range(4) if (n >> i) & 1)
+    # bytes [f, t) of a 16-byte chunk, word k: the nibble of the range mask == the old per-word range computation
+    for f in range(17):
+        for t in range(17):
+            vm = ((1 << t) - 1) & ~((1 << f) - 1)
+            for k in range(4):
+                want = sum(0x80 << (8 * i) for i in range(4) if f <= 4 * k + i < t)
+                assert hd.hd_nibble_flags(vm >> (4 * k)) == want
+    rng = random.Random(4)
+    alpha = b"ACGTacgtN-"
+    for caller in (0, 1):
+        for _ in range(3000):
+            t = [rng.choice(alpha) for _ in range(4)]
+            q = [rng.choice(alpha) for _ in range(4)]
+            cw = hd.hd_class_codes(_word(t), _word(q), 0x80808080, caller)
+            for i in range(4):
+                want = (pyspec.cat_caller if caller else pyspec.cat_ext)(chr(t[i]), chr(q[i]))
+                assert CLS[(cw >> (8 * i)) & 7] == want and (cw >> (8 * i)) & 0xF8 == 0
+
+
 def test_prev_flags_and_funnel(hd):
     assert hd.hd_prev_flags(0x80000000, 0x00800080) == 0x80008080
     assert hd.hd_prev_flags(0, 0x80808080) == 0x80808000

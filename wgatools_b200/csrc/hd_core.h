@@ -87,6 +87,13 @@ WGA_HD Flags4 classify4(uint32_t t, uint32_t q, uint32_t valid /* 0x80 per in-re
     return f;
 }
 
+// 0x80 flags for the bytes of a word whose bits are set in the low nibble of n (bit i -> byte i): one multiply spreads the
+// four bits to bit 0 of the four bytes (bit i lands at i, i+7, i+14, i+21; only i + 7i = 8i survives the mask)
+WGA_HD uint32_t nibble_flags(uint32_t n) { return (((n & 0xFu) * 0x00204081u) & 0x01010101u) << 7; }
+
+// class code (CLS_*) of four columns, one per byte (bits 0-2), from their class flags: '=' is 0
+WGA_HD uint32_t class_codes(const Flags4 &f) { return (f.x >> 7) | (f.i >> 6) | (f.d >> 7) | (f.d >> 6) | (f.w >> 5); }
+
 // class flags of a single (t,q) byte pair placed at bit 31 (as the "previous word" of prev_flags)
 template <bool CALLER>
 WGA_HD Flags4 classify_prev(uint32_t tb, uint32_t qb, bool valid) {

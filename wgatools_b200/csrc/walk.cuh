@@ -99,8 +99,7 @@ __device__ __forceinline__ void walk_batch_q(const WalkArgs &A, const QA &qa, ui
     constexpr bool CALLER = MODE == MODE_RUNS_CALLER || MODE == MODE_RUNS_ALL;
     constexpr bool RUNS = MODE != MODE_STAT;
     constexpr bool COUNTS = MODE != MODE_RUNS_CALLER;
-    uint32_t H[4] = {0, 0, 0, 0}, hc = 0, item = 0xFFFFFFFFu, colrel = 0;
-    Flags4 F[4];
+    uint32_t H[4] = {0, 0, 0, 0}, CW[4] = {0, 0, 0, 0}, hc = 0, item = 0xFFFFFFFFu, colrel = 0;  // CW: class code per column
     const bool act = lane < cnt;
     if (act) {
         uint32_t tw[4], qw[4];
@@ -114,9 +113,12 @@ __device__ __forceinline__ void walk_batch_q(const WalkArgs &A, const QA &qa, ui
         uint32_t cX = 0, cI = 0, cD = 0, eI = 0, eD = 0, hw = 0;
         Flags4 pf = classify_prev<CALLER>(pv & 0xFFu, (pv >> 8) & 0xFFu, (pv >> 16) & 1u);
         uint32_t p_eq = pf.eq, p_x = pf.x, p_i = pf.i, p_d = pf.d, p_w = pf.w;
+        // bytes [f0, t0) of the chunk are the item's columns, [f1, t1) the record's (context): one bit per byte, a nibble per word
+        const uint32_t vm = ((1u << t0) - 1u) & ~((1u << f0) - 1u), vc = ((1u << t1) - 1u) & ~((1u << f1) - 1u);
+        Flags4 F[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t cm = range_flags(f0 - 4 * k, t0 - 4 * k), ctx = range_flags(f1 - 4 * k, t1 - 4 * k);
+            const uint32_t cm = nibble_flags(vm >> (4 * k)), ctx = nibble_flags(vc >> (4 * k));
             F[k] = classify4<CALLER>(tw[k], qw[k], ctx);
             uint32_t Pi = prev_flags(p_i, F[k].i), Pd = prev_flags(p_d, F[k].d);
             if (COUNTS) {
@@ -133,6 +135,7 @@ __device__ __forceinline__ void walk_batch_q(const WalkArgs &A, const QA &qa, ui
                 H[k] = cm & ~same;
                 hc += __popc(H[k]);
                 if (MODE == MODE_RUNS_ALL) hw |= H[k] & F[k].w;
+                CW[k] = class_codes(F[k]);
             }
             p_eq = F[k].eq; p_x = F[k].x; p_i = F[k].i; p_d = F[k].d; p_w = F[k].w;
         }
@@ -179,10 +182,9 @@ __device__ __forceinline__ void walk_batch_q(const WalkArgs &A, const QA &qa, ui
                 for (int k = 0; k < 4; ++k) {
                     uint32_t m = H[k];
                     while (m) {
-                        int bit = __ffs(m) - 1;
+                        int bit = __ffs(m) - 1;  // 7, 15, 23 or 31: the flag bit of byte bit >> 3
                         m &= m - 1;
-                        uint32_t cls = ((F[k].x >> bit) & 1u) * CLS_X + ((F[k].i >> bit) & 1u) * CLS_I +
-                                       ((F[k].d >> bit) & 1u) * CLS_D + ((F[k].w >> bit) & 1u) * CLS_W;
+                        uint32_t cls = (CW[k] >> (bit - 7)) & 7u;
                         uint32_t col = colrel + 4u * k + (uint32_t)(bit >> 3) - 16u;
                         A.slots[sbase + o] = (col << 3) | cls;
                         ++o;
