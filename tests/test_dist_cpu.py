@@ -171,6 +171,52 @@ def test_stat_allreduce_dictionary_paths_world3():
         assert ci == 3 or want.count(b"\n") > 10
 
 
+def test_stat_allreduce_large_tables_world2():
+    """the threaded host paths of wga_stat_allreduce (>= 16384 pairs, >= 200000 '-' records): uniform key sets in two orders
+    (threaded counter table and rebuild), and a non-uniform pair of ranks (sequential rebuild from the name blobs); numerators
+    small enough for the order-free integer column in the first case, a few pairs over 2^24 in the second (compact ring)."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    import wgatools_b200 as w
+    from wgatools_b200 import dist as wd
+    rng = np.random.default_rng(23)
+    P = 20000
+
+    def part(ids, n_inv, num_hi, hot=0):
+        keys = [(b"g%d#chr%d" % (i % 40, i // 40 % 25), 1000 + i % 7, b"h%d#c%d" % (i // 1000, i % 1000), 2000 + i % 5) for i in ids]
+        vals = rng.integers(0, 1 << 30, size=(len(keys), 13), dtype=np.uint64)
+        inv_pair = rng.integers(0, len(keys), size=n_inv, dtype=np.uint32)
+        inv_num = rng.integers(1, num_hi, size=n_inv, dtype=np.uint64) | np.uint64(1)
+        if hot:
+            sel = inv_pair < hot
+            inv_num[sel] = rng.integers(1 << 22, 1 << 25, size=int(sel.sum()), dtype=np.uint64) | np.uint64(1)
+        return wd.build_blob(0, keys, vals, np.zeros(len(keys), np.float32), inv_pair, inv_num)
+
+    ids = np.arange(P)
+    cases = [
+        [part(ids, 250000, 9000), part(rng.permutation(P), 250000, 9000)],
+        [part(ids[:17000], 220000, 9000, hot=5), part(rng.permutation(P)[:18000], 230000, 9000, hot=9)],
+    ]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_blob_worker, args=(r, 2, port, cases, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    outs = dict(q.get(timeout=300) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for ci, case in enumerate(cases):
+        one = w.StatAcc(False)
+        for blob in case:
+            one.import_(blob)
+        want = one.write()
+        assert outs[0][ci] == want and outs[1][ci] == want, ci
+        assert want.count(b"\n") > 17000
+
+
 def _shard_worker(rank, world, port, text, paf, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -377,13 +377,28 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     constexpr size_t SC = 12;
     uint64_t *sums = (uint64_t *)T.scratch(4, (size_t)P * SC * 8), *mins = (uint64_t *)T.scratch(5, (size_t)P * 2 * 8);
     if (!sums || !mins) return WGA_E_NOMEM;
-    memset(sums, 0, (size_t)P * SC * 8);
-    memset(mins, 0xFF, (size_t)P * 16);
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint64_t *v = acc->rows[i].v;
-        memcpy(sums + (size_t)lmap[i] * SC, v, 88);
-        mins[2 * (size_t)lmap[i]] = v[11];
-        mins[2 * (size_t)lmap[i] + 1] = v[12];
+    if (n != P) {  // pairs this rank does not hold (n == P: lmap is a bijection, every entry is written below)
+        memset(sums, 0, (size_t)P * SC * 8);
+        memset(mins, 0xFF, (size_t)P * 16);
+    }
+    {
+        const unsigned nt = n >= 16384 ? 4u : 1u;
+        auto part = [&](unsigned t) {
+            for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
+                const uint64_t *v = acc->rows[i].v;
+                uint64_t *d = sums + (size_t)lmap[i] * SC;
+                memcpy(d, v, 88);
+                d[11] = 0;
+                mins[2 * (size_t)lmap[i]] = v[11];
+                mins[2 * (size_t)lmap[i] + 1] = v[12];
+            }
+        };
+        if (nt == 1) part(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(part, t);
+            for (auto &x : th) x.join();
+        }
     }
     {
         // integer sums are order-free: the record list is cut into one range per thread, each with its own compact table
@@ -460,30 +475,64 @@ int stat_allreduce_impl(Transport &T, wga_stat_acc *acc, std::string *err) {
     size_t noff = 0;
     if (uniform) out.names.resize(acc->names.size());
     char *nm = out.names.data();
-    for (uint32_t g = 0; g < P; ++g) {
-        wga_stat_acc::Row &row = out.rows[g];
-        const char *src;
-        if (uniform) {  // every rank holds every pair: its own copy of the names and sizes
-            const wga_stat_acc::Row &l = acc->rows[g2l[g]];
-            row.lr = l.lr; row.lq = l.lq; row.ref_size = l.ref_size; row.query_size = l.query_size; row.key = l.key;
-            src = acc->names.data() + l.name_off;
-        } else {
+    auto finish_row = [&](wga_stat_acc::Row &row, uint32_t g) {
+        memcpy(row.v, sums + (size_t)g * SC, 88);
+        row.v[11] = mins[2 * (size_t)g];
+        row.v[12] = mins[2 * (size_t)g + 1];
+        row.inv_size = fin[g];
+    };
+    if (uniform) {
+        // every rank holds every pair: its own copy of the names and sizes.  Rows are independent once their name offsets
+        // are known: ranges of the global order per thread, name bytes per range first, then the rows
+        const unsigned nt = P >= 16384 ? 4u : 1u;
+        std::vector<size_t> base(nt + 1, 0);
+        auto count = [&](unsigned t) {
+            size_t b = 0;
+            for (uint32_t g = (uint32_t)((uint64_t)P * t / nt); g < (uint32_t)((uint64_t)P * (t + 1) / nt); ++g) {
+                const wga_stat_acc::Row &l = acc->rows[g2l[g]];
+                b += (size_t)l.lr + l.lq;
+            }
+            base[t + 1] = b;
+        };
+        auto fill = [&](unsigned t) {
+            size_t off = base[t];
+            for (uint32_t g = (uint32_t)((uint64_t)P * t / nt); g < (uint32_t)((uint64_t)P * (t + 1) / nt); ++g) {
+                const wga_stat_acc::Row &l = acc->rows[g2l[g]];
+                wga_stat_acc::Row &row = out.rows[g];
+                row.lr = l.lr; row.lq = l.lq; row.ref_size = l.ref_size; row.query_size = l.query_size; row.key = l.key;
+                const size_t nl = (size_t)row.lr + row.lq;
+                row.name_off = off;
+                memcpy(nm + off, acc->names.data() + l.name_off, nl);
+                off += nl;
+                finish_row(row, g);
+            }
+        };
+        auto run = [&](auto &fn) {
+            if (nt == 1) { fn(0); return; }
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, t);
+            for (auto &x : th) x.join();
+        };
+        run(count);
+        for (unsigned t = 0; t < nt; ++t) base[t + 1] += base[t];
+        run(fill);
+        noff = base[nt];
+    } else {
+        for (uint32_t g = 0; g < P; ++g) {
+            wga_stat_acc::Row &row = out.rows[g];
             const char *p = cur[owner[g]];
             memcpy(&row.lr, p, 4); memcpy(&row.lq, p + 4, 4); memcpy(&row.ref_size, p + 8, 8); memcpy(&row.query_size, p + 16, 8);
             // identity across ranks is the 128-bit (pair hash, key2) the dictionary was built on; the rebuilt accumulator's
             // own lookup table is made on demand from the rows' keys (find_or_add -> grow_table)
             memcpy(&row.key, p + 24, 8);
-            src = p + 32;
+            const char *src = p + 32;
             cur[owner[g]] = p + 32 + (size_t)row.lr + row.lq;
+            const size_t nl = (size_t)row.lr + row.lq;
+            row.name_off = noff;
+            memcpy(nm + noff, src, nl);
+            noff += nl;
+            finish_row(row, g);
         }
-        const size_t nl = (size_t)row.lr + row.lq;
-        row.name_off = noff;
-        memcpy(nm + noff, src, nl);
-        noff += nl;
-        memcpy(row.v, sums + (size_t)g * SC, 88);
-        row.v[11] = mins[2 * (size_t)g];
-        row.v[12] = mins[2 * (size_t)g + 1];
-        row.inv_size = fin[g];
     }
     out.names.resize(noff);
     lap("rebuild");
