@@ -44,7 +44,7 @@ def worker(rank, world, port, P, NREC, q):
         tw = time.perf_counter() - t1
     if rank == 0:
         print(f"world {world}: allreduce {[round(t * 1e3, 1) for t in times]} ms, TSV write {tw * 1e3:.1f} ms, {len(out)} bytes", flush=True)
-    q.put((rank, hash(out)))
+    import hashlib; q.put((rank, hashlib.sha1(out).hexdigest()))
     dist.barrier()
     comm.close()
     dist.destroy_process_group()
