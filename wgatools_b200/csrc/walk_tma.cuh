@@ -7,8 +7,13 @@
 // windows ahead -- across item boundaries -- and the warp reads its vectors with LDS.128.  The 24 prefetch registers
 // of k_walk are gone.  Measured on the bench workload (1 M blocks): the bulk-copy REQUEST rate is what limits this
 // path -- 1 KB requests 2.3 TB/s, 1.5 KB 3.7 TB/s, 2 KB 4.2-4.5 TB/s -- and, at equal request size, the number of
-// resident warps (12 warps 3.5, 16 warps 4.2, 20 warps 4.5 TB/s).  Shared memory (2 x 4 KB of windows + 2.8 KB of
+// resident warps (12 warps 3.5, 16 warps 4.2, 20 warps 4.5 TB/s).  Shared memory (2 x 4 KB of windows + 3 KB of
 // slow-chunk queue per warp) caps the SM at 20 warps: 2 CTAs x 10 warps, 2 stages x 128 chunks.
+//
+// Round 2 (v6, 5.3 TB/s = 0.81 of the measured HBM peak): the consumer no longer goes through walk_step.  tma_steps<MODE, WS>
+// is the step loop instantiated for the four word shifts of the query realignment (dispatched once per window), the
+// slow-chunk queue is a ring of 16-byte vectors (3 STS.128 per push), and the kernel has one classification site
+// (walk_batch_q).  tma_steps2 (32 columns per lane) is a measured-slower experiment kept behind WGA_TMA_LANE32.
 #pragma once
 #include "walk.cuh"
 
@@ -108,7 +113,7 @@ __device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes) {
 }
 __device__ __forceinline__ uint4 lds16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
-// Steps st, st+32, ... of one window (same algorithm as walk_step, walk.cuh) until the window ends or 32 slow chunks are
+// Steps st, st+32, ... of one window (the algorithm of walk_step, walk.cuh) until the window ends or 32 slow chunks are
 // queued.  WS = word part of the query's byte shift (warp-uniform per item): the caller dispatches on it once per call,
 // not once per step.  Lane i of a step owns chunk st+i of the window; lanes past the window's end read stale shared
 // memory and are inactive.  jlm1 = (first chunk that is not fully inside the item) - 1: edge <=> j == 0 || j >= jl
